@@ -1,0 +1,116 @@
+/* uu3d.h — C ABI of the B200-native uplift-and-upsample transformer hot path.
+ *
+ * The reference (goldbricklemon/uplift-upsample-3dhpe) has no FFI of its own: the path sits
+ * behind three Python-level contracts.  Each entry point below names the
+ * reference interface it replaces (paths relative to the reference root):
+ *
+ *   uu_create / uu_destroy      build_uplift_upsample_transformer(config)
+ *                               common/net/uplift_upsample_transformer_constructor.py:14-50
+ *   uu_set_weight / uu_get_weight / uu_weight_info
+ *                               weight_io.load_weights_with_callback (by group name, then position)
+ *                               common/utils/weight_io.py:76-263 ; model.get_weights/set_weights train.py:400
+ *   uu_forward / uu_forward_host
+ *                               model([x2d, stride_mask], training=False) -> (full, central)
+ *                               common/net/uplift_upsample_transformer.py:388-421 ; caller eval.py:63-71
+ *   uu_train_step               train_step(): loss, gradients, AdamW   train.py:464-506, :403-415
+ *   uu_stride_mask              stride-mask rule of the data generators
+ *                               common/dataset/uplifiting_dataset.py:377-394
+ *
+ * Conventions: every function returns 0 on success and non-zero on failure, never throws;
+ * uu_last_error() returns a thread-local description of the last failure.  The caller owns all
+ * I/O buffers; the library owns weights, workspace and optimizer state.  Device entry points are
+ * asynchronous and stream-ordered on `stream` (a cudaStream_t passed as void*, NULL = default
+ * stream).  One model instance per device; calls on one instance are serialised by the caller.
+ * There is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef UU3D_H
+#define UU3D_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UU_MAX_STRIDED 8
+
+typedef struct uu_model uu_model;
+
+/* Hyper-parameters consumed by the constructor (config/ *.json keys in comments). */
+typedef struct uu_spec {
+  int32_t n_tok;                 /* SEQUENCE_LENGTH (71 for "N=351", 41 for "N=81") */
+  int32_t n_joints;              /* NUM_KEYPOINTS */
+  int32_t d_spatial;             /* SPATIAL_EMBED_DIM */
+  int32_t d_temporal;            /* TEMPORAL_EMBED_DIM */
+  int32_t spatial_depth;         /* SPATIAL_TRANSFORMER_BLOCKS */
+  int32_t temporal_depth;        /* TEMPORAL_TRANSFORMER_BLOCKS */
+  int32_t num_heads;             /* NUM_HEADS */
+  int32_t h_spatial;             /* int(SPATIAL_EMBED_DIM * MLP_RATIO) */
+  int32_t h_temporal;            /* int(TEMPORAL_EMBED_DIM * MLP_RATIO) */
+  int32_t n_strided;             /* len(STRIDES) */
+  int32_t strides[UU_MAX_STRIDED];
+  int32_t pad_left[UU_MAX_STRIDED];   /* PADDINGS[i][0] (null => 1) */
+  int32_t pad_right[UU_MAX_STRIDED];  /* PADDINGS[i][1] (null => 1) */
+  int32_t has_strided_input;     /* constructor.py:16-21 */
+  int32_t first_strided_token_attention_layer; /* FIRST_STRIDED_TOKEN_ATTENTION_LAYER */
+  int32_t full_output;           /* not USE_REFINE */
+} uu_spec;
+
+/* Arithmetic of the dense contractions. */
+enum { UU_PRECISION_FP32 = 0,    /* CUDA-core fp32, <= 1e-4 abs of the fp32 oracle           */
+       UU_PRECISION_BF16 = 1 };  /* tcgen05 bf16 x bf16 -> fp32, fp32 residual stream / LN / softmax */
+
+const char* uu_last_error(void);
+int uu_version(void);
+
+int uu_create(const uu_spec* spec, int device, uu_model** out);
+int uu_destroy(uu_model* m);
+int uu_set_precision(uu_model* m, int precision);
+int uu_get_precision(const uu_model* m);
+
+/* Weight inventory in Keras .h5 order: groups in `layer_names` order, tensors by position. */
+int uu_weight_count(const uu_model* m);
+int64_t uu_param_count(const uu_model* m);
+int uu_weight_info(const uu_model* m, int flat_index, char* group, int group_cap, int* index_in_group,
+                   int64_t shape[4], int* rank);
+/* host fp32 buffers; shape/rank are checked against the model (weight_io.py:219-232) */
+int uu_set_weight(uu_model* m, const char* group, int index, const float* host, const int64_t* shape, int rank);
+int uu_get_weight(uu_model* m, const char* group, int index, float* host, int64_t capacity);
+
+/* Forward pass on device buffers.
+ *   x2d    : fp32 (B, n_tok, n_joints, 2) row-major.  Frames with mask == 0 are never read
+ *            (equivalent to the caller-side mask multiply of eval.py:67).
+ *   mask   : uint8 (B, n_tok), non-zero on tokens that carry a 2-D pose; may be NULL when the
+ *            model has no strided input.
+ *   full   : fp32 (B, n_tok, n_joints, 3) or NULL;  central : fp32 (B, n_joints, 3). */
+int uu_forward(uu_model* m, const float* x2d, const uint8_t* mask, int B, float* full, float* central, void* stream);
+/* Same call with HOST buffers (pinned recommended): H2D copy, forward, D2H copy, stream sync. */
+int uu_forward_host(uu_model* m, const float* x2d, const uint8_t* mask, int B, float* full, float* central);
+
+/* Number of kernels of this library launched by the most recent forward on `m`. */
+int uu_last_launch_count(const uu_model* m);
+
+/* Stride-mask rule (host, integer, bit-exact): mask[n] = ((n - n_tok/2)*s_out + shift) floor-mod s_in == 0.
+ * shift = centre frame index (eval, global alignment) or rand_shift*s_out (training). */
+int uu_stride_mask(int n_tok, int s_out, int s_in, int64_t shift, uint8_t* mask_out);
+
+/* ---- single-kernel entry points (device pointers) used by the parity tests ------------------- */
+int uu_op_build_gather(const uint8_t* mask, int B, int n_tok, int32_t* scratch /*B+1*/, int32_t* list, int32_t* count,
+                       void* stream);
+int uu_op_token_fill(const uint8_t* mask, int rows, int n_tok, int d, const float* token, const float* pe, float* x,
+                     void* stream);
+int uu_op_layernorm(float* x, int rows, int d, const float* gamma, const float* beta, float eps, const float* table,
+                    int period, void* y, int y_bf16, void* stream);
+int uu_op_attention(const void* qkv, int is_bf16, int B, int S, int heads, int dh, const uint8_t* keep_mask,
+                    int mask_stride, void* out, void* stream);
+/* C = act(A @ W + bias) (+ res); flags: 1 = ReLU, 2 = residual.  fp32 CUDA-core GEMM, W is (K, N). */
+int uu_op_gemm_f32(const float* A, int64_t lda, const float* W, int M, int N, int K, const float* bias, int flags,
+                   const float* res, int64_t ldr, float* C, int64_t ldc, void* stream);
+/* tcgen05 GEMM: A bf16 (M, K) row-major, Wt bf16 (N_pad, K) = W^T with N_pad % 64 == 0. */
+int uu_op_gemm_bf16(const void* A, int64_t lda, int M, int K, const void* Wt, int N_pad, int N, const float* bias,
+                    int flags, const float* res, int64_t ldr, void* C, int c_bf16, int64_t ldc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UU3D_H */

@@ -1,0 +1,129 @@
+"""End-to-end parity on the B200: the CUDA forward (through the C ABI) against the oracle on the
+same seeded inputs, both precisions, BASELINE configs at oracle-sized batches."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+from oracle import forward_np as O
+from uplift_upsample_3dhpe_b200 import UpliftUpsampleConfig, spec_from_config, stride_mask, weights
+from uplift_upsample_3dhpe_b200.model import build_uplift_upsample_transformer, test_step
+
+# Tolerances (absolute, outputs are O(1..10) with the perturbed random-init weights):
+#   fp32 path: <= 1e-4 against the fp64 oracle (north_star's fp32 bound; the fp32 oracle itself sits ~1e-5 away)
+#   bf16 path: bf16 operands, fp32 accumulate/residual/LN/softmax — measured floor a few 1e-2; bound 0.25
+TOL = {"fp32": 1e-4, "bf16": 0.25}
+
+
+def _case(name, s_in, B, mode, seed=0):
+    cfg = UpliftUpsampleConfig.preset(name)
+    spec = spec_from_config(cfg)
+    w = weights.init_weights(spec, 1, perturb=True)
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(-1, 1, (B, spec.n_tok, 17, 2)).astype(np.float32)
+    so = cfg.SEQUENCE_STRIDE
+    if mode == "centred":
+        m = np.stack([stride_mask.stride_mask(spec.n_tok, so, s_in)] * B)
+    elif mode == "shifted":
+        lo, hi, ep = stride_mask.rand_shift_range(s_in // so)
+        sh = rng.integers(lo, hi, size=B, endpoint=ep)
+        m = np.stack([stride_mask.stride_mask(spec.n_tok, so, s_in, shift_tokens=int(s)) for s in sh])
+    else:  # "global": eval alignment, includes all-masked windows when i % s_out != 0
+        m = stride_mask.batch_stride_masks_eval(spec.n_tok, so, s_in, center_frames=np.arange(B) * 3)
+    return cfg, spec, w, x, m
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name,s_in,B,mode", [
+    ("h36m_81", 4, 16, "centred"),
+    ("h36m_81", 10, 9, "shifted"),
+    ("h36m_81", 20, 5, "global"),
+    ("h36m_351", 5, 6, "centred"),
+    ("h36m_351", 10, 7, "shifted"),
+    ("h36m_351", 20, 8, "shifted"),
+    ("h36m_351", 20, 11, "global"),
+])
+def test_forward_matches_oracle(name, s_in, B, mode, precision):
+    cfg, spec, w, x, m = _case(name, s_in, B, mode)
+    want_full, want_central = O.test_step(spec, w, x, m, dtype=np.float64)
+    model = build_uplift_upsample_transformer(cfg, precision=precision, weights=w)
+    full, central = test_step(model, torch.from_numpy(x).cuda(), torch.from_numpy(m).cuda())
+    torch.cuda.synchronize()
+    e_f = np.abs(full.cpu().numpy() - want_full).max()
+    e_c = np.abs(central.cpu().numpy() - want_central).max()
+    print(f"{name} s_in={s_in} {mode} {precision}: max|err| full {e_f:.3e} central {e_c:.3e}")
+    assert e_f <= TOL[precision] and e_c <= TOL[precision]
+    assert model.last_launch_count > 0
+    model.close()
+
+
+def test_masked_frame_values_are_never_read():
+    cfg, spec, w, x, m = _case("h36m_351", 20, 6, "shifted")
+    model = build_uplift_upsample_transformer(cfg, precision="fp32", weights=w)
+    md = torch.from_numpy(m).cuda()
+    f1, c1 = test_step(model, torch.from_numpy(x).cuda(), md)
+    x2 = x.copy()
+    x2[~m] = np.nan                      # garbage in frames without 2-D input
+    f2, c2 = test_step(model, torch.from_numpy(x2).cuda(), md)
+    torch.cuda.synchronize()
+    assert torch.equal(f1, f2) and torch.equal(c1, c2)
+    model.close()
+
+
+def test_no_strided_input_model_and_weight_roundtrip(tmp_path):
+    cfg = UpliftUpsampleConfig.preset("h36m_81", MASK_STRIDE=None)
+    spec = spec_from_config(cfg)
+    w = weights.init_weights(spec, 3, perturb=True)
+    x = np.random.default_rng(5).uniform(-1, 1, (4, 41, 17, 2)).astype(np.float32)
+    want_full, want_central = O.forward(spec, w, x, None)
+    model = build_uplift_upsample_transformer(cfg, precision="fp32", weights=w)
+    full, central = model(torch.from_numpy(x).cuda())
+    torch.cuda.synchronize()
+    assert np.abs(full.cpu().numpy() - want_full).max() < 1e-4
+    assert np.abs(central.cpu().numpy() - want_central).max() < 1e-4
+    got = model.get_weights()
+    assert all(np.array_equal(got[k], w[k]) for k in w)
+    p = str(tmp_path / "w.npz")
+    model.save_weights(p)
+    m2 = build_uplift_upsample_transformer(cfg, precision="fp32")
+    m2.load_weights(p)
+    f2, c2 = m2(torch.from_numpy(x).cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(c2, central) and torch.equal(f2, full)
+    with pytest.raises(Exception):
+        bad = dict(w); bad[("temporal_fc", 0)] = np.zeros((384, 50), np.float32)
+        model.set_weights(bad)
+    model.close(); m2.close()
+
+
+def test_forward_host_and_batch_growth():
+    cfg, spec, w, x, m = _case("h36m_351", 10, 12, "shifted")
+    want_full, want_central = O.test_step(spec, w, x, m, dtype=np.float64)
+    model = build_uplift_upsample_transformer(cfg, precision="fp32", weights=w)
+    for B in (3, 12, 5):                 # workspace grows, then a smaller batch reuses it
+        full = np.empty((B, 71, 17, 3), np.float32)
+        central = np.empty((B, 17, 3), np.float32)
+        model.forward_host(x[:B].copy(), m[:B].astype(np.uint8).copy(), full, central)
+        assert np.abs(full - want_full[:B]).max() < 1e-4 and np.abs(central - want_central[:B]).max() < 1e-4
+    model.close()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_large_batch_properties(precision):
+    """BASELINE-size batch (512 windows): batch-permutation equivariance and agreement with a
+    window-by-window evaluation of a subset — properties that do not need the oracle at full size."""
+    cfg, spec, w, x, m = _case("h36m_351", 20, 512, "shifted", seed=3)
+    model = build_uplift_upsample_transformer(cfg, precision=precision, weights=w)
+    xd, md = torch.from_numpy(x).cuda(), torch.from_numpy(m).cuda()
+    full, central = test_step(model, xd, md)
+    perm = torch.randperm(512, device="cuda", generator=torch.Generator(device="cuda").manual_seed(0))
+    fp, cp = test_step(model, xd[perm].contiguous(), md[perm].contiguous())
+    torch.cuda.synchronize()
+    assert torch.equal(fp, full[perm]) and torch.equal(cp, central[perm])
+    fs, cs = test_step(model, xd[100:116].contiguous(), md[100:116].contiguous())
+    torch.cuda.synchronize()
+    assert torch.equal(cs, central[100:116]) and torch.equal(fs, full[100:116])
+    want_full, want_central = O.test_step(spec, w, x[:4], m[:4], dtype=np.float64)
+    assert np.abs(central[:4].cpu().numpy() - want_central).max() <= TOL[precision]
+    model.close()

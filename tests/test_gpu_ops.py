@@ -1,0 +1,176 @@
+"""Single-kernel parity on the B200: each CUDA kernel against the oracle, through the C ABI."""
+import ctypes
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+from oracle import forward_np as O
+from uplift_upsample_3dhpe_b200 import _lib, stride_mask
+
+
+def P(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return _lib.load()
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return t.to(dtype) if dtype is not None else t
+
+
+@pytest.mark.parametrize("B,n_tok", [(1, 71), (7, 41), (513, 71), (3000, 71), (5, 128), (4, 1)])
+def test_gather_list_is_bit_exact(lib, B, n_tok):
+    rng = np.random.default_rng(B)
+    mask = rng.random((B, n_tok)) < 0.4
+    if B > 2:
+        mask[1] = False          # an all-masked window
+        mask[2] = True
+    m = dev(mask.astype(np.uint8))
+    scratch = torch.zeros(B + 1, dtype=torch.int32, device="cuda")
+    lst = torch.full((B * n_tok,), -1, dtype=torch.int32, device="cuda")
+    cnt = torch.zeros(4, dtype=torch.int32, device="cuda")
+    _lib.check(lib.uu_op_build_gather(P(m), B, n_tok, P(scratch), P(lst), P(cnt), None))
+    torch.cuda.synchronize()
+    want = np.nonzero(mask.reshape(-1))[0]
+    assert int(cnt[0]) == want.size
+    assert np.array_equal(lst.cpu().numpy()[:want.size], want.astype(np.int32))
+    assert np.array_equal(scratch.cpu().numpy()[:B], np.concatenate([[0], np.cumsum(mask.sum(1))[:-1]]))
+
+
+def test_gather_empty_mask(lib):
+    m = torch.zeros((9, 71), dtype=torch.uint8, device="cuda")
+    scratch = torch.zeros(10, dtype=torch.int32, device="cuda")
+    lst = torch.full((9 * 71,), -1, dtype=torch.int32, device="cuda")
+    cnt = torch.ones(4, dtype=torch.int32, device="cuda")
+    _lib.check(lib.uu_op_build_gather(P(m), 9, 71, P(scratch), P(lst), P(cnt), None))
+    torch.cuda.synchronize()
+    assert int(cnt[0]) == 0 and int(lst.max()) == -1
+
+
+def test_token_fill(lib):
+    rng = np.random.default_rng(0)
+    B, N, d = 37, 71, 384
+    mask = np.stack([stride_mask.stride_mask(N, 5, 20, shift_tokens=b % 4 - 2) for b in range(B)])
+    x0 = rng.normal(size=(B * N, d)).astype(np.float32)
+    tok = rng.normal(size=d).astype(np.float32)
+    pe = rng.normal(size=(N, d)).astype(np.float32)
+    x = dev(x0)
+    _lib.check(lib.uu_op_token_fill(P(dev(mask.astype(np.uint8))), B * N, N, d, P(dev(tok)), P(dev(pe)), P(x), None))
+    torch.cuda.synchronize()
+    want = x0.copy().reshape(B, N, d)
+    want[~mask] = (tok + pe)[np.nonzero(~mask)[1]]
+    assert np.array_equal(x.cpu().numpy().reshape(B, N, d), want)      # selection + one fp32 add: exact
+
+
+@pytest.mark.parametrize("with_table", [False, True])
+def test_layernorm(lib, with_table):
+    rng = np.random.default_rng(1)
+    rows, d, period = 1001, 384, 23
+    x0 = (rng.normal(size=(rows, d)) * 3 + 1.5).astype(np.float32)
+    g = (1 + 0.1 * rng.normal(size=d)).astype(np.float32)
+    b = (0.1 * rng.normal(size=d)).astype(np.float32)
+    table = rng.normal(size=(period, d)).astype(np.float32)
+    xin = x0 + table[np.arange(rows) % period] if with_table else x0
+    want = O.layer_norm(xin.astype(np.float64), g.astype(np.float64), b.astype(np.float64), 1e-5)
+    for y_bf16 in (0, 1):
+        x = dev(x0)
+        y = torch.empty((rows, d), dtype=torch.bfloat16 if y_bf16 else torch.float32, device="cuda")
+        _lib.check(lib.uu_op_layernorm(P(x), rows, d, P(dev(g)), P(dev(b)), 1e-5, P(dev(table)) if with_table else None,
+                                       period, P(y), y_bf16, None))
+        torch.cuda.synchronize()
+        err = np.abs(y.float().cpu().numpy() - want).max()
+        assert err < (3e-2 if y_bf16 else 2e-5), err
+        if with_table:
+            assert np.array_equal(x.cpu().numpy(), xin)                 # PE add is written back
+
+
+@pytest.mark.parametrize("S,dh,masked", [(71, 48, True), (71, 48, False), (23, 48, False), (3, 48, False),
+                                          (41, 48, True), (128, 64, False), (11, 16, False)])
+def test_attention(lib, S, dh, masked):
+    rng = np.random.default_rng(S)
+    B, H = 5, 8
+    d = H * dh
+    qkv = rng.normal(size=(B, S, 3 * d)).astype(np.float32)
+    keep = np.ones((B, S), dtype=bool)
+    if masked:
+        keep = rng.random((B, S)) < 0.3
+        keep[0] = False                      # all-masked window -> uniform attention (fp32 rounding of -1e9)
+        keep[1, :] = False; keep[1, S // 2] = True
+
+    def ref(dtype):
+        q, k, v = [qkv[..., i * d:(i + 1) * d].astype(dtype).reshape(B, S, H, dh).transpose(0, 2, 1, 3) for i in range(3)]
+        logits = (q @ k.transpose(0, 1, 3, 2)) / dtype(math.sqrt(dh))
+        if masked:
+            logits = logits + (1 - keep[:, None, None, :].astype(dtype)) * dtype(-1e9)
+        return (O.softmax(logits) @ v).transpose(0, 2, 1, 3).reshape(B, S, d)
+
+    want = ref(np.float32)                   # fp32 semantics define the all-masked case
+    out = torch.empty((B, S, d), dtype=torch.float32, device="cuda")
+    _lib.check(lib.uu_op_attention(P(dev(qkv)), 0, B, S, H, dh, P(dev(keep.astype(np.uint8))) if masked else None, S,
+                                   P(out), None))
+    torch.cuda.synchronize()
+    assert np.abs(out.cpu().numpy() - want).max() < 2e-5
+    q16 = dev(qkv, torch.bfloat16)
+    out16 = torch.empty((B, S, d), dtype=torch.bfloat16, device="cuda")
+    _lib.check(lib.uu_op_attention(P(q16), 1, B, S, H, dh, P(dev(keep.astype(np.uint8))) if masked else None, S,
+                                   P(out16), None))
+    torch.cuda.synchronize()
+    assert np.abs(out16.float().cpu().numpy() - want).max() < 6e-2
+
+
+@pytest.mark.parametrize("M,N,K,flags", [(300, 384, 384, 0), (129, 51, 384, 0), (1000, 768, 384, 1),
+                                         (77, 384, 2304, 2), (64, 1152, 544, 3)])
+def test_gemm_f32(lib, M, N, K, flags):
+    rng = np.random.default_rng(M)
+    A = rng.normal(size=(M, K)).astype(np.float32)
+    Wm = (rng.normal(size=(K, N)) / math.sqrt(K)).astype(np.float32)
+    bias = rng.normal(size=N).astype(np.float32)
+    res = rng.normal(size=(M, N)).astype(np.float32)
+    want = A.astype(np.float64) @ Wm + bias
+    if flags & 1:
+        want = np.maximum(want, 0)
+    if flags & 2:
+        want = want + res
+    C = dev(res.copy())                       # residual aliases the output, as in the forward pass
+    _lib.check(lib.uu_op_gemm_f32(P(dev(A)), K, P(dev(Wm)), M, N, K, P(dev(bias)), flags, P(C), N, P(C), N, None))
+    torch.cuda.synchronize()
+    assert np.abs(C.cpu().numpy() - want).max() < 2e-5 * math.sqrt(K)
+
+
+@pytest.mark.parametrize("M,N,K,flags,c_bf16", [(128, 128, 64, 0, 0), (300, 384, 384, 0, 0), (129, 51, 384, 0, 0),
+                                                (1000, 768, 384, 1, 1), (77, 384, 2304, 2, 0), (640, 1152, 544, 1, 1),
+                                                (36352, 1152, 384, 0, 1)])
+def test_gemm_bf16_tcgen05(lib, M, N, K, flags, c_bf16):
+    rng = np.random.default_rng(M + N)
+    A = dev(rng.normal(size=(M, K)).astype(np.float32), torch.bfloat16)
+    Wm = dev((rng.normal(size=(K, N)) / math.sqrt(K)).astype(np.float32), torch.bfloat16)
+    n_pad = (N + 63) // 64 * 64
+    Wt = torch.zeros((n_pad, K), dtype=torch.bfloat16, device="cuda")
+    Wt[:N] = Wm.t()
+    bias = rng.normal(size=N).astype(np.float32)
+    res = rng.normal(size=(M, N)).astype(np.float32)
+    want = A.float().cpu().numpy().astype(np.float64) @ Wm.float().cpu().numpy().astype(np.float64) + bias
+    if flags & 1:
+        want = np.maximum(want, 0)
+    if flags & 2:
+        want = want + res
+    if c_bf16:
+        C = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device="cuda")
+        r = dev(res)
+    else:
+        C = dev(res.copy())
+        r = C
+    _lib.check(lib.uu_op_gemm_bf16(P(A), K, M, K, P(Wt), n_pad, N, P(dev(bias)), flags, P(r), N, P(C), c_bf16, N, None))
+    torch.cuda.synchronize()
+    got = C.float().cpu().numpy()
+    assert np.isfinite(got).all()
+    err = np.abs(got - want).max()
+    assert err < (5e-2 if c_bf16 else 1e-3), err

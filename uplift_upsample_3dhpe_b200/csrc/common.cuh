@@ -1,0 +1,125 @@
+// Shared declarations of the uu3d CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+namespace uu {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- error plumbing: never throw across the C ABI -------------------------------------------
+void set_error(const std::string& msg);
+#define UU_CUDA(expr)                                                                            \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess) {                                                                     \
+      ::uu::set_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " at " +       \
+                      __FILE__ + ":" + std::to_string(__LINE__));                                \
+      return 1;                                                                                  \
+    }                                                                                            \
+  } while (0)
+#define UU_CHECK(cond, msg)                                                                      \
+  do {                                                                                           \
+    if (!(cond)) {                                                                               \
+      ::uu::set_error(std::string(msg) + " (" #cond ") at " + __FILE__ + ":" +                   \
+                      std::to_string(__LINE__));                                                 \
+      return 1;                                                                                  \
+    }                                                                                            \
+  } while (0)
+
+// ---- row addressing shared by every GEMM flavour --------------------------------------------
+// Logical GEMM row r -> physical row of a (batch, position) matrix:
+//   pos = (r % rpb) * step + offset ; row = (r / rpb) * batch_rows + pos ; dropped if pos >= batch_rows.
+// plain matrix:           rpb = INT_MAX
+// zero-padded conv input: rpb = L,  batch_rows = L_out*s, offset = pad_left, step = 1   (write side)
+// strided identity path:  rpb = L_out, batch_rows = L, offset = c0, step = s            (read side)
+struct RowMap {
+  int rpb = 0x7fffffff;
+  int batch_rows = 0x7fffffff;
+  int offset = 0;
+  int step = 1;
+};
+__host__ __device__ inline long long map_row(const RowMap& m, int r) {
+  if (m.rpb == 0x7fffffff) return r;
+  int b = r / m.rpb;
+  int pos = (r - b * m.rpb) * m.step + m.offset;
+  if (pos >= m.batch_rows) return -1;
+  return (long long)b * m.batch_rows + pos;
+}
+
+enum EpiFlags : int {
+  EPI_RELU = 1,       // max(., 0) after bias
+  EPI_RESIDUAL = 2,   // += Res[map_row(rmap, r)][col]
+  EPI_ROWTABLE = 4,   // += table[(crow % table_period)][col]   (temporal positional encoding)
+};
+
+// Epilogue description shared by the SIMT and the tcgen05 GEMM.
+struct Epilogue {
+  const float* bias = nullptr;       // [N] or null
+  int flags = 0;
+  const float* res = nullptr;        // fp32 residual source (may alias the fp32 output)
+  long long ldr = 0;
+  RowMap rmap;
+  const float* table = nullptr;      // [table_period, N]
+  int table_period = 1;
+  const int* c_rowidx = nullptr;     // optional scatter list: physical output row of logical row r
+  const int* m_dev = nullptr;        // optional device-side row count (<= M)
+  RowMap cmap;                       // output row mapping (ignored when c_rowidx is set)
+};
+
+// ---- kernel launchers (kernels_f32.cu) --------------------------------------------------------
+// All launchers are asynchronous on `st` and return cudaGetLastError().
+
+// Valid-frame gather list from the stride mask: list[0..count) = b*n_tok+n of frames with mask != 0,
+// ascending.  count_out[0] = count.  `scratch` holds B+1 ints.
+cudaError_t launch_build_gather(const uint8_t* mask, int B, int n_tok, int* scratch, int* list, int* count_out,
+                                cudaStream_t st);
+
+struct SpatialParams {
+  const float* x2d;          // (B*n_tok, J, 2)
+  const int* list;           // gather list (frame ids) or null = all frames
+  const int* count;          // device count of valid frames (null with list == null)
+  int max_frames;            // B*n_tok
+  int J, depth;
+  const float* embed_k;      // (2, 32)
+  const float* embed_b;      // (32)
+  const float* pe;           // (J, 32)
+  const float* const* blocks;  // device array [depth][16] of tensor pointers, file order
+  const float* norm_g;       // spatial_norm
+  const float* norm_b;
+  void* out;                 // (n_valid, J*32) compact, fp32 or bf16
+  int out_bf16;
+};
+cudaError_t launch_spatial_f32(const SpatialParams& p, cudaStream_t st);
+
+// Rows without 2-D input: x[row] = token + pe[row % n_tok]   (net:350-352 for masked frames)
+cudaError_t launch_token_fill(const uint8_t* mask, int rows, int n_tok, int d, const float* token, const float* pe,
+                              float* x, cudaStream_t st);
+
+// y = LN(x (+ table[row % period], written back to x when table != null)); d % 128 == 0, d <= 1024
+cudaError_t launch_layernorm(float* x, int rows, int d, const float* gamma, const float* beta, float eps,
+                             const float* table, int period, void* y, int y_bf16, cudaStream_t st);
+
+// fp32 -> bf16 copy of n elements (n % 4 == 0): operand cast for the tensor-core heads
+cudaError_t launch_cast_bf16(const float* x, bf16* y, long long n, cudaStream_t st);
+
+// softmax(q k^T / sqrt(dh) + keymask * -1e9) v per (window, head); qkv rows = [q | k | v] (3*d)
+cudaError_t launch_attention(const void* qkv, int is_bf16, int B, int S, int heads, int dh, const uint8_t* mask,
+                             int mask_stride, void* out, cudaStream_t st);
+
+// C = epi(A[M,K] * W[K,N]); A fp32 or bf16 row-major with leading dimension lda; W fp32 (in,out).
+cudaError_t launch_gemm_simt(const void* A, int a_bf16, long long lda, const float* W, int M, int N, int K,
+                             const Epilogue& epi, void* C, int c_bf16, long long ldc, cudaStream_t st);
+
+// ---- tcgen05 GEMM (gemm_tc.cu) ----------------------------------------------------------------
+struct TcGemmPlan;   // holds the TMA tensor maps of one GEMM call site
+int tc_gemm_plan_create(TcGemmPlan** out, const bf16* A, long long lda, int M, int K, const bf16* Wt, int N_pad,
+                        int N);
+void tc_gemm_plan_destroy(TcGemmPlan* p);
+cudaError_t tc_gemm_launch(const TcGemmPlan* p, const Epilogue& epi, void* C, int c_bf16, long long ldc,
+                           cudaStream_t st);
+
+}  // namespace uu

@@ -1,0 +1,353 @@
+// K3: bf16 GEMM on the 5th-generation tensor cores (sm_100a):
+//   TMA (cp.async.bulk.tensor, 128B swizzle) -> shared-memory ring -> tcgen05.mma (accumulator in
+//   TMEM) -> tcgen05.ld -> fused epilogue (bias / ReLU / residual / positional table / row scatter).
+// Warp roles in a 192-thread CTA: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (one TMEM lane quarter each).  One 128 x BLOCK_N output tile per CTA; two
+// CTAs are co-resident per SM so one CTA's epilogue overlaps the other's MMA main loop.
+//
+// A  : bf16 row-major [M, K] with leading dimension lda (activations; the strided Conv1D reads its
+//      zero-padded input as a [B*L_out, 3*C] matrix with lda = stride*C — implicit GEMM, no im2col).
+// Wt : bf16 [N_pad, K] = W^T, i.e. both operands are K-major.
+#include <cuda.h>   // CUtensorMap types only; the encoder is fetched through the runtime (no -lcuda)
+
+#include "common.cuh"
+#include "epilogue.cuh"
+
+namespace uu {
+
+constexpr int TC_BLOCK_M = 128;
+constexpr int TC_BLOCK_K = 64;          // 64 bf16 = 128 B = one swizzle atom row
+constexpr int TC_UMMA_K = 16;
+constexpr int TC_THREADS = 192;
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Bounded wait: a protocol bug must trap, not hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  const long long t0 = clock64();
+  while (true) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 4000000000LL) {
+      printf("uu3d: mbarrier timeout block (%d,%d) thread %d\n", blockIdx.x, blockIdx.y, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor, K-major operand, 128B swizzle: rows are 128 B apart, 8-row
+// groups 1024 B apart (SBO); LBO is unused for swizzled K-major layouts (encoded 1).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);        // start address, bits [0,14)
+  d |= (uint64_t)1 << 16;                              // leading byte offset (>>4), bits [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;                    // stride byte offset (>>4), bits [32,46)
+  d |= (uint64_t)1 << 46;                              // descriptor version 1 (sm_100)
+  d |= (uint64_t)2 << 61;                              // layout type: SWIZZLE_128B
+  return d;
+}
+// Instruction descriptor, kind::f16: D = f32, A = B = bf16, both K-major, M x N tile.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4)                      // c_format = F32
+         | (1u << 7)                    // a_format = BF16
+         | (1u << 10)                   // b_format = BF16
+         | ((uint32_t)(N >> 3) << 17)   // n_dim
+         | ((uint32_t)(M >> 4) << 24);  // m_dim
+}
+
+template <int BLOCK_N>
+struct TcCfg {
+  static constexpr int A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;   // 16 KB
+  static constexpr int B_BYTES = BLOCK_N * TC_BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = BLOCK_N >= 256 ? 4 : 3;
+  static constexpr int TMEM_COLS = BLOCK_N <= 32 ? 32 : BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BLOCK_N, typename TC>
+__global__ void __launch_bounds__(TC_THREADS) k_gemm_tc(const __grid_constant__ CUtensorMap map_a,
+                                                        const __grid_constant__ CUtensorMap map_b, int M, int N,
+                                                        int K, Epilogue epi, TC* __restrict__ C, long long ldc) {
+  using Cfg = TcCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  const int m_eff = epi.m_dev ? min(M, *epi.m_dev) : M;
+  const int row0 = blockIdx.x * TC_BLOCK_M, col0 = blockIdx.y * BLOCK_N;
+  if (row0 >= m_eff) return;   // uniform for the CTA (compact valid-frame GEMM, device-side row count)
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tmem_full_bar = empty_bar + Cfg::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_kb = (K + TC_BLOCK_K - 1) / TC_BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % Cfg::STAGES;
+        const uint32_t ph = (kb / Cfg::STAGES) & 1;
+        mbar_wait(empty_bar + s, ph ^ 1);
+        uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
+        uint8_t* b_dst = a_dst + Cfg::A_BYTES;
+        mbar_expect_tx(full_bar + s, Cfg::STAGE_BYTES);
+        tma_load_2d(a_dst, &map_a, full_bar + s, kb * TC_BLOCK_K, row0);
+        tma_load_2d(b_dst, &map_b, full_bar + s, kb * TC_BLOCK_K, col0);
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(TC_BLOCK_M, BLOCK_N);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % Cfg::STAGES;
+        const uint32_t ph = (kb / Cfg::STAGES) & 1;
+        mbar_wait(full_bar + s, ph);
+        tcgen05_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
+        const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+        const uint64_t a_desc = make_sw128_desc(a_addr), b_desc = make_sw128_desc(b_addr);
+#pragma unroll
+        for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
+          // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (>>4) address field
+          umma_bf16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+        }
+        umma_commit(empty_bar + s);           // frees the smem stage when these MMAs retire
+      }
+      umma_commit(tmem_full_bar);             // accumulator complete
+    }
+  } else {
+    // ---------------- epilogue: TMEM -> registers -> global ----------------
+    const int q = warp & 3;                   // TMEM lane quarter this warp may access
+    const int r = row0 + q * 32 + lane;
+    mbar_wait(tmem_full_bar, 0);
+    tcgen05_fence_after();
+    const bool row_ok = r < m_eff;
+    EpiRow er;
+    er.crow = -1; er.rrow = 0; er.trow = 0;
+    if (row_ok) er = epi_row(epi, r);
+    const bool vec_ok = (N % 4 == 0) && (ldc % 4 == 0) && (!(epi.flags & EPI_RESIDUAL) || (epi.ldr % 4 == 0));
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      const int cbase = col0 + c0;
+      const bool do_store = row_ok && er.crow >= 0 && cbase < N;
+      TC* crow_ptr = C + (do_store ? er.crow : 0) * ldc;
+      if (!do_store) {
+        // nothing to write for this row / column chunk
+      } else if (vec_ok) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const int c = cbase + g * 4;
+          if (c >= N) break;
+          float o[4] = {__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]),
+                        __uint_as_float(v[4 * g + 3])};
+          if (epi.bias) {
+            const float4 b = *reinterpret_cast<const float4*>(epi.bias + c);
+            o[0] += b.x; o[1] += b.y; o[2] += b.z; o[3] += b.w;
+          }
+          if (epi.flags & EPI_RELU) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[i] = fmaxf(o[i], 0.f);
+          }
+          if (epi.flags & EPI_RESIDUAL) {
+            const float4 t = *reinterpret_cast<const float4*>(epi.res + er.rrow * epi.ldr + c);
+            o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w;
+          }
+          if (epi.flags & EPI_ROWTABLE) {
+            const float4 t = *reinterpret_cast<const float4*>(epi.table + (long long)er.trow * N + c);
+            o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w;
+          }
+          if constexpr (sizeof(TC) == 4) {
+            *reinterpret_cast<float4*>(crow_ptr + c) = make_float4(o[0], o[1], o[2], o[3]);
+          } else {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(o[0], o[1]), hi = __floats2bfloat162_rn(o[2], o[3]);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&lo);
+            pk.y = *reinterpret_cast<uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(crow_ptr + c) = pk;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int c = cbase + i;
+          if (c < N) store_out(crow_ptr + c, epi_value(epi, er, __uint_as_float(v[i]), c, N));
+        }
+      }
+      __syncwarp();   // reconverge before the next warp-collective tcgen05.ld
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side: tensor maps and launch
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encoder() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+static int encode_2d(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box_cols,
+                     uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encoder();
+  UU_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  UU_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16-byte aligned");
+  UU_CHECK((ld_elems * 2) % 16 == 0, "TMA row pitch must be a multiple of 16 bytes");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  UU_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
+  return 0;
+}
+
+struct TcGemmPlan {
+  CUtensorMap map_a, map_b;
+  int M, N, N_pad, K, block_n;
+};
+
+int tc_gemm_plan_create(TcGemmPlan** out, const bf16* A, long long lda, int M, int K, const bf16* Wt, int N_pad, int N) {
+  UU_CHECK(M > 0 && N > 0 && K > 0 && N <= N_pad, "bad GEMM shape");
+  TcGemmPlan* p = new TcGemmPlan();
+  p->M = M; p->N = N; p->N_pad = N_pad; p->K = K;
+  p->block_n = (N_pad % 128 == 0) ? 128 : 64;
+  if (N_pad % p->block_n != 0) {
+    delete p;
+    set_error("tcgen05 GEMM needs the packed weight rows padded to a multiple of 64");
+    return 1;
+  }
+  if (encode_2d(&p->map_a, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, TC_BLOCK_K, TC_BLOCK_M) ||
+      encode_2d(&p->map_b, Wt, (uint64_t)K, (uint64_t)N_pad, (uint64_t)K, TC_BLOCK_K, (uint32_t)p->block_n)) {
+    delete p;
+    return 1;
+  }
+  *out = p;
+  return 0;
+}
+
+void tc_gemm_plan_destroy(TcGemmPlan* p) { delete p; }
+
+template <int BLOCK_N, typename TC>
+static cudaError_t tc_launch_t(const TcGemmPlan* p, const Epilogue& epi, void* C, long long ldc, cudaStream_t st) {
+  using Cfg = TcCfg<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BLOCK_N, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  dim3 grid((p->M + TC_BLOCK_M - 1) / TC_BLOCK_M, p->N_pad / BLOCK_N);
+  k_gemm_tc<BLOCK_N, TC><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(p->map_a, p->map_b, p->M, p->N, p->K, epi,
+                                                                    reinterpret_cast<TC*>(C), ldc);
+  return cudaGetLastError();
+}
+
+cudaError_t tc_gemm_launch(const TcGemmPlan* p, const Epilogue& epi, void* C, int c_bf16, long long ldc,
+                           cudaStream_t st) {
+  if (p->block_n == 128)
+    return c_bf16 ? tc_launch_t<128, bf16>(p, epi, C, ldc, st) : tc_launch_t<128, float>(p, epi, C, ldc, st);
+  return c_bf16 ? tc_launch_t<64, bf16>(p, epi, C, ldc, st) : tc_launch_t<64, float>(p, epi, C, ldc, st);
+}
+
+}  // namespace uu

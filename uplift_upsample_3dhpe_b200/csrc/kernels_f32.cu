@@ -1,0 +1,652 @@
+// CUDA-core kernels of the uu3d hot path (sm_100a): stride-mask gather list, fused spatial
+// transformer, upsampling-token fill, LayerNorm, softmax attention and the fp32 reference-precision
+// GEMM.  Together they are the complete fp32 ("exact") forward path; the bf16 path swaps the GEMMs
+// for the tcgen05 kernel in gemm_tc.cu and keeps the memory-bound kernels.
+#include <algorithm>
+
+#include "common.cuh"
+#include "epilogue.cuh"
+
+namespace uu {
+
+// =================================================================================================
+// K1a: valid-frame gather list from the stride mask (bit-exact index work).
+// reference semantics: frames with mask==0 never influence the output (their spatial result is
+// multiplied by 0, net:350), so the spatial stage only runs on list[0..count).
+// =================================================================================================
+__global__ void k_mask_count(const uint8_t* __restrict__ mask, int B, int n_tok, int* __restrict__ counts) {
+  int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= B) return;
+  int c = 0;
+  for (int n0 = 0; n0 < n_tok; n0 += 32) {
+    int n = n0 + lane;
+    bool v = n < n_tok && mask[(long long)w * n_tok + n] != 0;
+    c += __popc(__ballot_sync(0xffffffffu, v));
+  }
+  if (lane == 0) counts[w] = c;
+}
+
+// single-CTA exclusive scan of counts[0..B) in place; counts[B] = total; count_out[0] = total
+__global__ void k_mask_scan(int* __restrict__ counts, int B, int* __restrict__ count_out) {
+  __shared__ int warp_sums[32];
+  __shared__ int carry_s;
+  int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < B; base += blockDim.x) {
+    int i = base + tid;
+    int v = i < B ? counts[i] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      int s = lane < (blockDim.x >> 5) ? warp_sums[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, s, o);
+        if (lane >= o) s += y;
+      }
+      warp_sums[lane] = s;   // inclusive
+    }
+    __syncthreads();
+    int carry = carry_s;
+    int excl = carry + (wid ? warp_sums[wid - 1] : 0) + x - v;
+    if (i < B) counts[i] = excl;
+    __syncthreads();
+    if (tid == blockDim.x - 1) carry_s = carry + warp_sums[(blockDim.x >> 5) - 1];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    counts[B] = carry_s;
+    count_out[0] = carry_s;
+  }
+}
+
+__global__ void k_mask_fill(const uint8_t* __restrict__ mask, int B, int n_tok, const int* __restrict__ offs,
+                            int* __restrict__ list) {
+  int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= B) return;
+  int base = offs[w];
+  for (int n0 = 0; n0 < n_tok; n0 += 32) {
+    int n = n0 + lane;
+    bool v = n < n_tok && mask[(long long)w * n_tok + n] != 0;
+    unsigned bal = __ballot_sync(0xffffffffu, v);
+    if (v) list[base + __popc(bal & ((1u << lane) - 1u))] = w * n_tok + n;
+    base += __popc(bal);
+  }
+}
+
+cudaError_t launch_build_gather(const uint8_t* mask, int B, int n_tok, int* scratch, int* list, int* count_out,
+                                cudaStream_t st) {
+  int blocks = (B * 32 + 127) / 128;
+  k_mask_count<<<blocks, 128, 0, st>>>(mask, B, n_tok, scratch);
+  k_mask_scan<<<1, 1024, 0, st>>>(scratch, B, count_out);
+  k_mask_fill<<<blocks, 128, 0, st>>>(mask, B, n_tok, scratch, list);
+  return cudaGetLastError();
+}
+
+// =================================================================================================
+// K2 (fp32): fused spatial transformer.  One warp owns one frame (17 joint tokens x 32 channels,
+// lane == channel); a CTA of 8 warps shares one block's weights in shared memory.  Nothing but the
+// final (J*32) row per frame ever reaches HBM.
+// reference: net:313-333 (spatial_transformation), vit:176-195 (block), vit:99-156 (MHA).
+// =================================================================================================
+constexpr int SP_J = 17;        // joints
+constexpr int SP_D = 32;        // SPATIAL_EMBED_DIM
+constexpr int SP_HID = 64;      // hidden = d * MLP_RATIO
+constexpr int SP_HEADS = 8;     // head_dim 4
+constexpr int SP_F = 8;         // frames (warps) per CTA
+constexpr int SP_YS = 36;       // row stride of the LN/attention-output buffer (float4 aligned)
+constexpr int SP_QS = 100;      // row stride of the qkv / hidden buffer
+// per-block weight image in shared memory (floats)
+constexpr int W_LN1G = 0, W_LN1B = 32, W_QKV = 64, W_BQKV = W_QKV + 32 * 96, W_P = W_BQKV + 96,
+              W_BP = W_P + 32 * 32, W_LN2G = W_BP + 32, W_LN2B = W_LN2G + 32, W_FC1 = W_LN2B + 32,
+              W_B1 = W_FC1 + 32 * 64, W_FC2 = W_B1 + 64, W_B2 = W_FC2 + 64 * 32, W_TOTAL = W_B2 + 32;
+
+template <int K, int NC>
+__device__ __forceinline__ void warp_linear(const float* __restrict__ in, int in_stride, const float* __restrict__ W,
+                                            const float* __restrict__ bias, float (&acc)[SP_J][NC], int lane) {
+  constexpr int NOUT = NC * 32;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    float b = bias[lane + 32 * c];
+#pragma unroll
+    for (int r = 0; r < SP_J; ++r) acc[r][c] = b;
+  }
+#pragma unroll 2
+  for (int k = 0; k < K; k += 4) {
+    float w[4][NC];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+      for (int c = 0; c < NC; ++c) w[kk][c] = W[(k + kk) * NOUT + lane + 32 * c];
+#pragma unroll
+    for (int r = 0; r < SP_J; ++r) {
+      float4 a = *reinterpret_cast<const float4*>(in + r * in_stride + k);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        acc[r][c] = fmaf(a.x, w[0][c], acc[r][c]);
+        acc[r][c] = fmaf(a.y, w[1][c], acc[r][c]);
+        acc[r][c] = fmaf(a.z, w[2][c], acc[r][c]);
+        acc[r][c] = fmaf(a.w, w[3][c], acc[r][c]);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// LayerNorm over the 32 channels of each of the 17 rows (lane == channel), Keras non-fused form.
+__device__ __forceinline__ void warp_ln_rows(const float* __restrict__ xs, float* __restrict__ ys, float g, float b,
+                                             float eps, int lane) {
+#pragma unroll
+  for (int r = 0; r < SP_J; ++r) {
+    float v = xs[r * SP_D + lane];
+    float mean = warp_sum(v) * (1.f / SP_D);
+    float d = v - mean;
+    float var = warp_sum(d * d) * (1.f / SP_D);
+    float inv = g * rsqrtf(var + eps);
+    ys[r * SP_YS + lane] = v * inv + (b - mean * inv);
+  }
+}
+
+template <typename TOut>
+__global__ void __launch_bounds__(SP_F * 32, 1) k_spatial_f32(SpatialParams p) {
+  extern __shared__ __align__(16) float smem[];
+  float* wbuf = smem;                                     // W_TOTAL
+  float* xs_all = wbuf + W_TOTAL;                         // SP_F * 17*32
+  float* ys_all = xs_all + SP_F * SP_J * SP_D;            // SP_F * 17*36
+  float* qs_all = ys_all + SP_F * SP_J * SP_YS;           // SP_F * 17*100
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_valid = p.count ? *p.count : p.max_frames;
+  const int g0 = blockIdx.x * SP_F;
+  if (g0 >= n_valid) return;                              // whole CTA past the gather list
+  const int g = g0 + warp;
+  const bool active = g < n_valid;
+  float* xs = xs_all + warp * SP_J * SP_D;
+  float* ys = ys_all + warp * SP_J * SP_YS;
+  float* qs = qs_all + warp * SP_J * SP_QS;
+
+  // S1: key-point embedding + spatial positional encoding (net:321-323)
+  if (active) {
+    const int fr = p.list ? p.list[g] : g;
+    const float* x = p.x2d + (long long)fr * SP_J * 2;
+    const float w0 = p.embed_k[lane], w1 = p.embed_k[SP_D + lane], be = p.embed_b[lane];
+#pragma unroll
+    for (int j = 0; j < SP_J; ++j) {
+      float2 xy = *reinterpret_cast<const float2*>(x + 2 * j);
+      // Dense = x @ W + b (sum over k in order), then + PE
+      xs[j * SP_D + lane] = (fmaf(xy.y, w1, xy.x * w0) + be) + p.pe[j * SP_D + lane];
+    }
+  }
+
+  for (int l = 0; l < p.depth; ++l) {
+    __syncthreads();                                      // everyone done with the previous block's weights
+    const float* const* t = p.blocks + l * 16;
+    for (int i = threadIdx.x; i < 32; i += blockDim.x) {
+      wbuf[W_LN1G + i] = t[0][i]; wbuf[W_LN1B + i] = t[1][i];
+      wbuf[W_BQKV + i] = t[3][i]; wbuf[W_BQKV + 32 + i] = t[5][i]; wbuf[W_BQKV + 64 + i] = t[7][i];
+      wbuf[W_BP + i] = t[9][i];
+      wbuf[W_LN2G + i] = t[10][i]; wbuf[W_LN2B + i] = t[11][i];
+      wbuf[W_B2 + i] = t[15][i];
+    }
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) wbuf[W_B1 + i] = t[13][i];
+    for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) {
+      int k = i >> 5, c = i & 31;
+      wbuf[W_QKV + k * 96 + c] = t[2][i];
+      wbuf[W_QKV + k * 96 + 32 + c] = t[4][i];
+      wbuf[W_QKV + k * 96 + 64 + c] = t[6][i];
+      wbuf[W_P + i] = t[8][i];
+    }
+    for (int i = threadIdx.x; i < 32 * 64; i += blockDim.x) {
+      wbuf[W_FC1 + i] = t[12][i];
+      wbuf[W_FC2 + i] = t[14][i];
+    }
+    __syncthreads();
+    if (!active) continue;
+
+    // y = LN1(x)
+    warp_ln_rows(xs, ys, wbuf[W_LN1G + lane], wbuf[W_LN1B + lane], 1e-5f, lane);
+    __syncwarp();
+    {  // q | k | v = y @ [Wq Wk Wv] + b
+      float acc[SP_J][3];
+      warp_linear<SP_D, 3>(ys, SP_YS, wbuf + W_QKV, wbuf + W_BQKV, acc, lane);
+#pragma unroll
+      for (int r = 0; r < SP_J; ++r) {
+        qs[r * SP_QS + lane] = acc[r][0];
+        qs[r * SP_QS + 32 + lane] = acc[r][1];
+        qs[r * SP_QS + 64 + lane] = acc[r][2];
+      }
+    }
+    __syncwarp();
+    // attention: 8 heads x 17 queries = 136 items over 32 lanes (vit:117-129), head_dim 4, scale 1/2
+    for (int it = lane; it < SP_HEADS * SP_J; it += 32) {
+      const int h = it / SP_J, i = it - h * SP_J;
+      const float4 q = *reinterpret_cast<const float4*>(qs + i * SP_QS + h * 4);
+      float s[SP_J];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < SP_J; ++j) {
+        const float4 kk = *reinterpret_cast<const float4*>(qs + j * SP_QS + 32 + h * 4);
+        float d = fmaf(q.w, kk.w, fmaf(q.z, kk.z, fmaf(q.y, kk.y, q.x * kk.x)));
+        s[j] = d * 0.5f;
+        mx = fmaxf(mx, s[j]);
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < SP_J; ++j) {
+        s[j] = expf(s[j] - mx);
+        sum += s[j];
+      }
+      const float inv = 1.f / sum;
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < SP_J; ++j) {
+        const float4 v = *reinterpret_cast<const float4*>(qs + j * SP_QS + 64 + h * 4);
+        const float pj = s[j] * inv;
+        o.x = fmaf(pj, v.x, o.x); o.y = fmaf(pj, v.y, o.y); o.z = fmaf(pj, v.z, o.z); o.w = fmaf(pj, v.w, o.w);
+      }
+      *reinterpret_cast<float4*>(ys + i * SP_YS + h * 4) = o;     // heads merged: channel = h*4 + d
+    }
+    __syncwarp();
+    {  // x += attn @ Wp + bp
+      float acc[SP_J][1];
+      warp_linear<SP_D, 1>(ys, SP_YS, wbuf + W_P, wbuf + W_BP, acc, lane);
+#pragma unroll
+      for (int r = 0; r < SP_J; ++r) xs[r * SP_D + lane] += acc[r][0];
+    }
+    __syncwarp();
+    warp_ln_rows(xs, ys, wbuf[W_LN2G + lane], wbuf[W_LN2B + lane], 1e-5f, lane);
+    __syncwarp();
+    {  // h = gelu_erf(z @ W1 + b1)
+      float acc[SP_J][2];
+      warp_linear<SP_D, 2>(ys, SP_YS, wbuf + W_FC1, wbuf + W_B1, acc, lane);
+#pragma unroll
+      for (int r = 0; r < SP_J; ++r)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          float v = acc[r][c];
+          qs[r * SP_QS + lane + 32 * c] = 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+        }
+    }
+    __syncwarp();
+    {  // x += h @ W2 + b2
+      float acc[SP_J][1];
+      warp_linear<SP_HID, 1>(qs, SP_QS, wbuf + W_FC2, wbuf + W_B2, acc, lane);
+#pragma unroll
+      for (int r = 0; r < SP_J; ++r) xs[r * SP_D + lane] += acc[r][0];
+    }
+    __syncwarp();
+  }
+  if (!active) return;
+  // spatial_norm (eps 1e-6, net:238) and joint-major flatten (net:330): out[g][j*32 + c]
+  {
+    const float gn = p.norm_g[lane], bn = p.norm_b[lane];
+    TOut* out = reinterpret_cast<TOut*>(p.out) + (long long)g * SP_J * SP_D;
+#pragma unroll
+    for (int r = 0; r < SP_J; ++r) {
+      float v = xs[r * SP_D + lane];
+      float mean = warp_sum(v) * (1.f / SP_D);
+      float d = v - mean;
+      float var = warp_sum(d * d) * (1.f / SP_D);
+      float inv = gn * rsqrtf(var + 1e-6f);
+      store_out(out + r * SP_D + lane, v * inv + (bn - mean * inv));
+    }
+  }
+}
+
+cudaError_t launch_spatial_f32(const SpatialParams& p, cudaStream_t st) {
+  if (p.J != SP_J) return cudaErrorInvalidValue;
+  const size_t smem = sizeof(float) * (W_TOTAL + SP_F * SP_J * (SP_D + SP_YS + SP_QS));
+  const int grid = (p.max_frames + SP_F - 1) / SP_F;
+  if (grid == 0) return cudaSuccess;
+  cudaError_t e;
+  if (p.out_bf16) {
+    e = cudaFuncSetAttribute(k_spatial_f32<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_spatial_f32<bf16><<<grid, SP_F * 32, smem, st>>>(p);
+  } else {
+    e = cudaFuncSetAttribute(k_spatial_f32<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_spatial_f32<float><<<grid, SP_F * 32, smem, st>>>(p);
+  }
+  return cudaGetLastError();
+}
+
+// =================================================================================================
+// K1b: upsampling-token fill for frames without 2-D input: x[row] = token + PE[row % n_tok].
+// (net:350-352; rows with mask==1 are written by the 544->384 GEMM epilogue.)  float4, coalesced.
+// =================================================================================================
+__global__ void k_token_fill(const uint8_t* __restrict__ mask, int rows, int n_tok, int d4,
+                             const float4* __restrict__ token, const float4* __restrict__ pe, float4* __restrict__ x) {
+  const int per_block = blockDim.x / 32;
+  const int lane = threadIdx.x & 31;
+  for (int row = blockIdx.x * per_block + (threadIdx.x >> 5); row < rows; row += gridDim.x * per_block) {
+    if (mask[row]) continue;
+    const int n = row % n_tok;
+    for (int c = lane; c < d4; c += 32) {
+      float4 t = token[c], q = pe[(long long)n * d4 + c];
+      // m*x + (1-m)*tok with m == 0 is exactly tok (x finite), then + PE
+      x[(long long)row * d4 + c] = make_float4(t.x + q.x, t.y + q.y, t.z + q.z, t.w + q.w);
+    }
+  }
+}
+
+cudaError_t launch_token_fill(const uint8_t* mask, int rows, int n_tok, int d, const float* token, const float* pe,
+                              float* x, cudaStream_t st) {
+  if (rows == 0) return cudaSuccess;
+  if (d % 4) return cudaErrorInvalidValue;
+  int grid = (rows + 7) / 8;
+  if (grid > 148 * 16) grid = 148 * 16;
+  k_token_fill<<<grid, 256, 0, st>>>(mask, rows, n_tok, d / 4, reinterpret_cast<const float4*>(token),
+                                     reinterpret_cast<const float4*>(pe), reinterpret_cast<float4*>(x));
+  return cudaGetLastError();
+}
+
+// =================================================================================================
+// K4: LayerNorm over rows of d = 128*V channels, one warp per row, fp32 statistics (two-pass in
+// registers), Keras non-fused form.  Optional fused "x += table[row % period]" written back to x
+// (the strided blocks' positional encoding, net:126-128).
+// =================================================================================================
+template <int V, typename TOut>
+__global__ void k_layernorm(float* __restrict__ x, int rows, const float* __restrict__ gamma,
+                            const float* __restrict__ beta, float eps, const float* __restrict__ table, int period,
+                            TOut* __restrict__ y) {
+  constexpr int D = V * 128;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float4 v[V];
+  float4* xr = reinterpret_cast<float4*>(x + (long long)row * D);
+#pragma unroll
+  for (int i = 0; i < V; ++i) v[i] = xr[lane + 32 * i];
+  if (table) {
+    const float4* tr = reinterpret_cast<const float4*>(table + (long long)(row % period) * D);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float4 t = tr[lane + 32 * i];
+      v[i].x += t.x; v[i].y += t.y; v[i].z += t.z; v[i].w += t.w;
+      xr[lane + 32 * i] = v[i];
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(s) * (1.f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / D) + eps);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+  TOut* yr = y + (long long)row * D;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    float4 g = g4[lane + 32 * i], b = b4[lane + 32 * i];
+    float o0 = v[i].x * (g.x * rstd) + (b.x - mean * (g.x * rstd));
+    float o1 = v[i].y * (g.y * rstd) + (b.y - mean * (g.y * rstd));
+    float o2 = v[i].z * (g.z * rstd) + (b.z - mean * (g.z * rstd));
+    float o3 = v[i].w * (g.w * rstd) + (b.w - mean * (g.w * rstd));
+    if constexpr (sizeof(TOut) == 4) {
+      reinterpret_cast<float4*>(yr)[lane + 32 * i] = make_float4(o0, o1, o2, o3);
+    } else {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(o0, o1), hi = __floats2bfloat162_rn(o2, o3);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      reinterpret_cast<uint2*>(yr)[lane + 32 * i] = pk;
+    }
+  }
+}
+
+template <int V>
+static cudaError_t ln_dispatch(float* x, int rows, const float* g, const float* b, float eps, const float* table,
+                               int period, void* y, int y_bf16, cudaStream_t st) {
+  const int wpb = 8;
+  const int grid = (rows + wpb - 1) / wpb;
+  if (y_bf16)
+    k_layernorm<V, bf16><<<grid, wpb * 32, 0, st>>>(x, rows, g, b, eps, table, period, (bf16*)y);
+  else
+    k_layernorm<V, float><<<grid, wpb * 32, 0, st>>>(x, rows, g, b, eps, table, period, (float*)y);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_layernorm(float* x, int rows, int d, const float* gamma, const float* beta, float eps,
+                             const float* table, int period, void* y, int y_bf16, cudaStream_t st) {
+  if (rows == 0) return cudaSuccess;
+  switch (d) {
+    case 128: return ln_dispatch<1>(x, rows, gamma, beta, eps, table, period, y, y_bf16, st);
+    case 256: return ln_dispatch<2>(x, rows, gamma, beta, eps, table, period, y, y_bf16, st);
+    case 384: return ln_dispatch<3>(x, rows, gamma, beta, eps, table, period, y, y_bf16, st);
+    case 512: return ln_dispatch<4>(x, rows, gamma, beta, eps, table, period, y, y_bf16, st);
+    case 768: return ln_dispatch<6>(x, rows, gamma, beta, eps, table, period, y, y_bf16, st);
+    case 1024: return ln_dispatch<8>(x, rows, gamma, beta, eps, table, period, y, y_bf16, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+__global__ void k_cast_bf16(const float4* __restrict__ x, uint2* __restrict__ y, long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 v = x[i];
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+    y[i] = pk;
+  }
+}
+
+cudaError_t launch_cast_bf16(const float* x, bf16* y, long long n, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  if (n % 4) return cudaErrorInvalidValue;
+  long long n4 = n / 4;
+  int grid = (int)std::min<long long>((n4 + 255) / 256, 148 * 16);
+  k_cast_bf16<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<uint2*>(y), n4);
+  return cudaGetLastError();
+}
+
+// =================================================================================================
+// K5 (CUDA-core version): softmax attention per (window, head), S <= 128 keys, thread == query.
+// Literal reference arithmetic: logits = q.k / sqrt(dh) + keymask * -1e9 in fp32 (vit:117-123), so
+// an all-masked window reproduces the reference's uniform attention.
+// =================================================================================================
+__device__ __forceinline__ float ld_as_float(const float* p) { return *p; }
+__device__ __forceinline__ float ld_as_float(const bf16* p) { return __bfloat162float(*p); }
+
+template <int DH, typename T>
+__global__ void __launch_bounds__(128) k_attention(const T* __restrict__ qkv, int S, int heads,
+                                                   const uint8_t* __restrict__ mask, int mask_stride,
+                                                   T* __restrict__ out) {
+  extern __shared__ __align__(16) float sm[];
+  float* Ks = sm;                    // [S][DH]
+  float* Vs = Ks + S * DH;           // [S][DH]
+  float* Km = Vs + S * DH;           // [S] additive key-mask term
+  float* Sc = Km + ((S + 3) & ~3);   // [S][128] scores, thread-major columns
+  const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
+  const int d = heads * DH;
+  const long long row0 = (long long)b * S;
+  for (int i = tid; i < S * DH; i += 128) {
+    int j = i / DH, c = i - j * DH;
+    const T* r = qkv + (row0 + j) * 3 * d + h * DH + c;
+    Ks[i] = ld_as_float(r + d);
+    Vs[i] = ld_as_float(r + 2 * d);
+  }
+  for (int j = tid; j < S; j += 128)
+    Km[j] = mask ? (1.0f - (mask[(long long)b * mask_stride + j] ? 1.0f : 0.0f)) * -1e9f : 0.0f;
+  __syncthreads();
+  if (tid >= S) return;
+  float q[DH];
+  const T* qr = qkv + (row0 + tid) * 3 * d + h * DH;
+#pragma unroll
+  for (int c = 0; c < DH; ++c) q[c] = ld_as_float(qr + c);
+  const float scale = 1.0f / sqrtf((float)DH);
+  float mx = -INFINITY;
+  for (int j = 0; j < S; ++j) {
+    const float4* kr = reinterpret_cast<const float4*>(Ks + j * DH);
+    float a = 0.f;
+#pragma unroll
+    for (int c = 0; c < DH / 4; ++c) {
+      float4 k4 = kr[c];
+      a = fmaf(q[4 * c], k4.x, a); a = fmaf(q[4 * c + 1], k4.y, a);
+      a = fmaf(q[4 * c + 2], k4.z, a); a = fmaf(q[4 * c + 3], k4.w, a);
+    }
+    a = a * scale + Km[j];
+    Sc[j * 128 + tid] = a;
+    mx = fmaxf(mx, a);
+  }
+  float o[DH];
+#pragma unroll
+  for (int c = 0; c < DH; ++c) o[c] = 0.f;
+  float sum = 0.f;
+  for (int j = 0; j < S; ++j) {
+    const float pj = expf(Sc[j * 128 + tid] - mx);
+    sum += pj;
+    const float4* vr = reinterpret_cast<const float4*>(Vs + j * DH);
+#pragma unroll
+    for (int c = 0; c < DH / 4; ++c) {
+      float4 v4 = vr[c];
+      o[4 * c] = fmaf(pj, v4.x, o[4 * c]); o[4 * c + 1] = fmaf(pj, v4.y, o[4 * c + 1]);
+      o[4 * c + 2] = fmaf(pj, v4.z, o[4 * c + 2]); o[4 * c + 3] = fmaf(pj, v4.w, o[4 * c + 3]);
+    }
+  }
+  const float inv = 1.f / sum;
+  T* orow = out + (row0 + tid) * d + h * DH;
+#pragma unroll
+  for (int c = 0; c < DH; ++c) store_out(orow + c, o[c] * inv);
+}
+
+template <int DH, typename T>
+static cudaError_t attn_dispatch(const void* qkv, int B, int S, int heads, const uint8_t* mask, int mask_stride,
+                                 void* out, cudaStream_t st) {
+  size_t smem = sizeof(float) * (2 * S * DH + ((S + 3) & ~3) + S * 128);
+  cudaError_t e = cudaFuncSetAttribute(k_attention<DH, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_attention<DH, T><<<dim3(B, heads), 128, smem, st>>>((const T*)qkv, S, heads, mask, mask_stride, (T*)out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_attention(const void* qkv, int is_bf16, int B, int S, int heads, int dh, const uint8_t* mask,
+                             int mask_stride, void* out, cudaStream_t st) {
+  if (B == 0) return cudaSuccess;
+  if (S > 128 || S < 1) return cudaErrorInvalidValue;
+#define UU_ATTN_CASE(DHV)                                                                                   \
+  case DHV:                                                                                                 \
+    return is_bf16 ? attn_dispatch<DHV, bf16>(qkv, B, S, heads, mask, mask_stride, out, st)                 \
+                   : attn_dispatch<DHV, float>(qkv, B, S, heads, mask, mask_stride, out, st);
+  switch (dh) {
+    UU_ATTN_CASE(16)
+    UU_ATTN_CASE(32)
+    UU_ATTN_CASE(48)
+    UU_ATTN_CASE(64)
+    default: return cudaErrorInvalidValue;
+  }
+#undef UU_ATTN_CASE
+}
+
+// =================================================================================================
+// K3 (fp32): CUDA-core GEMM with the shared fused epilogue, 64x64x16 tiles, 4x4 micro-tiles.
+// This is the exact-precision path (<= 1e-4 against the fp32 oracle); throughput work goes through
+// the tcgen05 kernel.
+// =================================================================================================
+constexpr int GB_M = 64, GB_N = 64, GB_K = 16;
+
+template <typename TA, typename TC>
+__global__ void __launch_bounds__(256) k_gemm_simt(const TA* __restrict__ A, long long lda,
+                                                   const float* __restrict__ W, int M, int N, int K, Epilogue epi,
+                                                   TC* __restrict__ C, long long ldc) {
+  __shared__ __align__(16) float As[GB_K][GB_M + 4];
+  __shared__ __align__(16) float Bs[GB_K][GB_N];
+  const int m_eff = epi.m_dev ? min(M, *epi.m_dev) : M;
+  const int row0 = blockIdx.x * GB_M, col0 = blockIdx.y * GB_N;
+  if (row0 >= m_eff) return;
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int a_row = tid >> 2, a_k = (tid & 3) * 4;
+  const int b_k = tid >> 4, b_n = (tid & 15) * 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += GB_K) {
+    {  // A tile (K % 4 == 0 and lda % 4 == 0 are checked by the launcher)
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      const int r = row0 + a_row, k = k0 + a_k;
+      if (r < m_eff && k < K) {
+        const TA* src = A + (long long)r * lda + k;
+        if constexpr (sizeof(TA) == 4) {
+          float4 t = *reinterpret_cast<const float4*>(src);
+          v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        } else {
+          uint2 t = *reinterpret_cast<const uint2*>(src);
+          __nv_bfloat162 lo = *reinterpret_cast<__nv_bfloat162*>(&t.x), hi = *reinterpret_cast<__nv_bfloat162*>(&t.y);
+          v[0] = __low2float(lo); v[1] = __high2float(lo); v[2] = __low2float(hi); v[3] = __high2float(hi);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) As[a_k + i][a_row] = v[i];
+    }
+    {  // W tile
+      const int k = k0 + b_k;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int n = col0 + b_n + i;
+        Bs[b_k][b_n + i] = (k < K && n < N) ? W[(long long)k * N + n] : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GB_K; ++kk) {
+      float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = row0 + ty * 4 + i;
+    if (r >= m_eff) continue;
+    const EpiRow er = epi_row(epi, r);
+    if (er.crow < 0) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = col0 + tx * 4 + j;
+      if (c < N) store_out(C + er.crow * ldc + c, epi_value(epi, er, acc[i][j], c, N));
+    }
+  }
+}
+
+cudaError_t launch_gemm_simt(const void* A, int a_bf16, long long lda, const float* W, int M, int N, int K,
+                             const Epilogue& epi, void* C, int c_bf16, long long ldc, cudaStream_t st) {
+  if (M == 0) return cudaSuccess;
+  if ((K % 4) || (lda % 4)) return cudaErrorInvalidValue;
+  dim3 grid((M + GB_M - 1) / GB_M, (N + GB_N - 1) / GB_N);
+  if (a_bf16) {
+    if (c_bf16) k_gemm_simt<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)A, lda, W, M, N, K, epi, (bf16*)C, ldc);
+    else k_gemm_simt<bf16, float><<<grid, 256, 0, st>>>((const bf16*)A, lda, W, M, N, K, epi, (float*)C, ldc);
+  } else {
+    if (c_bf16) k_gemm_simt<float, bf16><<<grid, 256, 0, st>>>((const float*)A, lda, W, M, N, K, epi, (bf16*)C, ldc);
+    else k_gemm_simt<float, float><<<grid, 256, 0, st>>>((const float*)A, lda, W, M, N, K, epi, (float*)C, ldc);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace uu

@@ -1,0 +1,682 @@
+// C ABI of the uu3d library (include/uu3d.h): model object, weight inventory, forward schedule.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/uu3d.h"
+#include "common.cuh"
+
+namespace uu {
+
+static thread_local std::string g_error;
+void set_error(const std::string& msg) { g_error = msg; }
+
+// ------------------------------------------------------------------------------------------------
+struct TensorInfo {
+  std::string group;
+  int index;
+  std::vector<int64_t> shape;
+  size_t offset;   // into the flat fp32 parameter buffer (elements)
+  size_t numel;
+};
+
+struct Pack {          // bf16 W^T [n_pad, k] of a (k, n) fp32 matrix
+  bf16* ptr = nullptr;
+  int n = 0, n_pad = 0, k = 0;
+};
+
+struct BlockW {        // one temporal / strided block
+  const float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+  float* wqkv = nullptr;   // fused fp32 [d, 3d]
+  float* bqkv = nullptr;   // [3d]
+  // w2: fc2 (h, d) or strided conv (3, h, d) == [3h, d]
+  const float *wp = nullptr, *bp = nullptr, *w1 = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr;
+  Pack p_qkv, p_proj, p_fc1, p_fc2;
+};
+
+}  // namespace uu
+
+using namespace uu;
+
+struct uu_model {
+  uu_spec spec;
+  int device = 0;
+  int precision = UU_PRECISION_FP32;
+  std::vector<TensorInfo> tensors;
+  std::map<std::pair<std::string, int>, int> lookup;
+  std::vector<int> seq_lens;
+  float* params = nullptr;
+  size_t n_params = 0;
+  bool dirty = true;
+
+  // derived weights
+  std::vector<BlockW> tblocks, sblocks;
+  const float** spatial_ptrs = nullptr;    // device array [depth][16]
+  Pack p_s2t, p_head1, p_head2;
+  std::vector<void*> derived_allocs;
+
+  // workspace (sized for cap_B windows in the current precision)
+  int cap_B = 0;
+  int ws_precision = -1;
+  int *g_scratch = nullptr, *g_list = nullptr, *g_count = nullptr;
+  void *S = nullptr, *Y = nullptr, *QKV = nullptr, *O = nullptr, *Hd = nullptr;
+  float* X = nullptr;
+  std::vector<float*> Xs;      // strided stream after block i: [cap_B * seq_lens[i+1], d]
+  std::vector<void*> Hp;       // zero-padded conv inputs: [cap_B * Lo*s, h]
+  std::vector<void*> ws_allocs;
+  // device staging for uu_forward_host
+  float *d_x = nullptr, *d_full = nullptr, *d_central = nullptr;
+  uint8_t* d_mask = nullptr;
+  int stage_B = 0;
+  cudaStream_t own_stream = nullptr;
+
+  // tcgen05 plans for the current batch size
+  int plan_B = -1;
+  int plan_full = -1;
+  std::vector<TcGemmPlan*> plans;
+  int launches = 0;
+};
+
+namespace uu {
+
+static const float* W(const uu_model* m, const std::string& g, int i) {
+  auto it = m->lookup.find({g, i});
+  return it == m->lookup.end() ? nullptr : m->params + m->tensors[it->second].offset;
+}
+
+static void add_tensor(uu_model* m, const std::string& g, int idx, std::vector<int64_t> shape) {
+  TensorInfo t;
+  t.group = g; t.index = idx; t.shape = shape; t.offset = m->n_params;
+  t.numel = 1;
+  for (auto s : shape) t.numel *= (size_t)s;
+  m->n_params += t.numel;
+  m->lookup[{g, idx}] = (int)m->tensors.size();
+  m->tensors.push_back(t);
+}
+
+static void add_block(uu_model* m, const std::string& g, int64_t d, int64_t h, bool strided) {
+  int i = 0;
+  add_tensor(m, g, i++, {d}); add_tensor(m, g, i++, {d});                 // norm1 gamma, beta
+  for (int k = 0; k < 4; ++k) { add_tensor(m, g, i++, {d, d}); add_tensor(m, g, i++, {d}); }   // wq wk wv proj
+  add_tensor(m, g, i++, {d}); add_tensor(m, g, i++, {d});                 // norm2
+  if (strided) {
+    add_tensor(m, g, i++, {1, d, h}); add_tensor(m, g, i++, {h});         // Conv1D k=1
+    add_tensor(m, g, i++, {3, h, d}); add_tensor(m, g, i++, {d});         // strided Conv1D k=3
+  } else {
+    add_tensor(m, g, i++, {d, h}); add_tensor(m, g, i++, {h});
+    add_tensor(m, g, i++, {h, d}); add_tensor(m, g, i++, {d});
+  }
+}
+
+// Keras .h5 order (weight_io.py:155-198)
+static void build_inventory(uu_model* m) {
+  const uu_spec& s = m->spec;
+  const int64_t J = s.n_joints, ds = s.d_spatial, dt = s.d_temporal;
+  add_tensor(m, "keypoint_embedding", 0, {2, ds});
+  add_tensor(m, "keypoint_embedding", 1, {ds});
+  add_tensor(m, "spatial_pe", 0, {J, ds});
+  add_tensor(m, "temporal_pe", 0, {s.n_tok, dt});
+  for (int i = 0; i < s.n_strided; ++i)
+    add_tensor(m, "strided_temporal_pe_" + std::to_string(i + 1), 0, {m->seq_lens[i], dt});
+  if (s.has_strided_input) add_tensor(m, "strided_input_token_layer", 0, {dt});
+  for (int i = 0; i < s.spatial_depth; ++i) add_block(m, "spatial_block_" + std::to_string(i + 1), ds, s.h_spatial, false);
+  add_tensor(m, "spatial_norm", 0, {ds});
+  add_tensor(m, "spatial_norm", 1, {ds});
+  add_tensor(m, "spatial_to_temporal_fc", 0, {J * ds, dt});
+  add_tensor(m, "spatial_to_temporal_fc", 1, {dt});
+  for (int i = 0; i < s.temporal_depth; ++i) add_block(m, "temporal_block_" + std::to_string(i + 1), dt, s.h_temporal, false);
+  for (int i = 0; i < s.n_strided; ++i) add_block(m, "strided_temporal_block_" + std::to_string(i + 1), dt, s.h_temporal, true);
+  if (s.full_output) {
+    add_tensor(m, "temporal_fc", 0, {dt, 3 * J});
+    add_tensor(m, "temporal_fc", 1, {3 * J});
+  }
+  add_tensor(m, "strided_temporal_fc", 0, {dt, 3 * J});
+  add_tensor(m, "strided_temporal_fc", 1, {3 * J});
+}
+
+// ---- small device helpers -----------------------------------------------------------------------
+__global__ void k_concat_cols(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
+                              int rows, int d, float* __restrict__ out) {
+  // out[r][0:d]=a[r], [d:2d]=b[r], [2d:3d]=c[r]
+  long long n = (long long)rows * 3 * d;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int r = (int)(i / (3 * d)), col = (int)(i % (3 * d));
+    const float* src = col < d ? a : (col < 2 * d ? b : c);
+    out[i] = src[(long long)r * d + (col % d)];
+  }
+}
+// Wt[n][k] = bf16(W[k][n]) for n < N, zero rows up to n_pad
+__global__ void k_pack_wt(const float* __restrict__ Wm, int K, int N, int n_pad, bf16* __restrict__ Wt) {
+  long long total = (long long)n_pad * K;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int n = (int)(i / K), k = (int)(i % K);
+    Wt[i] = __float2bfloat16_rn(n < N ? Wm[(long long)k * N + n] : 0.f);
+  }
+}
+
+static int dev_alloc(std::vector<void*>& pool, void** p, size_t bytes, bool zero) {
+  UU_CUDA(cudaMalloc(p, bytes ? bytes : 16));
+  pool.push_back(*p);
+  if (zero) UU_CUDA(cudaMemset(*p, 0, bytes ? bytes : 16));
+  return 0;
+}
+
+static int make_pack(uu_model* m, Pack& pk, const float* Wsrc, int K, int N) {
+  pk.k = K; pk.n = N; pk.n_pad = (N + 63) / 64 * 64;
+  if (!pk.ptr) {
+    void* p;
+    if (dev_alloc(m->derived_allocs, &p, sizeof(bf16) * (size_t)pk.n_pad * K, false)) return 1;
+    pk.ptr = (bf16*)p;
+  }
+  k_pack_wt<<<256, 256>>>(Wsrc, K, N, pk.n_pad, pk.ptr);
+  UU_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int setup_block(uu_model* m, BlockW& b, const std::string& g, int d, int h, bool strided) {
+  b.ln1_g = W(m, g, 0); b.ln1_b = W(m, g, 1);
+  b.wp = W(m, g, 8); b.bp = W(m, g, 9);
+  b.ln2_g = W(m, g, 10); b.ln2_b = W(m, g, 11);
+  b.w1 = W(m, g, 12); b.b1 = W(m, g, 13); b.w2 = W(m, g, 14); b.b2 = W(m, g, 15);
+  if (!b.wqkv) {
+    void* p;
+    if (dev_alloc(m->derived_allocs, &p, sizeof(float) * (size_t)d * 3 * d, false)) return 1;
+    b.wqkv = (float*)p;
+    if (dev_alloc(m->derived_allocs, &p, sizeof(float) * 3 * d, false)) return 1;
+    b.bqkv = (float*)p;
+  }
+  k_concat_cols<<<256, 256>>>(W(m, g, 2), W(m, g, 4), W(m, g, 6), d, d, b.wqkv);
+  k_concat_cols<<<1, 256>>>(W(m, g, 3), W(m, g, 5), W(m, g, 7), 1, d, b.bqkv);
+  UU_CUDA(cudaGetLastError());
+  if (make_pack(m, b.p_qkv, b.wqkv, d, 3 * d)) return 1;
+  if (make_pack(m, b.p_proj, b.wp, d, d)) return 1;
+  if (make_pack(m, b.p_fc1, b.w1, d, h)) return 1;
+  if (make_pack(m, b.p_fc2, b.w2, strided ? 3 * h : h, d)) return 1;
+  return 0;
+}
+
+// (Re)derive fused / packed weights after uu_set_weight.
+static int commit_weights(uu_model* m) {
+  if (!m->dirty) return 0;
+  const uu_spec& s = m->spec;
+  UU_CUDA(cudaSetDevice(m->device));
+  if (!m->spatial_ptrs) {
+    void* p;
+    if (dev_alloc(m->derived_allocs, &p, sizeof(float*) * 16 * s.spatial_depth, false)) return 1;
+    m->spatial_ptrs = (const float**)p;
+    std::vector<const float*> h(16 * s.spatial_depth);
+    for (int l = 0; l < s.spatial_depth; ++l)
+      for (int i = 0; i < 16; ++i) h[l * 16 + i] = W(m, "spatial_block_" + std::to_string(l + 1), i);
+    UU_CUDA(cudaMemcpy(p, h.data(), sizeof(float*) * h.size(), cudaMemcpyHostToDevice));
+  }
+  m->tblocks.resize(s.temporal_depth);
+  m->sblocks.resize(s.n_strided);
+  for (int i = 0; i < s.temporal_depth; ++i)
+    if (setup_block(m, m->tblocks[i], "temporal_block_" + std::to_string(i + 1), s.d_temporal, s.h_temporal, false)) return 1;
+  for (int i = 0; i < s.n_strided; ++i)
+    if (setup_block(m, m->sblocks[i], "strided_temporal_block_" + std::to_string(i + 1), s.d_temporal, s.h_temporal, true)) return 1;
+  if (make_pack(m, m->p_s2t, W(m, "spatial_to_temporal_fc", 0), s.n_joints * s.d_spatial, s.d_temporal)) return 1;
+  if (s.full_output && make_pack(m, m->p_head1, W(m, "temporal_fc", 0), s.d_temporal, 3 * s.n_joints)) return 1;
+  if (make_pack(m, m->p_head2, W(m, "strided_temporal_fc", 0), s.d_temporal, 3 * s.n_joints)) return 1;
+  UU_CUDA(cudaDeviceSynchronize());
+  m->dirty = false;
+  return 0;
+}
+
+static void free_pool(std::vector<void*>& pool) {
+  for (void* p : pool) cudaFree(p);
+  pool.clear();
+}
+
+static void drop_plans(uu_model* m) {
+  for (auto* p : m->plans) tc_gemm_plan_destroy(p);
+  m->plans.clear();
+  m->plan_B = -1;
+}
+
+static int ensure_workspace(uu_model* m, int B) {
+  if (B <= m->cap_B && m->ws_precision == m->precision) return 0;
+  const uu_spec& s = m->spec;
+  UU_CUDA(cudaDeviceSynchronize());
+  free_pool(m->ws_allocs);
+  drop_plans(m);
+  m->Xs.clear(); m->Hp.clear();
+  const int cap = std::max(B, m->cap_B);
+  const size_t R = (size_t)cap * s.n_tok;
+  const size_t es = m->precision == UU_PRECISION_BF16 ? 2 : 4;
+  const size_t dt = s.d_temporal, ht = s.h_temporal;
+  void* p;
+  if (dev_alloc(m->ws_allocs, &p, sizeof(int) * (cap + 1), true)) return 1; m->g_scratch = (int*)p;
+  if (dev_alloc(m->ws_allocs, &p, sizeof(int) * R, true)) return 1; m->g_list = (int*)p;
+  if (dev_alloc(m->ws_allocs, &p, sizeof(int) * 4, true)) return 1; m->g_count = (int*)p;
+  if (dev_alloc(m->ws_allocs, &m->S, es * R * s.n_joints * s.d_spatial, true)) return 1;
+  if (dev_alloc(m->ws_allocs, &p, 4 * R * dt, true)) return 1; m->X = (float*)p;
+  if (dev_alloc(m->ws_allocs, &m->Y, es * R * dt, true)) return 1;
+  if (dev_alloc(m->ws_allocs, &m->QKV, es * R * 3 * dt, true)) return 1;
+  if (dev_alloc(m->ws_allocs, &m->O, es * R * dt, true)) return 1;
+  if (dev_alloc(m->ws_allocs, &m->Hd, es * R * ht, true)) return 1;
+  for (int i = 0; i < s.n_strided; ++i) {
+    const size_t Lo = m->seq_lens[i + 1];
+    if (dev_alloc(m->ws_allocs, &p, 4 * (size_t)cap * Lo * dt, true)) return 1;
+    m->Xs.push_back((float*)p);
+    if (dev_alloc(m->ws_allocs, &p, es * (size_t)cap * Lo * s.strides[i] * ht, true)) return 1;   // pad rows stay zero
+    m->Hp.push_back(p);
+  }
+  m->cap_B = cap;
+  m->ws_precision = m->precision;
+  return 0;
+}
+
+// ---- forward schedule ---------------------------------------------------------------------------
+struct Fwd {
+  uu_model* m;
+  cudaStream_t st;
+  int B;
+  bool tc;             // tcgen05 GEMMs (bf16 activations) or CUDA-core fp32
+  bool building;       // first run at this batch size: create TMA plans
+  size_t plan_i = 0;
+  int launches = 0;
+};
+
+// One GEMM call site. A: activations in the workspace dtype; Wf: fp32 (K, N); pk: bf16 W^T.
+static int gemm(Fwd& f, const void* A, long long lda, int M, int K, const float* Wf, const Pack& pk, int N,
+                const Epilogue& epi, void* C, int c_bf16, long long ldc) {
+  if (M == 0) return 0;
+  if (f.tc) {
+    if (f.building) {
+      TcGemmPlan* p = nullptr;
+      if (tc_gemm_plan_create(&p, (const bf16*)A, lda, M, K, pk.ptr, pk.n_pad, N)) return 1;
+      f.m->plans.push_back(p);
+    }
+    UU_CHECK(f.plan_i < f.m->plans.size(), "internal: GEMM plan list out of sync");
+    UU_CUDA(tc_gemm_launch(f.m->plans[f.plan_i++], epi, C, c_bf16, ldc, f.st));
+  } else {
+    UU_CUDA(launch_gemm_simt(A, 0, lda, Wf, M, N, K, epi, C, c_bf16, ldc, f.st));
+  }
+  f.launches++;
+  return 0;
+}
+
+static int attention_block(Fwd& f, const BlockW& w, float* x, int L, const uint8_t* keymask) {
+  // x += Proj(MHA(LN1(x)))   (vit:183-188 / net:129-133); LN1 is done by the caller (it may fuse the PE add)
+  uu_model* m = f.m;
+  const uu_spec& s = m->spec;
+  const int d = s.d_temporal, R = f.B * L, bf = f.tc ? 1 : 0;
+  Epilogue e;
+  e.bias = w.bqkv;
+  if (gemm(f, m->Y, d, R, d, w.wqkv, w.p_qkv, 3 * d, e, m->QKV, bf, 3 * d)) return 1;
+  UU_CUDA(launch_attention(m->QKV, bf, f.B, L, s.num_heads, d / s.num_heads, keymask, s.n_tok, m->O, f.st));
+  f.launches++;
+  Epilogue ep;
+  ep.bias = w.bp; ep.flags = EPI_RESIDUAL; ep.res = x; ep.ldr = d;
+  if (gemm(f, m->O, d, R, d, w.wp, w.p_proj, d, ep, x, 0, d)) return 1;
+  return 0;
+}
+
+static int run_forward(uu_model* m, const float* x2d, const uint8_t* mask, int B, float* full, float* central,
+                       cudaStream_t st) {
+  const uu_spec& s = m->spec;
+  UU_CHECK(B > 0, "batch must be positive");
+  UU_CHECK(x2d && central, "x2d and central must not be null");
+  UU_CHECK(!s.has_strided_input || mask, "this model has strided input: a stride mask is required");
+  UU_CUDA(cudaSetDevice(m->device));
+  if (commit_weights(m)) return 1;
+  if (ensure_workspace(m, B)) return 1;
+  Fwd f;
+  f.m = m; f.st = st; f.B = B; f.tc = m->precision == UU_PRECISION_BF16;
+  const int want_full = (s.full_output && full) ? 1 : 0;
+  if (f.tc && (m->plan_B != B || m->plan_full != want_full)) drop_plans(m);
+  f.building = f.tc && m->plans.empty();
+  const int bf = f.tc ? 1 : 0;
+  const int N = s.n_tok, J = s.n_joints, ds = s.d_spatial, d = s.d_temporal, h = s.h_temporal;
+  const int R = B * N;
+  const bool use_mask = s.has_strided_input != 0;
+
+  // K1a: gather list of frames that carry a 2-D pose
+  if (use_mask) {
+    UU_CUDA(launch_build_gather(mask, B, N, m->g_scratch, m->g_list, m->g_count, st));
+    f.launches += 3;
+  }
+  // K2: fused spatial transformer on the valid frames -> S (compact rows)
+  SpatialParams sp;
+  sp.x2d = x2d; sp.list = use_mask ? m->g_list : nullptr; sp.count = use_mask ? m->g_count : nullptr;
+  sp.max_frames = R; sp.J = J; sp.depth = s.spatial_depth;
+  sp.embed_k = W(m, "keypoint_embedding", 0); sp.embed_b = W(m, "keypoint_embedding", 1);
+  sp.pe = W(m, "spatial_pe", 0); sp.blocks = m->spatial_ptrs;
+  sp.norm_g = W(m, "spatial_norm", 0); sp.norm_b = W(m, "spatial_norm", 1);
+  sp.out = m->S; sp.out_bf16 = bf;
+  UU_CUDA(launch_spatial_f32(sp, st));
+  f.launches++;
+  // S4 + T1: 544->384 GEMM, rows scattered to their token position, + bias + temporal PE
+  {
+    Epilogue e;
+    e.bias = W(m, "spatial_to_temporal_fc", 1);
+    e.flags = EPI_ROWTABLE; e.table = W(m, "temporal_pe", 0); e.table_period = N;
+    if (use_mask) { e.c_rowidx = m->g_list; e.m_dev = m->g_count; }
+    if (gemm(f, m->S, J * ds, R, J * ds, W(m, "spatial_to_temporal_fc", 0), m->p_s2t, d, e, m->X, 0, d)) return 1;
+    if (use_mask) {
+      UU_CUDA(launch_token_fill(mask, R, N, d, W(m, "strided_input_token_layer", 0), W(m, "temporal_pe", 0), m->X, st));
+      f.launches++;
+    }
+  }
+  // T2/T3: temporal transformer blocks (ReLU MLP)
+  for (int i = 0; i < s.temporal_depth; ++i) {
+    const BlockW& w = m->tblocks[i];
+    UU_CUDA(launch_layernorm(m->X, R, d, w.ln1_g, w.ln1_b, 1e-5f, nullptr, 1, m->Y, bf, st));
+    f.launches++;
+    const uint8_t* km = (use_mask && i < s.first_strided_token_attention_layer) ? mask : nullptr;
+    if (attention_block(f, w, m->X, N, km)) return 1;
+    UU_CUDA(launch_layernorm(m->X, R, d, w.ln2_g, w.ln2_b, 1e-5f, nullptr, 1, m->Y, bf, st));
+    f.launches++;
+    Epilogue e1;
+    e1.bias = w.b1; e1.flags = EPI_RELU;
+    if (gemm(f, m->Y, d, R, d, w.w1, w.p_fc1, h, e1, m->Hd, bf, h)) return 1;
+    Epilogue e2;
+    e2.bias = w.b2; e2.flags = EPI_RESIDUAL; e2.res = m->X; e2.ldr = d;
+    if (gemm(f, m->Hd, h, R, h, w.w2, w.p_fc2, d, e2, m->X, 0, d)) return 1;
+  }
+  // T4: full-sequence head (before the strided blocks modify X in place)
+  if (s.full_output && full) {
+    Epilogue e;
+    e.bias = W(m, "temporal_fc", 1);
+    const void* A = m->X;
+    if (f.tc) {   // the tensor-core GEMM wants a bf16 operand: cast the fp32 residual stream into Y
+      UU_CUDA(launch_cast_bf16(m->X, (bf16*)m->Y, (long long)R * d, st));
+      f.launches++;
+      A = m->Y;
+    }
+    if (gemm(f, A, d, R, d, W(m, "temporal_fc", 0), m->p_head1, 3 * J, e, full, 0, 3 * J)) return 1;
+  }
+  // Q1/Q2: strided transformer blocks (net:122-160)
+  float* x_in = m->X;
+  for (int i = 0; i < s.n_strided; ++i) {
+    const BlockW& w = m->sblocks[i];
+    const int L = m->seq_lens[i], Lo = m->seq_lens[i + 1], st_i = s.strides[i];
+    const int pl = s.pad_left[i], pr = s.pad_right[i];
+    const int Rl = B * L;
+    // x += PE_i (written back), y = LN1(x)
+    UU_CUDA(launch_layernorm(x_in, Rl, d, w.ln1_g, w.ln1_b, 1e-5f,
+                             W(m, "strided_temporal_pe_" + std::to_string(i + 1), 0), L, m->Y, bf, st));
+    f.launches++;
+    if (attention_block(f, w, x_in, L, nullptr)) return 1;
+    UU_CUDA(launch_layernorm(x_in, Rl, d, w.ln2_g, w.ln2_b, 1e-5f, nullptr, 1, m->Y, bf, st));
+    f.launches++;
+    // Conv1D k=1 + ReLU, written into the zero-padded layout [B, Lo*s, h] (rows never read by the
+    // strided conv are dropped; pad rows stay zero from allocation)
+    Epilogue e1;
+    e1.bias = w.b1; e1.flags = EPI_RELU;
+    e1.cmap.rpb = L; e1.cmap.batch_rows = Lo * st_i; e1.cmap.offset = pl; e1.cmap.step = 1;
+    if (gemm(f, m->Y, d, Rl, d, w.w1, w.p_fc1, h, e1, m->Hp[i], bf, h)) return 1;
+    // strided Conv1D k=3 as an implicit GEMM: row (b,t) = Hp[b, t*s : t*s+3, :] is contiguous (3h values),
+    // consecutive rows are s*h apart.  Residual = x[b, c0 + t*s] (MaxPool1D(pool 1, stride s) of the trimmed x).
+    Epilogue e2;
+    e2.bias = w.b2; e2.flags = EPI_RESIDUAL; e2.res = x_in; e2.ldr = d;
+    e2.rmap.rpb = Lo; e2.rmap.batch_rows = L;
+    e2.rmap.offset = (st_i > 1 && pl == 0) ? 1 : 0; e2.rmap.step = st_i;
+    (void)pr;
+    if (gemm(f, m->Hp[i], (long long)st_i * h, B * Lo, 3 * h, w.w2, w.p_fc2, d, e2, m->Xs[i], 0, d)) return 1;
+    x_in = m->Xs[i];
+  }
+  // Q3: central-frame head on the single remaining token
+  {
+    Epilogue e;
+    e.bias = W(m, "strided_temporal_fc", 1);
+    const void* A = x_in;
+    if (f.tc) {
+      UU_CUDA(launch_cast_bf16(x_in, (bf16*)m->Y, (long long)B * d, st));
+      f.launches++;
+      A = m->Y;
+    }
+    if (gemm(f, A, d, B, d, W(m, "strided_temporal_fc", 0), m->p_head2, 3 * J, e, central, 0, 3 * J)) return 1;
+  }
+  if (f.tc) { m->plan_B = B; m->plan_full = want_full; }
+  m->launches = f.launches;
+  return 0;
+}
+
+static int check_spec(const uu_spec& s, std::vector<int>& lens) {
+  UU_CHECK(s.n_tok >= 1 && s.n_tok <= 128, "n_tok must be in [1,128] (attention keeps a whole window on one SM)");
+  UU_CHECK(s.n_joints == 17, "the fused spatial kernel is built for NUM_KEYPOINTS == 17");
+  UU_CHECK(s.d_spatial == 32 && s.h_spatial == 64 && s.num_heads == 8,
+           "the fused spatial kernel is built for SPATIAL_EMBED_DIM 32, MLP_RATIO 2, NUM_HEADS 8");
+  UU_CHECK(s.d_temporal % 128 == 0 && s.d_temporal <= 1024, "TEMPORAL_EMBED_DIM must be a multiple of 128, <= 1024");
+  UU_CHECK(s.d_temporal % s.num_heads == 0, "TEMPORAL_EMBED_DIM must be divisible by NUM_HEADS");
+  const int dh = s.d_temporal / s.num_heads;
+  UU_CHECK(dh == 16 || dh == 32 || dh == 48 || dh == 64, "temporal head_dim must be 16, 32, 48 or 64");
+  UU_CHECK(s.h_temporal % 64 == 0, "temporal MLP width must be a multiple of 64");
+  UU_CHECK(s.spatial_depth >= 1 && s.temporal_depth >= 1, "depths must be >= 1");
+  UU_CHECK(s.n_strided >= 1 && s.n_strided <= UU_MAX_STRIDED, "1..8 strided blocks");
+  lens.clear();
+  lens.push_back(s.n_tok);
+  int L = s.n_tok;
+  for (int i = 0; i < s.n_strided; ++i) {
+    const int st = s.strides[i], pl = s.pad_left[i], pr = s.pad_right[i];
+    UU_CHECK(st >= 1 && pl >= 0 && pr >= 0, "bad stride / padding");
+    const int Lp = L + pl + pr;
+    UU_CHECK(Lp >= 3, "sequence too short for the k=3 strided conv");
+    const int Lo = (Lp - 3) / st + 1;
+    UU_CHECK(Lo == (L + pl + pr - 2 + st - 1) / st, "strided PE length (net:216) disagrees with the conv output length");
+    // identity path length (net:137-152) must equal the conv output length
+    int Lt = L;
+    if (st > 1) {
+      if (pl == 0) Lt -= 1;
+      if (pr == 0) Lt -= 1;
+      UU_CHECK((Lt - 1) / st + 1 == Lo, "identity path and strided conv lengths differ (the reference would fail too)");
+    } else {
+      UU_CHECK(L == Lo, "stride 1 needs paddings [1,1]");
+    }
+    UU_CHECK(st >= 3, "strides < 3 (overlapping conv windows) are not supported by the implicit-GEMM layout");
+    lens.push_back(Lo);
+    L = Lo;
+  }
+  UU_CHECK(L == 1, "the strided blocks must reduce the sequence to a single token");
+  return 0;
+}
+
+}  // namespace uu
+
+// =================================================================================================
+// extern "C"
+// =================================================================================================
+extern "C" {
+
+const char* uu_last_error(void) { return g_error.c_str(); }
+int uu_version(void) { return 100; }
+
+int uu_create(const uu_spec* spec, int device, uu_model** out) {
+  UU_CHECK(spec && out, "null argument");
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0) {
+    set_error("no CUDA device available: uu3d has no CPU fallback");
+    return 1;
+  }
+  UU_CHECK(device >= 0 && device < n_dev, "device index out of range");
+  std::vector<int> lens;
+  if (check_spec(*spec, lens)) return 1;
+  UU_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  UU_CUDA(cudaGetDeviceProperties(&prop, device));
+  UU_CHECK(prop.major == 10, "uu3d is built for sm_100a (B200) only");
+  uu_model* m = new uu_model();
+  m->spec = *spec;
+  m->device = device;
+  m->seq_lens = lens;
+  build_inventory(m);
+  if (cudaMalloc(&m->params, sizeof(float) * m->n_params) != cudaSuccess ||
+      cudaMemset(m->params, 0, sizeof(float) * m->n_params) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    set_error("device allocation failed in uu_create");
+    delete m;
+    return 1;
+  }
+  *out = m;
+  return 0;
+}
+
+int uu_destroy(uu_model* m) {
+  if (!m) return 0;
+  cudaSetDevice(m->device);
+  cudaDeviceSynchronize();
+  drop_plans(m);
+  free_pool(m->ws_allocs);
+  free_pool(m->derived_allocs);
+  cudaFree(m->params);
+  cudaFree(m->d_x);
+  cudaFree(m->d_mask);
+  cudaFree(m->d_full);
+  cudaFree(m->d_central);
+  if (m->own_stream) cudaStreamDestroy(m->own_stream);
+  delete m;
+  return 0;
+}
+
+int uu_set_precision(uu_model* m, int precision) {
+  UU_CHECK(m, "null model");
+  UU_CHECK(precision == UU_PRECISION_FP32 || precision == UU_PRECISION_BF16, "unknown precision");
+  m->precision = precision;
+  return 0;
+}
+int uu_get_precision(const uu_model* m) { return m ? m->precision : -1; }
+
+int uu_weight_count(const uu_model* m) { return m ? (int)m->tensors.size() : -1; }
+int64_t uu_param_count(const uu_model* m) { return m ? (int64_t)m->n_params : -1; }
+
+int uu_weight_info(const uu_model* m, int i, char* group, int group_cap, int* index_in_group, int64_t shape[4],
+                   int* rank) {
+  UU_CHECK(m && i >= 0 && i < (int)m->tensors.size(), "weight index out of range");
+  const TensorInfo& t = m->tensors[i];
+  if (group && group_cap > 0) {
+    std::strncpy(group, t.group.c_str(), group_cap - 1);
+    group[group_cap - 1] = 0;
+  }
+  if (index_in_group) *index_in_group = t.index;
+  if (rank) *rank = (int)t.shape.size();
+  if (shape) for (size_t k = 0; k < 4; ++k) shape[k] = k < t.shape.size() ? t.shape[k] : 1;
+  return 0;
+}
+
+static const TensorInfo* find_tensor(uu_model* m, const char* group, int index) {
+  auto it = m->lookup.find({std::string(group), index});
+  if (it == m->lookup.end()) {
+    set_error(std::string("no weight ") + group + "[" + std::to_string(index) + "] in this model");
+    return nullptr;
+  }
+  return &m->tensors[it->second];
+}
+
+int uu_set_weight(uu_model* m, const char* group, int index, const float* host, const int64_t* shape, int rank) {
+  UU_CHECK(m && group && host && shape, "null argument");
+  const TensorInfo* t = find_tensor(m, group, index);
+  if (!t) return 1;
+  bool ok = rank == (int)t->shape.size();
+  for (int k = 0; ok && k < rank; ++k) ok = shape[k] == t->shape[k];
+  if (!ok) {   // weight_io.py:219-232 raises ValueError on a shape mismatch
+    set_error(std::string("shape mismatch for ") + group + "[" + std::to_string(index) + "]");
+    return 1;
+  }
+  UU_CUDA(cudaSetDevice(m->device));
+  UU_CUDA(cudaMemcpy(m->params + t->offset, host, sizeof(float) * t->numel, cudaMemcpyHostToDevice));
+  m->dirty = true;
+  return 0;
+}
+
+int uu_get_weight(uu_model* m, const char* group, int index, float* host, int64_t capacity) {
+  UU_CHECK(m && group && host, "null argument");
+  const TensorInfo* t = find_tensor(m, group, index);
+  if (!t) return 1;
+  UU_CHECK((int64_t)t->numel <= capacity, "output buffer too small");
+  UU_CUDA(cudaSetDevice(m->device));
+  UU_CUDA(cudaMemcpy(host, m->params + t->offset, sizeof(float) * t->numel, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int uu_forward(uu_model* m, const float* x2d, const uint8_t* mask, int B, float* full, float* central, void* stream) {
+  UU_CHECK(m, "null model");
+  return run_forward(m, x2d, mask, B, full, central, (cudaStream_t)stream);
+}
+
+int uu_forward_host(uu_model* m, const float* x2d, const uint8_t* mask, int B, float* full, float* central) {
+  UU_CHECK(m && x2d && central, "null argument");
+  const uu_spec& s = m->spec;
+  UU_CUDA(cudaSetDevice(m->device));
+  if (B > m->stage_B) {
+    UU_CUDA(cudaDeviceSynchronize());
+    cudaFree(m->d_x); cudaFree(m->d_mask); cudaFree(m->d_full); cudaFree(m->d_central);
+    m->d_x = m->d_full = m->d_central = nullptr; m->d_mask = nullptr;
+    const size_t R = (size_t)B * s.n_tok;
+    UU_CUDA(cudaMalloc(&m->d_x, sizeof(float) * R * s.n_joints * 2));
+    UU_CUDA(cudaMalloc(&m->d_mask, R));
+    UU_CUDA(cudaMalloc(&m->d_full, sizeof(float) * R * s.n_joints * 3));
+    UU_CUDA(cudaMalloc(&m->d_central, sizeof(float) * (size_t)B * s.n_joints * 3));
+    m->stage_B = B;
+  }
+  const size_t R = (size_t)B * s.n_tok;
+  cudaStream_t st = m->own_stream;
+  UU_CUDA(cudaMemcpyAsync(m->d_x, x2d, sizeof(float) * R * s.n_joints * 2, cudaMemcpyHostToDevice, st));
+  if (mask) UU_CUDA(cudaMemcpyAsync(m->d_mask, mask, R, cudaMemcpyHostToDevice, st));
+  if (run_forward(m, m->d_x, mask ? m->d_mask : nullptr, B, full ? m->d_full : nullptr, m->d_central, st)) return 1;
+  if (full) UU_CUDA(cudaMemcpyAsync(full, m->d_full, sizeof(float) * R * s.n_joints * 3, cudaMemcpyDeviceToHost, st));
+  UU_CUDA(cudaMemcpyAsync(central, m->d_central, sizeof(float) * (size_t)B * s.n_joints * 3, cudaMemcpyDeviceToHost, st));
+  UU_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int uu_last_launch_count(const uu_model* m) { return m ? m->launches : -1; }
+
+int uu_stride_mask(int n_tok, int s_out, int s_in, int64_t shift, uint8_t* mask_out) {
+  UU_CHECK(mask_out && n_tok > 0 && s_out > 0 && s_in > 0, "bad argument");
+  UU_CHECK(s_in >= s_out && s_in % s_out == 0, "MASK_STRIDE must be a multiple of SEQUENCE_STRIDE");   // :252-254
+  for (int n = 0; n < n_tok; ++n) {
+    int64_t idx = (int64_t)(n - n_tok / 2) * s_out + shift;
+    int64_t r = idx % s_in;
+    if (r < 0) r += s_in;   // numpy floor-mod
+    mask_out[n] = r == 0;
+  }
+  return 0;
+}
+
+// ---- single-kernel entry points ------------------------------------------------------------------
+int uu_op_build_gather(const uint8_t* mask, int B, int n_tok, int32_t* scratch, int32_t* list, int32_t* count,
+                       void* stream) {
+  UU_CUDA(launch_build_gather(mask, B, n_tok, scratch, list, count, (cudaStream_t)stream));
+  return 0;
+}
+int uu_op_token_fill(const uint8_t* mask, int rows, int n_tok, int d, const float* token, const float* pe, float* x,
+                     void* stream) {
+  UU_CUDA(launch_token_fill(mask, rows, n_tok, d, token, pe, x, (cudaStream_t)stream));
+  return 0;
+}
+int uu_op_layernorm(float* x, int rows, int d, const float* gamma, const float* beta, float eps, const float* table,
+                    int period, void* y, int y_bf16, void* stream) {
+  UU_CUDA(launch_layernorm(x, rows, d, gamma, beta, eps, table, period, y, y_bf16, (cudaStream_t)stream));
+  return 0;
+}
+int uu_op_attention(const void* qkv, int is_bf16, int B, int S, int heads, int dh, const uint8_t* keep_mask,
+                    int mask_stride, void* out, void* stream) {
+  UU_CUDA(launch_attention(qkv, is_bf16, B, S, heads, dh, keep_mask, mask_stride, out, (cudaStream_t)stream));
+  return 0;
+}
+int uu_op_gemm_f32(const float* A, int64_t lda, const float* Wm, int M, int N, int K, const float* bias, int flags,
+                   const float* res, int64_t ldr, float* C, int64_t ldc, void* stream) {
+  Epilogue e;
+  e.bias = bias; e.flags = flags & (EPI_RELU | EPI_RESIDUAL); e.res = res; e.ldr = ldr;
+  UU_CUDA(launch_gemm_simt(A, 0, lda, Wm, M, N, K, e, C, 0, ldc, (cudaStream_t)stream));
+  return 0;
+}
+int uu_op_gemm_bf16(const void* A, int64_t lda, int M, int K, const void* Wt, int N_pad, int N, const float* bias,
+                    int flags, const float* res, int64_t ldr, void* C, int c_bf16, int64_t ldc, void* stream) {
+  Epilogue e;
+  e.bias = bias; e.flags = flags & (EPI_RELU | EPI_RESIDUAL); e.res = res; e.ldr = ldr;
+  TcGemmPlan* p = nullptr;
+  if (tc_gemm_plan_create(&p, (const bf16*)A, lda, M, K, (const bf16*)Wt, N_pad, N)) return 1;
+  cudaError_t err = tc_gemm_launch(p, e, C, c_bf16, ldc, (cudaStream_t)stream);
+  tc_gemm_plan_destroy(p);
+  UU_CUDA(err);
+  return 0;
+}
+
+}  // extern "C"
