@@ -8,7 +8,8 @@ pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 from oracle import forward_np as O
 from uplift_upsample_3dhpe_b200 import UpliftUpsampleConfig, spec_from_config, stride_mask, weights
-from uplift_upsample_3dhpe_b200.model import build_uplift_upsample_transformer, test_step
+from uplift_upsample_3dhpe_b200.model import build_uplift_upsample_transformer
+from uplift_upsample_3dhpe_b200.model import test_step as run_test_step
 
 # Tolerances (absolute, outputs are O(1..10) with the perturbed random-init weights):
 #   fp32 path: <= 1e-4 against the fp64 oracle (north_star's fp32 bound; the fp32 oracle itself sits ~1e-5 away)
@@ -46,9 +47,12 @@ def _case(name, s_in, B, mode, seed=0):
 ])
 def test_forward_matches_oracle(name, s_in, B, mode, precision):
     cfg, spec, w, x, m = _case(name, s_in, B, mode)
-    want_full, want_central = O.test_step(spec, w, x, m, dtype=np.float64)
+    # Windows without any valid token (global alignment, i % s_out != 0) are defined by the reference's
+    # fp32 arithmetic (x - 1e9 rounds to -1e9 => uniform attention, vit:122-123); fp64 would not round.
+    all_masked = bool((m.sum(axis=1) == 0).any())
+    want_full, want_central = O.test_step(spec, w, x, m, dtype=np.float32 if all_masked else np.float64)
     model = build_uplift_upsample_transformer(cfg, precision=precision, weights=w)
-    full, central = test_step(model, torch.from_numpy(x).cuda(), torch.from_numpy(m).cuda())
+    full, central = run_test_step(model, torch.from_numpy(x).cuda(), torch.from_numpy(m).cuda())
     torch.cuda.synchronize()
     e_f = np.abs(full.cpu().numpy() - want_full).max()
     e_c = np.abs(central.cpu().numpy() - want_central).max()
@@ -62,10 +66,10 @@ def test_masked_frame_values_are_never_read():
     cfg, spec, w, x, m = _case("h36m_351", 20, 6, "shifted")
     model = build_uplift_upsample_transformer(cfg, precision="fp32", weights=w)
     md = torch.from_numpy(m).cuda()
-    f1, c1 = test_step(model, torch.from_numpy(x).cuda(), md)
+    f1, c1 = run_test_step(model, torch.from_numpy(x).cuda(), md)
     x2 = x.copy()
     x2[~m] = np.nan                      # garbage in frames without 2-D input
-    f2, c2 = test_step(model, torch.from_numpy(x2).cuda(), md)
+    f2, c2 = run_test_step(model, torch.from_numpy(x2).cuda(), md)
     torch.cuda.synchronize()
     assert torch.equal(f1, f2) and torch.equal(c1, c2)
     model.close()
@@ -116,12 +120,12 @@ def test_large_batch_properties(precision):
     cfg, spec, w, x, m = _case("h36m_351", 20, 512, "shifted", seed=3)
     model = build_uplift_upsample_transformer(cfg, precision=precision, weights=w)
     xd, md = torch.from_numpy(x).cuda(), torch.from_numpy(m).cuda()
-    full, central = test_step(model, xd, md)
+    full, central = run_test_step(model, xd, md)
     perm = torch.randperm(512, device="cuda", generator=torch.Generator(device="cuda").manual_seed(0))
-    fp, cp = test_step(model, xd[perm].contiguous(), md[perm].contiguous())
+    fp, cp = run_test_step(model, xd[perm].contiguous(), md[perm].contiguous())
     torch.cuda.synchronize()
     assert torch.equal(fp, full[perm]) and torch.equal(cp, central[perm])
-    fs, cs = test_step(model, xd[100:116].contiguous(), md[100:116].contiguous())
+    fs, cs = run_test_step(model, xd[100:116].contiguous(), md[100:116].contiguous())
     torch.cuda.synchronize()
     assert torch.equal(cs, central[100:116]) and torch.equal(fs, full[100:116])
     want_full, want_central = O.test_step(spec, w, x[:4], m[:4], dtype=np.float64)

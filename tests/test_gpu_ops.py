@@ -21,9 +21,21 @@ def lib():
     return _lib.load()
 
 
+_KEEP = []          # ctypes pointers do not own the tensors: keep them alive until the test ends
+
+
+@pytest.fixture(autouse=True)
+def _release():
+    yield
+    torch.cuda.synchronize()
+    _KEEP.clear()
+
+
 def dev(a, dtype=None):
     t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
-    return t.to(dtype) if dtype is not None else t
+    t = t.to(dtype) if dtype is not None else t
+    _KEEP.append(t)
+    return t
 
 
 @pytest.mark.parametrize("B,n_tok", [(1, 71), (7, 41), (513, 71), (3000, 71), (5, 128), (4, 1)])
