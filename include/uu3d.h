@@ -84,11 +84,20 @@ int uu_get_weight(uu_model* m, const char* group, int index, float* host, int64_
  *            model has no strided input.
  *   full   : fp32 (B, n_tok, n_joints, 3) or NULL;  central : fp32 (B, n_joints, 3). */
 int uu_forward(uu_model* m, const float* x2d, const uint8_t* mask, int B, float* full, float* central, void* stream);
-/* Same call with HOST buffers (pinned recommended): H2D copy, forward, D2H copy, stream sync. */
+/* Same call with HOST buffers (pinned recommended): H2D copy, forward, D2H copy, stream sync.
+ * full == NULL: the full-sequence head still runs on the device (as in the reference) but is not copied back. */
 int uu_forward_host(uu_model* m, const float* x2d, const uint8_t* mask, int B, float* full, float* central);
 
 /* Number of kernels of this library launched by the most recent forward on `m`. */
 int uu_last_launch_count(const uu_model* m);
+
+/* Per-kernel-kind device timing of the most recent forward: with profiling on, every launch is
+ * bracketed by CUDA events on its own stream; uu_get_profile sums them by kind (ms) after the
+ * forward.  Used by bench.py for the roofline of the dominant kernel; off by default. */
+enum { UU_KIND_GATHER = 0, UU_KIND_SPATIAL, UU_KIND_TOKEN_FILL, UU_KIND_LAYERNORM, UU_KIND_ATTENTION,
+       UU_KIND_GEMM_TC, UU_KIND_GEMM_F32, UU_KIND_CAST, UU_KIND_COUNT };
+int uu_set_profiling(uu_model* m, int on);
+int uu_get_profile(uu_model* m, float* ms_by_kind, int32_t* launches_by_kind, int n_kinds);
 
 /* Stride-mask rule (host, integer, bit-exact): mask[n] = ((n - n_tok/2)*s_out + shift) floor-mod s_in == 0.
  * shift = centre frame index (eval, global alignment) or rand_shift*s_out (training). */

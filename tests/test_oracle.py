@@ -107,3 +107,16 @@ def test_all_masked_window_gives_uniform_attention_in_fp32():
     v = O.dense(y, p[6], p[7])
     want = O.dense(np.broadcast_to(v.mean(axis=1, keepdims=True), v.shape), p[8], p[9])
     assert np.allclose(out, want, atol=1e-5)
+
+
+def test_torch_restatement_agrees_with_numpy_restatement():
+    """Two independent restatements (numpy / torch-CPU incl. F.conv1d and F.gelu) must agree in fp64."""
+    import torch
+    from oracle import forward_torch as OT
+    for name, s_in in (("h36m_351", 20), ("h36m_81", 4)):
+        cfg, spec, w, x = _setup(name, B=3)
+        m = stride_mask.batch_stride_masks_train(spec.n_tok, cfg.SEQUENCE_STRIDE, [s_in], 3, seed=1)
+        f, c = O.test_step(spec, w, x, m, np.float64)
+        wt = OT.to_torch(w, torch.float64)
+        ft, ct = OT.test_step(spec, wt, torch.tensor(x, dtype=torch.float64), torch.tensor(m))
+        assert np.abs(ft.numpy() - f).max() < 1e-10 and np.abs(ct.numpy() - c).max() < 1e-10

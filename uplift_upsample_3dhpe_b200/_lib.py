@@ -22,6 +22,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 UU_MAX_STRIDED = 8
 PRECISION = {"fp32": 0, "bf16": 1}
+KINDS = ["gather", "spatial", "token_fill", "layernorm", "attention", "gemm_tc", "gemm_f32", "cast"]
 
 
 class UUSpec(ctypes.Structure):
@@ -94,6 +95,8 @@ def _declare(lib) -> None:
     lib.uu_forward.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]
     lib.uu_forward_host.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]
     lib.uu_last_launch_count.argtypes = [c_void_p]
+    lib.uu_set_profiling.argtypes = [c_void_p, c_int]
+    lib.uu_get_profile.argtypes = [c_void_p, c_void_p, c_void_p, c_int]
     lib.uu_stride_mask.argtypes = [c_int, c_int, c_int, c_int64, c_void_p]
     lib.uu_op_build_gather.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.uu_op_token_fill.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
@@ -112,7 +115,7 @@ def _declare(lib) -> None:
 EXPORTS = [
     "uu_last_error", "uu_version", "uu_create", "uu_destroy", "uu_set_precision", "uu_get_precision",
     "uu_weight_count", "uu_param_count", "uu_weight_info", "uu_set_weight", "uu_get_weight",
-    "uu_forward", "uu_forward_host", "uu_last_launch_count", "uu_stride_mask",
+    "uu_forward", "uu_forward_host", "uu_last_launch_count", "uu_set_profiling", "uu_get_profile", "uu_stride_mask",
     "uu_op_build_gather", "uu_op_token_fill", "uu_op_layernorm", "uu_op_attention", "uu_op_gemm_f32",
     "uu_op_gemm_bf16",
 ]

@@ -78,6 +78,12 @@ struct uu_model {
   int plan_full = -1;
   std::vector<TcGemmPlan*> plans;
   int launches = 0;
+
+  // optional per-kernel-kind timing (uu_set_profiling): CUDA events around every launch
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_used;   // (kind, (start, stop))
+  size_t ev_next = 0;
 };
 
 namespace uu {
@@ -281,6 +287,30 @@ struct Fwd {
   int launches = 0;
 };
 
+static cudaEvent_t prof_event(uu_model* m) {
+  if (m->ev_next == m->ev_pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    m->ev_pool.push_back(e);
+  }
+  return m->ev_pool[m->ev_next++];
+}
+// Launch wrapper: counts launches and, in profiling mode, brackets the launch with events on its stream.
+#define UU_LAUNCH(f, kind, n, expr)                                                   \
+  do {                                                                                \
+    cudaEvent_t _e0 = nullptr, _e1 = nullptr;                                         \
+    if ((f).m->profiling) {                                                           \
+      _e0 = prof_event((f).m); _e1 = prof_event((f).m);                               \
+      cudaEventRecord(_e0, (f).st);                                                   \
+    }                                                                                 \
+    UU_CUDA(expr);                                                                    \
+    if ((f).m->profiling) {                                                           \
+      cudaEventRecord(_e1, (f).st);                                                   \
+      (f).m->ev_used.push_back({(kind), {_e0, _e1}});                                 \
+    }                                                                                 \
+    (f).launches += (n);                                                              \
+  } while (0)
+
 // One GEMM call site. A: activations in the workspace dtype; Wf: fp32 (K, N); pk: bf16 W^T.
 static int gemm(Fwd& f, const void* A, long long lda, int M, int K, const float* Wf, const Pack& pk, int N,
                 const Epilogue& epi, void* C, int c_bf16, long long ldc) {
@@ -292,11 +322,10 @@ static int gemm(Fwd& f, const void* A, long long lda, int M, int K, const float*
       f.m->plans.push_back(p);
     }
     UU_CHECK(f.plan_i < f.m->plans.size(), "internal: GEMM plan list out of sync");
-    UU_CUDA(tc_gemm_launch(f.m->plans[f.plan_i++], epi, C, c_bf16, ldc, f.st));
+    UU_LAUNCH(f, UU_KIND_GEMM_TC, 1, tc_gemm_launch(f.m->plans[f.plan_i++], epi, C, c_bf16, ldc, f.st));
   } else {
-    UU_CUDA(launch_gemm_simt(A, 0, lda, Wf, M, N, K, epi, C, c_bf16, ldc, f.st));
+    UU_LAUNCH(f, UU_KIND_GEMM_F32, 1, launch_gemm_simt(A, 0, lda, Wf, M, N, K, epi, C, c_bf16, ldc, f.st));
   }
-  f.launches++;
   return 0;
 }
 
@@ -308,16 +337,26 @@ static int attention_block(Fwd& f, const BlockW& w, float* x, int L, const uint8
   Epilogue e;
   e.bias = w.bqkv;
   if (gemm(f, m->Y, d, R, d, w.wqkv, w.p_qkv, 3 * d, e, m->QKV, bf, 3 * d)) return 1;
-  UU_CUDA(launch_attention(m->QKV, bf, f.B, L, s.num_heads, d / s.num_heads, keymask, s.n_tok, m->O, f.st));
-  f.launches++;
+  UU_LAUNCH(f, UU_KIND_ATTENTION, 1,
+            launch_attention(m->QKV, bf, f.B, L, s.num_heads, d / s.num_heads, keymask, s.n_tok, m->O, f.st));
   Epilogue ep;
   ep.bias = w.bp; ep.flags = EPI_RESIDUAL; ep.res = x; ep.ldr = d;
   if (gemm(f, m->O, d, R, d, w.wp, w.p_proj, d, ep, x, 0, d)) return 1;
   return 0;
 }
 
+static int run_forward_impl(uu_model* m, const float* x2d, const uint8_t* mask, int B, float* full, float* central,
+                            cudaStream_t st);
 static int run_forward(uu_model* m, const float* x2d, const uint8_t* mask, int B, float* full, float* central,
                        cudaStream_t st) {
+  m->ev_next = 0;
+  m->ev_used.clear();
+  const int rc = run_forward_impl(m, x2d, mask, B, full, central, st);
+  if (rc) drop_plans(m);   // never keep a half-built plan list
+  return rc;
+}
+static int run_forward_impl(uu_model* m, const float* x2d, const uint8_t* mask, int B, float* full, float* central,
+                            cudaStream_t st) {
   const uu_spec& s = m->spec;
   UU_CHECK(B > 0, "batch must be positive");
   UU_CHECK(x2d && central, "x2d and central must not be null");
@@ -337,8 +376,7 @@ static int run_forward(uu_model* m, const float* x2d, const uint8_t* mask, int B
 
   // K1a: gather list of frames that carry a 2-D pose
   if (use_mask) {
-    UU_CUDA(launch_build_gather(mask, B, N, m->g_scratch, m->g_list, m->g_count, st));
-    f.launches += 3;
+    UU_LAUNCH(f, UU_KIND_GATHER, 3, launch_build_gather(mask, B, N, m->g_scratch, m->g_list, m->g_count, st));
   }
   // K2: fused spatial transformer on the valid frames -> S (compact rows)
   SpatialParams sp;
@@ -348,8 +386,7 @@ static int run_forward(uu_model* m, const float* x2d, const uint8_t* mask, int B
   sp.pe = W(m, "spatial_pe", 0); sp.blocks = m->spatial_ptrs;
   sp.norm_g = W(m, "spatial_norm", 0); sp.norm_b = W(m, "spatial_norm", 1);
   sp.out = m->S; sp.out_bf16 = bf;
-  UU_CUDA(launch_spatial_f32(sp, st));
-  f.launches++;
+  UU_LAUNCH(f, UU_KIND_SPATIAL, 1, launch_spatial_f32(sp, st));
   // S4 + T1: 544->384 GEMM, rows scattered to their token position, + bias + temporal PE
   {
     Epilogue e;
@@ -358,19 +395,17 @@ static int run_forward(uu_model* m, const float* x2d, const uint8_t* mask, int B
     if (use_mask) { e.c_rowidx = m->g_list; e.m_dev = m->g_count; }
     if (gemm(f, m->S, J * ds, R, J * ds, W(m, "spatial_to_temporal_fc", 0), m->p_s2t, d, e, m->X, 0, d)) return 1;
     if (use_mask) {
-      UU_CUDA(launch_token_fill(mask, R, N, d, W(m, "strided_input_token_layer", 0), W(m, "temporal_pe", 0), m->X, st));
-      f.launches++;
+      UU_LAUNCH(f, UU_KIND_TOKEN_FILL, 1,
+                launch_token_fill(mask, R, N, d, W(m, "strided_input_token_layer", 0), W(m, "temporal_pe", 0), m->X, st));
     }
   }
   // T2/T3: temporal transformer blocks (ReLU MLP)
   for (int i = 0; i < s.temporal_depth; ++i) {
     const BlockW& w = m->tblocks[i];
-    UU_CUDA(launch_layernorm(m->X, R, d, w.ln1_g, w.ln1_b, 1e-5f, nullptr, 1, m->Y, bf, st));
-    f.launches++;
+    UU_LAUNCH(f, UU_KIND_LAYERNORM, 1, launch_layernorm(m->X, R, d, w.ln1_g, w.ln1_b, 1e-5f, nullptr, 1, m->Y, bf, st));
     const uint8_t* km = (use_mask && i < s.first_strided_token_attention_layer) ? mask : nullptr;
     if (attention_block(f, w, m->X, N, km)) return 1;
-    UU_CUDA(launch_layernorm(m->X, R, d, w.ln2_g, w.ln2_b, 1e-5f, nullptr, 1, m->Y, bf, st));
-    f.launches++;
+    UU_LAUNCH(f, UU_KIND_LAYERNORM, 1, launch_layernorm(m->X, R, d, w.ln2_g, w.ln2_b, 1e-5f, nullptr, 1, m->Y, bf, st));
     Epilogue e1;
     e1.bias = w.b1; e1.flags = EPI_RELU;
     if (gemm(f, m->Y, d, R, d, w.w1, w.p_fc1, h, e1, m->Hd, bf, h)) return 1;
@@ -384,8 +419,7 @@ static int run_forward(uu_model* m, const float* x2d, const uint8_t* mask, int B
     e.bias = W(m, "temporal_fc", 1);
     const void* A = m->X;
     if (f.tc) {   // the tensor-core GEMM wants a bf16 operand: cast the fp32 residual stream into Y
-      UU_CUDA(launch_cast_bf16(m->X, (bf16*)m->Y, (long long)R * d, st));
-      f.launches++;
+      UU_LAUNCH(f, UU_KIND_CAST, 1, launch_cast_bf16(m->X, (bf16*)m->Y, (long long)R * d, st));
       A = m->Y;
     }
     if (gemm(f, A, d, R, d, W(m, "temporal_fc", 0), m->p_head1, 3 * J, e, full, 0, 3 * J)) return 1;
@@ -398,12 +432,11 @@ static int run_forward(uu_model* m, const float* x2d, const uint8_t* mask, int B
     const int pl = s.pad_left[i], pr = s.pad_right[i];
     const int Rl = B * L;
     // x += PE_i (written back), y = LN1(x)
-    UU_CUDA(launch_layernorm(x_in, Rl, d, w.ln1_g, w.ln1_b, 1e-5f,
-                             W(m, "strided_temporal_pe_" + std::to_string(i + 1), 0), L, m->Y, bf, st));
-    f.launches++;
+    UU_LAUNCH(f, UU_KIND_LAYERNORM, 1,
+              launch_layernorm(x_in, Rl, d, w.ln1_g, w.ln1_b, 1e-5f,
+                               W(m, "strided_temporal_pe_" + std::to_string(i + 1), 0), L, m->Y, bf, st));
     if (attention_block(f, w, x_in, L, nullptr)) return 1;
-    UU_CUDA(launch_layernorm(x_in, Rl, d, w.ln2_g, w.ln2_b, 1e-5f, nullptr, 1, m->Y, bf, st));
-    f.launches++;
+    UU_LAUNCH(f, UU_KIND_LAYERNORM, 1, launch_layernorm(x_in, Rl, d, w.ln2_g, w.ln2_b, 1e-5f, nullptr, 1, m->Y, bf, st));
     // Conv1D k=1 + ReLU, written into the zero-padded layout [B, Lo*s, h] (rows never read by the
     // strided conv are dropped; pad rows stay zero from allocation)
     Epilogue e1;
@@ -426,8 +459,7 @@ static int run_forward(uu_model* m, const float* x2d, const uint8_t* mask, int B
     e.bias = W(m, "strided_temporal_fc", 1);
     const void* A = x_in;
     if (f.tc) {
-      UU_CUDA(launch_cast_bf16(x_in, (bf16*)m->Y, (long long)B * d, st));
-      f.launches++;
+      UU_LAUNCH(f, UU_KIND_CAST, 1, launch_cast_bf16(x_in, (bf16*)m->Y, (long long)B * d, st));
       A = m->Y;
     }
     if (gemm(f, A, d, B, d, W(m, "strided_temporal_fc", 0), m->p_head2, 3 * J, e, central, 0, 3 * J)) return 1;
@@ -530,6 +562,7 @@ int uu_destroy(uu_model* m) {
   cudaFree(m->d_full);
   cudaFree(m->d_central);
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
+  for (auto e : m->ev_pool) cudaEventDestroy(e);
   delete m;
   return 0;
 }
@@ -618,7 +651,8 @@ int uu_forward_host(uu_model* m, const float* x2d, const uint8_t* mask, int B, f
   cudaStream_t st = m->own_stream;
   UU_CUDA(cudaMemcpyAsync(m->d_x, x2d, sizeof(float) * R * s.n_joints * 2, cudaMemcpyHostToDevice, st));
   if (mask) UU_CUDA(cudaMemcpyAsync(m->d_mask, mask, R, cudaMemcpyHostToDevice, st));
-  if (run_forward(m, m->d_x, mask ? m->d_mask : nullptr, B, full ? m->d_full : nullptr, m->d_central, st)) return 1;
+  // full == NULL: the full-sequence head still runs (the reference always computes it) but stays on the device
+  if (run_forward(m, m->d_x, mask ? m->d_mask : nullptr, B, m->d_full, m->d_central, st)) return 1;
   if (full) UU_CUDA(cudaMemcpyAsync(full, m->d_full, sizeof(float) * R * s.n_joints * 3, cudaMemcpyDeviceToHost, st));
   UU_CUDA(cudaMemcpyAsync(central, m->d_central, sizeof(float) * (size_t)B * s.n_joints * 3, cudaMemcpyDeviceToHost, st));
   UU_CUDA(cudaStreamSynchronize(st));
@@ -626,6 +660,25 @@ int uu_forward_host(uu_model* m, const float* x2d, const uint8_t* mask, int B, f
 }
 
 int uu_last_launch_count(const uu_model* m) { return m ? m->launches : -1; }
+
+int uu_set_profiling(uu_model* m, int on) {
+  UU_CHECK(m, "null model");
+  m->profiling = on != 0;
+  return 0;
+}
+
+int uu_get_profile(uu_model* m, float* ms_by_kind, int32_t* launches_by_kind, int n_kinds) {
+  UU_CHECK(m && ms_by_kind && launches_by_kind && n_kinds >= UU_KIND_COUNT, "bad argument");
+  for (int i = 0; i < n_kinds; ++i) { ms_by_kind[i] = 0.f; launches_by_kind[i] = 0; }
+  for (auto& e : m->ev_used) {
+    UU_CUDA(cudaEventSynchronize(e.second.second));
+    float ms = 0.f;
+    UU_CUDA(cudaEventElapsedTime(&ms, e.second.first, e.second.second));
+    ms_by_kind[e.first] += ms;
+    launches_by_kind[e.first] += 1;
+  }
+  return 0;
+}
 
 int uu_stride_mask(int n_tok, int s_out, int s_in, int64_t shift, uint8_t* mask_out) {
   UU_CHECK(mask_out && n_tok > 0 && s_out > 0 && s_in > 0, "bad argument");

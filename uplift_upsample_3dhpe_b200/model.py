@@ -116,6 +116,17 @@ class UpliftUpsampleTransformer:
     def last_launch_count(self) -> int:
         return int(self._lib.uu_last_launch_count(self._h))
 
+    def set_profiling(self, on: bool) -> None:
+        _lib.check(self._lib.uu_set_profiling(self._h, int(on)))
+
+    def get_profile(self) -> Dict[str, Tuple[float, int]]:
+        """{kernel kind: (device ms, launches)} of the most recent forward (profiling must be on)."""
+        n = len(_lib.KINDS)
+        ms = (ctypes.c_float * n)()
+        cnt = (ctypes.c_int32 * n)()
+        _lib.check(self._lib.uu_get_profile(self._h, ms, cnt, n))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(_lib.KINDS)}
+
     # ---- forward -------------------------------------------------------------------------------
     def __call__(self, inputs, training: bool = False, want_full: bool = True):
         """inputs = [x2d (B,n_tok,J,2) float32 cuda, stride_mask (B,n_tok) bool/uint8 cuda] (or x2d alone when
