@@ -16,9 +16,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libuu3d.so")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
-SOURCES = ["kernels_f32.cu", "gemm_tc.cu", "uu_api.cu"]
+SOURCES = ["kernels_f32.cu", "spatial_tc.cu", "attention_tc.cu", "gemm_tc.cu", "uu_api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "550"]
+              "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "550,177"]
 
 UU_MAX_STRIDED = 8
 PRECISION = {"fp32": 0, "bf16": 1}

@@ -114,6 +114,19 @@ cudaError_t launch_attention(const void* qkv, int is_bf16, int B, int S, int hea
 cudaError_t launch_gemm_simt(const void* A, int a_bf16, long long lda, const float* W, int M, int N, int K,
                              const Epilogue& epi, void* C, int c_bf16, long long ldc, cudaStream_t st);
 
+// ---- tensor-core attention (attention_tc.cu): bf16 q|k|v rows in, bf16 merged heads out ---------
+cudaError_t launch_attention_tc(const bf16* qkv, int B, int S, int heads, int dh, const uint8_t* mask, int mask_stride,
+                                bf16* out, cudaStream_t st);
+
+// ---- tensor-core spatial transformer (spatial_tc.cu) -------------------------------------------
+size_t spatial_tc_frag_bytes(int depth);
+size_t spatial_tc_param_bytes(int depth);
+cudaError_t launch_spatial_pack(const float* const* blocks, int depth, const float* embed_k, const float* embed_b,
+                                const float* pe, const float* norm_g, const float* norm_b, void* frags, float* params,
+                                cudaStream_t s);
+cudaError_t launch_spatial_tc(const float* x2d, const int* list, const int* count, int max_frames, int depth,
+                              const void* frags, const float* params, bf16* out, int num_sms, cudaStream_t s);
+
 // ---- tcgen05 GEMM (gemm_tc.cu) ----------------------------------------------------------------
 struct TcGemmPlan;   // holds the TMA tensor maps of one GEMM call site
 int tc_gemm_plan_create(TcGemmPlan** out, const bf16* A, long long lda, int M, int K, const bf16* Wt, int N_pad,

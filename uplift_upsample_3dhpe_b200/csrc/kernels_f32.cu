@@ -541,10 +541,11 @@ cudaError_t launch_attention(const void* qkv, int is_bf16, int B, int S, int hea
                              int mask_stride, void* out, cudaStream_t st) {
   if (B == 0) return cudaSuccess;
   if (S > 128 || S < 1) return cudaErrorInvalidValue;
-#define UU_ATTN_CASE(DHV)                                                                                   \
-  case DHV:                                                                                                 \
-    return is_bf16 ? attn_dispatch<DHV, bf16>(qkv, B, S, heads, mask, mask_stride, out, st)                 \
-                   : attn_dispatch<DHV, float>(qkv, B, S, heads, mask, mask_stride, out, st);
+  if (is_bf16)   // the bf16 path has its own tensor-core kernel (attention_tc.cu)
+    return launch_attention_tc((const bf16*)qkv, B, S, heads, dh, mask, mask_stride, (bf16*)out, st);
+#define UU_ATTN_CASE(DHV) \
+  case DHV:               \
+    return attn_dispatch<DHV, float>(qkv, B, S, heads, mask, mask_stride, out, st);
   switch (dh) {
     UU_ATTN_CASE(16)
     UU_ATTN_CASE(32)

@@ -55,6 +55,9 @@ struct uu_model {
   // derived weights
   std::vector<BlockW> tblocks, sblocks;
   const float** spatial_ptrs = nullptr;    // device array [depth][16]
+  void* sp_frags = nullptr;                // tensor-core spatial kernel: B-fragment image + fp32 params
+  float* sp_params = nullptr;
+  int num_sms = 148;
   Pack p_s2t, p_head1, p_head2;
   std::vector<void*> derived_allocs;
 
@@ -218,6 +221,15 @@ static int commit_weights(uu_model* m) {
       for (int i = 0; i < 16; ++i) h[l * 16 + i] = W(m, "spatial_block_" + std::to_string(l + 1), i);
     UU_CUDA(cudaMemcpy(p, h.data(), sizeof(float*) * h.size(), cudaMemcpyHostToDevice));
   }
+  if (!m->sp_frags) {
+    void* p;
+    if (dev_alloc(m->derived_allocs, &m->sp_frags, spatial_tc_frag_bytes(s.spatial_depth), false)) return 1;
+    if (dev_alloc(m->derived_allocs, &p, spatial_tc_param_bytes(s.spatial_depth), false)) return 1;
+    m->sp_params = (float*)p;
+  }
+  UU_CUDA(launch_spatial_pack(m->spatial_ptrs, s.spatial_depth, W(m, "keypoint_embedding", 0),
+                              W(m, "keypoint_embedding", 1), W(m, "spatial_pe", 0), W(m, "spatial_norm", 0),
+                              W(m, "spatial_norm", 1), m->sp_frags, m->sp_params, 0));
   m->tblocks.resize(s.temporal_depth);
   m->sblocks.resize(s.n_strided);
   for (int i = 0; i < s.temporal_depth; ++i)
@@ -386,7 +398,13 @@ static int run_forward_impl(uu_model* m, const float* x2d, const uint8_t* mask, 
   sp.pe = W(m, "spatial_pe", 0); sp.blocks = m->spatial_ptrs;
   sp.norm_g = W(m, "spatial_norm", 0); sp.norm_b = W(m, "spatial_norm", 1);
   sp.out = m->S; sp.out_bf16 = bf;
-  UU_LAUNCH(f, UU_KIND_SPATIAL, 1, launch_spatial_f32(sp, st));
+  if (f.tc) {
+    UU_LAUNCH(f, UU_KIND_SPATIAL, 1,
+              launch_spatial_tc(x2d, sp.list, sp.count, R, s.spatial_depth, m->sp_frags, m->sp_params, (bf16*)m->S,
+                                m->num_sms, st));
+  } else {
+    UU_LAUNCH(f, UU_KIND_SPATIAL, 1, launch_spatial_f32(sp, st));
+  }
   // S4 + T1: 544->384 GEMM, rows scattered to their token position, + bias + temporal PE
   {
     Epilogue e;
@@ -480,6 +498,7 @@ static int check_spec(const uu_spec& s, std::vector<int>& lens) {
   UU_CHECK(dh == 16 || dh == 32 || dh == 48 || dh == 64, "temporal head_dim must be 16, 32, 48 or 64");
   UU_CHECK(s.h_temporal % 64 == 0, "temporal MLP width must be a multiple of 64");
   UU_CHECK(s.spatial_depth >= 1 && s.temporal_depth >= 1, "depths must be >= 1");
+  UU_CHECK(s.spatial_depth <= 4, "the tensor-core spatial kernel keeps at most 4 blocks of weights in shared memory");
   UU_CHECK(s.n_strided >= 1 && s.n_strided <= UU_MAX_STRIDED, "1..8 strided blocks");
   lens.clear();
   lens.push_back(s.n_tok);
@@ -534,6 +553,7 @@ int uu_create(const uu_spec* spec, int device, uu_model** out) {
   UU_CUDA(cudaGetDeviceProperties(&prop, device));
   UU_CHECK(prop.major == 10, "uu3d is built for sm_100a (B200) only");
   uu_model* m = new uu_model();
+  m->num_sms = prop.multiProcessorCount;
   m->spec = *spec;
   m->device = device;
   m->seq_lens = lens;
