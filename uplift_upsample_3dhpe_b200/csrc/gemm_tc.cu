@@ -31,6 +31,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 // Bounded wait: a protocol bug must trap, not hang the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
@@ -111,26 +114,35 @@ struct TcCfg {
   static constexpr int A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;   // 16 KB
   static constexpr int B_BYTES = BLOCK_N * TC_BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BLOCK_N >= 256 ? 4 : 3;
-  static constexpr int TMEM_COLS = BLOCK_N <= 32 ? 32 : BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES < 8 ? (200 * 1024) / STAGE_BYTES : 8;
+  static constexpr int ACC_STAGES = 2;                           // double-buffered accumulator in TMEM
+  static constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N <= 32 ? 32 : ACC_STAGES * BLOCK_N <= 64 ? 64
+                                   : ACC_STAGES * BLOCK_N <= 128 ? 128 : ACC_STAGES * BLOCK_N <= 256 ? 256 : 512;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(ACC_STAGES * BLOCK_N <= 512, "accumulator stages exceed TMEM");
+  static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024-byte alignment for the 128B swizzle");
 };
 
+// Persistent, warp-specialised: every CTA walks the tile list t = blockIdx.x, += gridDim.x with
+// (m_blk, n_blk) = (t / n_tiles, t % n_tiles), so CTAs running concurrently share the same A rows in L2.
+// Three pipelines: smem ring (TMA -> MMA), TMEM accumulator ring (MMA -> epilogue), tile list.
 template <int BLOCK_N, typename TC>
-__global__ void __launch_bounds__(TC_THREADS) k_gemm_tc(const __grid_constant__ CUtensorMap map_a,
-                                                        const __grid_constant__ CUtensorMap map_b, int M, int N,
-                                                        int K, Epilogue epi, TC* __restrict__ C, long long ldc) {
+__global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant__ CUtensorMap map_a,
+                                                           const __grid_constant__ CUtensorMap map_b, int M, int N,
+                                                           int n_tiles, int K, Epilogue epi, TC* __restrict__ C,
+                                                           long long ldc) {
   using Cfg = TcCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   const int m_eff = epi.m_dev ? min(M, *epi.m_dev) : M;
-  const int row0 = blockIdx.x * TC_BLOCK_M, col0 = blockIdx.y * BLOCK_N;
-  if (row0 >= m_eff) return;   // uniform for the CTA (compact valid-frame GEMM, device-side row count)
+  const int m_tiles = (m_eff + TC_BLOCK_M - 1) / TC_BLOCK_M;
+  const int total_tiles = m_tiles * n_tiles;
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
   uint64_t* tmem_full_bar = empty_bar + Cfg::STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_empty_bar = tmem_full_bar + Cfg::ACC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + Cfg::ACC_STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = (K + TC_BLOCK_K - 1) / TC_BLOCK_K;
@@ -142,7 +154,10 @@ __global__ void __launch_bounds__(TC_THREADS) k_gemm_tc(const __grid_constant__ 
       mbar_init(full_bar + s, 1);
       mbar_init(empty_bar + s, 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < Cfg::ACC_STAGES; ++s) {
+      mbar_init(tmem_full_bar + s, 1);
+      mbar_init(tmem_empty_bar + s, 4);      // one arrive per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -159,99 +174,130 @@ __global__ void __launch_bounds__(TC_THREADS) k_gemm_tc(const __grid_constant__ 
   if (warp == 0) {
     // ---------------- TMA producer ----------------
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % Cfg::STAGES;
-        const uint32_t ph = (kb / Cfg::STAGES) & 1;
-        mbar_wait(empty_bar + s, ph ^ 1);
-        uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
-        uint8_t* b_dst = a_dst + Cfg::A_BYTES;
-        mbar_expect_tx(full_bar + s, Cfg::STAGE_BYTES);
-        tma_load_2d(a_dst, &map_a, full_bar + s, kb * TC_BLOCK_K, row0);
-        tma_load_2d(b_dst, &map_b, full_bar + s, kb * TC_BLOCK_K, col0);
+      uint32_t it = 0;                        // running k-block counter across tiles -> stage / phase
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int row0 = (tile / n_tiles) * TC_BLOCK_M, col0 = (tile % n_tiles) * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % Cfg::STAGES;
+          const uint32_t ph = (it / Cfg::STAGES) & 1;
+          mbar_wait(empty_bar + s, ph ^ 1);
+          uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
+          uint8_t* b_dst = a_dst + Cfg::A_BYTES;
+          mbar_expect_tx(full_bar + s, Cfg::STAGE_BYTES);
+          tma_load_2d(a_dst, &map_a, full_bar + s, kb * TC_BLOCK_K, row0);
+          tma_load_2d(b_dst, &map_b, full_bar + s, kb * TC_BLOCK_K, col0);
+        }
       }
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(TC_BLOCK_M, BLOCK_N);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % Cfg::STAGES;
-        const uint32_t ph = (kb / Cfg::STAGES) & 1;
-        mbar_wait(full_bar + s, ph);
+      uint32_t it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+        const int as = tcount % Cfg::ACC_STAGES;
+        const uint32_t aph = (tcount / Cfg::ACC_STAGES) & 1;
+        mbar_wait(tmem_empty_bar + as, aph ^ 1);          // epilogue has drained this accumulator
         tcgen05_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
-        const uint32_t b_addr = a_addr + Cfg::A_BYTES;
-        const uint64_t a_desc = make_sw128_desc(a_addr), b_desc = make_sw128_desc(b_addr);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BLOCK_N);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % Cfg::STAGES;
+          const uint32_t ph = (it / Cfg::STAGES) & 1;
+          mbar_wait(full_bar + s, ph);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+          const uint64_t a_desc = make_sw128_desc(a_addr), b_desc = make_sw128_desc(b_addr);
 #pragma unroll
-        for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
-          // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (>>4) address field
-          umma_bf16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
+            // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (>>4) address field
+            umma_bf16(tmem_d, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(empty_bar + s);           // frees the smem stage when these MMAs retire
         }
-        umma_commit(empty_bar + s);           // frees the smem stage when these MMAs retire
+        umma_commit(tmem_full_bar + as);        // accumulator complete
       }
-      umma_commit(tmem_full_bar);             // accumulator complete
     }
   } else {
     // ---------------- epilogue: TMEM -> registers -> global ----------------
     const int q = warp & 3;                   // TMEM lane quarter this warp may access
-    const int r = row0 + q * 32 + lane;
-    mbar_wait(tmem_full_bar, 0);
-    tcgen05_fence_after();
-    const bool row_ok = r < m_eff;
-    EpiRow er;
-    er.crow = -1; er.rrow = 0; er.trow = 0;
-    if (row_ok) er = epi_row(epi, r);
-    const bool vec_ok = (N % 4 == 0) && (ldc % 4 == 0) && (!(epi.flags & EPI_RESIDUAL) || (epi.ldr % 4 == 0));
+    const bool vec_ok = (N % 8 == 0) && (ldc % 8 == 0) && (!(epi.flags & EPI_RESIDUAL) || (epi.ldr % 4 == 0));
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      const int row0 = (tile / n_tiles) * TC_BLOCK_M, col0 = (tile % n_tiles) * BLOCK_N;
+      const int as = tcount % Cfg::ACC_STAGES;
+      const uint32_t aph = (tcount / Cfg::ACC_STAGES) & 1;
+      const int r = row0 + q * 32 + lane;
+      const bool row_ok = r < m_eff;
+      EpiRow er;
+      er.crow = -1; er.rrow = 0; er.trow = 0;
+      if (row_ok) er = epi_row(epi, r);
+      mbar_wait(tmem_full_bar + as, aph);
+      tcgen05_fence_after();
+      const uint32_t tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      const int cbase = col0 + c0;
-      const bool do_store = row_ok && er.crow >= 0 && cbase < N;
-      TC* crow_ptr = C + (do_store ? er.crow : 0) * ldc;
-      if (!do_store) {
-        // nothing to write for this row / column chunk
-      } else if (vec_ok) {
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_acc + (uint32_t)c0, v);
+        const int cbase = col0 + c0;
+        const bool do_store = row_ok && er.crow >= 0 && cbase < N;
+        TC* crow_ptr = C + (do_store ? er.crow : 0) * ldc;
+        if (!do_store) {
+          // nothing to write for this row / column chunk
+        } else if (vec_ok) {
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const int c = cbase + g * 4;
-          if (c >= N) break;
-          float o[4] = {__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]),
-                        __uint_as_float(v[4 * g + 3])};
-          if (epi.bias) {
-            const float4 b = *reinterpret_cast<const float4*>(epi.bias + c);
-            o[0] += b.x; o[1] += b.y; o[2] += b.z; o[3] += b.w;
-          }
-          if (epi.flags & EPI_RELU) {
+          for (int g = 0; g < 4; ++g) {          // 8 columns per step: one 16-byte (bf16) or two 16-byte (fp32) stores
+            const int c = cbase + g * 8;
+            if (c >= N) break;
+            float o[8];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) o[i] = fmaxf(o[i], 0.f);
+            for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v[8 * g + i]);
+            if (epi.bias) {
+              const float4 b0 = *reinterpret_cast<const float4*>(epi.bias + c);
+              const float4 b1 = *reinterpret_cast<const float4*>(epi.bias + c + 4);
+              o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w;
+              o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
+            }
+            if (epi.flags & EPI_RELU) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o[i] = fmaxf(o[i], 0.f);
+            }
+            if (epi.flags & EPI_RESIDUAL) {
+              const float* rp = epi.res + er.rrow * epi.ldr + c;
+              const float4 t0 = *reinterpret_cast<const float4*>(rp), t1 = *reinterpret_cast<const float4*>(rp + 4);
+              o[0] += t0.x; o[1] += t0.y; o[2] += t0.z; o[3] += t0.w;
+              o[4] += t1.x; o[5] += t1.y; o[6] += t1.z; o[7] += t1.w;
+            }
+            if (epi.flags & EPI_ROWTABLE) {
+              const float* tp = epi.table + (long long)er.trow * N + c;
+              const float4 t0 = *reinterpret_cast<const float4*>(tp), t1 = *reinterpret_cast<const float4*>(tp + 4);
+              o[0] += t0.x; o[1] += t0.y; o[2] += t0.z; o[3] += t0.w;
+              o[4] += t1.x; o[5] += t1.y; o[6] += t1.z; o[7] += t1.w;
+            }
+            if constexpr (sizeof(TC) == 4) {
+              *reinterpret_cast<float4*>(crow_ptr + c) = make_float4(o[0], o[1], o[2], o[3]);
+              *reinterpret_cast<float4*>(crow_ptr + c + 4) = make_float4(o[4], o[5], o[6], o[7]);
+            } else {
+              __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
+              __nv_bfloat162 p2 = __floats2bfloat162_rn(o[4], o[5]), p3 = __floats2bfloat162_rn(o[6], o[7]);
+              uint4 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+              pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
+              *reinterpret_cast<uint4*>(crow_ptr + c) = pk;
+            }
           }
-          if (epi.flags & EPI_RESIDUAL) {
-            const float4 t = *reinterpret_cast<const float4*>(epi.res + er.rrow * epi.ldr + c);
-            o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w;
-          }
-          if (epi.flags & EPI_ROWTABLE) {
-            const float4 t = *reinterpret_cast<const float4*>(epi.table + (long long)er.trow * N + c);
-            o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w;
-          }
-          if constexpr (sizeof(TC) == 4) {
-            *reinterpret_cast<float4*>(crow_ptr + c) = make_float4(o[0], o[1], o[2], o[3]);
-          } else {
-            __nv_bfloat162 lo = __floats2bfloat162_rn(o[0], o[1]), hi = __floats2bfloat162_rn(o[2], o[3]);
-            uint2 pk;
-            pk.x = *reinterpret_cast<uint32_t*>(&lo);
-            pk.y = *reinterpret_cast<uint32_t*>(&hi);
-            *reinterpret_cast<uint2*>(crow_ptr + c) = pk;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int c = cbase + i;
+            if (c < N) store_out(crow_ptr + c, epi_value(epi, er, __uint_as_float(v[i]), c, N));
           }
         }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int c = cbase + i;
-          if (c < N) store_out(crow_ptr + c, epi_value(epi, er, __uint_as_float(v[i]), c, N));
-        }
+        __syncwarp();   // reconverge before the next warp-collective tcgen05.ld
       }
-      __syncwarp();   // reconverge before the next warp-collective tcgen05.ld
+      // all TMEM reads of this warp are complete (tcgen05.wait::ld): hand the accumulator back to the MMA warp
+      tcgen05_fence_before();
+      if (lane == 0) mbar_arrive(tmem_empty_bar + as);
     }
   }
 
@@ -310,7 +356,8 @@ int tc_gemm_plan_create(TcGemmPlan** out, const bf16* A, long long lda, int M, i
   UU_CHECK(M > 0 && N > 0 && K > 0 && N <= N_pad, "bad GEMM shape");
   TcGemmPlan* p = new TcGemmPlan();
   p->M = M; p->N = N; p->N_pad = N_pad; p->K = K;
-  p->block_n = (N_pad % 128 == 0) ? 128 : 64;
+  // widest tile that divides the padded N: 256 (fc1), 192 (q|k|v, 384-wide outputs), 128, 64 (heads)
+  p->block_n = (N_pad % 256 == 0) ? 256 : (N_pad % 192 == 0) ? 192 : (N_pad % 128 == 0) ? 128 : 64;
   if (N_pad % p->block_n != 0) {
     delete p;
     set_error("tcgen05 GEMM needs the packed weight rows padded to a multiple of 64");
@@ -327,6 +374,8 @@ int tc_gemm_plan_create(TcGemmPlan** out, const bf16* A, long long lda, int M, i
 
 void tc_gemm_plan_destroy(TcGemmPlan* p) { delete p; }
 
+static int g_num_sms = 0;
+
 template <int BLOCK_N, typename TC>
 static cudaError_t tc_launch_t(const TcGemmPlan* p, const Epilogue& epi, void* C, long long ldc, cudaStream_t st) {
   using Cfg = TcCfg<BLOCK_N>;
@@ -337,17 +386,27 @@ static cudaError_t tc_launch_t(const TcGemmPlan* p, const Epilogue& epi, void* C
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  dim3 grid((p->M + TC_BLOCK_M - 1) / TC_BLOCK_M, p->N_pad / BLOCK_N);
-  k_gemm_tc<BLOCK_N, TC><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(p->map_a, p->map_b, p->M, p->N, p->K, epi,
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int n_tiles = p->N_pad / BLOCK_N;
+  const int total = ((p->M + TC_BLOCK_M - 1) / TC_BLOCK_M) * n_tiles;
+  const int grid = total < g_num_sms ? total : g_num_sms;          // persistent: one CTA per SM
+  k_gemm_tc<BLOCK_N, TC><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(p->map_a, p->map_b, p->M, p->N, n_tiles, p->K, epi,
                                                                     reinterpret_cast<TC*>(C), ldc);
   return cudaGetLastError();
 }
 
 cudaError_t tc_gemm_launch(const TcGemmPlan* p, const Epilogue& epi, void* C, int c_bf16, long long ldc,
                            cudaStream_t st) {
-  if (p->block_n == 128)
-    return c_bf16 ? tc_launch_t<128, bf16>(p, epi, C, ldc, st) : tc_launch_t<128, float>(p, epi, C, ldc, st);
-  return c_bf16 ? tc_launch_t<64, bf16>(p, epi, C, ldc, st) : tc_launch_t<64, float>(p, epi, C, ldc, st);
+  switch (p->block_n) {
+    case 256: return c_bf16 ? tc_launch_t<256, bf16>(p, epi, C, ldc, st) : tc_launch_t<256, float>(p, epi, C, ldc, st);
+    case 192: return c_bf16 ? tc_launch_t<192, bf16>(p, epi, C, ldc, st) : tc_launch_t<192, float>(p, epi, C, ldc, st);
+    case 128: return c_bf16 ? tc_launch_t<128, bf16>(p, epi, C, ldc, st) : tc_launch_t<128, float>(p, epi, C, ldc, st);
+    default: return c_bf16 ? tc_launch_t<64, bf16>(p, epi, C, ldc, st) : tc_launch_t<64, float>(p, epi, C, ldc, st);
+  }
 }
 
 }  // namespace uu

@@ -49,7 +49,8 @@ struct uu_model {
   std::map<std::pair<std::string, int>, int> lookup;
   std::vector<int> seq_lens;
   float* params = nullptr;
-  size_t n_params = 0;
+  size_t n_params = 0;     // exact parameter count
+  size_t n_alloc = 0;      // floats in the flat buffer (tensors padded to 16 bytes)
   bool dirty = true;
 
   // derived weights
@@ -98,10 +99,11 @@ static const float* W(const uu_model* m, const std::string& g, int i) {
 
 static void add_tensor(uu_model* m, const std::string& g, int idx, std::vector<int64_t> shape) {
   TensorInfo t;
-  t.group = g; t.index = idx; t.shape = shape; t.offset = m->n_params;
+  t.group = g; t.index = idx; t.shape = shape; t.offset = m->n_alloc;
   t.numel = 1;
   for (auto s : shape) t.numel *= (size_t)s;
   m->n_params += t.numel;
+  m->n_alloc += (t.numel + 3) & ~(size_t)3;     // every tensor starts 16-byte aligned (vector loads of biases)
   m->lookup[{g, idx}] = (int)m->tensors.size();
   m->tensors.push_back(t);
 }
@@ -558,8 +560,8 @@ int uu_create(const uu_spec* spec, int device, uu_model** out) {
   m->device = device;
   m->seq_lens = lens;
   build_inventory(m);
-  if (cudaMalloc(&m->params, sizeof(float) * m->n_params) != cudaSuccess ||
-      cudaMemset(m->params, 0, sizeof(float) * m->n_params) != cudaSuccess ||
+  if (cudaMalloc(&m->params, sizeof(float) * m->n_alloc) != cudaSuccess ||
+      cudaMemset(m->params, 0, sizeof(float) * m->n_alloc) != cudaSuccess ||
       cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
     set_error("device allocation failed in uu_create");
     delete m;
