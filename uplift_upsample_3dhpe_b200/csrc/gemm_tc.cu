@@ -1,9 +1,9 @@
 // K3: bf16 GEMM on the 5th-generation tensor cores (sm_100a):
 //   TMA (cp.async.bulk.tensor, 128B swizzle) -> shared-memory ring -> tcgen05.mma (accumulator in
 //   TMEM) -> tcgen05.ld -> fused epilogue (bias / ReLU / residual / positional table / row scatter).
-// Warp roles in a 192-thread CTA: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = epilogue (one TMEM lane quarter each).  One 128 x BLOCK_N output tile per CTA; two
-// CTAs are co-resident per SM so one CTA's epilogue overlaps the other's MMA main loop.
+// Warp roles in a 320-thread persistent CTA (one per SM): warp 0 = TMA producer, warp 1 = TMEM allocator +
+// MMA issuer, warps 2..9 = epilogue.  The accumulator is double-buffered in TMEM so the epilogue of tile i
+// overlaps the MMA main loop of tile i+1.
 //
 // A  : bf16 row-major [M, K] with leading dimension lda (activations; the strided Conv1D reads its
 //      zero-padded input as a [B*L_out, 3*C] matrix with lda = stride*C — implicit GEMM, no im2col).
@@ -18,7 +18,9 @@ namespace uu {
 constexpr int TC_BLOCK_M = 128;
 constexpr int TC_BLOCK_K = 64;          // 64 bf16 = 128 B = one swizzle atom row
 constexpr int TC_UMMA_K = 16;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;        // TMA warp, MMA warp, 8 epilogue warps
+constexpr int TC_TSTRIDE = 36;          // fp32 row stride of the epilogue transpose tiles (conflict-free float4)
+constexpr int TC_EPI_SMEM = 8 * 32 * TC_TSTRIDE * 4;
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -114,11 +116,11 @@ struct TcCfg {
   static constexpr int A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;   // 16 KB
   static constexpr int B_BYTES = BLOCK_N * TC_BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES < 8 ? (200 * 1024) / STAGE_BYTES : 8;
+  static constexpr int STAGES = (160 * 1024) / STAGE_BYTES < 8 ? (160 * 1024) / STAGE_BYTES : 8;
   static constexpr int ACC_STAGES = 2;                           // double-buffered accumulator in TMEM
   static constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N <= 32 ? 32 : ACC_STAGES * BLOCK_N <= 64 ? 64
                                    : ACC_STAGES * BLOCK_N <= 128 ? 128 : ACC_STAGES * BLOCK_N <= 256 ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + TC_EPI_SMEM;
   static_assert(ACC_STAGES * BLOCK_N <= 512, "accumulator stages exceed TMEM");
   static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024-byte alignment for the 128B swizzle");
 };
@@ -156,7 +158,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
     }
     for (int s = 0; s < Cfg::ACC_STAGES; ++s) {
       mbar_init(tmem_full_bar + s, 1);
-      mbar_init(tmem_empty_bar + s, 4);      // one arrive per epilogue warp
+      mbar_init(tmem_empty_bar + s, 8);      // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -219,81 +221,89 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
       }
     }
   } else {
-    // ---------------- epilogue: TMEM -> registers -> global ----------------
+    // ---------------- epilogue: TMEM -> registers -> smem transpose -> coalesced global ----------------
+    // 8 warps; warps e and e+4 share a TMEM lane quarter and alternate over the 32-column chunks.  The
+    // tcgen05.ld layout is row-per-thread; a 32x32 fp32 transpose through a private, padded smem tile turns
+    // every global access (residual read, positional table read, output write) into full 128-byte rows.
+    const int e = warp - 2;                   // 0..7
     const int q = warp & 3;                   // TMEM lane quarter this warp may access
-    const bool vec_ok = (N % 8 == 0) && (ldc % 8 == 0) && (!(epi.flags & EPI_RESIDUAL) || (epi.ldr % 4 == 0));
+    const int hsel = e >> 2;                  // chunk parity handled by this warp
+    float* tbuf = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256) + e * (32 * TC_TSTRIDE);
+    const int rsub = lane >> 3, g4 = (lane & 7) * 4;
+    const bool vec_ok = (N % 4 == 0) && (ldc % 4 == 0) && (!(epi.flags & EPI_RESIDUAL) || (epi.ldr % 4 == 0));
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
       const int row0 = (tile / n_tiles) * TC_BLOCK_M, col0 = (tile % n_tiles) * BLOCK_N;
       const int as = tcount % Cfg::ACC_STAGES;
       const uint32_t aph = (tcount / Cfg::ACC_STAGES) & 1;
       const int r = row0 + q * 32 + lane;
-      const bool row_ok = r < m_eff;
-      EpiRow er;
-      er.crow = -1; er.rrow = 0; er.trow = 0;
-      if (row_ok) er = epi_row(epi, r);
+      int my_crow = -1, my_rrow = 0;
+      if (r < m_eff) {
+        const EpiRow er = epi_row(epi, r);
+        my_crow = (int)er.crow; my_rrow = (int)er.rrow;
+      }
+      int crow[8], rrow[8];                   // rows this lane stores in the transposed pass: 4*it + rsub
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        crow[it] = __shfl_sync(0xffffffffu, my_crow, it * 4 + rsub);
+        rrow[it] = __shfl_sync(0xffffffffu, my_rrow, it * 4 + rsub);
+      }
       mbar_wait(tmem_full_bar + as, aph);
       tcgen05_fence_after();
       const uint32_t tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      for (int ch = hsel; ch < BLOCK_N / 32; ch += 2) {
+        const int cbase = col0 + ch * 32;
         uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_acc + (uint32_t)c0, v);
-        const int cbase = col0 + c0;
-        const bool do_store = row_ok && er.crow >= 0 && cbase < N;
-        TC* crow_ptr = C + (do_store ? er.crow : 0) * ldc;
-        if (!do_store) {
-          // nothing to write for this row / column chunk
-        } else if (vec_ok) {
+        tmem_ld_32x32b_x32(tmem_acc + (uint32_t)(ch * 32), v);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {          // 8 columns per step: one 16-byte (bf16) or two 16-byte (fp32) stores
-            const int c = cbase + g * 8;
-            if (c >= N) break;
-            float o[8];
+        for (int g = 0; g < 8; ++g)
+          *reinterpret_cast<float4*>(tbuf + lane * TC_TSTRIDE + 4 * g) =
+              make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]),
+                          __uint_as_float(v[4 * g + 3]));
+        __syncwarp();
+        if (vec_ok) {
+          const int c = cbase + g4;
+          const bool col_ok = c < N;
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (epi.bias && col_ok) b4 = *reinterpret_cast<const float4*>(epi.bias + c);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v[8 * g + i]);
-            if (epi.bias) {
-              const float4 b0 = *reinterpret_cast<const float4*>(epi.bias + c);
-              const float4 b1 = *reinterpret_cast<const float4*>(epi.bias + c + 4);
-              o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w;
-              o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
-            }
-            if (epi.flags & EPI_RELU) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) o[i] = fmaxf(o[i], 0.f);
-            }
+          for (int it = 0; it < 8; ++it) {
+            if (!col_ok || crow[it] < 0) continue;
+            const float4 a = *reinterpret_cast<const float4*>(tbuf + (it * 4 + rsub) * TC_TSTRIDE + g4);
+            float o0 = a.x + b4.x, o1 = a.y + b4.y, o2 = a.z + b4.z, o3 = a.w + b4.w;
+            if (epi.flags & EPI_RELU) { o0 = fmaxf(o0, 0.f); o1 = fmaxf(o1, 0.f); o2 = fmaxf(o2, 0.f); o3 = fmaxf(o3, 0.f); }
             if (epi.flags & EPI_RESIDUAL) {
-              const float* rp = epi.res + er.rrow * epi.ldr + c;
-              const float4 t0 = *reinterpret_cast<const float4*>(rp), t1 = *reinterpret_cast<const float4*>(rp + 4);
-              o[0] += t0.x; o[1] += t0.y; o[2] += t0.z; o[3] += t0.w;
-              o[4] += t1.x; o[5] += t1.y; o[6] += t1.z; o[7] += t1.w;
+              const float4 t = *reinterpret_cast<const float4*>(epi.res + (long long)rrow[it] * epi.ldr + c);
+              o0 += t.x; o1 += t.y; o2 += t.z; o3 += t.w;
             }
             if (epi.flags & EPI_ROWTABLE) {
-              const float* tp = epi.table + (long long)er.trow * N + c;
-              const float4 t0 = *reinterpret_cast<const float4*>(tp), t1 = *reinterpret_cast<const float4*>(tp + 4);
-              o[0] += t0.x; o[1] += t0.y; o[2] += t0.z; o[3] += t0.w;
-              o[4] += t1.x; o[5] += t1.y; o[6] += t1.z; o[7] += t1.w;
+              const float4 t = *reinterpret_cast<const float4*>(epi.table + (long long)(crow[it] % epi.table_period) * N + c);
+              o0 += t.x; o1 += t.y; o2 += t.z; o3 += t.w;
             }
+            TC* dst = C + (long long)crow[it] * ldc + c;
             if constexpr (sizeof(TC) == 4) {
-              *reinterpret_cast<float4*>(crow_ptr + c) = make_float4(o[0], o[1], o[2], o[3]);
-              *reinterpret_cast<float4*>(crow_ptr + c + 4) = make_float4(o[4], o[5], o[6], o[7]);
+              *reinterpret_cast<float4*>(dst) = make_float4(o0, o1, o2, o3);
             } else {
-              __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
-              __nv_bfloat162 p2 = __floats2bfloat162_rn(o[4], o[5]), p3 = __floats2bfloat162_rn(o[6], o[7]);
-              uint4 pk;
+              __nv_bfloat162 p0 = __floats2bfloat162_rn(o0, o1), p1 = __floats2bfloat162_rn(o2, o3);
+              uint2 pk;
               pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
-              pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
-              *reinterpret_cast<uint4*>(crow_ptr + c) = pk;
+              *reinterpret_cast<uint2*>(dst) = pk;
             }
           }
         } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int c = cbase + i;
-            if (c < N) store_out(crow_ptr + c, epi_value(epi, er, __uint_as_float(v[i]), c, N));
+          // generic path (e.g. the 51-wide heads): lane == column, one row per step
+          const int c = cbase + lane;
+#pragma unroll 4
+          for (int it = 0; it < 32; ++it) {
+            const int cr = __shfl_sync(0xffffffffu, my_crow, it), rr = __shfl_sync(0xffffffffu, my_rrow, it);
+            if (cr < 0 || c >= N) continue;
+            EpiRow er;
+            er.crow = cr; er.rrow = rr; er.trow = (epi.flags & EPI_ROWTABLE) ? cr % epi.table_period : 0;
+            store_out(C + (long long)cr * ldc + c, epi_value(epi, er, tbuf[it * TC_TSTRIDE + lane], c, N));
           }
         }
-        __syncwarp();   // reconverge before the next warp-collective tcgen05.ld
+        __syncwarp();   // the transpose tile is reused by the next chunk; also reconverges before tcgen05.ld
       }
       // all TMEM reads of this warp are complete (tcgen05.wait::ld): hand the accumulator back to the MMA warp
       tcgen05_fence_before();
