@@ -103,6 +103,11 @@ cudaError_t launch_token_fill(const uint8_t* mask, int rows, int n_tok, int d, c
 cudaError_t launch_layernorm(float* x, int rows, int d, const float* gamma, const float* beta, float eps,
                              const float* table, int period, void* y, int y_bf16, cudaStream_t st);
 
+// bf16 path: v = xsrc[map(r)] + upd[r]; xcast = bf16(v) (opt); v += table[r % period] (opt); xdst = v; y = LN(v) (opt)
+cudaError_t launch_residual_ln(const float* xsrc, const RowMap& smap, const bf16* upd, float* xdst, int rows, int d,
+                               const float* gamma, const float* beta, float eps, const float* table, int period,
+                               bf16* y, bf16* xcast, cudaStream_t st);
+
 // fp32 -> bf16 copy of n elements (n % 4 == 0): operand cast for the tensor-core heads
 cudaError_t launch_cast_bf16(const float* x, bf16* y, long long n, cudaStream_t st);
 

@@ -66,7 +66,7 @@ struct uu_model {
   int cap_B = 0;
   int ws_precision = -1;
   int *g_scratch = nullptr, *g_list = nullptr, *g_count = nullptr;
-  void *S = nullptr, *Y = nullptr, *QKV = nullptr, *O = nullptr, *Hd = nullptr;
+  void *S = nullptr, *Y = nullptr, *QKV = nullptr, *O = nullptr, *Hd = nullptr, *P = nullptr;
   float* X = nullptr;
   std::vector<float*> Xs;      // strided stream after block i: [cap_B * seq_lens[i+1], d]
   std::vector<void*> Hp;       // zero-padded conv inputs: [cap_B * Lo*s, h]
@@ -278,6 +278,7 @@ static int ensure_workspace(uu_model* m, int B) {
   if (dev_alloc(m->ws_allocs, &m->QKV, es * R * 3 * dt, true)) return 1;
   if (dev_alloc(m->ws_allocs, &m->O, es * R * dt, true)) return 1;
   if (dev_alloc(m->ws_allocs, &m->Hd, es * R * ht, true)) return 1;
+  if (m->precision == UU_PRECISION_BF16 && dev_alloc(m->ws_allocs, &m->P, es * R * dt, true)) return 1;
   for (int i = 0; i < s.n_strided; ++i) {
     const size_t Lo = m->seq_lens[i + 1];
     if (dev_alloc(m->ws_allocs, &p, 4 * (size_t)cap * Lo * dt, true)) return 1;
@@ -369,6 +370,106 @@ static int run_forward(uu_model* m, const float* x2d, const uint8_t* mask, int B
   if (rc) drop_plans(m);   // never keep a half-built plan list
   return rc;
 }
+// ---- bf16 schedule --------------------------------------------------------------------------------
+// Every dense contraction is a tcgen05 GEMM with bf16 operands and a bf16 result; the fp32 residual
+// stream is touched only by the streaming residual+LayerNorm kernel (one read, one write per half block).
+static int tc_gemm_bf16(Fwd& f, const void* A, long long lda, int M, int K, const Pack& pk, int N, const float* bias,
+                        bool relu, void* C, long long ldc, const RowMap* cmap = nullptr) {
+  Epilogue e;
+  e.bias = bias; e.flags = relu ? EPI_RELU : 0;
+  if (cmap) e.cmap = *cmap;
+  return gemm(f, A, lda, M, K, nullptr, pk, N, e, C, 1, ldc);
+}
+
+static int run_forward_bf16(Fwd& f, const float* x2d, const uint8_t* mask, float* full, float* central) {
+  uu_model* m = f.m;
+  const uu_spec& s = m->spec;
+  cudaStream_t st = f.st;
+  const int B = f.B, N = s.n_tok, J = s.n_joints, ds = s.d_spatial, d = s.d_temporal, h = s.h_temporal;
+  const int R = B * N, H = s.num_heads, dh = d / H;
+  const bool use_mask = s.has_strided_input != 0;
+  const bool want_full = s.full_output && full;
+  bf16 *Y = (bf16*)m->Y, *QKV = (bf16*)m->QKV, *O = (bf16*)m->O, *Hd = (bf16*)m->Hd, *P = (bf16*)m->P;
+  const RowMap plain;
+
+  if (use_mask) UU_LAUNCH(f, UU_KIND_GATHER, 3, launch_build_gather(mask, B, N, m->g_scratch, m->g_list, m->g_count, st));
+  UU_LAUNCH(f, UU_KIND_SPATIAL, 1,
+            launch_spatial_tc(x2d, use_mask ? m->g_list : nullptr, use_mask ? m->g_count : nullptr, R, s.spatial_depth,
+                              m->sp_frags, m->sp_params, (bf16*)m->S, m->num_sms, st));
+  {  // S4 + T1: 544->384 GEMM scattered to token rows, + bias + temporal PE; then the upsampling-token fill
+    Epilogue e;
+    e.bias = W(m, "spatial_to_temporal_fc", 1);
+    e.flags = EPI_ROWTABLE; e.table = W(m, "temporal_pe", 0); e.table_period = N;
+    if (use_mask) { e.c_rowidx = m->g_list; e.m_dev = m->g_count; }
+    if (gemm(f, m->S, J * ds, R, J * ds, nullptr, m->p_s2t, d, e, m->X, 0, d)) return 1;
+    if (use_mask)
+      UU_LAUNCH(f, UU_KIND_TOKEN_FILL, 1,
+                launch_token_fill(mask, R, N, d, W(m, "strided_input_token_layer", 0), W(m, "temporal_pe", 0), m->X, st));
+  }
+  UU_LAUNCH(f, UU_KIND_LAYERNORM, 1,
+            launch_layernorm(m->X, R, d, m->tblocks[0].ln1_g, m->tblocks[0].ln1_b, 1e-5f, nullptr, 1, Y, 1, st));
+  for (int i = 0; i < s.temporal_depth; ++i) {
+    const BlockW& w = m->tblocks[i];
+    const uint8_t* km = (use_mask && i < s.first_strided_token_attention_layer) ? mask : nullptr;
+    if (tc_gemm_bf16(f, Y, d, R, d, w.p_qkv, 3 * d, w.bqkv, false, QKV, 3 * d)) return 1;
+    UU_LAUNCH(f, UU_KIND_ATTENTION, 1, launch_attention_tc(QKV, B, N, H, dh, km, N, O, st));
+    if (tc_gemm_bf16(f, O, d, R, d, w.p_proj, d, w.bp, false, P, d)) return 1;
+    UU_LAUNCH(f, UU_KIND_LAYERNORM, 1,
+              launch_residual_ln(m->X, plain, P, m->X, R, d, w.ln2_g, w.ln2_b, 1e-5f, nullptr, 1, Y, nullptr, st));
+    if (tc_gemm_bf16(f, Y, d, R, d, w.p_fc1, h, w.b1, true, Hd, h)) return 1;
+    if (tc_gemm_bf16(f, Hd, h, R, h, w.p_fc2, d, w.b2, false, P, d)) return 1;
+    if (i + 1 < s.temporal_depth) {
+      const BlockW& nx = m->tblocks[i + 1];
+      UU_LAUNCH(f, UU_KIND_LAYERNORM, 1,
+                launch_residual_ln(m->X, plain, P, m->X, R, d, nx.ln1_g, nx.ln1_b, 1e-5f, nullptr, 1, Y, nullptr, st));
+    } else {   // last temporal block: bf16 copy for the full-sequence head, then + PE_1 and LN1 of strided block 1
+      const BlockW& nx = m->sblocks[0];
+      UU_LAUNCH(f, UU_KIND_LAYERNORM, 1,
+                launch_residual_ln(m->X, plain, P, m->X, R, d, nx.ln1_g, nx.ln1_b, 1e-5f,
+                                   W(m, "strided_temporal_pe_1", 0), N, Y, want_full ? O : nullptr, st));
+    }
+  }
+  if (want_full) {   // T4
+    Epilogue e;
+    e.bias = W(m, "temporal_fc", 1);
+    if (gemm(f, O, d, R, d, nullptr, m->p_head1, 3 * J, e, full, 0, 3 * J)) return 1;
+  }
+  float* x_in = m->X;
+  for (int i = 0; i < s.n_strided; ++i) {   // Q1/Q2
+    const BlockW& w = m->sblocks[i];
+    const int L = m->seq_lens[i], Lo = m->seq_lens[i + 1], st_i = s.strides[i], pl = s.pad_left[i];
+    const int Rl = B * L, Ro = B * Lo;
+    if (tc_gemm_bf16(f, Y, d, Rl, d, w.p_qkv, 3 * d, w.bqkv, false, QKV, 3 * d)) return 1;
+    UU_LAUNCH(f, UU_KIND_ATTENTION, 1, launch_attention_tc(QKV, B, L, H, dh, nullptr, L, O, st));
+    if (tc_gemm_bf16(f, O, d, Rl, d, w.p_proj, d, w.bp, false, P, d)) return 1;
+    UU_LAUNCH(f, UU_KIND_LAYERNORM, 1,
+              launch_residual_ln(x_in, plain, P, x_in, Rl, d, w.ln2_g, w.ln2_b, 1e-5f, nullptr, 1, Y, nullptr, st));
+    RowMap cm;   // Conv1D k=1 + ReLU into the zero-padded layout [B, Lo*s, h]
+    cm.rpb = L; cm.batch_rows = Lo * st_i; cm.offset = pl; cm.step = 1;
+    if (tc_gemm_bf16(f, Y, d, Rl, d, w.p_fc1, h, w.b1, true, m->Hp[i], h, &cm)) return 1;
+    // strided Conv1D k=3 as an implicit GEMM over contiguous 3h-wide rows, s*h apart
+    if (tc_gemm_bf16(f, m->Hp[i], (long long)st_i * h, Ro, 3 * h, w.p_fc2, d, w.b2, false, P, d)) return 1;
+    RowMap idm;  // identity path x[b, c0 + t*s]
+    idm.rpb = Lo; idm.batch_rows = L; idm.offset = (st_i > 1 && pl == 0) ? 1 : 0; idm.step = st_i;
+    if (i + 1 < s.n_strided) {
+      const BlockW& nx = m->sblocks[i + 1];
+      UU_LAUNCH(f, UU_KIND_LAYERNORM, 1,
+                launch_residual_ln(x_in, idm, P, m->Xs[i], Ro, d, nx.ln1_g, nx.ln1_b, 1e-5f,
+                                   W(m, "strided_temporal_pe_" + std::to_string(i + 2), 0), Lo, Y, nullptr, st));
+    } else {
+      UU_LAUNCH(f, UU_KIND_LAYERNORM, 1,
+                launch_residual_ln(x_in, idm, P, m->Xs[i], Ro, d, nullptr, nullptr, 0.f, nullptr, 1, nullptr, O, st));
+    }
+    x_in = m->Xs[i];
+  }
+  {   // Q3
+    Epilogue e;
+    e.bias = W(m, "strided_temporal_fc", 1);
+    if (gemm(f, O, d, B, d, nullptr, m->p_head2, 3 * J, e, central, 0, 3 * J)) return 1;
+  }
+  return 0;
+}
+
 static int run_forward_impl(uu_model* m, const float* x2d, const uint8_t* mask, int B, float* full, float* central,
                             cudaStream_t st) {
   const uu_spec& s = m->spec;
@@ -387,6 +488,12 @@ static int run_forward_impl(uu_model* m, const float* x2d, const uint8_t* mask, 
   const int N = s.n_tok, J = s.n_joints, ds = s.d_spatial, d = s.d_temporal, h = s.h_temporal;
   const int R = B * N;
   const bool use_mask = s.has_strided_input != 0;
+  if (f.tc) {
+    if (run_forward_bf16(f, x2d, mask, full, central)) return 1;
+    m->plan_B = B; m->plan_full = want_full;
+    m->launches = f.launches;
+    return 0;
+  }
 
   // K1a: gather list of frames that carry a 2-D pose
   if (use_mask) {
