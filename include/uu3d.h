@@ -99,6 +99,28 @@ enum { UU_KIND_GATHER = 0, UU_KIND_SPATIAL, UU_KIND_TOKEN_FILL, UU_KIND_LAYERNOR
 int uu_set_profiling(uu_model* m, int on);
 int uu_get_profile(uu_model* m, float* ms_by_kind, int32_t* launches_by_kind, int n_kinds);
 
+/* ---- training step (train.py:464-506, optimizer train.py:403-415) -------------------------------
+ * uu_train_config      : BATCH_SIZE (the GLOBAL constant the losses are divided by), ROOT_KEYTPOINT,
+ *                        LOSS_WEIGHT_CENTER / _SEQUENCE, DROP_PATH_RATE[3]; droppath_mode 0 = off, 1 = on
+ *                        (counter-based RNG keyed by seed and step).
+ * uu_train_forward_backward : forward (training=True), loss, gradients of every trainable tensor into the
+ *                        flat gradient buffer.  gt3d: fp32 (B, n_tok, n_joints, 3) absolute key-points (root-
+ *                        centring happens inside, train.py:467).  loss_dev: device pointer to one float.
+ *                        Data-parallel: each rank passes its B_local windows; gradients combine by SUM.
+ * uu_grad_buffer       : flat fp32 gradient buffer (same layout as the parameters) for the all-reduce.
+ * uu_adamw_step        : tfa.optimizers.AdamW update with host-evaluated schedule values lr_t, wd_t and
+ *                        Adam step t = iterations + 1; ema_decay < 0 disables the EMA copy. */
+int uu_train_config(uu_model* m, int global_batch, int root_keypoint, float w_center, float w_sequence,
+                    const float* drop_path_rate3, int droppath_mode, uint64_t seed);
+int uu_train_forward_backward(uu_model* m, const float* x2d, const uint8_t* mask, const float* gt3d, int B,
+                              int64_t step, float* loss_dev, void* stream);
+int uu_grad_buffer(uu_model* m, float** dev_ptr, int64_t* n_floats);
+int uu_get_grad(uu_model* m, const char* group, int index, float* host, int64_t capacity);
+int uu_get_droppath_scale(uu_model* m, int stage, int block, float* host, int64_t capacity, float* keep_prob);
+int uu_adamw_step(uu_model* m, float lr_t, float wd_t, float beta1, float beta2, float epsilon, int64_t t,
+                  float ema_decay, void* stream);
+int uu_get_ema_weight(uu_model* m, const char* group, int index, float* host, int64_t capacity);
+
 /* Stride-mask rule (host, integer, bit-exact): mask[n] = ((n - n_tok/2)*s_out + shift) floor-mod s_in == 0.
  * shift = centre frame index (eval, global alignment) or rand_shift*s_out (training). */
 int uu_stride_mask(int n_tok, int s_out, int s_in, int64_t shift, uint8_t* mask_out);

@@ -1,0 +1,94 @@
+"""Training-step parity on the B200: loss, every gradient, and the weights after k AdamW steps against the
+torch-CPU autograd oracle (fp64 for gradients), stochastic depth included (the masks the library drew are fed
+to the oracle)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+from oracle import forward_torch as OT
+from oracle import train_torch as TT
+from uplift_upsample_3dhpe_b200 import UpliftUpsampleConfig, spec_from_config, stride_mask, weights
+from uplift_upsample_3dhpe_b200.model import build_uplift_upsample_transformer
+from uplift_upsample_3dhpe_b200.train import Trainer
+
+
+def _data(cfg, spec, B, seed=0):
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(-1, 1, (B, spec.n_tok, 17, 2)).astype(np.float32)
+    gt = rng.normal(0, 0.3, (B, spec.n_tok, 17, 3)).astype(np.float32)
+    m = stride_mask.batch_stride_masks_train(spec.n_tok, cfg.SEQUENCE_STRIDE, cfg.MASK_STRIDE, B, seed=0)
+    return x, gt, m
+
+
+def _rel(a, b):
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-12))
+
+
+@pytest.mark.parametrize("name,B,droppath", [("h36m_81", 6, False), ("h36m_351", 4, False), ("h36m_81", 5, True)])
+def test_loss_and_gradients_match_autograd(name, B, droppath):
+    cfg = UpliftUpsampleConfig.preset(name, BATCH_SIZE=B)
+    spec = spec_from_config(cfg)
+    w = weights.init_weights(spec, 1, perturb=True)
+    x, gt, m = _data(cfg, spec, B)
+    model = build_uplift_upsample_transformer(cfg, precision="fp32", weights=w)
+    tr = Trainer(model, cfg, droppath=droppath, seed=7)
+    loss = tr.forward_backward(torch.from_numpy(x).cuda(), torch.from_numpy(gt).cuda(), torch.from_numpy(m).cuda())
+    torch.cuda.synchronize()
+    keeps = None
+    if droppath:
+        raw = tr.droppath_keeps(B)
+        assert raw, "stochastic depth should be active"
+        keeps = {k: (kp, torch.tensor(mk, dtype=torch.float64)) for k, (kp, mk) in raw.items()}
+        assert all(set(np.unique(mk.numpy())) <= {0.0, 1.0} for _, mk in keeps.values())
+    ref_loss, ref_g = TT.loss_and_grads(spec, w, x, gt, m, B, keeps=keeps)
+    assert abs(float(loss.item()) - ref_loss) < 2e-5 * max(1.0, abs(ref_loss))
+    g = tr.get_grads()
+    worst = max((_rel(g[k], ref_g[k]), k) for k in ref_g)
+    print("worst relative gradient error", worst)
+    for k in ref_g:
+        assert _rel(g[k], ref_g[k]) < 2e-3, (k, _rel(g[k], ref_g[k]))
+    model.close()
+
+
+def test_three_adamw_steps_match_oracle():
+    cfg = UpliftUpsampleConfig.preset("h36m_81", BATCH_SIZE=4)
+    spec = spec_from_config(cfg)
+    w0 = weights.init_weights(spec, 1, perturb=True)
+    x, gt, m = _data(cfg, spec, 4)
+    model = build_uplift_upsample_transformer(cfg, precision="fp32", weights=w0)
+    tr = Trainer(model, cfg, droppath=False)
+    assert tr.ema_enabled and tr.ema_decay == 0.999          # h36m_81 enables EMA
+    xd, gd, md = torch.from_numpy(x).cuda(), torch.from_numpy(gt).cuda(), torch.from_numpy(m).cuda()
+    w = {k: v.astype(np.float64) for k, v in w0.items()}
+    am = {k: np.zeros_like(v) for k, v in w.items()}
+    av = {k: np.zeros_like(v) for k, v in w.items()}
+    ema = {k: v.copy() for k, v in w.items()}
+    sp = cfg.SCHEDULE_PARAMS
+    for it in range(3):
+        loss = tr.train_step(xd, gd, md)
+        ref_loss, g = TT.loss_and_grads(spec, w, x, gt, m, 4)
+        assert abs(float(loss.item()) - ref_loss) < 1e-4 * max(1.0, abs(ref_loss))
+        lr = TT.exponential_decay(sp["initial_learning_rate"], sp["decay_steps"], sp["decay_rate"], sp["staircase"], it)
+        wd = TT.exponential_decay(cfg.WEIGHT_DECAY, sp["decay_steps"], sp["decay_rate"], sp["staircase"], it)
+        TT.adamw_step(w, g, am, av, lr, wd, it + 1)
+        TT.ema_update(ema, w, min(0.999, (1 + it) / (10 + it)))
+    torch.cuda.synchronize()
+    got, got_ema = model.get_weights(), tr.get_ema_weights()
+    # a step moves each weight by ~lr = 4e-5; compare the total displacement
+    for k in w:
+        dw_ref, dw = w[k] - w0[k], got[k] - w0[k]
+        assert np.abs(dw - dw_ref).max() < 0.05 * np.abs(dw_ref).max() + 1e-7, k
+        assert np.abs(got_ema[k] - ema[k]).max() < 1e-5, k
+    # the inference path sees the updated weights (derived bf16/fused copies are refreshed)
+    f, c = model([xd, md])
+    rf, rc = OT.test_step(spec, OT.to_torch(got, torch.float64), torch.tensor(x, dtype=torch.float64), torch.tensor(m))
+    assert np.abs(c.cpu().numpy() - rc.numpy()).max() < 1e-4
+    model.close()
+
+
+def test_lr_and_wd_schedules():
+    from uplift_upsample_3dhpe_b200.train import scheduler_by_name
+    s = scheduler_by_name("ExponentialDecay")(initial_learning_rate=4e-5, decay_steps=6000, decay_rate=0.99, staircase=True)
+    assert s(0) == 4e-5 and s(5999) == 4e-5 and abs(s(6000) - 4e-5 * 0.99) < 1e-18 and abs(s(12001) - 4e-5 * 0.99 ** 2) < 1e-18

@@ -16,7 +16,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libuu3d.so")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
-SOURCES = ["kernels_f32.cu", "spatial_tc.cu", "attention_tc.cu", "gemm_tc.cu", "uu_api.cu"]
+SOURCES = ["kernels_f32.cu", "spatial_tc.cu", "attention_tc.cu", "gemm_tc.cu", "train_kernels.cu", "uu_train.cu",
+           "uu_api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "550,177"]
 
@@ -97,6 +98,13 @@ def _declare(lib) -> None:
     lib.uu_last_launch_count.argtypes = [c_void_p]
     lib.uu_set_profiling.argtypes = [c_void_p, c_int]
     lib.uu_get_profile.argtypes = [c_void_p, c_void_p, c_void_p, c_int]
+    lib.uu_train_config.argtypes = [c_void_p, c_int, c_int, c_float, c_float, P(c_float), c_int, ctypes.c_uint64]
+    lib.uu_train_forward_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p]
+    lib.uu_grad_buffer.argtypes = [c_void_p, P(c_void_p), P(c_int64)]
+    lib.uu_get_grad.argtypes = [c_void_p, c_char_p, c_int, c_void_p, c_int64]
+    lib.uu_get_droppath_scale.argtypes = [c_void_p, c_int, c_int, c_void_p, c_int64, P(c_float)]
+    lib.uu_adamw_step.argtypes = [c_void_p, c_float, c_float, c_float, c_float, c_float, c_int64, c_float, c_void_p]
+    lib.uu_get_ema_weight.argtypes = [c_void_p, c_char_p, c_int, c_void_p, c_int64]
     lib.uu_stride_mask.argtypes = [c_int, c_int, c_int, c_int64, c_void_p]
     lib.uu_op_build_gather.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.uu_op_token_fill.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
@@ -116,6 +124,8 @@ EXPORTS = [
     "uu_last_error", "uu_version", "uu_create", "uu_destroy", "uu_set_precision", "uu_get_precision",
     "uu_weight_count", "uu_param_count", "uu_weight_info", "uu_set_weight", "uu_get_weight",
     "uu_forward", "uu_forward_host", "uu_last_launch_count", "uu_set_profiling", "uu_get_profile", "uu_stride_mask",
+    "uu_train_config", "uu_train_forward_backward", "uu_grad_buffer", "uu_get_grad", "uu_get_droppath_scale",
+    "uu_adamw_step", "uu_get_ema_weight",
     "uu_op_build_gather", "uu_op_token_fill", "uu_op_layernorm", "uu_op_attention", "uu_op_gemm_f32",
     "uu_op_gemm_bf16",
 ]

@@ -643,6 +643,7 @@ cudaError_t launch_attention(const void* qkv, int is_bf16, int B, int S, int hea
   case DHV:               \
     return attn_dispatch<DHV, float>(qkv, B, S, heads, mask, mask_stride, out, st);
   switch (dh) {
+    UU_ATTN_CASE(4)
     UU_ATTN_CASE(16)
     UU_ATTN_CASE(32)
     UU_ATTN_CASE(48)

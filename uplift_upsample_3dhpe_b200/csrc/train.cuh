@@ -1,0 +1,54 @@
+// Declarations of the training-step kernels (train_kernels.cu).
+#pragma once
+#include "common.cuh"
+
+namespace uu {
+
+struct GemmGen {
+  const float* A = nullptr; long long lda = 0; int transA = 0; RowMap amap;   // amap only when !transA
+  const float* B = nullptr; long long ldb = 0; int transB = 0;
+  float* C = nullptr; long long ldc = 0; RowMap cmap;
+  int M = 0, N = 0, K = 0;
+  const float* bias = nullptr;   // forward only
+  int relu = 0;                  // forward only
+  int accumulate = 0;            // C += ...
+  int split_k = 1;               // > 1: fp32 atomics into C (requires accumulate)
+};
+cudaError_t launch_gemm_gen(const GemmGen& g, cudaStream_t st);
+cudaError_t launch_colsum(const float* Y, int M, int N, long long ld, float* out, cudaStream_t st);
+cudaError_t launch_period_sum(const float* X, long long rows, int period, int d, const uint8_t* rowmask, int want,
+                              float* out, cudaStream_t st);
+cudaError_t launch_ln_fwd_gen(const float* x, long long rows, int d, const float* gamma, const float* beta, float eps,
+                              float* y, cudaStream_t st);
+cudaError_t launch_ln_bwd_gen(const float* x, const float* dy, long long rows, int d, const float* gamma, float eps,
+                              float* dx, int accumulate, float* dgamma, float* dbeta, cudaStream_t st);
+cudaError_t launch_attention_bwd(const float* qkv, const float* dO, long long B, int S, int heads, int dh,
+                                 const uint8_t* mask, int mask_stride, float* dqkv, cudaStream_t st);
+cudaError_t launch_act_fwd(const float* pre, long long n, int act, float* out, cudaStream_t st);
+cudaError_t launch_act_bwd(const float* pre, const float* dout, const RowMap& dmap, long long ldd, long long rows,
+                           int cols, int act, float* dpre, cudaStream_t st);
+cudaError_t launch_act_bwd_mapped(const float* hp, const float* dhp, const RowMap& map, long long ld, long long rows,
+                                  int cols, float* dpre, cudaStream_t st);
+cudaError_t launch_residual(const float* base, const RowMap& bmap, const float* y, const float* scale,
+                            int rows_per_sample, const float* table, int period, long long rows, int d, float* out,
+                            cudaStream_t st);
+cudaError_t launch_scale_rows(const float* src, const float* scale, int rps, long long rows, int d, float* dst,
+                              cudaStream_t st);
+cudaError_t launch_scatter_add(const float* src, const RowMap& dmap, long long rows, int d, float* dst, cudaStream_t st);
+cudaError_t launch_embed_fwd(const float* x2d, const uint8_t* mask, int J, long long rows, int d, const float* Wk,
+                             const float* b, const float* pe, float* out, cudaStream_t st);
+cudaError_t launch_embed_wgrad(const float* x2d, const uint8_t* mask, int J, const float* de, long long rows, int d,
+                               float* dW, cudaStream_t st);
+cudaError_t launch_fill_fwd(const float* s, const uint8_t* mask, const float* token, const float* pe, int n_tok,
+                            long long rows, int d, float* x, cudaStream_t st);
+cudaError_t launch_fill_bwd(const float* dx, const uint8_t* mask, long long rows, int d, float* ds, cudaStream_t st);
+int loss_blocks(int B, int n_tok, int J, bool has_full);
+cudaError_t launch_loss(const float* full, const float* central, const float* gt, int B, int n_tok, int J, int root,
+                        float w_seq, float w_cen, float* dfull, float* dcentral, float* partials, float* loss,
+                        cudaStream_t st);
+cudaError_t launch_droppath_scale(unsigned long long seed, unsigned long long stream, long long n, float keep,
+                                  float* scale, cudaStream_t st);
+cudaError_t launch_adamw(float* p, float* m, float* v, const float* g, long long n, float wd, float alpha, float b1,
+                         float b2, float eps, float* ema, float ema_decay, cudaStream_t st);
+
+}  // namespace uu

@@ -1,0 +1,703 @@
+// Kernels of the training step (train.py:464-506): generic fp32 GEMM with transposed operands and
+// split-K (dgrad / wgrad), reductions for bias / positional-encoding / token gradients, LayerNorm,
+// attention and activation backward, the MPJPE loss with its gradient, stochastic depth, and the fused
+// multi-tensor AdamW (tfa.optimizers.AdamW semantics) + EMA update.
+// The reference relies on TensorFlow autodiff for all of this; every formula below
+// is the hand-derived adjoint of the forward op it names.
+#include <algorithm>
+
+#include "common.cuh"
+#include "train.cuh"
+
+namespace uu {
+
+__device__ __forceinline__ float warp_sum_t(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// =================================================================================================
+// Generic fp32 GEMM: C[crow(r)][n] (+)= sum_k opA(r,k) * opB(k,n)   (+ bias[n])
+//   opA(r,k) = TA ? A[k*lda + r] : A[arow(r)*lda + k]   (arow via RowMap, dropped rows read as 0)
+//   opB(k,n) = TB ? B[n*ldb + k] : B[k*ldb + n]
+//   split-K over gridDim.z with fp32 atomics (C must be pre-initialised; used for weight gradients).
+// =================================================================================================
+constexpr int GG_M = 64, GG_N = 64, GG_K = 16;
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) k_gemm_gen(GemmGen g) {
+  __shared__ __align__(16) float As[GG_K][GG_M + 4];
+  __shared__ __align__(16) float Bs[GG_K][GG_N + 4];
+  const int row0 = blockIdx.x * GG_M, col0 = blockIdx.y * GG_N;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int kchunk = (((g.K + gridDim.z - 1) / gridDim.z) + GG_K - 1) / GG_K * GG_K;
+  const int kbeg = blockIdx.z * kchunk, kend = min(g.K, kbeg + kchunk);
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = kbeg; k0 < kend; k0 += GG_K) {
+    if constexpr (!TA) {
+      const int a_row = tid >> 2, a_k = (tid & 3) * 4;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      const int r = row0 + a_row, k = k0 + a_k;
+      if (r < g.M && k < kend) {
+        const long long ar = map_row(g.amap, r);
+        if (ar >= 0) {
+          const float* src = g.A + ar * g.lda + k;
+          if (k + 3 < kend) {
+            const float4 t = *reinterpret_cast<const float4*>(src);
+            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+          } else {
+            for (int i = 0; i < 4 && k + i < kend; ++i) v[i] = src[i];
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) As[a_k + i][a_row] = v[i];
+    } else {
+      const int kk = tid >> 4, r4 = (tid & 15) * 4;
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int k = k0 + kk, r = row0 + r4;
+      if (k < kend && r < g.M) {
+        const float* src = g.A + (long long)k * g.lda + r;
+        if (r + 3 < g.M) t = *reinterpret_cast<const float4*>(src);
+        else { t.x = src[0]; if (r + 1 < g.M) t.y = src[1]; if (r + 2 < g.M) t.z = src[2]; }
+      }
+      *reinterpret_cast<float4*>(&As[kk][r4]) = t;
+    }
+    if constexpr (!TB) {
+      const int b_k = tid >> 4, b_n = (tid & 15) * 4;
+      const int k = k0 + b_k;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int n = col0 + b_n + i;
+        Bs[b_k][b_n + i] = (k < kend && n < g.N) ? g.B[(long long)k * g.ldb + n] : 0.f;
+      }
+    } else {
+      const int n_l = tid >> 2, k4 = (tid & 3) * 4;
+      const int n = col0 + n_l, k = k0 + k4;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (n < g.N) {
+        const float* src = g.B + (long long)n * g.ldb + k;
+        for (int i = 0; i < 4; ++i)
+          if (k + i < kend) v[i] = src[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) Bs[k4 + i][n_l] = v[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GG_K; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = row0 + ty * 4 + i;
+    if (r >= g.M) continue;
+    const long long cr = map_row(g.cmap, r);
+    if (cr < 0) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = col0 + tx * 4 + j;
+      if (c >= g.N) continue;
+      float v = acc[i][j];
+      float* dst = g.C + cr * g.ldc + c;
+      if (gridDim.z > 1) {
+        atomicAdd(dst, v);
+      } else {
+        if (g.bias) v += g.bias[c];
+        if (g.relu) v = fmaxf(v, 0.f);
+        *dst = g.accumulate ? *dst + v : v;
+      }
+    }
+  }
+}
+
+cudaError_t launch_gemm_gen(const GemmGen& g, cudaStream_t st) {
+  if (g.M == 0 || g.N == 0 || g.K == 0) return cudaSuccess;
+  if (!g.transA && (g.lda % 4)) return cudaErrorInvalidValue;
+  if (g.transA && (g.lda % 4)) return cudaErrorInvalidValue;
+  int splits = g.split_k < 1 ? 1 : g.split_k;
+  if (splits > 1 && (g.bias || g.relu || !g.accumulate)) return cudaErrorInvalidValue;
+  dim3 grid((g.M + GG_M - 1) / GG_M, (g.N + GG_N - 1) / GG_N, splits);
+  if (g.transA) {
+    if (g.transB) k_gemm_gen<true, true><<<grid, 256, 0, st>>>(g);
+    else k_gemm_gen<true, false><<<grid, 256, 0, st>>>(g);
+  } else {
+    if (g.transB) k_gemm_gen<false, true><<<grid, 256, 0, st>>>(g);
+    else k_gemm_gen<false, false><<<grid, 256, 0, st>>>(g);
+  }
+  return cudaGetLastError();
+}
+
+// out[n] += sum_r Y[r*ld + n]   (bias gradients)
+__global__ void k_colsum(const float* __restrict__ Y, int M, int N, long long ld, float* __restrict__ out) {
+  const int n = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int rl = threadIdx.x >> 5, nr = blockDim.x >> 5;
+  const int rows_per = (M + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
+  float s = 0.f;
+  if (n < N)
+    for (int r = r0 + rl; r < r1; r += nr) s += Y[(long long)r * ld + n];
+  __shared__ float sm[8][33];
+  sm[rl][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (rl == 0 && n < N) {
+    for (int i = 1; i < nr; ++i) s += sm[i][threadIdx.x & 31];
+    atomicAdd(out + n, s);
+  }
+}
+cudaError_t launch_colsum(const float* Y, int M, int N, long long ld, float* out, cudaStream_t st) {
+  if (M == 0 || N == 0) return cudaSuccess;
+  dim3 grid((N + 31) / 32, std::max(1, std::min(256, M / 64)));
+  k_colsum<<<grid, 256, 0, st>>>(Y, M, N, ld, out);
+  return cudaGetLastError();
+}
+
+// out[(r % period)*d + c] += X[r*d + c]  (positional-encoding gradients: sum over the batch);
+// with `rowmask`: only rows where (rowmask[r] != 0) == want are summed (upsampling-token gradient uses period 1).
+__global__ void k_period_sum(const float* __restrict__ X, long long rows, int period, int d,
+                             const uint8_t* __restrict__ rowmask, int want, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = blockIdx.y;
+  if (c >= d) return;
+  const long long nb = rows / period;
+  const long long b0 = (long long)blockIdx.z * ((nb + gridDim.z - 1) / gridDim.z);
+  const long long b1 = min(nb, b0 + (nb + gridDim.z - 1) / gridDim.z);
+  float s = 0.f;
+  for (long long b = b0; b < b1; ++b) {
+    const long long r = b * period + p;
+    if (rowmask && ((rowmask[r] != 0) != (want != 0))) continue;
+    s += X[r * d + c];
+  }
+  atomicAdd(out + (long long)p * d + c, s);
+}
+cudaError_t launch_period_sum(const float* X, long long rows, int period, int d, const uint8_t* rowmask, int want,
+                              float* out, cudaStream_t st) {
+  if (rows == 0) return cudaSuccess;
+  const int bx = d >= 128 ? 128 : 32;
+  const long long nb = rows / period;
+  dim3 grid((d + bx - 1) / bx, period, (unsigned)std::max<long long>(1, std::min<long long>(64, nb / 32)));
+  k_period_sum<<<grid, bx, 0, st>>>(X, rows, period, d, rowmask, want, out);
+  return cudaGetLastError();
+}
+
+// =================================================================================================
+// LayerNorm forward / backward for any width d (one warp per row).
+//   y = (x - mean) * rstd * gamma + beta ;  dx = rstd * (dyg - mean(dyg) - xhat * mean(dyg * xhat)), dyg = dy*gamma
+//   dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy.  dx is added to `dx_acc` when accumulate != 0.
+// =================================================================================================
+__global__ void k_ln_fwd_gen(const float* __restrict__ x, long long rows, int d, const float* __restrict__ gamma,
+                             const float* __restrict__ beta, float eps, float* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + row * d;
+  float s = 0.f;
+  for (int c = lane; c < d; c += 32) s += xr[c];
+  const float mean = warp_sum_t(s) / d;
+  float q = 0.f;
+  for (int c = lane; c < d; c += 32) { const float t = xr[c] - mean; q += t * t; }
+  const float rstd = rsqrtf(warp_sum_t(q) / d + eps);
+  float* yr = y + row * d;
+  for (int c = lane; c < d; c += 32) {
+    const float inv = gamma[c] * rstd;
+    yr[c] = xr[c] * inv + (beta[c] - mean * inv);
+  }
+}
+cudaError_t launch_ln_fwd_gen(const float* x, long long rows, int d, const float* gamma, const float* beta, float eps,
+                              float* y, cudaStream_t st) {
+  if (rows == 0) return cudaSuccess;
+  k_ln_fwd_gen<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, rows, d, gamma, beta, eps, y);
+  return cudaGetLastError();
+}
+
+__global__ void k_ln_bwd_gen(const float* __restrict__ x, const float* __restrict__ dy, long long rows, int d,
+                             const float* __restrict__ gamma, float eps, float* __restrict__ dx, int accumulate,
+                             float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  extern __shared__ float sm[];            // [2][d] per-block partial dgamma / dbeta
+  float* sg = sm;
+  float* sb = sm + d;
+  for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) sm[c] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * wpb) {
+    const float* xr = x + row * d;
+    const float* dyr = dy + row * d;
+    float s = 0.f;
+    for (int c = lane; c < d; c += 32) s += xr[c];
+    const float mean = warp_sum_t(s) / d;
+    float q = 0.f;
+    for (int c = lane; c < d; c += 32) { const float t = xr[c] - mean; q += t * t; }
+    const float rstd = rsqrtf(warp_sum_t(q) / d + eps);
+    float m1 = 0.f, m2 = 0.f;
+    for (int c = lane; c < d; c += 32) {
+      const float xh = (xr[c] - mean) * rstd, g = dyr[c] * gamma[c];
+      m1 += g; m2 += g * xh;
+    }
+    m1 = warp_sum_t(m1) / d; m2 = warp_sum_t(m2) / d;
+    float* dxr = dx + row * d;
+    for (int c = lane; c < d; c += 32) {
+      const float xh = (xr[c] - mean) * rstd, g = dyr[c] * gamma[c];
+      const float v = rstd * (g - m1 - xh * m2);
+      dxr[c] = accumulate ? dxr[c] + v : v;
+      atomicAdd(sg + c, dyr[c] * xh);
+      atomicAdd(sb + c, dyr[c]);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    atomicAdd(dgamma + c, sg[c]);
+    atomicAdd(dbeta + c, sb[c]);
+  }
+}
+cudaError_t launch_ln_bwd_gen(const float* x, const float* dy, long long rows, int d, const float* gamma, float eps,
+                              float* dx, int accumulate, float* dgamma, float* dbeta, cudaStream_t st) {
+  if (rows == 0) return cudaSuccess;
+  const unsigned grid = (unsigned)std::min<long long>((rows + 7) / 8, 148 * 8);
+  k_ln_bwd_gen<<<grid, 256, 2 * d * sizeof(float), st>>>(x, dy, rows, d, gamma, eps, dx, accumulate, dgamma, dbeta);
+  return cudaGetLastError();
+}
+
+// =================================================================================================
+// Attention backward per (sample, head), S <= 128, thread == query row, then thread == key row.
+//   A = softmax(q k^T * scale + keyterm) (recomputed); dV = A^T dO; dA = dO V^T;
+//   dS = A o (dA - rowsum(dA o A)); dQ = dS K * scale; dK = dS^T Q * scale.   (vit:99-130)
+// qkv / dqkv rows are [q | k | v] (3*d); dO rows are d wide (merged heads).
+// =================================================================================================
+template <int DH>
+__global__ void __launch_bounds__(128) k_attention_bwd(const float* __restrict__ qkv, const float* __restrict__ dO,
+                                                       int S, int heads, const uint8_t* __restrict__ mask,
+                                                       int mask_stride, float* __restrict__ dqkv) {
+  extern __shared__ __align__(16) float sm[];
+  float* Qs = sm;                  // [S][DH]
+  float* Ks = Qs + S * DH;
+  float* Vs = Ks + S * DH;
+  float* Gs = Vs + S * DH;         // dO
+  float* Km = Gs + S * DH;         // [S]
+  float* As = Km + ((S + 3) & ~3); // [S][S+1]  attention weights
+  float* Ds = As + S * (S + 1);    // [S][S+1]  dS
+  const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
+  const int d = heads * DH;
+  const long long row0 = (long long)b * S;
+  for (int i = tid; i < S * DH; i += 128) {
+    const int j = i / DH, c = i - j * DH;
+    const float* r = qkv + (row0 + j) * 3 * d + h * DH + c;
+    Qs[i] = r[0]; Ks[i] = r[d]; Vs[i] = r[2 * d];
+    Gs[i] = dO[(row0 + j) * d + h * DH + c];
+  }
+  for (int j = tid; j < S; j += 128)
+    Km[j] = mask ? (1.0f - (mask[(long long)b * mask_stride + j] ? 1.0f : 0.0f)) * -1e9f : 0.0f;
+  __syncthreads();
+  const float scale = 1.0f / sqrtf((float)DH);
+  if (tid < S) {
+    const int i = tid;
+    float mx = -INFINITY;
+    for (int j = 0; j < S; ++j) {
+      float a = 0.f;
+#pragma unroll
+      for (int c = 0; c < DH; ++c) a = fmaf(Qs[i * DH + c], Ks[j * DH + c], a);
+      a = a * scale + Km[j];
+      As[i * (S + 1) + j] = a;
+      mx = fmaxf(mx, a);
+    }
+    float sum = 0.f;
+    for (int j = 0; j < S; ++j) { const float p = expf(As[i * (S + 1) + j] - mx); As[i * (S + 1) + j] = p; sum += p; }
+    const float inv = 1.f / sum;
+    float dot = 0.f;
+    for (int j = 0; j < S; ++j) {
+      const float p = As[i * (S + 1) + j] * inv;
+      float da = 0.f;
+#pragma unroll
+      for (int c = 0; c < DH; ++c) da = fmaf(Gs[i * DH + c], Vs[j * DH + c], da);
+      As[i * (S + 1) + j] = p;
+      Ds[i * (S + 1) + j] = da;
+      dot = fmaf(da, p, dot);
+    }
+    float dq[DH];
+#pragma unroll
+    for (int c = 0; c < DH; ++c) dq[c] = 0.f;
+    for (int j = 0; j < S; ++j) {
+      const float ds = As[i * (S + 1) + j] * (Ds[i * (S + 1) + j] - dot);
+      Ds[i * (S + 1) + j] = ds;
+#pragma unroll
+      for (int c = 0; c < DH; ++c) dq[c] = fmaf(ds, Ks[j * DH + c], dq[c]);
+    }
+    float* o = dqkv + (row0 + i) * 3 * d + h * DH;
+#pragma unroll
+    for (int c = 0; c < DH; ++c) o[c] = dq[c] * scale;
+  }
+  __syncthreads();
+  if (tid < S) {
+    const int j = tid;
+    float dk[DH], dv[DH];
+#pragma unroll
+    for (int c = 0; c < DH; ++c) { dk[c] = 0.f; dv[c] = 0.f; }
+    for (int i = 0; i < S; ++i) {
+      const float ds = Ds[i * (S + 1) + j], p = As[i * (S + 1) + j];
+#pragma unroll
+      for (int c = 0; c < DH; ++c) {
+        dk[c] = fmaf(ds, Qs[i * DH + c], dk[c]);
+        dv[c] = fmaf(p, Gs[i * DH + c], dv[c]);
+      }
+    }
+    float* o = dqkv + (row0 + j) * 3 * d + h * DH;
+#pragma unroll
+    for (int c = 0; c < DH; ++c) { o[d + c] = dk[c] * scale; o[2 * d + c] = dv[c]; }
+  }
+}
+
+cudaError_t launch_attention_bwd(const float* qkv, const float* dO, long long B, int S, int heads, int dh,
+                                 const uint8_t* mask, int mask_stride, float* dqkv, cudaStream_t st) {
+  if (B == 0) return cudaSuccess;
+  if (S < 1 || S > 128) return cudaErrorInvalidValue;
+  const size_t smem = sizeof(float) * (4 * S * dh + ((S + 3) & ~3) + 2 * S * (S + 1));
+  dim3 grid((unsigned)B, heads);
+#define UU_AB_CASE(DHV)                                                                                        \
+  case DHV: {                                                                                                  \
+    cudaError_t e = cudaFuncSetAttribute(k_attention_bwd<DHV>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                         (int)smem);                                                           \
+    if (e != cudaSuccess) return e;                                                                            \
+    k_attention_bwd<DHV><<<grid, 128, smem, st>>>(qkv, dO, S, heads, mask, mask_stride, dqkv);                 \
+    break;                                                                                                     \
+  }
+  switch (dh) {
+    UU_AB_CASE(4) UU_AB_CASE(16) UU_AB_CASE(32) UU_AB_CASE(48) UU_AB_CASE(64)
+    default: return cudaErrorInvalidValue;
+  }
+#undef UU_AB_CASE
+  return cudaGetLastError();
+}
+
+// =================================================================================================
+// Element-wise pieces
+// =================================================================================================
+// act: 0 = ReLU (uses the activation output), 1 = exact-erf GELU (uses the pre-activation)
+__global__ void k_act_fwd(const float* __restrict__ pre, long long n, int act, float* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = pre[i];
+    out[i] = act == 0 ? fmaxf(v, 0.f) : 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+  }
+}
+// dpre = dout * act'(pre).  `dout` may be read through a row map (strided block: gradient of the zero-padded
+// conv input gathered back to sequence rows; dropped rows have zero gradient).
+__global__ void k_act_bwd(const float* __restrict__ pre, const float* __restrict__ dout, RowMap dmap, long long ldd,
+                          long long rows, int cols, int act, float* __restrict__ dpre) {
+  const long long n = rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols;
+    const int c = (int)(i - r * cols);
+    const long long dr = map_row(dmap, (int)r);
+    const float gout = dr < 0 ? 0.f : dout[dr * ldd + c];
+    const float v = pre[i];
+    float gp;
+    if (act == 0) gp = v > 0.f ? 1.f : 0.f;     // TF: relu'(0) = 0
+    else gp = 0.5f * (1.f + erff(v * 0.70710678118654752440f)) + v * 0.3989422804014327f * expf(-0.5f * v * v);
+    dpre[i] = gout * gp;
+  }
+}
+// ReLU backward when both the activation and its incoming gradient live in the zero-padded conv-input layout:
+// dpre[r][c] = (hp[map r][c] > 0) * dhp[map r][c]; rows the map drops get 0.
+__global__ void k_act_bwd_mapped(const float* __restrict__ hp, const float* __restrict__ dhp, RowMap map, long long ld,
+                                 long long rows, int cols, float* __restrict__ dpre) {
+  const long long n = rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols;
+    const int c = (int)(i - r * cols);
+    const long long pr = map_row(map, (int)r);
+    dpre[i] = (pr >= 0 && hp[pr * ld + c] > 0.f) ? dhp[pr * ld + c] : 0.f;
+  }
+}
+static inline unsigned ew_grid(long long n) { return (unsigned)std::min<long long>((n + 255) / 256, 148 * 32); }
+cudaError_t launch_act_fwd(const float* pre, long long n, int act, float* out, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  k_act_fwd<<<ew_grid(n), 256, 0, st>>>(pre, n, act, out);
+  return cudaGetLastError();
+}
+cudaError_t launch_act_bwd(const float* pre, const float* dout, const RowMap& dmap, long long ldd, long long rows, int cols,
+                           int act, float* dpre, cudaStream_t st) {
+  if (rows == 0) return cudaSuccess;
+  k_act_bwd<<<ew_grid(rows * cols), 256, 0, st>>>(pre, dout, dmap, ldd, rows, cols, act, dpre);
+  return cudaGetLastError();
+}
+
+// out[r] = (base ? base[map(r)] : 0) + scale[r / rows_per_sample] * y[r] (+ table[r % period])
+// residual add with the stochastic-depth factor of vit:16-28 (scale = mask / keep_prob, or null = 1).
+__global__ void k_residual(const float* __restrict__ base, RowMap bmap, const float* __restrict__ y,
+                           const float* __restrict__ scale, int rows_per_sample, const float* __restrict__ table,
+                           int period, long long rows, int d, float* __restrict__ out) {
+  const long long n = rows * d;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / d;
+    const int c = (int)(i - r * d);
+    float v = y ? y[i] * (scale ? scale[r / rows_per_sample] : 1.f) : 0.f;
+    if (base) v += base[map_row(bmap, (int)r) * d + c];
+    if (table) v += table[(r % period) * d + c];
+    out[i] = v;
+  }
+}
+cudaError_t launch_act_bwd_mapped(const float* hp, const float* dhp, const RowMap& map, long long ld, long long rows,
+                                  int cols, float* dpre, cudaStream_t st) {
+  if (rows == 0) return cudaSuccess;
+  k_act_bwd_mapped<<<ew_grid(rows * cols), 256, 0, st>>>(hp, dhp, map, ld, rows, cols, dpre);
+  return cudaGetLastError();
+}
+cudaError_t launch_residual(const float* base, const RowMap& bmap, const float* y, const float* scale,
+                            int rows_per_sample, const float* table, int period, long long rows, int d, float* out,
+                            cudaStream_t st) {
+  if (rows == 0) return cudaSuccess;
+  k_residual<<<ew_grid(rows * d), 256, 0, st>>>(base, bmap, y, scale, rows_per_sample, table, period, rows, d, out);
+  return cudaGetLastError();
+}
+
+// dst[r] = scale[r / rps] * src[r]       (gradient through the stochastic-depth factor)
+__global__ void k_scale_rows(const float* __restrict__ src, const float* __restrict__ scale, int rps, long long rows,
+                             int d, float* __restrict__ dst) {
+  const long long n = rows * d;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = src[i] * (scale ? scale[(i / d) / rps] : 1.f);
+}
+cudaError_t launch_scale_rows(const float* src, const float* scale, int rps, long long rows, int d, float* dst,
+                              cudaStream_t st) {
+  if (rows == 0) return cudaSuccess;
+  k_scale_rows<<<ew_grid(rows * d), 256, 0, st>>>(src, scale, rps, rows, d, dst);
+  return cudaGetLastError();
+}
+
+// dst[map(r)] += src[r]   (adjoint of the strided identity gather; map is injective)
+__global__ void k_scatter_add(const float* __restrict__ src, RowMap dmap, long long rows, int d, float* __restrict__ dst) {
+  const long long n = rows * d;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / d;
+    const long long dr = map_row(dmap, (int)r);
+    if (dr >= 0) dst[dr * d + (i - r * d)] += src[i];
+  }
+}
+cudaError_t launch_scatter_add(const float* src, const RowMap& dmap, long long rows, int d, float* dst, cudaStream_t st) {
+  if (rows == 0) return cudaSuccess;
+  k_scatter_add<<<ew_grid(rows * d), 256, 0, st>>>(src, dmap, rows, d, dst);
+  return cudaGetLastError();
+}
+
+// Key-point embedding (K = 2): e[r][c] = x[r][0] W[0][c] + x[r][1] W[1][c] + b[c] + pe[r % J][c]  (net:321-323);
+// frames without 2-D input see zeros (the caller-side mask multiply, train.py:474).
+__global__ void k_embed_fwd(const float* __restrict__ x2d, const uint8_t* __restrict__ mask, int J, long long rows, int d,
+                            const float* __restrict__ Wk, const float* __restrict__ b, const float* __restrict__ pe,
+                            float* __restrict__ out) {
+  const long long n = rows * d;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / d;
+    const int c = (int)(i - r * d);
+    const bool ok = !mask || mask[r / J];
+    const float x0 = ok ? x2d[2 * r] : 0.f, x1 = ok ? x2d[2 * r + 1] : 0.f;
+    out[i] = (fmaf(x1, Wk[d + c], x0 * Wk[c]) + b[c]) + pe[(r % J) * d + c];
+  }
+}
+cudaError_t launch_embed_fwd(const float* x2d, const uint8_t* mask, int J, long long rows, int d, const float* Wk,
+                             const float* b, const float* pe, float* out, cudaStream_t st) {
+  if (rows == 0) return cudaSuccess;
+  k_embed_fwd<<<ew_grid(rows * d), 256, 0, st>>>(x2d, mask, J, rows, d, Wk, b, pe, out);
+  return cudaGetLastError();
+}
+// dW[k][c] += sum_r x[r][k] * de[r][c]   (k in {0,1})
+__global__ void k_embed_wgrad(const float* __restrict__ x2d, const uint8_t* __restrict__ mask, int J,
+                              const float* __restrict__ de, long long rows, int d, float* __restrict__ dW) {
+  const int c = threadIdx.x % d;
+  const int sub = threadIdx.x / d, nsub = blockDim.x / d;
+  const long long per = (rows + gridDim.x - 1) / gridDim.x;
+  const long long r0 = blockIdx.x * per, r1 = min(rows, r0 + per);
+  float s0 = 0.f, s1 = 0.f;
+  for (long long r = r0 + sub; r < r1; r += nsub) {
+    if (mask && !mask[r / J]) continue;
+    const float g = de[r * d + c];
+    s0 = fmaf(x2d[2 * r], g, s0);
+    s1 = fmaf(x2d[2 * r + 1], g, s1);
+  }
+  atomicAdd(dW + c, s0);
+  atomicAdd(dW + d + c, s1);
+}
+cudaError_t launch_embed_wgrad(const float* x2d, const uint8_t* mask, int J, const float* de, long long rows, int d,
+                               float* dW, cudaStream_t st) {
+  if (rows == 0) return cudaSuccess;
+  if (256 % d) return cudaErrorInvalidValue;
+  k_embed_wgrad<<<(unsigned)std::min<long long>(148 * 4, (rows + 255) / 256), 256, 0, st>>>(x2d, mask, J, de, rows, d, dW);
+  return cudaGetLastError();
+}
+
+// Token fill (net:350-352), dense form used in training:
+//   x[r] = m ? s[r] : token ; x += pe[r % n_tok].  Backward: ds[r] = m ? dx[r] : 0.
+__global__ void k_fill_fwd(const float* __restrict__ s, const uint8_t* __restrict__ mask, const float* __restrict__ token,
+                           const float* __restrict__ pe, int n_tok, long long rows, int d, float* __restrict__ x) {
+  const long long n = rows * d;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / d;
+    const int c = (int)(i - r * d);
+    const float v = (!mask || mask[r]) ? s[i] : token[c];
+    x[i] = v + pe[(r % n_tok) * d + c];
+  }
+}
+__global__ void k_fill_bwd(const float* __restrict__ dx, const uint8_t* __restrict__ mask, long long rows, int d,
+                           float* __restrict__ ds) {
+  const long long n = rows * d;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    ds[i] = (!mask || mask[i / d]) ? dx[i] : 0.f;
+}
+cudaError_t launch_fill_fwd(const float* s, const uint8_t* mask, const float* token, const float* pe, int n_tok,
+                            long long rows, int d, float* x, cudaStream_t st) {
+  if (rows == 0) return cudaSuccess;
+  k_fill_fwd<<<ew_grid(rows * d), 256, 0, st>>>(s, mask, token, pe, n_tok, rows, d, x);
+  return cudaGetLastError();
+}
+cudaError_t launch_fill_bwd(const float* dx, const uint8_t* mask, long long rows, int d, float* ds, cudaStream_t st) {
+  if (rows == 0) return cudaSuccess;
+  k_fill_bwd<<<ew_grid(rows * d), 256, 0, st>>>(dx, mask, rows, d, ds);
+  return cudaGetLastError();
+}
+
+// =================================================================================================
+// Loss (train.py:467-491, losses_3d.py:13-14) and its gradient.
+//   gt is root-centred on the fly: gt[b,n,j] - gt[b,n,root]; central gt = centred gt[:, n_tok/2].
+//   loss = wc * sum ||gt_c - pred_c|| / (BS*J) + ws * sum ||gt - pred|| / (BS*N*J), BS = config BATCH_SIZE.
+//   dpred = -w * (gt - pred) / ||gt - pred||   (NaN at a zero residual, like tf.norm — documented, not "fixed").
+// One thread per (sample, token-or-central, joint); per-block partial sums go to `partials` (deterministic
+// second pass in k_loss_reduce).
+// =================================================================================================
+__global__ void k_loss(const float* __restrict__ full, const float* __restrict__ central, const float* __restrict__ gt,
+                       int B, int n_tok, int J, int root, float w_seq, float w_cen, float* __restrict__ dfull,
+                       float* __restrict__ dcentral, float* __restrict__ partials) {
+  const long long n_seq = full ? (long long)B * n_tok * J : 0, n_cen = (long long)B * J;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  float contrib = 0.f;
+  if (i < n_seq + n_cen) {
+    long long b, n, j;
+    const float* pred;
+    float* dp;
+    float w;
+    if (i < n_seq) {
+      b = i / ((long long)n_tok * J); n = (i / J) % n_tok; j = i % J;
+      pred = full + i * 3; dp = dfull + i * 3; w = w_seq;
+    } else {
+      const long long k = i - n_seq;
+      b = k / J; n = n_tok / 2; j = k % J;
+      pred = central + k * 3; dp = dcentral + k * 3; w = w_cen;
+    }
+    const float* g = gt + ((b * n_tok + n) * J + j) * 3;
+    const float* g0 = gt + ((b * n_tok + n) * J + root) * 3;
+    const float dx = (g[0] - g0[0]) - pred[0], dy = (g[1] - g0[1]) - pred[1], dz = (g[2] - g0[2]) - pred[2];
+    const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
+    contrib = w * nrm;
+    const float s = -w / nrm;
+    dp[0] = s * dx; dp[1] = s * dy; dp[2] = s * dz;
+  }
+  __shared__ float sm[8];
+  contrib = warp_sum_t(contrib);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = contrib;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) s += sm[k];
+    partials[blockIdx.x] = s;
+  }
+}
+__global__ void k_loss_reduce(const float* __restrict__ partials, int n, float* __restrict__ loss) {
+  __shared__ float sm[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += partials[i];
+  s = warp_sum_t(s);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0.f;
+    s = warp_sum_t(s);
+    if (threadIdx.x == 0) loss[0] = s;
+  }
+}
+int loss_blocks(int B, int n_tok, int J, bool has_full) {
+  const long long n = (has_full ? (long long)B * n_tok * J : 0) + (long long)B * J;
+  return (int)((n + 255) / 256);
+}
+cudaError_t launch_loss(const float* full, const float* central, const float* gt, int B, int n_tok, int J, int root,
+                        float w_seq, float w_cen, float* dfull, float* dcentral, float* partials, float* loss,
+                        cudaStream_t st) {
+  const int nb = loss_blocks(B, n_tok, J, full != nullptr);
+  k_loss<<<nb, 256, 0, st>>>(full, central, gt, B, n_tok, J, root, w_seq, w_cen, dfull, dcentral, partials);
+  k_loss_reduce<<<1, 1024, 0, st>>>(partials, nb, loss);
+  return cudaGetLastError();
+}
+
+// =================================================================================================
+// Stochastic depth (vit:16-28): scale[i] = floor(u_i + keep) / keep with u_i from a counter-based hash RNG
+// (splitmix64 of (seed, stream, i)); rate 0 gives scale 1.
+// =================================================================================================
+__global__ void k_droppath_scale(unsigned long long seed, unsigned long long stream, long long n, float keep,
+                                 float* __restrict__ scale) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ULL * (stream * 0x100000001B3ULL + (unsigned long long)i + 1ULL);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  z ^= z >> 31;
+  const float u = (float)(z >> 40) * (1.0f / 16777216.0f);      // [0, 1)
+  scale[i] = floorf(u + keep) / keep;
+}
+cudaError_t launch_droppath_scale(unsigned long long seed, unsigned long long stream, long long n, float keep,
+                                  float* scale, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  k_droppath_scale<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(seed, stream, n, keep, scale);
+  return cudaGetLastError();
+}
+
+// =================================================================================================
+// Fused multi-tensor AdamW, tfa.optimizers.AdamW (DecoupledWeightDecayExtension + Keras Adam) semantics:
+//   p -= wd_t * p  (NOT multiplied by lr; every variable decays);  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;
+//   p -= lr_t * sqrt(1-b2^t)/(1-b1^t) * m / (sqrt(v) + eps)          (train.py:403-415)
+// One pass over the flat parameter buffer: 7 x 4 B per parameter of HBM traffic.  Optional EMA in the same pass:
+//   ema -= (1 - d) * (ema - p)   (train.py:502-504).
+// =================================================================================================
+__global__ void k_adamw(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ g,
+                        long long n, float wd, float alpha, float b1, float b2, float eps, float* __restrict__ ema,
+                        float ema_decay) {
+  const long long n4 = n >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i], mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+    const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float* pa = &pp.x; float* ma = &mm.x; float* va = &vv.x; const float* ga = &gg.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float x = pa[k];
+      x -= wd * x;
+      ma[k] = b1 * ma[k] + (1.f - b1) * ga[k];
+      va[k] = b2 * va[k] + (1.f - b2) * ga[k] * ga[k];
+      x -= alpha * ma[k] / (sqrtf(va[k]) + eps);
+      pa[k] = x;
+    }
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    if (ema) {
+      float4 e = reinterpret_cast<float4*>(ema)[i];
+      e.x -= (1.f - ema_decay) * (e.x - pp.x); e.y -= (1.f - ema_decay) * (e.y - pp.y);
+      e.z -= (1.f - ema_decay) * (e.z - pp.z); e.w -= (1.f - ema_decay) * (e.w - pp.w);
+      reinterpret_cast<float4*>(ema)[i] = e;
+    }
+  }
+}
+cudaError_t launch_adamw(float* p, float* m, float* v, const float* g, long long n, float wd, float alpha, float b1,
+                         float b2, float eps, float* ema, float ema_decay, cudaStream_t st) {
+  if (n % 4) return cudaErrorInvalidValue;
+  k_adamw<<<148 * 8, 256, 0, st>>>(p, m, v, g, n, wd, alpha, b1, b2, eps, ema, ema_decay);
+  return cudaGetLastError();
+}
+
+}  // namespace uu

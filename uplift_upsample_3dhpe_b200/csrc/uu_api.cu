@@ -6,95 +6,28 @@
 #include <string>
 #include <vector>
 
-#include "../../include/uu3d.h"
-#include "common.cuh"
+#include "model.cuh"
 
 namespace uu {
 
 static thread_local std::string g_error;
 void set_error(const std::string& msg) { g_error = msg; }
-
-// ------------------------------------------------------------------------------------------------
-struct TensorInfo {
-  std::string group;
-  int index;
-  std::vector<int64_t> shape;
-  size_t offset;   // into the flat fp32 parameter buffer (elements)
-  size_t numel;
-};
-
-struct Pack {          // bf16 W^T [n_pad, k] of a (k, n) fp32 matrix
-  bf16* ptr = nullptr;
-  int n = 0, n_pad = 0, k = 0;
-};
-
-struct BlockW {        // one temporal / strided block
-  const float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
-  float* wqkv = nullptr;   // fused fp32 [d, 3d]
-  float* bqkv = nullptr;   // [3d]
-  // w2: fc2 (h, d) or strided conv (3, h, d) == [3h, d]
-  const float *wp = nullptr, *bp = nullptr, *w1 = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr;
-  Pack p_qkv, p_proj, p_fc1, p_fc2;
-};
+const std::string& get_error() { return g_error; }
 
 }  // namespace uu
 
 using namespace uu;
 
-struct uu_model {
-  uu_spec spec;
-  int device = 0;
-  int precision = UU_PRECISION_FP32;
-  std::vector<TensorInfo> tensors;
-  std::map<std::pair<std::string, int>, int> lookup;
-  std::vector<int> seq_lens;
-  float* params = nullptr;
-  size_t n_params = 0;     // exact parameter count
-  size_t n_alloc = 0;      // floats in the flat buffer (tensors padded to 16 bytes)
-  bool dirty = true;
-
-  // derived weights
-  std::vector<BlockW> tblocks, sblocks;
-  const float** spatial_ptrs = nullptr;    // device array [depth][16]
-  void* sp_frags = nullptr;                // tensor-core spatial kernel: B-fragment image + fp32 params
-  float* sp_params = nullptr;
-  int num_sms = 148;
-  Pack p_s2t, p_head1, p_head2;
-  std::vector<void*> derived_allocs;
-
-  // workspace (sized for cap_B windows in the current precision)
-  int cap_B = 0;
-  int ws_precision = -1;
-  int *g_scratch = nullptr, *g_list = nullptr, *g_count = nullptr;
-  void *S = nullptr, *Y = nullptr, *QKV = nullptr, *O = nullptr, *Hd = nullptr, *P = nullptr;
-  float* X = nullptr;
-  std::vector<float*> Xs;      // strided stream after block i: [cap_B * seq_lens[i+1], d]
-  std::vector<void*> Hp;       // zero-padded conv inputs: [cap_B * Lo*s, h]
-  std::vector<void*> ws_allocs;
-  // device staging for uu_forward_host
-  float *d_x = nullptr, *d_full = nullptr, *d_central = nullptr;
-  uint8_t* d_mask = nullptr;
-  int stage_B = 0;
-  cudaStream_t own_stream = nullptr;
-
-  // tcgen05 plans for the current batch size
-  int plan_B = -1;
-  int plan_full = -1;
-  std::vector<TcGemmPlan*> plans;
-  int launches = 0;
-
-  // optional per-kernel-kind timing (uu_set_profiling): CUDA events around every launch
-  bool profiling = false;
-  std::vector<cudaEvent_t> ev_pool;
-  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_used;   // (kind, (start, stop))
-  size_t ev_next = 0;
-};
-
 namespace uu {
 
-static const float* W(const uu_model* m, const std::string& g, int i) {
+const float* W(const uu_model* m, const std::string& g, int i) {
   auto it = m->lookup.find({g, i});
   return it == m->lookup.end() ? nullptr : m->params + m->tensors[it->second].offset;
+}
+
+size_t tensor_offset(const uu_model* m, const std::string& g, int i) {
+  auto it = m->lookup.find({g, i});
+  return it == m->lookup.end() ? (size_t)-1 : m->tensors[it->second].offset;
 }
 
 static void add_tensor(uu_model* m, const std::string& g, int idx, std::vector<int64_t> shape) {
@@ -168,7 +101,7 @@ __global__ void k_pack_wt(const float* __restrict__ Wm, int K, int N, int n_pad,
   }
 }
 
-static int dev_alloc(std::vector<void*>& pool, void** p, size_t bytes, bool zero) {
+int dev_alloc(std::vector<void*>& pool, void** p, size_t bytes, bool zero) {
   UU_CUDA(cudaMalloc(p, bytes ? bytes : 16));
   pool.push_back(*p);
   if (zero) UU_CUDA(cudaMemset(*p, 0, bytes ? bytes : 16));
@@ -246,7 +179,7 @@ static int commit_weights(uu_model* m) {
   return 0;
 }
 
-static void free_pool(std::vector<void*>& pool) {
+void free_pool(std::vector<void*>& pool) {
   for (void* p : pool) cudaFree(p);
   pool.clear();
 }
@@ -685,6 +618,8 @@ int uu_destroy(uu_model* m) {
   drop_plans(m);
   free_pool(m->ws_allocs);
   free_pool(m->derived_allocs);
+  train_state_destroy(m);
+  cudaFree(m->grads); cudaFree(m->adam_m); cudaFree(m->adam_v); cudaFree(m->ema);
   cudaFree(m->params);
   cudaFree(m->d_x);
   cudaFree(m->d_mask);

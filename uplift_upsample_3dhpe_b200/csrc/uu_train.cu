@@ -1,0 +1,491 @@
+// Training step of the hot path (train.py:464-506): forward with saved activations and stochastic depth,
+// MPJPE loss, hand-derived backward for every trainable tensor, and the fused AdamW/EMA update.
+// All arithmetic is fp32 (the reference trains in fp32); gradients live in one flat buffer with the same
+// layout as the parameters so the data-parallel exchange is a single sum all-reduce.
+#include <cstring>
+
+#include "model.cuh"
+#include "train.cuh"
+
+namespace uu {
+
+const std::string& get_error();
+
+struct BlkTape {   // saved activations of one transformer block
+  float *x0 = nullptr, *y1 = nullptr, *qkv = nullptr, *o = nullptr, *x1 = nullptr, *y2 = nullptr, *hpre = nullptr,
+        *hact = nullptr, *x2 = nullptr, *scale = nullptr;
+  float keep = 1.f;
+};
+
+struct TrainState {
+  int B = 0;                                    // capacity / current batch of the arena
+  int global_batch = 0, root = 6;
+  float w_center = 1.f, w_seq = 1.f;
+  float dpr[3] = {0.f, 0.f, 0.f};
+  int droppath_mode = 0;                        // 0 = off, 1 = hash RNG
+  unsigned long long seed = 0;
+  std::vector<void*> pool;
+  // tapes
+  float *emb = nullptr;                         // not kept separately: spatial block 0 x0
+  std::vector<BlkTape> sp, tp, st;
+  float *sp_normed = nullptr;                   // S: spatial_norm output viewed as [R, J*ds]
+  float *s4 = nullptr;                          // spatial_to_temporal output [R, d]
+  float *full = nullptr, *central = nullptr, *dfull = nullptr, *dcentral = nullptr;
+  std::vector<float*> hp, dhp;                  // zero-padded conv input / its gradient per strided block
+  // gradient flow + scratch
+  float *dx_sp = nullptr, *dx_t = nullptr;      // [R*J, ds], [R, d]
+  std::vector<float*> dx_s;                     // per strided level output: [B*Lo, d]
+  float *tmp1 = nullptr, *tmp2 = nullptr, *tmp_h = nullptr, *tmp_qkv = nullptr, *dS = nullptr;
+  float *partials = nullptr, *loss = nullptr;
+};
+
+void train_state_destroy(uu_model* m) {
+  if (!m->train) return;
+  free_pool(m->train->pool);
+  delete m->train;
+  m->train = nullptr;
+}
+
+static float* G(uu_model* m, const std::string& g, int i) {   // gradient slot of a tensor
+  const size_t off = tensor_offset(m, g, i);
+  return off == (size_t)-1 ? nullptr : m->grads + off;
+}
+
+struct Ctx {
+  uu_model* m;
+  TrainState* t;
+  cudaStream_t st;
+};
+
+#define UU_TL(expr) UU_CUDA(expr)
+
+static int falloc(TrainState* t, float** p, size_t n_floats, bool zero = false) {
+  void* q;
+  if (dev_alloc(t->pool, &q, n_floats * sizeof(float), zero)) return 1;
+  *p = (float*)q;
+  return 0;
+}
+
+// y = x @ W + b (forward linear), C may use a row map and a wider leading dimension
+static int lin_fwd(Ctx& c, const float* A, long long lda, int M, int K, const float* Wm, int N, const float* bias,
+                   float* C, long long ldc, const RowMap* cmap = nullptr) {
+  GemmGen g;
+  g.A = A; g.lda = lda; g.B = Wm; g.ldb = N; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K; g.bias = bias;
+  if (cmap) g.cmap = *cmap;
+  UU_TL(launch_gemm_gen(g, c.st));
+  return 0;
+}
+// dX (+)= dY @ W^T ; dW += X^T dY ; db += colsum(dY).  X rows may be lda apart, dY rows ldy apart.
+static int lin_bwd(Ctx& c, const float* X, long long ldx, const float* dY, long long ldy, int M, int K, int N,
+                   const float* Wm, float* dX, long long lddx, int accumulate_dx, float* dW, float* db,
+                   const RowMap* dxmap = nullptr) {
+  if (dX) {
+    GemmGen g;
+    g.A = dY; g.lda = ldy; g.B = Wm; g.ldb = N; g.transB = 1; g.C = dX; g.ldc = lddx; g.M = M; g.N = K; g.K = N;
+    g.accumulate = accumulate_dx;
+    if (dxmap) g.cmap = *dxmap;
+    UU_TL(launch_gemm_gen(g, c.st));
+  }
+  {
+    GemmGen g;
+    g.A = X; g.lda = ldx; g.transA = 1; g.B = dY; g.ldb = ldy; g.C = dW; g.ldc = N; g.M = K; g.N = N; g.K = M;
+    g.accumulate = 1;
+    const int tiles = ((K + 63) / 64) * ((N + 63) / 64);
+    int splits = (148 * 2 + tiles - 1) / tiles;
+    splits = std::max(1, std::min(splits, std::max(1, M / 256)));
+    g.split_k = splits;
+    UU_TL(launch_gemm_gen(g, c.st));
+  }
+  if (db) UU_TL(launch_colsum(dY, M, N, ldy, db, c.st));
+  return 0;
+}
+
+struct BlkDims {
+  int d, h, S, heads;
+  long long nb;       // samples (windows, or frames for the spatial blocks)
+  int act;            // 0 ReLU, 1 GELU
+};
+
+static int alloc_tape(TrainState* t, BlkTape& tp, const BlkDims& b, bool strided) {
+  const size_t R = (size_t)b.nb * b.S;
+  if (falloc(t, &tp.y1, R * b.d) || falloc(t, &tp.qkv, R * 3 * b.d) || falloc(t, &tp.o, R * b.d) ||
+      falloc(t, &tp.x1, R * b.d) || falloc(t, &tp.y2, R * b.d) || falloc(t, &tp.scale, b.nb))
+    return 1;
+  if (!strided) {
+    if (falloc(t, &tp.hpre, R * b.h) || falloc(t, &tp.hact, R * b.h) || falloc(t, &tp.x2, R * b.d)) return 1;
+  }
+  return 0;
+}
+
+// ---- attention half, shared by plain and strided blocks --------------------------------------------
+static int attn_half_fwd(Ctx& c, const BlkDims& b, const std::string& g, BlkTape& tp, const uint8_t* keymask,
+                         int mask_stride) {
+  uu_model* m = c.m;
+  const long long R = b.nb * b.S;
+  const int d = b.d;
+  UU_TL(launch_ln_fwd_gen(tp.x0, R, d, W(m, g, 0), W(m, g, 1), 1e-5f, tp.y1, c.st));
+  for (int k = 0; k < 3; ++k)
+    if (lin_fwd(c, tp.y1, d, (int)R, d, W(m, g, 2 + 2 * k), d, W(m, g, 3 + 2 * k), tp.qkv + k * d, 3 * d)) return 1;
+  UU_TL(launch_attention(tp.qkv, 0, (int)b.nb, b.S, b.heads, d / b.heads, keymask, mask_stride, tp.o, c.st));
+  if (lin_fwd(c, tp.o, d, (int)R, d, W(m, g, 8), d, W(m, g, 9), c.t->tmp1, d)) return 1;
+  const RowMap plain;
+  UU_TL(launch_residual(tp.x0, plain, c.t->tmp1, tp.keep < 1.f ? tp.scale : nullptr, b.S, nullptr, 1, R, d, tp.x1, c.st));
+  return 0;
+}
+// dx holds d(loss)/d(x1) on entry and d(loss)/d(x0) on exit
+static int attn_half_bwd(Ctx& c, const BlkDims& b, const std::string& g, BlkTape& tp, const uint8_t* keymask,
+                         int mask_stride, float* dx) {
+  uu_model* m = c.m;
+  TrainState* t = c.t;
+  const long long R = b.nb * b.S;
+  const int d = b.d;
+  UU_TL(launch_scale_rows(dx, tp.keep < 1.f ? tp.scale : nullptr, b.S, R, d, t->tmp1, c.st));
+  if (lin_bwd(c, tp.o, d, t->tmp1, d, (int)R, d, d, W(m, g, 8), t->tmp2, d, 0, G(m, g, 8), G(m, g, 9))) return 1;
+  UU_TL(launch_attention_bwd(tp.qkv, t->tmp2, b.nb, b.S, b.heads, d / b.heads, keymask, mask_stride, t->tmp_qkv, c.st));
+  for (int k = 0; k < 3; ++k)
+    if (lin_bwd(c, tp.y1, d, t->tmp_qkv + k * d, 3 * d, (int)R, d, d, W(m, g, 2 + 2 * k), t->tmp2, d, k > 0,
+                G(m, g, 2 + 2 * k), G(m, g, 3 + 2 * k)))
+      return 1;
+  UU_TL(launch_ln_bwd_gen(tp.x0, t->tmp2, R, d, W(m, g, 0), 1e-5f, dx, 1, G(m, g, 0), G(m, g, 1), c.st));
+  return 0;
+}
+
+static int block_fwd(Ctx& c, const BlkDims& b, const std::string& g, BlkTape& tp, const uint8_t* keymask, int mstride) {
+  uu_model* m = c.m;
+  const long long R = b.nb * b.S;
+  const int d = b.d, h = b.h;
+  if (attn_half_fwd(c, b, g, tp, keymask, mstride)) return 1;
+  UU_TL(launch_ln_fwd_gen(tp.x1, R, d, W(m, g, 10), W(m, g, 11), 1e-5f, tp.y2, c.st));
+  if (lin_fwd(c, tp.y2, d, (int)R, d, W(m, g, 12), h, W(m, g, 13), tp.hpre, h)) return 1;
+  UU_TL(launch_act_fwd(tp.hpre, R * h, b.act, tp.hact, c.st));
+  if (lin_fwd(c, tp.hact, h, (int)R, h, W(m, g, 14), d, W(m, g, 15), c.t->tmp1, d)) return 1;
+  const RowMap plain;
+  UU_TL(launch_residual(tp.x1, plain, c.t->tmp1, tp.keep < 1.f ? tp.scale : nullptr, b.S, nullptr, 1, R, d, tp.x2, c.st));
+  return 0;
+}
+// dx: d/d(x2) on entry, d/d(x0) on exit (in place)
+static int block_bwd(Ctx& c, const BlkDims& b, const std::string& g, BlkTape& tp, const uint8_t* keymask, int mstride,
+                     float* dx) {
+  uu_model* m = c.m;
+  TrainState* t = c.t;
+  const long long R = b.nb * b.S;
+  const int d = b.d, h = b.h;
+  const RowMap plain;
+  UU_TL(launch_scale_rows(dx, tp.keep < 1.f ? tp.scale : nullptr, b.S, R, d, t->tmp1, c.st));
+  if (lin_bwd(c, tp.hact, h, t->tmp1, d, (int)R, h, d, W(m, g, 14), t->tmp_h, h, 0, G(m, g, 14), G(m, g, 15))) return 1;
+  UU_TL(launch_act_bwd(tp.hpre, t->tmp_h, plain, h, R, h, b.act, t->tmp_h, c.st));
+  if (lin_bwd(c, tp.y2, d, t->tmp_h, h, (int)R, d, h, W(m, g, 12), t->tmp2, d, 0, G(m, g, 12), G(m, g, 13))) return 1;
+  UU_TL(launch_ln_bwd_gen(tp.x1, t->tmp2, R, d, W(m, g, 10), 1e-5f, dx, 1, G(m, g, 10), G(m, g, 11), c.st));
+  return attn_half_bwd(c, b, g, tp, keymask, mstride, dx);
+}
+
+static int ensure_train(uu_model* m, int B) {
+  const uu_spec& s = m->spec;
+  if (!m->grads) {
+    UU_CUDA(cudaMalloc(&m->grads, sizeof(float) * m->n_alloc));
+    UU_CUDA(cudaMalloc(&m->adam_m, sizeof(float) * m->n_alloc));
+    UU_CUDA(cudaMalloc(&m->adam_v, sizeof(float) * m->n_alloc));
+    UU_CUDA(cudaMemset(m->grads, 0, sizeof(float) * m->n_alloc));
+    UU_CUDA(cudaMemset(m->adam_m, 0, sizeof(float) * m->n_alloc));
+    UU_CUDA(cudaMemset(m->adam_v, 0, sizeof(float) * m->n_alloc));
+  }
+  if (!m->train) m->train = new TrainState();
+  TrainState* t = m->train;
+  if (t->B == B) return 0;
+  UU_CUDA(cudaDeviceSynchronize());
+  free_pool(t->pool);
+  t->sp.assign(s.spatial_depth, BlkTape());
+  t->tp.assign(s.temporal_depth, BlkTape());
+  t->st.assign(s.n_strided, BlkTape());
+  t->hp.assign(s.n_strided, nullptr); t->dhp.assign(s.n_strided, nullptr); t->dx_s.assign(s.n_strided, nullptr);
+  const size_t N = s.n_tok, J = s.n_joints, ds = s.d_spatial, d = s.d_temporal, h = s.h_temporal;
+  const size_t R = (size_t)B * N, Rs = R * J;
+  float* x;
+  if (falloc(t, &x, Rs * ds)) return 1;                         // embedding = x0 of spatial block 0
+  for (int i = 0; i < s.spatial_depth; ++i) {
+    BlkDims bd{(int)ds, s.h_spatial, (int)J, s.num_heads, (long long)R, 1};
+    t->sp[i].x0 = x;
+    if (alloc_tape(t, t->sp[i], bd, false)) return 1;
+    x = t->sp[i].x2;
+  }
+  if (falloc(t, &t->sp_normed, Rs * ds) || falloc(t, &t->s4, R * d)) return 1;
+  if (falloc(t, &x, R * d)) return 1;                           // temporal input = x0 of temporal block 0
+  for (int i = 0; i < s.temporal_depth; ++i) {
+    BlkDims bd{(int)d, (int)h, (int)N, s.num_heads, (long long)B, 0};
+    t->tp[i].x0 = x;
+    if (alloc_tape(t, t->tp[i], bd, false)) return 1;
+    x = t->tp[i].x2;
+  }
+  for (int i = 0; i < s.n_strided; ++i) {
+    const size_t L = m->seq_lens[i], Lo = m->seq_lens[i + 1];
+    BlkDims bd{(int)d, (int)h, (int)L, s.num_heads, (long long)B, 0};
+    if (falloc(t, &t->st[i].x0, (size_t)B * L * d)) return 1;   // x_in + PE_i
+    if (alloc_tape(t, t->st[i], bd, true)) return 1;
+    if (falloc(t, &t->st[i].x2, (size_t)B * Lo * d)) return 1;
+    if (falloc(t, &t->hp[i], (size_t)B * Lo * s.strides[i] * h, true)) return 1;
+    if (falloc(t, &t->dhp[i], (size_t)B * Lo * s.strides[i] * h, true)) return 1;
+    if (falloc(t, &t->dx_s[i], (size_t)B * Lo * d)) return 1;
+  }
+  if (falloc(t, &t->full, R * 3 * J) || falloc(t, &t->central, (size_t)B * 3 * J) || falloc(t, &t->dfull, R * 3 * J) ||
+      falloc(t, &t->dcentral, (size_t)B * 3 * J))
+    return 1;
+  if (falloc(t, &t->dx_sp, Rs * ds) || falloc(t, &t->dx_t, R * d)) return 1;
+  const size_t rows_big = std::max(Rs, R);                      // scratch is shared by the d=32 and d=384 stages
+  const size_t dmax = std::max(Rs * ds, R * d);
+  (void)rows_big;
+  if (falloc(t, &t->tmp1, dmax) || falloc(t, &t->tmp2, dmax) ||
+      falloc(t, &t->tmp_h, std::max(Rs * (size_t)s.h_spatial, R * h)) ||
+      falloc(t, &t->tmp_qkv, std::max(Rs * 3 * ds, R * 3 * d)) || falloc(t, &t->dS, R * J * ds))
+    return 1;
+  if (falloc(t, &t->partials, loss_blocks(B, (int)N, (int)J, true) + 8) || falloc(t, &t->loss, 4)) return 1;
+  t->B = B;
+  return 0;
+}
+
+static float block_keep(const TrainState* t, int stage, int i, int depth) {
+  if (t->droppath_mode == 0 || depth <= 1) return 1.f;
+  const float rate = t->dpr[stage] * (float)i / (float)(depth - 1);      // np.linspace(0, dpr, depth)[i]
+  return 1.f - rate;
+}
+
+static int train_fb(uu_model* m, const float* x2d, const uint8_t* mask, const float* gt3d, int B, long long step,
+                    float* loss_out, cudaStream_t stream) {
+  const uu_spec& s = m->spec;
+  UU_CHECK(m->train && m->train->global_batch > 0, "call uu_train_config first");
+  UU_CHECK(B > 0 && x2d && gt3d && loss_out, "bad argument");
+  UU_CHECK(!s.has_strided_input || mask, "this model has strided input: a stride mask is required");
+  UU_CHECK(s.full_output, "training without the full-sequence head (USE_REFINE) is not supported");
+  UU_CUDA(cudaSetDevice(m->device));
+  if (ensure_train(m, B)) return 1;
+  TrainState* t = m->train;
+  Ctx c{m, t, stream};
+  const int N = s.n_tok, J = s.n_joints, ds = s.d_spatial, d = s.d_temporal, h = s.h_temporal, H = s.num_heads;
+  const long long R = (long long)B * N, Rs = R * J;
+  const bool use_mask = s.has_strided_input != 0;
+  const RowMap plain;
+  UU_CUDA(cudaMemsetAsync(m->grads, 0, sizeof(float) * m->n_alloc, stream));
+
+  // stochastic-depth factors for this step
+  for (int stage = 0; stage < 3; ++stage) {
+    std::vector<BlkTape>& tapes = stage == 0 ? t->sp : stage == 1 ? t->tp : t->st;
+    const long long ns = stage == 0 ? R : B;
+    for (size_t i = 0; i < tapes.size(); ++i) {
+      tapes[i].keep = block_keep(t, stage, (int)i, (int)tapes.size());
+      if (tapes[i].keep < 1.f)
+        UU_TL(launch_droppath_scale(t->seed, (unsigned long long)step * 64ULL + stage * 16 + i, ns, tapes[i].keep,
+                                    tapes[i].scale, stream));
+    }
+  }
+
+  // ================= forward =================
+  UU_TL(launch_embed_fwd(x2d, use_mask ? mask : nullptr, J, Rs, ds, W(m, "keypoint_embedding", 0),
+                         W(m, "keypoint_embedding", 1), W(m, "spatial_pe", 0), t->sp[0].x0, stream));
+  const BlkDims sp_dims{ds, s.h_spatial, J, H, R, 1};
+  for (int i = 0; i < s.spatial_depth; ++i)
+    if (block_fwd(c, sp_dims, "spatial_block_" + std::to_string(i + 1), t->sp[i], nullptr, 0)) return 1;
+  float* sp_out = t->sp[s.spatial_depth - 1].x2;
+  UU_TL(launch_ln_fwd_gen(sp_out, Rs, ds, W(m, "spatial_norm", 0), W(m, "spatial_norm", 1), 1e-6f, t->sp_normed, stream));
+  if (lin_fwd(c, t->sp_normed, J * ds, (int)R, J * ds, W(m, "spatial_to_temporal_fc", 0), d,
+              W(m, "spatial_to_temporal_fc", 1), t->s4, d))
+    return 1;
+  UU_TL(launch_fill_fwd(t->s4, use_mask ? mask : nullptr, use_mask ? W(m, "strided_input_token_layer", 0) : nullptr,
+                        W(m, "temporal_pe", 0), N, R, d, t->tp[0].x0, stream));
+  const BlkDims tp_dims{d, h, N, H, (long long)B, 0};
+  for (int i = 0; i < s.temporal_depth; ++i) {
+    const uint8_t* km = (use_mask && i < s.first_strided_token_attention_layer) ? mask : nullptr;
+    if (block_fwd(c, tp_dims, "temporal_block_" + std::to_string(i + 1), t->tp[i], km, N)) return 1;
+  }
+  float* xT = t->tp[s.temporal_depth - 1].x2;
+  if (lin_fwd(c, xT, d, (int)R, d, W(m, "temporal_fc", 0), 3 * J, W(m, "temporal_fc", 1), t->full, 3 * J)) return 1;
+  const float* x_in = xT;
+  for (int i = 0; i < s.n_strided; ++i) {
+    const std::string g = "strided_temporal_block_" + std::to_string(i + 1);
+    const int L = m->seq_lens[i], Lo = m->seq_lens[i + 1], st_i = s.strides[i], pl = s.pad_left[i];
+    const long long Rl = (long long)B * L, Ro = (long long)B * Lo;
+    BlkTape& tp = t->st[i];
+    const BlkDims bd{d, h, L, H, (long long)B, 0};
+    UU_TL(launch_residual(x_in, plain, nullptr, nullptr, 1, W(m, "strided_temporal_pe_" + std::to_string(i + 1), 0), L, Rl,
+                          d, tp.x0, stream));
+    if (attn_half_fwd(c, bd, g, tp, nullptr, 0)) return 1;
+    UU_TL(launch_ln_fwd_gen(tp.x1, Rl, d, W(m, g, 10), W(m, g, 11), 1e-5f, tp.y2, stream));
+    RowMap cm;
+    cm.rpb = L; cm.batch_rows = Lo * st_i; cm.offset = pl; cm.step = 1;
+    {   // Conv1D k=1 + ReLU straight into the zero-padded layout (pad rows stay zero)
+      GemmGen gg;
+      gg.A = tp.y2; gg.lda = d; gg.B = W(m, g, 12); gg.ldb = h; gg.C = t->hp[i]; gg.ldc = h; gg.cmap = cm;
+      gg.M = (int)Rl; gg.N = h; gg.K = d; gg.bias = W(m, g, 13); gg.relu = 1;
+      UU_TL(launch_gemm_gen(gg, stream));
+    }
+    if (lin_fwd(c, t->hp[i], (long long)st_i * h, (int)Ro, 3 * h, W(m, g, 14), d, W(m, g, 15), t->tmp1, d)) return 1;
+    RowMap idm;
+    idm.rpb = Lo; idm.batch_rows = L; idm.offset = (st_i > 1 && pl == 0) ? 1 : 0; idm.step = st_i;
+    UU_TL(launch_residual(tp.x1, idm, t->tmp1, tp.keep < 1.f ? tp.scale : nullptr, Lo, nullptr, 1, Ro, d, tp.x2, stream));
+    x_in = tp.x2;
+  }
+  if (lin_fwd(c, x_in, d, B, d, W(m, "strided_temporal_fc", 0), 3 * J, W(m, "strided_temporal_fc", 1), t->central, 3 * J))
+    return 1;
+
+  // ================= loss =================
+  const float bs = (float)t->global_batch;
+  UU_TL(launch_loss(t->full, t->central, gt3d, B, N, J, t->root, t->w_seq / (bs * N * J), t->w_center / (bs * J),
+                    t->dfull, t->dcentral, t->partials, t->loss, stream));
+  UU_CUDA(cudaMemcpyAsync(loss_out, t->loss, sizeof(float), cudaMemcpyDeviceToDevice, stream));
+
+  // ================= backward =================
+  float* dx = t->dx_s[s.n_strided - 1];
+  if (lin_bwd(c, x_in, d, t->dcentral, 3 * J, B, d, 3 * J, W(m, "strided_temporal_fc", 0), dx, d, 0,
+              G(m, "strided_temporal_fc", 0), G(m, "strided_temporal_fc", 1)))
+    return 1;
+  for (int i = s.n_strided - 1; i >= 0; --i) {
+    const std::string g = "strided_temporal_block_" + std::to_string(i + 1);
+    const int L = m->seq_lens[i], Lo = m->seq_lens[i + 1], st_i = s.strides[i], pl = s.pad_left[i];
+    const long long Rl = (long long)B * L, Ro = (long long)B * Lo;
+    BlkTape& tp = t->st[i];
+    const BlkDims bd{d, h, L, H, (long long)B, 0};
+    float* dx_prev = i > 0 ? t->dx_s[i - 1] : t->dx_t;        // gradient w.r.t. this block's input sequence
+    // z path
+    UU_TL(launch_scale_rows(dx, tp.keep < 1.f ? tp.scale : nullptr, Lo, Ro, d, t->tmp1, stream));
+    UU_CUDA(cudaMemsetAsync(t->dhp[i], 0, sizeof(float) * (size_t)B * Lo * st_i * h, stream));
+    if (lin_bwd(c, t->hp[i], (long long)st_i * h, t->tmp1, d, (int)Ro, 3 * h, d, W(m, g, 14), t->dhp[i],
+                (long long)st_i * h, 0, G(m, g, 14), G(m, g, 15)))
+      return 1;
+    RowMap cm;
+    cm.rpb = L; cm.batch_rows = Lo * st_i; cm.offset = pl; cm.step = 1;
+    // d(pre-activation)[r] = relu'(hp[map r]) * dhp[map r]; rows the conv never reads have zero gradient
+    UU_TL(launch_act_bwd_mapped(t->hp[i], t->dhp[i], cm, h, Rl, h, t->tmp_h, stream));
+    if (lin_bwd(c, tp.y2, d, t->tmp_h, h, (int)Rl, d, h, W(m, g, 12), t->tmp2, d, 0, G(m, g, 12), G(m, g, 13))) return 1;
+    // dx1 = scatter(dx over the identity rows) + LN2 backward
+    UU_CUDA(cudaMemsetAsync(dx_prev, 0, sizeof(float) * (size_t)Rl * d, stream));
+    RowMap idm;
+    idm.rpb = Lo; idm.batch_rows = L; idm.offset = (st_i > 1 && pl == 0) ? 1 : 0; idm.step = st_i;
+    UU_TL(launch_scatter_add(dx, idm, Ro, d, dx_prev, stream));
+    UU_TL(launch_ln_bwd_gen(tp.x1, t->tmp2, Rl, d, W(m, g, 10), 1e-5f, dx_prev, 1, G(m, g, 10), G(m, g, 11), stream));
+    if (attn_half_bwd(c, bd, g, tp, nullptr, 0, dx_prev)) return 1;
+    UU_TL(launch_period_sum(dx_prev, Rl, L, d, nullptr, 0, G(m, "strided_temporal_pe_" + std::to_string(i + 1), 0), stream));
+    dx = dx_prev;
+  }
+  // dx == dx_t: gradient w.r.t. the temporal output from the strided path; add the full-sequence head
+  if (lin_bwd(c, xT, d, t->dfull, 3 * J, (int)R, d, 3 * J, W(m, "temporal_fc", 0), t->dx_t, d, 1, G(m, "temporal_fc", 0),
+              G(m, "temporal_fc", 1)))
+    return 1;
+  for (int i = s.temporal_depth - 1; i >= 0; --i) {
+    const uint8_t* km = (use_mask && i < s.first_strided_token_attention_layer) ? mask : nullptr;
+    if (block_bwd(c, tp_dims, "temporal_block_" + std::to_string(i + 1), t->tp[i], km, N, t->dx_t)) return 1;
+  }
+  // temporal input: x = m*s4 + (1-m)*token + PE
+  UU_TL(launch_period_sum(t->dx_t, R, N, d, nullptr, 0, G(m, "temporal_pe", 0), stream));
+  if (use_mask) {
+    UU_TL(launch_period_sum(t->dx_t, R, 1, d, mask, 0, G(m, "strided_input_token_layer", 0), stream));
+    UU_TL(launch_fill_bwd(t->dx_t, mask, R, d, t->dx_t, stream));
+  }
+  if (lin_bwd(c, t->sp_normed, J * ds, t->dx_t, d, (int)R, J * ds, d, W(m, "spatial_to_temporal_fc", 0), t->dS, J * ds, 0,
+              G(m, "spatial_to_temporal_fc", 0), G(m, "spatial_to_temporal_fc", 1)))
+    return 1;
+  UU_TL(launch_ln_bwd_gen(sp_out, t->dS, Rs, ds, W(m, "spatial_norm", 0), 1e-6f, t->dx_sp, 0, G(m, "spatial_norm", 0),
+                          G(m, "spatial_norm", 1), stream));
+  for (int i = s.spatial_depth - 1; i >= 0; --i)
+    if (block_bwd(c, sp_dims, "spatial_block_" + std::to_string(i + 1), t->sp[i], nullptr, 0, t->dx_sp)) return 1;
+  UU_TL(launch_colsum(t->dx_sp, (int)Rs, ds, ds, G(m, "keypoint_embedding", 1), stream));
+  UU_TL(launch_period_sum(t->dx_sp, Rs, J, ds, nullptr, 0, G(m, "spatial_pe", 0), stream));
+  UU_TL(launch_embed_wgrad(x2d, use_mask ? mask : nullptr, J, t->dx_sp, Rs, ds, G(m, "keypoint_embedding", 0), stream));
+  return 0;
+}
+
+}  // namespace uu
+
+using namespace uu;
+
+extern "C" {
+
+int uu_train_config(uu_model* m, int global_batch, int root_keypoint, float w_center, float w_sequence,
+                    const float* drop_path_rate3, int droppath_mode, uint64_t seed) {
+  UU_CHECK(m && global_batch > 0, "bad argument");
+  UU_CHECK(root_keypoint >= 0 && root_keypoint < m->spec.n_joints, "ROOT_KEYTPOINT out of range");
+  if (!m->train) m->train = new TrainState();
+  TrainState* t = m->train;
+  t->global_batch = global_batch; t->root = root_keypoint; t->w_center = w_center; t->w_seq = w_sequence;
+  for (int i = 0; i < 3; ++i) t->dpr[i] = drop_path_rate3 ? drop_path_rate3[i] : 0.f;
+  t->droppath_mode = droppath_mode; t->seed = seed;
+  return 0;
+}
+
+int uu_train_forward_backward(uu_model* m, const float* x2d, const uint8_t* mask, const float* gt3d, int B,
+                              int64_t step, float* loss_dev, void* stream) {
+  UU_CHECK(m, "null model");
+  return train_fb(m, x2d, mask, gt3d, B, step, loss_dev, (cudaStream_t)stream);
+}
+
+int uu_grad_buffer(uu_model* m, float** dev_ptr, int64_t* n_floats) {
+  UU_CHECK(m && dev_ptr && n_floats, "null argument");
+  UU_CUDA(cudaSetDevice(m->device));
+  if (!m->grads) {
+    UU_CUDA(cudaMalloc(&m->grads, sizeof(float) * m->n_alloc));
+    UU_CUDA(cudaMalloc(&m->adam_m, sizeof(float) * m->n_alloc));
+    UU_CUDA(cudaMalloc(&m->adam_v, sizeof(float) * m->n_alloc));
+    UU_CUDA(cudaMemset(m->grads, 0, sizeof(float) * m->n_alloc));
+    UU_CUDA(cudaMemset(m->adam_m, 0, sizeof(float) * m->n_alloc));
+    UU_CUDA(cudaMemset(m->adam_v, 0, sizeof(float) * m->n_alloc));
+  }
+  *dev_ptr = m->grads;
+  *n_floats = (int64_t)m->n_alloc;
+  return 0;
+}
+
+int uu_get_grad(uu_model* m, const char* group, int index, float* host, int64_t capacity) {
+  UU_CHECK(m && group && host && m->grads, "no gradients yet");
+  auto it = m->lookup.find({std::string(group), index});
+  UU_CHECK(it != m->lookup.end(), "no such weight");
+  const TensorInfo& t = m->tensors[it->second];
+  UU_CHECK((int64_t)t.numel <= capacity, "output buffer too small");
+  UU_CUDA(cudaSetDevice(m->device));
+  UU_CUDA(cudaMemcpy(host, m->grads + t.offset, sizeof(float) * t.numel, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int uu_get_droppath_scale(uu_model* m, int stage, int block, float* host, int64_t capacity, float* keep_prob) {
+  UU_CHECK(m && m->train && host && keep_prob, "bad argument");
+  TrainState* t = m->train;
+  UU_CHECK(stage >= 0 && stage < 3, "stage must be 0 (spatial), 1 (temporal) or 2 (strided)");
+  std::vector<BlkTape>& tapes = stage == 0 ? t->sp : stage == 1 ? t->tp : t->st;
+  UU_CHECK(block >= 0 && block < (int)tapes.size(), "block out of range");
+  const long long ns = stage == 0 ? (long long)t->B * m->spec.n_tok : t->B;
+  UU_CHECK(ns <= capacity, "output buffer too small");
+  *keep_prob = tapes[block].keep;
+  UU_CUDA(cudaSetDevice(m->device));
+  if (tapes[block].keep < 1.f) {
+    UU_CUDA(cudaMemcpy(host, tapes[block].scale, sizeof(float) * ns, cudaMemcpyDeviceToHost));
+  } else {
+    for (long long i = 0; i < ns; ++i) host[i] = 1.f;
+  }
+  return 0;
+}
+
+int uu_adamw_step(uu_model* m, float lr_t, float wd_t, float beta1, float beta2, float epsilon, int64_t t,
+                  float ema_decay, void* stream) {
+  UU_CHECK(m && m->grads, "no gradients: run uu_train_forward_backward first");
+  UU_CHECK(t >= 1, "Adam step t starts at 1 (iterations + 1)");
+  UU_CUDA(cudaSetDevice(m->device));
+  if (ema_decay >= 0.f && !m->ema) {   // EMA clone starts as a copy of the weights (train.py:396-401)
+    UU_CUDA(cudaMalloc(&m->ema, sizeof(float) * m->n_alloc));
+    UU_CUDA(cudaMemcpy(m->ema, m->params, sizeof(float) * m->n_alloc, cudaMemcpyDeviceToDevice));
+  }
+  const double alpha = (double)lr_t * std::sqrt(1.0 - std::pow((double)beta2, (double)t)) /
+                       (1.0 - std::pow((double)beta1, (double)t));
+  UU_CUDA(launch_adamw(m->params, m->adam_m, m->adam_v, m->grads, (long long)m->n_alloc, wd_t, (float)alpha, beta1, beta2,
+                       epsilon, ema_decay >= 0.f ? m->ema : nullptr, ema_decay, (cudaStream_t)stream));
+  m->dirty = true;   // fused / packed inference weights are stale now
+  return 0;
+}
+
+int uu_get_ema_weight(uu_model* m, const char* group, int index, float* host, int64_t capacity) {
+  UU_CHECK(m && group && host && m->ema, "EMA is not enabled");
+  auto it = m->lookup.find({std::string(group), index});
+  UU_CHECK(it != m->lookup.end(), "no such weight");
+  const TensorInfo& t = m->tensors[it->second];
+  UU_CHECK((int64_t)t.numel <= capacity, "output buffer too small");
+  UU_CUDA(cudaSetDevice(m->device));
+  UU_CUDA(cudaMemcpy(host, m->ema + t.offset, sizeof(float) * t.numel, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+}  // extern "C"

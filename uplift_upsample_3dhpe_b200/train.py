@@ -1,0 +1,147 @@
+"""Host-side mirror of the reference's training step (train.py:464-506) and optimizer setup (:403-415).
+
+    trainer = Trainer(model, config)                       # AdamW + staircase ExponentialDecay for lr and wd
+    loss = trainer.train_step(keypoints2d, keypoints3d, stride_masks)
+
+The arithmetic (forward with stochastic depth, MPJPE loss, backward, fused AdamW/EMA) runs in libuu3d.so.
+Data-parallel training: one process per GPU, every rank passes its local windows, the flat gradient buffer
+is summed with one NCCL all-reduce (losses are normalised by the GLOBAL config BATCH_SIZE, so the combine
+is a sum, not a mean — train.py:482, :488-489).
+"""
+from __future__ import annotations
+
+import copy
+import ctypes
+import math
+from ctypes import byref, c_float, c_int64, c_void_p
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+
+
+def scheduler_by_name(name: str):
+    """common/utils/schedules.py:17-32.  Only the schedule the shipped configs use is implemented."""
+    if name != "ExponentialDecay":
+        raise NotImplementedError(f"schedule {name!r} (shipped configs use ExponentialDecay)")
+
+    def make(initial_learning_rate, decay_steps, decay_rate, staircase=False):
+        def schedule(step: int) -> float:
+            p = step / decay_steps
+            if staircase:
+                p = math.floor(p)
+            return initial_learning_rate * decay_rate ** p
+        return schedule
+    return make
+
+
+class _DevView:
+    """Zero-copy torch view of a library-owned device buffer (via __cuda_array_interface__)."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+class Trainer:
+    def __init__(self, model, config, droppath: bool = True, seed: int = 0):
+        import torch
+        self.torch = torch
+        self.model = model
+        self.config = config
+        self.lib = model._lib
+        if config.OPTIMIZER != "AdamW":
+            raise NotImplementedError("only OPTIMIZER == 'AdamW' (all shipped configs) is implemented")
+        mk = scheduler_by_name(config.SCHEDULE)
+        self.lr_schedule = mk(**config.SCHEDULE_PARAMS)
+        wd_params = copy.deepcopy(config.SCHEDULE_PARAMS)            # train.py:408-411
+        wd_params["initial_learning_rate"] = config.WEIGHT_DECAY
+        self.wd_schedule = mk(**wd_params)
+        self.beta1, self.beta2 = 0.9, 0.999
+        self.epsilon = float(config.OPTIMIZER_PARAMS.get("epsilon", 1e-8))     # train.py:414
+        self.iterations = 0
+        self.ema_enabled = bool(config.EMA_ENABLED)
+        self.ema_decay = config.EMA_DECAY
+        dpr = config.DROP_PATH_RATE if isinstance(config.DROP_PATH_RATE, (list, tuple)) else [config.DROP_PATH_RATE] * 3
+        arr = (c_float * 3)(*[float(x) for x in dpr])
+        _lib.check(self.lib.uu_train_config(model._h, int(config.BATCH_SIZE), int(config.ROOT_KEYTPOINT),
+                                            float(config.LOSS_WEIGHT_CENTER), float(config.LOSS_WEIGHT_SEQUENCE),
+                                            arr, 1 if droppath else 0, seed))
+        self._loss = torch.zeros(1, dtype=torch.float32, device=f"cuda:{model.device}")
+        self._grad_view = None
+
+    def grad_view(self):
+        """Flat fp32 gradient buffer as a torch tensor (no copy) — the all-reduce operand."""
+        if self._grad_view is None:
+            ptr, n = c_void_p(), c_int64()
+            _lib.check(self.lib.uu_grad_buffer(self.model._h, byref(ptr), byref(n)))
+            self._grad_view = self.torch.as_tensor(_DevView(ptr.value, n.value), device=f"cuda:{self.model.device}")
+        return self._grad_view
+
+    def forward_backward(self, keypoints2d, keypoints3d, stride_masks):
+        """Loss and gradients of the local windows; returns the loss as a device tensor (1,)."""
+        torch = self.torch
+        s = self.model.spec
+        x = keypoints2d.contiguous().float()
+        g = keypoints3d.contiguous().float()
+        B = x.shape[0]
+        assert tuple(x.shape[1:]) == (s.n_tok, s.n_joints, 2) and tuple(g.shape) == (B, s.n_tok, s.n_joints, 3)
+        mptr = None
+        if self.model.has_strided_input:
+            mk = stride_masks.to(device=x.device, dtype=torch.uint8).contiguous()
+            mptr = mk.data_ptr()
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        _lib.check(self.lib.uu_train_forward_backward(self.model._h, x.data_ptr(), mptr, g.data_ptr(), B,
+                                                      self.iterations, self._loss.data_ptr(), stream))
+        return self._loss
+
+    def apply_gradients(self):
+        """optimizer.apply_gradients (train.py:499) + optional EMA (train.py:502-504, :554-556)."""
+        it = self.iterations
+        lr_t, wd_t = self.lr_schedule(it), self.wd_schedule(it)
+        ema = -1.0
+        if self.ema_enabled:
+            ema = min(self.ema_decay, (1 + it) / (10 + it))
+        stream = self.torch.cuda.current_stream().cuda_stream
+        _lib.check(self.lib.uu_adamw_step(self.model._h, lr_t, wd_t, self.beta1, self.beta2, self.epsilon, it + 1,
+                                          ema, stream))
+        self.iterations += 1
+
+    def train_step(self, keypoints2d, keypoints3d, stride_masks, dist=None):
+        loss = self.forward_backward(keypoints2d, keypoints3d, stride_masks)
+        if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.grad_view(), op=dist.ReduceOp.SUM)       # NCCL over NVLink
+            dist.all_reduce(loss, op=dist.ReduceOp.SUM)
+        self.apply_gradients()
+        return loss
+
+    # ---- introspection for the parity tests ----------------------------------------------------------
+    def get_grads(self):
+        out = {}
+        for (g, k), shp in self.model._keys:
+            a = np.empty(shp, dtype=np.float32)
+            _lib.check(self.lib.uu_get_grad(self.model._h, g.encode(), k, a.ctypes.data_as(c_void_p), a.size))
+            out[(g, k)] = a
+        return out
+
+    def get_ema_weights(self):
+        out = {}
+        for (g, k), shp in self.model._keys:
+            a = np.empty(shp, dtype=np.float32)
+            _lib.check(self.lib.uu_get_ema_weight(self.model._h, g.encode(), k, a.ctypes.data_as(c_void_p), a.size))
+            out[(g, k)] = a
+        return out
+
+    def droppath_keeps(self, B: int):
+        """{(stage, block): (keep_prob, mask ndarray)} actually used by the last step, in the oracle's format."""
+        s = self.model.spec
+        out = {}
+        for si, (stage, depth, n) in enumerate((("spatial", s.spatial_depth, B * s.n_tok), ("temporal", s.temporal_depth, B),
+                                                 ("strided", len(s.strides), B))):
+            for i in range(depth):
+                buf = np.empty(n, dtype=np.float32)
+                kp = c_float()
+                _lib.check(self.lib.uu_get_droppath_scale(self.model._h, si, i, buf.ctypes.data_as(c_void_p), n, byref(kp)))
+                if kp.value < 1.0:
+                    out[(stage, i)] = (kp.value, buf * kp.value)
+        return out
