@@ -45,7 +45,7 @@ def loss_and_grads(spec, w_np, x2d, keypoints3d, stride_mask, batch_size, keeps=
     full, central = OT.forward(spec, w, x, m, keeps=keeps)
     loss = loss_fn(spec, full, central, torch.tensor(keypoints3d, dtype=dtype), batch_size)
     loss.backward()
-    return float(loss), {k: v.grad.numpy().copy() for k, v in w.items()}
+    return float(loss.detach()), {k: v.grad.numpy().copy() for k, v in w.items()}
 
 
 def adamw_step(w, g, m, v, lr_t, wd_t, t, beta1=0.9, beta2=0.999, eps=1e-8):

@@ -45,10 +45,12 @@ def test_loss_and_gradients_match_autograd(name, B, droppath):
     ref_loss, ref_g = TT.loss_and_grads(spec, w, x, gt, m, B, keeps=keeps)
     assert abs(float(loss.item()) - ref_loss) < 2e-5 * max(1.0, abs(ref_loss))
     g = tr.get_grads()
-    worst = max((_rel(g[k], ref_g[k]), k) for k in ref_g)
+    # key biases have an exactly-zero gradient (softmax is shift invariant): compare with an absolute floor
+    floor = 1e-6 * max(np.abs(v).max() for v in ref_g.values())
+    worst = max((float(np.abs(g[k] - ref_g[k]).max() / (np.abs(ref_g[k]).max() + floor)), k) for k in ref_g)
     print("worst relative gradient error", worst)
     for k in ref_g:
-        assert _rel(g[k], ref_g[k]) < 2e-3, (k, _rel(g[k], ref_g[k]))
+        assert np.abs(g[k] - ref_g[k]).max() <= 2e-3 * np.abs(ref_g[k]).max() + floor, k
     model.close()
 
 
@@ -66,9 +68,14 @@ def test_three_adamw_steps_match_oracle():
     av = {k: np.zeros_like(v) for k, v in w.items()}
     ema = {k: v.copy() for k, v in w.items()}
     sp = cfg.SCHEDULE_PARAMS
+    noise_only = set()
     for it in range(3):
         loss = tr.train_step(xd, gd, md)
         ref_loss, g = TT.loss_and_grads(spec, w, x, gt, m, 4)
+        gmax = max(np.abs(v).max() for v in g.values())
+        # Key biases have a mathematically zero gradient; Adam's m/sqrt(v) turns their round-off noise into
+        # +-lr steps (in the reference too), so their trajectory is not comparable between implementations.
+        noise_only |= {k for k, v in g.items() if np.abs(v).max() < 1e-9 * gmax}
         assert abs(float(loss.item()) - ref_loss) < 1e-4 * max(1.0, abs(ref_loss))
         lr = TT.exponential_decay(sp["initial_learning_rate"], sp["decay_steps"], sp["decay_rate"], sp["staircase"], it)
         wd = TT.exponential_decay(cfg.WEIGHT_DECAY, sp["decay_steps"], sp["decay_rate"], sp["staircase"], it)
@@ -77,7 +84,10 @@ def test_three_adamw_steps_match_oracle():
     torch.cuda.synchronize()
     got, got_ema = model.get_weights(), tr.get_ema_weights()
     # a step moves each weight by ~lr = 4e-5; compare the total displacement
+    assert noise_only and all(k[1] == 5 for k in noise_only)      # exactly the wk biases
     for k in w:
+        if k in noise_only:
+            continue
         dw_ref, dw = w[k] - w0[k], got[k] - w0[k]
         assert np.abs(dw - dw_ref).max() < 0.05 * np.abs(dw_ref).max() + 1e-7, k
         assert np.abs(got_ema[k] - ema[k]).max() < 1e-5, k

@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(256) k_gemm_gen(GemmGen g) {
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int kchunk = (((g.K + gridDim.z - 1) / gridDim.z) + GG_K - 1) / GG_K * GG_K;
   const int kbeg = blockIdx.z * kchunk, kend = min(g.K, kbeg + kchunk);
+  const bool avec = (g.lda & 3) == 0 && (reinterpret_cast<uintptr_t>(g.A) & 15) == 0;   // 16-byte loads allowed
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -47,7 +48,7 @@ __global__ void __launch_bounds__(256) k_gemm_gen(GemmGen g) {
         const long long ar = map_row(g.amap, r);
         if (ar >= 0) {
           const float* src = g.A + ar * g.lda + k;
-          if (k + 3 < kend) {
+          if (k + 3 < kend && avec) {
             const float4 t = *reinterpret_cast<const float4*>(src);
             v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
           } else {
@@ -63,8 +64,8 @@ __global__ void __launch_bounds__(256) k_gemm_gen(GemmGen g) {
       const int k = k0 + kk, r = row0 + r4;
       if (k < kend && r < g.M) {
         const float* src = g.A + (long long)k * g.lda + r;
-        if (r + 3 < g.M) t = *reinterpret_cast<const float4*>(src);
-        else { t.x = src[0]; if (r + 1 < g.M) t.y = src[1]; if (r + 2 < g.M) t.z = src[2]; }
+        if (r + 3 < g.M && avec) t = *reinterpret_cast<const float4*>(src);
+        else { t.x = src[0]; if (r + 1 < g.M) t.y = src[1]; if (r + 2 < g.M) t.z = src[2]; if (r + 3 < g.M) t.w = src[3]; }
       }
       *reinterpret_cast<float4*>(&As[kk][r4]) = t;
     }
@@ -126,8 +127,6 @@ __global__ void __launch_bounds__(256) k_gemm_gen(GemmGen g) {
 
 cudaError_t launch_gemm_gen(const GemmGen& g, cudaStream_t st) {
   if (g.M == 0 || g.N == 0 || g.K == 0) return cudaSuccess;
-  if (!g.transA && (g.lda % 4)) return cudaErrorInvalidValue;
-  if (g.transA && (g.lda % 4)) return cudaErrorInvalidValue;
   int splits = g.split_k < 1 ? 1 : g.split_k;
   if (splits > 1 && (g.bias || g.relu || !g.accumulate)) return cudaErrorInvalidValue;
   dim3 grid((g.M + GG_M - 1) / GG_M, (g.N + GG_N - 1) / GG_N, splits);
