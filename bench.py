@@ -126,6 +126,59 @@ def cpu_reference_run(spec, cfg, s_in: int, sample_B: int, steps: int, warmup: i
                       f"forward (TensorFlow not installable here)"}
 
 
+def train_bench(a, cfg, spec, rank, world, local_rank):
+    """BASELINE config 4: training step at the config's GLOBAL batch (512), data-parallel over `world` GPUs
+    (strong scaling: each rank takes BATCH_SIZE / world windows), gradients summed with one NCCL all-reduce."""
+    assert torch.cuda.is_available()
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from uplift_upsample_3dhpe_b200.model import build_uplift_upsample_transformer
+    from uplift_upsample_3dhpe_b200.train import Trainer
+    model = build_uplift_upsample_transformer(cfg, device=local_rank, precision="fp32")
+    tr = Trainer(model, cfg, droppath=True, seed=rank)
+    Bg = int(cfg.BATCH_SIZE)
+    B = Bg // world
+    rng = np.random.default_rng(rank)
+    x = torch.from_numpy(rng.uniform(-1, 1, (B, spec.n_tok, spec.n_joints, 2)).astype(np.float32)).cuda()
+    gt = torch.from_numpy(rng.normal(0, 0.3, (B, spec.n_tok, spec.n_joints, 3)).astype(np.float32)).cuda()
+    m = torch.from_numpy(stride_mask.batch_stride_masks_train(spec.n_tok, cfg.SEQUENCE_STRIDE, cfg.MASK_STRIDE, B,
+                                                              seed=rank)).cuda()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        tr.train_step(x, gt, m, dist)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        loss = tr.train_step(x, gt, m, dist)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / a.steps
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if rank == 0:
+        print(json.dumps({"metric": "training windows/sec (fwd+bwd+AdamW)", "value": Bg / (ms / 1e3), "unit": "windows/s",
+                          "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms,
+                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                          "data": "synthetic", "loss": float(loss.item()),
+                          "config": {"workload": f"config/{a.config}.json training step, global batch {Bg}, mask strides "
+                                                 f"{cfg.MASK_STRIDE} drawn per window, DropPath on",
+                                     "parallelism": f"data-parallel x{world}, NCCL sum all-reduce of "
+                                                    f"{model.param_count} fp32 gradients"}}))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -137,6 +190,8 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="windows per GPU per step")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-sample", type=int, default=64, help="windows per CPU-baseline step")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="train: amass_351-style training step (fwd+bwd+AdamW, NCCL gradient all-reduce), strong scaling")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
 
@@ -147,6 +202,9 @@ def main():
     spec = spec_from_config(cfg)
     workload = (f"config/{a.config}.json forward (N={spec.receptive_field} frames = {spec.n_tok} tokens, "
                 f"s_out={cfg.SEQUENCE_STRIDE}, s_in={a.s_in}), batched sliding-window inference")
+
+    if a.mode == "train":
+        return train_bench(a, cfg, spec, rank, world, local_rank)
 
     if a.impl == "reference":
         if rank != 0:

@@ -7,6 +7,6 @@ the C-ABI declared in include/uu3d.h.
 """
 from .config import UpliftUpsampleConfig, PRESETS            # noqa: F401
 from .spec import ModelSpec, spec_from_config, forward_macs   # noqa: F401
-from . import stride_mask, weights                            # noqa: F401
+from . import stride_mask, weights, h5lite                    # noqa: F401
 
 __version__ = "0.1.0"

@@ -19,6 +19,7 @@ from typing import Optional
 import numpy as np
 
 from . import _lib
+from .sharding import allreduce_gradients
 
 
 def scheduler_by_name(name: str):
@@ -110,7 +111,7 @@ class Trainer:
     def train_step(self, keypoints2d, keypoints3d, stride_masks, dist=None):
         loss = self.forward_backward(keypoints2d, keypoints3d, stride_masks)
         if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.grad_view(), op=dist.ReduceOp.SUM)       # NCCL over NVLink
+            allreduce_gradients(self.grad_view(), dist)                   # NCCL sum over NVLink
             dist.all_reduce(loss, op=dist.ReduceOp.SUM)
         self.apply_gradients()
         return loss
