@@ -137,7 +137,7 @@ struct TcGemmPlan;   // holds the TMA tensor maps of one GEMM call site
 int tc_gemm_plan_create(TcGemmPlan** out, const bf16* A, long long lda, int M, int K, const bf16* Wt, int N_pad,
                         int N);
 void tc_gemm_plan_destroy(TcGemmPlan* p);
-cudaError_t tc_gemm_launch(const TcGemmPlan* p, const Epilogue& epi, void* C, int c_bf16, long long ldc,
+cudaError_t tc_gemm_launch(TcGemmPlan* p, const Epilogue& epi, void* C, int c_bf16, long long ldc,
                            cudaStream_t st);
 
 }  // namespace uu

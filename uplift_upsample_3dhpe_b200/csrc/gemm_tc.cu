@@ -128,9 +128,10 @@ struct TcCfg {
 // Persistent, warp-specialised: every CTA walks the tile list t = blockIdx.x, += gridDim.x with
 // (m_blk, n_blk) = (t / n_tiles, t % n_tiles), so CTAs running concurrently share the same A rows in L2.
 // Three pipelines: smem ring (TMA -> MMA), TMEM accumulator ring (MMA -> epilogue), tile list.
-template <int BLOCK_N, typename TC>
+template <int BLOCK_N, typename TC, bool TMA_OUT>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant__ CUtensorMap map_a,
-                                                           const __grid_constant__ CUtensorMap map_b, int M, int N,
+                                                           const __grid_constant__ CUtensorMap map_b,
+                                                           const __grid_constant__ CUtensorMap map_c, int M, int N,
                                                            int n_tiles, int K, Epilogue epi, TC* __restrict__ C,
                                                            long long ldc) {
   using Cfg = TcCfg<BLOCK_N>;
@@ -152,6 +153,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    if constexpr (TMA_OUT) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
     for (int s = 0; s < Cfg::STAGES; ++s) {
       mbar_init(full_bar + s, 1);
       mbar_init(empty_bar + s, 1);
@@ -228,6 +230,71 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
     const int e = warp - 2;                   // 0..7
     const int q = warp & 3;                   // TMEM lane quarter this warp may access
     const int hsel = e >> 2;                  // chunk parity handled by this warp
+    if constexpr (TMA_OUT) {
+      // ---- bf16 output through shared memory + TMA store --------------------------------------------------
+      // Per 64-column sub-tile: every thread converts 32 columns of its own row (bias, ReLU, bf16 pack) and
+      // writes them into a 128 x 64 bf16 staging tile in the 128B-swizzle layout (conflict-free 16-byte
+      // stores); one thread then issues a single cp.async.bulk.tensor store.  Two staging tiles alternate, so
+      // the store of sub-tile s overlaps the conversion of sub-tile s+1.  Rows past M are clipped by TMA.
+      uint8_t* stage_base = reinterpret_cast<uint8_t*>(
+          (reinterpret_cast<uintptr_t>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256) + 1023) & ~uintptr_t(1023));
+      const int r_in_tile = q * 32 + lane;
+      const bool issuer = (warp == 2 && lane == 0);
+      uint32_t tcount = 0, sub_count = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+        const int row0 = (tile / n_tiles) * TC_BLOCK_M, col0 = (tile % n_tiles) * BLOCK_N;
+        const int as = tcount % Cfg::ACC_STAGES;
+        const uint32_t aph = (tcount / Cfg::ACC_STAGES) & 1;
+        mbar_wait(tmem_full_bar + as, aph);
+        tcgen05_fence_after();
+        const uint32_t tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N);
+#pragma unroll 1
+        for (int sub = 0; sub < BLOCK_N / 64; ++sub, ++sub_count) {
+          uint8_t* sbuf = stage_base + (sub_count & 1) * (TC_BLOCK_M * 128);
+          const int cbase = col0 + sub * 64 + hsel * 32;
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_acc + (uint32_t)(sub * 64 + hsel * 32), v);
+          if (sub == BLOCK_N / 64 - 1) {          // last TMEM read of this tile: release the accumulator early
+            tcgen05_fence_before();
+            if (lane == 0) mbar_arrive(tmem_empty_bar + as);
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {           // 8 columns -> one 16-byte chunk
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v[8 * g + i]);
+            if (epi.bias) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(epi.bias + cbase + 8 * g));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(epi.bias + cbase + 8 * g + 4));
+              o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w;
+              o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
+            }
+            if (epi.flags & EPI_RELU) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o[i] = fmaxf(o[i], 0.f);
+            }
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(o[4], o[5]), p3 = __floats2bfloat162_rn(o[6], o[7]);
+            uint4 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+            pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
+            const int c16 = hsel * 4 + g;         // 16-byte chunk index inside the 128-byte row
+            *reinterpret_cast<uint4*>(sbuf + r_in_tile * 128 + ((c16 ^ (r_in_tile & 7)) << 4)) = pk;
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async proxy
+          // the previous store (other staging tile) must have finished READING before anyone refills that tile
+          if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (issuer) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&map_c),
+                         "r"(smem_u32(sbuf)), "r"(col0 + sub * 64), "r"(row0)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+      }
+      if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    } else {
     float* tbuf = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256) + e * (32 * TC_TSTRIDE);
     const int rsub = lane >> 3, g4 = (lane & 7) * 4;
     const bool vec_ok = (N % 4 == 0) && (ldc % 4 == 0) && (!(epi.flags & EPI_RESIDUAL) || (epi.ldr % 4 == 0));
@@ -309,6 +376,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
       tcgen05_fence_before();
       if (lane == 0) mbar_arrive(tmem_empty_bar + as);
     }
+    }   // !TMA_OUT
   }
 
   tcgen05_fence_before();
@@ -358,8 +426,10 @@ static int encode_2d(CUtensorMap* map, const void* base, uint64_t cols, uint64_t
 }
 
 struct TcGemmPlan {
-  CUtensorMap map_a, map_b;
+  CUtensorMap map_a, map_b, map_c;
   int M, N, N_pad, K, block_n;
+  const void* c_ptr = nullptr;      // output the store map was encoded for
+  long long c_ld = 0;
 };
 
 int tc_gemm_plan_create(TcGemmPlan** out, const bf16* A, long long lda, int M, int K, const bf16* Wt, int N_pad, int N) {
@@ -386,12 +456,12 @@ void tc_gemm_plan_destroy(TcGemmPlan* p) { delete p; }
 
 static int g_num_sms = 0;
 
-template <int BLOCK_N, typename TC>
+template <int BLOCK_N, typename TC, bool TMA_OUT>
 static cudaError_t tc_launch_t(const TcGemmPlan* p, const Epilogue& epi, void* C, long long ldc, cudaStream_t st) {
   using Cfg = TcCfg<BLOCK_N>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BLOCK_N, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BLOCK_N, TC, TMA_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
@@ -404,18 +474,36 @@ static cudaError_t tc_launch_t(const TcGemmPlan* p, const Epilogue& epi, void* C
   const int n_tiles = p->N_pad / BLOCK_N;
   const int total = ((p->M + TC_BLOCK_M - 1) / TC_BLOCK_M) * n_tiles;
   const int grid = total < g_num_sms ? total : g_num_sms;          // persistent: one CTA per SM
-  k_gemm_tc<BLOCK_N, TC><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(p->map_a, p->map_b, p->M, p->N, n_tiles, p->K, epi,
-                                                                    reinterpret_cast<TC*>(C), ldc);
+  k_gemm_tc<BLOCK_N, TC, TMA_OUT><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(
+      p->map_a, p->map_b, p->map_c, p->M, p->N, n_tiles, p->K, epi, reinterpret_cast<TC*>(C), ldc);
   return cudaGetLastError();
 }
 
-cudaError_t tc_gemm_launch(const TcGemmPlan* p, const Epilogue& epi, void* C, int c_bf16, long long ldc,
-                           cudaStream_t st) {
+// bf16 output, plain row mapping, no residual / table / scatter, full 64-column sub-tiles: TMA-store epilogue
+static bool tma_out_eligible(const TcGemmPlan* p, const Epilogue& epi, int c_bf16, long long ldc) {
+  return c_bf16 && !epi.c_rowidx && !epi.m_dev && epi.cmap.rpb == 0x7fffffff &&
+         !(epi.flags & (EPI_RESIDUAL | EPI_ROWTABLE)) && p->N == p->N_pad && (p->N % 64) == 0 && (ldc % 8) == 0 &&
+         p->block_n >= 64;
+}
+
+cudaError_t tc_gemm_launch(TcGemmPlan* p, const Epilogue& epi, void* C, int c_bf16, long long ldc, cudaStream_t st) {
+  if (tma_out_eligible(p, epi, c_bf16, ldc)) {
+    if (p->c_ptr != C || p->c_ld != ldc) {
+      if (encode_2d(&p->map_c, C, (uint64_t)p->N, (uint64_t)p->M, (uint64_t)ldc, 64, TC_BLOCK_M)) return cudaErrorInvalidValue;
+      p->c_ptr = C; p->c_ld = ldc;
+    }
+    switch (p->block_n) {
+      case 256: return tc_launch_t<256, bf16, true>(p, epi, C, ldc, st);
+      case 192: return tc_launch_t<192, bf16, true>(p, epi, C, ldc, st);
+      case 128: return tc_launch_t<128, bf16, true>(p, epi, C, ldc, st);
+      default: return tc_launch_t<64, bf16, true>(p, epi, C, ldc, st);
+    }
+  }
   switch (p->block_n) {
-    case 256: return c_bf16 ? tc_launch_t<256, bf16>(p, epi, C, ldc, st) : tc_launch_t<256, float>(p, epi, C, ldc, st);
-    case 192: return c_bf16 ? tc_launch_t<192, bf16>(p, epi, C, ldc, st) : tc_launch_t<192, float>(p, epi, C, ldc, st);
-    case 128: return c_bf16 ? tc_launch_t<128, bf16>(p, epi, C, ldc, st) : tc_launch_t<128, float>(p, epi, C, ldc, st);
-    default: return c_bf16 ? tc_launch_t<64, bf16>(p, epi, C, ldc, st) : tc_launch_t<64, float>(p, epi, C, ldc, st);
+    case 256: return c_bf16 ? tc_launch_t<256, bf16, false>(p, epi, C, ldc, st) : tc_launch_t<256, float, false>(p, epi, C, ldc, st);
+    case 192: return c_bf16 ? tc_launch_t<192, bf16, false>(p, epi, C, ldc, st) : tc_launch_t<192, float, false>(p, epi, C, ldc, st);
+    case 128: return c_bf16 ? tc_launch_t<128, bf16, false>(p, epi, C, ldc, st) : tc_launch_t<128, float, false>(p, epi, C, ldc, st);
+    default: return c_bf16 ? tc_launch_t<64, bf16, false>(p, epi, C, ldc, st) : tc_launch_t<64, float, false>(p, epi, C, ldc, st);
   }
 }
 
