@@ -1,9 +1,9 @@
 // K5 (bf16 path): fused softmax attention per (window, head) on tensor cores.
 //   S = Q K^T / sqrt(dh) (+ key mask * -1e9, literal fp32 arithmetic of vit:117-123), softmax, O = P V,
-//   heads merged on store.  A whole window (<= 128 tokens) lives in one CTA: K and V^T of the head sit in
-//   shared memory (padded strides, conflict-free B-fragment loads), every warp owns 16 query rows, the
-//   score tile stays in registers (mma.sync m16n8k16 accumulators) and is re-used as the A operand of P V
-//   without leaving the register file.  The (B,8,S,S) score tensor of the reference never exists.
+//   heads merged on store.  A whole window (<= 128 tokens) lives in one CTA: Q, K and V of the head sit
+//   row-major in shared memory (cp.async in, ldmatrix / ldmatrix.trans out), every warp owns 16 query rows,
+//   the score tile stays in registers (mma.sync m16n8k16 accumulators) and is re-used as the A operand of
+//   P V without leaving the register file.  The (B,8,S,S) score tensor of the reference never exists.
 #include "common.cuh"
 
 namespace uu {
@@ -19,63 +19,93 @@ __device__ __forceinline__ uint32_t pack2_att(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t (&r)[2], const void* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+
 // ST = number of 16-row tiles covering the sequence (S <= 16*ST); blockDim = 32*ST.
+// Q, K and V rows of the head are staged row-major in shared memory with cp.async (16-byte chunks, fully
+// coalesced 32-byte sectors); the row stride DH+8 makes every ldmatrix phase (8 rows x 16 B) conflict-free.
+// K feeds the B operand of Q K^T through ldmatrix, V the B operand of P V through ldmatrix.trans, so no
+// explicit transposition is ever stored.  The output tile goes back through the warp's own (already
+// consumed) Q rows and leaves as 16-byte row chunks.
 template <int DH, int ST>
 __global__ void __launch_bounds__(32 * ST) k_attention_tc(const bf16* __restrict__ qkv, int S, int heads,
                                                           const uint8_t* __restrict__ mask, int mask_stride,
                                                           bf16* __restrict__ out) {
   constexpr int SP = 16 * ST;            // padded sequence
   constexpr int NT = SP / 8;             // key n-tiles of the score matrix
-  constexpr int KS = DH + 8;             // K row stride (bf16): (KS/2) % 8 == 4 -> conflict-free fragment loads
-  constexpr int VS = SP + 8;             // V^T row stride (bf16)
-  __shared__ __align__(16) bf16 Ks[SP * KS];
-  __shared__ __align__(16) bf16 Vt[DH * VS];
-  __shared__ float Km[SP];               // additive key term: 0, -1e9 (masked key) or -inf (padding)
+  constexpr int RS = DH + 8;             // row stride (bf16)
+  constexpr int CH = DH / 8;             // 16-byte chunks per head row
+  extern __shared__ __align__(16) uint8_t att_smem[];
+  bf16* Qs = reinterpret_cast<bf16*>(att_smem);
+  bf16* Ks = Qs + SP * RS;
+  bf16* Vs = Ks + SP * RS;
+  float* Km = reinterpret_cast<float*>(Vs + SP * RS);   // additive key term: 0, -1e9 (masked key) or -inf (padding)
   const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const int d = heads * DH;
   const long long row0 = (long long)b * S;
-  constexpr int CH = DH / 8;             // 16-byte chunks per head row
   for (int i = tid; i < SP * CH; i += 32 * ST) {
     const int key = i / CH, c = i - key * CH;
-    uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+    const int so = key * RS + c * 8;
     if (key < S) {
       const bf16* r = qkv + (row0 + key) * 3 * d + h * DH + c * 8;
-      kv = *reinterpret_cast<const uint4*>(r + d);
-      vv = *reinterpret_cast<const uint4*>(r + 2 * d);
+      cp_async16(Qs + so, r);
+      cp_async16(Ks + so, r + d);
+      cp_async16(Vs + so, r + 2 * d);
+    } else {
+      const uint4 z = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(Qs + so) = z;
+      *reinterpret_cast<uint4*>(Ks + so) = z;
+      *reinterpret_cast<uint4*>(Vs + so) = z;
     }
-    *reinterpret_cast<uint4*>(Ks + key * KS + c * 8) = kv;
-    const bf16* ve = reinterpret_cast<const bf16*>(&vv);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) Vt[(c * 8 + e) * VS + key] = ve[e];
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
   for (int j = tid; j < SP; j += 32 * ST)
     Km[j] = j >= S ? -INFINITY : ((mask && !mask[(long long)b * mask_stride + j]) ? -1e9f : 0.f);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
-  const int q0 = warp * 16 + g, q1 = q0 + 8;         // query rows of this thread
-  // Q fragments straight from global memory (each row is read exactly once)
+  // Q fragments of this warp's 16 query rows
   uint32_t aq[DH / 16][4];
   {
-    const bf16* qr0 = qkv + (row0 + min(q0, S - 1)) * 3 * d + h * DH;
-    const bf16* qr1 = qkv + (row0 + min(q1, S - 1)) * 3 * d + h * DH;
+    const bf16* qb = Qs + (warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * RS + (lane >> 4) * 8;
 #pragma unroll
-    for (int kk = 0; kk < DH / 16; ++kk) {
-      aq[kk][0] = *reinterpret_cast<const uint32_t*>(qr0 + 16 * kk + 2 * t);
-      aq[kk][1] = *reinterpret_cast<const uint32_t*>(qr1 + 16 * kk + 2 * t);
-      aq[kk][2] = *reinterpret_cast<const uint32_t*>(qr0 + 16 * kk + 8 + 2 * t);
-      aq[kk][3] = *reinterpret_cast<const uint32_t*>(qr1 + 16 * kk + 8 + 2 * t);
-    }
+    for (int kk = 0; kk < DH / 16; ++kk) ldsm_x4(aq[kk], qb + 16 * kk);
   }
   float sc[NT][4];
 #pragma unroll
   for (int j = 0; j < NT; ++j) {
     sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
-    const bf16* kr = Ks + (8 * j + g) * KS + 2 * t;
+    const bf16* kb = Ks + (8 * j + (lane & 7)) * RS + (lane >> 3) * 8;
 #pragma unroll
-    for (int kk = 0; kk < DH / 16; ++kk)
-      mma16816_att(sc[j], aq[kk], *reinterpret_cast<const uint32_t*>(kr + 16 * kk),
-                   *reinterpret_cast<const uint32_t*>(kr + 16 * kk + 8));
+    for (int c0 = 0; c0 + 4 <= CH; c0 += 4) {
+      uint32_t bk[4];
+      ldsm_x4(bk, kb + c0 * 8);
+      mma16816_att(sc[j], aq[c0 / 2], bk[0], bk[1]);
+      mma16816_att(sc[j], aq[c0 / 2 + 1], bk[2], bk[3]);
+    }
+    if constexpr (CH % 4 == 2) {
+      uint32_t bk[2];
+      ldsm_x2(bk, Ks + (8 * j + (lane & 7)) * RS + (CH - 2 + ((lane >> 3) & 1)) * 8);
+      mma16816_att(sc[j], aq[DH / 16 - 1], bk[0], bk[1]);
+    }
   }
   // logits = s / sqrt(dh) + key term (fp32, literal), row max, exp, row sum
   const float scale = 1.0f / sqrtf((float)DH);
@@ -112,22 +142,31 @@ __global__ void __launch_bounds__(32 * ST) k_attention_tc(const bf16* __restrict
     ap[1] = pack2_att(sc[2 * kk][2], sc[2 * kk][3]);
     ap[2] = pack2_att(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
     ap[3] = pack2_att(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
+    const bf16* vb = Vs + (16 * kk + ((lane >> 3) & 1) * 8 + (lane & 7)) * RS + (lane >> 4) * 8;
 #pragma unroll
-    for (int jn = 0; jn < DH / 8; ++jn) {
-      const bf16* vr = Vt + (8 * jn + g) * VS + 16 * kk + 2 * t;
-      mma16816_att(o[jn], ap, *reinterpret_cast<const uint32_t*>(vr), *reinterpret_cast<const uint32_t*>(vr + 8));
+    for (int jn = 0; jn < DH / 8; jn += 2) {
+      uint32_t bv[4];
+      ldsm_x4_t(bv, vb + jn * 8);
+      mma16816_att(o[jn], ap, bv[0], bv[1]);
+      mma16816_att(o[jn + 1], ap, bv[2], bv[3]);
     }
   }
+  // normalise, stage the 16 x DH tile in this warp's own Q rows, store 16-byte chunks
   const float i0 = 1.f / l0, i1 = 1.f / l1;
-  if (q0 < S) {
-    bf16* orow = out + (row0 + q0) * d + h * DH + 2 * t;
+  __syncwarp();
+  bf16* stg = Qs + warp * 16 * RS;
 #pragma unroll
-    for (int jn = 0; jn < DH / 8; ++jn) *reinterpret_cast<uint32_t*>(orow + 8 * jn) = pack2_att(o[jn][0] * i0, o[jn][1] * i0);
+  for (int jn = 0; jn < DH / 8; ++jn) {
+    *reinterpret_cast<uint32_t*>(stg + g * RS + 8 * jn + 2 * t) = pack2_att(o[jn][0] * i0, o[jn][1] * i0);
+    *reinterpret_cast<uint32_t*>(stg + (g + 8) * RS + 8 * jn + 2 * t) = pack2_att(o[jn][2] * i1, o[jn][3] * i1);
   }
-  if (q1 < S) {
-    bf16* orow = out + (row0 + q1) * d + h * DH + 2 * t;
+  __syncwarp();
 #pragma unroll
-    for (int jn = 0; jn < DH / 8; ++jn) *reinterpret_cast<uint32_t*>(orow + 8 * jn) = pack2_att(o[jn][2] * i1, o[jn][3] * i1);
+  for (int i = lane; i < 16 * CH; i += 32) {
+    const int r = i / CH, c = i - r * CH;
+    const int q = warp * 16 + r;
+    if (q < S)
+      *reinterpret_cast<uint4*>(out + (row0 + q) * d + h * DH + c * 8) = *reinterpret_cast<const uint4*>(stg + r * RS + c * 8);
   }
 }
 
@@ -137,9 +176,18 @@ static cudaError_t att_tc_dh(const bf16* qkv, int B, int S, int heads, const uin
   const int tiles = (S + 15) / 16;
   dim3 grid(B, heads);
 #define UU_ATT_CASE(T)                                                                               \
-  case T:                                                                                            \
-    k_attention_tc<DH, T><<<grid, 32 * T, 0, st>>>(qkv, S, heads, mask, mask_stride, out);           \
-    break;
+  case T: {                                                                                          \
+    constexpr int smem = 3 * 16 * T * (DH + 8) * 2 + 16 * T * 4;                                     \
+    if (smem > 48 * 1024) {                                                                          \
+      static bool attr = false;                                                                      \
+      if (!attr) {                                                                                   \
+        cudaError_t e = cudaFuncSetAttribute(k_attention_tc<DH, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+        if (e != cudaSuccess) return e;                                                              \
+        attr = true;                                                                                 \
+      }                                                                                              \
+    }                                                                                                \
+    k_attention_tc<DH, T><<<grid, 32 * T, smem, st>>>(qkv, S, heads, mask, mask_stride, out);        \
+  } break;
   switch (tiles) {
     UU_ATT_CASE(1) UU_ATT_CASE(2) UU_ATT_CASE(3) UU_ATT_CASE(4)
     UU_ATT_CASE(5) UU_ATT_CASE(6) UU_ATT_CASE(7) UU_ATT_CASE(8)
