@@ -1,0 +1,158 @@
+"""Generate tests/golden/*.npz by executing the REFERENCE's own Python sources.
+
+Runs only in the build container (needs /root/reference); the fixtures it writes are committed and
+are what the GPU box tests against.  The reference modules are imported unmodified; TensorFlow,
+Keras and h5py (absent from this image) are replaced by the NumPy stand-ins under oracle/tfshim.
+
+Executed from the reference, not restated:
+  * config loading            common/utils/config.py + config/*.json
+  * model construction        common/net/uplift_upsample_transformer_constructor.py:14-50
+  * the forward graph         common/net/uplift_upsample_transformer.py, common/net/vision_transformer.py
+  * .h5 weight loading        common/utils/weight_io.py:76-263  (reads files written by our h5lite writer)
+  * eval-time glue            eval.py:63-71 (mask multiply) — restated in three lines below, eval.py imports datasets at top level
+  * window + stride-mask generator  common/dataset/uplifiting_dataset.py:213-428
+
+usage: python scripts/make_golden.py [--out tests/golden]
+"""
+import argparse
+import hashlib
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("UU_REFERENCE_ROOT", "/root/reference")
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden"))
+args = ap.parse_args()
+
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle", "tfshim"))
+sys.path.insert(0, REF)
+
+import numpy as np  # noqa: E402
+
+import tensorflow as tf  # noqa: E402  (the shim)
+from common.net.uplift_upsample_transformer_config import UpliftUpsampleConfig as RefConfig  # noqa: E402
+from common.net.uplift_upsample_transformer_constructor import build_uplift_upsample_transformer as ref_build  # noqa: E402
+from common.utils import weight_io as ref_weight_io  # noqa: E402
+from common.dataset.uplifiting_dataset import H36mSequenceGenerator  # noqa: E402
+
+from uplift_upsample_3dhpe_b200 import UpliftUpsampleConfig, h5lite, spec_from_config, weights  # noqa: E402
+
+assert tf.__version__.endswith("numpy-shim")
+os.makedirs(args.out, exist_ok=True)
+TMP = os.path.join("/tmp", "uu_golden")
+os.makedirs(TMP, exist_ok=True)
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+def ref_test_step(model, keypoints2d, stride_masks):
+    """eval.py:63-71."""
+    if model.has_strided_input:
+        mask = tf.cast(stride_masks, dtype=tf.float32)
+        inputs = [keypoints2d * mask[:, :, tf.newaxis, tf.newaxis], stride_masks]
+    else:
+        inputs = keypoints2d
+    return model(inputs, training=False)
+
+
+def forward_case(tag, cfg_name, mask_stride, B, mode, seed, subsample=1):
+    ref_cfg = RefConfig(config_file=os.path.join(REF, "config", cfg_name + ".json"))
+    ref_cfg.MASK_STRIDE = mask_stride            # eval.py:264-266 sets an int per run
+    ref_cfg.BATCH_SIZE = B
+
+    ours = UpliftUpsampleConfig.preset(cfg_name, MASK_STRIDE=mask_stride)
+    spec = spec_from_config(ours)
+    # every key the hot path consumes must agree between our preset and the reference's JSON
+    for k in ("SEQUENCE_LENGTH", "SEQUENCE_STRIDE", "NUM_KEYPOINTS", "SPATIAL_EMBED_DIM", "TEMPORAL_EMBED_DIM",
+              "SPATIAL_TRANSFORMER_BLOCKS", "TEMPORAL_TRANSFORMER_BLOCKS", "STRIDES", "PADDINGS", "NUM_HEADS", "MLP_RATIO",
+              "QKV_BIAS", "FIRST_STRIDED_TOKEN_ATTENTION_LAYER", "USE_REFINE"):
+        assert getattr(ref_cfg, k) == getattr(ours, k), (k, getattr(ref_cfg, k), getattr(ours, k))
+
+    w = weights.init_weights(spec, seed=seed, perturb=True)
+    h5 = os.path.join(TMP, f"{tag}.h5")
+    h5lite.save_keras_weights(h5, spec, w)
+    rng = np.random.default_rng(seed + 100)
+    n_tok = ref_cfg.SEQUENCE_LENGTH
+    x = rng.uniform(-1, 1, (B, n_tok, 17, 2)).astype(np.float32)
+    gen = mask_generator(n_tok, ref_cfg.SEQUENCE_STRIDE, mask_stride, mode, B, subsample)
+    masks = np.stack([m for _, m in gen])
+    centers = np.array([c for c, _ in gen])
+    out = {}
+    # float64 = truth; float32 = the precision TensorFlow computes in (it defines all-masked windows: x - 1e9 rounds to -1e9)
+    for dt in ("float64", "float32"):
+        tf.set_float_dtype(dt)
+        model = ref_build(ref_cfg)
+        assert model.has_strided_input == bool(spec.has_strided_input)
+        ref_weight_io.load_weights_with_callback(model, h5, verbose=True)      # the reference's own loader
+        assert model.count_params() == weights.param_count(spec), (model.count_params(), weights.param_count(spec))
+        # the loader matched every tensor: values in the reference model equal the inventory, by group and position
+        by_name = {l.name: l for l in model.layers}
+        for (g, i), a in w.items():
+            got = np.asarray(by_name[g].weights[i])
+            assert got.shape == a.shape and np.array_equal(got.astype(np.float32), a), (g, i)
+        full, central = ref_test_step(model, x.astype(tf.float32), masks)
+        assert np.asarray(central).dtype == np.dtype(dt)
+        out[dt] = (np.asarray(full), np.asarray(central))
+    np.savez_compressed(os.path.join(args.out, f"forward_{tag}.npz"), config=cfg_name, mask_stride=mask_stride, seed=seed,
+                        x=x, mask=masks, center_frames=centers, full=out["float64"][0], central=out["float64"][1],
+                        full_f32=out["float32"][0], central_f32=out["float32"][1],
+                        weights_sha=sha(weights.to_flat(spec, w)))
+    d = np.abs(out["float64"][1] - out["float32"][1]).reshape(B, -1).max(1)
+    print(f"forward_{tag}: full {out['float64'][0].shape} central {out['float64'][1].shape} "
+          f"valid/window {masks.sum(1).tolist()} |central|max {np.abs(out['float64'][1]).max():.3f} "
+          f"f32-vs-f64 per window {np.array2string(d, precision=2)}")
+
+
+def run_generator(n_tok, stride, mask_stride, mode, n_windows, video_len=400, seed=0, subsample=1):
+    """Drive the reference's H36mSequenceGenerator on one synthetic video."""
+    rng = np.random.default_rng(7)
+    p3 = rng.normal(size=(video_len, 17, 3)).astype(np.float32)
+    p2 = rng.normal(size=(video_len, 17, 2)).astype(np.float32)
+    cam = np.zeros(11, dtype=np.float32)
+    g = H36mSequenceGenerator([p3], [p2], [cam], ["S1"], ["Walking"], [50], split="test", seq_len=n_tok,
+                              subsample=subsample, stride=stride, padding_type="copy", flip_augment=False,
+                              mask_stride=mask_stride, stride_mask_align_global=(mode == "eval"),
+                              rand_shift_stride_mask=(mode == "train"), shuffle=False, seed=seed, verbose=False)
+    out = []
+    for k, item in enumerate(g.next_epoch_iterator()):
+        if k >= n_windows:
+            break
+        out.append(item)
+    return p2, out
+
+
+def mask_generator(n_tok, stride, mask_stride, mode, B, subsample):
+    _, items = run_generator(n_tok, stride, mask_stride, mode, B, subsample=subsample)
+    return [(int(it[6]), np.asarray(it[7], dtype=bool)) for it in items]
+
+
+def stride_mask_case(tag, n_tok, stride, mask_stride, mode, n_windows, video_len):
+    p2, items = run_generator(n_tok, stride, mask_stride, mode, n_windows, video_len=video_len)
+    np.savez_compressed(os.path.join(args.out, f"windows_{tag}.npz"), n_tok=n_tok, stride=stride,
+                        mask_stride=np.asarray(mask_stride), mode=mode, video_2d=p2,
+                        centers=np.array([it[6] for it in items]),
+                        stride_masks=np.stack([np.asarray(it[7], dtype=bool) for it in items]),
+                        pad_masks=np.stack([it[2] for it in items]),
+                        seq_2d=np.stack([it[1] for it in items]).astype(np.float32))
+    print(f"windows_{tag}: {len(items)} windows, valid tokens min/max "
+          f"{min(int(it[7].sum()) for it in items)}/{max(int(it[7].sum()) for it in items)}")
+
+
+if __name__ == "__main__":
+    # forward: the BASELINE.json configs at fixture size (the full-size runs use properties instead)
+    # (window centres step by `subsample` frames; centres off the s_out grid give all-masked windows, eval.py global alignment)
+    forward_case("h36m_81_sin4", "h36m_81", 4, 4, "eval", seed=1, subsample=3)            # valid tokens 21, 0, 20, 0
+    forward_case("h36m_351_sin5", "h36m_351", 5, 3, "eval", seed=2, subsample=5)          # mask all ones (no-op)
+    forward_case("h36m_351_sin5_unaligned", "h36m_351", 5, 3, "eval", seed=2, subsample=3)  # 71, 0, 0
+    forward_case("h36m_351_sin20", "h36m_351", 20, 5, "eval", seed=3, subsample=5)        # 17/18 valid, every alignment
+    forward_case("amass_351_train_masks", "amass_351", [5, 10, 20], 6, "train", seed=4)
+    # window + stride-mask generator (bit-exact contract)
+    stride_mask_case("eval_351_sin20", 71, 5, 20, "eval", 120, 150)
+    stride_mask_case("eval_81_sin10", 41, 2, 10, "eval", 60, 90)
+    stride_mask_case("train_351_mixed", 71, 5, [5, 10, 20], "train", 64, 400)
+    stride_mask_case("train_81_mixed", 41, 2, [4, 10, 20], "train", 64, 200)

@@ -1,0 +1,74 @@
+"""The oracle and the host logic against golden vectors produced by the REFERENCE's own code.
+
+tests/golden/*.npz were written by scripts/make_golden.py, which imports the reference's unmodified
+modules (constructor, network, weight_io loader, sequence generator) over the NumPy TensorFlow
+stand-in in oracle/tfshim and runs them on seeded inputs.  These tests need neither the reference
+nor a GPU: they pin oracle/forward_np.py, the weight inventory order, the .h5 writer and the
+stride-mask rule to what the reference computes."""
+import glob
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from oracle import forward_np as O
+from uplift_upsample_3dhpe_b200 import UpliftUpsampleConfig, spec_from_config, stride_mask, weights
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FORWARD = sorted(glob.glob(os.path.join(GOLDEN, "forward_*.npz")))
+WINDOWS = sorted(glob.glob(os.path.join(GOLDEN, "windows_*.npz")))
+
+
+def load_forward_case(path):
+    z = np.load(path, allow_pickle=False)
+    ms = z["mask_stride"]
+    ms = int(ms) if ms.ndim == 0 else [int(v) for v in ms]
+    cfg = UpliftUpsampleConfig.preset(str(z["config"]), MASK_STRIDE=ms)
+    spec = spec_from_config(cfg)
+    w = weights.init_weights(spec, seed=int(z["seed"]), perturb=True)
+    sha = hashlib.sha256(np.ascontiguousarray(weights.to_flat(spec, w)).tobytes()).hexdigest()[:16]
+    assert sha == str(z["weights_sha"]), "weights.init_weights changed: regenerate tests/golden (scripts/make_golden.py)"
+    return cfg, spec, w, z
+
+
+def test_fixtures_present():
+    assert len(FORWARD) >= 5 and len(WINDOWS) >= 4
+
+
+@pytest.mark.parametrize("path", FORWARD, ids=[os.path.basename(p)[8:-4] for p in FORWARD])
+def test_oracle_matches_reference_forward(path):
+    cfg, spec, w, z = load_forward_case(path)
+    x, m = z["x"], z["mask"]
+    valid = m.sum(axis=1) > 0
+    # float64: exact restatement => agreement to rounding noise on every window that has a valid token
+    full, central = O.test_step(spec, w, x, m, dtype=np.float64)
+    assert np.abs(central[valid] - z["central"][valid]).max() < 1e-9
+    assert np.abs(full[valid] - z["full"][valid]).max() < 1e-9
+    # float32: the precision TensorFlow computes in; it defines the all-masked windows (x - 1e9 rounds to -1e9)
+    full32, central32 = O.test_step(spec, w, x, m, dtype=np.float32)
+    assert full32.dtype == np.float32
+    assert np.abs(central32 - z["central_f32"]).max() < 2e-4
+    assert np.abs(full32 - z["full_f32"]).max() < 2e-4
+    if (~valid).any():     # the two precisions really disagree there, so the fp32 definition is load-bearing
+        assert np.abs(z["central_f32"][~valid] - z["central"][~valid]).max() > 1e-2
+
+
+@pytest.mark.parametrize("path", WINDOWS, ids=[os.path.basename(p)[8:-4] for p in WINDOWS])
+def test_stride_masks_are_bit_exact(path):
+    z = np.load(path, allow_pickle=False)
+    n_tok, stride, mode = int(z["n_tok"]), int(z["stride"]), str(z["mode"])
+    want = z["stride_masks"]
+    if mode == "eval":
+        got = stride_mask.batch_stride_masks_eval(n_tok, stride, int(z["mask_stride"]), z["centers"])
+    else:
+        got = stride_mask.batch_stride_masks_train(n_tok, stride, [int(v) for v in z["mask_stride"]], want.shape[0], seed=0)
+    assert got.dtype == np.bool_ and np.array_equal(got, want)
+    from uplift_upsample_3dhpe_b200 import _lib     # the C-ABI rule must agree too (host-only entry point)
+    import ctypes
+    lib = _lib.load()
+    if mode == "eval":
+        buf = (ctypes.c_uint8 * n_tok)()
+        for c, row in zip(z["centers"], want):
+            _lib.check(lib.uu_stride_mask(n_tok, stride, int(z["mask_stride"]), int(c), buf))
+            assert np.array_equal(np.frombuffer(buf, dtype=np.uint8).astype(bool), row)
