@@ -135,6 +135,11 @@ int uu_op_layernorm(float* x, int rows, int d, const float* gamma, const float* 
 int uu_op_attention(const void* qkv, int is_bf16, int B, int S, int heads, int dh, const uint8_t* keep_mask,
                     int mask_stride, void* out, void* stream);
 /* C = act(A @ W + bias) (+ res); flags: 1 = ReLU, 2 = residual.  fp32 CUDA-core GEMM, W is (K, N). */
+/* K2 alone: the fused spatial transformer (S1-S3 + spatial_norm, net:313-330) of a loaded model on the frames the
+ * mask keeps (mask NULL: all B*n_tok frames).  precision fp32 -> out is float, bf16 -> out is bf16; out holds
+ * [n_valid, 17*32] compact rows in gather-list order; n_valid_out (host) receives the row count. */
+int uu_op_spatial(uu_model* m, const float* x2d, const uint8_t* mask, int B, void* out, int32_t* n_valid_out,
+                  void* stream);
 int uu_op_gemm_f32(const float* A, int64_t lda, const float* W, int M, int N, int K, const float* bias, int flags,
                    const float* res, int64_t ldr, float* C, int64_t ldc, void* stream);
 /* tcgen05 GEMM: A bf16 (M, K) row-major, Wt bf16 (N_pad, K) = W^T with N_pad % 64 == 0. */

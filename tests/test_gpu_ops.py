@@ -186,3 +186,36 @@ def test_gemm_bf16_tcgen05(lib, M, N, K, flags, c_bf16):
     assert np.isfinite(got).all()
     err = np.abs(got - want).max()
     assert err < (5e-2 if c_bf16 else 1e-3), err
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("B,masked", [(3, False), (5, True), (40, True)])
+def test_spatial_transformer(lib, precision, B, masked):
+    """K2 alone (S1-S3 + spatial_norm) against the oracle's LayerNorm'd (frames, 544) features, valid frames only."""
+    from uplift_upsample_3dhpe_b200 import UpliftUpsampleConfig, spec_from_config, weights
+    from uplift_upsample_3dhpe_b200.model import build_uplift_upsample_transformer
+    cfg = UpliftUpsampleConfig.preset("h36m_351", MASK_STRIDE=20 if masked else 5)
+    spec = spec_from_config(cfg)
+    w = weights.init_weights(spec, 3, perturb=True)
+    rng = np.random.default_rng(B)
+    x = rng.uniform(-1, 1, (B, spec.n_tok, 17, 2)).astype(np.float32)
+    if masked:
+        m = np.stack([stride_mask.stride_mask(spec.n_tok, 5, 20, shift_tokens=b % 4 - 2) for b in range(B)])
+        m[1] = False
+    else:
+        m = np.ones((B, spec.n_tok), dtype=bool)
+    _, _, inter = O.forward(spec, w, x * m[:, :, None, None], m, dtype=np.float64, return_intermediates=True)
+    want = inter["spatial"].reshape(B * spec.n_tok, 544)[m.reshape(-1)]
+    model = build_uplift_upsample_transformer(cfg, precision=precision, weights=w)
+    out = torch.full((B * spec.n_tok, 544), float("nan"), dtype=torch.bfloat16 if precision == "bf16" else torch.float32,
+                     device="cuda")
+    n = ctypes.c_int32(-1)
+    _lib.check(lib.uu_op_spatial(model._h, P(dev(x)), P(dev(m.astype(np.uint8))) if masked else None, B, P(out),
+                                 ctypes.byref(n), None))
+    assert n.value == want.shape[0]
+    got = out.float().cpu().numpy()[:n.value]
+    assert np.isfinite(got).all()
+    err = np.abs(got - want).max()
+    print(f"spatial {precision} B={B} masked={masked}: max|err| {err:.3e} (|want|max {np.abs(want).max():.2f})")
+    assert err < (1e-4 if precision == "fp32" else 6e-2), err
+    model.close()

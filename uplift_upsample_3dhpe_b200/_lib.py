@@ -111,6 +111,7 @@ def _declare(lib) -> None:
     lib.uu_op_layernorm.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_void_p,
                                     c_int, c_void_p]
     lib.uu_op_attention.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]
+    lib.uu_op_spatial.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, P(c_int32), c_void_p]
     lib.uu_op_gemm_f32.argtypes = [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
                                    c_int64, c_void_p, c_int64, c_void_p]
     lib.uu_op_gemm_bf16.argtypes = [c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int,
@@ -126,7 +127,7 @@ EXPORTS = [
     "uu_forward", "uu_forward_host", "uu_last_launch_count", "uu_set_profiling", "uu_get_profile", "uu_stride_mask",
     "uu_train_config", "uu_train_forward_backward", "uu_grad_buffer", "uu_get_grad", "uu_get_droppath_scale",
     "uu_adamw_step", "uu_get_ema_weight",
-    "uu_op_build_gather", "uu_op_token_fill", "uu_op_layernorm", "uu_op_attention", "uu_op_gemm_f32",
+    "uu_op_build_gather", "uu_op_token_fill", "uu_op_layernorm", "uu_op_attention", "uu_op_spatial", "uu_op_gemm_f32",
     "uu_op_gemm_bf16",
 ]
 

@@ -1,17 +1,21 @@
-// K2 (bf16 path): fused spatial transformer on tensor cores.
+// K2 (bf16 path): fused spatial transformer, everything on tensor cores.
 //
 // reference: net:313-333 (spatial_transformation), vit:176-195 (TransformerBlock), vit:99-156 (MHA).
-// Shapes are tiny (17 joint tokens x 32 channels per frame, head_dim 4), so the kernel is built around
-// keeping everything on chip rather than around one big MMA:
-//   * a persistent CTA of 17 warps owns a group of 16 frames = 272 token rows = 17 row tiles of 16;
-//     warp w owns row tile w for the whole network, its residual stream lives in registers
+// Shapes are tiny (17 joint tokens x 32 channels per frame, 8 heads of dim 4), so the kernel is organised
+// around keeping a frame inside ONE warp:
+//   * a persistent CTA of 17 warps owns a group of 16 frames.  Warp w < 16 owns joints 0..15 of frame w as
+//     one m16 row tile; warp 16 owns joint 16 of all 16 frames.  The residual stream lives in registers
 //     (m16n8 accumulator layout) from the key-point embedding to the final LayerNorm;
-//   * the 32/64/96-wide linears run on mma.sync.m16n8k16 (bf16 x bf16 -> fp32); LayerNorm and GELU
-//     are applied on the accumulator fragments, which convert to the next A operand without shuffles;
-//   * all four blocks' weights sit in shared memory, pre-swizzled at weight-commit time into
-//     per-lane B-fragment order (one conflict-free 8-byte load per MMA);
-//   * only q/k/v (fp32) and the attention output (bf16) go through shared memory, because the
-//     17x17 attention of a frame needs rows owned by two different warps.
+//   * linears: mma.sync.m16n8k16 (bf16 x bf16 -> fp32) against weights held in shared memory, pre-swizzled at
+//     weight-commit time into per-lane B-fragment order; LayerNorm / GELU are applied on accumulator fragments;
+//   * attention (17 x 17, head_dim 4) never leaves the warp: Q K^T per head is two m16n8k8 MMAs whose A operand
+//     is the q accumulator masked to the head's 4 channels and whose B operand is the k accumulator as-is
+//     (C layout == col-major B layout); P V is one m16n8k16 MMA against V^T obtained with movmatrix.trans.  The V
+//     projection emits, per head, the columns [v0,1,v1,1,v2,1,v3,1], so the same MMA also yields the softmax
+//     row sums.  The 17th key is an extra MMA column / k-step fed from warp 16 through shared memory, the 17th
+//     query is evaluated in transposed form (keys as the M dimension) so that all 32 lanes hold live scores;
+//   * the softmax scale and log2(e) are folded into W_q, so scores come out of the tensor core in the exp2 domain.
+// Two block barriers per layer (joint-16 q/k/v out, joint-16 attention rows back); no other cross-warp traffic.
 // HBM traffic: 136 B of key-points in, 1088 B (17x32 bf16) out per frame.
 #include <algorithm>
 
@@ -22,21 +26,34 @@ namespace uu {
 namespace st {
 constexpr int J = 17, D = 32, HID = 64, HEADS = 8, DEPTH_MAX = 4;
 constexpr int FRAMES = 16;                  // frames per group
-constexpr int ROWS = FRAMES * J;            // 272 = 17 tiles of 16
 constexpr int WARPS = 17, THREADS = WARPS * 32;
-constexpr int QS = 100;                     // fp32 q|k|v row stride (96 + pad)
-constexpr int OS = 40;                      // bf16 attention-output row stride (32 + pad): conflict-free A loads
 // B-fragment image of one block: [frag][lane] uint2
-constexpr int F_QKV = 0, F_PROJ = 24, F_FC1 = 32, F_FC2 = 48, F_TOTAL = 64;
+constexpr int F_Q = 0, F_K = 8, F_V = 16, F_PROJ = 32, F_FC1 = 40, F_FC2 = 56, F_TOTAL = 72;
 // fp32 parameter image of one block
-constexpr int P_LN1G = 0, P_LN1B = 32, P_BQKV = 64, P_BP = 160, P_LN2G = 192, P_LN2B = 224, P_B1 = 256, P_B2 = 320,
-              P_TOTAL = 352;
+constexpr int P_LN1G = 0, P_LN1B = 32, P_BQKV = 64, P_BP = 192, P_LN2G = 224, P_LN2B = 256, P_B1 = 288, P_B2 = 352,
+              P_TOTAL = 384;
 // global fp32 parameters
 constexpr int G_EK = 0, G_EB = 64, G_PE = 96, G_NG = G_PE + J * D, G_NB = G_NG + 32, G_TOTAL = G_NB + 32;
+constexpr float QSCALE = 0.72134752044448170368f;     // (1 / sqrt(4)) * log2(e)
+constexpr int STG = 40;                     // bf16 row stride of the per-warp output staging tile (80 B)
+// joint-16 exchange area (bytes)
+constexpr int X_Q = 0, X_K = 1024, X_V = 2048, X_S = 4096, X_O = 4608, X_TOTAL = 5632;
+
+// physical channel read by logical k index `kap` (0..15) of k-step kk in the output projection: the attention
+// output of head h, dim dd sits in lane t == dd, and heads 4kk..4kk+3 fill the A-fragment slots 2t, 2t+1, 2t+8, 2t+9
+__host__ __device__ inline int proj_channel(int kk, int kap) {
+  const int hi = kap >= 8, k2 = kap & 7;
+  return 4 * (4 * kk + 2 * hi + (k2 & 1)) + (k2 >> 1);
+}
+// position of (head h, dim dd) in a row laid out in that A-fragment order
+__host__ __device__ inline int proj_position(int h, int dd) {
+  const int kk = h >> 2, i = h & 3;
+  return 16 * kk + ((i < 2) ? 2 * dd + i : 8 + 2 * dd + (i - 2));
+}
 }  // namespace st
 
 // ---- weight image (built once per uu_set_weight round) -------------------------------------------
-// frags: [depth][64][32] uint2 ; params: [depth][352] + [704] floats
+// frags: [depth][72][32] uint2 ; params: [depth][384] + [704] floats
 __global__ void k_spatial_pack(const float* const* __restrict__ blocks, int depth, const float* __restrict__ embed_k,
                                const float* __restrict__ embed_b, const float* __restrict__ pe,
                                const float* __restrict__ norm_g, const float* __restrict__ norm_b,
@@ -47,16 +64,28 @@ __global__ void k_spatial_pack(const float* const* __restrict__ blocks, int dept
     const int lane = i & 31, fr = (i >> 5) % F_TOTAL, l = (i >> 5) / F_TOTAL;
     const int g = lane >> 2, t = lane & 3;
     const float* const* tb = blocks + l * 16;
-    // which matrix, n-tile j, k-step kk
-    const float* Wm; int N, j, kk, ncol0 = 0;
-    if (fr < F_PROJ) { j = fr >> 1; kk = fr & 1; N = 32; const int which = j >> 2;   // q | k | v, 4 n-tiles each
-      Wm = tb[2 + 2 * which]; ncol0 = (j & 3) * 8; }
-    else if (fr < F_FC1) { const int f = fr - F_PROJ; j = f >> 1; kk = f & 1; N = 32; Wm = tb[8]; ncol0 = j * 8; }
-    else if (fr < F_FC2) { const int f = fr - F_FC1; j = f >> 1; kk = f & 1; N = 64; Wm = tb[12]; ncol0 = j * 8; }
-    else { const int f = fr - F_FC2; j = f >> 2; kk = f & 3; N = 32; Wm = tb[14]; ncol0 = j * 8; }
-    const int n = ncol0 + g, k0 = 16 * kk + 2 * t;
-    __nv_bfloat162 b0 = __floats2bfloat162_rn(Wm[(k0)*N + n], Wm[(k0 + 1) * N + n]);
-    __nv_bfloat162 b1 = __floats2bfloat162_rn(Wm[(k0 + 8) * N + n], Wm[(k0 + 9) * N + n]);
+    float w[4];                              // B[k0][n], B[k0+1][n], B[k0+8][n], B[k0+9][n]
+    if (fr < F_PROJ) {                       // q | k | v : K = 32 (two k-steps)
+      const int f = fr < F_K ? fr - F_Q : (fr < F_V ? fr - F_K : fr - F_V);
+      const int j = f >> 1, kk = f & 1;
+      for (int e = 0; e < 4; ++e) {
+        const int k = 16 * kk + 2 * t + (e & 1) + 8 * (e >> 1);
+        if (fr < F_K) w[e] = tb[2][k * 32 + 8 * j + g] * QSCALE;
+        else if (fr < F_V) w[e] = tb[4][k * 32 + 8 * j + g];
+        else w[e] = (g & 1) ? 0.f : tb[6][k * 32 + 4 * j + (g >> 1)];       // head j: [v0,1,v1,1,v2,1,v3,1]
+      }
+    } else if (fr < F_FC1) {                 // projection, permuted k order
+      const int f = fr - F_PROJ, j = f >> 1, kk = f & 1;
+      for (int e = 0; e < 4; ++e) w[e] = tb[8][proj_channel(kk, 2 * t + (e & 1) + 8 * (e >> 1)) * 32 + 8 * j + g];
+    } else if (fr < F_FC2) {
+      const int f = fr - F_FC1, j = f >> 1, kk = f & 1;
+      for (int e = 0; e < 4; ++e) w[e] = tb[12][(16 * kk + 2 * t + (e & 1) + 8 * (e >> 1)) * 64 + 8 * j + g];
+    } else {
+      const int f = fr - F_FC2, j = f >> 2, kk = f & 3;
+      for (int e = 0; e < 4; ++e) w[e] = tb[14][(16 * kk + 2 * t + (e & 1) + 8 * (e >> 1)) * 32 + 8 * j + g];
+    }
+    __nv_bfloat162 b0 = __floats2bfloat162_rn(w[0], w[1]);
+    __nv_bfloat162 b1 = __floats2bfloat162_rn(w[2], w[3]);
     uint2 o;
     o.x = *reinterpret_cast<uint32_t*>(&b0);
     o.y = *reinterpret_cast<uint32_t*>(&b1);
@@ -70,7 +99,12 @@ __global__ void k_spatial_pack(const float* const* __restrict__ blocks, int dept
       const float* const* tb = blocks + l * 16;
       if (o < P_LN1B) v = tb[0][o];
       else if (o < P_BQKV) v = tb[1][o - P_LN1B];
-      else if (o < P_BP) { const int c = o - P_BQKV; v = tb[3 + 2 * (c >> 5)][c & 31]; }
+      else if (o < P_BP) {                   // bias image of the 16 q|k|v n-tiles
+        const int c = o - P_BQKV, tile = c >> 3, col = c & 7;
+        if (tile < 4) v = tb[3][8 * tile + col] * QSCALE;
+        else if (tile < 8) v = tb[5][8 * (tile - 4) + col];
+        else v = (col & 1) ? 1.f : tb[7][4 * (tile - 8) + (col >> 1)];
+      }
       else if (o < P_LN2G) v = tb[9][o - P_BP];
       else if (o < P_LN2B) v = tb[10][o - P_LN2G];
       else if (o < P_B1) v = tb[11][o - P_LN2B];
@@ -99,11 +133,23 @@ cudaError_t launch_spatial_pack(const float* const* blocks, int depth, const flo
 }
 
 // ---- device helpers ---------------------------------------------------------------------------------
-__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], const uint2 b) {
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma1688(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(b0));
+}
+// 8x8 b16 transpose inside the warp: in (row g; cols 2t,2t+1) -> out (row g; cols 2t,2t+1) of the transpose
+__device__ __forceinline__ uint32_t movm_t(uint32_t a) {
+  uint32_t d;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+  return d;
 }
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -112,6 +158,24 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 __device__ __forceinline__ float quad_sum(float v) {
   v += __shfl_xor_sync(0xffffffffu, v, 1);
   v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
+}
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+  return v;
+}
+// reductions over the 8 row groups g (lanes with equal t)
+__device__ __forceinline__ float col_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 4));
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 8));
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 16));
+  return v;
+}
+__device__ __forceinline__ float col_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
   return v;
 }
 // GELU(x) = 0.5 x (1 + erf(x / sqrt 2)) with erf(x / sqrt 2) ~ tanh(x (a + x^2 (b + c x^2))): max |error| 3e-5 over
@@ -129,6 +193,11 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 
@@ -167,41 +236,6 @@ __device__ __forceinline__ void ln_to_afrag(const float (&x)[4][4], const float*
   }
 }
 
-// One (frame, head, query) item of the 17x17 attention: softmax(q k^T / 2) v in fp32, result as 4 bf16.
-__device__ __forceinline__ void attention_item(const float* __restrict__ s_qkv, bf16* __restrict__ s_o, int it) {
-  using namespace st;
-  const int pr = it / J, i = it - pr * J;
-  const int f = pr >> 3, h = pr & 7;
-  const float* base = s_qkv + f * J * QS + h * 4;
-  const float4 q = *reinterpret_cast<const float4*>(base + i * QS);
-  float s[J];
-  float mx = -INFINITY;
-#pragma unroll
-  for (int jj = 0; jj < J; ++jj) {
-    const float4 k4 = *reinterpret_cast<const float4*>(base + jj * QS + 32);
-    s[jj] = fmaf(q.w, k4.w, fmaf(q.z, k4.z, fmaf(q.y, k4.y, q.x * k4.x)));
-    mx = fmaxf(mx, s[jj]);
-  }
-  // softmax(s / sqrt(4)): exp((s - max)/2) = exp2(s * c - max * c), c = 0.5*log2(e)
-  const float sc = 0.72134752044448170368f;
-  const float nm = -mx * sc;
-  float sum = 0.f;
-  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-  for (int jj = 0; jj < J; ++jj) {
-    const float pj = ex2_approx(fmaf(s[jj], sc, nm));
-    sum += pj;
-    const float4 v4 = *reinterpret_cast<const float4*>(base + jj * QS + 64);
-    o.x = fmaf(pj, v4.x, o.x); o.y = fmaf(pj, v4.y, o.y);
-    o.z = fmaf(pj, v4.z, o.z); o.w = fmaf(pj, v4.w, o.w);
-  }
-  const float inv = __frcp_rn(sum);
-  uint2 pk;
-  pk.x = pack2(o.x * inv, o.y * inv);
-  pk.y = pack2(o.z * inv, o.w * inv);
-  *reinterpret_cast<uint2*>(s_o + (f * J + i) * OS + h * 4) = pk;       // heads merged: channel = 4h + d
-}
-
 struct SpatialTcParams {
   const float* x2d;      // (B*n_tok, 17, 2)
   const int* list;       // gather list or null
@@ -216,11 +250,17 @@ struct SpatialTcParams {
 __global__ void __launch_bounds__(st::THREADS, 1) k_spatial_tc(SpatialTcParams p) {
   using namespace st;
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  uint2* s_frag = reinterpret_cast<uint2*>(smem_raw);                              // depth*64*32 uint2
+  uint2* s_frag = reinterpret_cast<uint2*>(smem_raw);                              // depth*72*32 uint2
   float* s_par = reinterpret_cast<float*>(smem_raw + sizeof(uint2) * p.depth * F_TOTAL * 32);
-  float* s_qkv = s_par + ((p.depth * P_TOTAL + G_TOTAL + 3) & ~3);                 // ROWS * QS floats
-  bf16* s_o = reinterpret_cast<bf16*>(s_qkv + ROWS * QS);                          // ROWS * OS bf16
+  uint8_t* s_x = reinterpret_cast<uint8_t*>(s_par + ((p.depth * P_TOTAL + G_TOTAL + 3) & ~3));
+  bf16* xq16 = reinterpret_cast<bf16*>(s_x + X_Q);      // [16 frames][32] joint-16 q (exp2 domain)
+  bf16* xk16 = reinterpret_cast<bf16*>(s_x + X_K);      // [16][32]
+  bf16* xv16 = reinterpret_cast<bf16*>(s_x + X_V);      // [16][8 heads][v0,1,v1,1,v2,1,v3,1]
+  float* xs16 = reinterpret_cast<float*>(s_x + X_S);    // [16][8] score of (query 16, key 16)
+  bf16* xo16 = reinterpret_cast<bf16*>(s_x + X_O);      // [16][32] joint-16 attention rows, projection A order
+  bf16* s_stage = reinterpret_cast<bf16*>(s_x + X_TOTAL);   // [17 warps][16 rows][STG]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const bool w16 = warp == WARPS - 1;
 
   // weights -> shared memory, once per CTA
   {
@@ -234,8 +274,11 @@ __global__ void __launch_bounds__(st::THREADS, 1) k_spatial_tc(SpatialTcParams p
 
   const int n_valid = p.count ? *p.count : p.max_frames;
   const int n_groups = (n_valid + FRAMES - 1) / FRAMES;
-  const int r0 = warp * 16 + g, r1 = r0 + 8;        // the two token rows this thread holds pieces of
-  const int f0 = r0 / J, j0 = r0 - f0 * J, f1 = r1 / J, j1 = r1 - f1 * J;
+  // rows this thread holds pieces of: (frame, joint) of accumulator rows g and g+8
+  const int f0 = w16 ? g : warp, f1 = w16 ? g + 8 : warp;
+  const int j0 = w16 ? 16 : g, j1 = w16 ? 16 : g + 8;
+  const uint32_t hmask0 = (t < 2) ? 0xffffffffu : 0u, hmask1 = ~hmask0;   // lanes holding the even / odd head of a k8 slice
+  bf16* stg = s_stage + warp * 16 * STG;
 
   for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
     const int fbase = grp * FRAMES;
@@ -270,98 +313,215 @@ __global__ void __launch_bounds__(st::THREADS, 1) k_spatial_tc(SpatialTcParams p
       const uint2* fr = s_frag + l * F_TOTAL * 32 + lane;
       const float* bp = s_par + l * P_TOTAL;
       uint32_t a[2][4];
-      // ---- y = LN1(x); q|k|v = y @ Wqkv + b -> shared memory (fp32)
+      uint32_t ao[2][4];                      // attention output as the A operand of the projection
+      // ---- y = LN1(x); q|k|v = y @ Wqkv + b (bias preloaded into the accumulators)
       ln_to_afrag(x, bp + P_LN1G, bp + P_LN1B, 1e-5f, t, a);
+      uint32_t qa[4][2], kb[4][2], vt[8][2];
 #pragma unroll
-      for (int j = 0; j < 12; ++j) {
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
-        mma16816(c, a[0], fr[(F_QKV + 2 * j) * 32]);
-        mma16816(c, a[1], fr[(F_QKV + 2 * j + 1) * 32]);
-        const float2 b = *reinterpret_cast<const float2*>(bp + P_BQKV + 8 * j + 2 * t);
-        *reinterpret_cast<float2*>(s_qkv + r0 * QS + 8 * j + 2 * t) = make_float2(c[0] + b.x, c[1] + b.y);
-        *reinterpret_cast<float2*>(s_qkv + r1 * QS + 8 * j + 2 * t) = make_float2(c[2] + b.x, c[3] + b.y);
+      for (int tile = 0; tile < 16; ++tile) {
+        const float2 b = *reinterpret_cast<const float2*>(bp + P_BQKV + 8 * tile + 2 * t);
+        float c[4] = {b.x, b.y, b.x, b.y};
+        const uint2 w0 = fr[(2 * tile) * 32], w1 = fr[(2 * tile + 1) * 32];
+        mma16816(c, a[0], w0.x, w0.y);
+        mma16816(c, a[1], w1.x, w1.y);
+        const uint32_t lo = pack2(c[0], c[1]), hi = pack2(c[2], c[3]);     // rows g / g+8, cols 2t,2t+1 of the tile
+        if (tile < 4) { qa[tile][0] = lo; qa[tile][1] = hi; }
+        else if (tile < 8) { kb[tile - 4][0] = lo; kb[tile - 4][1] = hi; }
+        else { vt[tile - 8][0] = lo; vt[tile - 8][1] = hi; }
       }
-      __syncthreads();
-      // ---- attention: 16 frames x 8 heads x 17 queries = 2176 items, 4 per thread (vit:117-129);
-      //      two independent items per iteration keep more shared-memory loads in flight
-#pragma unroll 1
-      for (int it = tid; it < FRAMES * HEADS * J; it += 2 * THREADS) {
-        attention_item(s_qkv, s_o, it);
-        attention_item(s_qkv, s_o, it + THREADS);
-      }
-      __syncthreads();
-      // ---- x += attn @ Wp + bp
-      {
-        uint32_t ao[2][4];
-#pragma unroll
-        for (int kk = 0; kk < 2; ++kk) {
-          ao[kk][0] = *reinterpret_cast<const uint32_t*>(s_o + r0 * OS + 16 * kk + 2 * t);
-          ao[kk][1] = *reinterpret_cast<const uint32_t*>(s_o + r1 * OS + 16 * kk + 2 * t);
-          ao[kk][2] = *reinterpret_cast<const uint32_t*>(s_o + r0 * OS + 16 * kk + 8 + 2 * t);
-          ao[kk][3] = *reinterpret_cast<const uint32_t*>(s_o + r1 * OS + 16 * kk + 8 + 2 * t);
-        }
+      if (w16) {
+        // joint 16 of 16 frames: publish q, k, v and the (query 16, key 16) scores
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          float c[4] = {0.f, 0.f, 0.f, 0.f};
-          mma16816(c, ao[0], fr[(F_PROJ + 2 * j) * 32]);
-          mma16816(c, ao[1], fr[(F_PROJ + 2 * j + 1) * 32]);
-          const float2 b = *reinterpret_cast<const float2*>(bp + P_BP + 8 * j + 2 * t);
-          x[j][0] += c[0] + b.x; x[j][1] += c[1] + b.y; x[j][2] += c[2] + b.x; x[j][3] += c[3] + b.y;
+          *reinterpret_cast<uint32_t*>(xq16 + g * 32 + 8 * j + 2 * t) = qa[j][0];
+          *reinterpret_cast<uint32_t*>(xq16 + (g + 8) * 32 + 8 * j + 2 * t) = qa[j][1];
+          *reinterpret_cast<uint32_t*>(xk16 + g * 32 + 8 * j + 2 * t) = kb[j][0];
+          *reinterpret_cast<uint32_t*>(xk16 + (g + 8) * 32 + 8 * j + 2 * t) = kb[j][1];
+          // q.k over the two channels this lane holds, completed with the neighbour lane (t ^ 1): head 2j + (t >> 1)
+          const __nv_bfloat162 q0 = *reinterpret_cast<const __nv_bfloat162*>(&qa[j][0]);
+          const __nv_bfloat162 q1 = *reinterpret_cast<const __nv_bfloat162*>(&qa[j][1]);
+          const __nv_bfloat162 k0 = *reinterpret_cast<const __nv_bfloat162*>(&kb[j][0]);
+          const __nv_bfloat162 k1 = *reinterpret_cast<const __nv_bfloat162*>(&kb[j][1]);
+          float d0 = __low2float(q0) * __low2float(k0) + __high2float(q0) * __high2float(k0);
+          float d1 = __low2float(q1) * __low2float(k1) + __high2float(q1) * __high2float(k1);
+          d0 += __shfl_xor_sync(0xffffffffu, d0, 1);
+          d1 += __shfl_xor_sync(0xffffffffu, d1, 1);
+          if ((t & 1) == 0) {
+            xs16[g * 8 + 2 * j + (t >> 1)] = d0;
+            xs16[(g + 8) * 8 + 2 * j + (t >> 1)] = d1;
+          }
         }
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+          *reinterpret_cast<uint32_t*>(xv16 + g * 64 + 8 * h + 2 * t) = vt[h][0];
+          *reinterpret_cast<uint32_t*>(xv16 + (g + 8) * 64 + 8 * h + 2 * t) = vt[h][1];
+        }
+      }
+      __syncthreads();
+      if (!w16) {
+        // ---- attention of frame `warp`: queries/keys 0..15 in registers, key/query 16 from shared memory
+#pragma unroll
+        for (int h = 0; h < 8; ++h) { vt[h][0] = movm_t(vt[h][0]); vt[h][1] = movm_t(vt[h][1]); }   // -> V^T B fragments
+        const bf16* q16 = xq16 + warp * 32;
+        const bf16* k16 = xk16 + warp * 32;
+        const bf16* v16 = xv16 + warp * 64;
+        // scores against key 16: s16[0/1] = (row g; heads 2t, 2t+1), s16[2/3] = (row g+8; ...).
+        // scores of query 16 (transposed): t16[0/1] = (key g; heads 2t, 2t+1), t16[2/3] = (key g+8; ...).
+        float s16[4] = {0.f, 0.f, 0.f, 0.f}, t16[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool mine = g == 2 * j + (t >> 1);           // B[k = 2t,2t+1][n = g] is non-zero iff channel's head == g
+          const uint32_t bk = mine ? *reinterpret_cast<const uint32_t*>(k16 + 8 * j + 2 * t) : 0u;
+          const uint32_t bq = mine ? *reinterpret_cast<const uint32_t*>(q16 + 8 * j + 2 * t) : 0u;
+          mma1688(s16, qa[j][0], qa[j][1], bk);
+          mma1688(t16, kb[j][0], kb[j][1], bq);
+        }
+        // B fragment of the key-16 step of P V: (k = heads 2t,2t+1; n = g) = v16ext[head][g]
+        uint32_t bv16;
+        {
+          const uint16_t lo = *reinterpret_cast<const uint16_t*>(v16 + 8 * (2 * t) + g);
+          const uint16_t hi = *reinterpret_cast<const uint16_t*>(v16 + 8 * (2 * t + 1) + g);
+          bv16 = (uint32_t)lo | ((uint32_t)hi << 16);
+        }
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+          const int j = h >> 1, e = h & 1;
+          const uint32_t hm = e ? hmask1 : hmask0;
+          const uint32_t a0 = qa[j][0] & hm, a1 = qa[j][1] & hm;
+          float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+          mma1688(s0, a0, a1, kb[j][0]);        // keys 0..7
+          mma1688(s1, a0, a1, kb[j][1]);        // keys 8..15
+          const bool owner = t == (h >> 1);     // this lane holds the key-16 score of head h
+          float mg = fmaxf(fmaxf(s0[0], s0[1]), fmaxf(s1[0], s1[1]));
+          float mh = fmaxf(fmaxf(s0[2], s0[3]), fmaxf(s1[2], s1[3]));
+          if (owner) { mg = fmaxf(mg, s16[e]); mh = fmaxf(mh, s16[2 + e]); }
+          mg = quad_max(mg);
+          mh = quad_max(mh);
+          uint32_t pa[4];
+          pa[0] = pack2(ex2_approx(s0[0] - mg), ex2_approx(s0[1] - mg));
+          pa[1] = pack2(ex2_approx(s0[2] - mh), ex2_approx(s0[3] - mh));
+          pa[2] = pack2(ex2_approx(s1[0] - mg), ex2_approx(s1[1] - mg));
+          pa[3] = pack2(ex2_approx(s1[2] - mh), ex2_approx(s1[3] - mh));
+          const float pg = owner ? ex2_approx(s16[e] - mg) : 0.f;
+          const float ph = owner ? ex2_approx(s16[2 + e] - mh) : 0.f;
+          float o[4] = {0.f, 0.f, 0.f, 0.f};
+          mma16816(o, pa, vt[h][0], vt[h][1]);  // o[0] = sum_k p v[ch t], o[1] = sum_k p   (row g); o[2], o[3]: row g+8
+          mma1688(o, e ? pack2(0.f, pg) : pack2(pg, 0.f), e ? pack2(0.f, ph) : pack2(ph, 0.f), bv16);   // key 16
+          const float og = o[0] * rcp_approx(o[1]), oh = o[2] * rcp_approx(o[3]);
+          // heads 4kk..4kk+3 fill slots (2t,2t+1 | 2t+8,2t+9) of k-step kk: pairs (h, h+1) pack into one register
+          if (e == 0) {
+            ao[h >> 2][(h & 2) ? 2 : 0] = __float_as_uint(og);      // parked as fp32 until the odd head arrives
+            ao[h >> 2][(h & 2) ? 3 : 1] = __float_as_uint(oh);
+          } else {
+            ao[h >> 2][(h & 2) ? 2 : 0] = pack2(__uint_as_float(ao[h >> 2][(h & 2) ? 2 : 0]), og);
+            ao[h >> 2][(h & 2) ? 3 : 1] = pack2(__uint_as_float(ao[h >> 2][(h & 2) ? 3 : 1]), oh);
+          }
+        }
+        // ---- query 16 (joint 16 of this frame): softmax over the 17 keys with keys as the M dimension
+        {
+          const float sA = xs16[warp * 8 + 2 * t], sB = xs16[warp * 8 + 2 * t + 1];
+          const float mA = fmaxf(col_max(fmaxf(t16[0], t16[2])), sA);
+          const float mB = fmaxf(col_max(fmaxf(t16[1], t16[3])), sB);
+          float pA0 = ex2_approx(t16[0] - mA), pA1 = ex2_approx(t16[2] - mA), pA16 = ex2_approx(sA - mA);
+          float pB0 = ex2_approx(t16[1] - mB), pB1 = ex2_approx(t16[3] - mB), pB16 = ex2_approx(sB - mB);
+          const float iA = rcp_approx(col_sum(pA0 + pA1) + pA16), iB = rcp_approx(col_sum(pB0 + pB1) + pB16);
+          pA0 *= iA; pA1 *= iA; pA16 *= iA;
+          pB0 *= iB; pB1 *= iB; pB16 *= iB;
+          // (key g; heads 2t,2t+1) -> transpose -> (head g; keys 2t,2t+1): A fragments with heads as rows
+          const uint32_t pt0 = movm_t(pack2(pA0, pB0)), pt1 = movm_t(pack2(pA1, pB1));
+          float e16[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int h = 0; h < 8; ++h) {        // row h of the product with head h's V^T; other rows masked to zero
+            const uint32_t aa[4] = {g == h ? pt0 : 0u, 0u, g == h ? pt1 : 0u, 0u};
+            mma16816(e16, aa, vt[h][0], vt[h][1]);
+          }
+          // e16[0] = (head g, dim t) over keys 0..15; add key 16 with the normalised weight of head g
+          const float v0 = __shfl_sync(0xffffffffu, pA16, g >> 1), v1 = __shfl_sync(0xffffffffu, pB16, g >> 1);
+          const float pn = (g & 1) ? v1 : v0;
+          const float out = fmaf(pn, __bfloat162float(v16[8 * g + 2 * t]), e16[0]);
+          xo16[warp * 32 + proj_position(g, t)] = __float2bfloat16_rn(out);
+        }
+      }
+      __syncthreads();
+      if (w16) {
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          ao[kk][0] = *reinterpret_cast<const uint32_t*>(xo16 + g * 32 + 16 * kk + 2 * t);
+          ao[kk][1] = *reinterpret_cast<const uint32_t*>(xo16 + (g + 8) * 32 + 16 * kk + 2 * t);
+          ao[kk][2] = *reinterpret_cast<const uint32_t*>(xo16 + g * 32 + 16 * kk + 8 + 2 * t);
+          ao[kk][3] = *reinterpret_cast<const uint32_t*>(xo16 + (g + 8) * 32 + 16 * kk + 8 + 2 * t);
+        }
+      }
+      // ---- x += attn @ Wp + bp   (projection rows permuted to the A order above)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+        const uint2 w0 = fr[(F_PROJ + 2 * j) * 32], w1 = fr[(F_PROJ + 2 * j + 1) * 32];
+        mma16816(c, ao[0], w0.x, w0.y);
+        mma16816(c, ao[1], w1.x, w1.y);
+        const float2 b = *reinterpret_cast<const float2*>(bp + P_BP + 8 * j + 2 * t);
+        x[j][0] += c[0] + b.x; x[j][1] += c[1] + b.y; x[j][2] += c[2] + b.x; x[j][3] += c[3] + b.y;
       }
       // ---- x += fc2(gelu(fc1(LN2(x))))
       ln_to_afrag(x, bp + P_LN2G, bp + P_LN2B, 1e-5f, t, a);
       uint32_t ah[4][4];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
-        mma16816(c, a[0], fr[(F_FC1 + 2 * j) * 32]);
-        mma16816(c, a[1], fr[(F_FC1 + 2 * j + 1) * 32]);
         const float2 b = *reinterpret_cast<const float2*>(bp + P_B1 + 8 * j + 2 * t);
-        const float h0 = gelu_erf_fast(c[0] + b.x), h1 = gelu_erf_fast(c[1] + b.y);
-        const float h2 = gelu_erf_fast(c[2] + b.x), h3 = gelu_erf_fast(c[3] + b.y);
+        float c[4] = {b.x, b.y, b.x, b.y};
+        const uint2 w0 = fr[(F_FC1 + 2 * j) * 32], w1 = fr[(F_FC1 + 2 * j + 1) * 32];
+        mma16816(c, a[0], w0.x, w0.y);
+        mma16816(c, a[1], w1.x, w1.y);
         // accumulator n-tile j -> A fragment of k-step j/2 (cols 16*(j/2) + 8*(j&1) + 2t)
-        ah[j >> 1][(j & 1) * 2] = pack2(h0, h1);
-        ah[j >> 1][(j & 1) * 2 + 1] = pack2(h2, h3);
+        ah[j >> 1][(j & 1) * 2] = pack2(gelu_erf_fast(c[0]), gelu_erf_fast(c[1]));
+        ah[j >> 1][(j & 1) * 2 + 1] = pack2(gelu_erf_fast(c[2]), gelu_erf_fast(c[3]));
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float c[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) mma16816(c, ah[kk], fr[(F_FC2 + 4 * j + kk) * 32]);
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint2 w = fr[(F_FC2 + 4 * j + kk) * 32];
+          mma16816(c, ah[kk], w.x, w.y);
+        }
         const float2 b = *reinterpret_cast<const float2*>(bp + P_B2 + 8 * j + 2 * t);
         x[j][0] += c[0] + b.x; x[j][1] += c[1] + b.y; x[j][2] += c[2] + b.x; x[j][3] += c[3] + b.y;
       }
     }
 
-    // ---- spatial_norm (eps 1e-6, net:238), joint-major flatten (net:330): 16 frames x 544 bf16 contiguous
+    // ---- spatial_norm (eps 1e-6, net:238), joint-major flatten (net:330): frame row = 17 x 32 bf16
     {
       uint32_t a[2][4];
       ln_to_afrag(x, gp + G_NG, gp + G_NB, 1e-6f, t, a);
-      // stage in shared memory (the q|k|v buffer is free: every warp is past the last attention)
-      uint32_t* stage = reinterpret_cast<uint32_t*>(s_qkv);     // [ROWS][16] words (32 bf16 per row)
+      __syncwarp();
+      uint32_t* sw = reinterpret_cast<uint32_t*>(stg);             // per-warp tile [16 rows][STG/2 words]
 #pragma unroll
       for (int kk = 0; kk < 2; ++kk) {
-        stage[r0 * 16 + 8 * kk + t] = a[kk][0];          // cols 16kk + 2t
-        stage[r1 * 16 + 8 * kk + t] = a[kk][1];
-        stage[r0 * 16 + 8 * kk + 4 + t] = a[kk][2];      // cols 16kk + 8 + 2t
-        stage[r1 * 16 + 8 * kk + 4 + t] = a[kk][3];
+        sw[g * (STG / 2) + 8 * kk + t] = a[kk][0];                  // cols 16kk + 2t
+        sw[(g + 8) * (STG / 2) + 8 * kk + t] = a[kk][1];
+        sw[g * (STG / 2) + 8 * kk + 4 + t] = a[kk][2];              // cols 16kk + 8 + 2t
+        sw[(g + 8) * (STG / 2) + 8 * kk + 4 + t] = a[kk][3];
       }
-      __syncthreads();
-      const int frames_here = min(FRAMES, n_valid - fbase);
-      const int n16 = frames_here * J * D * 2 / 16;                 // 16-byte chunks
-      const uint4* src = reinterpret_cast<const uint4*>(s_qkv);
-      uint4* dst = reinterpret_cast<uint4*>(p.out + (long long)fbase * J * D);
-      for (int i = tid; i < n16; i += THREADS) dst[i] = src[i];
-      __syncthreads();                                              // staging is reused as q|k|v by the next group
+      __syncwarp();
+      // 16 rows x 64 B = 64 chunks of 16 B, two per lane.  Warp w < 16: one contiguous 1 KB run of frame w;
+      // warp 16: the last 64 B of each of the 16 frames.
+#pragma unroll
+      for (int i = lane; i < 64; i += 32) {
+        const int r = i >> 2, c = i & 3;
+        const int frame = w16 ? fbase + r : fbase + warp;
+        const int joint = w16 ? 16 : r;
+        if (frame < n_valid)
+          *reinterpret_cast<uint4*>(p.out + ((long long)frame * J + joint) * D + c * 8) =
+              *reinterpret_cast<const uint4*>(stg + r * STG + c * 8);
+      }
     }
   }
 }
 
 size_t spatial_tc_smem_bytes(int depth) {
   using namespace st;
-  return sizeof(uint2) * depth * F_TOTAL * 32 + sizeof(float) * ((depth * P_TOTAL + G_TOTAL + 3) & ~3) +
-         sizeof(float) * ROWS * QS + sizeof(bf16) * ROWS * OS;
+  return sizeof(uint2) * depth * F_TOTAL * 32 + sizeof(float) * ((depth * P_TOTAL + G_TOTAL + 3) & ~3) + X_TOTAL +
+         sizeof(bf16) * WARPS * 16 * STG;
 }
 
 cudaError_t launch_spatial_tc(const float* x2d, const int* list, const int* count, int max_frames, int depth,

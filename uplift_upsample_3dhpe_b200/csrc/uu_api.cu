@@ -777,6 +777,38 @@ int uu_op_attention(const void* qkv, int is_bf16, int B, int S, int heads, int d
   UU_CUDA(launch_attention(qkv, is_bf16, B, S, heads, dh, keep_mask, mask_stride, out, (cudaStream_t)stream));
   return 0;
 }
+int uu_op_spatial(uu_model* m, const float* x2d, const uint8_t* mask, int B, void* out, int32_t* n_valid_out,
+                  void* stream) {
+  UU_CHECK(m && x2d && out && B > 0, "bad argument");
+  const uu_spec& s = m->spec;
+  cudaStream_t st = (cudaStream_t)stream;
+  UU_CUDA(cudaSetDevice(m->device));
+  if (commit_weights(m)) return 1;
+  if (ensure_workspace(m, B)) return 1;
+  const int R = B * s.n_tok;
+  const bool use_mask = mask != nullptr;
+  if (use_mask) UU_CUDA(launch_build_gather(mask, B, s.n_tok, m->g_scratch, m->g_list, m->g_count, st));
+  if (m->precision == UU_PRECISION_BF16) {
+    UU_CUDA(launch_spatial_tc(x2d, use_mask ? m->g_list : nullptr, use_mask ? m->g_count : nullptr, R, s.spatial_depth,
+                              m->sp_frags, m->sp_params, (bf16*)out, m->num_sms, st));
+  } else {
+    SpatialParams sp;
+    sp.x2d = x2d; sp.list = use_mask ? m->g_list : nullptr; sp.count = use_mask ? m->g_count : nullptr;
+    sp.max_frames = R; sp.J = s.n_joints; sp.depth = s.spatial_depth;
+    sp.embed_k = W(m, "keypoint_embedding", 0); sp.embed_b = W(m, "keypoint_embedding", 1);
+    sp.pe = W(m, "spatial_pe", 0); sp.blocks = m->spatial_ptrs;
+    sp.norm_g = W(m, "spatial_norm", 0); sp.norm_b = W(m, "spatial_norm", 1);
+    sp.out = out; sp.out_bf16 = 0;
+    UU_CUDA(launch_spatial_f32(sp, st));
+  }
+  int n = R;
+  if (use_mask) {
+    UU_CUDA(cudaMemcpyAsync(&n, m->g_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+  }
+  UU_CUDA(cudaStreamSynchronize(st));
+  if (n_valid_out) *n_valid_out = n;
+  return 0;
+}
 int uu_op_gemm_f32(const float* A, int64_t lda, const float* Wm, int M, int N, int K, const float* bias, int flags,
                    const float* res, int64_t ldr, float* C, int64_t ldc, void* stream) {
   Epilogue e;
