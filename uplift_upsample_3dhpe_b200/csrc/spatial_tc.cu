@@ -3,9 +3,9 @@
 // reference: net:313-333 (spatial_transformation), vit:176-195 (TransformerBlock), vit:99-156 (MHA).
 // Shapes are tiny (17 joint tokens x 32 channels per frame, 8 heads of dim 4), so the kernel is organised
 // around keeping a frame inside ONE warp:
-//   * a persistent CTA of 17 warps owns a group of 16 frames.  Warp w < 16 owns joints 0..15 of frame w as
-//     one m16 row tile; warp 16 owns joint 16 of all 16 frames.  The residual stream lives in registers
-//     (m16n8 accumulator layout) from the key-point embedding to the final LayerNorm;
+//   * a persistent CTA of 16 warps (4 per scheduler, 128 registers each) owns a group of 15 frames.  Warp w < 15
+//     owns joints 0..15 of frame w as one m16 row tile; warp 15 owns joint 16 of all 15 frames.  The residual
+//     stream lives in registers (m16n8 accumulator layout) from the key-point embedding to the final LayerNorm;
 //   * linears: mma.sync.m16n8k16 (bf16 x bf16 -> fp32) against weights held in shared memory, pre-swizzled at
 //     weight-commit time into per-lane B-fragment order; LayerNorm / GELU are applied on accumulator fragments;
 //   * attention (17 x 17, head_dim 4) never leaves the warp: Q K^T per head is two m16n8k8 MMAs whose A operand
@@ -15,7 +15,8 @@
 //     row sums.  The 17th key is an extra MMA column / k-step fed from warp 16 through shared memory, the 17th
 //     query is evaluated in transposed form (keys as the M dimension) so that all 32 lanes hold live scores;
 //   * the softmax scale and log2(e) are folded into W_q, so scores come out of the tensor core in the exp2 domain.
-// Two block barriers per layer (joint-16 q/k/v out, joint-16 attention rows back); no other cross-warp traffic.
+// Cross-warp traffic is two point-to-point mbarrier hand-offs per layer (joint-16 q/k/v out, joint-16 attention
+// rows back); frame warps never wait for each other.
 // HBM traffic: 136 B of key-points in, 1088 B (17x32 bf16) out per frame.
 #include <algorithm>
 
@@ -25,8 +26,8 @@ namespace uu {
 
 namespace st {
 constexpr int J = 17, D = 32, HID = 64, HEADS = 8, DEPTH_MAX = 4;
-constexpr int FRAMES = 16;                  // frames per group
-constexpr int WARPS = 17, THREADS = WARPS * 32;
+constexpr int FRAMES = 15;                  // frames per group
+constexpr int WARPS = 16, THREADS = WARPS * 32;
 // B-fragment image of one block: [frag][lane] uint2
 constexpr int F_Q = 0, F_K = 8, F_V = 16, F_PROJ = 32, F_FC1 = 40, F_FC2 = 56, F_TOTAL = 72;
 // fp32 parameter image of one block
@@ -37,7 +38,7 @@ constexpr int G_EK = 0, G_EB = 64, G_PE = 96, G_NG = G_PE + J * D, G_NB = G_NG +
 constexpr float QSCALE = 0.72134752044448170368f;     // (1 / sqrt(4)) * log2(e)
 constexpr int STG = 40;                     // bf16 row stride of the per-warp output staging tile (80 B)
 // joint-16 exchange area (bytes)
-constexpr int X_Q = 0, X_K = 1024, X_V = 2048, X_S = 4096, X_O = 4608, X_TOTAL = 5632;
+constexpr int X_Q = 0, X_K = 1024, X_V = 2048, X_S = 4096, X_O = 4608, X_BAR = 5632, X_TOTAL = 5648;
 
 // physical channel read by logical k index `kap` (0..15) of k-step kk in the output projection: the attention
 // output of head h, dim dd sits in lane t == dd, and heads 4kk..4kk+3 fill the A-fragment slots 2t, 2t+1, 2t+8, 2t+9
@@ -151,6 +152,32 @@ __device__ __forceinline__ uint32_t movm_t(uint32_t a) {
   asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
   return d;
 }
+// point-to-point hand-off between the joint-16 warp and the frame warps
+__device__ __forceinline__ void sp_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void sp_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void sp_mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(bar);
+  const long long t0 = clock64();
+  while (true) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 4000000000LL) {     // a protocol bug must trap, not hang the GPU
+      printf("uu3d: spatial mbarrier timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -258,7 +285,9 @@ __global__ void __launch_bounds__(st::THREADS, 1) k_spatial_tc(SpatialTcParams p
   bf16* xv16 = reinterpret_cast<bf16*>(s_x + X_V);      // [16][8 heads][v0,1,v1,1,v2,1,v3,1]
   float* xs16 = reinterpret_cast<float*>(s_x + X_S);    // [16][8] score of (query 16, key 16)
   bf16* xo16 = reinterpret_cast<bf16*>(s_x + X_O);      // [16][32] joint-16 attention rows, projection A order
-  bf16* s_stage = reinterpret_cast<bf16*>(s_x + X_TOTAL);   // [17 warps][16 rows][STG]
+  uint64_t* bar_pub = reinterpret_cast<uint64_t*>(s_x + X_BAR);   // joint-16 warp -> frame warps (1 arrival)
+  uint64_t* bar_ret = bar_pub + 1;                                // frame warps -> joint-16 warp (FRAMES arrivals)
+  bf16* s_stage = reinterpret_cast<bf16*>(s_x + X_TOTAL);   // [16 warps][16 rows][STG]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const bool w16 = warp == WARPS - 1;
 
@@ -268,13 +297,20 @@ __global__ void __launch_bounds__(st::THREADS, 1) k_spatial_tc(SpatialTcParams p
     for (int i = tid; i < nf; i += THREADS) s_frag[i] = p.frags[i];
     const int np = p.depth * P_TOTAL + G_TOTAL;
     for (int i = tid; i < np; i += THREADS) s_par[i] = p.params[i];
+    if (tid == 0) {
+      sp_mbar_init(bar_pub, 1);
+      sp_mbar_init(bar_ret, FRAMES);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
   }
   __syncthreads();
+  uint32_t phase = 0;                               // one hand-off pair per (group, layer)
   const float* gp = s_par + p.depth * P_TOTAL;      // global params
 
   const int n_valid = p.count ? *p.count : p.max_frames;
   const int n_groups = (n_valid + FRAMES - 1) / FRAMES;
   // rows this thread holds pieces of: (frame, joint) of accumulator rows g and g+8
+  // (the joint-16 tile has 15 live rows; row 15 computes on zeros and is never stored)
   const int f0 = w16 ? g : warp, f1 = w16 ? g + 8 : warp;
   const int j0 = w16 ? 16 : g, j1 = w16 ? 16 : g + 8;
   const uint32_t hmask0 = (t < 2) ? 0xffffffffu : 0u, hmask1 = ~hmask0;   // lanes holding the even / odd head of a k8 slice
@@ -286,11 +322,11 @@ __global__ void __launch_bounds__(st::THREADS, 1) k_spatial_tc(SpatialTcParams p
     float x[4][4];
     {
       float2 p0 = make_float2(0.f, 0.f), p1 = make_float2(0.f, 0.f);
-      if (fbase + f0 < n_valid) {
+      if (f0 < FRAMES && fbase + f0 < n_valid) {
         const int fr = p.list ? p.list[fbase + f0] : fbase + f0;
         p0 = *reinterpret_cast<const float2*>(p.x2d + ((long long)fr * J + j0) * 2);
       }
-      if (fbase + f1 < n_valid) {
+      if (f1 < FRAMES && fbase + f1 < n_valid) {
         const int fr = p.list ? p.list[fbase + f1] : fbase + f1;
         p1 = *reinterpret_cast<const float2*>(p.x2d + ((long long)fr * J + j1) * 2);
       }
@@ -309,7 +345,7 @@ __global__ void __launch_bounds__(st::THREADS, 1) k_spatial_tc(SpatialTcParams p
       }
     }
 
-    for (int l = 0; l < p.depth; ++l) {
+    for (int l = 0; l < p.depth; ++l, phase ^= 1) {
       const uint2* fr = s_frag + l * F_TOTAL * 32 + lane;
       const float* bp = s_par + l * P_TOTAL;
       uint32_t a[2][4];
@@ -356,12 +392,13 @@ __global__ void __launch_bounds__(st::THREADS, 1) k_spatial_tc(SpatialTcParams p
           *reinterpret_cast<uint32_t*>(xv16 + g * 64 + 8 * h + 2 * t) = vt[h][0];
           *reinterpret_cast<uint32_t*>(xv16 + (g + 8) * 64 + 8 * h + 2 * t) = vt[h][1];
         }
-      }
-      __syncthreads();
-      if (!w16) {
+        __syncwarp();
+        if (lane == 0) sp_mbar_arrive(bar_pub);
+      } else {
         // ---- attention of frame `warp`: queries/keys 0..15 in registers, key/query 16 from shared memory
 #pragma unroll
         for (int h = 0; h < 8; ++h) { vt[h][0] = movm_t(vt[h][0]); vt[h][1] = movm_t(vt[h][1]); }   // -> V^T B fragments
+        sp_mbar_wait(bar_pub, phase);
         const bf16* q16 = xq16 + warp * 32;
         const bf16* k16 = xk16 + warp * 32;
         const bf16* v16 = xv16 + warp * 64;
@@ -441,9 +478,11 @@ __global__ void __launch_bounds__(st::THREADS, 1) k_spatial_tc(SpatialTcParams p
           const float out = fmaf(pn, __bfloat162float(v16[8 * g + 2 * t]), e16[0]);
           xo16[warp * 32 + proj_position(g, t)] = __float2bfloat16_rn(out);
         }
+        __syncwarp();
+        if (lane == 0) sp_mbar_arrive(bar_ret);
       }
-      __syncthreads();
       if (w16) {
+        sp_mbar_wait(bar_ret, phase);
 #pragma unroll
         for (int kk = 0; kk < 2; ++kk) {
           ao[kk][0] = *reinterpret_cast<const uint32_t*>(xo16 + g * 32 + 16 * kk + 2 * t);
@@ -503,14 +542,14 @@ __global__ void __launch_bounds__(st::THREADS, 1) k_spatial_tc(SpatialTcParams p
         sw[(g + 8) * (STG / 2) + 8 * kk + 4 + t] = a[kk][3];
       }
       __syncwarp();
-      // 16 rows x 64 B = 64 chunks of 16 B, two per lane.  Warp w < 16: one contiguous 1 KB run of frame w;
-      // warp 16: the last 64 B of each of the 16 frames.
+      // 16 rows x 64 B = 64 chunks of 16 B, two per lane.  Frame warp w: one contiguous 1 KB run of frame w;
+      // joint-16 warp: the last 64 B of each of the 15 frames.
 #pragma unroll
       for (int i = lane; i < 64; i += 32) {
         const int r = i >> 2, c = i & 3;
         const int frame = w16 ? fbase + r : fbase + warp;
         const int joint = w16 ? 16 : r;
-        if (frame < n_valid)
+        if (frame < n_valid && r < (w16 ? FRAMES : 16))
           *reinterpret_cast<uint4*>(p.out + ((long long)frame * J + joint) * D + c * 8) =
               *reinterpret_cast<const uint4*>(stg + r * STG + c * 8);
       }
