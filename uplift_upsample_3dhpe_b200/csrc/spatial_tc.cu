@@ -14,11 +14,17 @@
 //     projection emits, per head, the columns [v0,1,v1,1,v2,1,v3,1], so the same MMA also yields the softmax
 //     row sums.  The 17th key is an extra MMA column / k-step fed from warp 16 through shared memory, the 17th
 //     query is evaluated in transposed form (keys as the M dimension) so that all 32 lanes hold live scores;
-//   * the softmax scale and log2(e) are folded into W_q, so scores come out of the tensor core in the exp2 domain.
+//   * the softmax scale and log2(e) are folded into W_q, so scores come out of the tensor core in the exp2 domain;
+//     LayerNorm gamma/beta of norm1/norm2 are folded into the q|k|v and fc1 weights and biases at pack time;
+//   * P, V and the GELU output are fp16 (11-bit mantissa, values are O(1)); GELU runs in packed half2 arithmetic;
+//     P V and fc2 are f16 MMAs; q, k and every other operand stay bf16 (range).  (ex2/tanh.approx.f16x2 still cost
+//     one MUFU per element on sm_100a, so the softmax exponentials stay fp32.)
 // Cross-warp traffic is two point-to-point mbarrier hand-offs per layer (joint-16 q/k/v out, joint-16 attention
 // rows back); frame warps never wait for each other.
 // HBM traffic: 136 B of key-points in, 1088 B (17x32 bf16) out per frame.
 #include <algorithm>
+
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -69,27 +75,36 @@ __global__ void k_spatial_pack(const float* const* __restrict__ blocks, int dept
     if (fr < F_PROJ) {                       // q | k | v : K = 32 (two k-steps)
       const int f = fr < F_K ? fr - F_Q : (fr < F_V ? fr - F_K : fr - F_V);
       const int j = f >> 1, kk = f & 1;
-      for (int e = 0; e < 4; ++e) {
+      for (int e = 0; e < 4; ++e) {           // norm1 gamma folded in: (gamma * xhat) W == xhat (diag(gamma) W)
         const int k = 16 * kk + 2 * t + (e & 1) + 8 * (e >> 1);
-        if (fr < F_K) w[e] = tb[2][k * 32 + 8 * j + g] * QSCALE;
-        else if (fr < F_V) w[e] = tb[4][k * 32 + 8 * j + g];
-        else w[e] = (g & 1) ? 0.f : tb[6][k * 32 + 4 * j + (g >> 1)];       // head j: [v0,1,v1,1,v2,1,v3,1]
+        if (fr < F_K) w[e] = tb[0][k] * tb[2][k * 32 + 8 * j + g] * QSCALE;
+        else if (fr < F_V) w[e] = tb[0][k] * tb[4][k * 32 + 8 * j + g];
+        else w[e] = (g & 1) ? 0.f : tb[0][k] * tb[6][k * 32 + 4 * j + (g >> 1)];       // head j: [v0,1,v1,1,v2,1,v3,1]
       }
     } else if (fr < F_FC1) {                 // projection, permuted k order
       const int f = fr - F_PROJ, j = f >> 1, kk = f & 1;
       for (int e = 0; e < 4; ++e) w[e] = tb[8][proj_channel(kk, 2 * t + (e & 1) + 8 * (e >> 1)) * 32 + 8 * j + g];
     } else if (fr < F_FC2) {
       const int f = fr - F_FC1, j = f >> 1, kk = f & 1;
-      for (int e = 0; e < 4; ++e) w[e] = tb[12][(16 * kk + 2 * t + (e & 1) + 8 * (e >> 1)) * 64 + 8 * j + g];
+      for (int e = 0; e < 4; ++e) {
+        const int k = 16 * kk + 2 * t + (e & 1) + 8 * (e >> 1);
+        w[e] = tb[10][k] * tb[12][k * 64 + 8 * j + g];                      // norm2 gamma folded in
+      }
     } else {
       const int f = fr - F_FC2, j = f >> 2, kk = f & 3;
       for (int e = 0; e < 4; ++e) w[e] = tb[14][(16 * kk + 2 * t + (e & 1) + 8 * (e >> 1)) * 32 + 8 * j + g];
     }
-    __nv_bfloat162 b0 = __floats2bfloat162_rn(w[0], w[1]);
-    __nv_bfloat162 b1 = __floats2bfloat162_rn(w[2], w[3]);
     uint2 o;
-    o.x = *reinterpret_cast<uint32_t*>(&b0);
-    o.y = *reinterpret_cast<uint32_t*>(&b1);
+    if (fr >= F_FC2) {                       // fc2 runs as an f16 MMA (its A operand is the f16 GELU output)
+      __half2 b0 = __floats2half2_rn(w[0], w[1]), b1 = __floats2half2_rn(w[2], w[3]);
+      o.x = *reinterpret_cast<uint32_t*>(&b0);
+      o.y = *reinterpret_cast<uint32_t*>(&b1);
+    } else {
+      __nv_bfloat162 b0 = __floats2bfloat162_rn(w[0], w[1]);
+      __nv_bfloat162 b1 = __floats2bfloat162_rn(w[2], w[3]);
+      o.x = *reinterpret_cast<uint32_t*>(&b0);
+      o.y = *reinterpret_cast<uint32_t*>(&b1);
+    }
     frags[i] = o;
   }
   const int total_p = depth * P_TOTAL + G_TOTAL;
@@ -101,15 +116,29 @@ __global__ void k_spatial_pack(const float* const* __restrict__ blocks, int dept
       if (o < P_LN1B) v = tb[0][o];
       else if (o < P_BQKV) v = tb[1][o - P_LN1B];
       else if (o < P_BP) {                   // bias image of the 16 q|k|v n-tiles
+        // (norm1 beta folded in: b' = b + beta W)
         const int c = o - P_BQKV, tile = c >> 3, col = c & 7;
-        if (tile < 4) v = tb[3][8 * tile + col] * QSCALE;
-        else if (tile < 8) v = tb[5][8 * (tile - 4) + col];
-        else v = (col & 1) ? 1.f : tb[7][4 * (tile - 8) + (col >> 1)];
+        if (tile < 8) {
+          const int which = tile >> 2, n = 8 * (tile & 3) + col;
+          v = tb[3 + 2 * which][n];
+          for (int k = 0; k < 32; ++k) v += tb[1][k] * tb[2 + 2 * which][k * 32 + n];
+          if (which == 0) v *= QSCALE;
+        } else if (col & 1) {
+          v = 1.f;
+        } else {
+          const int n = 4 * (tile - 8) + (col >> 1);
+          v = tb[7][n];
+          for (int k = 0; k < 32; ++k) v += tb[1][k] * tb[6][k * 32 + n];
+        }
       }
       else if (o < P_LN2G) v = tb[9][o - P_BP];
       else if (o < P_LN2B) v = tb[10][o - P_LN2G];
       else if (o < P_B1) v = tb[11][o - P_LN2B];
-      else if (o < P_B2) v = tb[13][o - P_B1];
+      else if (o < P_B2) {                   // norm2 beta folded in
+        const int n = o - P_B1;
+        v = tb[13][n];
+        for (int k = 0; k < 32; ++k) v += tb[11][k] * tb[12][k * 64 + n];
+      }
       else v = tb[15][o - P_B2];
     } else {
       const int o = i - depth * P_TOTAL;
@@ -145,6 +174,22 @@ __device__ __forceinline__ void mma1688(float (&c)[4], uint32_t a0, uint32_t a1,
       "mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a0), "r"(a1), "r"(b0));
+}
+__device__ __forceinline__ void mma16816h(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma1688h(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(b0));
+}
+__device__ __forceinline__ uint32_t pack2h(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
 }
 // 8x8 b16 transpose inside the warp: in (row g; cols 2t,2t+1) -> out (row g; cols 2t,2t+1) of the transpose
 __device__ __forceinline__ uint32_t movm_t(uint32_t a) {
@@ -217,6 +262,20 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   const float hx = 0.5f * x;
   return fmaf(hx, t, hx);
 }
+// The same GELU on two values in packed fp16 arithmetic (one MUFU, 7 half2 ops per pair): the result feeds the f16
+// fc2 MMA directly.  |x| >= 9 saturates through the clamp exactly as above; fp16 keeps 11 mantissa bits.
+__device__ __forceinline__ uint32_t gelu_h2(float lo, float hi) {
+  const __half2 x = __floats2half2_rn(lo, hi);
+  const __half2 x2 = __hmin2(__hmul2(x, x), __float2half2_rn(81.0f));
+  const __half2 pl = __hfma2(x2, __hfma2(x2, __float2half2_rn(-3.58732362e-4f), __float2half2_rn(3.70503451e-2f)),
+                             __float2half2_rn(7.97458471e-1f));
+  const __half2 u = __hmul2(x, pl);
+  uint32_t tu;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(tu) : "r"(*reinterpret_cast<const uint32_t*>(&u)));
+  const __half2 hx = __hmul2(x, __float2half2_rn(0.5f));
+  const __half2 r = __hfma2(hx, *reinterpret_cast<const __half2*>(&tu), hx);
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -260,6 +319,29 @@ __device__ __forceinline__ void ln_to_afrag(const float (&x)[4][4], const float*
     a[kk][1] = pack2(y[2 * kk][2], y[2 * kk][3]);
     a[kk][2] = pack2(y[2 * kk + 1][0], y[2 * kk + 1][1]);
     a[kk][3] = pack2(y[2 * kk + 1][2], y[2 * kk + 1][3]);
+  }
+}
+
+// The same without gamma / beta (folded into the following linear layer at pack time): xhat = (x - mean) * rstd.
+__device__ __forceinline__ void lnhat_to_afrag(const float (&x)[4][4], float eps, uint32_t (&a)[2][4]) {
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { s0 += x[j][0] + x[j][1]; s1 += x[j][2] + x[j][3]; }
+  const float m0 = quad_sum(s0) * (1.f / 32), m1 = quad_sum(s1) * (1.f / 32);
+  float d[4][4];
+  float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    d[j][0] = x[j][0] - m0; q0 = fmaf(d[j][0], d[j][0], q0); d[j][1] = x[j][1] - m0; q0 = fmaf(d[j][1], d[j][1], q0);
+    d[j][2] = x[j][2] - m1; q1 = fmaf(d[j][2], d[j][2], q1); d[j][3] = x[j][3] - m1; q1 = fmaf(d[j][3], d[j][3], q1);
+  }
+  const float r0 = rsqrtf(quad_sum(q0) * (1.f / 32) + eps), r1 = rsqrtf(quad_sum(q1) * (1.f / 32) + eps);
+#pragma unroll
+  for (int kk = 0; kk < 2; ++kk) {
+    a[kk][0] = pack2(d[2 * kk][0] * r0, d[2 * kk][1] * r0);
+    a[kk][1] = pack2(d[2 * kk][2] * r1, d[2 * kk][3] * r1);
+    a[kk][2] = pack2(d[2 * kk + 1][0] * r0, d[2 * kk + 1][1] * r0);
+    a[kk][3] = pack2(d[2 * kk + 1][2] * r1, d[2 * kk + 1][3] * r1);
   }
 }
 
@@ -351,7 +433,7 @@ __global__ void __launch_bounds__(st::THREADS, 1) k_spatial_tc(SpatialTcParams p
       uint32_t a[2][4];
       uint32_t ao[2][4];                      // attention output as the A operand of the projection
       // ---- y = LN1(x); q|k|v = y @ Wqkv + b (bias preloaded into the accumulators)
-      ln_to_afrag(x, bp + P_LN1G, bp + P_LN1B, 1e-5f, t, a);
+      lnhat_to_afrag(x, 1e-5f, a);
       uint32_t qa[4][2], kb[4][2], vt[8][2];
 #pragma unroll
       for (int tile = 0; tile < 16; ++tile) {
@@ -360,10 +442,10 @@ __global__ void __launch_bounds__(st::THREADS, 1) k_spatial_tc(SpatialTcParams p
         const uint2 w0 = fr[(2 * tile) * 32], w1 = fr[(2 * tile + 1) * 32];
         mma16816(c, a[0], w0.x, w0.y);
         mma16816(c, a[1], w1.x, w1.y);
-        const uint32_t lo = pack2(c[0], c[1]), hi = pack2(c[2], c[3]);     // rows g / g+8, cols 2t,2t+1 of the tile
-        if (tile < 4) { qa[tile][0] = lo; qa[tile][1] = hi; }
-        else if (tile < 8) { kb[tile - 4][0] = lo; kb[tile - 4][1] = hi; }
-        else { vt[tile - 8][0] = lo; vt[tile - 8][1] = hi; }
+        // rows g / g+8, cols 2t,2t+1 of the tile: q, k as bf16, v as fp16
+        if (tile < 4) { qa[tile][0] = pack2(c[0], c[1]); qa[tile][1] = pack2(c[2], c[3]); }
+        else if (tile < 8) { kb[tile - 4][0] = pack2(c[0], c[1]); kb[tile - 4][1] = pack2(c[2], c[3]); }
+        else { vt[tile - 8][0] = pack2h(c[0], c[1]); vt[tile - 8][1] = pack2h(c[2], c[3]); }
       }
       if (w16) {
         // joint 16 of 16 frames: publish q, k, v and the (query 16, key 16) scores
@@ -401,7 +483,7 @@ __global__ void __launch_bounds__(st::THREADS, 1) k_spatial_tc(SpatialTcParams p
         sp_mbar_wait(bar_pub, phase);
         const bf16* q16 = xq16 + warp * 32;
         const bf16* k16 = xk16 + warp * 32;
-        const bf16* v16 = xv16 + warp * 64;
+        const __half* v16 = reinterpret_cast<const __half*>(xv16) + warp * 64;
         // scores against key 16: s16[0/1] = (row g; heads 2t, 2t+1), s16[2/3] = (row g+8; ...).
         // scores of query 16 (transposed): t16[0/1] = (key g; heads 2t, 2t+1), t16[2/3] = (key g+8; ...).
         float s16[4] = {0.f, 0.f, 0.f, 0.f}, t16[4] = {0.f, 0.f, 0.f, 0.f};
@@ -435,15 +517,15 @@ __global__ void __launch_bounds__(st::THREADS, 1) k_spatial_tc(SpatialTcParams p
           mg = quad_max(mg);
           mh = quad_max(mh);
           uint32_t pa[4];
-          pa[0] = pack2(ex2_approx(s0[0] - mg), ex2_approx(s0[1] - mg));
-          pa[1] = pack2(ex2_approx(s0[2] - mh), ex2_approx(s0[3] - mh));
-          pa[2] = pack2(ex2_approx(s1[0] - mg), ex2_approx(s1[1] - mg));
-          pa[3] = pack2(ex2_approx(s1[2] - mh), ex2_approx(s1[3] - mh));
+          pa[0] = pack2h(ex2_approx(s0[0] - mg), ex2_approx(s0[1] - mg));
+          pa[1] = pack2h(ex2_approx(s0[2] - mh), ex2_approx(s0[3] - mh));
+          pa[2] = pack2h(ex2_approx(s1[0] - mg), ex2_approx(s1[1] - mg));
+          pa[3] = pack2h(ex2_approx(s1[2] - mh), ex2_approx(s1[3] - mh));
           const float pg = owner ? ex2_approx(s16[e] - mg) : 0.f;
           const float ph = owner ? ex2_approx(s16[2 + e] - mh) : 0.f;
           float o[4] = {0.f, 0.f, 0.f, 0.f};
-          mma16816(o, pa, vt[h][0], vt[h][1]);  // o[0] = sum_k p v[ch t], o[1] = sum_k p   (row g); o[2], o[3]: row g+8
-          mma1688(o, e ? pack2(0.f, pg) : pack2(pg, 0.f), e ? pack2(0.f, ph) : pack2(ph, 0.f), bv16);   // key 16
+          mma16816h(o, pa, vt[h][0], vt[h][1]);  // o[0] = sum_k p v[ch t], o[1] = sum_k p   (row g); o[2], o[3]: row g+8
+          mma1688h(o, e ? pack2h(0.f, pg) : pack2h(pg, 0.f), e ? pack2h(0.f, ph) : pack2h(ph, 0.f), bv16);   // key 16
           const float og = o[0] * rcp_approx(o[1]), oh = o[2] * rcp_approx(o[3]);
           // heads 4kk..4kk+3 fill slots (2t,2t+1 | 2t+8,2t+9) of k-step kk: pairs (h, h+1) pack into one register
           if (e == 0) {
@@ -465,17 +547,17 @@ __global__ void __launch_bounds__(st::THREADS, 1) k_spatial_tc(SpatialTcParams p
           pA0 *= iA; pA1 *= iA; pA16 *= iA;
           pB0 *= iB; pB1 *= iB; pB16 *= iB;
           // (key g; heads 2t,2t+1) -> transpose -> (head g; keys 2t,2t+1): A fragments with heads as rows
-          const uint32_t pt0 = movm_t(pack2(pA0, pB0)), pt1 = movm_t(pack2(pA1, pB1));
+          const uint32_t pt0 = movm_t(pack2h(pA0, pB0)), pt1 = movm_t(pack2h(pA1, pB1));
           float e16[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int h = 0; h < 8; ++h) {        // row h of the product with head h's V^T; other rows masked to zero
             const uint32_t aa[4] = {g == h ? pt0 : 0u, 0u, g == h ? pt1 : 0u, 0u};
-            mma16816(e16, aa, vt[h][0], vt[h][1]);
+            mma16816h(e16, aa, vt[h][0], vt[h][1]);
           }
           // e16[0] = (head g, dim t) over keys 0..15; add key 16 with the normalised weight of head g
           const float v0 = __shfl_sync(0xffffffffu, pA16, g >> 1), v1 = __shfl_sync(0xffffffffu, pB16, g >> 1);
           const float pn = (g & 1) ? v1 : v0;
-          const float out = fmaf(pn, __bfloat162float(v16[8 * g + 2 * t]), e16[0]);
+          const float out = fmaf(pn, __half2float(v16[8 * g + 2 * t]), e16[0]);
           xo16[warp * 32 + proj_position(g, t)] = __float2bfloat16_rn(out);
         }
         __syncwarp();
@@ -493,16 +575,15 @@ __global__ void __launch_bounds__(st::THREADS, 1) k_spatial_tc(SpatialTcParams p
       }
       // ---- x += attn @ Wp + bp   (projection rows permuted to the A order above)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
-        const uint2 w0 = fr[(F_PROJ + 2 * j) * 32], w1 = fr[(F_PROJ + 2 * j + 1) * 32];
-        mma16816(c, ao[0], w0.x, w0.y);
-        mma16816(c, ao[1], w1.x, w1.y);
+      for (int j = 0; j < 4; ++j) {             // the residual stream is the accumulator
         const float2 b = *reinterpret_cast<const float2*>(bp + P_BP + 8 * j + 2 * t);
-        x[j][0] += c[0] + b.x; x[j][1] += c[1] + b.y; x[j][2] += c[2] + b.x; x[j][3] += c[3] + b.y;
+        x[j][0] += b.x; x[j][1] += b.y; x[j][2] += b.x; x[j][3] += b.y;
+        const uint2 w0 = fr[(F_PROJ + 2 * j) * 32], w1 = fr[(F_PROJ + 2 * j + 1) * 32];
+        mma16816(x[j], ao[0], w0.x, w0.y);
+        mma16816(x[j], ao[1], w1.x, w1.y);
       }
       // ---- x += fc2(gelu(fc1(LN2(x))))
-      ln_to_afrag(x, bp + P_LN2G, bp + P_LN2B, 1e-5f, t, a);
+      lnhat_to_afrag(x, 1e-5f, a);
       uint32_t ah[4][4];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -512,19 +593,18 @@ __global__ void __launch_bounds__(st::THREADS, 1) k_spatial_tc(SpatialTcParams p
         mma16816(c, a[0], w0.x, w0.y);
         mma16816(c, a[1], w1.x, w1.y);
         // accumulator n-tile j -> A fragment of k-step j/2 (cols 16*(j/2) + 8*(j&1) + 2t)
-        ah[j >> 1][(j & 1) * 2] = pack2(gelu_erf_fast(c[0]), gelu_erf_fast(c[1]));
-        ah[j >> 1][(j & 1) * 2 + 1] = pack2(gelu_erf_fast(c[2]), gelu_erf_fast(c[3]));
+        ah[j >> 1][(j & 1) * 2] = gelu_h2(c[0], c[1]);
+        ah[j >> 1][(j & 1) * 2 + 1] = gelu_h2(c[2], c[3]);
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
+        const float2 b = *reinterpret_cast<const float2*>(bp + P_B2 + 8 * j + 2 * t);
+        x[j][0] += b.x; x[j][1] += b.y; x[j][2] += b.x; x[j][3] += b.y;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           const uint2 w = fr[(F_FC2 + 4 * j + kk) * 32];
-          mma16816(c, ah[kk], w.x, w.y);
+          mma16816h(x[j], ah[kk], w.x, w.y);
         }
-        const float2 b = *reinterpret_cast<const float2*>(bp + P_B2 + 8 * j + 2 * t);
-        x[j][0] += c[0] + b.x; x[j][1] += c[1] + b.y; x[j][2] += c[2] + b.x; x[j][3] += c[3] + b.y;
       }
     }
 
