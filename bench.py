@@ -21,6 +21,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("NCCL_DEBUG_FILE", os.devnull)     # keep NCCL's banner off stdout: rank 0 prints ONE JSON line
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402

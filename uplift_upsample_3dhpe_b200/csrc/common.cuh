@@ -108,6 +108,13 @@ cudaError_t launch_residual_ln(const float* xsrc, const RowMap& smap, const bf16
                                const float* gamma, const float* beta, float eps, const float* table, int period,
                                bf16* y, bf16* xcast, cudaStream_t st);
 
+// bf16-resident residual stream variants (X stored as bf16; arithmetic fp32).  upd / xdst / y / xcast optional.
+cudaError_t launch_token_fill_bx(const uint8_t* mask, int rows, int n_tok, int d, const float* token, const float* pe,
+                                 bf16* x, cudaStream_t st);
+cudaError_t launch_residual_ln_bx(const bf16* xsrc, const RowMap& smap, const bf16* upd, bf16* xdst, int rows, int d,
+                                  const float* gamma, const float* beta, float eps, const float* table, int period,
+                                  bf16* y, bf16* xcast, cudaStream_t st);
+
 // fp32 -> bf16 copy of n elements (n % 4 == 0): operand cast for the tensor-core heads
 cudaError_t launch_cast_bf16(const float* x, bf16* y, long long n, cudaStream_t st);
 

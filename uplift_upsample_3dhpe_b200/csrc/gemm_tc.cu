@@ -8,6 +8,8 @@
 // A  : bf16 row-major [M, K] with leading dimension lda (activations; the strided Conv1D reads its
 //      zero-padded input as a [B*L_out, 3*C] matrix with lda = stride*C — implicit GEMM, no im2col).
 // Wt : bf16 [N_pad, K] = W^T, i.e. both operands are K-major.
+#include <cstdlib>
+
 #include <cuda.h>   // CUtensorMap types only; the encoder is fetched through the runtime (no -lcuda)
 
 #include "common.cuh"
@@ -20,7 +22,7 @@ constexpr int TC_BLOCK_K = 64;          // 64 bf16 = 128 B = one swizzle atom ro
 constexpr int TC_UMMA_K = 16;
 constexpr int TC_THREADS = 320;        // TMA warp, MMA warp, 8 epilogue warps
 constexpr int TC_TSTRIDE = 36;          // fp32 row stride of the epilogue transpose tiles (conflict-free float4)
-constexpr int TC_EPI_SMEM = 8 * 32 * TC_TSTRIDE * 4;
+constexpr int TC_EPI_SMEM = 8 * 2 * 32 * 128 + 1024;   // max(fp32 transpose tiles 36 KB, per-warp TMA staging 64 KB + align)
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -111,16 +113,83 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
          | ((uint32_t)(M >> 4) << 24);  // m_dim
 }
 
-template <int BLOCK_N>
+// BS_KB > 0 selects the B-STATIONARY schedule: the CTA keeps its whole [BLOCK_N x K] weight tile (BS_KB k-block
+// panels) resident in shared memory, owns one column block for its lifetime and streams only A.  With M >> N the
+// streaming schedule re-reads the weight tile once per 128-row tile (QKV: 2.0 GB of L2 -> SM traffic per call on
+// top of 1.3 GB of A), which pins these short-K GEMMs to the ~12 TB/s L2 -> SM ceiling; B-stationary removes that term.
+// Epilogue of one warp for one tile (bf16 output): sub-tiles first, first+2, ... of its 32 accumulator rows go
+// TMEM -> registers -> bias / ReLU / bf16 -> private swizzled staging tile -> cp.async.bulk.tensor store of a
+// [32 x 64] box.  `release` is called right after the warp's last TMEM read of the tile.
+template <int BLOCK_N, int NBUF, typename Release>
+__device__ __forceinline__ void epi_warp_store_tile(uint32_t tmem_acc, int first, uint8_t* my_stage, uint32_t& my_count,
+                                                    const Epilogue& epi, const CUtensorMap* map_c, int row_q0, int col0,
+                                                    int lane, Release release) {
+  constexpr int NSUB = BLOCK_N / 64;
+#pragma unroll 1
+  for (int sub = first; sub < NSUB; sub += 2, ++my_count) {
+    uint8_t* sbuf = my_stage + (my_count % NBUF) * (32 * 128);
+    uint32_t v0[32], v1[32];
+    tmem_ld_32x32b_x32(tmem_acc + (uint32_t)(sub * 64), v0);
+    tmem_ld_32x32b_x32(tmem_acc + (uint32_t)(sub * 64 + 32), v1);
+    if (sub + 2 >= NSUB) release();         // last TMEM read of this warp for this tile: hand the accumulator back
+    // the store issued NBUF sub-tiles ago read this staging tile: it must have finished reading
+    if (lane == 0) {
+      if constexpr (NBUF == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    __syncwarp();
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {           // 8 columns -> one 16-byte chunk
+      const int cb = col0 + sub * 64 + 8 * g;
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(g < 4 ? v0[8 * g + i] : v1[8 * (g - 4) + i]);
+      if (epi.bias) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(epi.bias + cb));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(epi.bias + cb + 4));
+        o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w;
+        o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
+      }
+      if (epi.flags & EPI_RELU) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = fmaxf(o[i], 0.f);
+      }
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
+      __nv_bfloat162 p2 = __floats2bfloat162_rn(o[4], o[5]), p3 = __floats2bfloat162_rn(o[6], o[7]);
+      uint4 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+      pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
+      *reinterpret_cast<uint4*>(sbuf + lane * 128 + ((g ^ (lane & 7)) << 4)) = pk;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async proxy
+    __syncwarp();
+    if (lane == 0 && !(epi.flags & 64)) {   // (flag 64: timing experiment, UU_GEMM_NOSTORE)
+      asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map_c),
+                   "r"(smem_u32(sbuf)), "r"(col0 + sub * 64), "r"(row_q0)
+                   : "memory");
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+}
+
+template <int BLOCK_N, int BS_KB = 0>
 struct TcCfg {
   static constexpr int A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;   // 16 KB
   static constexpr int B_BYTES = BLOCK_N * TC_BLOCK_K * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (160 * 1024) / STAGE_BYTES < 8 ? (160 * 1024) / STAGE_BYTES : 8;
+  static constexpr int B_RES_BYTES = BS_KB * B_BYTES;            // resident weight panels (B-stationary only)
+  static constexpr int STAGE_BYTES = BS_KB ? A_BYTES : A_BYTES + B_BYTES;
+  // epilogue scratch: per-warp TMA-store staging, 8 warps x NBUF x 4 KB (+ alignment); the generic fp32 transpose
+  // tiles (36 KB) fit in the same region.  B-stationary keeps one staging tile per warp to leave room for the A ring.
+  static constexpr int EPI_NBUF = BS_KB ? 1 : 2;
+  static constexpr int EPI_BYTES = BS_KB ? 8 * 32 * 128 + 1024 : TC_EPI_SMEM;
+  static constexpr int STAGES_BS = (227 * 1024 - B_RES_BYTES - EPI_BYTES - 1280) / A_BYTES;
+  static constexpr int STAGES = BS_KB ? (STAGES_BS < 8 ? STAGES_BS : 8)
+                                      : ((160 * 1024) / STAGE_BYTES < 8 ? (160 * 1024) / STAGE_BYTES : 8);
   static constexpr int ACC_STAGES = 2;                           // double-buffered accumulator in TMEM
   static constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N <= 32 ? 32 : ACC_STAGES * BLOCK_N <= 64 ? 64
                                    : ACC_STAGES * BLOCK_N <= 128 ? 128 : ACC_STAGES * BLOCK_N <= 256 ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + TC_EPI_SMEM;
+  static constexpr int SMEM_BYTES = B_RES_BYTES + STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
   static_assert(ACC_STAGES * BLOCK_N <= 512, "accumulator stages exceed TMEM");
   static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024-byte alignment for the 128B swizzle");
 };
@@ -128,32 +197,43 @@ struct TcCfg {
 // Persistent, warp-specialised: every CTA walks the tile list t = blockIdx.x, += gridDim.x with
 // (m_blk, n_blk) = (t / n_tiles, t % n_tiles), so CTAs running concurrently share the same A rows in L2.
 // Three pipelines: smem ring (TMA -> MMA), TMEM accumulator ring (MMA -> epilogue), tile list.
-template <int BLOCK_N, typename TC, bool TMA_OUT>
+template <int BLOCK_N, typename TC, bool TMA_OUT, int BS_KB = 0>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant__ CUtensorMap map_a,
                                                            const __grid_constant__ CUtensorMap map_b,
                                                            const __grid_constant__ CUtensorMap map_c, int M, int N,
                                                            int n_tiles, int K, Epilogue epi, TC* __restrict__ C,
                                                            long long ldc) {
-  using Cfg = TcCfg<BLOCK_N>;
+  using Cfg = TcCfg<BLOCK_N, BS_KB>;
+  constexpr bool BS = BS_KB > 0;
   extern __shared__ uint8_t smem_raw[];
   const int m_eff = epi.m_dev ? min(M, *epi.m_dev) : M;
   const int m_tiles = (m_eff + TC_BLOCK_M - 1) / TC_BLOCK_M;
   const int total_tiles = m_tiles * n_tiles;
+  // tile walk: streaming = (t / n_tiles, t % n_tiles) over t = blockIdx.x, += gridDim.x;
+  // B-stationary = fixed column block blockIdx.x % n_tiles, row blocks blockIdx.x / n_tiles, += gridDim.x / n_tiles
+  // (the host sizes the grid as a multiple of n_tiles), expressed as the same linear walk with a stride that is
+  // a multiple of n_tiles so t % n_tiles never changes.
+  const int tile_first = BS ? (blockIdx.x / n_tiles) * n_tiles + (blockIdx.x % n_tiles) : blockIdx.x;
+  const int tile_step = gridDim.x;
 
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_al = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_bres = smem_al;                           // resident weight panels (B-stationary)
+  uint8_t* smem = smem_al + Cfg::B_RES_BYTES;             // operand ring
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
   uint64_t* tmem_full_bar = empty_bar + Cfg::STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + Cfg::ACC_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + Cfg::ACC_STAGES);
+  uint64_t* bres_bar = tmem_empty_bar + Cfg::ACC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_kb = (K + TC_BLOCK_K - 1) / TC_BLOCK_K;
+  const int num_kb = BS ? BS_KB : (K + TC_BLOCK_K - 1) / TC_BLOCK_K;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     if constexpr (TMA_OUT) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
+    mbar_init(bres_bar, 1);
     for (int s = 0; s < Cfg::STAGES; ++s) {
       mbar_init(full_bar + s, 1);
       mbar_init(empty_bar + s, 1);
@@ -179,17 +259,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
     // ---------------- TMA producer ----------------
     if (lane == 0) {
       uint32_t it = 0;                        // running k-block counter across tiles -> stage / phase
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      if constexpr (BS) {                     // the CTA's weight tile, once: BS_KB panels of [BLOCK_N x 64]
+        if (tile_first < total_tiles) {
+          const int col0 = (tile_first % n_tiles) * BLOCK_N;
+          mbar_expect_tx(bres_bar, Cfg::B_RES_BYTES);
+          for (int kb = 0; kb < BS_KB; ++kb)
+            tma_load_2d(smem_bres + kb * Cfg::B_BYTES, &map_b, bres_bar, kb * TC_BLOCK_K, col0);
+        }
+      }
+      for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
         const int row0 = (tile / n_tiles) * TC_BLOCK_M, col0 = (tile % n_tiles) * BLOCK_N;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % Cfg::STAGES;
           const uint32_t ph = (it / Cfg::STAGES) & 1;
           mbar_wait(empty_bar + s, ph ^ 1);
           uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
-          uint8_t* b_dst = a_dst + Cfg::A_BYTES;
+          if (epi.flags & 128) {                 // (flag 128: timing experiment UU_GEMM_NOLOAD — MMA on stale smem)
+            mbar_arrive(full_bar + s);
+            continue;
+          }
           mbar_expect_tx(full_bar + s, Cfg::STAGE_BYTES);
           tma_load_2d(a_dst, &map_a, full_bar + s, kb * TC_BLOCK_K, row0);
-          tma_load_2d(b_dst, &map_b, full_bar + s, kb * TC_BLOCK_K, col0);
+          if constexpr (!BS) tma_load_2d(a_dst + Cfg::A_BYTES, &map_b, full_bar + s, kb * TC_BLOCK_K, col0);
         }
       }
     }
@@ -198,7 +289,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(TC_BLOCK_M, BLOCK_N);
       uint32_t it = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      if constexpr (BS) {
+        if (tile_first < total_tiles) mbar_wait(bres_bar, 0);   // weight tile resident
+      }
+      for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++tcount) {
         const int as = tcount % Cfg::ACC_STAGES;
         const uint32_t aph = (tcount / Cfg::ACC_STAGES) & 1;
         mbar_wait(tmem_empty_bar + as, aph ^ 1);          // epilogue has drained this accumulator
@@ -210,7 +304,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
           mbar_wait(full_bar + s, ph);
           tcgen05_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+          const uint32_t b_addr = BS ? smem_u32(smem_bres + kb * Cfg::B_BYTES) : a_addr + Cfg::A_BYTES;
           const uint64_t a_desc = make_sw128_desc(a_addr), b_desc = make_sw128_desc(b_addr);
 #pragma unroll
           for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
@@ -232,74 +326,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
     const int hsel = e >> 2;                  // chunk parity handled by this warp
     if constexpr (TMA_OUT) {
       // ---- bf16 output through shared memory + TMA store --------------------------------------------------
-      // Per 64-column sub-tile: every thread converts 32 columns of its own row (bias, ReLU, bf16 pack) and
-      // writes them into a 128 x 64 bf16 staging tile in the 128B-swizzle layout (conflict-free 16-byte
-      // stores); one thread then issues a single cp.async.bulk.tensor store.  Two staging tiles alternate, so
-      // the store of sub-tile s overlaps the conversion of sub-tile s+1.  Rows past M are clipped by TMA.
+      // Every epilogue warp is self-contained: it owns 32 accumulator rows (its TMEM lane quarter), converts whole
+      // 64-column sub-tiles of them (bias, ReLU, bf16 pack) into a private 32 x 128 B staging tile in the
+      // 128B-swizzle layout (conflict-free 16-byte stores) and issues its own cp.async.bulk.tensor store of that
+      // [32 x 64] box; two private tiles alternate so a store overlaps the next conversion.  The two warps that
+      // share a lane quarter take alternate sub-tiles.  No cross-warp barrier, no single issuing thread.
+      // Rows past M are clipped by TMA.
       uint8_t* stage_base = reinterpret_cast<uint8_t*>(
           (reinterpret_cast<uintptr_t>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256) + 1023) & ~uintptr_t(1023));
-      const int r_in_tile = q * 32 + lane;
-      const bool issuer = (warp == 2 && lane == 0);
-      uint32_t tcount = 0, sub_count = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      uint8_t* my_stage = stage_base + e * (Cfg::EPI_NBUF * 32 * 128);          // NBUF x 4 KB per warp
+      constexpr int NSUB = BLOCK_N / 64;
+      uint32_t tcount = 0, my_count = 0;
+      for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++tcount) {
         const int row0 = (tile / n_tiles) * TC_BLOCK_M, col0 = (tile % n_tiles) * BLOCK_N;
         const int as = tcount % Cfg::ACC_STAGES;
         const uint32_t aph = (tcount / Cfg::ACC_STAGES) & 1;
         mbar_wait(tmem_full_bar + as, aph);
         tcgen05_fence_after();
         const uint32_t tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N);
-#pragma unroll 1
-        for (int sub = 0; sub < BLOCK_N / 64; ++sub, ++sub_count) {
-          uint8_t* sbuf = stage_base + (sub_count & 1) * (TC_BLOCK_M * 128);
-          const int cbase = col0 + sub * 64 + hsel * 32;
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem_acc + (uint32_t)(sub * 64 + hsel * 32), v);
-          if (sub == BLOCK_N / 64 - 1) {          // last TMEM read of this tile: release the accumulator early
-            tcgen05_fence_before();
-            if (lane == 0) mbar_arrive(tmem_empty_bar + as);
-          }
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {           // 8 columns -> one 16-byte chunk
-            float o[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v[8 * g + i]);
-            if (epi.bias) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(epi.bias + cbase + 8 * g));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(epi.bias + cbase + 8 * g + 4));
-              o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w;
-              o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
-            }
-            if (epi.flags & EPI_RELU) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) o[i] = fmaxf(o[i], 0.f);
-            }
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
-            __nv_bfloat162 p2 = __floats2bfloat162_rn(o[4], o[5]), p3 = __floats2bfloat162_rn(o[6], o[7]);
-            uint4 pk;
-            pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
-            pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
-            const int c16 = hsel * 4 + g;         // 16-byte chunk index inside the 128-byte row
-            *reinterpret_cast<uint4*>(sbuf + r_in_tile * 128 + ((c16 ^ (r_in_tile & 7)) << 4)) = pk;
-          }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async proxy
-          // the previous store (other staging tile) must have finished READING before anyone refills that tile
-          if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          if (issuer) {
-            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&map_c),
-                         "r"(smem_u32(sbuf)), "r"(col0 + sub * 64), "r"(row0)
-                         : "memory");
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          }
+        // sub-tiles of this warp: those with (sub + tcount) % 2 == hsel (alternating start balances odd NSUB)
+        const int first = (hsel + (int)tcount) & 1;
+        if (first >= NSUB) {                    // nothing to do for this tile (only possible for NSUB == 1)
+          tcgen05_fence_before();
+          if (lane == 0) mbar_arrive(tmem_empty_bar + as);
+          continue;
         }
+        epi_warp_store_tile<BLOCK_N, Cfg::EPI_NBUF>(tmem_acc, first, my_stage, my_count, epi, &map_c, row0 + q * 32, col0, lane, [&] {
+          tcgen05_fence_before();
+          if (lane == 0) mbar_arrive(tmem_empty_bar + as);
+        });
       }
-      if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     } else {
     float* tbuf = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256) + e * (32 * TC_TSTRIDE);
     const int rsub = lane >> 3, g4 = (lane & 7) * 4;
     const bool vec_ok = (N % 4 == 0) && (ldc % 4 == 0) && (!(epi.flags & EPI_RESIDUAL) || (epi.ldr % 4 == 0));
     uint32_t tcount = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++tcount) {
       const int row0 = (tile / n_tiles) * TC_BLOCK_M, col0 = (tile % n_tiles) * BLOCK_N;
       const int as = tcount % Cfg::ACC_STAGES;
       const uint32_t aph = (tcount / Cfg::ACC_STAGES) & 1;
@@ -388,6 +451,208 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
   }
 }
 
+// ================================================================================================
+// 2-CTA variant (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x BLOCK_N tile.
+//   * each CTA loads its own 128 rows of A and HALF of the B tile (BLOCK_N/2 rows of W^T) per k-block, so the
+//     L2 -> SM operand traffic per output drops by a third against the 128-row tile and a stage is 28-32 KB
+//     (5 stages of 64-wide k-blocks instead of 3-4);
+//   * the leader CTA (cluster rank 0) issues tcgen05.mma.cta_group::2 with M = 256: the hardware reads A and B
+//     from both CTAs' shared memory and writes each CTA's 128 accumulator rows into its own TMEM;
+//   * barriers: TMA loads of both CTAs complete on the leader's full barrier; tcgen05.commit multicasts the
+//     "stage free" and "accumulator ready" arrivals to both CTAs; the epilogue warps of both CTAs hand the
+//     accumulator back by arriving on the leader's barrier.
+// Only the hot-path epilogue (bias, ReLU, bf16, TMA store) exists in this variant.
+// ================================================================================================
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` (a shared::cta address of this CTA) in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t mapa_rank(const void* p, uint32_t rank) {
+  uint32_t d;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(d) : "r"(smem_u32(p)), "r"(rank));
+  return d;
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {      // arrives on `bar` of BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+template <int BLOCK_N>
+struct Tc2Cfg {
+  static constexpr int A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;          // 16 KB: this CTA's 128 rows
+  static constexpr int B_BYTES = (BLOCK_N / 2) * TC_BLOCK_K * 2;       // this CTA's half of the B tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (160 * 1024) / STAGE_BYTES < 8 ? (160 * 1024) / STAGE_BYTES : 8;
+  static constexpr int ACC_STAGES = 2;
+  static constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N <= 128 ? 128 : ACC_STAGES * BLOCK_N <= 256 ? 256 : 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + TC_EPI_SMEM;
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
+  static_assert(ACC_STAGES * BLOCK_N <= 512, "accumulator stages exceed TMEM");
+  static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024-byte alignment for the 128B swizzle");
+  static_assert(BLOCK_N % 32 == 0 && BLOCK_N <= 256, "UMMA M=256 needs N % 16 == 0, N <= 256");
+};
+
+template <int BLOCK_N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+    k_gemm_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_c, int M, int n_tiles, int K, Epilogue epi) {
+  using Cfg = Tc2Cfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  const int m_pairs = (M + 2 * TC_BLOCK_M - 1) / (2 * TC_BLOCK_M);
+  const int total_tiles = m_pairs * n_tiles;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tmem_full_bar = empty_bar + Cfg::STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + Cfg::ACC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + Cfg::ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_kb = (K + TC_BLOCK_K - 1) / TC_BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(full_bar + s, 1);            // leader's producer arms it; bytes of both CTAs complete it
+      mbar_init(empty_bar + s, 1);           // one multicast commit per use
+    }
+    for (int s = 0; s < Cfg::ACC_STAGES; ++s) {
+      mbar_init(tmem_full_bar + s, 1);       // one multicast commit per tile
+      mbar_init(tmem_empty_bar + s, 16);     // 8 epilogue warps of each CTA (only the leader's copy is waited on)
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();                        // peer barriers are initialised before anyone signals them
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------- TMA producer (both CTAs) ----------------
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+        const int row0 = (tile / n_tiles) * (2 * TC_BLOCK_M) + (int)rank * TC_BLOCK_M;
+        const int col0 = (tile % n_tiles) * BLOCK_N + (int)rank * (BLOCK_N / 2);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % Cfg::STAGES;
+          const uint32_t ph = (it / Cfg::STAGES) & 1;
+          mbar_wait(empty_bar + s, ph ^ 1);                 // own slot free (multicast commit of the leader)
+          uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
+          uint8_t* b_dst = a_dst + Cfg::A_BYTES;
+          const uint32_t lbar = mapa_rank(full_bar + s, 0);
+          if (leader) mbar_expect_tx(full_bar + s, 2 * Cfg::STAGE_BYTES);
+          tma_load_2d_2sm(a_dst, &map_a, lbar, kb * TC_BLOCK_K, row0);
+          tma_load_2d_2sm(b_dst, &map_b, lbar, kb * TC_BLOCK_K, col0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer (leader CTA only) ----------------
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * TC_BLOCK_M, BLOCK_N);
+      uint32_t it = 0, tcount = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++tcount) {
+        const int as = tcount % Cfg::ACC_STAGES;
+        const uint32_t aph = (tcount / Cfg::ACC_STAGES) & 1;
+        mbar_wait(tmem_empty_bar + as, aph ^ 1);            // both CTAs' epilogues have drained this accumulator
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BLOCK_N);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % Cfg::STAGES;
+          const uint32_t ph = (it / Cfg::STAGES) & 1;
+          mbar_wait(full_bar + s, ph);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+          const uint64_t a_desc = make_sw128_desc(a_addr), b_desc = make_sw128_desc(b_addr);
+#pragma unroll
+          for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k)
+            umma_bf16_2sm(tmem_d, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit_2sm(empty_bar + s);       // frees the stage in both CTAs
+        }
+        umma_commit_2sm(tmem_full_bar + as);    // accumulator complete in both CTAs
+      }
+    }
+  } else {
+    // ---------------- epilogue (both CTAs): TMEM -> bias/ReLU -> bf16 -> swizzled smem -> TMA store ----------------
+    const int e = warp - 2;
+    const int q = warp & 3;
+    const int hsel = e >> 2;
+    uint8_t* stage_base = reinterpret_cast<uint8_t*>(
+        (reinterpret_cast<uintptr_t>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256) + 1023) & ~uintptr_t(1023));
+    uint8_t* my_stage = stage_base + e * (2 * 32 * 128);
+    constexpr int NSUB = BLOCK_N / 64;
+    uint32_t tcount = 0, my_count = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++tcount) {
+      const int row0 = (tile / n_tiles) * (2 * TC_BLOCK_M) + (int)rank * TC_BLOCK_M;
+      const int col0 = (tile % n_tiles) * BLOCK_N;
+      const int as = tcount % Cfg::ACC_STAGES;
+      const uint32_t aph = (tcount / Cfg::ACC_STAGES) & 1;
+      mbar_wait(tmem_full_bar + as, aph);
+      tcgen05_fence_after();
+      const uint32_t tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N);
+      const int first = (hsel + (int)tcount) & 1;
+      auto release = [&] {                     // hand the accumulator back to the leader's MMA thread
+        tcgen05_fence_before();
+        if (lane == 0) mbar_arrive_cluster(mapa_rank(tmem_empty_bar + as, 0));
+      };
+      if (first >= NSUB) { release(); continue; }
+      epi_warp_store_tile<BLOCK_N, 2>(tmem_acc, first, my_stage, my_count, epi, &map_c, row0 + q * 32, col0, lane, release);
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();                        // nobody exits (or frees TMEM) while the peer may still touch it
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Host side: tensor maps and launch
 // ------------------------------------------------------------------------------------------------
@@ -427,6 +692,8 @@ static int encode_2d(CUtensorMap* map, const void* base, uint64_t cols, uint64_t
 
 struct TcGemmPlan {
   CUtensorMap map_a, map_b, map_c;
+  CUtensorMap map_b2;               // 2-CTA variant: box of block_n / 2 rows of W^T
+  CUtensorMap map_bs;               // B-stationary variant: box of 128 rows of W^T (valid when N_pad % 128 == 0)
   int M, N, N_pad, K, block_n;
   const void* c_ptr = nullptr;      // output the store map was encoded for
   long long c_ld = 0;
@@ -438,6 +705,10 @@ int tc_gemm_plan_create(TcGemmPlan** out, const bf16* A, long long lda, int M, i
   p->M = M; p->N = N; p->N_pad = N_pad; p->K = K;
   // widest tile that divides the padded N: 256 (fc1), 192 (q|k|v, 384-wide outputs), 128, 64 (heads)
   p->block_n = (N_pad % 256 == 0) ? 256 : (N_pad % 192 == 0) ? 192 : (N_pad % 128 == 0) ? 128 : 64;
+  if (const char* e = getenv("UU_GEMM_BN")) {           // tile-width experiment
+    const int bn = atoi(e);
+    if ((bn == 64 || bn == 128 || bn == 192 || bn == 256) && N_pad % bn == 0) p->block_n = bn;
+  }
   if (N_pad % p->block_n != 0) {
     delete p;
     set_error("tcgen05 GEMM needs the packed weight rows padded to a multiple of 64");
@@ -445,6 +716,14 @@ int tc_gemm_plan_create(TcGemmPlan** out, const bf16* A, long long lda, int M, i
   }
   if (encode_2d(&p->map_a, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, TC_BLOCK_K, TC_BLOCK_M) ||
       encode_2d(&p->map_b, Wt, (uint64_t)K, (uint64_t)N_pad, (uint64_t)K, TC_BLOCK_K, (uint32_t)p->block_n)) {
+    delete p;
+    return 1;
+  }
+  if (N_pad % 128 == 0 && encode_2d(&p->map_bs, Wt, (uint64_t)K, (uint64_t)N_pad, (uint64_t)K, TC_BLOCK_K, 128)) {
+    delete p;
+    return 1;
+  }
+  if (encode_2d(&p->map_b2, Wt, (uint64_t)K, (uint64_t)N_pad, (uint64_t)K, TC_BLOCK_K, (uint32_t)p->block_n / 2)) {
     delete p;
     return 1;
   }
@@ -479,6 +758,54 @@ static cudaError_t tc_launch_t(const TcGemmPlan* p, const Epilogue& epi, void* C
   return cudaGetLastError();
 }
 
+// B-stationary launch: grid = n_tiles * floor(SMs / n_tiles) so that every CTA keeps one column block
+template <int BLOCK_N, int BS_KB>
+static cudaError_t tc_launch_bs(const TcGemmPlan* p, const Epilogue& epi, void* C, long long ldc, cudaStream_t st) {
+  using Cfg = TcCfg<BLOCK_N, BS_KB>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BLOCK_N, bf16, true, BS_KB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int n_tiles = p->N_pad / BLOCK_N;
+  const int m_tiles = (p->M + TC_BLOCK_M - 1) / TC_BLOCK_M;
+  int per_col = g_num_sms / n_tiles;
+  if (per_col > m_tiles) per_col = m_tiles;
+  k_gemm_tc<BLOCK_N, bf16, true, BS_KB><<<n_tiles * per_col, TC_THREADS, Cfg::SMEM_BYTES, st>>>(
+      p->map_a, p->map_bs, p->map_c, p->M, p->N, n_tiles, p->K, epi, reinterpret_cast<bf16*>(C), ldc);
+  return cudaGetLastError();
+}
+
+template <int BLOCK_N>
+static cudaError_t tc2_launch_t(const TcGemmPlan* p, const Epilogue& epi, cudaStream_t st) {
+  using Cfg = Tc2Cfg<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_tc2<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int n_tiles = p->N_pad / BLOCK_N;
+  const int total = ((p->M + 2 * TC_BLOCK_M - 1) / (2 * TC_BLOCK_M)) * n_tiles;
+  const int clusters = total < g_num_sms / 2 ? total : g_num_sms / 2;      // persistent: one CTA pair per TPC
+  k_gemm_tc2<BLOCK_N><<<2 * clusters, TC_THREADS, Cfg::SMEM_BYTES, st>>>(p->map_a, p->map_b2, p->map_c, p->M, n_tiles, p->K, epi);
+  return cudaGetLastError();
+}
+
+static int g_use_2cta = -1;     // UU_GEMM_2CTA=0/1 forces the single-CTA / 2-CTA kernel (A/B comparison)
+
 // bf16 output, plain row mapping, no residual / table / scatter, full 64-column sub-tiles: TMA-store epilogue
 static bool tma_out_eligible(const TcGemmPlan* p, const Epilogue& epi, int c_bf16, long long ldc) {
   return c_bf16 && !epi.c_rowidx && !epi.m_dev && epi.cmap.rpb == 0x7fffffff &&
@@ -486,11 +813,34 @@ static bool tma_out_eligible(const TcGemmPlan* p, const Epilogue& epi, int c_bf1
          p->block_n >= 64;
 }
 
-cudaError_t tc_gemm_launch(TcGemmPlan* p, const Epilogue& epi, void* C, int c_bf16, long long ldc, cudaStream_t st) {
+cudaError_t tc_gemm_launch(TcGemmPlan* p, const Epilogue& epi_in, void* C, int c_bf16, long long ldc, cudaStream_t st) {
+  static int nostore = -1;
+  if (nostore < 0) { const char* e = getenv("UU_GEMM_NOSTORE"); nostore = (e && e[0] == '1') ? 1 : 0; }
+  Epilogue epi = epi_in;
+  if (nostore) epi.flags |= 64;
+  static int noload = -1;
+  if (noload < 0) { const char* e = getenv("UU_GEMM_NOLOAD"); noload = (e && e[0] == '1') ? 1 : 0; }
+  if (noload) epi.flags |= 128;
   if (tma_out_eligible(p, epi, c_bf16, ldc)) {
     if (p->c_ptr != C || p->c_ld != ldc) {
-      if (encode_2d(&p->map_c, C, (uint64_t)p->N, (uint64_t)p->M, (uint64_t)ldc, 64, TC_BLOCK_M)) return cudaErrorInvalidValue;
+      if (encode_2d(&p->map_c, C, (uint64_t)p->N, (uint64_t)p->M, (uint64_t)ldc, 64, 32)) return cudaErrorInvalidValue;
       p->c_ptr = C; p->c_ld = ldc;
+    }
+    if (g_use_2cta < 0) {
+      const char* e = getenv("UU_GEMM_2CTA");
+      g_use_2cta = e ? (e[0] == '1' ? 1 : 0) : 2;   // default (2): only where it measured faster, the K >= 768 GEMMs
+    }
+    static int use_bs = -1;
+    if (use_bs < 0) { const char* e = getenv("UU_GEMM_BSTAT"); use_bs = (e && e[0] == '1') ? 1 : 0; }   // default off: measured no faster
+    // short-K GEMMs with M >> N: keep the weight tile resident (K = 384 -> 6 panels of a 128-wide column block)
+    if (use_bs && p->K == 384 && p->N_pad % 128 == 0 && p->M >= 4 * TC_BLOCK_M * (p->N_pad / 128))
+      return tc_launch_bs<128, 6>(p, epi, C, ldc, st);
+    if ((g_use_2cta == 1 || (g_use_2cta == 2 && p->K >= 768)) && p->M >= 512 && (p->block_n == 256 || p->block_n == 192 || p->block_n == 128)) {
+      switch (p->block_n) {
+        case 256: return tc2_launch_t<256>(p, epi, st);
+        case 192: return tc2_launch_t<192>(p, epi, st);
+        default: return tc2_launch_t<128>(p, epi, st);
+      }
     }
     switch (p->block_n) {
       case 256: return tc_launch_t<256, bf16, true>(p, epi, C, ldc, st);

@@ -533,6 +533,128 @@ cudaError_t launch_residual_ln(const float* xsrc, const RowMap& smap, const bf16
   return cudaGetLastError();
 }
 
+// =================================================================================================
+// bf16-resident residual stream (bf16 schedule): the same three streaming kernels with X stored as bf16
+// between kernels (statistics, adds and the LayerNorm arithmetic stay fp32).  Halves the dominant HBM
+// stream of the temporal blocks (the fp32 X round trip was 2/3 of the residual+LN traffic).
+// =================================================================================================
+__device__ __forceinline__ float4 ld_bf16x4(const bf16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&u.x), hi = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+  return make_float4(__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi));
+}
+__device__ __forceinline__ void st_bf16x4(bf16* p, float a, float b, float c, float d) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  uint2 pk;
+  pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = pk;
+}
+
+__global__ void k_token_fill_bx(const uint8_t* __restrict__ mask, int rows, int n_tok, int d4,
+                                const float4* __restrict__ token, const float4* __restrict__ pe, bf16* __restrict__ x) {
+  const int per_block = blockDim.x / 32;
+  const int lane = threadIdx.x & 31;
+  for (int row = blockIdx.x * per_block + (threadIdx.x >> 5); row < rows; row += gridDim.x * per_block) {
+    if (mask[row]) continue;
+    const int n = row % n_tok;
+    for (int c = lane; c < d4; c += 32) {
+      const float4 t = token[c], q = pe[(long long)n * d4 + c];
+      st_bf16x4(x + ((long long)row * d4 + c) * 4, t.x + q.x, t.y + q.y, t.z + q.z, t.w + q.w);
+    }
+  }
+}
+cudaError_t launch_token_fill_bx(const uint8_t* mask, int rows, int n_tok, int d, const float* token, const float* pe,
+                                 bf16* x, cudaStream_t st) {
+  if (rows == 0) return cudaSuccess;
+  if (d % 4) return cudaErrorInvalidValue;
+  int grid = (rows + 7) / 8;
+  if (grid > 148 * 16) grid = 148 * 16;
+  k_token_fill_bx<<<grid, 256, 0, st>>>(mask, rows, n_tok, d / 4, reinterpret_cast<const float4*>(token),
+                                        reinterpret_cast<const float4*>(pe), x);
+  return cudaGetLastError();
+}
+
+// v = xsrc[map(r)] (+ upd[r]) ; xcast[r] = bf16(v) (opt) ; v += table[r % period] (opt) ; xdst[r] = bf16(v) (opt) ;
+// y[r] = bf16(LN(v)) (opt).  upd == null: plain LayerNorm of the stream (first temporal block).
+template <int V>
+__global__ void k_residual_ln_bx(const bf16* __restrict__ xsrc, RowMap smap, const bf16* __restrict__ upd,
+                                 bf16* __restrict__ xdst, int rows, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, float eps, const float* __restrict__ table, int period,
+                                 bf16* __restrict__ y, bf16* __restrict__ xcast) {
+  constexpr int D = V * 128;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const long long srow = map_row(smap, row);
+  const bf16* xr = xsrc + srow * D;
+  float4 v[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) v[i] = ld_bf16x4(xr + (lane + 32 * i) * 4);
+  if (upd) {
+    const bf16* ur = upd + (long long)row * D;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float4 u = ld_bf16x4(ur + (lane + 32 * i) * 4);
+      v[i].x += u.x; v[i].y += u.y; v[i].z += u.z; v[i].w += u.w;
+    }
+  }
+  if (xcast) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) st_bf16x4(xcast + (long long)row * D + (lane + 32 * i) * 4, v[i].x, v[i].y, v[i].z, v[i].w);
+  }
+  if (table) {
+    const float4* tr = reinterpret_cast<const float4*>(table + (long long)(row % period) * D);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float4 t = tr[lane + 32 * i];
+      v[i].x += t.x; v[i].y += t.y; v[i].z += t.z; v[i].w += t.w;
+    }
+  }
+  if (xdst) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) st_bf16x4(xdst + (long long)row * D + (lane + 32 * i) * 4, v[i].x, v[i].y, v[i].z, v[i].w);
+  }
+  if (!y) return;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(s) * (1.f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / D) + eps);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const float4 g = g4[lane + 32 * i], b = b4[lane + 32 * i];
+    st_bf16x4(y + (long long)row * D + (lane + 32 * i) * 4,
+              v[i].x * (g.x * rstd) + (b.x - mean * (g.x * rstd)), v[i].y * (g.y * rstd) + (b.y - mean * (g.y * rstd)),
+              v[i].z * (g.z * rstd) + (b.z - mean * (g.z * rstd)), v[i].w * (g.w * rstd) + (b.w - mean * (g.w * rstd)));
+  }
+}
+
+cudaError_t launch_residual_ln_bx(const bf16* xsrc, const RowMap& smap, const bf16* upd, bf16* xdst, int rows, int d,
+                                  const float* gamma, const float* beta, float eps, const float* table, int period,
+                                  bf16* y, bf16* xcast, cudaStream_t st) {
+  if (rows == 0) return cudaSuccess;
+  const int wpb = 8, grid = (rows + wpb - 1) / wpb;
+#define UU_RLN_CASE(VV)                                                                                           \
+  case VV * 128:                                                                                                  \
+    k_residual_ln_bx<VV><<<grid, wpb * 32, 0, st>>>(xsrc, smap, upd, xdst, rows, gamma, beta, eps, table, period, \
+                                                    y, xcast);                                                    \
+    break;
+  switch (d) {
+    UU_RLN_CASE(1) UU_RLN_CASE(2) UU_RLN_CASE(3) UU_RLN_CASE(4) UU_RLN_CASE(6) UU_RLN_CASE(8)
+    default: return cudaErrorInvalidValue;
+  }
+#undef UU_RLN_CASE
+  return cudaGetLastError();
+}
+
 __global__ void k_cast_bf16(const float4* __restrict__ x, uint2* __restrict__ y, long long n4) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 v = x[i];

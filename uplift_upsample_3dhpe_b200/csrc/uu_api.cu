@@ -304,8 +304,9 @@ static int run_forward(uu_model* m, const float* x2d, const uint8_t* mask, int B
   return rc;
 }
 // ---- bf16 schedule --------------------------------------------------------------------------------
-// Every dense contraction is a tcgen05 GEMM with bf16 operands and a bf16 result; the fp32 residual
-// stream is touched only by the streaming residual+LayerNorm kernel (one read, one write per half block).
+// Every dense contraction is a tcgen05 GEMM with bf16 operands and a bf16 result; the residual stream is
+// bf16-resident and touched only by the streaming residual+LayerNorm kernel (one read, one write per half
+// block; adds, statistics and the normalisation are fp32 in registers).
 static int tc_gemm_bf16(Fwd& f, const void* A, long long lda, int M, int K, const Pack& pk, int N, const float* bias,
                         bool relu, void* C, long long ldc, const RowMap* cmap = nullptr) {
   Epilogue e;
@@ -323,6 +324,7 @@ static int run_forward_bf16(Fwd& f, const float* x2d, const uint8_t* mask, float
   const bool use_mask = s.has_strided_input != 0;
   const bool want_full = s.full_output && full;
   bf16 *Y = (bf16*)m->Y, *QKV = (bf16*)m->QKV, *O = (bf16*)m->O, *Hd = (bf16*)m->Hd, *P = (bf16*)m->P;
+  bf16* X = reinterpret_cast<bf16*>(m->X);      // residual stream, bf16-resident in this schedule (buffer sized for fp32)
   const RowMap plain;
 
   if (use_mask) UU_LAUNCH(f, UU_KIND_GATHER, 3, launch_build_gather(mask, B, N, m->g_scratch, m->g_list, m->g_count, st));
@@ -334,13 +336,14 @@ static int run_forward_bf16(Fwd& f, const float* x2d, const uint8_t* mask, float
     e.bias = W(m, "spatial_to_temporal_fc", 1);
     e.flags = EPI_ROWTABLE; e.table = W(m, "temporal_pe", 0); e.table_period = N;
     if (use_mask) { e.c_rowidx = m->g_list; e.m_dev = m->g_count; }
-    if (gemm(f, m->S, J * ds, R, J * ds, nullptr, m->p_s2t, d, e, m->X, 0, d)) return 1;
+    if (gemm(f, m->S, J * ds, R, J * ds, nullptr, m->p_s2t, d, e, X, 1, d)) return 1;
     if (use_mask)
       UU_LAUNCH(f, UU_KIND_TOKEN_FILL, 1,
-                launch_token_fill(mask, R, N, d, W(m, "strided_input_token_layer", 0), W(m, "temporal_pe", 0), m->X, st));
+                launch_token_fill_bx(mask, R, N, d, W(m, "strided_input_token_layer", 0), W(m, "temporal_pe", 0), X, st));
   }
   UU_LAUNCH(f, UU_KIND_LAYERNORM, 1,
-            launch_layernorm(m->X, R, d, m->tblocks[0].ln1_g, m->tblocks[0].ln1_b, 1e-5f, nullptr, 1, Y, 1, st));
+            launch_residual_ln_bx(X, plain, nullptr, nullptr, R, d, m->tblocks[0].ln1_g, m->tblocks[0].ln1_b, 1e-5f, nullptr,
+                                  1, Y, nullptr, st));
   for (int i = 0; i < s.temporal_depth; ++i) {
     const BlockW& w = m->tblocks[i];
     const uint8_t* km = (use_mask && i < s.first_strided_token_attention_layer) ? mask : nullptr;
@@ -348,17 +351,17 @@ static int run_forward_bf16(Fwd& f, const float* x2d, const uint8_t* mask, float
     UU_LAUNCH(f, UU_KIND_ATTENTION, 1, launch_attention_tc(QKV, B, N, H, dh, km, N, O, st));
     if (tc_gemm_bf16(f, O, d, R, d, w.p_proj, d, w.bp, false, P, d)) return 1;
     UU_LAUNCH(f, UU_KIND_LAYERNORM, 1,
-              launch_residual_ln(m->X, plain, P, m->X, R, d, w.ln2_g, w.ln2_b, 1e-5f, nullptr, 1, Y, nullptr, st));
+              launch_residual_ln_bx(X, plain, P, X, R, d, w.ln2_g, w.ln2_b, 1e-5f, nullptr, 1, Y, nullptr, st));
     if (tc_gemm_bf16(f, Y, d, R, d, w.p_fc1, h, w.b1, true, Hd, h)) return 1;
     if (tc_gemm_bf16(f, Hd, h, R, h, w.p_fc2, d, w.b2, false, P, d)) return 1;
     if (i + 1 < s.temporal_depth) {
       const BlockW& nx = m->tblocks[i + 1];
       UU_LAUNCH(f, UU_KIND_LAYERNORM, 1,
-                launch_residual_ln(m->X, plain, P, m->X, R, d, nx.ln1_g, nx.ln1_b, 1e-5f, nullptr, 1, Y, nullptr, st));
+                launch_residual_ln_bx(X, plain, P, X, R, d, nx.ln1_g, nx.ln1_b, 1e-5f, nullptr, 1, Y, nullptr, st));
     } else {   // last temporal block: bf16 copy for the full-sequence head, then + PE_1 and LN1 of strided block 1
       const BlockW& nx = m->sblocks[0];
       UU_LAUNCH(f, UU_KIND_LAYERNORM, 1,
-                launch_residual_ln(m->X, plain, P, m->X, R, d, nx.ln1_g, nx.ln1_b, 1e-5f,
+                launch_residual_ln_bx(X, plain, P, X, R, d, nx.ln1_g, nx.ln1_b, 1e-5f,
                                    W(m, "strided_temporal_pe_1", 0), N, Y, want_full ? O : nullptr, st));
     }
   }
@@ -367,7 +370,7 @@ static int run_forward_bf16(Fwd& f, const float* x2d, const uint8_t* mask, float
     e.bias = W(m, "temporal_fc", 1);
     if (gemm(f, O, d, R, d, nullptr, m->p_head1, 3 * J, e, full, 0, 3 * J)) return 1;
   }
-  float* x_in = m->X;
+  bf16* x_in = X;
   for (int i = 0; i < s.n_strided; ++i) {   // Q1/Q2
     const BlockW& w = m->sblocks[i];
     const int L = m->seq_lens[i], Lo = m->seq_lens[i + 1], st_i = s.strides[i], pl = s.pad_left[i];
@@ -376,7 +379,7 @@ static int run_forward_bf16(Fwd& f, const float* x2d, const uint8_t* mask, float
     UU_LAUNCH(f, UU_KIND_ATTENTION, 1, launch_attention_tc(QKV, B, L, H, dh, nullptr, L, O, st));
     if (tc_gemm_bf16(f, O, d, Rl, d, w.p_proj, d, w.bp, false, P, d)) return 1;
     UU_LAUNCH(f, UU_KIND_LAYERNORM, 1,
-              launch_residual_ln(x_in, plain, P, x_in, Rl, d, w.ln2_g, w.ln2_b, 1e-5f, nullptr, 1, Y, nullptr, st));
+              launch_residual_ln_bx(x_in, plain, P, x_in, Rl, d, w.ln2_g, w.ln2_b, 1e-5f, nullptr, 1, Y, nullptr, st));
     RowMap cm;   // Conv1D k=1 + ReLU into the zero-padded layout [B, Lo*s, h]
     cm.rpb = L; cm.batch_rows = Lo * st_i; cm.offset = pl; cm.step = 1;
     if (tc_gemm_bf16(f, Y, d, Rl, d, w.p_fc1, h, w.b1, true, m->Hp[i], h, &cm)) return 1;
@@ -387,13 +390,13 @@ static int run_forward_bf16(Fwd& f, const float* x2d, const uint8_t* mask, float
     if (i + 1 < s.n_strided) {
       const BlockW& nx = m->sblocks[i + 1];
       UU_LAUNCH(f, UU_KIND_LAYERNORM, 1,
-                launch_residual_ln(x_in, idm, P, m->Xs[i], Ro, d, nx.ln1_g, nx.ln1_b, 1e-5f,
+                launch_residual_ln_bx(x_in, idm, P, reinterpret_cast<bf16*>(m->Xs[i]), Ro, d, nx.ln1_g, nx.ln1_b, 1e-5f,
                                    W(m, "strided_temporal_pe_" + std::to_string(i + 2), 0), Lo, Y, nullptr, st));
     } else {
       UU_LAUNCH(f, UU_KIND_LAYERNORM, 1,
-                launch_residual_ln(x_in, idm, P, m->Xs[i], Ro, d, nullptr, nullptr, 0.f, nullptr, 1, nullptr, O, st));
+                launch_residual_ln_bx(x_in, idm, P, reinterpret_cast<bf16*>(m->Xs[i]), Ro, d, nullptr, nullptr, 0.f, nullptr, 1, nullptr, O, st));
     }
-    x_in = m->Xs[i];
+    x_in = reinterpret_cast<bf16*>(m->Xs[i]);
   }
   {   // Q3
     Epilogue e;
