@@ -58,43 +58,65 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled every ~5 ms from a thread
+    (nvidia-smi -lms is the fallback; its first sample can arrive after a short timed region has ended)."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+               ("sw_power_cap", 0x4))
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.samples, self.mask, self.max_mhz = index, [], 0, None
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
+
+    def _visible_index(self) -> int:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.index < len(ids) and ids[self.index].isdigit():
+                return int(ids[self.index])
+        return self.index
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            h = pynvml.nvmlDeviceGetHandleByIndex(self._visible_index())
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            def poll():
+                while not self._stop.is_set():
+                    try:
+                        self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                    except Exception:
+                        pass
+                    time.sleep(0.005)
+            self._thread = threading.Thread(target=poll, daemon=True)
+            self._thread.start()
+        except Exception:
+            self._nvml = None
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], None, set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx = float(r[1])
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        top = sorted(sm)[len(sm) // 2:] if sm else []       # samples under load = upper half
-        return {"sm_mhz": statistics.median(top) if top else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        if self._nvml is None:
+            return self._smi_once()
+        self._stop.set()
+        self._thread.join(timeout=1.0)
+        if not self.samples:
+            return self._smi_once()
+        reasons = [n for n, bit in self.REASONS if self.mask & bit]
+        return {"sm_mhz": statistics.median(self.samples), "sm_min_mhz": min(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": reasons, "samples": len(self.samples), "source": "nvml, 5 ms polling over the timed region"}
+
+    def _smi_once(self) -> dict:
+        try:
+            out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm",
+                                  "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+            a, b = [float(v) for v in out.strip().split(",")]
+            return {"sm_mhz": a, "sm_max_mhz": b, "reasons": [], "samples": 1, "source": "nvidia-smi after the timed region"}
+        except Exception:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable"], "samples": 0}
 
 
 def synth_inputs(spec: ModelSpec, cfg, B: int, s_in: int, seed: int):

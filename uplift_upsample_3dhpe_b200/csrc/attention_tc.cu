@@ -19,6 +19,11 @@ __device__ __forceinline__ uint32_t pack2_att(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+__device__ __forceinline__ float ex2_att(float x) {      // x <= 0 (or -inf): 2^x, flushing to zero
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
   const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
@@ -61,8 +66,12 @@ __global__ void __launch_bounds__(32 * ST) k_attention_tc(const bf16* __restrict
   const int g = lane >> 2, t = lane & 3;
   const int d = heads * DH;
   const long long row0 = (long long)b * S;
-  for (int i = tid; i < SP * CH; i += 32 * ST) {
-    const int key = i / CH, c = i - key * CH;
+  // (key, chunk) walk without per-iteration division: thread tid starts at (tid / CH, tid % CH) and advances by
+  // 32*ST chunks = (32*ST / CH) keys + (32*ST % CH) chunks
+  constexpr int DK = (32 * ST) / CH, DC = (32 * ST) % CH;
+  int key = tid / CH, c = tid - key * CH;
+  for (int i = tid; i < SP * CH; i += 32 * ST, key += DK, c += DC) {
+    if (c >= CH) { c -= CH; ++key; }
     const int so = key * RS + c * 8;
     if (key < S) {
       const bf16* r = qkv + (row0 + key) * 3 * d + h * DH + c * 8;
@@ -78,7 +87,7 @@ __global__ void __launch_bounds__(32 * ST) k_attention_tc(const bf16* __restrict
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
   for (int j = tid; j < SP; j += 32 * ST)
-    Km[j] = j >= S ? -INFINITY : ((mask && !mask[(long long)b * mask_stride + j]) ? -1e9f : 0.f);
+    Km[j] = j >= S ? -INFINITY : ((mask && !mask[(long long)b * mask_stride + j]) ? -1e9f * 1.4426950408889634f : 0.f);
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
@@ -107,25 +116,28 @@ __global__ void __launch_bounds__(32 * ST) k_attention_tc(const bf16* __restrict
       mma16816_att(sc[j], aq[DH / 16 - 1], bk[0], bk[1]);
     }
   }
-  // logits = s / sqrt(dh) + key term (fp32, literal), row max, exp, row sum
-  const float scale = 1.0f / sqrtf((float)DH);
+  // logits * log2(e) = s * (log2(e) / sqrt(dh)) + key term * log2(e): one FMA per score, softmax evaluated with exp2.
+  // The key term keeps the reference's fp32 behaviour (vit:122-123): a masked key sits ~1e9 below every kept one
+  // (its weight underflows to exactly 0), and when every key is masked all logits round to the same value
+  // (|s| << ulp(1.44e9) = 128), i.e. uniform attention, exactly as x - 1e9 rounds to -1e9 in the reference.
+  const float LOG2E = 1.4426950408889634f;
+  const float scale = LOG2E / sqrtf((float)DH);
   float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
   for (int j = 0; j < NT; ++j) {
     const float2 km = *reinterpret_cast<const float2*>(Km + 8 * j + 2 * t);
-    sc[j][0] = sc[j][0] * scale + km.x; sc[j][1] = sc[j][1] * scale + km.y;
-    sc[j][2] = sc[j][2] * scale + km.x; sc[j][3] = sc[j][3] * scale + km.y;
+    sc[j][0] = fmaf(sc[j][0], scale, km.x); sc[j][1] = fmaf(sc[j][1], scale, km.y);
+    sc[j][2] = fmaf(sc[j][2], scale, km.x); sc[j][3] = fmaf(sc[j][3], scale, km.y);
     m0 = fmaxf(m0, fmaxf(sc[j][0], sc[j][1]));
     m1 = fmaxf(m1, fmaxf(sc[j][2], sc[j][3]));
   }
   m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
   m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
   float l0 = 0.f, l1 = 0.f;
-  const float LOG2E = 1.4426950408889634f;
 #pragma unroll
   for (int j = 0; j < NT; ++j) {
-    sc[j][0] = exp2f((sc[j][0] - m0) * LOG2E); sc[j][1] = exp2f((sc[j][1] - m0) * LOG2E);
-    sc[j][2] = exp2f((sc[j][2] - m1) * LOG2E); sc[j][3] = exp2f((sc[j][3] - m1) * LOG2E);
+    sc[j][0] = ex2_att(sc[j][0] - m0); sc[j][1] = ex2_att(sc[j][1] - m0);
+    sc[j][2] = ex2_att(sc[j][2] - m1); sc[j][3] = ex2_att(sc[j][3] - m1);
     l0 += sc[j][0] + sc[j][1];
     l1 += sc[j][2] + sc[j][3];
   }

@@ -65,6 +65,14 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {      // global -> L2 only
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {          // true in exactly one lane of a converged warp
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -267,11 +275,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
             tma_load_2d(smem_bres + kb * Cfg::B_BYTES, &map_b, bres_bar, kb * TC_BLOCK_K, col0);
         }
       }
+      int s = 0;
+      uint32_t ph = 0;
       for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
         const int row0 = (tile / n_tiles) * TC_BLOCK_M, col0 = (tile % n_tiles) * BLOCK_N;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % Cfg::STAGES;
-          const uint32_t ph = (it / Cfg::STAGES) & 1;
+        // A rows are streamed from HBM exactly once but needed by all n_tiles column blocks at about the same time,
+        // so every stage used to pay the full DRAM latency (~1.9 us under load, more than the ring covers).  The CTA
+        // that will own column block 0 of a row block pulls that row block into L2 one tile ahead.
+        {
+          const int nt = tile + tile_step;
+          if (nt < total_tiles && (nt % n_tiles) == 0 && !(epi.flags & 256)) {
+            const int prow = (nt / n_tiles) * TC_BLOCK_M;
+            for (int kb = 0; kb < num_kb; ++kb) tma_prefetch_2d(&map_a, kb * TC_BLOCK_K, prow);
+          }
+        }
+        for (int kb = 0; kb < num_kb; ++kb, ++it, s = (s + 1 == Cfg::STAGES ? 0 : s + 1), ph ^= (s == 0)) {
           mbar_wait(empty_bar + s, ph ^ 1);
           uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
           if (epi.flags & 128) {                 // (flag 128: timing experiment UU_GEMM_NOLOAD — MMA on stale smem)
@@ -286,34 +304,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
-    if (lane == 0) {
+    // The whole warp walks the loop (warp-uniform control flow, every lane polls the barriers) and one elected
+    // lane issues the tcgen05 instructions.  The loop body is kept to a handful of instructions per MMA: a
+    // 128 x BLOCK_N x 16 MMA retires in BLOCK_N / 2 cycles, so with 64-wide k-blocks the issue loop, not the tensor
+    // pipe, was the pacer of these short-K GEMMs (descriptors are now one add from a per-kernel base, stage and
+    // phase are carried incrementally).
+    {
       constexpr uint32_t idesc = make_idesc_bf16(TC_BLOCK_M, BLOCK_N);
-      uint32_t it = 0, tcount = 0;
+      const uint64_t a_desc0 = make_sw128_desc(smem_u32(smem));
+      const uint64_t b_desc0 = BS ? make_sw128_desc(smem_u32(smem_bres)) : make_sw128_desc(smem_u32(smem + Cfg::A_BYTES));
+      int s = 0;
+      uint32_t ph = 0, tcount = 0;
       if constexpr (BS) {
         if (tile_first < total_tiles) mbar_wait(bres_bar, 0);   // weight tile resident
       }
       for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++tcount) {
-        const int as = tcount % Cfg::ACC_STAGES;
-        const uint32_t aph = (tcount / Cfg::ACC_STAGES) & 1;
+        const int as = tcount & 1;
+        const uint32_t aph = (tcount >> 1) & 1;
         mbar_wait(tmem_empty_bar + as, aph ^ 1);          // epilogue has drained this accumulator
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BLOCK_N);
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % Cfg::STAGES;
-          const uint32_t ph = (it / Cfg::STAGES) & 1;
+#pragma unroll 1
+        for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar + s, ph);
           tcgen05_fence_after();
-          const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
-          const uint32_t b_addr = BS ? smem_u32(smem_bres + kb * Cfg::B_BYTES) : a_addr + Cfg::A_BYTES;
-          const uint64_t a_desc = make_sw128_desc(a_addr), b_desc = make_sw128_desc(b_addr);
+          if (elect_one()) {
+            const uint64_t a_desc = a_desc0 + (uint64_t)((s * Cfg::STAGE_BYTES) >> 4);
+            const uint64_t b_desc = b_desc0 + (uint64_t)(BS ? ((kb * Cfg::B_BYTES) >> 4) : ((s * Cfg::STAGE_BYTES) >> 4));
 #pragma unroll
-          for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
-            // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (>>4) address field
-            umma_bf16(tmem_d, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
+              // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (>>4) address field
+              umma_bf16(tmem_d, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            }
+            umma_commit(empty_bar + s);           // frees the smem stage when these MMAs retire
+            if (kb == num_kb - 1) umma_commit(tmem_full_bar + as);        // accumulator complete
           }
-          umma_commit(empty_bar + s);           // frees the smem stage when these MMAs retire
+          __syncwarp();
+          if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(tmem_full_bar + as);        // accumulator complete
       }
     }
   } else {
@@ -588,30 +616,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       }
     }
   } else if (warp == 1) {
-    // ---------------- MMA issuer (leader CTA only) ----------------
-    if (leader && lane == 0) {
+    // ---------------- MMA issuer (leader CTA only; warp-uniform loop, one elected lane issues) ----------------
+    if (leader) {
       constexpr uint32_t idesc = make_idesc_bf16(2 * TC_BLOCK_M, BLOCK_N);
-      uint32_t it = 0, tcount = 0;
+      const uint64_t a_desc0 = make_sw128_desc(smem_u32(smem));
+      const uint64_t b_desc0 = make_sw128_desc(smem_u32(smem + Cfg::A_BYTES));
+      int s = 0;
+      uint32_t ph = 0, tcount = 0;
       for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++tcount) {
-        const int as = tcount % Cfg::ACC_STAGES;
-        const uint32_t aph = (tcount / Cfg::ACC_STAGES) & 1;
+        const int as = tcount & 1;
+        const uint32_t aph = (tcount >> 1) & 1;
         mbar_wait(tmem_empty_bar + as, aph ^ 1);            // both CTAs' epilogues have drained this accumulator
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BLOCK_N);
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % Cfg::STAGES;
-          const uint32_t ph = (it / Cfg::STAGES) & 1;
+#pragma unroll 1
+        for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar + s, ph);
           tcgen05_fence_after();
-          const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
-          const uint64_t a_desc = make_sw128_desc(a_addr), b_desc = make_sw128_desc(b_addr);
+          if (elect_one()) {
+            const uint64_t off = (uint64_t)((s * Cfg::STAGE_BYTES) >> 4);
 #pragma unroll
-          for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k)
-            umma_bf16_2sm(tmem_d, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
-          umma_commit_2sm(empty_bar + s);       // frees the stage in both CTAs
+            for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k)
+              umma_bf16_2sm(tmem_d, a_desc0 + off + 2 * k, b_desc0 + off + 2 * k, idesc, (kb | k) != 0);
+            umma_commit_2sm(empty_bar + s);       // frees the stage in both CTAs
+            if (kb == num_kb - 1) umma_commit_2sm(tmem_full_bar + as);    // accumulator complete in both CTAs
+          }
+          __syncwarp();
+          if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit_2sm(tmem_full_bar + as);    // accumulator complete in both CTAs
       }
     }
   } else {
@@ -821,6 +853,9 @@ cudaError_t tc_gemm_launch(TcGemmPlan* p, const Epilogue& epi_in, void* C, int c
   static int noload = -1;
   if (noload < 0) { const char* e = getenv("UU_GEMM_NOLOAD"); noload = (e && e[0] == '1') ? 1 : 0; }
   if (noload) epi.flags |= 128;
+  static int nopf = -1;
+  if (nopf < 0) { const char* e = getenv("UU_GEMM_NOPREFETCH"); nopf = (e && e[0] == '1') ? 1 : 0; }
+  if (nopf) epi.flags |= 256;
   if (tma_out_eligible(p, epi, c_bf16, ldc)) {
     if (p->c_ptr != C || p->c_ld != ldc) {
       if (encode_2d(&p->map_c, C, (uint64_t)p->N, (uint64_t)p->M, (uint64_t)ldc, 64, 32)) return cudaErrorInvalidValue;
