@@ -89,6 +89,22 @@ int uu_forward(uu_model* m, const float* x2d, const uint8_t* mask, int B, float*
 int uu_forward_host(uu_model* m, const float* x2d, const uint8_t* mask, int B, float* full, float* central);
 
 /* Number of kernels of this library launched by the most recent forward on `m`. */
+/* Sliding windows cut ON THE DEVICE from one video (replaces the host-side window
+ * materialisation of common/dataset/uplifiting_dataset.py:341-394 + eval.py:63-71 — a 71x input blow-up).
+ * video2d: (T, n_joints, 2) float; centers: B int32 frame indices in [0, T).  Window b, token k reads frame
+ * (k - n_tok/2) * s_out + centers[b]; frames outside the video are padded by repeating the first / last in-range
+ * strided sample (pad_copy = 1, PADDING_TYPE "copy") or with zeros (pad_copy = 0).  The stride mask is the globally
+ * aligned one of the eval generator, (frame mod s_in == 0) with floor-mod, built on the device; tokens it rejects are
+ * never read.  Outputs as uu_forward.  The _host variant takes host pointers for every buffer. */
+int uu_forward_video(uu_model* m, const float* video2d, int T, const int32_t* centers, int B, int s_out, int s_in,
+                     int pad_copy, float* full, float* central, void* stream);
+int uu_forward_video_host(uu_model* m, const float* video2d, int T, const int32_t* centers, int B, int s_out, int s_in,
+                          int pad_copy, float* full, float* central);
+/* The gather alone: src (B*n_tok int32 source frame, -1 = zeros), mask (B*n_tok), and, when x2d != NULL, the
+ * materialised (B, n_tok, n_joints, 2) windows exactly as the reference generator yields them (unmasked). */
+int uu_op_window_gather(const float* video2d, int T, const int32_t* centers, int B, int n_tok, int n_joints, int s_out,
+                        int s_in, int pad_copy, int32_t* src, uint8_t* mask, float* x2d, void* stream);
+
 int uu_last_launch_count(const uu_model* m);
 
 /* Per-kernel-kind device timing of the most recent forward: with profiling on, every launch is

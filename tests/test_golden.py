@@ -72,3 +72,17 @@ def test_stride_masks_are_bit_exact(path):
         for c, row in zip(z["centers"], want):
             _lib.check(lib.uu_stride_mask(n_tok, stride, int(z["mask_stride"]), int(c), buf))
             assert np.array_equal(np.frombuffer(buf, dtype=np.uint8).astype(bool), row)
+
+
+@pytest.mark.parametrize("path", [p for p in WINDOWS if "eval" in p], ids=lambda p: os.path.basename(p)[8:-4])
+def test_window_source_frames_match_reference_generator(path):
+    """Host twin of the device window gather: the reference generator's windows (edge-padded, strided) bit for bit."""
+    z = np.load(path, allow_pickle=False)
+    n_tok, stride = int(z["n_tok"]), int(z["stride"])
+    video = z["video_2d"]
+    src = stride_mask.window_source_frames(n_tok, stride, video.shape[0], z["centers"], pad_copy=True)
+    assert src.min() >= 0 and src.max() < video.shape[0]
+    assert np.array_equal(video[src], z["seq_2d"])
+    # padded positions are exactly those the generator's pad mask marks with 0
+    f = (np.arange(n_tok)[None, :] - n_tok // 2) * stride + z["centers"][:, None]
+    assert np.array_equal(((f >= 0) & (f < video.shape[0])).astype(np.float32), z["pad_masks"])

@@ -45,3 +45,51 @@ def test_h5_written_by_us_loads_through_c_abi(tmp_path):
     torch.cuda.synchronize()
     assert np.abs(central.cpu().numpy() - z["central_f32"]).max() <= 1e-4
     model.close()
+
+
+from test_golden import WINDOWS  # noqa: E402
+
+
+@pytest.mark.parametrize("path", [p for p in WINDOWS if "eval" in p], ids=lambda p: os.path.basename(p)[8:-4])
+def test_device_window_gather_is_bit_exact(path):
+    """uu_op_window_gather against the reference generator's windows and stride masks (tests/golden)."""
+    import ctypes
+    from uplift_upsample_3dhpe_b200 import _lib
+    lib = _lib.load()
+    z = np.load(path, allow_pickle=False)
+    n_tok, stride, s_in = int(z["n_tok"]), int(z["stride"]), int(z["mask_stride"])
+    video = torch.from_numpy(z["video_2d"]).cuda()
+    centers = torch.from_numpy(z["centers"].astype(np.int32)).cuda()
+    B, T = centers.shape[0], video.shape[0]
+    src = torch.empty((B, n_tok), dtype=torch.int32, device="cuda")
+    mask = torch.empty((B, n_tok), dtype=torch.uint8, device="cuda")
+    x = torch.empty((B, n_tok, 17, 2), dtype=torch.float32, device="cuda")
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    _lib.check(lib.uu_op_window_gather(P(video), T, P(centers), B, n_tok, 17, stride, s_in, 1, P(src), P(mask), P(x), None))
+    torch.cuda.synchronize()
+    assert np.array_equal(mask.cpu().numpy().astype(bool), z["stride_masks"])
+    assert np.array_equal(x.cpu().numpy(), z["seq_2d"])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_forward_video_equals_forward_on_materialised_windows(precision):
+    """The fused gather changes where the key-points are read from, not a single arithmetic operation."""
+    from uplift_upsample_3dhpe_b200 import UpliftUpsampleConfig, spec_from_config, stride_mask, weights
+    cfg = UpliftUpsampleConfig.preset("h36m_351", MASK_STRIDE=20)
+    spec = spec_from_config(cfg)
+    w = weights.init_weights(spec, 5, perturb=True)
+    rng = np.random.default_rng(11)
+    T = 260
+    video = rng.uniform(-1, 1, (T, 17, 2)).astype(np.float32)
+    centers = np.concatenate([np.arange(0, 40, 5), np.arange(100, 140, 5), np.arange(T - 40, T, 5), [3, 7]]).astype(np.int32)
+    src = stride_mask.window_source_frames(spec.n_tok, 5, T, centers)
+    m = stride_mask.batch_stride_masks_eval(spec.n_tok, 5, 20, centers)
+    model = build_uplift_upsample_transformer(cfg, precision=precision, weights=w)
+    f1, c1 = run_test_step(model, torch.from_numpy(video[src]).cuda(), torch.from_numpy(m).cuda())
+    f2, c2 = model.forward_video(torch.from_numpy(video).cuda(), torch.from_numpy(centers).cuda(), 5, 20)
+    torch.cuda.synchronize()
+    assert torch.equal(c1, c2) and torch.equal(f1, f2)
+    hc = np.empty((len(centers), 17, 3), dtype=np.float32)
+    model.forward_video_host(video, centers, 5, 20, hc)
+    assert np.array_equal(hc, c1.cpu().numpy())
+    model.close()

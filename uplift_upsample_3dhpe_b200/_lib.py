@@ -111,6 +111,12 @@ def _declare(lib) -> None:
     lib.uu_op_layernorm.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_void_p,
                                     c_int, c_void_p]
     lib.uu_op_attention.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]
+    lib.uu_forward_video.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                     c_void_p]
+    lib.uu_forward_video_host.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                          c_void_p]
+    lib.uu_op_window_gather.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                        c_void_p, c_void_p, c_void_p]
     lib.uu_op_spatial.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, P(c_int32), c_void_p]
     lib.uu_op_gemm_f32.argtypes = [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
                                    c_int64, c_void_p, c_int64, c_void_p]
@@ -124,7 +130,7 @@ def _declare(lib) -> None:
 EXPORTS = [
     "uu_last_error", "uu_version", "uu_create", "uu_destroy", "uu_set_precision", "uu_get_precision",
     "uu_weight_count", "uu_param_count", "uu_weight_info", "uu_set_weight", "uu_get_weight",
-    "uu_forward", "uu_forward_host", "uu_last_launch_count", "uu_set_profiling", "uu_get_profile", "uu_stride_mask",
+    "uu_forward", "uu_forward_host", "uu_forward_video", "uu_forward_video_host", "uu_op_window_gather", "uu_last_launch_count", "uu_set_profiling", "uu_get_profile", "uu_stride_mask",
     "uu_train_config", "uu_train_forward_backward", "uu_grad_buffer", "uu_get_grad", "uu_get_droppath_scale",
     "uu_adamw_step", "uu_get_ema_weight",
     "uu_op_build_gather", "uu_op_token_fill", "uu_op_layernorm", "uu_op_attention", "uu_op_spatial", "uu_op_gemm_f32",

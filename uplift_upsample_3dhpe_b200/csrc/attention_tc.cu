@@ -62,7 +62,10 @@ __global__ void __launch_bounds__(32 * ST) k_attention_tc(const bf16* __restrict
   bf16* Ks = Qs + SP * RS;
   bf16* Vs = Ks + SP * RS;
   float* Km = reinterpret_cast<float*>(Vs + SP * RS);   // additive key term: 0, -1e9 (masked key) or -inf (padding)
-  const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // heads are the fastest-varying block index: the 8 CTAs of a window run together, so the 96-byte head slices of
+  // one 2304-byte q|k|v row (1.5 DRAM bursts each) are fetched once while they sit in L2 (the ncu capture of the
+  // (window, head) order showed 1.7x the algorithmic DRAM traffic)
+  const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const int d = heads * DH;
   const long long row0 = (long long)b * S;
@@ -186,7 +189,7 @@ template <int DH>
 static cudaError_t att_tc_dh(const bf16* qkv, int B, int S, int heads, const uint8_t* mask, int mask_stride, bf16* out,
                              cudaStream_t st) {
   const int tiles = (S + 15) / 16;
-  dim3 grid(B, heads);
+  dim3 grid(heads, B);
 #define UU_ATT_CASE(T)                                                                               \
   case T: {                                                                                          \
     constexpr int smem = 3 * 16 * T * (DH + 8) * 2 + 16 * T * 4;                                     \

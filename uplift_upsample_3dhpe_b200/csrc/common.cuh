@@ -81,6 +81,7 @@ cudaError_t launch_build_gather(const uint8_t* mask, int B, int n_tok, int* scra
 struct SpatialParams {
   const float* x2d;          // (B*n_tok, J, 2)
   const int* list;           // gather list (frame ids) or null = all frames
+  const int* src = nullptr;  // optional: token id -> row of x2d (video frame; -1 = zeros), fused window gather
   const int* count;          // device count of valid frames (null with list == null)
   int max_frames;            // B*n_tok
   int J, depth;
@@ -137,7 +138,13 @@ cudaError_t launch_spatial_pack(const float* const* blocks, int depth, const flo
                                 const float* pe, const float* norm_g, const float* norm_b, void* frags, float* params,
                                 cudaStream_t s);
 cudaError_t launch_spatial_tc(const float* x2d, const int* list, const int* count, int max_frames, int depth,
-                              const void* frags, const float* params, bf16* out, int num_sms, cudaStream_t s);
+                              const void* frags, const float* params, bf16* out, int num_sms, cudaStream_t s,
+                              const int* src = nullptr);
+
+// ---- sliding windows of one video (kernels_f32.cu): source-frame table + globally aligned stride mask ----
+cudaError_t launch_window_index(const int* centers, int B, int n_tok, int s_out, int s_in, int T, int pad_copy, int* src,
+                                uint8_t* mask, cudaStream_t st);
+cudaError_t launch_window_copy(const float* video, const int* src, int n_tokens, int J, float* x, cudaStream_t st);
 
 // ---- tcgen05 GEMM (gemm_tc.cu) ----------------------------------------------------------------
 struct TcGemmPlan;   // holds the TMA tensor maps of one GEMM call site

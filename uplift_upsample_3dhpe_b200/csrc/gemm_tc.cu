@@ -602,6 +602,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
         const int row0 = (tile / n_tiles) * (2 * TC_BLOCK_M) + (int)rank * TC_BLOCK_M;
         const int col0 = (tile % n_tiles) * BLOCK_N + (int)rank * (BLOCK_N / 2);
+        {   // pull this CTA's rows of the cluster's next tile into L2 (see the single-CTA kernel)
+          const int nt = tile + n_clusters;
+          if (nt < total_tiles && (nt % n_tiles) == 0 && !(epi.flags & 256)) {
+            const int prow = (nt / n_tiles) * (2 * TC_BLOCK_M) + (int)rank * TC_BLOCK_M;
+            for (int kb = 0; kb < num_kb; ++kb) tma_prefetch_2d(&map_a, kb * TC_BLOCK_K, prow);
+          }
+        }
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % Cfg::STAGES;
           const uint32_t ph = (it / Cfg::STAGES) & 1;

@@ -178,12 +178,14 @@ __global__ void __launch_bounds__(SP_F * 32, 1) k_spatial_f32(SpatialParams p) {
 
   // S1: key-point embedding + spatial positional encoding (net:321-323)
   if (active) {
-    const int fr = p.list ? p.list[g] : g;
-    const float* x = p.x2d + (long long)fr * SP_J * 2;
+    const int tok = p.list ? p.list[g] : g;
+    const int fr = p.src ? p.src[tok] : tok;              // window token -> video frame (fused window gather)
+    const float* x = p.x2d + (long long)(fr < 0 ? 0 : fr) * SP_J * 2;
     const float w0 = p.embed_k[lane], w1 = p.embed_k[SP_D + lane], be = p.embed_b[lane];
 #pragma unroll
     for (int j = 0; j < SP_J; ++j) {
       float2 xy = *reinterpret_cast<const float2*>(x + 2 * j);
+      if (fr < 0) xy = make_float2(0.f, 0.f);             // zero padding outside the video
       // Dense = x @ W + b (sum over k in order), then + PE
       xs[j * SP_D + lane] = (fmaf(xy.y, w1, xy.x * w0) + be) + p.pe[j * SP_D + lane];
     }
@@ -319,6 +321,65 @@ cudaError_t launch_spatial_f32(const SpatialParams& p, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     k_spatial_f32<float><<<grid, SP_F * 32, smem, st>>>(p);
   }
+  return cudaGetLastError();
+}
+
+// =================================================================================================
+// K0: sliding-window index + globally aligned stride mask for windows cut from ONE video.
+// reference: common/dataset/uplifiting_dataset.py:341-394.  Window b is centred on video frame c = centers[b];
+// token k looks at frame f = (k - n_tok/2) * s_out + c.  Frames outside [0, T) are padded: "copy" (np.pad mode
+// "edge" on the strided sequence) repeats the first / last in-range strided sample, "zeros" yields zeros (src -1).
+// mask[b, k] = (f mod s_in == 0) with floor-mod on the UNclamped index.  Integer arithmetic only: bit-exact.
+// =================================================================================================
+__global__ void k_window_index(const int* __restrict__ centers, int B, int n_tok, int s_out, int s_in, int T,
+                               int pad_copy, int* __restrict__ src, uint8_t* __restrict__ mask) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * n_tok) return;
+  const int b = i / n_tok, k = i - b * n_tok;
+  const long long c = centers[b];
+  const long long f = (long long)(k - n_tok / 2) * s_out + c;
+  long long r = f % s_in;
+  if (r < 0) r += s_in;
+  mask[i] = r == 0;
+  long long sf = f;
+  if (f < 0 || f >= T) {
+    if (!pad_copy) {
+      sf = -1;
+    } else {
+      // first / last token whose frame is inside the video (the centre token always is)
+      const long long f0 = c - (long long)(n_tok / 2) * s_out;           // frame of token 0
+      const long long k_min = f0 >= 0 ? 0 : (-f0 + s_out - 1) / s_out;
+      const long long k_max = (T - 1 - f0) / s_out;                       // floor, T - 1 - f0 >= 0
+      const long long kc = f < 0 ? k_min : (k_max < n_tok - 1 ? k_max : n_tok - 1);
+      sf = f0 + kc * s_out;
+    }
+  }
+  src[i] = (int)sf;
+}
+
+cudaError_t launch_window_index(const int* centers, int B, int n_tok, int s_out, int s_in, int T, int pad_copy, int* src,
+                                uint8_t* mask, cudaStream_t st) {
+  if (B == 0) return cudaSuccess;
+  const int n = B * n_tok;
+  k_window_index<<<(n + 255) / 256, 256, 0, st>>>(centers, B, n_tok, s_out, s_in, T, pad_copy, src, mask);
+  return cudaGetLastError();
+}
+
+// materialised windows (tests / callers that want the reference's tensors): x[b,k] = video[src[b,k]] (or 0)
+__global__ void k_window_copy(const float2* __restrict__ video, const int* __restrict__ src, int n_tokens, int J,
+                              float2* __restrict__ x) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)n_tokens * J) return;
+  const int tok = (int)(i / J), j = (int)(i - (long long)tok * J);
+  const int f = src[tok];
+  x[i] = f < 0 ? make_float2(0.f, 0.f) : video[(long long)f * J + j];
+}
+
+cudaError_t launch_window_copy(const float* video, const int* src, int n_tokens, int J, float* x, cudaStream_t st) {
+  if (n_tokens == 0) return cudaSuccess;
+  const long long n = (long long)n_tokens * J;
+  k_window_copy<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float2*>(video), src, n_tokens, J,
+                                                             reinterpret_cast<float2*>(x));
   return cudaGetLastError();
 }
 

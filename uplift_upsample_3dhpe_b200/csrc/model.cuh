@@ -63,6 +63,12 @@ struct uu_model {
   int cap_B = 0;
   int ws_precision = -1;
   int *g_scratch = nullptr, *g_list = nullptr, *g_count = nullptr;
+  int* w_src = nullptr;          // sliding-window source-frame table [cap_B * n_tok] (uu_forward_video)
+  uint8_t* w_mask = nullptr;     // globally aligned stride mask built on the device [cap_B * n_tok]
+  const int* cur_src = nullptr;  // non-null while a video forward is being scheduled
+  float* d_video = nullptr;      // device staging for uu_forward_video_host
+  int* d_centers = nullptr;
+  int video_cap = 0, centers_cap = 0;
   void *S = nullptr, *Y = nullptr, *QKV = nullptr, *O = nullptr, *Hd = nullptr, *P = nullptr;
   float* X = nullptr;
   std::vector<float*> Xs;      // strided stream after block i: [cap_B * seq_lens[i+1], d]

@@ -349,6 +349,7 @@ struct SpatialTcParams {
   const float* x2d;      // (B*n_tok, 17, 2)
   const int* list;       // gather list or null
   const int* count;      // device count or null
+  const int* src;        // optional token id -> row of x2d (video frame, -1 = zeros): fused sliding-window gather
   int max_frames;
   int depth;
   const uint2* frags;    // weight image
@@ -405,12 +406,14 @@ __global__ void __launch_bounds__(st::THREADS, 1) k_spatial_tc(SpatialTcParams p
     {
       float2 p0 = make_float2(0.f, 0.f), p1 = make_float2(0.f, 0.f);
       if (f0 < FRAMES && fbase + f0 < n_valid) {
-        const int fr = p.list ? p.list[fbase + f0] : fbase + f0;
-        p0 = *reinterpret_cast<const float2*>(p.x2d + ((long long)fr * J + j0) * 2);
+        int fr = p.list ? p.list[fbase + f0] : fbase + f0;
+        if (p.src) fr = p.src[fr];
+        if (fr >= 0) p0 = *reinterpret_cast<const float2*>(p.x2d + ((long long)fr * J + j0) * 2);
       }
       if (f1 < FRAMES && fbase + f1 < n_valid) {
-        const int fr = p.list ? p.list[fbase + f1] : fbase + f1;
-        p1 = *reinterpret_cast<const float2*>(p.x2d + ((long long)fr * J + j1) * 2);
+        int fr = p.list ? p.list[fbase + f1] : fbase + f1;
+        if (p.src) fr = p.src[fr];
+        if (fr >= 0) p1 = *reinterpret_cast<const float2*>(p.x2d + ((long long)fr * J + j1) * 2);
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -644,7 +647,8 @@ size_t spatial_tc_smem_bytes(int depth) {
 }
 
 cudaError_t launch_spatial_tc(const float* x2d, const int* list, const int* count, int max_frames, int depth,
-                              const void* frags, const float* params, bf16* out, int num_sms, cudaStream_t s) {
+                              const void* frags, const float* params, bf16* out, int num_sms, cudaStream_t s,
+                              const int* src) {
   if (max_frames == 0) return cudaSuccess;
   if (depth > st::DEPTH_MAX) return cudaErrorInvalidValue;
   const size_t smem = spatial_tc_smem_bytes(depth);
@@ -655,7 +659,7 @@ cudaError_t launch_spatial_tc(const float* x2d, const int* list, const int* coun
     attr = true;
   }
   SpatialTcParams p;
-  p.x2d = x2d; p.list = list; p.count = count; p.max_frames = max_frames; p.depth = depth;
+  p.x2d = x2d; p.list = list; p.count = count; p.src = src; p.max_frames = max_frames; p.depth = depth;
   p.frags = (const uint2*)frags; p.params = params; p.out = out;
   const int groups = (max_frames + st::FRAMES - 1) / st::FRAMES;
   k_spatial_tc<<<std::min(groups, num_sms), st::THREADS, smem, s>>>(p);

@@ -205,6 +205,8 @@ static int ensure_workspace(uu_model* m, int B) {
   if (dev_alloc(m->ws_allocs, &p, sizeof(int) * (cap + 1), true)) return 1; m->g_scratch = (int*)p;
   if (dev_alloc(m->ws_allocs, &p, sizeof(int) * R, true)) return 1; m->g_list = (int*)p;
   if (dev_alloc(m->ws_allocs, &p, sizeof(int) * 4, true)) return 1; m->g_count = (int*)p;
+  if (dev_alloc(m->ws_allocs, &p, sizeof(int) * R, true)) return 1; m->w_src = (int*)p;
+  if (dev_alloc(m->ws_allocs, &p, R, true)) return 1; m->w_mask = (uint8_t*)p;
   if (dev_alloc(m->ws_allocs, &m->S, es * R * s.n_joints * s.d_spatial, true)) return 1;
   if (dev_alloc(m->ws_allocs, &p, 4 * R * dt, true)) return 1; m->X = (float*)p;
   if (dev_alloc(m->ws_allocs, &m->Y, es * R * dt, true)) return 1;
@@ -330,7 +332,7 @@ static int run_forward_bf16(Fwd& f, const float* x2d, const uint8_t* mask, float
   if (use_mask) UU_LAUNCH(f, UU_KIND_GATHER, 3, launch_build_gather(mask, B, N, m->g_scratch, m->g_list, m->g_count, st));
   UU_LAUNCH(f, UU_KIND_SPATIAL, 1,
             launch_spatial_tc(x2d, use_mask ? m->g_list : nullptr, use_mask ? m->g_count : nullptr, R, s.spatial_depth,
-                              m->sp_frags, m->sp_params, (bf16*)m->S, m->num_sms, st));
+                              m->sp_frags, m->sp_params, (bf16*)m->S, m->num_sms, st, m->cur_src));
   {  // S4 + T1: 544->384 GEMM scattered to token rows, + bias + temporal PE; then the upsampling-token fill
     Epilogue e;
     e.bias = W(m, "spatial_to_temporal_fc", 1);
@@ -438,7 +440,7 @@ static int run_forward_impl(uu_model* m, const float* x2d, const uint8_t* mask, 
   // K2: fused spatial transformer on the valid frames -> S (compact rows)
   SpatialParams sp;
   sp.x2d = x2d; sp.list = use_mask ? m->g_list : nullptr; sp.count = use_mask ? m->g_count : nullptr;
-  sp.max_frames = R; sp.J = J; sp.depth = s.spatial_depth;
+  sp.max_frames = R; sp.J = J; sp.depth = s.spatial_depth; sp.src = m->cur_src;
   sp.embed_k = W(m, "keypoint_embedding", 0); sp.embed_b = W(m, "keypoint_embedding", 1);
   sp.pe = W(m, "spatial_pe", 0); sp.blocks = m->spatial_ptrs;
   sp.norm_g = W(m, "spatial_norm", 0); sp.norm_b = W(m, "spatial_norm", 1);
@@ -628,6 +630,8 @@ int uu_destroy(uu_model* m) {
   cudaFree(m->d_mask);
   cudaFree(m->d_full);
   cudaFree(m->d_central);
+  cudaFree(m->d_video);
+  cudaFree(m->d_centers);
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
   for (auto e : m->ev_pool) cudaEventDestroy(e);
   delete m;
@@ -723,6 +727,79 @@ int uu_forward_host(uu_model* m, const float* x2d, const uint8_t* mask, int B, f
   if (full) UU_CUDA(cudaMemcpyAsync(full, m->d_full, sizeof(float) * R * s.n_joints * 3, cudaMemcpyDeviceToHost, st));
   UU_CUDA(cudaMemcpyAsync(central, m->d_central, sizeof(float) * (size_t)B * s.n_joints * 3, cudaMemcpyDeviceToHost, st));
   UU_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ---- sliding windows cut on the device from one video ----------------------------------------
+static int forward_video_dev(uu_model* m, const float* video, int T, const int32_t* centers, int B, int s_out, int s_in,
+                             int pad_copy, float* full, float* central, cudaStream_t st) {
+  const uu_spec& s = m->spec;
+  UU_CHECK(video && centers && central && B > 0 && T > 0, "bad argument");
+  UU_CHECK(s_out >= 1 && s_in >= s_out && s_in % s_out == 0, "MASK_STRIDE must be a multiple of SEQUENCE_STRIDE");   // :252-254
+  UU_CUDA(cudaSetDevice(m->device));
+  if (ensure_workspace(m, B)) return 1;
+  UU_CUDA(launch_window_index(centers, B, s.n_tok, s_out, s_in, T, pad_copy, m->w_src, m->w_mask, st));
+  m->cur_src = m->w_src;
+  const int rc = run_forward(m, video, s.has_strided_input ? m->w_mask : nullptr, B, full, central, st);
+  m->cur_src = nullptr;
+  m->launches += 1;
+  return rc;
+}
+
+int uu_forward_video(uu_model* m, const float* video2d, int T, const int32_t* centers, int B, int s_out, int s_in,
+                     int pad_copy, float* full, float* central, void* stream) {
+  UU_CHECK(m, "null model");
+  return forward_video_dev(m, video2d, T, centers, B, s_out, s_in, pad_copy, full, central, (cudaStream_t)stream);
+}
+
+int uu_forward_video_host(uu_model* m, const float* video2d, int T, const int32_t* centers, int B, int s_out, int s_in,
+                          int pad_copy, float* full, float* central) {
+  UU_CHECK(m && video2d && centers && central && B > 0 && T > 0, "bad argument");
+  const uu_spec& s = m->spec;
+  UU_CUDA(cudaSetDevice(m->device));
+  if (T > m->video_cap) {
+    UU_CUDA(cudaDeviceSynchronize());
+    cudaFree(m->d_video); m->d_video = nullptr;
+    UU_CUDA(cudaMalloc(&m->d_video, sizeof(float) * (size_t)T * s.n_joints * 2));
+    m->video_cap = T;
+  }
+  if (B > m->centers_cap) {
+    UU_CUDA(cudaDeviceSynchronize());
+    cudaFree(m->d_centers); m->d_centers = nullptr;
+    UU_CUDA(cudaMalloc(&m->d_centers, sizeof(int) * (size_t)B));
+    m->centers_cap = B;
+  }
+  if (B > m->stage_B) {     // output staging shared with uu_forward_host
+    UU_CUDA(cudaDeviceSynchronize());
+    cudaFree(m->d_x); cudaFree(m->d_mask); cudaFree(m->d_full); cudaFree(m->d_central);
+    m->d_x = m->d_full = m->d_central = nullptr; m->d_mask = nullptr;
+    const size_t R = (size_t)B * s.n_tok;
+    UU_CUDA(cudaMalloc(&m->d_x, sizeof(float) * R * s.n_joints * 2));
+    UU_CUDA(cudaMalloc(&m->d_mask, R));
+    UU_CUDA(cudaMalloc(&m->d_full, sizeof(float) * R * s.n_joints * 3));
+    UU_CUDA(cudaMalloc(&m->d_central, sizeof(float) * (size_t)B * s.n_joints * 3));
+    m->stage_B = B;
+  }
+  const size_t R = (size_t)B * s.n_tok;
+  cudaStream_t st = m->own_stream;
+  UU_CUDA(cudaMemcpyAsync(m->d_video, video2d, sizeof(float) * (size_t)T * s.n_joints * 2, cudaMemcpyHostToDevice, st));
+  UU_CUDA(cudaMemcpyAsync(m->d_centers, centers, sizeof(int) * (size_t)B, cudaMemcpyHostToDevice, st));
+  if (forward_video_dev(m, m->d_video, T, m->d_centers, B, s_out, s_in, pad_copy, m->d_full, m->d_central, st)) return 1;
+  if (full) UU_CUDA(cudaMemcpyAsync(full, m->d_full, sizeof(float) * R * s.n_joints * 3, cudaMemcpyDeviceToHost, st));
+  UU_CUDA(cudaMemcpyAsync(central, m->d_central, sizeof(float) * (size_t)B * s.n_joints * 3, cudaMemcpyDeviceToHost, st));
+  UU_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int uu_op_window_gather(const float* video2d, int T, const int32_t* centers, int B, int n_tok, int n_joints, int s_out,
+                        int s_in, int pad_copy, int32_t* src, uint8_t* mask, float* x2d, void* stream) {
+  UU_CHECK(centers && src && mask && B > 0 && T > 0 && n_tok > 0, "bad argument");
+  UU_CHECK(s_out >= 1 && s_in >= s_out && s_in % s_out == 0, "MASK_STRIDE must be a multiple of SEQUENCE_STRIDE");
+  UU_CUDA(launch_window_index(centers, B, n_tok, s_out, s_in, T, pad_copy, src, mask, (cudaStream_t)stream));
+  if (x2d) {
+    UU_CHECK(video2d, "video2d is required to materialise the windows");
+    UU_CUDA(launch_window_copy(video2d, src, B * n_tok, n_joints, x2d, (cudaStream_t)stream));
+  }
   return 0;
 }
 

@@ -181,6 +181,42 @@ class UpliftUpsampleTransformer:
                                              central_out.ctypes.data_as(c_void_p)))
 
 
+    # ---- sliding windows cut on the device from one video -------------------
+    def forward_video(self, video2d, centers, s_out: int, s_in: int, pad_copy: bool = True, want_full: bool = True):
+        """video2d (T,J,2) float32 cuda, centers (B,) int32 cuda frame indices.  Equivalent to building the
+        reference generator's windows + globally aligned stride masks (uplifiting_dataset.py:341-394) and calling
+        test_step on them, without materialising the (B, n_tok, J, 2) tensor."""
+        torch = _torch()
+        s = self.spec
+        video2d = video2d.contiguous().float()
+        centers = centers.to(dtype=torch.int32).contiguous()
+        if video2d.dim() != 3 or tuple(video2d.shape[1:]) != (s.n_joints, 2):
+            raise ValueError(f"video2d must be (T,{s.n_joints},2), got {tuple(video2d.shape)}")
+        T, B = video2d.shape[0], centers.shape[0]
+        full = None
+        if self.full_output and want_full:
+            full = torch.empty((B, s.n_tok, s.n_joints, 3), dtype=torch.float32, device=video2d.device)
+        central = torch.empty((B, s.n_joints, 3), dtype=torch.float32, device=video2d.device)
+        stream = torch.cuda.current_stream(video2d.device).cuda_stream
+        _lib.check(self._lib.uu_forward_video(self._h, video2d.data_ptr(), T, centers.data_ptr(), B, int(s_out), int(s_in),
+                                              1 if pad_copy else 0, full.data_ptr() if full is not None else None,
+                                              central.data_ptr(), stream))
+        return full, central
+
+    def forward_video_host(self, video2d: np.ndarray, centers: np.ndarray, s_out: int, s_in: int,
+                           central_out: np.ndarray, full_out: Optional[np.ndarray] = None, pad_copy: bool = True) -> None:
+        """Host-buffer twin (uu_forward_video_host): H2D of the video and the centre list only."""
+        s = self.spec
+        assert video2d.dtype == np.float32 and video2d.flags.c_contiguous and video2d.shape[1:] == (s.n_joints, 2)
+        assert centers.dtype == np.int32 and centers.flags.c_contiguous
+        B = centers.shape[0]
+        assert central_out.dtype == np.float32 and central_out.shape == (B, s.n_joints, 3)
+        fptr = full_out.ctypes.data_as(c_void_p) if full_out is not None else None
+        _lib.check(self._lib.uu_forward_video_host(self._h, video2d.ctypes.data_as(c_void_p), video2d.shape[0],
+                                                   centers.ctypes.data_as(c_void_p), B, int(s_out), int(s_in),
+                                                   1 if pad_copy else 0, fptr, central_out.ctypes.data_as(c_void_p)))
+
+
 def build_uplift_upsample_transformer(config, device: int = 0, precision: str = "fp32",
                                       weights: Optional[Dict[W.WeightKey, np.ndarray]] = None,
                                       seed: int = 1) -> UpliftUpsampleTransformer:

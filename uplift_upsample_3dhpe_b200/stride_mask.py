@@ -66,3 +66,19 @@ def batch_stride_masks_train(n_tok: int, s_out: int, mask_strides: Sequence[int]
             shift = int(shift_rng.integers(low=lo, high=hi, endpoint=endpoint))
         out[b] = stride_mask(n_tok, s_out, s_in, shift_tokens=shift)
     return out
+
+
+def window_source_frames(n_tok: int, s_out: int, T: int, center_frames: Sequence[int], pad_copy: bool = True) -> np.ndarray:
+    """Source video frame of every token of the sliding windows centred on ``center_frames`` -> int32 (B, n_tok);
+    -1 marks zero padding.  Mirrors uplifiting_dataset.py:341-375: frames outside [0, T) repeat the first / last
+    in-range *strided* sample (PADDING_TYPE "copy" = np.pad mode "edge") or are zeros ("zeros")."""
+    c = np.asarray(center_frames, dtype=np.int64)[:, None]
+    k = np.arange(n_tok, dtype=np.int64)[None, :]
+    f = (k - n_tok // 2) * s_out + c
+    if not pad_copy:
+        return np.where((f < 0) | (f >= T), -1, f).astype(np.int32)
+    f0 = c - (n_tok // 2) * s_out
+    k_min = np.where(f0 >= 0, 0, (-f0 + s_out - 1) // s_out)
+    k_max = np.minimum((T - 1 - f0) // s_out, n_tok - 1)
+    kc = np.clip(k, k_min, k_max)
+    return (f0 + kc * s_out).astype(np.int32)
