@@ -131,3 +131,20 @@ def test_large_batch_properties(precision):
     want_full, want_central = O.test_step(spec, w, x[:4], m[:4], dtype=np.float64)
     assert np.abs(central[:4].cpu().numpy() - want_central).max() <= TOL[precision]
     model.close()
+
+
+@pytest.mark.parametrize("s_in", [5, 20])
+def test_chunked_host_forward_is_identical_to_device_forward(s_in):
+    """uu_forward_host splits the input copy of large bf16 batches into chunks overlapped with the spatial
+    kernel; the result must be bit-identical to uu_forward on device-resident inputs (ragged last chunk, masks
+    with different valid counts per window so the chunk boundaries fall at arbitrary gather-list positions)."""
+    cfg, spec, w, x, m = _case("h36m_351", s_in, 2050, "shifted" if s_in > 5 else "centred", seed=9)
+    m[7] = False                                  # an all-masked window inside a chunk
+    model = build_uplift_upsample_transformer(cfg, precision="bf16", weights=w)
+    full, central = run_test_step(model, torch.from_numpy(x).cuda(), torch.from_numpy(m).cuda())
+    torch.cuda.synchronize()
+    hf = np.empty((2050, 71, 17, 3), np.float32)
+    hc = np.empty((2050, 17, 3), np.float32)
+    model.forward_host(x, m.astype(np.uint8), hf, hc)
+    assert np.array_equal(hc, central.cpu().numpy()) and np.array_equal(hf, full.cpu().numpy())
+    model.close()

@@ -139,7 +139,8 @@ cudaError_t launch_spatial_pack(const float* const* blocks, int depth, const flo
                                 cudaStream_t s);
 cudaError_t launch_spatial_tc(const float* x2d, const int* list, const int* count, int max_frames, int depth,
                               const void* frags, const float* params, bf16* out, int num_sms, cudaStream_t s,
-                              const int* src = nullptr);
+                              const int* src = nullptr, const int* range_lo = nullptr, const int* range_hi = nullptr,
+                              int lo = 0, int hi = -1);
 
 // ---- sliding windows of one video (kernels_f32.cu): source-frame table + globally aligned stride mask ----
 cudaError_t launch_window_index(const int* centers, int B, int n_tok, int s_out, int s_in, int T, int pad_copy, int* src,

@@ -79,6 +79,12 @@ struct uu_model {
   uint8_t* d_mask = nullptr;
   int stage_B = 0;
   cudaStream_t own_stream = nullptr;
+  // uu_forward_host: the input copy is split into chunks on a second stream; the spatial kernel of chunk c waits
+  // only for its own chunk, so the rest of the copy overlaps spatial compute
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t chunk_ev[8] = {};
+  int n_chunks = 0;              // > 1 while such a forward is being scheduled
+  int chunk_windows = 0;
 
   // tcgen05 plans for the current batch size
   int plan_B = -1;

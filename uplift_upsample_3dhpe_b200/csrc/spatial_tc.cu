@@ -191,6 +191,20 @@ __device__ __forceinline__ uint32_t pack2h(float lo, float hi) {
   __half2 v = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// D = A B with a zero accumulator: separate output registers and literal-zero C inputs let ptxas feed RZ instead of
+// materialising four zeros per MMA chain (about a hundred MOVs per layer in the head loop).
+__device__ __forceinline__ void mma1688_z(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%7,%7,%7,%7};"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(a0), "r"(a1), "r"(b0), "f"(0.f));
+}
+__device__ __forceinline__ void mma16816h_z(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.f));
+}
 // 8x8 b16 transpose inside the warp: in (row g; cols 2t,2t+1) -> out (row g; cols 2t,2t+1) of the transpose
 __device__ __forceinline__ uint32_t movm_t(uint32_t a) {
   uint32_t d;
@@ -324,24 +338,25 @@ __device__ __forceinline__ void ln_to_afrag(const float (&x)[4][4], const float*
 
 // The same without gamma / beta (folded into the following linear layer at pack time): xhat = (x - mean) * rstd.
 __device__ __forceinline__ void lnhat_to_afrag(const float (&x)[4][4], float eps, uint32_t (&a)[2][4]) {
-  float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) { s0 += x[j][0] + x[j][1]; s1 += x[j][2] + x[j][3]; }
-  const float m0 = quad_sum(s0) * (1.f / 32), m1 = quad_sum(s1) * (1.f / 32);
-  float d[4][4];
-  float q0 = 0.f, q1 = 0.f;
+  // single pass: sum and sum of squares together (32 values of O(1) in fp32: the cancellation in E[x^2] - mean^2 costs
+  // ~1e-7 * mean^2 / var relative, far below the bf16 rounding of the result), then xhat = x * rstd - mean * rstd
+  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    d[j][0] = x[j][0] - m0; q0 = fmaf(d[j][0], d[j][0], q0); d[j][1] = x[j][1] - m0; q0 = fmaf(d[j][1], d[j][1], q0);
-    d[j][2] = x[j][2] - m1; q1 = fmaf(d[j][2], d[j][2], q1); d[j][3] = x[j][3] - m1; q1 = fmaf(d[j][3], d[j][3], q1);
+    s0 += x[j][0] + x[j][1]; s1 += x[j][2] + x[j][3];
+    q0 = fmaf(x[j][0], x[j][0], fmaf(x[j][1], x[j][1], q0));
+    q1 = fmaf(x[j][2], x[j][2], fmaf(x[j][3], x[j][3], q1));
   }
-  const float r0 = rsqrtf(quad_sum(q0) * (1.f / 32) + eps), r1 = rsqrtf(quad_sum(q1) * (1.f / 32) + eps);
+  const float m0 = quad_sum(s0) * (1.f / 32), m1 = quad_sum(s1) * (1.f / 32);
+  const float v0 = fmaxf(fmaf(quad_sum(q0), 1.f / 32, -m0 * m0), 0.f), v1 = fmaxf(fmaf(quad_sum(q1), 1.f / 32, -m1 * m1), 0.f);
+  const float r0 = rsqrtf(v0 + eps), r1 = rsqrtf(v1 + eps);
+  const float n0 = -m0 * r0, n1 = -m1 * r1;
 #pragma unroll
   for (int kk = 0; kk < 2; ++kk) {
-    a[kk][0] = pack2(d[2 * kk][0] * r0, d[2 * kk][1] * r0);
-    a[kk][1] = pack2(d[2 * kk][2] * r1, d[2 * kk][3] * r1);
-    a[kk][2] = pack2(d[2 * kk + 1][0] * r0, d[2 * kk + 1][1] * r0);
-    a[kk][3] = pack2(d[2 * kk + 1][2] * r1, d[2 * kk + 1][3] * r1);
+    a[kk][0] = pack2(fmaf(x[2 * kk][0], r0, n0), fmaf(x[2 * kk][1], r0, n0));
+    a[kk][1] = pack2(fmaf(x[2 * kk][2], r1, n1), fmaf(x[2 * kk][3], r1, n1));
+    a[kk][2] = pack2(fmaf(x[2 * kk + 1][0], r0, n0), fmaf(x[2 * kk + 1][1], r0, n0));
+    a[kk][3] = pack2(fmaf(x[2 * kk + 1][2], r1, n1), fmaf(x[2 * kk + 1][3], r1, n1));
   }
 }
 
@@ -350,6 +365,9 @@ struct SpatialTcParams {
   const int* list;       // gather list or null
   const int* count;      // device count or null
   const int* src;        // optional token id -> row of x2d (video frame, -1 = zeros): fused sliding-window gather
+  const int* range_lo;   // optional device pointers: process list positions [*range_lo, *range_hi) only
+  const int* range_hi;   //   (chunked launches that overlap the host-to-device copy of the next chunk)
+  int lo, hi;            // the same as host values when the pointers are null (hi < 0: up to the valid count)
   int max_frames;
   int depth;
   const uint2* frags;    // weight image
@@ -390,8 +408,12 @@ __global__ void __launch_bounds__(st::THREADS, 1) k_spatial_tc(SpatialTcParams p
   uint32_t phase = 0;                               // one hand-off pair per (group, layer)
   const float* gp = s_par + p.depth * P_TOTAL;      // global params
 
-  const int n_valid = p.count ? *p.count : p.max_frames;
-  const int n_groups = (n_valid + FRAMES - 1) / FRAMES;
+  const int lo = p.range_lo ? *p.range_lo : p.lo;
+  int n_valid;                                      // end of this launch's range of list positions
+  if (p.range_hi) n_valid = *p.range_hi;
+  else if (p.hi >= 0) n_valid = p.count ? min(p.hi, *p.count) : p.hi;
+  else n_valid = p.count ? *p.count : p.max_frames;
+  const int n_groups = (n_valid - lo + FRAMES - 1) / FRAMES;
   // rows this thread holds pieces of: (frame, joint) of accumulator rows g and g+8
   // (the joint-16 tile has 15 live rows; row 15 computes on zeros and is never stored)
   const int f0 = w16 ? g : warp, f1 = w16 ? g + 8 : warp;
@@ -400,7 +422,7 @@ __global__ void __launch_bounds__(st::THREADS, 1) k_spatial_tc(SpatialTcParams p
   bf16* stg = s_stage + warp * 16 * STG;
 
   for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
-    const int fbase = grp * FRAMES;
+    const int fbase = lo + grp * FRAMES;
     // ---- S1: key-point embedding + spatial PE (net:321-323), straight into the accumulator layout
     float x[4][4];
     {
@@ -510,9 +532,9 @@ __global__ void __launch_bounds__(st::THREADS, 1) k_spatial_tc(SpatialTcParams p
           const int j = h >> 1, e = h & 1;
           const uint32_t hm = e ? hmask1 : hmask0;
           const uint32_t a0 = qa[j][0] & hm, a1 = qa[j][1] & hm;
-          float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
-          mma1688(s0, a0, a1, kb[j][0]);        // keys 0..7
-          mma1688(s1, a0, a1, kb[j][1]);        // keys 8..15
+          float s0[4], s1[4];
+          mma1688_z(s0, a0, a1, kb[j][0]);      // keys 0..7
+          mma1688_z(s1, a0, a1, kb[j][1]);      // keys 8..15
           const bool owner = t == (h >> 1);     // this lane holds the key-16 score of head h
           float mg = fmaxf(fmaxf(s0[0], s0[1]), fmaxf(s1[0], s1[1]));
           float mh = fmaxf(fmaxf(s0[2], s0[3]), fmaxf(s1[2], s1[3]));
@@ -526,8 +548,8 @@ __global__ void __launch_bounds__(st::THREADS, 1) k_spatial_tc(SpatialTcParams p
           pa[3] = pack2h(ex2_approx(s1[2] - mh), ex2_approx(s1[3] - mh));
           const float pg = owner ? ex2_approx(s16[e] - mg) : 0.f;
           const float ph = owner ? ex2_approx(s16[2 + e] - mh) : 0.f;
-          float o[4] = {0.f, 0.f, 0.f, 0.f};
-          mma16816h(o, pa, vt[h][0], vt[h][1]);  // o[0] = sum_k p v[ch t], o[1] = sum_k p   (row g); o[2], o[3]: row g+8
+          float o[4];
+          mma16816h_z(o, pa, vt[h][0], vt[h][1]);  // o[0] = sum_k p v[ch t], o[1] = sum_k p   (row g); o[2], o[3]: row g+8
           mma1688h(o, e ? pack2h(0.f, pg) : pack2h(pg, 0.f), e ? pack2h(0.f, ph) : pack2h(ph, 0.f), bv16);   // key 16
           const float og = o[0] * rcp_approx(o[1]), oh = o[2] * rcp_approx(o[3]);
           // heads 4kk..4kk+3 fill slots (2t,2t+1 | 2t+8,2t+9) of k-step kk: pairs (h, h+1) pack into one register
@@ -648,7 +670,7 @@ size_t spatial_tc_smem_bytes(int depth) {
 
 cudaError_t launch_spatial_tc(const float* x2d, const int* list, const int* count, int max_frames, int depth,
                               const void* frags, const float* params, bf16* out, int num_sms, cudaStream_t s,
-                              const int* src) {
+                              const int* src, const int* range_lo, const int* range_hi, int lo, int hi) {
   if (max_frames == 0) return cudaSuccess;
   if (depth > st::DEPTH_MAX) return cudaErrorInvalidValue;
   const size_t smem = spatial_tc_smem_bytes(depth);
@@ -660,6 +682,7 @@ cudaError_t launch_spatial_tc(const float* x2d, const int* list, const int* coun
   }
   SpatialTcParams p;
   p.x2d = x2d; p.list = list; p.count = count; p.src = src; p.max_frames = max_frames; p.depth = depth;
+  p.range_lo = range_lo; p.range_hi = range_hi; p.lo = lo; p.hi = hi;
   p.frags = (const uint2*)frags; p.params = params; p.out = out;
   const int groups = (max_frames + st::FRAMES - 1) / st::FRAMES;
   k_spatial_tc<<<std::min(groups, num_sms), st::THREADS, smem, s>>>(p);

@@ -330,9 +330,23 @@ static int run_forward_bf16(Fwd& f, const float* x2d, const uint8_t* mask, float
   const RowMap plain;
 
   if (use_mask) UU_LAUNCH(f, UU_KIND_GATHER, 3, launch_build_gather(mask, B, N, m->g_scratch, m->g_list, m->g_count, st));
-  UU_LAUNCH(f, UU_KIND_SPATIAL, 1,
-            launch_spatial_tc(x2d, use_mask ? m->g_list : nullptr, use_mask ? m->g_count : nullptr, R, s.spatial_depth,
-                              m->sp_frags, m->sp_params, (bf16*)m->S, m->num_sms, st, m->cur_src));
+  if (m->n_chunks > 1) {
+    // chunked input (uu_forward_host): window chunk c = list positions [scratch[c*Bc], scratch[(c+1)*Bc]) (device-side
+    // prefix counts) or, without a mask, frames [c*Bc*N, (c+1)*Bc*N); each launch waits for its chunk's copy only
+    for (int c = 0; c < m->n_chunks; ++c) {
+      const int w0 = c * m->chunk_windows, w1 = std::min(B, (c + 1) * m->chunk_windows);
+      UU_CUDA(cudaStreamWaitEvent(st, m->chunk_ev[c], 0));
+      UU_LAUNCH(f, UU_KIND_SPATIAL, 1,
+                launch_spatial_tc(x2d, use_mask ? m->g_list : nullptr, use_mask ? m->g_count : nullptr, (w1 - w0) * N,
+                                  s.spatial_depth, m->sp_frags, m->sp_params, (bf16*)m->S, m->num_sms, st, m->cur_src,
+                                  use_mask ? m->g_scratch + w0 : nullptr, use_mask ? m->g_scratch + w1 : nullptr,
+                                  w0 * N, w1 * N));
+    }
+  } else {
+    UU_LAUNCH(f, UU_KIND_SPATIAL, 1,
+              launch_spatial_tc(x2d, use_mask ? m->g_list : nullptr, use_mask ? m->g_count : nullptr, R, s.spatial_depth,
+                                m->sp_frags, m->sp_params, (bf16*)m->S, m->num_sms, st, m->cur_src));
+  }
   {  // S4 + T1: 544->384 GEMM scattered to token rows, + bias + temporal PE; then the upsampling-token fill
     Epilogue e;
     e.bias = W(m, "spatial_to_temporal_fc", 1);
@@ -633,6 +647,10 @@ int uu_destroy(uu_model* m) {
   cudaFree(m->d_video);
   cudaFree(m->d_centers);
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
+  if (m->copy_stream) {
+    cudaStreamDestroy(m->copy_stream);
+    for (int c = 0; c < 8; ++c) cudaEventDestroy(m->chunk_ev[c]);
+  }
   for (auto e : m->ev_pool) cudaEventDestroy(e);
   delete m;
   return 0;
@@ -720,10 +738,29 @@ int uu_forward_host(uu_model* m, const float* x2d, const uint8_t* mask, int B, f
   }
   const size_t R = (size_t)B * s.n_tok;
   cudaStream_t st = m->own_stream;
-  UU_CUDA(cudaMemcpyAsync(m->d_x, x2d, sizeof(float) * R * s.n_joints * 2, cudaMemcpyHostToDevice, st));
   if (mask) UU_CUDA(cudaMemcpyAsync(m->d_mask, mask, R, cudaMemcpyHostToDevice, st));
+  const int n_chunks = (m->precision == UU_PRECISION_BF16 && B >= 2048) ? 4 : 1;
+  if (n_chunks > 1) {
+    if (!m->copy_stream) {
+      UU_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+      for (int c = 0; c < 8; ++c) UU_CUDA(cudaEventCreateWithFlags(&m->chunk_ev[c], cudaEventDisableTiming));
+    }
+    const int Bc = (B + n_chunks - 1) / n_chunks;
+    const size_t per_window = (size_t)s.n_tok * s.n_joints * 2;
+    for (int c = 0; c < n_chunks; ++c) {
+      const size_t w0 = (size_t)c * Bc, w1 = std::min<size_t>(B, w0 + Bc);
+      UU_CUDA(cudaMemcpyAsync(m->d_x + w0 * per_window, x2d + w0 * per_window, sizeof(float) * (w1 - w0) * per_window,
+                              cudaMemcpyHostToDevice, m->copy_stream));
+      UU_CUDA(cudaEventRecord(m->chunk_ev[c], m->copy_stream));
+    }
+    m->n_chunks = n_chunks; m->chunk_windows = Bc;
+  } else {
+    UU_CUDA(cudaMemcpyAsync(m->d_x, x2d, sizeof(float) * R * s.n_joints * 2, cudaMemcpyHostToDevice, st));
+  }
   // full == NULL: the full-sequence head still runs (the reference always computes it) but stays on the device
-  if (run_forward(m, m->d_x, mask ? m->d_mask : nullptr, B, m->d_full, m->d_central, st)) return 1;
+  const int frc = run_forward(m, m->d_x, mask ? m->d_mask : nullptr, B, m->d_full, m->d_central, st);
+  m->n_chunks = 0;
+  if (frc) return 1;
   if (full) UU_CUDA(cudaMemcpyAsync(full, m->d_full, sizeof(float) * R * s.n_joints * 3, cudaMemcpyDeviceToHost, st));
   UU_CUDA(cudaMemcpyAsync(central, m->d_central, sizeof(float) * (size_t)B * s.n_joints * 3, cudaMemcpyDeviceToHost, st));
   UU_CUDA(cudaStreamSynchronize(st));
