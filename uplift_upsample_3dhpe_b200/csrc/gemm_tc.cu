@@ -128,11 +128,24 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 // Epilogue of one warp for one tile (bf16 output): sub-tiles first, first+2, ... of its 32 accumulator rows go
 // TMEM -> registers -> bias / ReLU / bf16 -> private swizzled staging tile -> cp.async.bulk.tensor store of a
 // [32 x 64] box.  `release` is called right after the warp's last TMEM read of the tile.
+// Row scatter (epi.c_rowidx: the compact valid-frame rows of the 544 -> 384 GEMM go to their token rows): the list is
+// ascending, so the 32 rows of a warp almost always land on 32 consecutive destination rows and still leave as one
+// TMA box; otherwise (a masked frame inside the run, or the ragged end of the list) every lane writes its own row.
 template <int BLOCK_N, int NBUF, typename Release>
 __device__ __forceinline__ void epi_warp_store_tile(uint32_t tmem_acc, int first, uint8_t* my_stage, uint32_t& my_count,
                                                     const Epilogue& epi, const CUtensorMap* map_c, int row_q0, int col0,
-                                                    int lane, Release release) {
+                                                    int lane, Release release, int m_eff = 0x7fffffff,
+                                                    bf16* c_ptr = nullptr, long long ldc = 0) {
   constexpr int NSUB = BLOCK_N / 64;
+  int dst_row = row_q0;                      // first destination row of the TMA box
+  bool boxed = true;
+  int my_dst = -1;
+  if (epi.c_rowidx) {
+    const int r = row_q0 + lane;
+    my_dst = r < m_eff ? epi.c_rowidx[r] : -1;
+    dst_row = __shfl_sync(0xffffffffu, my_dst, 0);
+    boxed = __all_sync(0xffffffffu, my_dst >= 0 && my_dst == dst_row + lane);
+  }
 #pragma unroll 1
   for (int sub = first; sub < NSUB; sub += 2, ++my_count) {
     uint8_t* sbuf = my_stage + (my_count % NBUF) * (32 * 128);
@@ -171,10 +184,17 @@ __device__ __forceinline__ void epi_warp_store_tile(uint32_t tmem_acc, int first
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async proxy
     __syncwarp();
-    if (lane == 0 && !(epi.flags & 64)) {   // (flag 64: timing experiment, UU_GEMM_NOSTORE)
-      asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map_c),
-                   "r"(smem_u32(sbuf)), "r"(col0 + sub * 64), "r"(row_q0)
-                   : "memory");
+    if (boxed) {
+      if (lane == 0 && !(epi.flags & 64)) {   // (flag 64: timing experiment, UU_GEMM_NOSTORE)
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map_c),
+                     "r"(smem_u32(sbuf)), "r"(col0 + sub * 64), "r"(dst_row)
+                     : "memory");
+      }
+    } else if (my_dst >= 0) {                // scattered rows: 128 bytes per lane straight from the staging tile
+      bf16* dst = c_ptr + (long long)my_dst * ldc + col0 + sub * 64;
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        *reinterpret_cast<uint4*>(dst + 8 * g) = *reinterpret_cast<const uint4*>(sbuf + lane * 128 + ((g ^ (lane & 7)) << 4));
     }
     if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   }
@@ -382,7 +402,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
         epi_warp_store_tile<BLOCK_N, Cfg::EPI_NBUF>(tmem_acc, first, my_stage, my_count, epi, &map_c, row0 + q * 32, col0, lane, [&] {
           tcgen05_fence_before();
           if (lane == 0) mbar_arrive(tmem_empty_bar + as);
-        });
+        }, m_eff, reinterpret_cast<bf16*>(C), ldc);
       }
       if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     } else {
@@ -847,9 +867,8 @@ static int g_use_2cta = -1;     // UU_GEMM_2CTA=0/1 forces the single-CTA / 2-CT
 
 // bf16 output, plain row mapping, no residual / table / scatter, full 64-column sub-tiles: TMA-store epilogue
 static bool tma_out_eligible(const TcGemmPlan* p, const Epilogue& epi, int c_bf16, long long ldc) {
-  return c_bf16 && !epi.c_rowidx && !epi.m_dev && epi.cmap.rpb == 0x7fffffff &&
-         !(epi.flags & (EPI_RESIDUAL | EPI_ROWTABLE)) && p->N == p->N_pad && (p->N % 64) == 0 && (ldc % 8) == 0 &&
-         p->block_n >= 64;
+  return c_bf16 && epi.cmap.rpb == 0x7fffffff && !(epi.flags & (EPI_RESIDUAL | EPI_ROWTABLE)) && p->N == p->N_pad &&
+         (p->N % 64) == 0 && (ldc % 8) == 0 && p->block_n >= 64;
 }
 
 cudaError_t tc_gemm_launch(TcGemmPlan* p, const Epilogue& epi_in, void* C, int c_bf16, long long ldc, cudaStream_t st) {
@@ -875,9 +894,10 @@ cudaError_t tc_gemm_launch(TcGemmPlan* p, const Epilogue& epi_in, void* C, int c
     static int use_bs = -1;
     if (use_bs < 0) { const char* e = getenv("UU_GEMM_BSTAT"); use_bs = (e && e[0] == '1') ? 1 : 0; }   // default off: measured no faster
     // short-K GEMMs with M >> N: keep the weight tile resident (K = 384 -> 6 panels of a 128-wide column block)
-    if (use_bs && p->K == 384 && p->N_pad % 128 == 0 && p->M >= 4 * TC_BLOCK_M * (p->N_pad / 128))
+    const bool scatter = epi.c_rowidx || epi.m_dev;
+    if (!scatter && use_bs && p->K == 384 && p->N_pad % 128 == 0 && p->M >= 4 * TC_BLOCK_M * (p->N_pad / 128))
       return tc_launch_bs<128, 6>(p, epi, C, ldc, st);
-    if ((g_use_2cta == 1 || (g_use_2cta == 2 && p->K >= 768)) && p->M >= 512 && (p->block_n == 256 || p->block_n == 192 || p->block_n == 128)) {
+    if (!scatter && (g_use_2cta == 1 || (g_use_2cta == 2 && p->K >= 768)) && p->M >= 512 && (p->block_n == 256 || p->block_n == 192 || p->block_n == 128)) {
       switch (p->block_n) {
         case 256: return tc2_launch_t<256>(p, epi, st);
         case 192: return tc2_launch_t<192>(p, epi, st);

@@ -619,7 +619,8 @@ __global__ void k_token_fill_bx(const uint8_t* __restrict__ mask, int rows, int 
     if (mask[row]) continue;
     const int n = row % n_tok;
     for (int c = lane; c < d4; c += 32) {
-      const float4 t = token[c], q = pe[(long long)n * d4 + c];
+      const float4 t = token[c];
+      const float4 q = pe ? pe[(long long)n * d4 + c] : make_float4(0.f, 0.f, 0.f, 0.f);   // pe == null: added downstream
       st_bf16x4(x + ((long long)row * d4 + c) * 4, t.x + q.x, t.y + q.y, t.z + q.z, t.w + q.w);
     }
   }

@@ -347,19 +347,19 @@ static int run_forward_bf16(Fwd& f, const float* x2d, const uint8_t* mask, float
               launch_spatial_tc(x2d, use_mask ? m->g_list : nullptr, use_mask ? m->g_count : nullptr, R, s.spatial_depth,
                                 m->sp_frags, m->sp_params, (bf16*)m->S, m->num_sms, st, m->cur_src));
   }
-  {  // S4 + T1: 544->384 GEMM scattered to token rows, + bias + temporal PE; then the upsampling-token fill
+  {  // S4 + T1: 544->384 GEMM (+ bias) scattered to the token rows through the TMA-store epilogue, upsampling token on
+     // the rows without 2-D input; the temporal PE (net:352, added to every row) rides on the first LayerNorm pass
     Epilogue e;
     e.bias = W(m, "spatial_to_temporal_fc", 1);
-    e.flags = EPI_ROWTABLE; e.table = W(m, "temporal_pe", 0); e.table_period = N;
     if (use_mask) { e.c_rowidx = m->g_list; e.m_dev = m->g_count; }
     if (gemm(f, m->S, J * ds, R, J * ds, nullptr, m->p_s2t, d, e, X, 1, d)) return 1;
     if (use_mask)
       UU_LAUNCH(f, UU_KIND_TOKEN_FILL, 1,
-                launch_token_fill_bx(mask, R, N, d, W(m, "strided_input_token_layer", 0), W(m, "temporal_pe", 0), X, st));
+                launch_token_fill_bx(mask, R, N, d, W(m, "strided_input_token_layer", 0), nullptr, X, st));
   }
   UU_LAUNCH(f, UU_KIND_LAYERNORM, 1,
-            launch_residual_ln_bx(X, plain, nullptr, nullptr, R, d, m->tblocks[0].ln1_g, m->tblocks[0].ln1_b, 1e-5f, nullptr,
-                                  1, Y, nullptr, st));
+            launch_residual_ln_bx(X, plain, nullptr, X, R, d, m->tblocks[0].ln1_g, m->tblocks[0].ln1_b, 1e-5f,
+                                  W(m, "temporal_pe", 0), N, Y, nullptr, st));
   for (int i = 0; i < s.temporal_depth; ++i) {
     const BlockW& w = m->tblocks[i];
     const uint8_t* km = (use_mask && i < s.first_strided_token_attention_layer) ? mask : nullptr;
