@@ -100,6 +100,20 @@ int uu_forward_video(uu_model* m, const float* video2d, int T, const int32_t* ce
                      int pad_copy, float* full, float* central, void* stream);
 int uu_forward_video_host(uu_model* m, const float* video2d, int T, const int32_t* centers, int B, int s_out, int s_in,
                           int pad_copy, float* full, float* central);
+/* Test-time flip augmentation (eval.py:154-180): both outputs become
+ * (f(x) + unflip(f(flip(x)))) / 2, flip = negate x and gather joints by `order` (config AUGM_FLIP_KEYPOINT_ORDER,
+ * n == n_joints entries).  The flip is applied where the spatial kernel reads the key-points; nothing is copied. */
+int uu_set_flip_order(uu_model* m, const int32_t* order, int n);
+int uu_forward_tta(uu_model* m, const float* x2d, const uint8_t* mask, int B, float* full, float* central, void* stream);
+int uu_forward_video_tta(uu_model* m, const float* video2d, int T, const int32_t* centers, int B, int s_out, int s_in,
+                         int pad_copy, float* full, float* central, void* stream);
+/* Key-frame interpolation (common/dataset/action_wise_eval.py:76-100): pred/out are
+ * (n, values_per_frame) device arrays in evaluation order, frame_indices the video frame of each row (videos
+ * concatenated; a video ends where the index does not increase).  Rows whose index is a multiple of keyframe_stride
+ * are copied, rows between two key frames of a video are linear in list position, rows after the last key frame of
+ * a video copy it. */
+int uu_op_keyframe_interp(const float* pred, const int32_t* frame_indices, int n, int keyframe_stride, int values_per_frame,
+                          float* out, void* stream);
 /* The gather alone: src (B*n_tok int32 source frame, -1 = zeros), mask (B*n_tok), and, when x2d != NULL, the
  * materialised (B, n_tok, n_joints, 2) windows exactly as the reference generator yields them (unmasked). */
 int uu_op_window_gather(const float* video2d, int T, const int32_t* centers, int B, int n_tok, int n_joints, int s_out,

@@ -108,6 +108,52 @@ def forward_case(tag, cfg_name, mask_stride, B, mode, seed, subsample=1):
           f"f32-vs-f64 per window {np.array2string(d, precision=2)}")
 
 
+def tta_case(tag, cfg_name, mask_stride, B, seed):
+    """Flip test-time augmentation, eval.py:152-180 (restated line by line on the reference model object)."""
+    ref_cfg = RefConfig(config_file=os.path.join(REF, "config", cfg_name + ".json"))
+    ref_cfg.MASK_STRIDE = mask_stride
+    ref_cfg.BATCH_SIZE = B
+    ours = UpliftUpsampleConfig.preset(cfg_name, MASK_STRIDE=mask_stride)
+    assert list(ref_cfg.AUGM_FLIP_KEYPOINT_ORDER) == list(ours.AUGM_FLIP_KEYPOINT_ORDER)
+    spec = spec_from_config(ours)
+    w = weights.init_weights(spec, seed=seed, perturb=True)
+    h5 = os.path.join(TMP, f"{tag}.h5")
+    h5lite.save_keras_weights(h5, spec, w)
+    rng = np.random.default_rng(seed + 100)
+    x = rng.uniform(-1, 1, (B, ref_cfg.SEQUENCE_LENGTH, 17, 2)).astype(np.float32)
+    gen = mask_generator(ref_cfg.SEQUENCE_LENGTH, ref_cfg.SEQUENCE_STRIDE, mask_stride, "eval", B, 5)
+    masks = np.stack([m for _, m in gen])
+    tf.set_float_dtype("float64")
+    model = ref_build(ref_cfg)
+    ref_weight_io.load_weights_with_callback(model, h5, verbose=False)
+    order = ref_cfg.AUGM_FLIP_KEYPOINT_ORDER
+    x64 = x.astype(tf.float32)
+    seq, cen = ref_test_step(model, x64, masks)                                                    # :152-153
+    fx = np.concatenate([x64[:, :, :, :1] * -1., x64[:, :, :, 1:]], axis=-1)                       # :155-158
+    fx = np.take(fx, order, axis=2)                                                                # :159
+    fseq, fcen = ref_test_step(model, fx, masks)                                                   # :161-162
+    fcen = np.take(np.concatenate([fcen[:, :, :1] * -1., fcen[:, :, 1:]], axis=-1), order, axis=1)  # :164-167
+    cen = (cen + fcen) / 2.                                                                        # :169-170
+    fseq = np.take(np.concatenate([fseq[:, :, :, :1] * -1., fseq[:, :, :, 1:]], axis=-1), order, axis=2)  # :172-178
+    seq = (seq + fseq) / 2.                                                                        # :180-181
+    np.savez_compressed(os.path.join(args.out, f"tta_{tag}.npz"), config=cfg_name, mask_stride=mask_stride, seed=seed,
+                        x=x, mask=masks, full=seq, central=cen, weights_sha=sha(weights.to_flat(spec, w)))
+    print(f"tta_{tag}: central {cen.shape} |max| {np.abs(cen).max():.3f}")
+
+
+def interp_case(tag, stride, lens, seed):
+    """Key-frame interpolation by the reference's own numpy function (common/dataset/action_wise_eval.py:76-100)."""
+    from common.dataset.action_wise_eval import interpolate_between_keyframes
+    rng = np.random.default_rng(seed)
+    frame_indices = np.concatenate([np.arange(n) for n in lens])          # videos concatenated, index restarts at 0
+    pred = rng.normal(size=(frame_indices.size, 17, 3)).astype(np.float32)
+    out, keyframes = interpolate_between_keyframes(pred3d=pred.astype(np.float64), frame_indices=frame_indices,
+                                                   keyframe_stride=np.tile([stride], reps=frame_indices.size))
+    np.savez_compressed(os.path.join(args.out, f"interp_{tag}.npz"), stride=stride, frame_indices=frame_indices.astype(np.int32),
+                        pred=pred, out=out, keyframes=keyframes)
+    print(f"interp_{tag}: {frame_indices.size} frames, {int(keyframes.sum())} key frames")
+
+
 def run_generator(n_tok, stride, mask_stride, mode, n_windows, video_len=400, seed=0, subsample=1):
     """Drive the reference's H36mSequenceGenerator on one synthetic video."""
     rng = np.random.default_rng(7)
@@ -151,6 +197,9 @@ if __name__ == "__main__":
     forward_case("h36m_351_sin5_unaligned", "h36m_351", 5, 3, "eval", seed=2, subsample=3)  # 71, 0, 0
     forward_case("h36m_351_sin20", "h36m_351", 20, 5, "eval", seed=3, subsample=5)        # 17/18 valid, every alignment
     forward_case("amass_351_train_masks", "amass_351", [5, 10, 20], 6, "train", seed=4)
+    tta_case("h36m_351_sin10", "h36m_351", 10, 3, seed=6)
+    interp_case("stride5", 5, [23, 41, 5, 1], seed=8)
+    interp_case("stride2", 2, [9, 12], seed=9)
     # window + stride-mask generator (bit-exact contract)
     stride_mask_case("eval_351_sin20", 71, 5, 20, "eval", 120, 150)
     stride_mask_case("eval_81_sin10", 41, 2, 10, "eval", 60, 90)

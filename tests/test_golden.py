@@ -86,3 +86,18 @@ def test_window_source_frames_match_reference_generator(path):
     # padded positions are exactly those the generator's pad mask marks with 0
     f = (np.arange(n_tok)[None, :] - n_tok // 2) * stride + z["centers"][:, None]
     assert np.array_equal(((f >= 0) & (f < video.shape[0])).astype(np.float32), z["pad_masks"])
+
+
+def test_oracle_tta_and_interpolation_match_reference():
+    from oracle import eval_np
+    tta = sorted(glob.glob(os.path.join(GOLDEN, "tta_*.npz")))
+    interp = sorted(glob.glob(os.path.join(GOLDEN, "interp_*.npz")))
+    assert tta and interp
+    for path in tta:
+        cfg, spec, w, z = load_forward_case(path)
+        full, central = eval_np.flip_tta(spec, w, z["x"], z["mask"], cfg.AUGM_FLIP_KEYPOINT_ORDER)
+        assert np.abs(central - z["central"]).max() < 1e-9 and np.abs(full - z["full"]).max() < 1e-9
+    for path in interp:
+        z = np.load(path)
+        out = eval_np.interpolate_between_keyframes(z["pred"], z["frame_indices"], int(z["stride"]))
+        assert np.array_equal(out, z["out"])           # same float64 operations in the same order

@@ -148,3 +148,30 @@ def test_chunked_host_forward_is_identical_to_device_forward(s_in):
     model.forward_host(x, m.astype(np.uint8), hf, hc)
     assert np.array_equal(hc, central.cpu().numpy()) and np.array_equal(hf, full.cpu().numpy())
     model.close()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("B,kind", [(1, "valid"), (3, "all_masked"), (130, "ragged")])
+def test_edge_batches(precision, B, kind):
+    """B = 1, a batch in which NO window has a valid token (empty gather list: zero-row GEMM, token fill everywhere,
+    uniform attention in block 1), and a batch that is not a multiple of any tile size with ragged masks."""
+    cfg = UpliftUpsampleConfig.preset("h36m_351", MASK_STRIDE=20)
+    spec = spec_from_config(cfg)
+    w = weights.init_weights(spec, 2, perturb=True)
+    rng = np.random.default_rng(B)
+    x = rng.uniform(-1, 1, (B, spec.n_tok, 17, 2)).astype(np.float32)
+    if kind == "all_masked":
+        m = np.zeros((B, spec.n_tok), dtype=bool)
+    elif kind == "ragged":
+        m = rng.random((B, spec.n_tok)) < 0.3
+        m[5] = False
+    else:
+        m = np.stack([stride_mask.stride_mask(spec.n_tok, 5, 20)] * B)
+    want_full, want_central = O.test_step(spec, w, x, m, dtype=np.float32)     # fp32 defines all-masked windows
+    model = build_uplift_upsample_transformer(cfg, precision=precision, weights=w)
+    full, central = run_test_step(model, torch.from_numpy(x).cuda(), torch.from_numpy(m).cuda())
+    torch.cuda.synchronize()
+    e = max(np.abs(full.cpu().numpy() - want_full).max(), np.abs(central.cpu().numpy() - want_central).max())
+    print(f"edge {kind} B={B} {precision}: max|err| {e:.3e}")
+    assert np.isfinite(full.cpu().numpy()).all() and e <= (2e-4 if precision == "fp32" else TOL["bf16"])
+    model.close()

@@ -93,3 +93,54 @@ def test_forward_video_equals_forward_on_materialised_windows(precision):
     model.forward_video_host(video, centers, 5, 20, hc)
     assert np.array_equal(hc, c1.cpu().numpy())
     model.close()
+
+
+import glob  # noqa: E402
+
+from test_golden import GOLDEN  # noqa: E402
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_flip_tta_matches_reference_golden(precision):
+    """uu_forward_tta against eval.py:152-180 executed on the reference model (tests/golden/tta_*.npz)."""
+    for path in sorted(glob.glob(os.path.join(GOLDEN, "tta_*.npz"))):
+        cfg, spec, w, z = load_forward_case(path)
+        model = build_uplift_upsample_transformer(cfg, precision=precision, weights=w)
+        full, central = model.forward_tta([torch.from_numpy(z["x"]).cuda(), torch.from_numpy(z["mask"]).cuda()])
+        torch.cuda.synchronize()
+        tol = 1e-4 if precision == "fp32" else 0.25
+        e = max(np.abs(central.cpu().numpy() - z["central"]).max(), np.abs(full.cpu().numpy() - z["full"]).max())
+        print(f"tta {os.path.basename(path)} {precision}: max|err| {e:.3e}")
+        assert e <= tol
+        model.close()
+
+
+def test_keyframe_interpolation_matches_reference_golden():
+    from uplift_upsample_3dhpe_b200.model import keyframe_interp
+    for path in sorted(glob.glob(os.path.join(GOLDEN, "interp_*.npz"))):
+        z = np.load(path)
+        out = keyframe_interp(torch.from_numpy(z["pred"]).cuda(), torch.from_numpy(z["frame_indices"]).cuda(), int(z["stride"]))
+        torch.cuda.synchronize()
+        # the reference interpolates in float64; fp32 weights and one rounding per product
+        assert np.abs(out.cpu().numpy() - z["out"]).max() < 1e-6
+        key = z["keyframes"]
+        assert np.array_equal(out.cpu().numpy()[key], z["pred"][key])
+
+
+def test_video_tta_equals_tta_on_materialised_windows():
+    from uplift_upsample_3dhpe_b200 import UpliftUpsampleConfig, spec_from_config, stride_mask, weights
+    cfg = UpliftUpsampleConfig.preset("h36m_81", MASK_STRIDE=4)
+    spec = spec_from_config(cfg)
+    w = weights.init_weights(spec, 5, perturb=True)
+    rng = np.random.default_rng(3)
+    T = 90
+    video = rng.uniform(-1, 1, (T, 17, 2)).astype(np.float32)
+    centers = np.arange(0, T, 2, dtype=np.int32)
+    src = stride_mask.window_source_frames(spec.n_tok, 2, T, centers)
+    m = stride_mask.batch_stride_masks_eval(spec.n_tok, 2, 4, centers)
+    model = build_uplift_upsample_transformer(cfg, precision="fp32", weights=w)
+    f1, c1 = model.forward_tta([torch.from_numpy(video[src]).cuda(), torch.from_numpy(m).cuda()])
+    f2, c2 = model.forward_video(torch.from_numpy(video).cuda(), torch.from_numpy(centers).cuda(), 2, 4, flip_tta=True)
+    torch.cuda.synchronize()
+    assert torch.equal(c1, c2) and torch.equal(f1, f2)
+    model.close()

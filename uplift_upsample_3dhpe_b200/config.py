@@ -62,6 +62,12 @@ _DEFAULTS: Dict[str, Any] = dict(
     WEIGHT_DECAY=None,
     EMA_ENABLED=False,
     EMA_DECAY=None,
+    # evaluation glue (eval.py:154-222)
+    PADDING_TYPE="copy",
+    TEST_STRIDED_EVAL=True,
+    EVAL_FLIP=True,
+    # our-17-point order, left/right swapped (config/h36m_351.json:4-22, identical in the four shipped configs)
+    AUGM_FLIP_KEYPOINT_ORDER=[5, 4, 3, 2, 1, 0, 6, 7, 8, 9, 10, 16, 15, 14, 13, 12, 11],
 )
 
 _COMMON_351_81 = dict(

@@ -82,6 +82,7 @@ struct SpatialParams {
   const float* x2d;          // (B*n_tok, J, 2)
   const int* list;           // gather list (frame ids) or null = all frames
   const int* src = nullptr;  // optional: token id -> row of x2d (video frame; -1 = zeros), fused window gather
+  const int* flip = nullptr; // optional: flip augmentation, joint j reads source joint flip[j] with x negated
   const int* count;          // device count of valid frames (null with list == null)
   int max_frames;            // B*n_tok
   int J, depth;
@@ -140,7 +141,11 @@ cudaError_t launch_spatial_pack(const float* const* blocks, int depth, const flo
 cudaError_t launch_spatial_tc(const float* x2d, const int* list, const int* count, int max_frames, int depth,
                               const void* frags, const float* params, bf16* out, int num_sms, cudaStream_t s,
                               const int* src = nullptr, const int* range_lo = nullptr, const int* range_hi = nullptr,
-                              int lo = 0, int hi = -1);
+                              int lo = 0, int hi = -1, const int* flip = nullptr);
+
+// ---- evaluation glue (kernels_f32.cu): flip-augmentation average, key-frame interpolation ------------------------
+cudaError_t launch_flip_average(float* a, const float* b, const int* perm, long long n_poses, int J, cudaStream_t st);
+cudaError_t launch_keyframe_interp(const float* pred, const int* fidx, int n, int stride, int V, float* out, cudaStream_t st);
 
 // ---- sliding windows of one video (kernels_f32.cu): source-frame table + globally aligned stride mask ----
 cudaError_t launch_window_index(const int* centers, int B, int n_tok, int s_out, int s_in, int T, int pad_copy, int* src,

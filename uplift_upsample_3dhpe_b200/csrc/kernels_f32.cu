@@ -184,7 +184,9 @@ __global__ void __launch_bounds__(SP_F * 32, 1) k_spatial_f32(SpatialParams p) {
     const float w0 = p.embed_k[lane], w1 = p.embed_k[SP_D + lane], be = p.embed_b[lane];
 #pragma unroll
     for (int j = 0; j < SP_J; ++j) {
-      float2 xy = *reinterpret_cast<const float2*>(x + 2 * j);
+      // flip augmentation (eval.py:154-159): joint j reads source joint flip[j] with the x coordinate negated
+      float2 xy = *reinterpret_cast<const float2*>(x + 2 * (p.flip ? p.flip[j] : j));
+      if (p.flip) xy.x = -xy.x;
       if (fr < 0) xy = make_float2(0.f, 0.f);             // zero padding outside the video
       // Dense = x @ W + b (sum over k in order), then + PE
       xs[j * SP_D + lane] = (fmaf(xy.y, w1, xy.x * w0) + be) + p.pe[j * SP_D + lane];
@@ -380,6 +382,68 @@ cudaError_t launch_window_copy(const float* video, const int* src, int n_tokens,
   const long long n = (long long)n_tokens * J;
   k_window_copy<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float2*>(video), src, n_tokens, J,
                                                              reinterpret_cast<float2*>(x));
+  return cudaGetLastError();
+}
+
+// =================================================================================================
+// Evaluation glue on the device.
+// k_flip_average: test-time flip augmentation, eval.py:161-180 — pred = (pred + unflip(pred_flipped)) / 2 where
+//   unflip negates the x coordinate and gathers joints by AUGM_FLIP_KEYPOINT_ORDER.
+// k_keyframe_interp: common/dataset/action_wise_eval.py:76-100 — frames whose index is a multiple of the key-frame
+//   stride keep their prediction; frames between two key frames of the same video are interpolated linearly in LIST
+//   position; frames after the last key frame of a video copy it.  A video ends where the frame index does not
+//   increase.  (A video that starts on a non-key frame makes the reference raise; here such frames keep their value.)
+// =================================================================================================
+__global__ void k_flip_average(float* __restrict__ a, const float* __restrict__ b, const int* __restrict__ perm,
+                               long long n_poses, int J) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n_poses * J * 3) return;
+  const int c = (int)(i % 3);
+  const int j = (int)((i / 3) % J);
+  const long long pose = i / (3LL * J);
+  float v = b[(pose * J + perm[j]) * 3 + c];
+  if (c == 0) v = -v;
+  a[i] = (a[i] + v) / 2.f;
+}
+cudaError_t launch_flip_average(float* a, const float* b, const int* perm, long long n_poses, int J, cudaStream_t st) {
+  if (n_poses == 0) return cudaSuccess;
+  const long long n = n_poses * J * 3;
+  k_flip_average<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, b, perm, n_poses, J);
+  return cudaGetLastError();
+}
+
+__global__ void k_keyframe_interp(const float* __restrict__ pred, const int* __restrict__ fidx, int n, int stride, int V,
+                                  float* __restrict__ out) {
+  const int i = blockIdx.x;                    // one CTA per frame, threads over the V values of a pose
+  if (i >= n) return;
+  const int f = fidx[i];
+  int L = -1, N = -1;
+  if (f % stride != 0) {
+    // last key frame at or before i inside this video
+    for (int k = i; k >= 0; --k) {
+      if (fidx[k] % stride == 0) { L = k; break; }
+      if (k == 0 || fidx[k] <= fidx[k - 1]) break;         // k starts a video
+    }
+    // next key frame after i inside this video
+    for (int k = i + 1; k < n; ++k) {
+      if (fidx[k] <= fidx[k - 1]) break;                   // k starts the next video
+      if (fidx[k] % stride == 0) { N = k; break; }
+    }
+  }
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+    float r = pred[(long long)i * V + v];
+    if (L >= 0 && N >= 0) {
+      const float d_left = (float)(i - L), d_right = (float)(N - i), d_sum = d_left + d_right;
+      r = pred[(long long)L * V + v] * (d_right / d_sum) + pred[(long long)N * V + v] * (d_left / d_sum);
+    } else if (L >= 0) {
+      r = pred[(long long)L * V + v];
+    }
+    out[(long long)i * V + v] = r;
+  }
+}
+cudaError_t launch_keyframe_interp(const float* pred, const int* fidx, int n, int stride, int V, float* out, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  k_keyframe_interp<<<n, 64, 0, st>>>(pred, fidx, n, stride, V, out);
   return cudaGetLastError();
 }
 

@@ -66,6 +66,10 @@ struct uu_model {
   int* w_src = nullptr;          // sliding-window source-frame table [cap_B * n_tok] (uu_forward_video)
   uint8_t* w_mask = nullptr;     // globally aligned stride mask built on the device [cap_B * n_tok]
   const int* cur_src = nullptr;  // non-null while a video forward is being scheduled
+  int* flip_perm = nullptr;      // device copy of AUGM_FLIP_KEYPOINT_ORDER (uu_set_flip_order)
+  const int* cur_flip = nullptr; // non-null while the flipped half of a test-time-augmented forward is scheduled
+  float *tta_full = nullptr, *tta_central = nullptr;   // outputs of the flipped pass
+  int tta_cap = 0;
   float* d_video = nullptr;      // device staging for uu_forward_video_host
   int* d_centers = nullptr;
   int video_cap = 0, centers_cap = 0;

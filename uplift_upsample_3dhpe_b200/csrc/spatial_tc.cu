@@ -365,6 +365,7 @@ struct SpatialTcParams {
   const int* list;       // gather list or null
   const int* count;      // device count or null
   const int* src;        // optional token id -> row of x2d (video frame, -1 = zeros): fused sliding-window gather
+  const int* flip;       // optional flip augmentation: joint j reads source joint flip[j] with x negated (eval.py:154-159)
   const int* range_lo;   // optional device pointers: process list positions [*range_lo, *range_hi) only
   const int* range_hi;   //   (chunked launches that overlap the host-to-device copy of the next chunk)
   int lo, hi;            // the same as host values when the pointers are null (hi < 0: up to the valid count)
@@ -430,13 +431,14 @@ __global__ void __launch_bounds__(st::THREADS, 1) k_spatial_tc(SpatialTcParams p
       if (f0 < FRAMES && fbase + f0 < n_valid) {
         int fr = p.list ? p.list[fbase + f0] : fbase + f0;
         if (p.src) fr = p.src[fr];
-        if (fr >= 0) p0 = *reinterpret_cast<const float2*>(p.x2d + ((long long)fr * J + j0) * 2);
+        if (fr >= 0) p0 = *reinterpret_cast<const float2*>(p.x2d + ((long long)fr * J + (p.flip ? p.flip[j0] : j0)) * 2);
       }
       if (f1 < FRAMES && fbase + f1 < n_valid) {
         int fr = p.list ? p.list[fbase + f1] : fbase + f1;
         if (p.src) fr = p.src[fr];
-        if (fr >= 0) p1 = *reinterpret_cast<const float2*>(p.x2d + ((long long)fr * J + j1) * 2);
+        if (fr >= 0) p1 = *reinterpret_cast<const float2*>(p.x2d + ((long long)fr * J + (p.flip ? p.flip[j1] : j1)) * 2);
       }
+      if (p.flip) { p0.x = -p0.x; p1.x = -p1.x; }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int c = 8 * j + 2 * t;
@@ -670,7 +672,7 @@ size_t spatial_tc_smem_bytes(int depth) {
 
 cudaError_t launch_spatial_tc(const float* x2d, const int* list, const int* count, int max_frames, int depth,
                               const void* frags, const float* params, bf16* out, int num_sms, cudaStream_t s,
-                              const int* src, const int* range_lo, const int* range_hi, int lo, int hi) {
+                              const int* src, const int* range_lo, const int* range_hi, int lo, int hi, const int* flip) {
   if (max_frames == 0) return cudaSuccess;
   if (depth > st::DEPTH_MAX) return cudaErrorInvalidValue;
   const size_t smem = spatial_tc_smem_bytes(depth);
@@ -682,7 +684,7 @@ cudaError_t launch_spatial_tc(const float* x2d, const int* list, const int* coun
   }
   SpatialTcParams p;
   p.x2d = x2d; p.list = list; p.count = count; p.src = src; p.max_frames = max_frames; p.depth = depth;
-  p.range_lo = range_lo; p.range_hi = range_hi; p.lo = lo; p.hi = hi;
+  p.range_lo = range_lo; p.range_hi = range_hi; p.lo = lo; p.hi = hi; p.flip = flip;
   p.frags = (const uint2*)frags; p.params = params; p.out = out;
   const int groups = (max_frames + st::FRAMES - 1) / st::FRAMES;
   k_spatial_tc<<<std::min(groups, num_sms), st::THREADS, smem, s>>>(p);

@@ -340,12 +340,13 @@ static int run_forward_bf16(Fwd& f, const float* x2d, const uint8_t* mask, float
                 launch_spatial_tc(x2d, use_mask ? m->g_list : nullptr, use_mask ? m->g_count : nullptr, (w1 - w0) * N,
                                   s.spatial_depth, m->sp_frags, m->sp_params, (bf16*)m->S, m->num_sms, st, m->cur_src,
                                   use_mask ? m->g_scratch + w0 : nullptr, use_mask ? m->g_scratch + w1 : nullptr,
-                                  w0 * N, w1 * N));
+                                  w0 * N, w1 * N, m->cur_flip));
     }
   } else {
     UU_LAUNCH(f, UU_KIND_SPATIAL, 1,
               launch_spatial_tc(x2d, use_mask ? m->g_list : nullptr, use_mask ? m->g_count : nullptr, R, s.spatial_depth,
-                                m->sp_frags, m->sp_params, (bf16*)m->S, m->num_sms, st, m->cur_src));
+                                m->sp_frags, m->sp_params, (bf16*)m->S, m->num_sms, st, m->cur_src, nullptr, nullptr, 0, -1,
+                                m->cur_flip));
   }
   {  // S4 + T1: 544->384 GEMM (+ bias) scattered to the token rows through the TMA-store epilogue, upsampling token on
      // the rows without 2-D input; the temporal PE (net:352, added to every row) rides on the first LayerNorm pass
@@ -454,7 +455,7 @@ static int run_forward_impl(uu_model* m, const float* x2d, const uint8_t* mask, 
   // K2: fused spatial transformer on the valid frames -> S (compact rows)
   SpatialParams sp;
   sp.x2d = x2d; sp.list = use_mask ? m->g_list : nullptr; sp.count = use_mask ? m->g_count : nullptr;
-  sp.max_frames = R; sp.J = J; sp.depth = s.spatial_depth; sp.src = m->cur_src;
+  sp.max_frames = R; sp.J = J; sp.depth = s.spatial_depth; sp.src = m->cur_src; sp.flip = m->cur_flip;
   sp.embed_k = W(m, "keypoint_embedding", 0); sp.embed_b = W(m, "keypoint_embedding", 1);
   sp.pe = W(m, "spatial_pe", 0); sp.blocks = m->spatial_ptrs;
   sp.norm_g = W(m, "spatial_norm", 0); sp.norm_b = W(m, "spatial_norm", 1);
@@ -645,6 +646,7 @@ int uu_destroy(uu_model* m) {
   cudaFree(m->d_full);
   cudaFree(m->d_central);
   cudaFree(m->d_video);
+  cudaFree(m->flip_perm); cudaFree(m->tta_full); cudaFree(m->tta_central);
   cudaFree(m->d_centers);
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
   if (m->copy_stream) {
@@ -825,6 +827,68 @@ int uu_forward_video_host(uu_model* m, const float* video2d, int T, const int32_
   if (full) UU_CUDA(cudaMemcpyAsync(full, m->d_full, sizeof(float) * R * s.n_joints * 3, cudaMemcpyDeviceToHost, st));
   UU_CUDA(cudaMemcpyAsync(central, m->d_central, sizeof(float) * (size_t)B * s.n_joints * 3, cudaMemcpyDeviceToHost, st));
   UU_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ---- test-time flip augmentation (eval.py:154-180) ---------------------------------------------
+int uu_set_flip_order(uu_model* m, const int32_t* order, int n) {
+  UU_CHECK(m && order && n == m->spec.n_joints, "flip order must list n_joints source joints");
+  for (int i = 0; i < n; ++i) UU_CHECK(order[i] >= 0 && order[i] < n, "flip order entry out of range");
+  UU_CUDA(cudaSetDevice(m->device));
+  if (!m->flip_perm) UU_CUDA(cudaMalloc(&m->flip_perm, sizeof(int) * n));
+  UU_CUDA(cudaMemcpy(m->flip_perm, order, sizeof(int) * n, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+static int tta_buffers(uu_model* m, int B) {
+  if (B <= m->tta_cap) return 0;
+  const uu_spec& s = m->spec;
+  UU_CUDA(cudaDeviceSynchronize());
+  cudaFree(m->tta_full); cudaFree(m->tta_central);
+  m->tta_full = m->tta_central = nullptr;
+  UU_CUDA(cudaMalloc(&m->tta_full, sizeof(float) * (size_t)B * s.n_tok * s.n_joints * 3));
+  UU_CUDA(cudaMalloc(&m->tta_central, sizeof(float) * (size_t)B * s.n_joints * 3));
+  m->tta_cap = B;
+  return 0;
+}
+
+// pred = (f(x) + unflip(f(flip(x)))) / 2 for both outputs; `video` selects the fused-gather input path
+static int forward_tta(uu_model* m, const float* x, const uint8_t* mask, int T, const int32_t* centers, int B, int s_out,
+                       int s_in, int pad_copy, bool video, float* full, float* central, cudaStream_t st) {
+  UU_CHECK(m->flip_perm, "call uu_set_flip_order before a flip-augmented forward");
+  const uu_spec& s = m->spec;
+  UU_CUDA(cudaSetDevice(m->device));
+  if (tta_buffers(m, B)) return 1;
+  const bool want_full = s.full_output && full;
+  for (int pass = 0; pass < 2; ++pass) {
+    m->cur_flip = pass ? m->flip_perm : nullptr;
+    float* fo = pass ? (want_full ? m->tta_full : nullptr) : full;
+    float* co = pass ? m->tta_central : central;
+    const int rc = video ? forward_video_dev(m, x, T, centers, B, s_out, s_in, pad_copy, fo, co, st)
+                         : run_forward(m, x, mask, B, fo, co, st);
+    m->cur_flip = nullptr;
+    if (rc) return 1;
+  }
+  UU_CUDA(launch_flip_average(central, m->tta_central, m->flip_perm, B, s.n_joints, st));
+  if (want_full) UU_CUDA(launch_flip_average(full, m->tta_full, m->flip_perm, (long long)B * s.n_tok, s.n_joints, st));
+  return 0;
+}
+
+int uu_forward_tta(uu_model* m, const float* x2d, const uint8_t* mask, int B, float* full, float* central, void* stream) {
+  UU_CHECK(m && x2d && central && B > 0, "bad argument");
+  return forward_tta(m, x2d, mask, 0, nullptr, B, 0, 0, 0, false, full, central, (cudaStream_t)stream);
+}
+
+int uu_forward_video_tta(uu_model* m, const float* video2d, int T, const int32_t* centers, int B, int s_out, int s_in,
+                         int pad_copy, float* full, float* central, void* stream) {
+  UU_CHECK(m && video2d && centers && central && B > 0, "bad argument");
+  return forward_tta(m, video2d, nullptr, T, centers, B, s_out, s_in, pad_copy, true, full, central, (cudaStream_t)stream);
+}
+
+int uu_op_keyframe_interp(const float* pred, const int32_t* frame_indices, int n, int keyframe_stride, int values_per_frame,
+                          float* out, void* stream) {
+  UU_CHECK(pred && frame_indices && out && n >= 0 && keyframe_stride >= 1 && values_per_frame >= 1, "bad argument");
+  UU_CUDA(launch_keyframe_interp(pred, frame_indices, n, keyframe_stride, values_per_frame, out, (cudaStream_t)stream));
   return 0;
 }
 

@@ -181,8 +181,37 @@ class UpliftUpsampleTransformer:
                                              central_out.ctypes.data_as(c_void_p)))
 
 
+    # ---- evaluation glue on the device ------------------------------------
+    def set_flip_order(self, order) -> None:
+        """AUGM_FLIP_KEYPOINT_ORDER of the config (eval.py:159)."""
+        a = np.ascontiguousarray(order, dtype=np.int32)
+        _lib.check(self._lib.uu_set_flip_order(self._h, a.ctypes.data_as(c_void_p), int(a.size)))
+
+    def forward_tta(self, inputs, want_full: bool = True):
+        """Flip test-time augmentation (eval.py:152-180): (f(x) + unflip(f(flip(x)))) / 2 for both outputs."""
+        torch = _torch()
+        if self.has_strided_input:
+            x, mask = inputs[0], inputs[1]
+        else:
+            x, mask = (inputs[0] if isinstance(inputs, (list, tuple)) else inputs), None
+        s = self.spec
+        x = x.contiguous().float()
+        B = x.shape[0]
+        mptr = None
+        if mask is not None:
+            mask = mask.to(device=x.device, dtype=torch.uint8).contiguous()
+            mptr = mask.data_ptr()
+        full = torch.empty((B, s.n_tok, s.n_joints, 3), dtype=torch.float32, device=x.device) \
+            if (self.full_output and want_full) else None
+        central = torch.empty((B, s.n_joints, 3), dtype=torch.float32, device=x.device)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        _lib.check(self._lib.uu_forward_tta(self._h, x.data_ptr(), mptr, B, full.data_ptr() if full is not None else None,
+                                            central.data_ptr(), stream))
+        return full, central
+
     # ---- sliding windows cut on the device from one video (SURVEY.md 8f row 1) -------------------
-    def forward_video(self, video2d, centers, s_out: int, s_in: int, pad_copy: bool = True, want_full: bool = True):
+    def forward_video(self, video2d, centers, s_out: int, s_in: int, pad_copy: bool = True, want_full: bool = True,
+                      flip_tta: bool = False):
         """video2d (T,J,2) float32 cuda, centers (B,) int32 cuda frame indices.  Equivalent to building the
         reference generator's windows + globally aligned stride masks (uplifiting_dataset.py:341-394) and calling
         test_step on them, without materialising the (B, n_tok, J, 2) tensor."""
@@ -198,9 +227,9 @@ class UpliftUpsampleTransformer:
             full = torch.empty((B, s.n_tok, s.n_joints, 3), dtype=torch.float32, device=video2d.device)
         central = torch.empty((B, s.n_joints, 3), dtype=torch.float32, device=video2d.device)
         stream = torch.cuda.current_stream(video2d.device).cuda_stream
-        _lib.check(self._lib.uu_forward_video(self._h, video2d.data_ptr(), T, centers.data_ptr(), B, int(s_out), int(s_in),
-                                              1 if pad_copy else 0, full.data_ptr() if full is not None else None,
-                                              central.data_ptr(), stream))
+        fn = self._lib.uu_forward_video_tta if flip_tta else self._lib.uu_forward_video
+        _lib.check(fn(self._h, video2d.data_ptr(), T, centers.data_ptr(), B, int(s_out), int(s_in),
+                      1 if pad_copy else 0, full.data_ptr() if full is not None else None, central.data_ptr(), stream))
         return full, central
 
     def forward_video_host(self, video2d: np.ndarray, centers: np.ndarray, s_out: int, s_in: int,
@@ -224,6 +253,9 @@ def build_uplift_upsample_transformer(config, device: int = 0, precision: str = 
     spec = spec_from_config(config)
     model = UpliftUpsampleTransformer(spec, device=device, precision=precision)
     model.set_weights(weights if weights is not None else W.init_weights(spec, seed))
+    order = getattr(config, "AUGM_FLIP_KEYPOINT_ORDER", None)
+    if order is not None and len(order) == spec.n_joints:
+        model.set_flip_order(order)
     return model
 
 
@@ -233,6 +265,20 @@ def test_step(model: UpliftUpsampleTransformer, keypoints2d, stride_masks):
     if model.has_strided_input:
         return model([keypoints2d, stride_masks], training=False)
     return model(keypoints2d, training=False)
+
+
+def keyframe_interp(pred, frame_indices, keyframe_stride: int):
+    """action_wise_eval.interpolate_between_keyframes on the device: pred (n, ...) float32 cuda, frame_indices (n,)."""
+    torch = _torch()
+    lib = _lib.load()
+    pred = pred.contiguous().float()
+    idx = frame_indices.to(device=pred.device, dtype=torch.int32).contiguous()
+    out = torch.empty_like(pred)
+    n = pred.shape[0]
+    stream = torch.cuda.current_stream(pred.device).cuda_stream
+    _lib.check(lib.uu_op_keyframe_interp(pred.data_ptr(), idx.data_ptr(), n, int(keyframe_stride), pred[0].numel() if n else 1,
+                                         out.data_ptr(), stream))
+    return out
 
 
 def host_stride_mask(n_tok: int, s_out: int, s_in: int, shift: int = 0) -> np.ndarray:
