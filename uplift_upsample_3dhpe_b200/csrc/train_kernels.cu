@@ -23,10 +23,67 @@ __device__ __forceinline__ float warp_sum_t(float v) {
 //   opB(k,n) = TB ? B[n*ldb + k] : B[k*ldb + n]
 //   split-K over gridDim.z with fp32 atomics (C must be pre-initialised; used for weight gradients).
 // =================================================================================================
-constexpr int GG_M = 64, GG_N = 64, GG_K = 16;
+// 128 x 128 x 16 tiles, 256 threads, 8 x 8 outputs per thread (two 4-wide strips in each dimension so that every
+// shared-memory read is a conflict-free float4: 16 FFMA per LDS.128), 16-byte global loads with a scalar fallback for
+// unaligned / ragged edges, next tile prefetched into registers while the current one is multiplied.
+constexpr int GG_M = 128, GG_N = 128, GG_K = 16;
+
+// 2 x float4 per thread per operand tile.  "Along K" operands (A row-major, B^T) are transposed on the way into
+// shared memory; "along M/N" operands (A^T, B row-major) are stored as they are loaded.
+template <bool ALONG_K>
+struct GgLoader {
+  float4 v[2];
+  // ALONG_K: element (rc, k) at base[map(rc)*ld + k]; else element (k, rc) at base[k*ld + rc]
+  __device__ __forceinline__ void load(const float* __restrict__ base, long long ld, const RowMap* map, int rc0, int rc_end,
+                                       int k0, int kend, bool vec_ok, int tid) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float t[4] = {0.f, 0.f, 0.f, 0.f};
+      if constexpr (ALONG_K) {
+        const int rc = rc0 + (tid >> 2) + 64 * h, k = k0 + (tid & 3) * 4;
+        if (rc < rc_end && k < kend) {
+          const long long rr = map ? map_row(*map, rc) : rc;
+          if (rr >= 0) {
+            const float* src = base + rr * ld + k;
+            if (k + 3 < kend && vec_ok) {
+              const float4 q = *reinterpret_cast<const float4*>(src);
+              t[0] = q.x; t[1] = q.y; t[2] = q.z; t[3] = q.w;
+            } else {
+              for (int i = 0; i < 4 && k + i < kend; ++i) t[i] = src[i];
+            }
+          }
+        }
+      } else {
+        const int k = k0 + (tid >> 5) + 8 * h, rc = rc0 + (tid & 31) * 4;
+        if (k < kend && rc < rc_end) {
+          const float* src = base + (long long)k * ld + rc;
+          if (rc + 3 < rc_end && vec_ok) {
+            const float4 q = *reinterpret_cast<const float4*>(src);
+            t[0] = q.x; t[1] = q.y; t[2] = q.z; t[3] = q.w;
+          } else {
+            for (int i = 0; i < 4 && rc + i < rc_end; ++i) t[i] = src[i];
+          }
+        }
+      }
+      v[h] = make_float4(t[0], t[1], t[2], t[3]);
+    }
+  }
+  __device__ __forceinline__ void store(float (*S)[GG_M + 4], int tid) const {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if constexpr (ALONG_K) {
+        const int rc = (tid >> 2) + 64 * h, k = (tid & 3) * 4;
+        S[k][rc] = v[h].x; S[k + 1][rc] = v[h].y; S[k + 2][rc] = v[h].z; S[k + 3][rc] = v[h].w;
+      } else {
+        *reinterpret_cast<float4*>(&S[(tid >> 5) + 8 * h][(tid & 31) * 4]) = v[h];
+      }
+    }
+  }
+};
 
 template <bool TA, bool TB>
-__global__ void __launch_bounds__(256) k_gemm_gen(GemmGen g) {
+__global__ void __launch_bounds__(256, 2) k_gemm_gen(GemmGen g) {
+  static_assert(GG_M == GG_N, "one padded tile type serves both operands");
   __shared__ __align__(16) float As[GG_K][GG_M + 4];
   __shared__ __align__(16) float Bs[GG_K][GG_N + 4];
   const int row0 = blockIdx.x * GG_M, col0 = blockIdx.y * GG_N;
@@ -34,83 +91,52 @@ __global__ void __launch_bounds__(256) k_gemm_gen(GemmGen g) {
   const int kchunk = (((g.K + gridDim.z - 1) / gridDim.z) + GG_K - 1) / GG_K * GG_K;
   const int kbeg = blockIdx.z * kchunk, kend = min(g.K, kbeg + kchunk);
   const bool avec = (g.lda & 3) == 0 && (reinterpret_cast<uintptr_t>(g.A) & 15) == 0;   // 16-byte loads allowed
-  float acc[4][4];
+  const bool bvec = (g.ldb & 3) == 0 && (reinterpret_cast<uintptr_t>(g.B) & 15) == 0;
+  const bool amapped = !TA && g.amap.rpb != 0x7fffffff;
+  float acc[8][8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  GgLoader<!TA> la;     // A row-major [M, K] is read along K; A^T [K, M] along M
+  GgLoader<TB> lb;      // B^T [N, K] is read along K; B row-major [K, N] along N
+  if (kbeg < kend) {
+    la.load(g.A, g.lda, amapped ? &g.amap : nullptr, row0, g.M, kbeg, kend, avec, tid);
+    lb.load(g.B, g.ldb, nullptr, col0, g.N, kbeg, kend, bvec, tid);
+  }
   for (int k0 = kbeg; k0 < kend; k0 += GG_K) {
-    if constexpr (!TA) {
-      const int a_row = tid >> 2, a_k = (tid & 3) * 4;
-      float v[4] = {0.f, 0.f, 0.f, 0.f};
-      const int r = row0 + a_row, k = k0 + a_k;
-      if (r < g.M && k < kend) {
-        const long long ar = map_row(g.amap, r);
-        if (ar >= 0) {
-          const float* src = g.A + ar * g.lda + k;
-          if (k + 3 < kend && avec) {
-            const float4 t = *reinterpret_cast<const float4*>(src);
-            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-          } else {
-            for (int i = 0; i < 4 && k + i < kend; ++i) v[i] = src[i];
-          }
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) As[a_k + i][a_row] = v[i];
-    } else {
-      const int kk = tid >> 4, r4 = (tid & 15) * 4;
-      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-      const int k = k0 + kk, r = row0 + r4;
-      if (k < kend && r < g.M) {
-        const float* src = g.A + (long long)k * g.lda + r;
-        if (r + 3 < g.M && avec) t = *reinterpret_cast<const float4*>(src);
-        else { t.x = src[0]; if (r + 1 < g.M) t.y = src[1]; if (r + 2 < g.M) t.z = src[2]; if (r + 3 < g.M) t.w = src[3]; }
-      }
-      *reinterpret_cast<float4*>(&As[kk][r4]) = t;
-    }
-    if constexpr (!TB) {
-      const int b_k = tid >> 4, b_n = (tid & 15) * 4;
-      const int k = k0 + b_k;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int n = col0 + b_n + i;
-        Bs[b_k][b_n + i] = (k < kend && n < g.N) ? g.B[(long long)k * g.ldb + n] : 0.f;
-      }
-    } else {
-      const int n_l = tid >> 2, k4 = (tid & 3) * 4;
-      const int n = col0 + n_l, k = k0 + k4;
-      float v[4] = {0.f, 0.f, 0.f, 0.f};
-      if (n < g.N) {
-        const float* src = g.B + (long long)n * g.ldb + k;
-        for (int i = 0; i < 4; ++i)
-          if (k + i < kend) v[i] = src[i];
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) Bs[k4 + i][n_l] = v[i];
-    }
+    la.store(As, tid);
+    lb.store(Bs, tid);
     __syncthreads();
+    if (k0 + GG_K < kend) {          // prefetch the next tile while this one is multiplied
+      la.load(g.A, g.lda, amapped ? &g.amap : nullptr, row0, g.M, k0 + GG_K, kend, avec, tid);
+      lb.load(g.B, g.ldb, nullptr, col0, g.N, k0 + GG_K, kend, bvec, tid);
+    }
 #pragma unroll
     for (int kk = 0; kk < GG_K; ++kk) {
-      const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
-      const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][64 + tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = row0 + ty * 4 + i;
+  for (int i = 0; i < 8; ++i) {
+    const int r = row0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
     if (r >= g.M) continue;
     const long long cr = map_row(g.cmap, r);
     if (cr < 0) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = col0 + tx * 4 + j;
+    for (int j = 0; j < 8; ++j) {
+      const int c = col0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
       if (c >= g.N) continue;
       float v = acc[i][j];
       float* dst = g.C + cr * g.ldc + c;
