@@ -15,6 +15,7 @@ struct GemmGen {
   int split_k = 1;               // > 1: fp32 atomics into C (requires accumulate)
 };
 cudaError_t launch_gemm_gen(const GemmGen& g, cudaStream_t st);
+void gemm_gen_tile(int N, int* bm, int* bn);      // tile shape launch_gemm_gen picks for an N-wide output
 cudaError_t launch_colsum(const float* Y, int M, int N, long long ld, float* out, cudaStream_t st);
 cudaError_t launch_period_sum(const float* X, long long rows, int period, int d, const uint8_t* rowmask, int want,
                               float* out, cudaStream_t st);

@@ -23,84 +23,93 @@ __device__ __forceinline__ float warp_sum_t(float v) {
 //   opB(k,n) = TB ? B[n*ldb + k] : B[k*ldb + n]
 //   split-K over gridDim.z with fp32 atomics (C must be pre-initialised; used for weight gradients).
 // =================================================================================================
-// 128 x 128 x 16 tiles, 256 threads, 8 x 8 outputs per thread (two 4-wide strips in each dimension so that every
-// shared-memory read is a conflict-free float4: 16 FFMA per LDS.128), 16-byte global loads with a scalar fallback for
-// unaligned / ragged edges, next tile prefetched into registers while the current one is multiplied.
-constexpr int GG_M = 128, GG_N = 128, GG_K = 16;
+// BM x BN x 16 tiles, 256 threads, 8 x TN outputs per thread (4-wide strips so that every shared-memory read is a
+// conflict-free float4), 16-byte global loads with a scalar fallback for unaligned / ragged edges, next tile
+// prefetched into registers while the current one is multiplied.  Tile shapes: 128 x 128 (TN 8) for the d = 384
+// layers, 128 x 64 and 256 x 32 (TN 4) for the 32 / 64-wide spatial layers and the 51-wide heads, so narrow outputs
+// do not pay for columns that do not exist.
+constexpr int GG_K = 16;
 
-// 2 x float4 per thread per operand tile.  "Along K" operands (A row-major, B^T) are transposed on the way into
+// One operand tile of RC rows/cols x 16 k.  "Along K" operands (A row-major, B^T) are transposed on the way into
 // shared memory; "along M/N" operands (A^T, B row-major) are stored as they are loaded.
-template <bool ALONG_K>
+template <bool ALONG_K, int RC>
 struct GgLoader {
-  float4 v[2];
+  static constexpr int NV = (RC * GG_K / 4 + 255) / 256;          // float4 per thread (RC = 32: half the threads idle)
+  static constexpr int ACTIVE = RC * GG_K / 4 < 256 ? RC * GG_K / 4 : 256;
+  static constexpr int PER_ROW = RC / 4;                           // float4 per k-row (along M/N)
+  float4 v[NV];
   // ALONG_K: element (rc, k) at base[map(rc)*ld + k]; else element (k, rc) at base[k*ld + rc]
   __device__ __forceinline__ void load(const float* __restrict__ base, long long ld, const RowMap* map, int rc0, int rc_end,
                                        int k0, int kend, bool vec_ok, int tid) {
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < NV; ++h) {
       float t[4] = {0.f, 0.f, 0.f, 0.f};
-      if constexpr (ALONG_K) {
-        const int rc = rc0 + (tid >> 2) + 64 * h, k = k0 + (tid & 3) * 4;
-        if (rc < rc_end && k < kend) {
-          const long long rr = map ? map_row(*map, rc) : rc;
-          if (rr >= 0) {
-            const float* src = base + rr * ld + k;
-            if (k + 3 < kend && vec_ok) {
+      if (tid < ACTIVE) {
+        if constexpr (ALONG_K) {
+          const int rc = rc0 + (tid >> 2) + 64 * h, k = k0 + (tid & 3) * 4;
+          if (rc < rc_end && k < kend) {
+            const long long rr = map ? map_row(*map, rc) : rc;
+            if (rr >= 0) {
+              const float* src = base + rr * ld + k;
+              if (k + 3 < kend && vec_ok) {
+                const float4 q = *reinterpret_cast<const float4*>(src);
+                t[0] = q.x; t[1] = q.y; t[2] = q.z; t[3] = q.w;
+              } else {
+                for (int i = 0; i < 4 && k + i < kend; ++i) t[i] = src[i];
+              }
+            }
+          }
+        } else {
+          const int k = k0 + tid / PER_ROW + (256 / PER_ROW) * h, rc = rc0 + (tid % PER_ROW) * 4;
+          if (k < kend && rc < rc_end) {
+            const float* src = base + (long long)k * ld + rc;
+            if (rc + 3 < rc_end && vec_ok) {
               const float4 q = *reinterpret_cast<const float4*>(src);
               t[0] = q.x; t[1] = q.y; t[2] = q.z; t[3] = q.w;
             } else {
-              for (int i = 0; i < 4 && k + i < kend; ++i) t[i] = src[i];
+              for (int i = 0; i < 4 && rc + i < rc_end; ++i) t[i] = src[i];
             }
-          }
-        }
-      } else {
-        const int k = k0 + (tid >> 5) + 8 * h, rc = rc0 + (tid & 31) * 4;
-        if (k < kend && rc < rc_end) {
-          const float* src = base + (long long)k * ld + rc;
-          if (rc + 3 < rc_end && vec_ok) {
-            const float4 q = *reinterpret_cast<const float4*>(src);
-            t[0] = q.x; t[1] = q.y; t[2] = q.z; t[3] = q.w;
-          } else {
-            for (int i = 0; i < 4 && rc + i < rc_end; ++i) t[i] = src[i];
           }
         }
       }
       v[h] = make_float4(t[0], t[1], t[2], t[3]);
     }
   }
-  __device__ __forceinline__ void store(float (*S)[GG_M + 4], int tid) const {
+  __device__ __forceinline__ void store(float (*S)[RC + 4], int tid) const {
+    if (tid >= ACTIVE) return;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < NV; ++h) {
       if constexpr (ALONG_K) {
         const int rc = (tid >> 2) + 64 * h, k = (tid & 3) * 4;
         S[k][rc] = v[h].x; S[k + 1][rc] = v[h].y; S[k + 2][rc] = v[h].z; S[k + 3][rc] = v[h].w;
       } else {
-        *reinterpret_cast<float4*>(&S[(tid >> 5) + 8 * h][(tid & 31) * 4]) = v[h];
+        *reinterpret_cast<float4*>(&S[tid / PER_ROW + (256 / PER_ROW) * h][(tid % PER_ROW) * 4]) = v[h];
       }
     }
   }
 };
 
-template <bool TA, bool TB>
+template <bool TA, bool TB, int BM, int BN>
 __global__ void __launch_bounds__(256, 2) k_gemm_gen(GemmGen g) {
-  static_assert(GG_M == GG_N, "one padded tile type serves both operands");
-  __shared__ __align__(16) float As[GG_K][GG_M + 4];
-  __shared__ __align__(16) float Bs[GG_K][GG_N + 4];
-  const int row0 = blockIdx.x * GG_M, col0 = blockIdx.y * GG_N;
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  constexpr int TM = 8, TN = BM * BN / (TM * 256), NTX = BN / TN;
+  static_assert(TN == 4 || TN == 8, "thread tile is 8 x 4 or 8 x 8");
+  __shared__ __align__(16) float As[GG_K][BM + 4];
+  __shared__ __align__(16) float Bs[GG_K][BN + 4];
+  const int row0 = blockIdx.x * BM, col0 = blockIdx.y * BN;
+  const int tid = threadIdx.x, tx = tid % NTX, ty = tid / NTX;
   const int kchunk = (((g.K + gridDim.z - 1) / gridDim.z) + GG_K - 1) / GG_K * GG_K;
   const int kbeg = blockIdx.z * kchunk, kend = min(g.K, kbeg + kchunk);
   const bool avec = (g.lda & 3) == 0 && (reinterpret_cast<uintptr_t>(g.A) & 15) == 0;   // 16-byte loads allowed
   const bool bvec = (g.ldb & 3) == 0 && (reinterpret_cast<uintptr_t>(g.B) & 15) == 0;
   const bool amapped = !TA && g.amap.rpb != 0x7fffffff;
-  float acc[8][8];
+  float acc[TM][TN];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < TM; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-  GgLoader<!TA> la;     // A row-major [M, K] is read along K; A^T [K, M] along M
-  GgLoader<TB> lb;      // B^T [N, K] is read along K; B row-major [K, N] along N
+  GgLoader<!TA, BM> la;     // A row-major [M, K] is read along K; A^T [K, M] along M
+  GgLoader<TB, BN> lb;      // B^T [N, K] is read along K; B row-major [K, N] along N
   if (kbeg < kend) {
     la.load(g.A, g.lda, amapped ? &g.amap : nullptr, row0, g.M, kbeg, kend, avec, tid);
     lb.load(g.B, g.ldb, nullptr, col0, g.N, kbeg, kend, bvec, tid);
@@ -116,27 +125,31 @@ __global__ void __launch_bounds__(256, 2) k_gemm_gen(GemmGen g) {
 #pragma unroll
     for (int kk = 0; kk < GG_K; ++kk) {
       const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
-      const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][64 + ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][BM / 2 + ty * 4]);
       const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][64 + tx * 4]);
       const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float bv[TN];
+      bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w;
+      if constexpr (TN == 8) {
+        const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][BN / 2 + tx * 4]);
+        bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+      }
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = row0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+  for (int i = 0; i < TM; ++i) {
+    const int r = row0 + (i < 4 ? ty * 4 + i : BM / 2 + ty * 4 + (i - 4));
     if (r >= g.M) continue;
     const long long cr = map_row(g.cmap, r);
     if (cr < 0) continue;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = col0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+    for (int j = 0; j < TN; ++j) {
+      const int c = col0 + (j < 4 ? tx * 4 + j : BN / 2 + tx * 4 + (j - 4));
       if (c >= g.N) continue;
       float v = acc[i][j];
       float* dst = g.C + cr * g.ldc + c;
@@ -151,18 +164,33 @@ __global__ void __launch_bounds__(256, 2) k_gemm_gen(GemmGen g) {
   }
 }
 
+void gemm_gen_tile(int N, int* bm, int* bn) {
+  if (N > 64) { *bm = 128; *bn = 128; }
+  else if (N > 32) { *bm = 128; *bn = 64; }
+  else { *bm = 256; *bn = 32; }
+}
+
+template <int BM, int BN>
+static void gg_launch(const GemmGen& g, int splits, cudaStream_t st) {
+  dim3 grid((g.M + BM - 1) / BM, (g.N + BN - 1) / BN, splits);
+  if (g.transA) {
+    if (g.transB) k_gemm_gen<true, true, BM, BN><<<grid, 256, 0, st>>>(g);
+    else k_gemm_gen<true, false, BM, BN><<<grid, 256, 0, st>>>(g);
+  } else {
+    if (g.transB) k_gemm_gen<false, true, BM, BN><<<grid, 256, 0, st>>>(g);
+    else k_gemm_gen<false, false, BM, BN><<<grid, 256, 0, st>>>(g);
+  }
+}
+
 cudaError_t launch_gemm_gen(const GemmGen& g, cudaStream_t st) {
   if (g.M == 0 || g.N == 0 || g.K == 0) return cudaSuccess;
   int splits = g.split_k < 1 ? 1 : g.split_k;
   if (splits > 1 && (g.bias || g.relu || !g.accumulate)) return cudaErrorInvalidValue;
-  dim3 grid((g.M + GG_M - 1) / GG_M, (g.N + GG_N - 1) / GG_N, splits);
-  if (g.transA) {
-    if (g.transB) k_gemm_gen<true, true><<<grid, 256, 0, st>>>(g);
-    else k_gemm_gen<true, false><<<grid, 256, 0, st>>>(g);
-  } else {
-    if (g.transB) k_gemm_gen<false, true><<<grid, 256, 0, st>>>(g);
-    else k_gemm_gen<false, false><<<grid, 256, 0, st>>>(g);
-  }
+  int bm, bn;
+  gemm_gen_tile(g.N, &bm, &bn);
+  if (bn == 128) gg_launch<128, 128>(g, splits, st);
+  else if (bn == 64) gg_launch<128, 64>(g, splits, st);
+  else gg_launch<256, 32>(g, splits, st);
   return cudaGetLastError();
 }
 

@@ -90,9 +90,11 @@ static int lin_bwd(Ctx& c, const float* X, long long ldx, const float* dY, long 
     GemmGen g;
     g.A = X; g.lda = ldx; g.transA = 1; g.B = dY; g.ldb = ldy; g.C = dW; g.ldc = N; g.M = K; g.N = N; g.K = M;
     g.accumulate = 1;
-    const int tiles = ((K + 63) / 64) * ((N + 63) / 64);
-    int splits = (148 * 2 + tiles - 1) / tiles;
-    splits = std::max(1, std::min(splits, std::max(1, M / 256)));
+    int bm, bn;
+    gemm_gen_tile(N, &bm, &bn);
+    const int tiles = ((K + bm - 1) / bm) * ((N + bn - 1) / bn);
+    int splits = (148 * 4 + tiles - 1) / tiles;          // two CTAs per SM, two waves
+    splits = std::max(1, std::min(splits, std::max(1, M / 512)));
     g.split_k = splits;
     UU_TL(launch_gemm_gen(g, c.st));
   }
