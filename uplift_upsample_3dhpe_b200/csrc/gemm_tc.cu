@@ -140,9 +140,9 @@ __device__ __forceinline__ void epi_warp_store_tile(uint32_t tmem_acc, int first
   int dst_row = row_q0;                      // first destination row of the TMA box
   bool boxed = true;
   int my_dst = -1;
-  if (epi.c_rowidx) {
+  if (epi.c_rowidx || epi.cmap.rpb != 0x7fffffff) {      // scatter list, or a (batch, position) row map that drops rows
     const int r = row_q0 + lane;
-    my_dst = r < m_eff ? epi.c_rowidx[r] : -1;
+    my_dst = r < m_eff ? (epi.c_rowidx ? epi.c_rowidx[r] : (int)map_row(epi.cmap, r)) : -1;
     dst_row = __shfl_sync(0xffffffffu, my_dst, 0);
     boxed = __all_sync(0xffffffffu, my_dst >= 0 && my_dst == dst_row + lane);
   }
@@ -867,8 +867,8 @@ static int g_use_2cta = -1;     // UU_GEMM_2CTA=0/1 forces the single-CTA / 2-CT
 
 // bf16 output, plain row mapping, no residual / table / scatter, full 64-column sub-tiles: TMA-store epilogue
 static bool tma_out_eligible(const TcGemmPlan* p, const Epilogue& epi, int c_bf16, long long ldc) {
-  return c_bf16 && epi.cmap.rpb == 0x7fffffff && !(epi.flags & (EPI_RESIDUAL | EPI_ROWTABLE)) && p->N == p->N_pad &&
-         (p->N % 64) == 0 && (ldc % 8) == 0 && p->block_n >= 64;
+  return c_bf16 && !(epi.flags & (EPI_RESIDUAL | EPI_ROWTABLE)) && p->N == p->N_pad && (p->N % 64) == 0 &&
+         (ldc % 8) == 0 && p->block_n >= 64;
 }
 
 cudaError_t tc_gemm_launch(TcGemmPlan* p, const Epilogue& epi_in, void* C, int c_bf16, long long ldc, cudaStream_t st) {
@@ -884,7 +884,11 @@ cudaError_t tc_gemm_launch(TcGemmPlan* p, const Epilogue& epi_in, void* C, int c
   if (nopf) epi.flags |= 256;
   if (tma_out_eligible(p, epi, c_bf16, ldc)) {
     if (p->c_ptr != C || p->c_ld != ldc) {
-      if (encode_2d(&p->map_c, C, (uint64_t)p->N, (uint64_t)p->M, (uint64_t)ldc, 64, 32)) return cudaErrorInvalidValue;
+      // rows of the output matrix: M, or with a (batch, position) row map the extent it can reach
+      uint64_t c_rows = (uint64_t)p->M;
+      if (epi.cmap.rpb != 0x7fffffff)
+        c_rows = (uint64_t)((p->M + epi.cmap.rpb - 1) / epi.cmap.rpb) * (uint64_t)epi.cmap.batch_rows;
+      if (encode_2d(&p->map_c, C, (uint64_t)p->N, c_rows, (uint64_t)ldc, 64, 32)) return cudaErrorInvalidValue;
       p->c_ptr = C; p->c_ld = ldc;
     }
     if (g_use_2cta < 0) {
@@ -894,7 +898,7 @@ cudaError_t tc_gemm_launch(TcGemmPlan* p, const Epilogue& epi_in, void* C, int c
     static int use_bs = -1;
     if (use_bs < 0) { const char* e = getenv("UU_GEMM_BSTAT"); use_bs = (e && e[0] == '1') ? 1 : 0; }   // default off: measured no faster
     // short-K GEMMs with M >> N: keep the weight tile resident (K = 384 -> 6 panels of a 128-wide column block)
-    const bool scatter = epi.c_rowidx || epi.m_dev;
+    const bool scatter = epi.c_rowidx || epi.m_dev || epi.cmap.rpb != 0x7fffffff;
     if (!scatter && use_bs && p->K == 384 && p->N_pad % 128 == 0 && p->M >= 4 * TC_BLOCK_M * (p->N_pad / 128))
       return tc_launch_bs<128, 6>(p, epi, C, ldc, st);
     if (!scatter && (g_use_2cta == 1 || (g_use_2cta == 2 && p->K >= 768)) && p->M >= 512 && (p->block_n == 256 || p->block_n == 192 || p->block_n == 128)) {
