@@ -329,67 +329,102 @@ cudaError_t launch_ln_bwd_gen(const float* x, const float* dy, long long rows, i
 //   dS = A o (dA - rowsum(dA o A)); dQ = dS K * scale; dK = dS^T Q * scale.   (vit:99-130)
 // qkv / dqkv rows are [q | k | v] (3*d); dO rows are d wide (merged heads).
 // =================================================================================================
+// One CTA per (sample, head), thread == query in the first phase and == key in the second.  The thread's own q / dO
+// row lives in registers (a [S][DH] shared row read with stride DH is a 16-way bank conflict for DH = 48); K, V, Q, dO
+// rows needed by everyone are read as broadcast float4; the S x S weight / gradient tiles use an odd row stride so
+// that both the row-wise writes and the column-wise reads are conflict-free.  blockDim = S rounded up to a warp.
 template <int DH>
 __global__ void __launch_bounds__(128) k_attention_bwd(const float* __restrict__ qkv, const float* __restrict__ dO,
                                                        int S, int heads, const uint8_t* __restrict__ mask,
                                                        int mask_stride, float* __restrict__ dqkv) {
   extern __shared__ __align__(16) float sm[];
+  const int ST = S | 1;            // odd row stride of the S x S tiles
   float* Qs = sm;                  // [S][DH]
   float* Ks = Qs + S * DH;
   float* Vs = Ks + S * DH;
   float* Gs = Vs + S * DH;         // dO
   float* Km = Gs + S * DH;         // [S]
-  float* As = Km + ((S + 3) & ~3); // [S][S+1]  attention weights
-  float* Ds = As + S * (S + 1);    // [S][S+1]  dS
-  const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
+  float* As = Km + ((S + 3) & ~3); // [S][ST]  attention weights
+  float* Ds = As + S * ST;         // [S][ST]  dS
+  const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x, nt = blockDim.x;
   const int d = heads * DH;
   const long long row0 = (long long)b * S;
-  for (int i = tid; i < S * DH; i += 128) {
-    const int j = i / DH, c = i - j * DH;
+  for (int i = tid; i < S * (DH / 4); i += nt) {
+    const int j = i / (DH / 4), c = (i - j * (DH / 4)) * 4;
     const float* r = qkv + (row0 + j) * 3 * d + h * DH + c;
-    Qs[i] = r[0]; Ks[i] = r[d]; Vs[i] = r[2 * d];
-    Gs[i] = dO[(row0 + j) * d + h * DH + c];
+    *reinterpret_cast<float4*>(Qs + j * DH + c) = *reinterpret_cast<const float4*>(r);
+    *reinterpret_cast<float4*>(Ks + j * DH + c) = *reinterpret_cast<const float4*>(r + d);
+    *reinterpret_cast<float4*>(Vs + j * DH + c) = *reinterpret_cast<const float4*>(r + 2 * d);
+    *reinterpret_cast<float4*>(Gs + j * DH + c) = *reinterpret_cast<const float4*>(dO + (row0 + j) * d + h * DH + c);
   }
-  for (int j = tid; j < S; j += 128)
+  for (int j = tid; j < S; j += nt)
     Km[j] = mask ? (1.0f - (mask[(long long)b * mask_stride + j] ? 1.0f : 0.0f)) * -1e9f : 0.0f;
   __syncthreads();
   const float scale = 1.0f / sqrtf((float)DH);
   if (tid < S) {
     const int i = tid;
+    float* Ai = As + i * ST;
+    float* Di = Ds + i * ST;
     float mx = -INFINITY;
-    for (int j = 0; j < S; ++j) {
-      float a = 0.f;
+    {   // scores and softmax of query i
+      float q[DH];
 #pragma unroll
-      for (int c = 0; c < DH; ++c) a = fmaf(Qs[i * DH + c], Ks[j * DH + c], a);
-      a = a * scale + Km[j];
-      As[i * (S + 1) + j] = a;
-      mx = fmaxf(mx, a);
+      for (int c = 0; c < DH; ++c) q[c] = Qs[i * DH + c];
+      for (int j = 0; j < S; ++j) {
+        const float4* kr = reinterpret_cast<const float4*>(Ks + j * DH);
+        float a = 0.f;
+#pragma unroll
+        for (int c = 0; c < DH / 4; ++c) {
+          const float4 k4 = kr[c];
+          a = fmaf(q[4 * c], k4.x, a); a = fmaf(q[4 * c + 1], k4.y, a);
+          a = fmaf(q[4 * c + 2], k4.z, a); a = fmaf(q[4 * c + 3], k4.w, a);
+        }
+        a = a * scale + Km[j];
+        Ai[j] = a;
+        mx = fmaxf(mx, a);
+      }
     }
     float sum = 0.f;
-    for (int j = 0; j < S; ++j) { const float p = expf(As[i * (S + 1) + j] - mx); As[i * (S + 1) + j] = p; sum += p; }
+    for (int j = 0; j < S; ++j) { const float p = expf(Ai[j] - mx); Ai[j] = p; sum += p; }
     const float inv = 1.f / sum;
     float dot = 0.f;
-    for (int j = 0; j < S; ++j) {
-      const float p = As[i * (S + 1) + j] * inv;
-      float da = 0.f;
+    {   // dA = dO V^T, dot = sum_j dA_j p_j
+      float gq[DH];
 #pragma unroll
-      for (int c = 0; c < DH; ++c) da = fmaf(Gs[i * DH + c], Vs[j * DH + c], da);
-      As[i * (S + 1) + j] = p;
-      Ds[i * (S + 1) + j] = da;
-      dot = fmaf(da, p, dot);
+      for (int c = 0; c < DH; ++c) gq[c] = Gs[i * DH + c];
+      for (int j = 0; j < S; ++j) {
+        const float p = Ai[j] * inv;
+        const float4* vr = reinterpret_cast<const float4*>(Vs + j * DH);
+        float da = 0.f;
+#pragma unroll
+        for (int c = 0; c < DH / 4; ++c) {
+          const float4 v4 = vr[c];
+          da = fmaf(gq[4 * c], v4.x, da); da = fmaf(gq[4 * c + 1], v4.y, da);
+          da = fmaf(gq[4 * c + 2], v4.z, da); da = fmaf(gq[4 * c + 3], v4.w, da);
+        }
+        Ai[j] = p;
+        Di[j] = da;
+        dot = fmaf(da, p, dot);
+      }
     }
     float dq[DH];
 #pragma unroll
     for (int c = 0; c < DH; ++c) dq[c] = 0.f;
     for (int j = 0; j < S; ++j) {
-      const float ds = As[i * (S + 1) + j] * (Ds[i * (S + 1) + j] - dot);
-      Ds[i * (S + 1) + j] = ds;
+      const float ds = Ai[j] * (Di[j] - dot);
+      Di[j] = ds;
+      const float4* kr = reinterpret_cast<const float4*>(Ks + j * DH);
 #pragma unroll
-      for (int c = 0; c < DH; ++c) dq[c] = fmaf(ds, Ks[j * DH + c], dq[c]);
+      for (int c = 0; c < DH / 4; ++c) {
+        const float4 k4 = kr[c];
+        dq[4 * c] = fmaf(ds, k4.x, dq[4 * c]); dq[4 * c + 1] = fmaf(ds, k4.y, dq[4 * c + 1]);
+        dq[4 * c + 2] = fmaf(ds, k4.z, dq[4 * c + 2]); dq[4 * c + 3] = fmaf(ds, k4.w, dq[4 * c + 3]);
+      }
     }
     float* o = dqkv + (row0 + i) * 3 * d + h * DH;
 #pragma unroll
-    for (int c = 0; c < DH; ++c) o[c] = dq[c] * scale;
+    for (int c = 0; c < DH; c += 4)
+      *reinterpret_cast<float4*>(o + c) = make_float4(dq[c] * scale, dq[c + 1] * scale, dq[c + 2] * scale, dq[c + 3] * scale);
   }
   __syncthreads();
   if (tid < S) {
@@ -398,16 +433,24 @@ __global__ void __launch_bounds__(128) k_attention_bwd(const float* __restrict__
 #pragma unroll
     for (int c = 0; c < DH; ++c) { dk[c] = 0.f; dv[c] = 0.f; }
     for (int i = 0; i < S; ++i) {
-      const float ds = Ds[i * (S + 1) + j], p = As[i * (S + 1) + j];
+      const float ds = Ds[i * ST + j], p = As[i * ST + j];
+      const float4* qr = reinterpret_cast<const float4*>(Qs + i * DH);
+      const float4* gr = reinterpret_cast<const float4*>(Gs + i * DH);
 #pragma unroll
-      for (int c = 0; c < DH; ++c) {
-        dk[c] = fmaf(ds, Qs[i * DH + c], dk[c]);
-        dv[c] = fmaf(p, Gs[i * DH + c], dv[c]);
+      for (int c = 0; c < DH / 4; ++c) {
+        const float4 q4 = qr[c], g4 = gr[c];
+        dk[4 * c] = fmaf(ds, q4.x, dk[4 * c]); dk[4 * c + 1] = fmaf(ds, q4.y, dk[4 * c + 1]);
+        dk[4 * c + 2] = fmaf(ds, q4.z, dk[4 * c + 2]); dk[4 * c + 3] = fmaf(ds, q4.w, dk[4 * c + 3]);
+        dv[4 * c] = fmaf(p, g4.x, dv[4 * c]); dv[4 * c + 1] = fmaf(p, g4.y, dv[4 * c + 1]);
+        dv[4 * c + 2] = fmaf(p, g4.z, dv[4 * c + 2]); dv[4 * c + 3] = fmaf(p, g4.w, dv[4 * c + 3]);
       }
     }
     float* o = dqkv + (row0 + j) * 3 * d + h * DH;
 #pragma unroll
-    for (int c = 0; c < DH; ++c) { o[d + c] = dk[c] * scale; o[2 * d + c] = dv[c]; }
+    for (int c = 0; c < DH; c += 4) {
+      *reinterpret_cast<float4*>(o + d + c) = make_float4(dk[c] * scale, dk[c + 1] * scale, dk[c + 2] * scale, dk[c + 3] * scale);
+      *reinterpret_cast<float4*>(o + 2 * d + c) = make_float4(dv[c], dv[c + 1], dv[c + 2], dv[c + 3]);
+    }
   }
 }
 
@@ -415,14 +458,19 @@ cudaError_t launch_attention_bwd(const float* qkv, const float* dO, long long B,
                                  const uint8_t* mask, int mask_stride, float* dqkv, cudaStream_t st) {
   if (B == 0) return cudaSuccess;
   if (S < 1 || S > 128) return cudaErrorInvalidValue;
-  const size_t smem = sizeof(float) * (4 * S * dh + ((S + 3) & ~3) + 2 * S * (S + 1));
+  const size_t smem = sizeof(float) * (4 * S * dh + ((S + 3) & ~3) + 2 * S * (S | 1));
   dim3 grid((unsigned)B, heads);
+  const int threads = (S + 31) / 32 * 32;
 #define UU_AB_CASE(DHV)                                                                                        \
   case DHV: {                                                                                                  \
-    cudaError_t e = cudaFuncSetAttribute(k_attention_bwd<DHV>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                                         (int)smem);                                                           \
-    if (e != cudaSuccess) return e;                                                                            \
-    k_attention_bwd<DHV><<<grid, 128, smem, st>>>(qkv, dO, S, heads, mask, mask_stride, dqkv);                 \
+    static size_t attr_smem = 0;                                                                               \
+    if (smem > attr_smem) {                                                                                    \
+      cudaError_t e = cudaFuncSetAttribute(k_attention_bwd<DHV>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                           (int)smem);                                                         \
+      if (e != cudaSuccess) return e;                                                                          \
+      attr_smem = smem;                                                                                        \
+    }                                                                                                          \
+    k_attention_bwd<DHV><<<grid, threads, smem, st>>>(qkv, dO, S, heads, mask, mask_stride, dqkv);             \
     break;                                                                                                     \
   }
   switch (dh) {
