@@ -190,19 +190,41 @@ def train_bench(a, cfg, spec, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     if rank == 0:
-        print(json.dumps({"metric": "training windows/sec (fwd+bwd+AdamW)", "value": Bg / (ms / 1e3), "unit": "windows/s",
+        emit({"metric": "training windows/sec (fwd+bwd+AdamW)", "value": Bg / (ms / 1e3), "unit": "windows/s",
                           "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms,
                           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                           "data": "synthetic", "loss": float(loss.item()),
                           "config": {"workload": f"config/{a.config}.json training step, global batch {Bg}, mask strides "
                                                  f"{cfg.MASK_STRIDE} drawn per window, DropPath on",
                                      "parallelism": f"data-parallel x{world}, NCCL sum all-reduce of "
-                                                    f"{model.param_count} fp32 gradients"}}))
+                                                    f"{model.param_count} fp32 gradients"}})
     if dist is not None:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Everything libraries print to fd 1 (NCCL's version banner, ...) goes to stderr; the JSON line is written to the
+    saved descriptor, so stdout carries exactly ONE line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj) -> None:
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -233,7 +255,7 @@ def main():
         if rank != 0:
             return
         r = cpu_reference_run(spec, cfg, a.s_in, a.cpu_sample, a.steps, a.warmup, budget_s=150.0)
-        print(json.dumps({
+        emit({
             "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus,
             "steps": r["steps"], "warmup": a.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -241,7 +263,7 @@ def main():
             "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
-        }))
+        })
         return
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
@@ -383,7 +405,7 @@ def main():
         r = cpu_reference_run(spec, cfg, a.s_in, a.cpu_sample, steps=5, warmup=1, budget_s=25.0)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
     if rank == 0:
-        print(json.dumps({
+        emit({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": a.precision, "data": "synthetic",
@@ -394,7 +416,7 @@ def main():
                        "parallelism": f"batch-sharded x{world}, no collective"},
             "clocks": clocks, "e2e": e2e, "e2e_video": e2e_video, "gpu_launches": launches, "roofline": roofline, "kernels": kernels,
             "cpu_baseline": cpu,
-        }))
+        })
     if dist is not None:
         dist.destroy_process_group()
 
