@@ -2,6 +2,7 @@
 #pragma once
 #include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/uu3d.h"
@@ -95,6 +96,18 @@ struct uu_model {
   int plan_full = -1;
   std::vector<TcGemmPlan*> plans;
   int launches = 0;
+
+  // CUDA-graph cache of the device-pointer forward (uu_forward): key = (batch, buffers, stream); the first call with a
+  // key runs eagerly, the second is captured, later ones replay (kernel-to-kernel launch gaps: -3 % at 4096 windows,
+  // -8 % at 512).  Dropped whenever plans / workspace / precision change.
+  struct GraphKey {
+    int B; const void *x, *mask, *full, *central; cudaStream_t st;
+    bool operator<(const GraphKey& o) const {
+      return std::tie(B, x, mask, full, central, st) < std::tie(o.B, o.x, o.mask, o.full, o.central, o.st);
+    }
+  };
+  struct GraphEntry { cudaGraphExec_t exec = nullptr; int seen = 0; bool failed = false; };
+  std::map<GraphKey, GraphEntry> graphs;
 
   // ---- training state (uu_train.cu) ----
   float* grads = nullptr;        // flat, same layout as params

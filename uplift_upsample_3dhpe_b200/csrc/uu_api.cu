@@ -1,6 +1,7 @@
 // C ABI of the uu3d library (include/uu3d.h): model object, weight inventory, forward schedule.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -184,7 +185,15 @@ void free_pool(std::vector<void*>& pool) {
   pool.clear();
 }
 
+static void drop_graphs(uu_model* m) {
+  for (auto& kv : m->graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  m->graphs.clear();
+}
+
 static void drop_plans(uu_model* m) {
+  // (captured graphs stay valid: tensor maps are kernel parameters, copied into the graph nodes; what they point
+  // at — workspace and weight packs — is only released in ensure_workspace / uu_destroy, which drop the cache)
   for (auto* p : m->plans) tc_gemm_plan_destroy(p);
   m->plans.clear();
   m->plan_B = -1;
@@ -194,6 +203,7 @@ static int ensure_workspace(uu_model* m, int B) {
   if (B <= m->cap_B && m->ws_precision == m->precision) return 0;
   const uu_spec& s = m->spec;
   UU_CUDA(cudaDeviceSynchronize());
+  drop_graphs(m);
   free_pool(m->ws_allocs);
   drop_plans(m);
   m->Xs.clear(); m->Hp.clear();
@@ -635,6 +645,7 @@ int uu_destroy(uu_model* m) {
   if (!m) return 0;
   cudaSetDevice(m->device);
   cudaDeviceSynchronize();
+  drop_graphs(m);
   drop_plans(m);
   free_pool(m->ws_allocs);
   free_pool(m->derived_allocs);
@@ -661,6 +672,7 @@ int uu_destroy(uu_model* m) {
 int uu_set_precision(uu_model* m, int precision) {
   UU_CHECK(m, "null model");
   UU_CHECK(precision == UU_PRECISION_FP32 || precision == UU_PRECISION_BF16, "unknown precision");
+  if (precision != m->precision) drop_graphs(m);
   m->precision = precision;
   return 0;
 }
@@ -720,7 +732,44 @@ int uu_get_weight(uu_model* m, const char* group, int index, float* host, int64_
 
 int uu_forward(uu_model* m, const float* x2d, const uint8_t* mask, int B, float* full, float* central, void* stream) {
   UU_CHECK(m, "null model");
-  return run_forward(m, x2d, mask, B, full, central, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  static int use_graphs = -1;
+  if (use_graphs < 0) { const char* e = getenv("UU_GRAPH"); use_graphs = (e && e[0] == '0') ? 0 : 1; }
+  // graph replay needs a capturable (non-legacy) stream, the tcgen05 schedule (fixed launch sequence) and no per-launch events
+  if (!use_graphs || st == nullptr || st == cudaStreamLegacy || m->precision != UU_PRECISION_BF16 || m->profiling || B <= 0)
+    return run_forward(m, x2d, mask, B, full, central, st);
+  UU_CUDA(cudaSetDevice(m->device));
+  if (commit_weights(m)) return 1;                   // derived weights are rebuilt outside any capture
+  if (ensure_workspace(m, B)) return 1;              // (drops the cache when it reallocates)
+  const uu_model::GraphKey key{B, x2d, mask, full, central, st};
+  if (m->graphs.size() > 32 && !m->graphs.count(key)) drop_graphs(m);
+  uu_model::GraphEntry& ge = m->graphs[key];
+  if (ge.exec) {
+    UU_CUDA(cudaGraphLaunch(ge.exec, st));
+    return 0;
+  }
+  if (ge.failed || ge.seen++ == 0) return run_forward(m, x2d, mask, B, full, central, st);   // first sight: eager (builds plans)
+  cudaGraph_t graph = nullptr;
+  if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    ge.failed = true;
+    return run_forward(m, x2d, mask, B, full, central, st);
+  }
+  const int launches = m->launches;
+  const int rc = run_forward(m, x2d, mask, B, full, central, st);
+  const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+  m->launches = launches;
+  if (rc || ce != cudaSuccess || !graph || cudaGraphInstantiate(&ge.exec, graph, 0) != cudaSuccess) {
+    cudaGetLastError();
+    if (graph) cudaGraphDestroy(graph);
+    ge.exec = nullptr;
+    ge.failed = true;
+    if (rc) return rc;
+    return run_forward(m, x2d, mask, B, full, central, st);
+  }
+  cudaGraphDestroy(graph);
+  UU_CUDA(cudaGraphLaunch(ge.exec, st));
+  return 0;
 }
 
 int uu_forward_host(uu_model* m, const float* x2d, const uint8_t* mask, int B, float* full, float* central) {
