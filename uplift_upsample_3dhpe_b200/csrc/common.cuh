@@ -117,9 +117,6 @@ cudaError_t launch_residual_ln_bx(const bf16* xsrc, const RowMap& smap, const bf
                                   const float* gamma, const float* beta, float eps, const float* table, int period,
                                   bf16* y, bf16* xcast, cudaStream_t st);
 
-// fp32 -> bf16 copy of n elements (n % 4 == 0): operand cast for the tensor-core heads
-cudaError_t launch_cast_bf16(const float* x, bf16* y, long long n, cudaStream_t st);
-
 // softmax(q k^T / sqrt(dh) + keymask * -1e9) v per (window, head); qkv rows = [q | k | v] (3*d)
 cudaError_t launch_attention(const void* qkv, int is_bf16, int B, int S, int heads, int dh, const uint8_t* mask,
                              int mask_stride, void* out, cudaStream_t st);

@@ -781,26 +781,6 @@ cudaError_t launch_residual_ln_bx(const bf16* xsrc, const RowMap& smap, const bf
   return cudaGetLastError();
 }
 
-__global__ void k_cast_bf16(const float4* __restrict__ x, uint2* __restrict__ y, long long n4) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    float4 v = x[i];
-    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-    uint2 pk;
-    pk.x = *reinterpret_cast<uint32_t*>(&lo);
-    pk.y = *reinterpret_cast<uint32_t*>(&hi);
-    y[i] = pk;
-  }
-}
-
-cudaError_t launch_cast_bf16(const float* x, bf16* y, long long n, cudaStream_t st) {
-  if (n == 0) return cudaSuccess;
-  if (n % 4) return cudaErrorInvalidValue;
-  long long n4 = n / 4;
-  int grid = (int)std::min<long long>((n4 + 255) / 256, 148 * 16);
-  k_cast_bf16<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<uint2*>(y), n4);
-  return cudaGetLastError();
-}
-
 // =================================================================================================
 // K5 (CUDA-core version): softmax attention per (window, head), S <= 128 keys, thread == query.
 // Literal reference arithmetic: logits = q.k / sqrt(dh) + keymask * -1e9 in fp32 (vit:117-123), so

@@ -458,6 +458,7 @@ static int run_forward_impl(uu_model* m, const float* x2d, const uint8_t* mask, 
     return 0;
   }
 
+  // ---- fp32 ("exact") schedule: CUDA-core kernels, fp32 activations -----------------------------------------
   // K1a: gather list of frames that carry a 2-D pose
   if (use_mask) {
     UU_LAUNCH(f, UU_KIND_GATHER, 3, launch_build_gather(mask, B, N, m->g_scratch, m->g_list, m->g_count, st));
@@ -470,13 +471,7 @@ static int run_forward_impl(uu_model* m, const float* x2d, const uint8_t* mask, 
   sp.pe = W(m, "spatial_pe", 0); sp.blocks = m->spatial_ptrs;
   sp.norm_g = W(m, "spatial_norm", 0); sp.norm_b = W(m, "spatial_norm", 1);
   sp.out = m->S; sp.out_bf16 = bf;
-  if (f.tc) {
-    UU_LAUNCH(f, UU_KIND_SPATIAL, 1,
-              launch_spatial_tc(x2d, sp.list, sp.count, R, s.spatial_depth, m->sp_frags, m->sp_params, (bf16*)m->S,
-                                m->num_sms, st));
-  } else {
-    UU_LAUNCH(f, UU_KIND_SPATIAL, 1, launch_spatial_f32(sp, st));
-  }
+  UU_LAUNCH(f, UU_KIND_SPATIAL, 1, launch_spatial_f32(sp, st));
   // S4 + T1: 544->384 GEMM, rows scattered to their token position, + bias + temporal PE
   {
     Epilogue e;
@@ -507,12 +502,7 @@ static int run_forward_impl(uu_model* m, const float* x2d, const uint8_t* mask, 
   if (s.full_output && full) {
     Epilogue e;
     e.bias = W(m, "temporal_fc", 1);
-    const void* A = m->X;
-    if (f.tc) {   // the tensor-core GEMM wants a bf16 operand: cast the fp32 residual stream into Y
-      UU_LAUNCH(f, UU_KIND_CAST, 1, launch_cast_bf16(m->X, (bf16*)m->Y, (long long)R * d, st));
-      A = m->Y;
-    }
-    if (gemm(f, A, d, R, d, W(m, "temporal_fc", 0), m->p_head1, 3 * J, e, full, 0, 3 * J)) return 1;
+    if (gemm(f, m->X, d, R, d, W(m, "temporal_fc", 0), m->p_head1, 3 * J, e, full, 0, 3 * J)) return 1;
   }
   // Q1/Q2: strided transformer blocks (net:122-160)
   float* x_in = m->X;
@@ -547,14 +537,8 @@ static int run_forward_impl(uu_model* m, const float* x2d, const uint8_t* mask, 
   {
     Epilogue e;
     e.bias = W(m, "strided_temporal_fc", 1);
-    const void* A = x_in;
-    if (f.tc) {
-      UU_LAUNCH(f, UU_KIND_CAST, 1, launch_cast_bf16(x_in, (bf16*)m->Y, (long long)B * d, st));
-      A = m->Y;
-    }
-    if (gemm(f, A, d, B, d, W(m, "strided_temporal_fc", 0), m->p_head2, 3 * J, e, central, 0, 3 * J)) return 1;
+    if (gemm(f, x_in, d, B, d, W(m, "strided_temporal_fc", 0), m->p_head2, 3 * J, e, central, 0, 3 * J)) return 1;
   }
-  if (f.tc) { m->plan_B = B; m->plan_full = want_full; }
   m->launches = f.launches;
   return 0;
 }
