@@ -57,8 +57,9 @@ typedef struct uu_spec {
 } uu_spec;
 
 /* Arithmetic of the dense contractions. */
-enum { UU_PRECISION_FP32 = 0,    /* CUDA-core fp32, <= 1e-4 abs of the fp32 oracle           */
-       UU_PRECISION_BF16 = 1 };  /* tcgen05 bf16 x bf16 -> fp32, fp32 residual stream / LN / softmax */
+enum { UU_PRECISION_FP32 = 0,    /* CUDA-core fp32 end to end, <= 1e-4 abs of the reference's float32 outputs */
+       UU_PRECISION_BF16 = 1 };  /* bf16 operands on tensor cores (tcgen05 / mma.sync), fp32 accumulation; LayerNorm,
+                                    softmax and residual adds in fp32 registers, activations stored as bf16 */
 
 const char* uu_last_error(void);
 int uu_version(void);
@@ -82,13 +83,15 @@ int uu_get_weight(uu_model* m, const char* group, int index, float* host, int64_
  *            (equivalent to the caller-side mask multiply of eval.py:67).
  *   mask   : uint8 (B, n_tok), non-zero on tokens that carry a 2-D pose; may be NULL when the
  *            model has no strided input.
- *   full   : fp32 (B, n_tok, n_joints, 3) or NULL;  central : fp32 (B, n_joints, 3). */
+ *   full   : fp32 (B, n_tok, n_joints, 3) or NULL;  central : fp32 (B, n_joints, 3).
+ * On a capturable stream (not NULL / legacy) the bf16 schedule is captured into a CUDA graph the second time a
+ * (B, buffers, stream) combination is seen and replayed afterwards (UU_GRAPH=0 disables); results are identical. */
 int uu_forward(uu_model* m, const float* x2d, const uint8_t* mask, int B, float* full, float* central, void* stream);
-/* Same call with HOST buffers (pinned recommended): H2D copy, forward, D2H copy, stream sync.
+/* Same call with HOST buffers (pinned recommended): H2D copy (for large bf16 batches in chunks on a second stream,
+ * overlapped with the spatial kernel of the previous chunk), forward, D2H copy, stream sync.
  * full == NULL: the full-sequence head still runs on the device (as in the reference) but is not copied back. */
 int uu_forward_host(uu_model* m, const float* x2d, const uint8_t* mask, int B, float* full, float* central);
 
-/* Number of kernels of this library launched by the most recent forward on `m`. */
 /* Sliding windows cut ON THE DEVICE from one video (replaces the host-side window
  * materialisation of common/dataset/uplifiting_dataset.py:341-394 + eval.py:63-71 — a 71x input blow-up).
  * video2d: (T, n_joints, 2) float; centers: B int32 frame indices in [0, T).  Window b, token k reads frame
@@ -119,6 +122,7 @@ int uu_op_keyframe_interp(const float* pred, const int32_t* frame_indices, int n
 int uu_op_window_gather(const float* video2d, int T, const int32_t* centers, int B, int n_tok, int n_joints, int s_out,
                         int s_in, int pad_copy, int32_t* src, uint8_t* mask, float* x2d, void* stream);
 
+/* Number of kernels of this library launched by the most recent forward on `m`. */
 int uu_last_launch_count(const uu_model* m);
 
 /* Per-kernel-kind device timing of the most recent forward: with profiling on, every launch is
