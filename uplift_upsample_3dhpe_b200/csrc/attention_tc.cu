@@ -49,12 +49,15 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 // K feeds the B operand of Q K^T through ldmatrix, V the B operand of P V through ldmatrix.trans, so no
 // explicit transposition is ever stored.  The output tile goes back through the warp's own (already
 // consumed) Q rows and leaves as 16-byte row chunks.
-template <int DH, int ST>
+// SKIP_LAST: the last 8-key tile holds only padding (S <= 16*ST - 8, e.g. S = 71 with ST = 5): its scores are not
+// computed and its probabilities are zero.
+template <int DH, int ST, bool SKIP_LAST>
 __global__ void __launch_bounds__(32 * ST) k_attention_tc(const bf16* __restrict__ qkv, int S, int heads,
                                                           const uint8_t* __restrict__ mask, int mask_stride,
                                                           bf16* __restrict__ out) {
   constexpr int SP = 16 * ST;            // padded sequence
   constexpr int NT = SP / 8;             // key n-tiles of the score matrix
+  constexpr int NTV = SKIP_LAST ? NT - 1 : NT;   // tiles that can hold a valid key
   constexpr int RS = DH + 8;             // row stride (bf16)
   constexpr int CH = DH / 8;             // 16-byte chunks per head row
   extern __shared__ __align__(16) uint8_t att_smem[];
@@ -102,8 +105,9 @@ __global__ void __launch_bounds__(32 * ST) k_attention_tc(const bf16* __restrict
     for (int kk = 0; kk < DH / 16; ++kk) ldsm_x4(aq[kk], qb + 16 * kk);
   }
   float sc[NT][4];
+  if constexpr (SKIP_LAST) sc[NT - 1][0] = sc[NT - 1][1] = sc[NT - 1][2] = sc[NT - 1][3] = 0.f;   // p = 0 for the padding tile
 #pragma unroll
-  for (int j = 0; j < NT; ++j) {
+  for (int j = 0; j < NTV; ++j) {
     sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
     const bf16* kb = Ks + (8 * j + (lane & 7)) * RS + (lane >> 3) * 8;
 #pragma unroll
@@ -127,7 +131,7 @@ __global__ void __launch_bounds__(32 * ST) k_attention_tc(const bf16* __restrict
   const float scale = LOG2E / sqrtf((float)DH);
   float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
-  for (int j = 0; j < NT; ++j) {
+  for (int j = 0; j < NTV; ++j) {
     const float2 km = *reinterpret_cast<const float2*>(Km + 8 * j + 2 * t);
     sc[j][0] = fmaf(sc[j][0], scale, km.x); sc[j][1] = fmaf(sc[j][1], scale, km.y);
     sc[j][2] = fmaf(sc[j][2], scale, km.x); sc[j][3] = fmaf(sc[j][3], scale, km.y);
@@ -138,7 +142,7 @@ __global__ void __launch_bounds__(32 * ST) k_attention_tc(const bf16* __restrict
   m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
   float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-  for (int j = 0; j < NT; ++j) {
+  for (int j = 0; j < NTV; ++j) {
     sc[j][0] = ex2_att(sc[j][0] - m0); sc[j][1] = ex2_att(sc[j][1] - m0);
     sc[j][2] = ex2_att(sc[j][2] - m1); sc[j][3] = ex2_att(sc[j][3] - m1);
     l0 += sc[j][0] + sc[j][1];
@@ -196,12 +200,17 @@ static cudaError_t att_tc_dh(const bf16* qkv, int B, int S, int heads, const uin
     if (smem > 48 * 1024) {                                                                          \
       static bool attr = false;                                                                      \
       if (!attr) {                                                                                   \
-        cudaError_t e = cudaFuncSetAttribute(k_attention_tc<DH, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+        cudaError_t e = cudaFuncSetAttribute(k_attention_tc<DH, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+        if (e != cudaSuccess) return e;                                                              \
+        e = cudaFuncSetAttribute(k_attention_tc<DH, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
         if (e != cudaSuccess) return e;                                                              \
         attr = true;                                                                                 \
       }                                                                                              \
     }                                                                                                \
-    k_attention_tc<DH, T><<<grid, 32 * T, smem, st>>>(qkv, S, heads, mask, mask_stride, out);        \
+    if (S <= 16 * T - 8)                                                                             \
+      k_attention_tc<DH, T, true><<<grid, 32 * T, smem, st>>>(qkv, S, heads, mask, mask_stride, out); \
+    else                                                                                             \
+      k_attention_tc<DH, T, false><<<grid, 32 * T, smem, st>>>(qkv, S, heads, mask, mask_stride, out); \
   } break;
   switch (tiles) {
     UU_ATT_CASE(1) UU_ATT_CASE(2) UU_ATT_CASE(3) UU_ATT_CASE(4)
