@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(st::THREADS, 1) k_spatial_tc(SpatialTcParams p
   uint2* s_frag = reinterpret_cast<uint2*>(smem_raw);                              // depth*72*32 uint2
   float* s_par = reinterpret_cast<float*>(smem_raw + sizeof(uint2) * p.depth * F_TOTAL * 32);
   uint8_t* s_x = reinterpret_cast<uint8_t*>(s_par + ((p.depth * P_TOTAL + G_TOTAL + 3) & ~3));
-  bf16* xq16 = reinterpret_cast<bf16*>(s_x + X_Q);      // [16 frames][32] joint-16 q (exp2 domain)
+  bf16* xq16 = reinterpret_cast<bf16*>(s_x + X_Q);      // [16 rows: 15 frames + 1 unused][32] joint-16 q (exp2 domain)
   bf16* xk16 = reinterpret_cast<bf16*>(s_x + X_K);      // [16][32]
   bf16* xv16 = reinterpret_cast<bf16*>(s_x + X_V);      // [16][8 heads][v0,1,v1,1,v2,1,v3,1]
   float* xs16 = reinterpret_cast<float*>(s_x + X_S);    // [16][8] score of (query 16, key 16)
@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(st::THREADS, 1) k_spatial_tc(SpatialTcParams p
         else { vt[tile - 8][0] = pack2h(c[0], c[1]); vt[tile - 8][1] = pack2h(c[2], c[3]); }
       }
       if (w16) {
-        // joint 16 of 16 frames: publish q, k, v and the (query 16, key 16) scores
+        // joint 16 of the 15 frames (row 15 unused): publish q, k, v and the (query 16, key 16) scores
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           *reinterpret_cast<uint32_t*>(xq16 + g * 32 + 8 * j + 2 * t) = qa[j][0];
