@@ -17,7 +17,7 @@ for (name, N, K) in [("qkv", 1152, 384), ("proj", 384, 384), ("fc1", 768, 384), 
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        _lib.check(lib.uu_op_gemm_bf16(P(A), K, M, K, P(Wt), N, N, P(bias), 0, None, 0, P(C), 1, N, None))
+        _lib.check(lib.uu_op_gemm_bf16(P(A), K, M, K, P(Wt), N, N, None if os.environ.get("NOBIAS") else P(bias), 0, None, 0, P(C), 1, N, None))
         e1.record()
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))

@@ -54,6 +54,10 @@ enum EpiFlags : int {
   EPI_RELU = 1,       // max(., 0) after bias
   EPI_RESIDUAL = 2,   // += Res[map_row(rmap, r)][col]
   EPI_ROWTABLE = 4,   // += table[(crow % table_period)][col]   (temporal positional encoding)
+  // tcgen05 TMA-store epilogue only (bf16 schedule, temporal blocks):
+  EPI_LNFOLD = 8,     // the GEMM consumed the raw residual stream with gamma folded into W:
+                      //   out = rstd[r] * (acc - mean[r] * csum[col]) + bias'[col]   ( == LN(x) W + b )
+  EPI_RESID_BF16 = 16 // out = acc + bias + res_bf16[r][col], rounded to bf16; optional row statistics of the result
 };
 
 // Epilogue description shared by the SIMT and the tcgen05 GEMM.
@@ -68,6 +72,14 @@ struct Epilogue {
   const int* c_rowidx = nullptr;     // optional scatter list: physical output row of logical row r
   const int* m_dev = nullptr;        // optional device-side row count (<= M)
   RowMap cmap;                       // output row mapping (ignored when c_rowidx is set)
+  // LayerNorm folded into the GEMMs.  Row statistics travel as per-row partials [rows][ln_slots][2] =
+  // (sum, sum of squares) over 64-column slots of the bf16 residual stream, summed in slot order by the consumer.
+  const float* ln_stats = nullptr;   // EPI_LNFOLD: partials of the A rows
+  const float* ln_csum = nullptr;    // EPI_LNFOLD: [N] column sums of the folded bf16 weight
+  int ln_slots = 0;
+  float ln_inv_k = 0.f, ln_eps = 0.f;
+  const bf16* res_bf16 = nullptr;    // EPI_RESID_BF16: residual rows, same row index and pitch as the output
+  float* stats_out = nullptr;        // EPI_RESID_BF16: partials of the rows written, [rows][N / 64][2] (optional)
 };
 
 // ---- kernel launchers (kernels_f32.cu) --------------------------------------------------------
@@ -105,17 +117,12 @@ cudaError_t launch_token_fill(const uint8_t* mask, int rows, int n_tok, int d, c
 cudaError_t launch_layernorm(float* x, int rows, int d, const float* gamma, const float* beta, float eps,
                              const float* table, int period, void* y, int y_bf16, cudaStream_t st);
 
-// bf16 path: v = xsrc[map(r)] + upd[r]; xcast = bf16(v) (opt); v += table[r % period] (opt); xdst = v; y = LN(v) (opt)
-cudaError_t launch_residual_ln(const float* xsrc, const RowMap& smap, const bf16* upd, float* xdst, int rows, int d,
-                               const float* gamma, const float* beta, float eps, const float* table, int period,
-                               bf16* y, bf16* xcast, cudaStream_t st);
-
 // bf16-resident residual stream variants (X stored as bf16; arithmetic fp32).  upd / xdst / y / xcast optional.
 cudaError_t launch_token_fill_bx(const uint8_t* mask, int rows, int n_tok, int d, const float* token, const float* pe,
                                  bf16* x, cudaStream_t st);
 cudaError_t launch_residual_ln_bx(const bf16* xsrc, const RowMap& smap, const bf16* upd, bf16* xdst, int rows, int d,
                                   const float* gamma, const float* beta, float eps, const float* table, int period,
-                                  bf16* y, bf16* xcast, cudaStream_t st);
+                                  bf16* y, bf16* xcast, cudaStream_t st, float* stats = nullptr, int slots = 0);
 
 // softmax(q k^T / sqrt(dh) + keymask * -1e9) v per (window, head); qkv rows = [q | k | v] (3*d)
 cudaError_t launch_attention(const void* qkv, int is_bf16, int B, int S, int heads, int dh, const uint8_t* mask,

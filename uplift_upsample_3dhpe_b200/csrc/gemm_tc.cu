@@ -121,21 +121,72 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
          | ((uint32_t)(M >> 4) << 24);  // m_dim
 }
 
-// BS_KB > 0 selects the B-STATIONARY schedule: the CTA keeps its whole [BLOCK_N x K] weight tile (BS_KB k-block
-// panels) resident in shared memory, owns one column block for its lifetime and streams only A.  With M >> N the
-// streaming schedule re-reads the weight tile once per 128-row tile (QKV: 2.0 GB of L2 -> SM traffic per call on
-// top of 1.3 GB of A), which pins these short-K GEMMs to the ~12 TB/s L2 -> SM ceiling; B-stationary removes that term.
 // Epilogue of one warp for one tile (bf16 output): sub-tiles first, first+2, ... of its 32 accumulator rows go
 // TMEM -> registers -> bias / ReLU / bf16 -> private swizzled staging tile -> cp.async.bulk.tensor store of a
 // [32 x 64] box.  `release` is called right after the warp's last TMEM read of the tile.
 // Row scatter (epi.c_rowidx: the compact valid-frame rows of the 544 -> 384 GEMM go to their token rows): the list is
 // ascending, so the 32 rows of a warp almost always land on 32 consecutive destination rows and still leave as one
 // TMA box; otherwise (a masked frame inside the run, or the ragged end of the list) every lane writes its own row.
-template <int BLOCK_N, int NBUF, typename Release>
+// Global-memory inputs of one warp's epilogue for one tile, fetched BEFORE the warp waits for the accumulator so their
+// latency hides behind the MMA main loop: the row statistics of a folded LayerNorm and the residual line of the first
+// sub-tile (the following sub-tiles' lines are fetched while the previous one is being stored).
+struct EpiPre {
+  float mu = 0.f, rstd = 1.f;
+  uint4 rres[8];
+};
+__device__ __forceinline__ void epi_load_residual(EpiPre& pre, const Epilogue& epi, int row, int col, int m_eff, long long ldc) {
+  const uint4* rp = reinterpret_cast<const uint4*>(epi.res_bf16 + (long long)row * ldc + col);
+#pragma unroll
+  for (int g = 0; g < 8; ++g) pre.rres[g] = row < m_eff ? rp[g] : make_uint4(0u, 0u, 0u, 0u);
+}
+template <int EMODE>
+__device__ __forceinline__ void epi_prefetch(EpiPre& pre, const Epilogue& epi, int row_q0, int col0, int first, int lane,
+                                             int m_eff, long long ldc) {
+  const int my_row = row_q0 + lane;
+  if constexpr (EMODE == 1) {
+    float s1 = 0.f, s2 = 0.f;
+    if (my_row < m_eff) {
+      const float2* sp = reinterpret_cast<const float2*>(epi.ln_stats) + (long long)my_row * epi.ln_slots;
+      for (int i = 0; i < epi.ln_slots; ++i) {
+        const float2 t = sp[i];
+        s1 += t.x; s2 += t.y;
+      }
+    }
+    pre.mu = s1 * epi.ln_inv_k;
+    pre.rstd = rsqrtf(fmaxf(s2 * epi.ln_inv_k - pre.mu * pre.mu, 0.f) + epi.ln_eps);
+  }
+  if constexpr (EMODE == 2) epi_load_residual(pre, epi, my_row, col0 + first * 64, m_eff, ldc);
+}
+
+// Packed fp32 pairs (sm_100 FFMA2 / FADD2): the epilogue is issue-bound on 8 warps, these halve its arithmetic.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
+        "l"(*reinterpret_cast<unsigned long long*>(&c)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 bf16x2_to_f2(uint32_t u) { return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)); }
+
+// EMODE selects the epilogue at compile time (runtime flag tests inside the 8-column loop doubled its instruction count):
+//   EMODE_PLAIN  out = acc (+ bias) (ReLU)
+//   EMODE_LNFOLD out = rstd * acc + ((-rstd * mean) * csum + bias') (ReLU)      two FFMA2 per column pair
+//   EMODE_RESID  out = acc + bias + residual, row partial sums of out and out^2 for the next folded LayerNorm
+constexpr int EMODE_PLAIN = 0, EMODE_LNFOLD = 1, EMODE_RESID = 2;
+
+template <int BLOCK_N, int NBUF, int EMODE, typename Release>
 __device__ __forceinline__ void epi_warp_store_tile(uint32_t tmem_acc, int first, uint8_t* my_stage, uint32_t& my_count,
                                                     const Epilogue& epi, const CUtensorMap* map_c, int row_q0, int col0,
-                                                    int lane, Release release, int m_eff = 0x7fffffff,
-                                                    bf16* c_ptr = nullptr, long long ldc = 0) {
+                                                    int lane, Release release, EpiPre& pre, int m_eff, bf16* c_ptr,
+                                                    long long ldc) {
   constexpr int NSUB = BLOCK_N / 64;
   int dst_row = row_q0;                      // first destination row of the TMA box
   bool boxed = true;
@@ -146,9 +197,14 @@ __device__ __forceinline__ void epi_warp_store_tile(uint32_t tmem_acc, int first
     dst_row = __shfl_sync(0xffffffffu, my_dst, 0);
     boxed = __all_sync(0xffffffffu, my_dst >= 0 && my_dst == dst_row + lane);
   }
+  const int my_row = row_q0 + lane;
+  const float2 a1 = make_float2(pre.rstd, pre.rstd), a2 = make_float2(-pre.rstd * pre.mu, -pre.rstd * pre.mu);
+  const bool relu = (epi.flags & EPI_RELU) != 0;
+  const bool has_bias = epi.bias != nullptr;
 #pragma unroll 1
   for (int sub = first; sub < NSUB; sub += 2, ++my_count) {
     uint8_t* sbuf = my_stage + (my_count % NBUF) * (32 * 128);
+    float2 st_s = make_float2(0.f, 0.f), st_q = make_float2(0.f, 0.f);
     uint32_t v0[32], v1[32];
     tmem_ld_32x32b_x32(tmem_acc + (uint32_t)(sub * 64), v0);
     tmem_ld_32x32b_x32(tmem_acc + (uint32_t)(sub * 64 + 32), v1);
@@ -162,25 +218,55 @@ __device__ __forceinline__ void epi_warp_store_tile(uint32_t tmem_acc, int first
 #pragma unroll
     for (int g = 0; g < 8; ++g) {           // 8 columns -> one 16-byte chunk
       const int cb = col0 + sub * 64 + 8 * g;
-      float o[8];
+      float2 o[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(g < 4 ? v0[8 * g + i] : v1[8 * (g - 4) + i]);
-      if (epi.bias) {
+      for (int i = 0; i < 4; ++i)
+        o[i] = g < 4 ? make_float2(__uint_as_float(v0[8 * g + 2 * i]), __uint_as_float(v0[8 * g + 2 * i + 1]))
+                     : make_float2(__uint_as_float(v1[8 * (g - 4) + 2 * i]), __uint_as_float(v1[8 * (g - 4) + 2 * i + 1]));
+      if constexpr (EMODE == EMODE_LNFOLD) {
+        const float4 c0 = __ldg(reinterpret_cast<const float4*>(epi.ln_csum + cb));
+        const float4 c1 = __ldg(reinterpret_cast<const float4*>(epi.ln_csum + cb + 4));
         const float4 b0 = __ldg(reinterpret_cast<const float4*>(epi.bias + cb));
         const float4 b1 = __ldg(reinterpret_cast<const float4*>(epi.bias + cb + 4));
-        o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w;
-        o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
+        o[0] = ffma2(a1, o[0], ffma2(a2, make_float2(c0.x, c0.y), make_float2(b0.x, b0.y)));
+        o[1] = ffma2(a1, o[1], ffma2(a2, make_float2(c0.z, c0.w), make_float2(b0.z, b0.w)));
+        o[2] = ffma2(a1, o[2], ffma2(a2, make_float2(c1.x, c1.y), make_float2(b1.x, b1.y)));
+        o[3] = ffma2(a1, o[3], ffma2(a2, make_float2(c1.z, c1.w), make_float2(b1.z, b1.w)));
+      } else if (EMODE == EMODE_RESID || has_bias) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(epi.bias + cb));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(epi.bias + cb + 4));
+        o[0] = fadd2(o[0], make_float2(b0.x, b0.y)); o[1] = fadd2(o[1], make_float2(b0.z, b0.w));
+        o[2] = fadd2(o[2], make_float2(b1.x, b1.y)); o[3] = fadd2(o[3], make_float2(b1.z, b1.w));
       }
-      if (epi.flags & EPI_RELU) {
+      if constexpr (EMODE != EMODE_RESID) {
+        if (relu) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = fmaxf(o[i], 0.f);
+          for (int i = 0; i < 4; ++i) o[i] = make_float2(fmaxf(o[i].x, 0.f), fmaxf(o[i].y, 0.f));
+        }
+      } else {
+        const uint4 r = pre.rres[g];
+        o[0] = fadd2(o[0], bf16x2_to_f2(r.x)); o[1] = fadd2(o[1], bf16x2_to_f2(r.y));
+        o[2] = fadd2(o[2], bf16x2_to_f2(r.z)); o[3] = fadd2(o[3], bf16x2_to_f2(r.w));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          st_s = fadd2(st_s, o[i]);
+          st_q = ffma2(o[i], o[i], st_q);
+        }
       }
-      __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
-      __nv_bfloat162 p2 = __floats2bfloat162_rn(o[4], o[5]), p3 = __floats2bfloat162_rn(o[6], o[7]);
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0].x, o[0].y), p1 = __floats2bfloat162_rn(o[1].x, o[1].y);
+      __nv_bfloat162 p2 = __floats2bfloat162_rn(o[2].x, o[2].y), p3 = __floats2bfloat162_rn(o[3].x, o[3].y);
       uint4 pk;
       pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
       pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
       *reinterpret_cast<uint4*>(sbuf + lane * 128 + ((g ^ (lane & 7)) << 4)) = pk;
+    }
+    if constexpr (EMODE == EMODE_RESID) {
+      // (statistics of the fp32 sums before the bf16 rounding: the difference to the stored values is far below the
+      // bf16 resolution of the normalised output)
+      if (epi.stats_out && my_row < m_eff)
+        reinterpret_cast<float2*>(epi.stats_out)[(long long)my_row * epi.ln_slots + ((col0 >> 6) + sub)] =
+            make_float2(st_s.x + st_s.y, st_q.x + st_q.y);
+      if (sub + 2 < NSUB) epi_load_residual(pre, epi, my_row, col0 + (sub + 2) * 64, m_eff, ldc);   // next sub-tile's line
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async proxy
     __syncwarp();
@@ -200,23 +286,20 @@ __device__ __forceinline__ void epi_warp_store_tile(uint32_t tmem_acc, int first
   }
 }
 
-template <int BLOCK_N, int BS_KB = 0>
+template <int BLOCK_N>
 struct TcCfg {
   static constexpr int A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;   // 16 KB
   static constexpr int B_BYTES = BLOCK_N * TC_BLOCK_K * 2;
-  static constexpr int B_RES_BYTES = BS_KB * B_BYTES;            // resident weight panels (B-stationary only)
-  static constexpr int STAGE_BYTES = BS_KB ? A_BYTES : A_BYTES + B_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   // epilogue scratch: per-warp TMA-store staging, 8 warps x NBUF x 4 KB (+ alignment); the generic fp32 transpose
-  // tiles (36 KB) fit in the same region.  B-stationary keeps one staging tile per warp to leave room for the A ring.
-  static constexpr int EPI_NBUF = BS_KB ? 1 : 2;
-  static constexpr int EPI_BYTES = BS_KB ? 8 * 32 * 128 + 1024 : TC_EPI_SMEM;
-  static constexpr int STAGES_BS = (227 * 1024 - B_RES_BYTES - EPI_BYTES - 1280) / A_BYTES;
-  static constexpr int STAGES = BS_KB ? (STAGES_BS < 8 ? STAGES_BS : 8)
-                                      : ((160 * 1024) / STAGE_BYTES < 8 ? (160 * 1024) / STAGE_BYTES : 8);
+  // tiles (36 KB) fit in the same region.
+  static constexpr int EPI_NBUF = 2;
+  static constexpr int EPI_BYTES = TC_EPI_SMEM;
+  static constexpr int STAGES = (160 * 1024) / STAGE_BYTES < 8 ? (160 * 1024) / STAGE_BYTES : 8;
   static constexpr int ACC_STAGES = 2;                           // double-buffered accumulator in TMEM
   static constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N <= 32 ? 32 : ACC_STAGES * BLOCK_N <= 64 ? 64
                                    : ACC_STAGES * BLOCK_N <= 128 ? 128 : ACC_STAGES * BLOCK_N <= 256 ? 256 : 512;
-  static constexpr int SMEM_BYTES = B_RES_BYTES + STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
   static_assert(ACC_STAGES * BLOCK_N <= 512, "accumulator stages exceed TMEM");
   static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024-byte alignment for the 128B swizzle");
@@ -225,43 +308,35 @@ struct TcCfg {
 // Persistent, warp-specialised: every CTA walks the tile list t = blockIdx.x, += gridDim.x with
 // (m_blk, n_blk) = (t / n_tiles, t % n_tiles), so CTAs running concurrently share the same A rows in L2.
 // Three pipelines: smem ring (TMA -> MMA), TMEM accumulator ring (MMA -> epilogue), tile list.
-template <int BLOCK_N, typename TC, bool TMA_OUT, int BS_KB = 0>
+template <int BLOCK_N, typename TC, bool TMA_OUT, int EMODE = 0>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant__ CUtensorMap map_a,
                                                            const __grid_constant__ CUtensorMap map_b,
                                                            const __grid_constant__ CUtensorMap map_c, int M, int N,
                                                            int n_tiles, int K, Epilogue epi, TC* __restrict__ C,
                                                            long long ldc) {
-  using Cfg = TcCfg<BLOCK_N, BS_KB>;
-  constexpr bool BS = BS_KB > 0;
+  using Cfg = TcCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   const int m_eff = epi.m_dev ? min(M, *epi.m_dev) : M;
   const int m_tiles = (m_eff + TC_BLOCK_M - 1) / TC_BLOCK_M;
   const int total_tiles = m_tiles * n_tiles;
-  // tile walk: streaming = (t / n_tiles, t % n_tiles) over t = blockIdx.x, += gridDim.x;
-  // B-stationary = fixed column block blockIdx.x % n_tiles, row blocks blockIdx.x / n_tiles, += gridDim.x / n_tiles
-  // (the host sizes the grid as a multiple of n_tiles), expressed as the same linear walk with a stride that is
-  // a multiple of n_tiles so t % n_tiles never changes.
-  const int tile_first = BS ? (blockIdx.x / n_tiles) * n_tiles + (blockIdx.x % n_tiles) : blockIdx.x;
+  const int tile_first = blockIdx.x;
   const int tile_step = gridDim.x;
 
   uint8_t* smem_al = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_bres = smem_al;                           // resident weight panels (B-stationary)
-  uint8_t* smem = smem_al + Cfg::B_RES_BYTES;             // operand ring
+  uint8_t* smem = smem_al;                                // operand ring
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
   uint64_t* tmem_full_bar = empty_bar + Cfg::STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + Cfg::ACC_STAGES;
-  uint64_t* bres_bar = tmem_empty_bar + Cfg::ACC_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_bar + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + Cfg::ACC_STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_kb = BS ? BS_KB : (K + TC_BLOCK_K - 1) / TC_BLOCK_K;
+  const int num_kb = (K + TC_BLOCK_K - 1) / TC_BLOCK_K;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     if constexpr (TMA_OUT) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
-    mbar_init(bres_bar, 1);
     for (int s = 0; s < Cfg::STAGES; ++s) {
       mbar_init(full_bar + s, 1);
       mbar_init(empty_bar + s, 1);
@@ -287,14 +362,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
     // ---------------- TMA producer ----------------
     if (lane == 0) {
       uint32_t it = 0;                        // running k-block counter across tiles -> stage / phase
-      if constexpr (BS) {                     // the CTA's weight tile, once: BS_KB panels of [BLOCK_N x 64]
-        if (tile_first < total_tiles) {
-          const int col0 = (tile_first % n_tiles) * BLOCK_N;
-          mbar_expect_tx(bres_bar, Cfg::B_RES_BYTES);
-          for (int kb = 0; kb < BS_KB; ++kb)
-            tma_load_2d(smem_bres + kb * Cfg::B_BYTES, &map_b, bres_bar, kb * TC_BLOCK_K, col0);
-        }
-      }
       int s = 0;
       uint32_t ph = 0;
       for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
@@ -308,6 +375,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
             const int prow = (nt / n_tiles) * TC_BLOCK_M;
             for (int kb = 0; kb < num_kb; ++kb) tma_prefetch_2d(&map_a, kb * TC_BLOCK_K, prow);
           }
+          if constexpr (TMA_OUT && EMODE == EMODE_RESID) {
+            // residual rows of this CTA's next tile (the output map describes the same matrix): the epilogue's
+            // row-per-lane loads then hit L2 instead of paying the DRAM latency in front of a sub-tile
+            if (nt < total_tiles && !(epi.flags & 256)) {
+              const int prow = (nt / n_tiles) * TC_BLOCK_M, pcol = (nt % n_tiles) * BLOCK_N;
+              for (int r = 0; r < TC_BLOCK_M; r += 32)
+                for (int c = 0; c < BLOCK_N; c += 64) tma_prefetch_2d(&map_c, pcol + c, prow + r);
+            }
+          }
         }
         for (int kb = 0; kb < num_kb; ++kb, ++it, s = (s + 1 == Cfg::STAGES ? 0 : s + 1), ph ^= (s == 0)) {
           mbar_wait(empty_bar + s, ph ^ 1);
@@ -318,7 +394,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
           }
           mbar_expect_tx(full_bar + s, Cfg::STAGE_BYTES);
           tma_load_2d(a_dst, &map_a, full_bar + s, kb * TC_BLOCK_K, row0);
-          if constexpr (!BS) tma_load_2d(a_dst + Cfg::A_BYTES, &map_b, full_bar + s, kb * TC_BLOCK_K, col0);
+          tma_load_2d(a_dst + Cfg::A_BYTES, &map_b, full_bar + s, kb * TC_BLOCK_K, col0);
         }
       }
     }
@@ -332,12 +408,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
     {
       constexpr uint32_t idesc = make_idesc_bf16(TC_BLOCK_M, BLOCK_N);
       const uint64_t a_desc0 = make_sw128_desc(smem_u32(smem));
-      const uint64_t b_desc0 = BS ? make_sw128_desc(smem_u32(smem_bres)) : make_sw128_desc(smem_u32(smem + Cfg::A_BYTES));
+      const uint64_t b_desc0 = make_sw128_desc(smem_u32(smem + Cfg::A_BYTES));
       int s = 0;
       uint32_t ph = 0, tcount = 0;
-      if constexpr (BS) {
-        if (tile_first < total_tiles) mbar_wait(bres_bar, 0);   // weight tile resident
-      }
       for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++tcount) {
         const int as = tcount & 1;
         const uint32_t aph = (tcount >> 1) & 1;
@@ -350,7 +423,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
           tcgen05_fence_after();
           if (elect_one()) {
             const uint64_t a_desc = a_desc0 + (uint64_t)((s * Cfg::STAGE_BYTES) >> 4);
-            const uint64_t b_desc = b_desc0 + (uint64_t)(BS ? ((kb * Cfg::B_BYTES) >> 4) : ((s * Cfg::STAGE_BYTES) >> 4));
+            const uint64_t b_desc = b_desc0 + (uint64_t)((s * Cfg::STAGE_BYTES) >> 4);
 #pragma unroll
             for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
               // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (>>4) address field
@@ -389,20 +462,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
         const int row0 = (tile / n_tiles) * TC_BLOCK_M, col0 = (tile % n_tiles) * BLOCK_N;
         const int as = tcount % Cfg::ACC_STAGES;
         const uint32_t aph = (tcount / Cfg::ACC_STAGES) & 1;
+        // sub-tiles of this warp: those with (sub + tcount) % 2 == hsel (alternating start balances odd NSUB)
+        const int first = (hsel + (int)tcount) & 1;
+        EpiPre pre;
+        if (first < NSUB) epi_prefetch<EMODE>(pre, epi, row0 + q * 32, col0, first, lane, m_eff, ldc);
         mbar_wait(tmem_full_bar + as, aph);
         tcgen05_fence_after();
         const uint32_t tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N);
-        // sub-tiles of this warp: those with (sub + tcount) % 2 == hsel (alternating start balances odd NSUB)
-        const int first = (hsel + (int)tcount) & 1;
         if (first >= NSUB) {                    // nothing to do for this tile (only possible for NSUB == 1)
           tcgen05_fence_before();
           if (lane == 0) mbar_arrive(tmem_empty_bar + as);
           continue;
         }
-        epi_warp_store_tile<BLOCK_N, Cfg::EPI_NBUF>(tmem_acc, first, my_stage, my_count, epi, &map_c, row0 + q * 32, col0, lane, [&] {
+        epi_warp_store_tile<BLOCK_N, Cfg::EPI_NBUF, EMODE>(tmem_acc, first, my_stage, my_count, epi, &map_c, row0 + q * 32, col0, lane, [&] {
           tcgen05_fence_before();
           if (lane == 0) mbar_arrive(tmem_empty_bar + as);
-        }, m_eff, reinterpret_cast<bf16*>(C), ldc);
+        }, pre, m_eff, reinterpret_cast<bf16*>(C), ldc);
       }
       if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     } else {
@@ -567,10 +642,11 @@ struct Tc2Cfg {
   static_assert(BLOCK_N % 32 == 0 && BLOCK_N <= 256, "UMMA M=256 needs N % 16 == 0, N <= 256");
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, int EMODE = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     k_gemm_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const __grid_constant__ CUtensorMap map_c, int M, int n_tiles, int K, Epilogue epi) {
+               const __grid_constant__ CUtensorMap map_c, int M, int n_tiles, int K, Epilogue epi,
+               bf16* __restrict__ C, long long ldc) {
   using Cfg = Tc2Cfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   const int m_pairs = (M + 2 * TC_BLOCK_M - 1) / (2 * TC_BLOCK_M);
@@ -627,6 +703,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           if (nt < total_tiles && (nt % n_tiles) == 0 && !(epi.flags & 256)) {
             const int prow = (nt / n_tiles) * (2 * TC_BLOCK_M) + (int)rank * TC_BLOCK_M;
             for (int kb = 0; kb < num_kb; ++kb) tma_prefetch_2d(&map_a, kb * TC_BLOCK_K, prow);
+          }
+          if constexpr (EMODE == EMODE_RESID) {      // residual rows of this CTA's half of the next tile
+            if (nt < total_tiles && !(epi.flags & 256)) {
+              const int prow = (nt / n_tiles) * (2 * TC_BLOCK_M) + (int)rank * TC_BLOCK_M, pcol = (nt % n_tiles) * BLOCK_N;
+              for (int r = 0; r < TC_BLOCK_M; r += 32)
+                for (int c = 0; c < BLOCK_N; c += 64) tma_prefetch_2d(&map_c, pcol + c, prow + r);
+            }
           }
         }
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
@@ -688,16 +771,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       const int col0 = (tile % n_tiles) * BLOCK_N;
       const int as = tcount % Cfg::ACC_STAGES;
       const uint32_t aph = (tcount / Cfg::ACC_STAGES) & 1;
+      const int first = (hsel + (int)tcount) & 1;
+      EpiPre pre;
+      if (first < NSUB) epi_prefetch<EMODE>(pre, epi, row0 + q * 32, col0, first, lane, M, ldc);
       mbar_wait(tmem_full_bar + as, aph);
       tcgen05_fence_after();
       const uint32_t tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N);
-      const int first = (hsel + (int)tcount) & 1;
       auto release = [&] {                     // hand the accumulator back to the leader's MMA thread
         tcgen05_fence_before();
         if (lane == 0) mbar_arrive_cluster(mapa_rank(tmem_empty_bar + as, 0));
       };
       if (first >= NSUB) { release(); continue; }
-      epi_warp_store_tile<BLOCK_N, 2>(tmem_acc, first, my_stage, my_count, epi, &map_c, row0 + q * 32, col0, lane, release);
+      epi_warp_store_tile<BLOCK_N, 2, EMODE>(tmem_acc, first, my_stage, my_count, epi, &map_c, row0 + q * 32, col0, lane, release,
+                                      pre, M, C, ldc);
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
@@ -752,7 +838,6 @@ static int encode_2d(CUtensorMap* map, const void* base, uint64_t cols, uint64_t
 struct TcGemmPlan {
   CUtensorMap map_a, map_b, map_c;
   CUtensorMap map_b2;               // 2-CTA variant: box of block_n / 2 rows of W^T
-  CUtensorMap map_bs;               // B-stationary variant: box of 128 rows of W^T (valid when N_pad % 128 == 0)
   int M, N, N_pad, K, block_n;
   const void* c_ptr = nullptr;      // output the store map was encoded for
   long long c_ld = 0;
@@ -778,10 +863,6 @@ int tc_gemm_plan_create(TcGemmPlan** out, const bf16* A, long long lda, int M, i
     delete p;
     return 1;
   }
-  if (N_pad % 128 == 0 && encode_2d(&p->map_bs, Wt, (uint64_t)K, (uint64_t)N_pad, (uint64_t)K, TC_BLOCK_K, 128)) {
-    delete p;
-    return 1;
-  }
   if (encode_2d(&p->map_b2, Wt, (uint64_t)K, (uint64_t)N_pad, (uint64_t)K, TC_BLOCK_K, (uint32_t)p->block_n / 2)) {
     delete p;
     return 1;
@@ -794,12 +875,12 @@ void tc_gemm_plan_destroy(TcGemmPlan* p) { delete p; }
 
 static int g_num_sms = 0;
 
-template <int BLOCK_N, typename TC, bool TMA_OUT>
+template <int BLOCK_N, typename TC, bool TMA_OUT, int EMODE = 0>
 static cudaError_t tc_launch_t(const TcGemmPlan* p, const Epilogue& epi, void* C, long long ldc, cudaStream_t st) {
   using Cfg = TcCfg<BLOCK_N>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BLOCK_N, TC, TMA_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BLOCK_N, TC, TMA_OUT, EMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
@@ -812,42 +893,17 @@ static cudaError_t tc_launch_t(const TcGemmPlan* p, const Epilogue& epi, void* C
   const int n_tiles = p->N_pad / BLOCK_N;
   const int total = ((p->M + TC_BLOCK_M - 1) / TC_BLOCK_M) * n_tiles;
   const int grid = total < g_num_sms ? total : g_num_sms;          // persistent: one CTA per SM
-  k_gemm_tc<BLOCK_N, TC, TMA_OUT><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(
+  k_gemm_tc<BLOCK_N, TC, TMA_OUT, EMODE><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(
       p->map_a, p->map_b, p->map_c, p->M, p->N, n_tiles, p->K, epi, reinterpret_cast<TC*>(C), ldc);
   return cudaGetLastError();
 }
 
-// B-stationary launch: grid = n_tiles * floor(SMs / n_tiles) so that every CTA keeps one column block
-template <int BLOCK_N, int BS_KB>
-static cudaError_t tc_launch_bs(const TcGemmPlan* p, const Epilogue& epi, void* C, long long ldc, cudaStream_t st) {
-  using Cfg = TcCfg<BLOCK_N, BS_KB>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BLOCK_N, bf16, true, BS_KB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
-  const int n_tiles = p->N_pad / BLOCK_N;
-  const int m_tiles = (p->M + TC_BLOCK_M - 1) / TC_BLOCK_M;
-  int per_col = g_num_sms / n_tiles;
-  if (per_col > m_tiles) per_col = m_tiles;
-  k_gemm_tc<BLOCK_N, bf16, true, BS_KB><<<n_tiles * per_col, TC_THREADS, Cfg::SMEM_BYTES, st>>>(
-      p->map_a, p->map_bs, p->map_c, p->M, p->N, n_tiles, p->K, epi, reinterpret_cast<bf16*>(C), ldc);
-  return cudaGetLastError();
-}
-
-template <int BLOCK_N>
-static cudaError_t tc2_launch_t(const TcGemmPlan* p, const Epilogue& epi, cudaStream_t st) {
+template <int BLOCK_N, int EMODE = 0>
+static cudaError_t tc2_launch_t(const TcGemmPlan* p, const Epilogue& epi, void* C, long long ldc, cudaStream_t st) {
   using Cfg = Tc2Cfg<BLOCK_N>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_gemm_tc2<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_tc2<BLOCK_N, EMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -859,7 +915,8 @@ static cudaError_t tc2_launch_t(const TcGemmPlan* p, const Epilogue& epi, cudaSt
   const int n_tiles = p->N_pad / BLOCK_N;
   const int total = ((p->M + 2 * TC_BLOCK_M - 1) / (2 * TC_BLOCK_M)) * n_tiles;
   const int clusters = total < g_num_sms / 2 ? total : g_num_sms / 2;      // persistent: one CTA pair per TPC
-  k_gemm_tc2<BLOCK_N><<<2 * clusters, TC_THREADS, Cfg::SMEM_BYTES, st>>>(p->map_a, p->map_b2, p->map_c, p->M, n_tiles, p->K, epi);
+  k_gemm_tc2<BLOCK_N, EMODE><<<2 * clusters, TC_THREADS, Cfg::SMEM_BYTES, st>>>(p->map_a, p->map_b2, p->map_c, p->M, n_tiles, p->K, epi,
+                                                                          reinterpret_cast<bf16*>(C), ldc);
   return cudaGetLastError();
 }
 
@@ -872,6 +929,8 @@ static bool tma_out_eligible(const TcGemmPlan* p, const Epilogue& epi, int c_bf1
 }
 
 cudaError_t tc_gemm_launch(TcGemmPlan* p, const Epilogue& epi_in, void* C, int c_bf16, long long ldc, cudaStream_t st) {
+  if ((epi_in.flags & (EPI_LNFOLD | EPI_RESID_BF16)) && !tma_out_eligible(p, epi_in, c_bf16, ldc))
+    return cudaErrorInvalidValue;     // folded-LayerNorm / bf16-residual epilogues exist on the TMA-store path only
   static int nostore = -1;
   if (nostore < 0) { const char* e = getenv("UU_GEMM_NOSTORE"); nostore = (e && e[0] == '1') ? 1 : 0; }
   Epilogue epi = epi_in;
@@ -895,17 +954,33 @@ cudaError_t tc_gemm_launch(TcGemmPlan* p, const Epilogue& epi_in, void* C, int c
       const char* e = getenv("UU_GEMM_2CTA");
       g_use_2cta = e ? (e[0] == '1' ? 1 : 0) : 2;   // default (2): only where it measured faster, the K >= 768 GEMMs
     }
-    static int use_bs = -1;
-    if (use_bs < 0) { const char* e = getenv("UU_GEMM_BSTAT"); use_bs = (e && e[0] == '1') ? 1 : 0; }   // default off: measured no faster
-    // short-K GEMMs with M >> N: keep the weight tile resident (K = 384 -> 6 panels of a 128-wide column block)
     const bool scatter = epi.c_rowidx || epi.m_dev || epi.cmap.rpb != 0x7fffffff;
-    if (!scatter && use_bs && p->K == 384 && p->N_pad % 128 == 0 && p->M >= 4 * TC_BLOCK_M * (p->N_pad / 128))
-      return tc_launch_bs<128, 6>(p, epi, C, ldc, st);
-    if (!scatter && (g_use_2cta == 1 || (g_use_2cta == 2 && p->K >= 768)) && p->M >= 512 && (p->block_n == 256 || p->block_n == 192 || p->block_n == 128)) {
+    const bool two_cta = !scatter && (g_use_2cta == 1 || (g_use_2cta == 2 && p->K >= 768)) && p->M >= 512;
+    // folded-LayerNorm / residual epilogues (temporal blocks): 128-, 192- and 256-wide tiles only
+    if (epi.flags & EPI_LNFOLD) {
+      if (!epi.bias || !epi.ln_stats || !epi.ln_csum || (epi.flags & EPI_RESID_BF16)) return cudaErrorInvalidValue;
       switch (p->block_n) {
-        case 256: return tc2_launch_t<256>(p, epi, st);
-        case 192: return tc2_launch_t<192>(p, epi, st);
-        default: return tc2_launch_t<128>(p, epi, st);
+        case 256: return tc_launch_t<256, bf16, true, EMODE_LNFOLD>(p, epi, C, ldc, st);
+        case 192: return tc_launch_t<192, bf16, true, EMODE_LNFOLD>(p, epi, C, ldc, st);
+        case 128: return tc_launch_t<128, bf16, true, EMODE_LNFOLD>(p, epi, C, ldc, st);
+        default: return cudaErrorInvalidValue;
+      }
+    }
+    if (epi.flags & EPI_RESID_BF16) {
+      // (in place only: the producer warp prefetches the residual through the output's tensor map)
+      if (!epi.bias || epi.res_bf16 != C || scatter || (epi.flags & EPI_RELU)) return cudaErrorInvalidValue;
+      switch (p->block_n) {
+        case 256: return two_cta ? tc2_launch_t<256, EMODE_RESID>(p, epi, C, ldc, st) : tc_launch_t<256, bf16, true, EMODE_RESID>(p, epi, C, ldc, st);
+        case 192: return two_cta ? tc2_launch_t<192, EMODE_RESID>(p, epi, C, ldc, st) : tc_launch_t<192, bf16, true, EMODE_RESID>(p, epi, C, ldc, st);
+        case 128: return two_cta ? tc2_launch_t<128, EMODE_RESID>(p, epi, C, ldc, st) : tc_launch_t<128, bf16, true, EMODE_RESID>(p, epi, C, ldc, st);
+        default: return cudaErrorInvalidValue;
+      }
+    }
+    if (two_cta && (p->block_n == 256 || p->block_n == 192 || p->block_n == 128)) {
+      switch (p->block_n) {
+        case 256: return tc2_launch_t<256>(p, epi, C, ldc, st);
+        case 192: return tc2_launch_t<192>(p, epi, C, ldc, st);
+        default: return tc2_launch_t<128>(p, epi, C, ldc, st);
       }
     }
     switch (p->block_n) {

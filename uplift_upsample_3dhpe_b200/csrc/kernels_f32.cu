@@ -563,105 +563,13 @@ cudaError_t launch_layernorm(float* x, int rows, int d, const float* gamma, cons
 }
 
 // =================================================================================================
-// K4b (bf16 path): residual add + LayerNorm in one streaming pass, one warp per row.
-//   v = xsrc[map(r)] + bf16 update[r]        (update = projection / MLP / strided-conv output)
+// bf16-resident residual stream (bf16 schedule): streaming kernels with X stored as bf16 between kernels
+// (statistics, adds and the LayerNorm arithmetic stay fp32), one warp per row:
+//   v = xsrc[map(r)] (+ bf16 update[r])      (update = strided-conv / projection output)
 //   xcast[r] = bf16(v)                       (optional: operand of the regression heads)
-//   v += table[r % period]                   (optional: positional encoding of the next strided block)
-//   xdst[r] = v ; y[r] = bf16(LN(v))         (y optional)
+//   v += table[r % period]                   (optional: positional encoding)
+//   xdst[r] = v ; y[r] = bf16(LN(v))         (both optional)
 // xsrc may be a different, longer sequence than xdst (strided identity path x[:, c0::s], net:146-152).
-// =================================================================================================
-template <int V>
-__global__ void k_residual_ln(const float* __restrict__ xsrc, RowMap smap, const bf16* __restrict__ upd,
-                              float* __restrict__ xdst, int rows, const float* __restrict__ gamma,
-                              const float* __restrict__ beta, float eps, const float* __restrict__ table, int period,
-                              bf16* __restrict__ y, bf16* __restrict__ xcast) {
-  constexpr int D = V * 128;
-  const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const long long srow = map_row(smap, row);
-  const float4* xr = reinterpret_cast<const float4*>(xsrc + srow * D);
-  const uint2* ur = reinterpret_cast<const uint2*>(upd + (long long)row * D);
-  float4 v[V];
-#pragma unroll
-  for (int i = 0; i < V; ++i) {
-    v[i] = xr[lane + 32 * i];
-    const uint2 u = ur[lane + 32 * i];
-    const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&u.x), hi = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
-    v[i].x += __low2float(lo); v[i].y += __high2float(lo); v[i].z += __low2float(hi); v[i].w += __high2float(hi);
-  }
-  if (xcast) {
-    uint2* cr = reinterpret_cast<uint2*>(xcast + (long long)row * D);
-#pragma unroll
-    for (int i = 0; i < V; ++i) {
-      __nv_bfloat162 lo = __floats2bfloat162_rn(v[i].x, v[i].y), hi = __floats2bfloat162_rn(v[i].z, v[i].w);
-      uint2 pk;
-      pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
-      cr[lane + 32 * i] = pk;
-    }
-  }
-  if (table) {
-    const float4* tr = reinterpret_cast<const float4*>(table + (long long)(row % period) * D);
-#pragma unroll
-    for (int i = 0; i < V; ++i) {
-      const float4 t = tr[lane + 32 * i];
-      v[i].x += t.x; v[i].y += t.y; v[i].z += t.z; v[i].w += t.w;
-    }
-  }
-  float4* xo = reinterpret_cast<float4*>(xdst + (long long)row * D);
-#pragma unroll
-  for (int i = 0; i < V; ++i) xo[lane + 32 * i] = v[i];
-  if (!y) return;
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < V; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-  const float mean = warp_sum(s) * (1.f / D);
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < V; ++i) {
-    float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-    q += (a * a + b * b) + (c * c + d * d);
-  }
-  const float rstd = rsqrtf(warp_sum(q) * (1.f / D) + eps);
-  const float4* g4 = reinterpret_cast<const float4*>(gamma);
-  const float4* b4 = reinterpret_cast<const float4*>(beta);
-  uint2* yr = reinterpret_cast<uint2*>(y + (long long)row * D);
-#pragma unroll
-  for (int i = 0; i < V; ++i) {
-    const float4 g = g4[lane + 32 * i], b = b4[lane + 32 * i];
-    const float o0 = v[i].x * (g.x * rstd) + (b.x - mean * (g.x * rstd));
-    const float o1 = v[i].y * (g.y * rstd) + (b.y - mean * (g.y * rstd));
-    const float o2 = v[i].z * (g.z * rstd) + (b.z - mean * (g.z * rstd));
-    const float o3 = v[i].w * (g.w * rstd) + (b.w - mean * (g.w * rstd));
-    __nv_bfloat162 lo = __floats2bfloat162_rn(o0, o1), hi = __floats2bfloat162_rn(o2, o3);
-    uint2 pk;
-    pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
-    yr[lane + 32 * i] = pk;
-  }
-}
-
-cudaError_t launch_residual_ln(const float* xsrc, const RowMap& smap, const bf16* upd, float* xdst, int rows, int d,
-                               const float* gamma, const float* beta, float eps, const float* table, int period,
-                               bf16* y, bf16* xcast, cudaStream_t st) {
-  if (rows == 0) return cudaSuccess;
-  const int wpb = 8, grid = (rows + wpb - 1) / wpb;
-#define UU_RLN_CASE(VV)                                                                                        \
-  case VV * 128:                                                                                               \
-    k_residual_ln<VV><<<grid, wpb * 32, 0, st>>>(xsrc, smap, upd, xdst, rows, gamma, beta, eps, table, period, \
-                                                 y, xcast);                                                    \
-    break;
-  switch (d) {
-    UU_RLN_CASE(1) UU_RLN_CASE(2) UU_RLN_CASE(3) UU_RLN_CASE(4) UU_RLN_CASE(6) UU_RLN_CASE(8)
-    default: return cudaErrorInvalidValue;
-  }
-#undef UU_RLN_CASE
-  return cudaGetLastError();
-}
-
-// =================================================================================================
-// bf16-resident residual stream (bf16 schedule): the same three streaming kernels with X stored as bf16
-// between kernels (statistics, adds and the LayerNorm arithmetic stay fp32).  Halves the dominant HBM
-// stream of the temporal blocks (the fp32 X round trip was 2/3 of the residual+LN traffic).
 // =================================================================================================
 __device__ __forceinline__ float4 ld_bf16x4(const bf16* p) {
   const uint2 u = *reinterpret_cast<const uint2*>(p);
@@ -706,7 +614,8 @@ template <int V>
 __global__ void k_residual_ln_bx(const bf16* __restrict__ xsrc, RowMap smap, const bf16* __restrict__ upd,
                                  bf16* __restrict__ xdst, int rows, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, float eps, const float* __restrict__ table, int period,
-                                 bf16* __restrict__ y, bf16* __restrict__ xcast) {
+                                 bf16* __restrict__ y, bf16* __restrict__ xcast, float* __restrict__ stats,
+                                 int slots) {
   constexpr int D = V * 128;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -740,6 +649,21 @@ __global__ void k_residual_ln_bx(const bf16* __restrict__ xsrc, RowMap smap, con
 #pragma unroll
     for (int i = 0; i < V; ++i) st_bf16x4(xdst + (long long)row * D + (lane + 32 * i) * 4, v[i].x, v[i].y, v[i].z, v[i].w);
   }
+  if (stats) {
+    // Row statistics for the GEMMs that fold the next LayerNorm (EPI_LNFOLD): (sum, sum of squares) of the row AS
+    // STORED (bf16-rounded), in slot 0 of the row's partials; the other slots are cleared.
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float a = __bfloat162float(__float2bfloat16_rn(v[i].x)), b = __bfloat162float(__float2bfloat16_rn(v[i].y));
+      const float c = __bfloat162float(__float2bfloat16_rn(v[i].z)), d = __bfloat162float(__float2bfloat16_rn(v[i].w));
+      s1 += (a + b) + (c + d);
+      s2 += (a * a + b * b) + (c * c + d * d);
+    }
+    s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if (lane < slots)
+      reinterpret_cast<float2*>(stats)[(long long)row * slots + lane] = lane == 0 ? make_float2(s1, s2) : make_float2(0.f, 0.f);
+  }
   if (!y) return;
   float s = 0.f;
 #pragma unroll
@@ -765,13 +689,14 @@ __global__ void k_residual_ln_bx(const bf16* __restrict__ xsrc, RowMap smap, con
 
 cudaError_t launch_residual_ln_bx(const bf16* xsrc, const RowMap& smap, const bf16* upd, bf16* xdst, int rows, int d,
                                   const float* gamma, const float* beta, float eps, const float* table, int period,
-                                  bf16* y, bf16* xcast, cudaStream_t st) {
+                                  bf16* y, bf16* xcast, cudaStream_t st, float* stats, int slots) {
   if (rows == 0) return cudaSuccess;
+  if (stats && (slots < 1 || slots > 32)) return cudaErrorInvalidValue;
   const int wpb = 8, grid = (rows + wpb - 1) / wpb;
 #define UU_RLN_CASE(VV)                                                                                           \
   case VV * 128:                                                                                                  \
     k_residual_ln_bx<VV><<<grid, wpb * 32, 0, st>>>(xsrc, smap, upd, xdst, rows, gamma, beta, eps, table, period, \
-                                                    y, xcast);                                                    \
+                                                    y, xcast, stats, slots);                                      \
     break;
   switch (d) {
     UU_RLN_CASE(1) UU_RLN_CASE(2) UU_RLN_CASE(3) UU_RLN_CASE(4) UU_RLN_CASE(6) UU_RLN_CASE(8)

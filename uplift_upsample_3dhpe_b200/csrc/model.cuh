@@ -31,6 +31,10 @@ struct BlockW {        // one temporal / strided block
   // w2: fc2 (h, d) or strided conv (3, h, d) == [3h, d]
   const float *wp = nullptr, *bp = nullptr, *w1 = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr;
   Pack p_qkv, p_proj, p_fc1, p_fc2;
+  // temporal blocks, bf16 schedule: LayerNorm folded into the consuming GEMM (EPI_LNFOLD).
+  //   p_*_ln = bf16((gamma (.) W)^T), cs_* = column sums of that bf16 matrix, bl_* = b + beta W
+  Pack p_qkv_ln, p_fc1_ln;
+  float *cs_qkv = nullptr, *bl_qkv = nullptr, *cs_fc1 = nullptr, *bl_fc1 = nullptr;
 };
 
 }  // namespace uu
@@ -75,6 +79,7 @@ struct uu_model {
   int* d_centers = nullptr;
   int video_cap = 0, centers_cap = 0;
   void *S = nullptr, *Y = nullptr, *QKV = nullptr, *O = nullptr, *Hd = nullptr, *P = nullptr;
+  float* ln_stats = nullptr;   // bf16 schedule: LayerNorm row partials [R][d / 64][2] (see Epilogue::ln_stats)
   float* X = nullptr;
   std::vector<float*> Xs;      // strided stream after block i: [cap_B * seq_lens[i+1], d]
   std::vector<void*> Hp;       // zero-padded conv inputs: [cap_B * Lo*s, h]

@@ -102,6 +102,32 @@ __global__ void k_pack_wt(const float* __restrict__ Wm, int K, int N, int n_pad,
   }
 }
 
+// LayerNorm folded into a GEMM: Wt[n][k] = bf16(gamma[k] W[k][n]); csum[n] = sum_k Wt[n][k] (of the rounded values, so
+// that rstd (x Wt - mean csum) is exactly the GEMM of the centred row); bias_out[n] = bias[n] + sum_k beta[k] W[k][n].
+// One warp per output column n.
+__global__ void k_pack_wt_ln(const float* __restrict__ Wm, int K, int N, int n_pad, const float* __restrict__ gamma,
+                             const float* __restrict__ beta, const float* __restrict__ bias, bf16* __restrict__ Wt,
+                             float* __restrict__ csum, float* __restrict__ bias_out) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (n >= n_pad) return;
+  float cs = 0.f, bb = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float w = n < N ? Wm[(long long)k * N + n] : 0.f;
+    const bf16 q = __float2bfloat16_rn(w * gamma[k]);
+    Wt[(long long)n * K + k] = q;
+    cs += __bfloat162float(q);
+    bb += beta[k] * w;
+  }
+  for (int o = 16; o; o >>= 1) {
+    cs += __shfl_xor_sync(0xffffffffu, cs, o);
+    bb += __shfl_xor_sync(0xffffffffu, bb, o);
+  }
+  if (lane == 0) {
+    csum[n] = cs;
+    bias_out[n] = (n < N ? bias[n] : 0.f) + bb;
+  }
+}
+
 int dev_alloc(std::vector<void*>& pool, void** p, size_t bytes, bool zero) {
   UU_CUDA(cudaMalloc(p, bytes ? bytes : 16));
   pool.push_back(*p);
@@ -117,6 +143,23 @@ static int make_pack(uu_model* m, Pack& pk, const float* Wsrc, int K, int N) {
     pk.ptr = (bf16*)p;
   }
   k_pack_wt<<<256, 256>>>(Wsrc, K, N, pk.n_pad, pk.ptr);
+  UU_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int make_pack_ln(uu_model* m, Pack& pk, float*& csum, float*& bias_out, const float* Wsrc, int K, int N,
+                        const float* gamma, const float* beta, const float* bias) {
+  pk.k = K; pk.n = N; pk.n_pad = (N + 63) / 64 * 64;
+  if (!pk.ptr) {
+    void* p;
+    if (dev_alloc(m->derived_allocs, &p, sizeof(bf16) * (size_t)pk.n_pad * K, false)) return 1;
+    pk.ptr = (bf16*)p;
+    if (dev_alloc(m->derived_allocs, &p, sizeof(float) * pk.n_pad, false)) return 1;
+    csum = (float*)p;
+    if (dev_alloc(m->derived_allocs, &p, sizeof(float) * pk.n_pad, false)) return 1;
+    bias_out = (float*)p;
+  }
+  k_pack_wt_ln<<<(pk.n_pad + 7) / 8, 256>>>(Wsrc, K, N, pk.n_pad, gamma, beta, bias, pk.ptr, csum, bias_out);
   UU_CUDA(cudaGetLastError());
   return 0;
 }
@@ -140,6 +183,10 @@ static int setup_block(uu_model* m, BlockW& b, const std::string& g, int d, int 
   if (make_pack(m, b.p_proj, b.wp, d, d)) return 1;
   if (make_pack(m, b.p_fc1, b.w1, d, h)) return 1;
   if (make_pack(m, b.p_fc2, b.w2, strided ? 3 * h : h, d)) return 1;
+  if (!strided) {
+    if (make_pack_ln(m, b.p_qkv_ln, b.cs_qkv, b.bl_qkv, b.wqkv, d, 3 * d, b.ln1_g, b.ln1_b, b.bqkv)) return 1;
+    if (make_pack_ln(m, b.p_fc1_ln, b.cs_fc1, b.bl_fc1, b.w1, d, h, b.ln2_g, b.ln2_b, b.b1)) return 1;
+  }
   return 0;
 }
 
@@ -224,6 +271,10 @@ static int ensure_workspace(uu_model* m, int B) {
   if (dev_alloc(m->ws_allocs, &m->O, es * R * dt, true)) return 1;
   if (dev_alloc(m->ws_allocs, &m->Hd, es * R * ht, true)) return 1;
   if (m->precision == UU_PRECISION_BF16 && dev_alloc(m->ws_allocs, &m->P, es * R * dt, true)) return 1;
+  if (m->precision == UU_PRECISION_BF16) {
+    if (dev_alloc(m->ws_allocs, &p, sizeof(float) * 2 * R * (dt / 64), true)) return 1;
+    m->ln_stats = (float*)p;
+  }
   for (int i = 0; i < s.n_strided; ++i) {
     const size_t Lo = m->seq_lens[i + 1];
     if (dev_alloc(m->ws_allocs, &p, 4 * (size_t)cap * Lo * dt, true)) return 1;
@@ -368,29 +419,41 @@ static int run_forward_bf16(Fwd& f, const float* x2d, const uint8_t* mask, float
       UU_LAUNCH(f, UU_KIND_TOKEN_FILL, 1,
                 launch_token_fill_bx(mask, R, N, d, W(m, "strided_input_token_layer", 0), nullptr, X, st));
   }
-  UU_LAUNCH(f, UU_KIND_LAYERNORM, 1,
-            launch_residual_ln_bx(X, plain, nullptr, X, R, d, m->tblocks[0].ln1_g, m->tblocks[0].ln1_b, 1e-5f,
-                                  W(m, "temporal_pe", 0), N, Y, nullptr, st));
+  // Temporal blocks (T2/T3).  Neither LayerNorm nor the residual adds are kernels of their own: the QKV and fc1 GEMMs
+  // read the bf16 residual stream directly with gamma folded into their weights and finish the normalisation in the
+  // epilogue from per-row statistics (EPI_LNFOLD); the projection and fc2 GEMMs add the residual in their epilogue,
+  // write the stream in place and emit the statistics of the rows they wrote (EPI_RESID_BF16).
+  const int slots = d / 64;
+  UU_CHECK(d % 64 == 0 && slots <= 32, "temporal width must be a multiple of 64 (<= 2048)");
+  UU_LAUNCH(f, UU_KIND_LAYERNORM, 1,     // + temporal PE (net:352), statistics for the first QKV GEMM
+            launch_residual_ln_bx(X, plain, nullptr, X, R, d, nullptr, nullptr, 1e-5f, W(m, "temporal_pe", 0), N, nullptr,
+                                  nullptr, st, m->ln_stats, slots));
+  auto ln_gemm = [&](const Pack& pk, int n_out, const float* bias_ln, const float* csum, bool relu, bf16* out) {
+    Epilogue e;
+    e.bias = bias_ln; e.flags = EPI_LNFOLD | (relu ? EPI_RELU : 0);
+    e.ln_stats = m->ln_stats; e.ln_csum = csum; e.ln_slots = slots; e.ln_inv_k = 1.f / d; e.ln_eps = 1e-5f;
+    return gemm(f, X, d, R, d, nullptr, pk, n_out, e, out, 1, n_out);
+  };
+  auto resid_gemm = [&](const bf16* A, int K, const Pack& pk, const float* bias) {
+    Epilogue e;
+    e.bias = bias; e.flags = EPI_RESID_BF16;
+    e.res_bf16 = X; e.stats_out = m->ln_stats; e.ln_slots = slots;
+    return gemm(f, A, K, R, K, nullptr, pk, d, e, X, 1, d);
+  };
   for (int i = 0; i < s.temporal_depth; ++i) {
     const BlockW& w = m->tblocks[i];
     const uint8_t* km = (use_mask && i < s.first_strided_token_attention_layer) ? mask : nullptr;
-    if (tc_gemm_bf16(f, Y, d, R, d, w.p_qkv, 3 * d, w.bqkv, false, QKV, 3 * d)) return 1;
+    if (ln_gemm(w.p_qkv_ln, 3 * d, w.bl_qkv, w.cs_qkv, false, QKV)) return 1;
     UU_LAUNCH(f, UU_KIND_ATTENTION, 1, launch_attention_tc(QKV, B, N, H, dh, km, N, O, st));
-    if (tc_gemm_bf16(f, O, d, R, d, w.p_proj, d, w.bp, false, P, d)) return 1;
+    if (resid_gemm(O, d, w.p_proj, w.bp)) return 1;
+    if (ln_gemm(w.p_fc1_ln, h, w.bl_fc1, w.cs_fc1, true, Hd)) return 1;
+    if (resid_gemm(Hd, h, w.p_fc2, w.b2)) return 1;
+  }
+  {   // bf16 copy for the full-sequence head, then + PE_1 and LN1 of strided block 1
+    const BlockW& nx = m->sblocks[0];
     UU_LAUNCH(f, UU_KIND_LAYERNORM, 1,
-              launch_residual_ln_bx(X, plain, P, X, R, d, w.ln2_g, w.ln2_b, 1e-5f, nullptr, 1, Y, nullptr, st));
-    if (tc_gemm_bf16(f, Y, d, R, d, w.p_fc1, h, w.b1, true, Hd, h)) return 1;
-    if (tc_gemm_bf16(f, Hd, h, R, h, w.p_fc2, d, w.b2, false, P, d)) return 1;
-    if (i + 1 < s.temporal_depth) {
-      const BlockW& nx = m->tblocks[i + 1];
-      UU_LAUNCH(f, UU_KIND_LAYERNORM, 1,
-                launch_residual_ln_bx(X, plain, P, X, R, d, nx.ln1_g, nx.ln1_b, 1e-5f, nullptr, 1, Y, nullptr, st));
-    } else {   // last temporal block: bf16 copy for the full-sequence head, then + PE_1 and LN1 of strided block 1
-      const BlockW& nx = m->sblocks[0];
-      UU_LAUNCH(f, UU_KIND_LAYERNORM, 1,
-                launch_residual_ln_bx(X, plain, P, X, R, d, nx.ln1_g, nx.ln1_b, 1e-5f,
-                                   W(m, "strided_temporal_pe_1", 0), N, Y, want_full ? O : nullptr, st));
-    }
+              launch_residual_ln_bx(X, plain, nullptr, X, R, d, nx.ln1_g, nx.ln1_b, 1e-5f,
+                                    W(m, "strided_temporal_pe_1", 0), N, Y, want_full ? O : nullptr, st));
   }
   if (want_full) {   // T4
     Epilogue e;
