@@ -119,7 +119,7 @@ cudaError_t launch_layernorm(float* x, int rows, int d, const float* gamma, cons
 
 // bf16-resident residual stream variants (X stored as bf16; arithmetic fp32).  upd / xdst / y / xcast optional.
 cudaError_t launch_token_fill_bx(const uint8_t* mask, int rows, int n_tok, int d, const float* token, const float* pe,
-                                 bf16* x, cudaStream_t st);
+                                 bf16* x, cudaStream_t st, float* stats = nullptr, int slots = 0);
 cudaError_t launch_residual_ln_bx(const bf16* xsrc, const RowMap& smap, const bf16* upd, bf16* xdst, int rows, int d,
                                   const float* gamma, const float* beta, float eps, const float* table, int period,
                                   bf16* y, bf16* xcast, cudaStream_t st, float* stats = nullptr, int slots = 0);

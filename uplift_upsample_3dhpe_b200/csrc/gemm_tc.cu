@@ -180,7 +180,9 @@ __device__ __forceinline__ float2 bf16x2_to_f2(uint32_t u) { return make_float2(
 //   EMODE_PLAIN  out = acc (+ bias) (ReLU)
 //   EMODE_LNFOLD out = rstd * acc + ((-rstd * mean) * csum + bias') (ReLU)      two FFMA2 per column pair
 //   EMODE_RESID  out = acc + bias + residual, row partial sums of out and out^2 for the next folded LayerNorm
-constexpr int EMODE_PLAIN = 0, EMODE_LNFOLD = 1, EMODE_RESID = 2;
+//   EMODE_TABLE  out = acc + bias + table[dst_row % period] (fp32 positional table), same row partial sums; rows may
+//                be scattered (c_rowidx): table row and statistics slot follow the DESTINATION row
+constexpr int EMODE_PLAIN = 0, EMODE_LNFOLD = 1, EMODE_RESID = 2, EMODE_TABLE = 3;
 
 template <int BLOCK_N, int NBUF, int EMODE, typename Release>
 __device__ __forceinline__ void epi_warp_store_tile(uint32_t tmem_acc, int first, uint8_t* my_stage, uint32_t& my_count,
@@ -198,6 +200,11 @@ __device__ __forceinline__ void epi_warp_store_tile(uint32_t tmem_acc, int first
     boxed = __all_sync(0xffffffffu, my_dst >= 0 && my_dst == dst_row + lane);
   }
   const int my_row = row_q0 + lane;
+  // destination row of this lane (EMODE_TABLE: positional-table row and statistics slot), -1 = dropped
+  const int out_row = (epi.c_rowidx || epi.cmap.rpb != 0x7fffffff) ? my_dst : (my_row < m_eff ? my_row : -1);
+  const float* trow = nullptr;
+  if constexpr (EMODE == EMODE_TABLE)
+    trow = epi.table + (long long)(out_row < 0 ? 0 : out_row % epi.table_period) * (long long)ldc;
   const float2 a1 = make_float2(pre.rstd, pre.rstd), a2 = make_float2(-pre.rstd * pre.mu, -pre.rstd * pre.mu);
   const bool relu = (epi.flags & EPI_RELU) != 0;
   const bool has_bias = epi.bias != nullptr;
@@ -215,6 +222,7 @@ __device__ __forceinline__ void epi_warp_store_tile(uint32_t tmem_acc, int first
       else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
     __syncwarp();
+    if (!(epi.flags & 512))                 // (flag 512: timing experiment UU_GEMM_NOEPI — no conversion)
 #pragma unroll
     for (int g = 0; g < 8; ++g) {           // 8 columns -> one 16-byte chunk
       const int cb = col0 + sub * 64 + 8 * g;
@@ -232,21 +240,28 @@ __device__ __forceinline__ void epi_warp_store_tile(uint32_t tmem_acc, int first
         o[1] = ffma2(a1, o[1], ffma2(a2, make_float2(c0.z, c0.w), make_float2(b0.z, b0.w)));
         o[2] = ffma2(a1, o[2], ffma2(a2, make_float2(c1.x, c1.y), make_float2(b1.x, b1.y)));
         o[3] = ffma2(a1, o[3], ffma2(a2, make_float2(c1.z, c1.w), make_float2(b1.z, b1.w)));
-      } else if (EMODE == EMODE_RESID || has_bias) {
+      } else if (EMODE == EMODE_RESID || EMODE == EMODE_TABLE || has_bias) {
         const float4 b0 = __ldg(reinterpret_cast<const float4*>(epi.bias + cb));
         const float4 b1 = __ldg(reinterpret_cast<const float4*>(epi.bias + cb + 4));
         o[0] = fadd2(o[0], make_float2(b0.x, b0.y)); o[1] = fadd2(o[1], make_float2(b0.z, b0.w));
         o[2] = fadd2(o[2], make_float2(b1.x, b1.y)); o[3] = fadd2(o[3], make_float2(b1.z, b1.w));
       }
-      if constexpr (EMODE != EMODE_RESID) {
+      if constexpr (EMODE == EMODE_PLAIN || EMODE == EMODE_LNFOLD) {
         if (relu) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) o[i] = make_float2(fmaxf(o[i].x, 0.f), fmaxf(o[i].y, 0.f));
         }
       } else {
-        const uint4 r = pre.rres[g];
-        o[0] = fadd2(o[0], bf16x2_to_f2(r.x)); o[1] = fadd2(o[1], bf16x2_to_f2(r.y));
-        o[2] = fadd2(o[2], bf16x2_to_f2(r.z)); o[3] = fadd2(o[3], bf16x2_to_f2(r.w));
+        if constexpr (EMODE == EMODE_RESID) {
+          const uint4 r = pre.rres[g];
+          o[0] = fadd2(o[0], bf16x2_to_f2(r.x)); o[1] = fadd2(o[1], bf16x2_to_f2(r.y));
+          o[2] = fadd2(o[2], bf16x2_to_f2(r.z)); o[3] = fadd2(o[3], bf16x2_to_f2(r.w));
+        } else {
+          const float4 t0 = __ldg(reinterpret_cast<const float4*>(trow + cb));
+          const float4 t1 = __ldg(reinterpret_cast<const float4*>(trow + cb + 4));
+          o[0] = fadd2(o[0], make_float2(t0.x, t0.y)); o[1] = fadd2(o[1], make_float2(t0.z, t0.w));
+          o[2] = fadd2(o[2], make_float2(t1.x, t1.y)); o[3] = fadd2(o[3], make_float2(t1.z, t1.w));
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           st_s = fadd2(st_s, o[i]);
@@ -260,12 +275,15 @@ __device__ __forceinline__ void epi_warp_store_tile(uint32_t tmem_acc, int first
       pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
       *reinterpret_cast<uint4*>(sbuf + lane * 128 + ((g ^ (lane & 7)) << 4)) = pk;
     }
-    if constexpr (EMODE == EMODE_RESID) {
+
+    if constexpr (EMODE == EMODE_RESID || EMODE == EMODE_TABLE) {
       // (statistics of the fp32 sums before the bf16 rounding: the difference to the stored values is far below the
       // bf16 resolution of the normalised output)
-      if (epi.stats_out && my_row < m_eff)
-        reinterpret_cast<float2*>(epi.stats_out)[(long long)my_row * epi.ln_slots + ((col0 >> 6) + sub)] =
+      if (epi.stats_out && out_row >= 0)
+        reinterpret_cast<float2*>(epi.stats_out)[(long long)out_row * epi.ln_slots + ((col0 >> 6) + sub)] =
             make_float2(st_s.x + st_s.y, st_q.x + st_q.y);
+    }
+    if constexpr (EMODE == EMODE_RESID) {
       if (sub + 2 < NSUB) epi_load_residual(pre, epi, my_row, col0 + (sub + 2) * 64, m_eff, ldc);   // next sub-tile's line
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async proxy
@@ -923,9 +941,10 @@ static cudaError_t tc2_launch_t(const TcGemmPlan* p, const Epilogue& epi, void* 
 static int g_use_2cta = -1;     // UU_GEMM_2CTA=0/1 forces the single-CTA / 2-CTA kernel (A/B comparison)
 
 // bf16 output, plain row mapping, no residual / table / scatter, full 64-column sub-tiles: TMA-store epilogue
+// (a positional table is allowed when the caller also asks for row statistics: EMODE_TABLE, table pitch == ldc)
 static bool tma_out_eligible(const TcGemmPlan* p, const Epilogue& epi, int c_bf16, long long ldc) {
-  return c_bf16 && !(epi.flags & (EPI_RESIDUAL | EPI_ROWTABLE)) && p->N == p->N_pad && (p->N % 64) == 0 &&
-         (ldc % 8) == 0 && p->block_n >= 64;
+  return c_bf16 && !(epi.flags & EPI_RESIDUAL) && (!(epi.flags & EPI_ROWTABLE) || epi.stats_out) && p->N == p->N_pad &&
+         (p->N % 64) == 0 && (ldc % 8) == 0 && p->block_n >= 64;
 }
 
 cudaError_t tc_gemm_launch(TcGemmPlan* p, const Epilogue& epi_in, void* C, int c_bf16, long long ldc, cudaStream_t st) {
@@ -941,6 +960,9 @@ cudaError_t tc_gemm_launch(TcGemmPlan* p, const Epilogue& epi_in, void* C, int c
   static int nopf = -1;
   if (nopf < 0) { const char* e = getenv("UU_GEMM_NOPREFETCH"); nopf = (e && e[0] == '1') ? 1 : 0; }
   if (nopf) epi.flags |= 256;
+  static int noepi = -1;
+  if (noepi < 0) { const char* e = getenv("UU_GEMM_NOEPI"); noepi = (e && e[0] == '1') ? 1 : 0; }
+  if (noepi) epi.flags |= 512;
   if (tma_out_eligible(p, epi, c_bf16, ldc)) {
     if (p->c_ptr != C || p->c_ld != ldc) {
       // rows of the output matrix: M, or with a (batch, position) row map the extent it can reach
@@ -963,6 +985,14 @@ cudaError_t tc_gemm_launch(TcGemmPlan* p, const Epilogue& epi_in, void* C, int c
         case 256: return tc_launch_t<256, bf16, true, EMODE_LNFOLD>(p, epi, C, ldc, st);
         case 192: return tc_launch_t<192, bf16, true, EMODE_LNFOLD>(p, epi, C, ldc, st);
         case 128: return tc_launch_t<128, bf16, true, EMODE_LNFOLD>(p, epi, C, ldc, st);
+        default: return cudaErrorInvalidValue;
+      }
+    }
+    if (epi.flags & EPI_ROWTABLE) {      // bias + positional table + row statistics (the 544 -> 384 GEMM)
+      if (!epi.bias || !epi.table || (epi.flags & (EPI_RELU | EPI_RESID_BF16)) || ldc != p->N) return cudaErrorInvalidValue;
+      switch (p->block_n) {
+        case 192: return tc_launch_t<192, bf16, true, EMODE_TABLE>(p, epi, C, ldc, st);
+        case 128: return tc_launch_t<128, bf16, true, EMODE_TABLE>(p, epi, C, ldc, st);
         default: return cudaErrorInvalidValue;
       }
     }

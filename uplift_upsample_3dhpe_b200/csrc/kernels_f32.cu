@@ -584,27 +584,37 @@ __device__ __forceinline__ void st_bf16x4(bf16* p, float a, float b, float c, fl
 }
 
 __global__ void k_token_fill_bx(const uint8_t* __restrict__ mask, int rows, int n_tok, int d4,
-                                const float4* __restrict__ token, const float4* __restrict__ pe, bf16* __restrict__ x) {
+                                const float4* __restrict__ token, const float4* __restrict__ pe, bf16* __restrict__ x,
+                                float* __restrict__ stats, int slots) {
   const int per_block = blockDim.x / 32;
   const int lane = threadIdx.x & 31;
   for (int row = blockIdx.x * per_block + (threadIdx.x >> 5); row < rows; row += gridDim.x * per_block) {
     if (mask[row]) continue;
     const int n = row % n_tok;
+    float s1 = 0.f, s2 = 0.f;
     for (int c = lane; c < d4; c += 32) {
       const float4 t = token[c];
       const float4 q = pe ? pe[(long long)n * d4 + c] : make_float4(0.f, 0.f, 0.f, 0.f);   // pe == null: added downstream
-      st_bf16x4(x + ((long long)row * d4 + c) * 4, t.x + q.x, t.y + q.y, t.z + q.z, t.w + q.w);
+      const float a = t.x + q.x, b = t.y + q.y, cc = t.z + q.z, dd = t.w + q.w;
+      st_bf16x4(x + ((long long)row * d4 + c) * 4, a, b, cc, dd);
+      s1 += (a + b) + (cc + dd);
+      s2 += (a * a + b * b) + (cc * cc + dd * dd);
+    }
+    if (stats) {      // row partials for a GEMM that folds the next LayerNorm: everything in slot 0
+      s1 = warp_sum(s1); s2 = warp_sum(s2);
+      if (lane < slots)
+        reinterpret_cast<float2*>(stats)[(long long)row * slots + lane] = lane == 0 ? make_float2(s1, s2) : make_float2(0.f, 0.f);
     }
   }
 }
 cudaError_t launch_token_fill_bx(const uint8_t* mask, int rows, int n_tok, int d, const float* token, const float* pe,
-                                 bf16* x, cudaStream_t st) {
+                                 bf16* x, cudaStream_t st, float* stats, int slots) {
   if (rows == 0) return cudaSuccess;
-  if (d % 4) return cudaErrorInvalidValue;
+  if (d % 4 || (stats && (slots < 1 || slots > 32))) return cudaErrorInvalidValue;
   int grid = (rows + 7) / 8;
   if (grid > 148 * 16) grid = 148 * 16;
   k_token_fill_bx<<<grid, 256, 0, st>>>(mask, rows, n_tok, d / 4, reinterpret_cast<const float4*>(token),
-                                        reinterpret_cast<const float4*>(pe), x);
+                                        reinterpret_cast<const float4*>(pe), x, stats, slots);
   return cudaGetLastError();
 }
 

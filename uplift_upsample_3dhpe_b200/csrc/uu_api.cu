@@ -183,10 +183,9 @@ static int setup_block(uu_model* m, BlockW& b, const std::string& g, int d, int 
   if (make_pack(m, b.p_proj, b.wp, d, d)) return 1;
   if (make_pack(m, b.p_fc1, b.w1, d, h)) return 1;
   if (make_pack(m, b.p_fc2, b.w2, strided ? 3 * h : h, d)) return 1;
-  if (!strided) {
-    if (make_pack_ln(m, b.p_qkv_ln, b.cs_qkv, b.bl_qkv, b.wqkv, d, 3 * d, b.ln1_g, b.ln1_b, b.bqkv)) return 1;
-    if (make_pack_ln(m, b.p_fc1_ln, b.cs_fc1, b.bl_fc1, b.w1, d, h, b.ln2_g, b.ln2_b, b.b1)) return 1;
-  }
+  // (strided blocks: fc1 is the k=1 Conv1D, a (d, h) matrix like the dense fc1)
+  if (make_pack_ln(m, b.p_qkv_ln, b.cs_qkv, b.bl_qkv, b.wqkv, d, 3 * d, b.ln1_g, b.ln1_b, b.bqkv)) return 1;
+  if (make_pack_ln(m, b.p_fc1_ln, b.cs_fc1, b.bl_fc1, b.w1, d, h, b.ln2_g, b.ln2_b, b.b1)) return 1;
   return 0;
 }
 
@@ -254,6 +253,7 @@ static int ensure_workspace(uu_model* m, int B) {
   free_pool(m->ws_allocs);
   drop_plans(m);
   m->Xs.clear(); m->Hp.clear();
+  m->Y = nullptr; m->P = nullptr; m->ln_stats = nullptr;
   const int cap = std::max(B, m->cap_B);
   const size_t R = (size_t)cap * s.n_tok;
   const size_t es = m->precision == UU_PRECISION_BF16 ? 2 : 4;
@@ -266,7 +266,7 @@ static int ensure_workspace(uu_model* m, int B) {
   if (dev_alloc(m->ws_allocs, &p, R, true)) return 1; m->w_mask = (uint8_t*)p;
   if (dev_alloc(m->ws_allocs, &m->S, es * R * s.n_joints * s.d_spatial, true)) return 1;
   if (dev_alloc(m->ws_allocs, &p, 4 * R * dt, true)) return 1; m->X = (float*)p;
-  if (dev_alloc(m->ws_allocs, &m->Y, es * R * dt, true)) return 1;
+  if (m->precision != UU_PRECISION_BF16 && dev_alloc(m->ws_allocs, &m->Y, es * R * dt, true)) return 1;   // LN output (fp32 schedule)
   if (dev_alloc(m->ws_allocs, &m->QKV, es * R * 3 * dt, true)) return 1;
   if (dev_alloc(m->ws_allocs, &m->O, es * R * dt, true)) return 1;
   if (dev_alloc(m->ws_allocs, &m->Hd, es * R * ht, true)) return 1;
@@ -386,7 +386,7 @@ static int run_forward_bf16(Fwd& f, const float* x2d, const uint8_t* mask, float
   const int R = B * N, H = s.num_heads, dh = d / H;
   const bool use_mask = s.has_strided_input != 0;
   const bool want_full = s.full_output && full;
-  bf16 *Y = (bf16*)m->Y, *QKV = (bf16*)m->QKV, *O = (bf16*)m->O, *Hd = (bf16*)m->Hd, *P = (bf16*)m->P;
+  bf16 *QKV = (bf16*)m->QKV, *O = (bf16*)m->O, *Hd = (bf16*)m->Hd, *P = (bf16*)m->P;
   bf16* X = reinterpret_cast<bf16*>(m->X);      // residual stream, bf16-resident in this schedule (buffer sized for fp32)
   const RowMap plain;
 
@@ -409,84 +409,85 @@ static int run_forward_bf16(Fwd& f, const float* x2d, const uint8_t* mask, float
                                 m->sp_frags, m->sp_params, (bf16*)m->S, m->num_sms, st, m->cur_src, nullptr, nullptr, 0, -1,
                                 m->cur_flip));
   }
-  {  // S4 + T1: 544->384 GEMM (+ bias) scattered to the token rows through the TMA-store epilogue, upsampling token on
-     // the rows without 2-D input; the temporal PE (net:352, added to every row) rides on the first LayerNorm pass
+  // Neither LayerNorm nor the residual / positional adds of the temporal and strided blocks are kernels of their own:
+  //  * GEMMs that consume LN(x) (QKV, fc1) read the bf16 residual stream directly with gamma folded into their weights
+  //    and finish the normalisation in the epilogue from per-row statistics (EPI_LNFOLD);
+  //  * GEMMs that produce a residual update (projection, fc2) add the stream in their epilogue, write it in place and
+  //    emit the statistics of the rows they wrote (EPI_RESID_BF16); the 544->384 GEMM does the same with the temporal
+  //    positional table (EPI_ROWTABLE).
+  const int slots = d / 64;
+  UU_CHECK(d % 64 == 0 && slots <= 32, "temporal width must be a multiple of 64 (<= 2048)");
+  {  // S4 + T1: 544->384 GEMM (+ bias + temporal PE, net:352) scattered to the token rows through the TMA-store epilogue;
+     // upsampling token + PE on the rows without 2-D input (net:350-352)
     Epilogue e;
     e.bias = W(m, "spatial_to_temporal_fc", 1);
+    e.flags = EPI_ROWTABLE; e.table = W(m, "temporal_pe", 0); e.table_period = N;
+    e.stats_out = m->ln_stats; e.ln_slots = slots;
     if (use_mask) { e.c_rowidx = m->g_list; e.m_dev = m->g_count; }
     if (gemm(f, m->S, J * ds, R, J * ds, nullptr, m->p_s2t, d, e, X, 1, d)) return 1;
     if (use_mask)
       UU_LAUNCH(f, UU_KIND_TOKEN_FILL, 1,
-                launch_token_fill_bx(mask, R, N, d, W(m, "strided_input_token_layer", 0), nullptr, X, st));
+                launch_token_fill_bx(mask, R, N, d, W(m, "strided_input_token_layer", 0), W(m, "temporal_pe", 0), X, st,
+                                     m->ln_stats, slots));
   }
-  // Temporal blocks (T2/T3).  Neither LayerNorm nor the residual adds are kernels of their own: the QKV and fc1 GEMMs
-  // read the bf16 residual stream directly with gamma folded into their weights and finish the normalisation in the
-  // epilogue from per-row statistics (EPI_LNFOLD); the projection and fc2 GEMMs add the residual in their epilogue,
-  // write the stream in place and emit the statistics of the rows they wrote (EPI_RESID_BF16).
-  const int slots = d / 64;
-  UU_CHECK(d % 64 == 0 && slots <= 32, "temporal width must be a multiple of 64 (<= 2048)");
-  UU_LAUNCH(f, UU_KIND_LAYERNORM, 1,     // + temporal PE (net:352), statistics for the first QKV GEMM
-            launch_residual_ln_bx(X, plain, nullptr, X, R, d, nullptr, nullptr, 1e-5f, W(m, "temporal_pe", 0), N, nullptr,
-                                  nullptr, st, m->ln_stats, slots));
-  auto ln_gemm = [&](const Pack& pk, int n_out, const float* bias_ln, const float* csum, bool relu, bf16* out) {
+  auto ln_gemm = [&](bf16* x, int rows, const Pack& pk, int n_out, const float* bias_ln, const float* csum, bool relu,
+                     void* out, const RowMap* cmap) {
     Epilogue e;
     e.bias = bias_ln; e.flags = EPI_LNFOLD | (relu ? EPI_RELU : 0);
     e.ln_stats = m->ln_stats; e.ln_csum = csum; e.ln_slots = slots; e.ln_inv_k = 1.f / d; e.ln_eps = 1e-5f;
-    return gemm(f, X, d, R, d, nullptr, pk, n_out, e, out, 1, n_out);
+    if (cmap) e.cmap = *cmap;
+    return gemm(f, x, d, rows, d, nullptr, pk, n_out, e, out, 1, n_out);
   };
-  auto resid_gemm = [&](const bf16* A, int K, const Pack& pk, const float* bias) {
+  auto resid_gemm = [&](const bf16* A, int K, bf16* x, int rows, const Pack& pk, const float* bias) {
     Epilogue e;
     e.bias = bias; e.flags = EPI_RESID_BF16;
-    e.res_bf16 = X; e.stats_out = m->ln_stats; e.ln_slots = slots;
-    return gemm(f, A, K, R, K, nullptr, pk, d, e, X, 1, d);
+    e.res_bf16 = x; e.stats_out = m->ln_stats; e.ln_slots = slots;
+    return gemm(f, A, K, rows, K, nullptr, pk, d, e, x, 1, d);
   };
-  for (int i = 0; i < s.temporal_depth; ++i) {
+  for (int i = 0; i < s.temporal_depth; ++i) {   // T2 / T3
     const BlockW& w = m->tblocks[i];
     const uint8_t* km = (use_mask && i < s.first_strided_token_attention_layer) ? mask : nullptr;
-    if (ln_gemm(w.p_qkv_ln, 3 * d, w.bl_qkv, w.cs_qkv, false, QKV)) return 1;
+    if (ln_gemm(X, R, w.p_qkv_ln, 3 * d, w.bl_qkv, w.cs_qkv, false, QKV, nullptr)) return 1;
     UU_LAUNCH(f, UU_KIND_ATTENTION, 1, launch_attention_tc(QKV, B, N, H, dh, km, N, O, st));
-    if (resid_gemm(O, d, w.p_proj, w.bp)) return 1;
-    if (ln_gemm(w.p_fc1_ln, h, w.bl_fc1, w.cs_fc1, true, Hd)) return 1;
-    if (resid_gemm(Hd, h, w.p_fc2, w.b2)) return 1;
+    if (resid_gemm(O, d, X, R, w.p_proj, w.bp)) return 1;
+    if (ln_gemm(X, R, w.p_fc1_ln, h, w.bl_fc1, w.cs_fc1, true, Hd, nullptr)) return 1;
+    if (resid_gemm(Hd, h, X, R, w.p_fc2, w.b2)) return 1;
   }
-  {   // bf16 copy for the full-sequence head, then + PE_1 and LN1 of strided block 1
-    const BlockW& nx = m->sblocks[0];
-    UU_LAUNCH(f, UU_KIND_LAYERNORM, 1,
-              launch_residual_ln_bx(X, plain, nullptr, X, R, d, nx.ln1_g, nx.ln1_b, 1e-5f,
-                                    W(m, "strided_temporal_pe_1", 0), N, Y, want_full ? O : nullptr, st));
-  }
-  if (want_full) {   // T4
+  if (want_full) {   // T4: full-sequence head on the temporal output
     Epilogue e;
     e.bias = W(m, "temporal_fc", 1);
-    if (gemm(f, O, d, R, d, nullptr, m->p_head1, 3 * J, e, full, 0, 3 * J)) return 1;
+    if (gemm(f, X, d, R, d, nullptr, m->p_head1, 3 * J, e, full, 0, 3 * J)) return 1;
   }
+  // + PE of strided block 1 (net:128) and the statistics its QKV GEMM needs
+  UU_LAUNCH(f, UU_KIND_LAYERNORM, 1,
+            launch_residual_ln_bx(X, plain, nullptr, X, R, d, nullptr, nullptr, 0.f, W(m, "strided_temporal_pe_1", 0), N,
+                                  nullptr, nullptr, st, m->ln_stats, slots));
   bf16* x_in = X;
   for (int i = 0; i < s.n_strided; ++i) {   // Q1/Q2
     const BlockW& w = m->sblocks[i];
     const int L = m->seq_lens[i], Lo = m->seq_lens[i + 1], st_i = s.strides[i], pl = s.pad_left[i];
     const int Rl = B * L, Ro = B * Lo;
-    if (tc_gemm_bf16(f, Y, d, Rl, d, w.p_qkv, 3 * d, w.bqkv, false, QKV, 3 * d)) return 1;
+    if (ln_gemm(x_in, Rl, w.p_qkv_ln, 3 * d, w.bl_qkv, w.cs_qkv, false, QKV, nullptr)) return 1;
     UU_LAUNCH(f, UU_KIND_ATTENTION, 1, launch_attention_tc(QKV, B, L, H, dh, nullptr, L, O, st));
-    if (tc_gemm_bf16(f, O, d, Rl, d, w.p_proj, d, w.bp, false, P, d)) return 1;
-    UU_LAUNCH(f, UU_KIND_LAYERNORM, 1,
-              launch_residual_ln_bx(x_in, plain, P, x_in, Rl, d, w.ln2_g, w.ln2_b, 1e-5f, nullptr, 1, Y, nullptr, st));
+    if (resid_gemm(O, d, x_in, Rl, w.p_proj, w.bp)) return 1;
     RowMap cm;   // Conv1D k=1 + ReLU into the zero-padded layout [B, Lo*s, h]
     cm.rpb = L; cm.batch_rows = Lo * st_i; cm.offset = pl; cm.step = 1;
-    if (tc_gemm_bf16(f, Y, d, Rl, d, w.p_fc1, h, w.b1, true, m->Hp[i], h, &cm)) return 1;
+    if (ln_gemm(x_in, Rl, w.p_fc1_ln, h, w.bl_fc1, w.cs_fc1, true, m->Hp[i], &cm)) return 1;
     // strided Conv1D k=3 as an implicit GEMM over contiguous 3h-wide rows, s*h apart
     if (tc_gemm_bf16(f, m->Hp[i], (long long)st_i * h, Ro, 3 * h, w.p_fc2, d, w.b2, false, P, d)) return 1;
     RowMap idm;  // identity path x[b, c0 + t*s]
     idm.rpb = Lo; idm.batch_rows = L; idm.offset = (st_i > 1 && pl == 0) ? 1 : 0; idm.step = st_i;
-    if (i + 1 < s.n_strided) {
-      const BlockW& nx = m->sblocks[i + 1];
+    bf16* x_out = reinterpret_cast<bf16*>(m->Xs[i]);
+    if (i + 1 < s.n_strided) {   // x_out = x_in[identity rows] + conv + PE of the next block; statistics for its QKV GEMM
       UU_LAUNCH(f, UU_KIND_LAYERNORM, 1,
-                launch_residual_ln_bx(x_in, idm, P, reinterpret_cast<bf16*>(m->Xs[i]), Ro, d, nx.ln1_g, nx.ln1_b, 1e-5f,
-                                   W(m, "strided_temporal_pe_" + std::to_string(i + 2), 0), Lo, Y, nullptr, st));
+                launch_residual_ln_bx(x_in, idm, P, x_out, Ro, d, nullptr, nullptr, 0.f,
+                                      W(m, "strided_temporal_pe_" + std::to_string(i + 2), 0), Lo, nullptr, nullptr, st,
+                                      m->ln_stats, slots));
     } else {
       UU_LAUNCH(f, UU_KIND_LAYERNORM, 1,
-                launch_residual_ln_bx(x_in, idm, P, reinterpret_cast<bf16*>(m->Xs[i]), Ro, d, nullptr, nullptr, 0.f, nullptr, 1, nullptr, O, st));
+                launch_residual_ln_bx(x_in, idm, P, x_out, Ro, d, nullptr, nullptr, 0.f, nullptr, 1, nullptr, O, st));
     }
-    x_in = reinterpret_cast<bf16*>(m->Xs[i]);
+    x_in = x_out;
   }
   {   // Q3
     Epilogue e;
