@@ -70,9 +70,10 @@ def load() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("UU3D_LIB") or LIB_PATH      # UU3D_LIB: development override (A/B builds of the library)
+    if path == LIB_PATH and not os.path.exists(LIB_PATH):
         build()
-    lib = ctypes.CDLL(LIB_PATH)
+    lib = ctypes.CDLL(path)
     _declare(lib)
     _lib = lib
     return lib

@@ -22,7 +22,13 @@ constexpr int TC_BLOCK_K = 64;          // 64 bf16 = 128 B = one swizzle atom ro
 constexpr int TC_UMMA_K = 16;
 constexpr int TC_THREADS = 320;        // TMA warp, MMA warp, 8 epilogue warps
 constexpr int TC_TSTRIDE = 36;          // fp32 row stride of the epilogue transpose tiles (conflict-free float4)
-constexpr int TC_EPI_SMEM = 8 * 2 * 32 * 128 + 1024;   // max(fp32 transpose tiles 36 KB, per-warp TMA staging 64 KB + align)
+#ifndef UU_TC_EPI_NBUF
+#define UU_TC_EPI_NBUF 2        // TMA-store staging tiles per epilogue warp
+#endif
+#ifndef UU_TC_RING_KB
+#define UU_TC_RING_KB 160       // operand ring budget
+#endif
+constexpr int TC_EPI_SMEM = 8 * UU_TC_EPI_NBUF * 32 * 128 + 1024;   // max(fp32 transpose tiles 36 KB, per-warp TMA staging + align)
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -218,7 +224,8 @@ __device__ __forceinline__ void epi_warp_store_tile(uint32_t tmem_acc, int first
     if (sub + 2 >= NSUB) release();         // last TMEM read of this warp for this tile: hand the accumulator back
     // the store issued NBUF sub-tiles ago read this staging tile: it must have finished reading
     if (lane == 0) {
-      if constexpr (NBUF == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      if constexpr (NBUF == 3) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+      else if constexpr (NBUF == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
       else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
     __syncwarp();
@@ -311,9 +318,9 @@ struct TcCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   // epilogue scratch: per-warp TMA-store staging, 8 warps x NBUF x 4 KB (+ alignment); the generic fp32 transpose
   // tiles (36 KB) fit in the same region.
-  static constexpr int EPI_NBUF = 2;
+  static constexpr int EPI_NBUF = UU_TC_EPI_NBUF;
   static constexpr int EPI_BYTES = TC_EPI_SMEM;
-  static constexpr int STAGES = (160 * 1024) / STAGE_BYTES < 8 ? (160 * 1024) / STAGE_BYTES : 8;
+  static constexpr int STAGES = (UU_TC_RING_KB * 1024) / STAGE_BYTES < 8 ? (UU_TC_RING_KB * 1024) / STAGE_BYTES : 8;
   static constexpr int ACC_STAGES = 2;                           // double-buffered accumulator in TMEM
   static constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N <= 32 ? 32 : ACC_STAGES * BLOCK_N <= 64 ? 64
                                    : ACC_STAGES * BLOCK_N <= 128 ? 128 : ACC_STAGES * BLOCK_N <= 256 ? 256 : 512;
@@ -508,10 +515,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
       const int as = tcount % Cfg::ACC_STAGES;
       const uint32_t aph = (tcount / Cfg::ACC_STAGES) & 1;
       const int r = row0 + q * 32 + lane;
-      int my_crow = -1, my_rrow = 0;
+      int my_crow = -1, my_rrow = 0, my_trow = 0;
       if (r < m_eff) {
         const EpiRow er = epi_row(epi, r);
-        my_crow = (int)er.crow; my_rrow = (int)er.rrow;
+        my_crow = (int)er.crow; my_rrow = (int)er.rrow; my_trow = er.trow;
       }
       int crow[8], rrow[8];                   // rows this lane stores in the transposed pass: 4*it + rsub
 #pragma unroll
@@ -568,9 +575,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
 #pragma unroll 4
           for (int it = 0; it < 32; ++it) {
             const int cr = __shfl_sync(0xffffffffu, my_crow, it), rr = __shfl_sync(0xffffffffu, my_rrow, it);
+            const int tr = __shfl_sync(0xffffffffu, my_trow, it);      // (one modulo per row, not per element)
             if (cr < 0 || c >= N) continue;
             EpiRow er;
-            er.crow = cr; er.rrow = rr; er.trow = (epi.flags & EPI_ROWTABLE) ? cr % epi.table_period : 0;
+            er.crow = cr; er.rrow = rr; er.trow = tr;
             store_out(C + (long long)cr * ldc + c, epi_value(epi, er, tbuf[it * TC_TSTRIDE + lane], c, N));
           }
         }
@@ -650,7 +658,7 @@ struct Tc2Cfg {
   static constexpr int A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;          // 16 KB: this CTA's 128 rows
   static constexpr int B_BYTES = (BLOCK_N / 2) * TC_BLOCK_K * 2;       // this CTA's half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (160 * 1024) / STAGE_BYTES < 8 ? (160 * 1024) / STAGE_BYTES : 8;
+  static constexpr int STAGES = (UU_TC_RING_KB * 1024) / STAGE_BYTES < 8 ? (UU_TC_RING_KB * 1024) / STAGE_BYTES : 8;
   static constexpr int ACC_STAGES = 2;
   static constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N <= 128 ? 128 : ACC_STAGES * BLOCK_N <= 256 ? 256 : 512;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + TC_EPI_SMEM;
@@ -781,7 +789,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     const int hsel = e >> 2;
     uint8_t* stage_base = reinterpret_cast<uint8_t*>(
         (reinterpret_cast<uintptr_t>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256) + 1023) & ~uintptr_t(1023));
-    uint8_t* my_stage = stage_base + e * (2 * 32 * 128);
+    uint8_t* my_stage = stage_base + e * (UU_TC_EPI_NBUF * 32 * 128);
     constexpr int NSUB = BLOCK_N / 64;
     uint32_t tcount = 0, my_count = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++tcount) {
@@ -800,7 +808,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         if (lane == 0) mbar_arrive_cluster(mapa_rank(tmem_empty_bar + as, 0));
       };
       if (first >= NSUB) { release(); continue; }
-      epi_warp_store_tile<BLOCK_N, 2, EMODE>(tmem_acc, first, my_stage, my_count, epi, &map_c, row0 + q * 32, col0, lane, release,
+      epi_warp_store_tile<BLOCK_N, UU_TC_EPI_NBUF, EMODE>(tmem_acc, first, my_stage, my_count, epi, &map_c, row0 + q * 32, col0, lane, release,
                                       pre, M, C, ldc);
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");

@@ -417,6 +417,7 @@ static int run_forward_bf16(Fwd& f, const float* x2d, const uint8_t* mask, float
   //    positional table (EPI_ROWTABLE).
   const int slots = d / 64;
   UU_CHECK(d % 64 == 0 && slots <= 32, "temporal width must be a multiple of 64 (<= 2048)");
+  UU_CHECK(s.temporal_depth > 0 && s.n_strided > 0, "the bf16 schedule needs at least one temporal and one strided block");
   {  // S4 + T1: 544->384 GEMM (+ bias + temporal PE, net:352) scattered to the token rows through the TMA-store epilogue;
      // upsampling token + PE on the rows without 2-D input (net:350-352)
     Epilogue e;
