@@ -1,6 +1,7 @@
 """Summarise an `ncu --page raw --csv` export of one forward pass: per-kernel table (markdown) and the DRAM
 traffic per launch by kernel kind (JSON, read by bench.py for roofline.traffic).
-usage: python scripts/summarize_ncu_raw.py gpurun_out/prof_raw.csv BATCH profiles/NAME  (writes NAME.md, ncu_traffic.json)"""
+usage: python scripts/summarize_ncu_raw.py gpurun_out/prof_raw.csv BATCH profiles/NAME [LAST_N]  (writes NAME.md,
+ncu_traffic.json; LAST_N keeps only the last N launches = the final forward pass of a longer capture)"""
 import collections
 import csv
 import json
@@ -11,6 +12,8 @@ import sys
 path, batch, out = sys.argv[1], int(sys.argv[2]), sys.argv[3]
 rows = list(csv.reader(l for l in open(path) if not l.startswith("==")))
 hdr, units, data = rows[0], rows[1], rows[2:]
+if len(sys.argv) > 4:
+    data = data[-int(sys.argv[4]):]
 col = {h: i for i, h in enumerate(hdr)}
 
 
