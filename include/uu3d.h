@@ -180,6 +180,17 @@ int uu_op_gemm_f32(const float* A, int64_t lda, const float* W, int M, int N, in
 int uu_op_gemm_bf16(const void* A, int64_t lda, int M, int K, const void* Wt, int N_pad, int N, const float* bias,
                     int flags, const float* res, int64_t ldr, void* C, int c_bf16, int64_t ldc, void* stream);
 
+/* The folded epilogues of the bf16 schedule in isolation ("LayerNorm and residual folding"); they
+ * replace LayerNormalization + Dense (vit:168-171, :183-195) and Dense + residual add.  Synchronous (temporaries).
+ *   out[rows, N] (bf16) = act( LN(x; gamma, beta, eps) . W + bias ),  x bf16 [rows, d], W fp32 (d, N) on the device */
+int uu_op_ln_gemm_bf16(const void* x, int rows, int d, const float* gamma, const float* beta, float eps, const float* W,
+                       const float* bias, int N, int relu, void* out, void* stream);
+/*   resid != 0: x[rows, d] (bf16, in place) += A . W + bias          A bf16 [rows, K], W fp32 (K, d)
+ *   resid == 0: x = A . W + bias + table[row % period]               table fp32 [period, d]
+ *   stats_out (optional) [rows, d / 64, 2] fp32 = (sum, sum of squares) of the result per 64-column slot */
+int uu_op_resid_gemm_bf16(const void* A, int rows, int K, const float* W, const float* bias, int d, void* x, int resid,
+                          const float* table, int period, float* stats_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

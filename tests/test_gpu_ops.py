@@ -188,6 +188,64 @@ def test_gemm_bf16_tcgen05(lib, M, N, K, flags, c_bf16):
     assert err < (5e-2 if c_bf16 else 1e-3), err
 
 
+@pytest.mark.parametrize("rows,N,relu", [(71, 1152, 0), (300, 768, 1), (36352, 1152, 0), (5000, 128, 1)])
+def test_layernorm_folded_into_gemm(lib, rows, N, relu):
+    """EPI_LNFOLD: the GEMM reads the raw bf16 stream with gamma folded into W and finishes LayerNorm (vit:168-171) in
+    the epilogue from per-row statistics.  Reference: float64 LN of the same bf16 rows, fp32 weights.  Rows get a large
+    common offset (|mean| >> std) so that a wrong mean / column-sum term cannot hide."""
+    d = 384
+    rng = np.random.default_rng(rows + N)
+    x = (rng.normal(size=(rows, d)) * rng.uniform(0.5, 3.0, (rows, 1)) + rng.normal(size=(rows, 1)) * 4).astype(np.float32)
+    xb = dev(x, torch.bfloat16)
+    gamma = (1 + 0.3 * rng.normal(size=d)).astype(np.float32)
+    beta = (0.3 * rng.normal(size=d)).astype(np.float32)
+    Wm = (rng.normal(size=(d, N)) / math.sqrt(d)).astype(np.float32)
+    bias = rng.normal(size=N).astype(np.float32)
+    x64 = xb.float().cpu().numpy().astype(np.float64)
+    mu, var = x64.mean(1, keepdims=True), x64.var(1, keepdims=True)
+    want = ((x64 - mu) / np.sqrt(var + 1e-5) * gamma + beta) @ Wm.astype(np.float64) + bias
+    if relu:
+        want = np.maximum(want, 0)
+    out = torch.full((rows, N), float("nan"), dtype=torch.bfloat16, device="cuda")
+    _lib.check(lib.uu_op_ln_gemm_bf16(P(xb), rows, d, P(dev(gamma)), P(dev(beta)), 1e-5, P(dev(Wm)), P(dev(bias)), N, relu,
+                                      P(out), None))
+    got = out.float().cpu().numpy()
+    assert np.isfinite(got).all()
+    err = np.abs(got - want)
+    # bf16 weights (2^-9 relative, sqrt(d) terms) + bf16 output rounding of O(1..4) values
+    assert err.max() < 6e-2 and np.sqrt((err ** 2).mean()) < 1e-2, (err.max(), np.sqrt((err ** 2).mean()))
+
+
+@pytest.mark.parametrize("rows,K,resid", [(71, 384, 1), (300, 768, 1), (36352, 384, 1), (2048, 768, 1), (5000, 544, 0), (213, 768, 0)])
+def test_residual_and_table_epilogues(lib, rows, K, resid):
+    """EPI_RESID_BF16 (x += A W + b in place) and the positional-table epilogue (x = A W + b + pe[row % period]), both
+    with the (sum, sum of squares) partials per 64-column slot that the next folded LayerNorm consumes."""
+    d, period = 384, 71
+    rng = np.random.default_rng(rows + K)
+    A = dev(rng.normal(size=(rows, K)).astype(np.float32), torch.bfloat16)
+    Wm = (rng.normal(size=(K, d)) / math.sqrt(K)).astype(np.float32)
+    bias = rng.normal(size=d).astype(np.float32)
+    x0 = dev((rng.normal(size=(rows, d)) * 2).astype(np.float32), torch.bfloat16)
+    table = rng.normal(size=(period, d)).astype(np.float32)
+    # the kernel multiplies bf16(A) by bf16(W): same operands for the reference
+    Wb = dev(Wm, torch.bfloat16).float().cpu().numpy().astype(np.float64)
+    want = A.float().cpu().numpy().astype(np.float64) @ Wb + bias
+    if resid:
+        want = want + x0.float().cpu().numpy()
+    else:
+        want = want + table[np.arange(rows) % period]
+    x = x0.clone()
+    stats = torch.full((rows, d // 64, 2), float("nan"), device="cuda")
+    _lib.check(lib.uu_op_resid_gemm_bf16(P(A), rows, K, P(dev(Wm)), P(dev(bias)), d, P(x), resid, P(dev(table)), period,
+                                         P(stats), None))
+    got = x.float().cpu().numpy()
+    assert np.abs(got - want).max() < 4e-2          # bf16 rounding of O(1..8) outputs
+    w = want.reshape(rows, d // 64, 64)
+    st = stats.cpu().numpy()
+    assert np.isfinite(st).all()
+    assert np.abs(st[..., 0] - w.sum(-1)).max() < 2e-3 and np.abs(st[..., 1] - (w ** 2).sum(-1)).max() < 2e-2
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 @pytest.mark.parametrize("B,masked", [(3, False), (5, True), (40, True)])
 def test_spatial_transformer(lib, precision, B, masked):

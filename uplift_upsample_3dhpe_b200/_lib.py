@@ -128,6 +128,10 @@ def _declare(lib) -> None:
                                    c_int64, c_void_p, c_int64, c_void_p]
     lib.uu_op_gemm_bf16.argtypes = [c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int,
                                     c_void_p, c_int64, c_void_p, c_int, c_int64, c_void_p]
+    lib.uu_op_ln_gemm_bf16.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int,
+                                       c_int, c_void_p, c_void_p]
+    lib.uu_op_resid_gemm_bf16.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p,
+                                          c_int, c_void_p, c_void_p]
     for name in EXPORTS:          # fail at load time, not at first use, if a symbol is missing
         getattr(lib, name)
 
@@ -141,7 +145,7 @@ EXPORTS = [
     "uu_train_config", "uu_train_forward_backward", "uu_grad_buffer", "uu_get_grad", "uu_get_droppath_scale",
     "uu_adamw_step", "uu_get_ema_weight",
     "uu_op_build_gather", "uu_op_token_fill", "uu_op_layernorm", "uu_op_attention", "uu_op_spatial", "uu_op_gemm_f32",
-    "uu_op_gemm_bf16",
+    "uu_op_gemm_bf16", "uu_op_ln_gemm_bf16", "uu_op_resid_gemm_bf16",
 ]
 
 

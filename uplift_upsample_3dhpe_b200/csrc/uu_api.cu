@@ -1107,4 +1107,62 @@ int uu_op_gemm_bf16(const void* A, int64_t lda, int M, int K, const void* Wt, in
   return 0;
 }
 
+// ---- the folded-LayerNorm / residual epilogues in isolation (parity tests) ------------------------------------------
+namespace {
+struct TmpPool {
+  std::vector<void*> v;
+  ~TmpPool() { for (void* p : v) cudaFree(p); }
+};
+}  // namespace
+
+int uu_op_ln_gemm_bf16(const void* x, int rows, int d, const float* gamma, const float* beta, float eps, const float* Wm,
+                       const float* bias, int N, int relu, void* out, void* stream) {
+  UU_CHECK(rows > 0 && d % 128 == 0 && d <= 1024 && N % 64 == 0, "uu_op_ln_gemm_bf16: d % 128 == 0, N % 64 == 0 required");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int slots = d / 64;
+  TmpPool tp;
+  void *wt, *cs, *bl, *stats;
+  if (dev_alloc(tp.v, &wt, sizeof(bf16) * (size_t)N * d, false) || dev_alloc(tp.v, &cs, sizeof(float) * N, false) ||
+      dev_alloc(tp.v, &bl, sizeof(float) * N, false) || dev_alloc(tp.v, &stats, sizeof(float) * 2 * (size_t)rows * slots, false))
+    return 1;
+  k_pack_wt_ln<<<(N + 7) / 8, 256, 0, st>>>(Wm, d, N, N, gamma, beta, bias, (bf16*)wt, (float*)cs, (float*)bl);
+  UU_CUDA(cudaGetLastError());
+  const RowMap plain;
+  UU_CUDA(launch_residual_ln_bx((const bf16*)x, plain, nullptr, nullptr, rows, d, nullptr, nullptr, 0.f, nullptr, 1, nullptr,
+                                nullptr, st, (float*)stats, slots));
+  Epilogue e;
+  e.bias = (const float*)bl; e.flags = EPI_LNFOLD | (relu ? EPI_RELU : 0);
+  e.ln_stats = (const float*)stats; e.ln_csum = (const float*)cs; e.ln_slots = slots; e.ln_inv_k = 1.f / d; e.ln_eps = eps;
+  TcGemmPlan* p = nullptr;
+  if (tc_gemm_plan_create(&p, (const bf16*)x, d, rows, d, (const bf16*)wt, N, N)) return 1;
+  cudaError_t err = tc_gemm_launch(p, e, out, 1, N, st);
+  tc_gemm_plan_destroy(p);
+  UU_CUDA(err);
+  UU_CUDA(cudaStreamSynchronize(st));     // temporaries are released on return
+  return 0;
+}
+
+int uu_op_resid_gemm_bf16(const void* A, int rows, int K, const float* Wm, const float* bias, int d, void* x, int resid,
+                          const float* table, int period, float* stats_out, void* stream) {
+  UU_CHECK(rows > 0 && K % 8 == 0 && d % 64 == 0 && d / 64 <= 32, "uu_op_resid_gemm_bf16: K % 8 == 0, d % 64 == 0 required");
+  UU_CHECK(resid || table, "uu_op_resid_gemm_bf16: residual mode or a positional table");
+  cudaStream_t st = (cudaStream_t)stream;
+  TmpPool tp;
+  void* wt;
+  if (dev_alloc(tp.v, &wt, sizeof(bf16) * (size_t)d * K, false)) return 1;
+  k_pack_wt<<<256, 256, 0, st>>>(Wm, K, d, d, (bf16*)wt);
+  UU_CUDA(cudaGetLastError());
+  Epilogue e;
+  e.bias = bias; e.stats_out = stats_out; e.ln_slots = d / 64;
+  if (resid) { e.flags = EPI_RESID_BF16; e.res_bf16 = (const bf16*)x; }
+  else { e.flags = EPI_ROWTABLE; e.table = table; e.table_period = period; }
+  TcGemmPlan* p = nullptr;
+  if (tc_gemm_plan_create(&p, (const bf16*)A, K, rows, K, (const bf16*)wt, d, d)) return 1;
+  cudaError_t err = tc_gemm_launch(p, e, x, 1, d, st);
+  tc_gemm_plan_destroy(p);
+  UU_CUDA(err);
+  UU_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
 }  // extern "C"
