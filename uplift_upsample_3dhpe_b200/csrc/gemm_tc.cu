@@ -142,8 +142,9 @@ struct EpiPre {
 };
 __device__ __forceinline__ void epi_load_residual(EpiPre& pre, const Epilogue& epi, int row, int col, int m_eff, long long ldc) {
   const uint4* rp = reinterpret_cast<const uint4*>(epi.res_bf16 + (long long)row * ldc + col);
+  const bool ok = row < m_eff && !(epi.flags & 1024);     // (flag 1024: timing experiment UU_GEMM_NORES)
 #pragma unroll
-  for (int g = 0; g < 8; ++g) pre.rres[g] = row < m_eff ? rp[g] : make_uint4(0u, 0u, 0u, 0u);
+  for (int g = 0; g < 8; ++g) pre.rres[g] = ok ? rp[g] : make_uint4(0u, 0u, 0u, 0u);
 }
 template <int EMODE>
 __device__ __forceinline__ void epi_prefetch(EpiPre& pre, const Epilogue& epi, int row_q0, int col0, int first, int lane,
@@ -971,6 +972,9 @@ cudaError_t tc_gemm_launch(TcGemmPlan* p, const Epilogue& epi_in, void* C, int c
   static int noepi = -1;
   if (noepi < 0) { const char* e = getenv("UU_GEMM_NOEPI"); noepi = (e && e[0] == '1') ? 1 : 0; }
   if (noepi) epi.flags |= 512;
+  static int nores = -1;
+  if (nores < 0) { const char* e = getenv("UU_GEMM_NORES"); nores = (e && e[0] == '1') ? 1 : 0; }
+  if (nores) epi.flags |= 1024;
   if (tma_out_eligible(p, epi, c_bf16, ldc)) {
     if (p->c_ptr != C || p->c_ld != ldc) {
       // rows of the output matrix: M, or with a (batch, position) row map the extent it can reach
