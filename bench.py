@@ -161,7 +161,7 @@ def train_bench(a, cfg, spec, rank, world, local_rank):
     from uplift_upsample_3dhpe_b200.model import build_uplift_upsample_transformer
     from uplift_upsample_3dhpe_b200.train import Trainer
     model = build_uplift_upsample_transformer(cfg, device=local_rank, precision="fp32")
-    tr = Trainer(model, cfg, droppath=True, seed=rank)
+    tr = Trainer(model, cfg, droppath=True, seed=rank, math=a.train_math)
     Bg = int(cfg.BATCH_SIZE)
     B = Bg // world
     rng = np.random.default_rng(rank)
@@ -192,7 +192,9 @@ def train_bench(a, cfg, spec, rank, world, local_rank):
     if rank == 0:
         emit({"metric": "training windows/sec (fwd+bwd+AdamW)", "value": Bg / (ms / 1e3), "unit": "windows/s",
                           "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms,
-                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                          "dtype": "f32" if a.train_math == "fp32" else "tf32 (fp32 data; TF32 products in the forward/dgrad "
+                                   "GEMMs of the temporal and strided blocks, TensorFlow's GPU default; rest fp32)",
                           "data": "synthetic", "loss": float(loss.item()),
                           "config": {"workload": f"config/{a.config}.json training step, global batch {Bg}, mask strides "
                                                  f"{cfg.MASK_STRIDE} drawn per window, DropPath on",
@@ -237,6 +239,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=64, help="windows per CPU-baseline step")
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
                     help="train: amass_351-style training step (fwd+bwd+AdamW, NCCL gradient all-reduce), strong scaling")
+    ap.add_argument("--train-math", default="fp32", choices=["tf32", "fp32"],
+                    help="--mode train: GEMM arithmetic (uu_train_set_math)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
 

@@ -148,6 +148,12 @@ int uu_train_config(uu_model* m, int global_batch, int root_keypoint, float w_ce
                     const float* drop_path_rate3, int droppath_mode, uint64_t seed);
 int uu_train_forward_backward(uu_model* m, const float* x2d, const uint8_t* mask, const float* gt3d, int B,
                               int64_t step, float* loss_dev, void* stream);
+/* Arithmetic of the training GEMMs.  0 (default): fp32 on CUDA cores, gradients within 2e-3 of fp32 autograd.
+ * 1: forward and dgrad GEMMs of the temporal / strided blocks on tcgen05 kind::tf32 (fp32 data, TF32 products, fp32
+ *    accumulation) -- what TensorFlow 2.4 itself does on Ampere-or-newer GPUs unless
+ *    tf.config.experimental.enable_tensor_float_32_execution(False) is called; wgrad, the spatial blocks and everything
+ *    that is not a GEMM stay fp32. */
+int uu_train_set_math(uu_model* m, int mode);
 int uu_grad_buffer(uu_model* m, float** dev_ptr, int64_t* n_floats);
 int uu_get_grad(uu_model* m, const char* group, int index, float* host, int64_t capacity);
 int uu_get_droppath_scale(uu_model* m, int stage, int block, float* host, int64_t capacity, float* keep_prob);
@@ -180,6 +186,10 @@ int uu_op_gemm_f32(const float* A, int64_t lda, const float* W, int M, int N, in
 int uu_op_gemm_bf16(const void* A, int64_t lda, int M, int K, const void* Wt, int N_pad, int N, const float* bias,
                     int flags, const float* res, int64_t ldr, void* C, int c_bf16, int64_t ldc, void* stream);
 
+/* tcgen05 kind::tf32 GEMM of the training step (uu_train_set_math 1): fp32 A (M, K) and Bt (N, K) = B^T, both row-major
+ * with pitches lda / ldb (multiples of 4), N % 64 == 0; C fp32 = A . B (+ bias) (ReLU: flags & 1) (+ res: flags & 2). */
+int uu_op_gemm_tf32(const float* A, int64_t lda, int M, int K, const float* Bt, int64_t ldb, int N, const float* bias,
+                    int flags, const float* res, int64_t ldr, float* C, int64_t ldc, void* stream);
 /* The folded epilogues of the bf16 schedule in isolation ("LayerNorm and residual folding"); they
  * replace LayerNormalization + Dense (vit:168-171, :183-195) and Dense + residual add.  Synchronous (temporaries).
  *   out[rows, N] (bf16) = act( LN(x; gamma, beta, eps) . W + bias ),  x bf16 [rows, d], W fp32 (d, N) on the device */

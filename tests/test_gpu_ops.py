@@ -188,6 +188,31 @@ def test_gemm_bf16_tcgen05(lib, M, N, K, flags, c_bf16):
     assert err < (5e-2 if c_bf16 else 1e-3), err
 
 
+@pytest.mark.parametrize("M,N,K,flags", [(300, 384, 384, 0), (1000, 768, 384, 1), (355, 384, 768, 2), (4096, 1152, 384, 0),
+                                         (512, 64, 2304, 2)])
+def test_gemm_tf32_tcgen05(lib, M, N, K, flags):
+    """kind::tf32: fp32 operands straight from TMA, TF32 products (the tensor core drops the low 13 mantissa bits of
+    each operand: truncation, up to 2^-10 relative per operand, biased towards zero), fp32 accumulation.  Against
+    float64 on the same fp32 data the measured max error is 3.4e-3 .. 4.2e-3 on unit-variance outputs (|max| ~ 5):
+    ~1e-3 of the output scale."""
+    rng = np.random.default_rng(M + N + K)
+    A = rng.normal(size=(M, K)).astype(np.float32)
+    Bt = (rng.normal(size=(N, K)) / math.sqrt(K)).astype(np.float32)
+    bias = rng.normal(size=N).astype(np.float32)
+    res = rng.normal(size=(M, N)).astype(np.float32)
+    want = A.astype(np.float64) @ Bt.astype(np.float64).T + bias
+    if flags & 1:
+        want = np.maximum(want, 0)
+    if flags & 2:
+        want = want + res
+    C = dev(res.copy())
+    _lib.check(lib.uu_op_gemm_tf32(P(dev(A)), K, M, K, P(dev(Bt)), K, N, P(dev(bias)), flags, P(C), N, P(C), N, None))
+    torch.cuda.synchronize()
+    err = np.abs(C.cpu().numpy() - want).max()
+    print(f"tf32 gemm {M}x{N}x{K}: max err {err:.2e}")
+    assert err < 8e-3, err
+
+
 @pytest.mark.parametrize("rows,N,relu", [(71, 1152, 0), (300, 768, 1), (36352, 1152, 0), (5000, 128, 1)])
 def test_layernorm_folded_into_gemm(lib, rows, N, relu):
     """EPI_LNFOLD: the GEMM reads the raw bf16 stream with gamma folded into W and finishes LayerNorm (vit:168-171) in

@@ -26,14 +26,21 @@ def _rel(a, b):
     return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-12))
 
 
-@pytest.mark.parametrize("name,B,droppath", [("h36m_81", 6, False), ("h36m_351", 4, False), ("h36m_81", 5, True)])
-def test_loss_and_gradients_match_autograd(name, B, droppath):
+# math "tf32": forward / dgrad GEMMs of the temporal and strided blocks on tcgen05 kind::tf32 (needs >= 256 rows to
+# engage).  TF32 products drop 13 mantissa bits per operand (~1e-3 per GEMM, see test_gemm_tf32_tcgen05) and the
+# LayerNorm / softmax backward passes amplify that where gradients cancel, so this mode is held to a per-tensor
+# relative L2 error of 4e-2 and a max-norm error of 0.2 (measured 2.5e-2 / 0.115; the outliers are ReLU-mask flips in the strided fc1) instead of the fp32 mode's 2e-3 max-norm.
+@pytest.mark.parametrize("name,B,droppath,math", [("h36m_81", 6, False, "fp32"), ("h36m_351", 4, False, "fp32"),
+                                                  ("h36m_81", 5, True, "fp32"), ("h36m_351", 5, False, "tf32"),
+                                                  ("h36m_81", 9, True, "tf32")])
+def test_loss_and_gradients_match_autograd(name, B, droppath, math):
     cfg = UpliftUpsampleConfig.preset(name, BATCH_SIZE=B)
     spec = spec_from_config(cfg)
     w = weights.init_weights(spec, 1, perturb=True)
     x, gt, m = _data(cfg, spec, B)
     model = build_uplift_upsample_transformer(cfg, precision="fp32", weights=w)
-    tr = Trainer(model, cfg, droppath=droppath, seed=7)
+    tr = Trainer(model, cfg, droppath=droppath, seed=7, math=math)
+    gtol, ltol = (2e-3, 2e-5) if math == "fp32" else (3e-2, 2e-3)
     loss = tr.forward_backward(torch.from_numpy(x).cuda(), torch.from_numpy(gt).cuda(), torch.from_numpy(m).cuda())
     torch.cuda.synchronize()
     keeps = None
@@ -43,14 +50,20 @@ def test_loss_and_gradients_match_autograd(name, B, droppath):
         keeps = {k: (kp, torch.tensor(mk, dtype=torch.float64)) for k, (kp, mk) in raw.items()}
         assert all(set(np.unique(mk.numpy())) <= {0.0, 1.0} for _, mk in keeps.values())
     ref_loss, ref_g = TT.loss_and_grads(spec, w, x, gt, m, B, keeps=keeps)
-    assert abs(float(loss.item()) - ref_loss) < 2e-5 * max(1.0, abs(ref_loss))
+    assert abs(float(loss.item()) - ref_loss) < ltol * max(1.0, abs(ref_loss))
     g = tr.get_grads()
     # key biases have an exactly-zero gradient (softmax is shift invariant): compare with an absolute floor
     floor = 1e-6 * max(np.abs(v).max() for v in ref_g.values())
     worst = max((float(np.abs(g[k] - ref_g[k]).max() / (np.abs(ref_g[k]).max() + floor)), k) for k in ref_g)
     print("worst relative gradient error", worst)
+    if math == "tf32":
+        l2 = max((float(np.linalg.norm(g[k] - ref_g[k]) / (np.linalg.norm(ref_g[k]) + floor)), k) for k in ref_g)
+        print("worst relative L2 gradient error", l2)
+        assert l2[0] <= 4e-2 and worst[0] <= 0.2
+        model.close()
+        return
     for k in ref_g:
-        assert np.abs(g[k] - ref_g[k]).max() <= 2e-3 * np.abs(ref_g[k]).max() + floor, k
+        assert np.abs(g[k] - ref_g[k]).max() <= gtol * np.abs(ref_g[k]).max() + floor, k
     model.close()
 
 

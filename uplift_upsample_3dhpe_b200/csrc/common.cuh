@@ -160,6 +160,8 @@ cudaError_t launch_window_copy(const float* video, const int* src, int n_tokens,
 struct TcGemmPlan;   // holds the TMA tensor maps of one GEMM call site
 int tc_gemm_plan_create(TcGemmPlan** out, const bf16* A, long long lda, int M, int K, const bf16* Wt, int N_pad,
                         int N);
+int tc_gemm_plan_create_tf32(TcGemmPlan** out, const float* A, long long lda, int M, int K, const float* Bt, long long ldb,
+                             int N);
 void tc_gemm_plan_destroy(TcGemmPlan* p);
 cudaError_t tc_gemm_launch(TcGemmPlan* p, const Epilogue& epi, void* C, int c_bf16, long long ldc,
                            cudaStream_t st);

@@ -94,6 +94,17 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::tf32: fp32 operands in shared memory read as TF32 (10-bit mantissa), K = 8 per instruction (32 bytes, the same
+// descriptor advance as 16 bf16).  The fp32 training GEMMs (forward and dgrad) run on this.
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -312,6 +323,11 @@ __device__ __forceinline__ void epi_warp_store_tile(uint32_t tmem_acc, int first
   }
 }
 
+// Instruction descriptor, kind::tf32: D = f32, A = B = TF32 (format 2), both K-major.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 template <int BLOCK_N>
 struct TcCfg {
   static constexpr int A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;   // 16 KB
@@ -334,13 +350,14 @@ struct TcCfg {
 // Persistent, warp-specialised: every CTA walks the tile list t = blockIdx.x, += gridDim.x with
 // (m_blk, n_blk) = (t / n_tiles, t % n_tiles), so CTAs running concurrently share the same A rows in L2.
 // Three pipelines: smem ring (TMA -> MMA), TMEM accumulator ring (MMA -> epilogue), tile list.
-template <int BLOCK_N, typename TC, bool TMA_OUT, int EMODE = 0>
+template <int BLOCK_N, typename TC, bool TMA_OUT, int EMODE = 0, bool TF32 = false>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant__ CUtensorMap map_a,
                                                            const __grid_constant__ CUtensorMap map_b,
                                                            const __grid_constant__ CUtensorMap map_c, int M, int N,
                                                            int n_tiles, int K, Epilogue epi, TC* __restrict__ C,
                                                            long long ldc) {
   using Cfg = TcCfg<BLOCK_N>;
+  constexpr int BK = TF32 ? TC_BLOCK_K / 2 : TC_BLOCK_K;      // elements per 128-byte k-block row: 32 fp32 or 64 bf16
   extern __shared__ uint8_t smem_raw[];
   const int m_eff = epi.m_dev ? min(M, *epi.m_dev) : M;
   const int m_tiles = (m_eff + TC_BLOCK_M - 1) / TC_BLOCK_M;
@@ -357,7 +374,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + Cfg::ACC_STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_kb = (K + TC_BLOCK_K - 1) / TC_BLOCK_K;
+  const int num_kb = (K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -399,7 +416,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
           const int nt = tile + tile_step;
           if (nt < total_tiles && (nt % n_tiles) == 0 && !(epi.flags & 256)) {
             const int prow = (nt / n_tiles) * TC_BLOCK_M;
-            for (int kb = 0; kb < num_kb; ++kb) tma_prefetch_2d(&map_a, kb * TC_BLOCK_K, prow);
+            for (int kb = 0; kb < num_kb; ++kb) tma_prefetch_2d(&map_a, kb * BK, prow);
           }
           if constexpr (TMA_OUT && EMODE == EMODE_RESID) {
             // residual rows of this CTA's next tile (the output map describes the same matrix): the epilogue's
@@ -419,8 +436,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
             continue;
           }
           mbar_expect_tx(full_bar + s, Cfg::STAGE_BYTES);
-          tma_load_2d(a_dst, &map_a, full_bar + s, kb * TC_BLOCK_K, row0);
-          tma_load_2d(a_dst + Cfg::A_BYTES, &map_b, full_bar + s, kb * TC_BLOCK_K, col0);
+          tma_load_2d(a_dst, &map_a, full_bar + s, kb * BK, row0);
+          tma_load_2d(a_dst + Cfg::A_BYTES, &map_b, full_bar + s, kb * BK, col0);
         }
       }
     }
@@ -432,7 +449,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
     // pipe, was the pacer of these short-K GEMMs (descriptors are now one add from a per-kernel base, stage and
     // phase are carried incrementally).
     {
-      constexpr uint32_t idesc = make_idesc_bf16(TC_BLOCK_M, BLOCK_N);
+      constexpr uint32_t idesc = TF32 ? make_idesc_tf32(TC_BLOCK_M, BLOCK_N) : make_idesc_bf16(TC_BLOCK_M, BLOCK_N);
       const uint64_t a_desc0 = make_sw128_desc(smem_u32(smem));
       const uint64_t b_desc0 = make_sw128_desc(smem_u32(smem + Cfg::A_BYTES));
       int s = 0;
@@ -453,7 +470,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
 #pragma unroll
             for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
               // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (>>4) address field
-              umma_bf16(tmem_d, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+              if constexpr (TF32) umma_tf32(tmem_d, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+              else umma_bf16(tmem_d, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
             }
             umma_commit(empty_bar + s);           // frees the smem stage when these MMAs retire
             if (kb == num_kb - 1) umma_commit(tmem_full_bar + as);        // accumulator complete
@@ -846,16 +864,16 @@ static PFN_encodeTiled get_encoder() {
 }
 
 static int encode_2d(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box_cols,
-                     uint32_t box_rows) {
+                     uint32_t box_rows, int esize = 2) {
   PFN_encodeTiled enc = get_encoder();
   UU_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
   UU_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16-byte aligned");
-  UU_CHECK((ld_elems * 2) % 16 == 0, "TMA row pitch must be a multiple of 16 bytes");
+  UU_CHECK((ld_elems * esize) % 16 == 0, "TMA row pitch must be a multiple of 16 bytes");
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld_elems * 2};
+  cuuint64_t strides[1] = {ld_elems * (uint64_t)esize};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = enc(map, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   UU_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
@@ -866,6 +884,7 @@ struct TcGemmPlan {
   CUtensorMap map_a, map_b, map_c;
   CUtensorMap map_b2;               // 2-CTA variant: box of block_n / 2 rows of W^T
   int M, N, N_pad, K, block_n;
+  bool tf32 = false;                // fp32 operands, kind::tf32 (training)
   const void* c_ptr = nullptr;      // output the store map was encoded for
   long long c_ld = 0;
 };
@@ -898,16 +917,34 @@ int tc_gemm_plan_create(TcGemmPlan** out, const bf16* A, long long lda, int M, i
   return 0;
 }
 
+// fp32 operands for kind::tf32: A (M, K) row-major with pitch lda, Bt (N, K) row-major with pitch ldb (= W^T, or for a
+// dgrad the weight matrix itself); N % 64 == 0.  fp32 output through the generic epilogue only.
+int tc_gemm_plan_create_tf32(TcGemmPlan** out, const float* A, long long lda, int M, int K, const float* Bt, long long ldb,
+                             int N) {
+  UU_CHECK(M > 0 && N > 0 && K > 0 && N % 64 == 0 && K % 4 == 0, "bad tf32 GEMM shape");
+  TcGemmPlan* p = new TcGemmPlan();
+  p->M = M; p->N = N; p->N_pad = N; p->K = K; p->tf32 = true;
+  p->block_n = (N % 256 == 0) ? 256 : (N % 192 == 0) ? 192 : (N % 128 == 0) ? 128 : 64;
+  if (encode_2d(&p->map_a, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, TC_BLOCK_K / 2, TC_BLOCK_M, 4) ||
+      encode_2d(&p->map_b, Bt, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, TC_BLOCK_K / 2, (uint32_t)p->block_n, 4)) {
+    delete p;
+    return 1;
+  }
+  p->map_c = p->map_a; p->map_b2 = p->map_b;     // unused by the generic epilogue / single-CTA kernel
+  *out = p;
+  return 0;
+}
+
 void tc_gemm_plan_destroy(TcGemmPlan* p) { delete p; }
 
 static int g_num_sms = 0;
 
-template <int BLOCK_N, typename TC, bool TMA_OUT, int EMODE = 0>
+template <int BLOCK_N, typename TC, bool TMA_OUT, int EMODE = 0, bool TF32 = false>
 static cudaError_t tc_launch_t(const TcGemmPlan* p, const Epilogue& epi, void* C, long long ldc, cudaStream_t st) {
   using Cfg = TcCfg<BLOCK_N>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BLOCK_N, TC, TMA_OUT, EMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BLOCK_N, TC, TMA_OUT, EMODE, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
@@ -920,7 +957,7 @@ static cudaError_t tc_launch_t(const TcGemmPlan* p, const Epilogue& epi, void* C
   const int n_tiles = p->N_pad / BLOCK_N;
   const int total = ((p->M + TC_BLOCK_M - 1) / TC_BLOCK_M) * n_tiles;
   const int grid = total < g_num_sms ? total : g_num_sms;          // persistent: one CTA per SM
-  k_gemm_tc<BLOCK_N, TC, TMA_OUT, EMODE><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(
+  k_gemm_tc<BLOCK_N, TC, TMA_OUT, EMODE, TF32><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(
       p->map_a, p->map_b, p->map_c, p->M, p->N, n_tiles, p->K, epi, reinterpret_cast<TC*>(C), ldc);
   return cudaGetLastError();
 }
@@ -975,6 +1012,15 @@ cudaError_t tc_gemm_launch(TcGemmPlan* p, const Epilogue& epi_in, void* C, int c
   static int nores = -1;
   if (nores < 0) { const char* e = getenv("UU_GEMM_NORES"); nores = (e && e[0] == '1') ? 1 : 0; }
   if (nores) epi.flags |= 1024;
+  if (p->tf32) {
+    if (c_bf16 || (epi.flags & (EPI_LNFOLD | EPI_RESID_BF16))) return cudaErrorInvalidValue;
+    switch (p->block_n) {
+      case 256: return tc_launch_t<256, float, false, 0, true>(p, epi, C, ldc, st);
+      case 192: return tc_launch_t<192, float, false, 0, true>(p, epi, C, ldc, st);
+      case 128: return tc_launch_t<128, float, false, 0, true>(p, epi, C, ldc, st);
+      default: return tc_launch_t<64, float, false, 0, true>(p, epi, C, ldc, st);
+    }
+  }
   if (tma_out_eligible(p, epi, c_bf16, ldc)) {
     if (p->c_ptr != C || p->c_ld != ldc) {
       // rows of the output matrix: M, or with a (batch, position) row map the extent it can reach

@@ -1107,6 +1107,19 @@ int uu_op_gemm_bf16(const void* A, int64_t lda, int M, int K, const void* Wt, in
   return 0;
 }
 
+/* tcgen05 kind::tf32 GEMM (training math mode 1): C (M, N) fp32 = A (M, K) fp32 . Bt^T (+ bias) (ReLU) (+ res). */
+int uu_op_gemm_tf32(const float* A, int64_t lda, int M, int K, const float* Bt, int64_t ldb, int N, const float* bias,
+                    int flags, const float* res, int64_t ldr, float* C, int64_t ldc, void* stream) {
+  Epilogue e;
+  e.bias = bias; e.flags = flags & (EPI_RELU | EPI_RESIDUAL); e.res = res; e.ldr = ldr;
+  TcGemmPlan* p = nullptr;
+  if (tc_gemm_plan_create_tf32(&p, A, lda, M, K, Bt, ldb, N)) return 1;
+  cudaError_t err = tc_gemm_launch(p, e, C, 0, ldc, (cudaStream_t)stream);
+  tc_gemm_plan_destroy(p);
+  UU_CUDA(err);
+  return 0;
+}
+
 // ---- the folded-LayerNorm / residual epilogues in isolation (parity tests) ------------------------------------------
 namespace {
 struct TmpPool {

@@ -2,6 +2,8 @@
 // MPJPE loss, hand-derived backward for every trainable tensor, and the fused AdamW/EMA update.
 // All arithmetic is fp32 (the reference trains in fp32); gradients live in one flat buffer with the same
 // layout as the parameters so the data-parallel exchange is a single sum all-reduce.
+#include <unordered_map>
+#include <unordered_set>
 #include <cstring>
 
 #include "model.cuh"
@@ -37,6 +39,11 @@ struct TrainState {
   std::vector<float*> dx_s;                     // per strided level output: [B*Lo, d]
   float *tmp1 = nullptr, *tmp2 = nullptr, *tmp_h = nullptr, *tmp_qkv = nullptr, *dS = nullptr;
   float *partials = nullptr, *loss = nullptr;
+  // math mode 1: forward and dgrad GEMMs of the temporal / strided blocks on tcgen05 kind::tf32 (fp32 data, TF32
+  // products, fp32 accumulation — what TensorFlow 2.4 does by default on Ampere+ GPUs); wgrad stays fp32.
+  int math = 0;
+  std::unordered_map<const float*, float*> wt;   // W (K, N) -> W^T (N, K) copies for the forward GEMMs
+  std::unordered_set<const float*> wt_valid;     // refreshed once per forward/backward call
 };
 
 void train_state_destroy(uu_model* m) {
@@ -66,9 +73,64 @@ static int falloc(TrainState* t, float** p, size_t n_floats, bool zero = false) 
   return 0;
 }
 
+// out[c][r] = in[r][c]
+__global__ void k_transpose_f32(const float* __restrict__ in, int rows, int cols, float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? in[(long long)r * cols + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) out[(long long)c * rows + r] = tile[threadIdx.x][i];
+  }
+}
+
+// tcgen05 kind::tf32 path for the large, regular GEMMs (math mode 1)
+static bool tf32_ok(const Ctx& c, const void* A, long long lda, const void* Bt, long long ldb, int M, int N, int K,
+                    const void* C, long long ldc) {
+  return c.t->math == 1 && M >= 256 && N >= 64 && N % 64 == 0 && K >= 64 && K % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 &&
+         ldc % 4 == 0 && ((uintptr_t)A & 15) == 0 && ((uintptr_t)Bt & 15) == 0 && ((uintptr_t)C & 15) == 0;
+}
+static int tf32_gemm(Ctx& c, const float* A, long long lda, int M, int K, const float* Bt, long long ldb, int N,
+                     const Epilogue& e, float* C, long long ldc) {
+  TcGemmPlan* p = nullptr;
+  if (tc_gemm_plan_create_tf32(&p, A, lda, M, K, Bt, ldb, N)) return 1;
+  cudaError_t err = tc_gemm_launch(p, e, C, 0, ldc, c.st);
+  tc_gemm_plan_destroy(p);      // (tensor maps are kernel parameters: copied at launch)
+  UU_CUDA(err);
+  return 0;
+}
+static int weight_transposed(Ctx& c, const float* Wm, int K, int N, const float** out) {
+  TrainState* t = c.t;
+  auto it = t->wt.find(Wm);
+  if (it == t->wt.end()) {
+    float* p;
+    if (falloc(t, &p, (size_t)K * N)) return 1;
+    it = t->wt.emplace(Wm, p).first;
+  }
+  if (!t->wt_valid.count(Wm)) {
+    k_transpose_f32<<<dim3((N + 31) / 32, (K + 31) / 32), dim3(32, 8), 0, c.st>>>(Wm, K, N, it->second);
+    UU_CUDA(cudaGetLastError());
+    t->wt_valid.insert(Wm);
+  }
+  *out = it->second;
+  return 0;
+}
+
 // y = x @ W + b (forward linear), C may use a row map and a wider leading dimension
 static int lin_fwd(Ctx& c, const float* A, long long lda, int M, int K, const float* Wm, int N, const float* bias,
                    float* C, long long ldc, const RowMap* cmap = nullptr) {
+  if (tf32_ok(c, A, lda, Wm, K, M, N, K, C, ldc)) {
+    const float* Wt;
+    if (weight_transposed(c, Wm, K, N, &Wt)) return 1;
+    Epilogue e;
+    e.bias = bias;
+    if (cmap) e.cmap = *cmap;
+    return tf32_gemm(c, A, lda, M, K, Wt, K, N, e, C, ldc);
+  }
   GemmGen g;
   g.A = A; g.lda = lda; g.B = Wm; g.ldb = N; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K; g.bias = bias;
   if (cmap) g.cmap = *cmap;
@@ -79,7 +141,13 @@ static int lin_fwd(Ctx& c, const float* A, long long lda, int M, int K, const fl
 static int lin_bwd(Ctx& c, const float* X, long long ldx, const float* dY, long long ldy, int M, int K, int N,
                    const float* Wm, float* dX, long long lddx, int accumulate_dx, float* dW, float* db,
                    const RowMap* dxmap = nullptr) {
-  if (dX) {
+  if (dX && tf32_ok(c, dY, ldy, Wm, N, M, K, N, dX, lddx)) {
+    // dX = dY . W^T: the weight matrix (K, N) is already the K-major B operand of this product
+    Epilogue e;
+    if (dxmap) e.cmap = *dxmap;
+    if (accumulate_dx) { e.flags = EPI_RESIDUAL; e.res = dX; e.ldr = lddx; if (dxmap) e.rmap = *dxmap; }
+    if (tf32_gemm(c, dY, ldy, M, N, Wm, N, K, e, dX, lddx)) return 1;
+  } else if (dX) {
     GemmGen g;
     g.A = dY; g.lda = ldy; g.B = Wm; g.ldb = N; g.transB = 1; g.C = dX; g.ldc = lddx; g.M = M; g.N = K; g.K = N;
     g.accumulate = accumulate_dx;
@@ -196,6 +264,7 @@ static int ensure_train(uu_model* m, int B) {
   if (t->B == B) return 0;
   UU_CUDA(cudaDeviceSynchronize());
   free_pool(t->pool);
+  t->wt.clear(); t->wt_valid.clear();          // the transposed-weight copies live in the same pool
   t->sp.assign(s.spatial_depth, BlkTape());
   t->tp.assign(s.temporal_depth, BlkTape());
   t->st.assign(s.n_strided, BlkTape());
@@ -414,7 +483,15 @@ int uu_train_config(uu_model* m, int global_batch, int root_keypoint, float w_ce
 int uu_train_forward_backward(uu_model* m, const float* x2d, const uint8_t* mask, const float* gt3d, int B,
                               int64_t step, float* loss_dev, void* stream) {
   UU_CHECK(m, "null model");
+  if (m->train) m->train->wt_valid.clear();     // weights may have changed since the last call
   return train_fb(m, x2d, mask, gt3d, B, step, loss_dev, (cudaStream_t)stream);
+}
+
+int uu_train_set_math(uu_model* m, int mode) {
+  UU_CHECK(m && (mode == 0 || mode == 1), "math mode: 0 = fp32, 1 = tf32 tensor cores");
+  if (!m->train) m->train = new TrainState();
+  m->train->math = mode;
+  return 0;
 }
 
 int uu_grad_buffer(uu_model* m, float** dev_ptr, int64_t* n_floats) {

@@ -45,8 +45,14 @@ class _DevView:
 
 
 class Trainer:
-    def __init__(self, model, config, droppath: bool = True, seed: int = 0):
+    def __init__(self, model, config, droppath: bool = True, seed: int = 0, math: str = "fp32"):
+        """math: "fp32" (CUDA-core GEMMs, gradients within 2e-3 of fp32 autograd) or "tf32" (forward and dgrad GEMMs of
+        the temporal / strided blocks on the tcgen05 tensor cores with TF32 products — TensorFlow's own default on
+        Ampere-or-newer GPUs)."""
         import torch
+        if math not in ("fp32", "tf32"):
+            raise ValueError("math must be 'fp32' or 'tf32'")
+        self.math = math
         self.torch = torch
         self.model = model
         self.config = config
@@ -68,6 +74,7 @@ class Trainer:
         _lib.check(self.lib.uu_train_config(model._h, int(config.BATCH_SIZE), int(config.ROOT_KEYTPOINT),
                                             float(config.LOSS_WEIGHT_CENTER), float(config.LOSS_WEIGHT_SEQUENCE),
                                             arr, 1 if droppath else 0, seed))
+        _lib.check(self.lib.uu_train_set_math(model._h, 1 if math == "tf32" else 0))
         self._loss = torch.zeros(1, dtype=torch.float32, device=f"cuda:{model.device}")
         self._grad_view = None
 
