@@ -148,6 +148,11 @@ int uu_train_config(uu_model* m, int global_batch, int root_keypoint, float w_ce
                     const float* drop_path_rate3, int droppath_mode, uint64_t seed);
 int uu_train_forward_backward(uu_model* m, const float* x2d, const uint8_t* mask, const float* gt3d, int B,
                               int64_t step, float* loss_dev, void* stream);
+/* Random token masking of the temporal input (net:287-311, :336-338; TOKEN_MASK_RATE > 0 with LEARNABLE_MASKED_TOKEN
+ * false: masked value 0).  Training only; the central token is never masked; drawn per step from the counter RNG seeded
+ * in uu_train_config.  uu_get_token_mask copies the 0 / 1 keep factors [B * n_tok] of the last step to the host. */
+int uu_train_set_token_masking(uu_model* m, float rate);
+int uu_get_token_mask(uu_model* m, float* host, int64_t capacity);
 /* Arithmetic of the training GEMMs.  0 (default): fp32 on CUDA cores, gradients within 2e-3 of fp32 autograd.
  * 1: forward and dgrad GEMMs of the temporal / strided blocks on tcgen05 kind::tf32 (fp32 data, TF32 products, fp32
  *    accumulation) -- what TensorFlow 2.4 itself does on Ampere-or-newer GPUs unless

@@ -84,10 +84,11 @@ def group(w, name):
     return out
 
 
-def forward(spec, w, x2d, stride_mask, keeps=None):
+def forward(spec, w, x2d, stride_mask, keeps=None, token_keep=None):
     """net:388-421.  w: {(group, index): tensor}; x2d (B,N,J,2) already masked by the caller;
     stride_mask (B,N) bool or None.  keeps: optional {(stage, i): (keep_prob, mask)} DropPath masks
-    for training-mode parity (stage in 'spatial' | 'temporal' | 'strided')."""
+    for training-mode parity (stage in 'spatial' | 'temporal' | 'strided').  token_keep: optional (B,N) 0/1 factors
+    = 1 - token_mask of random_token_masking (net:287-311, masked value 0), training mode only."""
     keeps = keeps or {}
     B, N, J, _ = x2d.shape
     H = spec.num_heads
@@ -100,6 +101,8 @@ def forward(spec, w, x2d, stride_mask, keeps=None):
     x = layer_norm(x, sn[0], sn[1], 1e-6).reshape(B, N, J * spec.d_spatial)
     fc = group(w, "spatial_to_temporal_fc")
     x = x @ fc[0] + fc[1]
+    if token_keep is not None:                       # net:336-338, before the strided-input token and the PE
+        x = x * token_keep.to(x.dtype)[..., None]
     inv = None
     if spec.has_strided_input:
         m = stride_mask.to(x.dtype)

@@ -35,14 +35,16 @@ def loss_fn(spec, full, central, keypoints3d, batch_size):
     return spec.loss_weight_center * central_loss + spec.loss_weight_sequence * seq_loss
 
 
-def loss_and_grads(spec, w_np, x2d, keypoints3d, stride_mask, batch_size, keeps=None, dtype=torch.float64):
+def loss_and_grads(spec, w_np, x2d, keypoints3d, stride_mask, batch_size, keeps=None, dtype=torch.float64,
+                   token_keep=None):
     """Returns (loss, {key: grad ndarray}).  x2d is masked here like train.py:474-475."""
     w = OT.to_torch(w_np, dtype, requires_grad=True)
     x = torch.tensor(x2d, dtype=dtype)
     m = torch.tensor(stride_mask) if stride_mask is not None else None
     if spec.has_strided_input:
         x = x * m.to(dtype)[:, :, None, None]
-    full, central = OT.forward(spec, w, x, m, keeps=keeps)
+    tk = torch.tensor(token_keep, dtype=dtype) if token_keep is not None else None
+    full, central = OT.forward(spec, w, x, m, keeps=keeps, token_keep=tk)
     loss = loss_fn(spec, full, central, torch.tensor(keypoints3d, dtype=dtype), batch_size)
     loss.backward()
     return float(loss.detach()), {k: v.grad.numpy().copy() for k, v in w.items()}

@@ -141,6 +141,50 @@ def tta_case(tag, cfg_name, mask_stride, B, seed):
     print(f"tta_{tag}: central {cen.shape} |max| {np.abs(cen).max():.3f}")
 
 
+def token_mask_case(tag, cfg_name, mask_stride, B, seed, rate):
+    """Training-mode forward with random_token_masking (net:287-311, :336-338): TOKEN_MASK_RATE > 0, masked value 0,
+    DropPath off.  The uniform draw the reference consumed is recorded so that the oracle can rebuild the mask."""
+    ref_cfg = RefConfig(config_file=os.path.join(REF, "config", cfg_name + ".json"))
+    ref_cfg.MASK_STRIDE = mask_stride
+    ref_cfg.BATCH_SIZE = B
+    ref_cfg.TOKEN_MASK_RATE = rate
+    ref_cfg.LEARNABLE_MASKED_TOKEN = False
+    ref_cfg.DROP_PATH_RATE = [0.0, 0.0, 0.0]
+    ours = UpliftUpsampleConfig.preset(cfg_name, MASK_STRIDE=mask_stride, TOKEN_MASK_RATE=rate)
+    spec = spec_from_config(ours)
+    w = weights.init_weights(spec, seed=seed, perturb=True)
+    h5 = os.path.join(TMP, f"{tag}.h5")
+    h5lite.save_keras_weights(h5, spec, w)
+    rng = np.random.default_rng(seed + 100)
+    n_tok = ref_cfg.SEQUENCE_LENGTH
+    x = rng.uniform(-1, 1, (B, n_tok, 17, 2)).astype(np.float32)
+    gen = mask_generator(n_tok, ref_cfg.SEQUENCE_STRIDE, mask_stride, "eval", B, 5)
+    masks = np.stack([m for _, m in gen])
+    tf.set_float_dtype("float64")
+    model = ref_build(ref_cfg)
+    ref_weight_io.load_weights_with_callback(model, h5, verbose=False)
+    draws = []
+    orig = tf.random.uniform
+
+    def recording_uniform(*a, **k):
+        u = orig(*a, **k)
+        draws.append(np.asarray(u).copy())
+        return u
+
+    tf.random.set_seed(seed)
+    tf.random.uniform = recording_uniform
+    try:
+        mask = tf.cast(masks, dtype=tf.float32)                                   # train.py:474-478
+        full, central = model([x.astype(tf.float32) * mask[:, :, tf.newaxis, tf.newaxis], masks], training=True)
+    finally:
+        tf.random.uniform = orig
+    assert len(draws) == 1 and draws[0].shape == (B, n_tok), [d.shape for d in draws]
+    np.savez_compressed(os.path.join(args.out, f"tokenmask_{tag}.npz"), config=cfg_name, mask_stride=mask_stride, seed=seed,
+                        rate=rate, x=x, mask=masks, uniform=draws[0], full=np.asarray(full), central=np.asarray(central),
+                        weights_sha=sha(weights.to_flat(spec, w)))
+    print(f"tokenmask_{tag}: masked tokens/window {(draws[0] < rate).sum(1).tolist()} |central|max {np.abs(np.asarray(central)).max():.3f}")
+
+
 def interp_case(tag, stride, lens, seed):
     """Key-frame interpolation by the reference's own numpy function (common/dataset/action_wise_eval.py:76-100)."""
     from common.dataset.action_wise_eval import interpolate_between_keyframes
@@ -198,6 +242,7 @@ if __name__ == "__main__":
     forward_case("h36m_351_sin20", "h36m_351", 20, 5, "eval", seed=3, subsample=5)        # 17/18 valid, every alignment
     forward_case("amass_351_train_masks", "amass_351", [5, 10, 20], 6, "train", seed=4)
     tta_case("h36m_351_sin10", "h36m_351", 10, 3, seed=6)
+    token_mask_case("h36m_81_sin4_rate03", "h36m_81", 4, 3, seed=8, rate=0.3)
     interp_case("stride5", 5, [23, 41, 5, 1], seed=8)
     interp_case("stride2", 2, [9, 12], seed=9)
     # window + stride-mask generator (bit-exact contract)

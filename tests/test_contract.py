@@ -42,7 +42,9 @@ def test_config_json_roundtrip(tmp_path):
 def test_unknown_keys_are_kept_and_unsupported_rejected():
     cfg = UpliftUpsampleConfig.preset("h36m_351", SOME_FUTURE_KEY=3)
     assert cfg.as_dict()["SOME_FUTURE_KEY"] == 3
-    for bad in (dict(OUTPUT_BN=True), dict(DROP_RATE=0.1), dict(TOKEN_MASK_RATE=0.2), dict(ATTENTION_DROP_RATE=0.1)):
+    spec_from_config(UpliftUpsampleConfig.preset("h36m_351", TOKEN_MASK_RATE=0.2))     # masked value 0: supported
+    for bad in (dict(OUTPUT_BN=True), dict(DROP_RATE=0.1), dict(TOKEN_MASK_RATE=0.2, LEARNABLE_MASKED_TOKEN=True),
+                dict(ATTENTION_DROP_RATE=0.1)):
         with pytest.raises(NotImplementedError):
             spec_from_config(UpliftUpsampleConfig.preset("h36m_351", **bad))
 

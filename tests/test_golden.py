@@ -101,3 +101,31 @@ def test_oracle_tta_and_interpolation_match_reference():
         z = np.load(path)
         out = eval_np.interpolate_between_keyframes(z["pred"], z["frame_indices"], int(z["stride"]))
         assert np.array_equal(out, z["out"])           # same float64 operations in the same order
+
+
+def test_random_token_masking_matches_reference_training_forward():
+    """D2 (net:287-311, :336-338): the reference model run with training=True, TOKEN_MASK_RATE = 0.3 and the recorded
+    uniform draw; the oracle's token_keep path must reproduce it (this is what the CUDA training step is tested against
+    in tests/test_gpu_train.py)."""
+    torch = pytest.importorskip("torch")
+    from oracle import forward_torch as OT
+    paths = sorted(glob.glob(os.path.join(GOLDEN, "tokenmask_*.npz")))
+    assert paths
+    for path in paths:
+        z = np.load(path, allow_pickle=False)
+        rate = float(z["rate"])
+        cfg = UpliftUpsampleConfig.preset(str(z["config"]), MASK_STRIDE=int(z["mask_stride"]), TOKEN_MASK_RATE=rate)
+        spec = spec_from_config(cfg)
+        w = weights.init_weights(spec, seed=int(z["seed"]), perturb=True)
+        u, m = z["uniform"], z["mask"]
+        token_mask = (u < rate) & (np.arange(spec.n_tok) != spec.n_tok // 2)[None, :]      # net:291-303
+        assert token_mask.any() and not token_mask[:, spec.n_tok // 2].any()
+        keep = 1.0 - token_mask.astype(np.float64)
+        x = torch.tensor(z["x"], dtype=torch.float64) * torch.tensor(m, dtype=torch.float64)[:, :, None, None]
+        full, central = OT.forward(spec, OT.to_torch(w, torch.float64), x, torch.tensor(m), token_keep=torch.tensor(keep))
+        valid = m.sum(axis=1) > 0
+        assert np.abs(central.numpy()[valid] - z["central"][valid]).max() < 1e-9
+        assert np.abs(full.numpy()[valid] - z["full"][valid]).max() < 1e-9
+        # and the mask matters: without it the outputs differ
+        _, c0 = OT.forward(spec, OT.to_torch(w, torch.float64), x, torch.tensor(m))
+        assert np.abs(c0.numpy()[valid] - z["central"][valid]).max() > 1e-4

@@ -67,6 +67,34 @@ def test_loss_and_gradients_match_autograd(name, B, droppath, math):
     model.close()
 
 
+def test_random_token_masking_matches_autograd():
+    """D2 (net:287-311, :336-338): TOKEN_MASK_RATE > 0, masked value 0.  The mask the library drew is fed to the oracle;
+    the central token must never be masked and the rate must be plausible."""
+    B = 6
+    cfg = UpliftUpsampleConfig.preset("h36m_81", BATCH_SIZE=B, TOKEN_MASK_RATE=0.3)
+    spec = spec_from_config(cfg)
+    w = weights.init_weights(spec, 4, perturb=True)
+    x, gt, m = _data(cfg, spec, B, seed=3)
+    model = build_uplift_upsample_transformer(cfg, precision="fp32", weights=w)
+    tr = Trainer(model, cfg, droppath=False, seed=11)
+    loss = tr.forward_backward(torch.from_numpy(x).cuda(), torch.from_numpy(gt).cuda(), torch.from_numpy(m).cuda())
+    torch.cuda.synchronize()
+    keep = tr.token_keep(B)
+    assert set(np.unique(keep)) <= {0.0, 1.0} and (keep[:, spec.n_tok // 2] == 1).all()
+    assert 0.1 < 1 - keep.mean() < 0.5
+    ref_loss, ref_g = TT.loss_and_grads(spec, w, x, gt, m, B, token_keep=keep)
+    assert abs(float(loss.item()) - ref_loss) < 2e-5 * max(1.0, abs(ref_loss))
+    g = tr.get_grads()
+    floor = 1e-6 * max(np.abs(v).max() for v in ref_g.values())
+    for k in ref_g:
+        assert np.abs(g[k] - ref_g[k]).max() <= 2e-3 * np.abs(ref_g[k]).max() + floor, k
+    # a second step draws a different mask
+    tr.iterations += 1
+    tr.forward_backward(torch.from_numpy(x).cuda(), torch.from_numpy(gt).cuda(), torch.from_numpy(m).cuda())
+    assert (tr.token_keep(B) != keep).any()
+    model.close()
+
+
 def test_three_adamw_steps_match_oracle():
     cfg = UpliftUpsampleConfig.preset("h36m_81", BATCH_SIZE=4)
     spec = spec_from_config(cfg)

@@ -129,6 +129,8 @@ def _declare(lib) -> None:
     lib.uu_op_gemm_bf16.argtypes = [c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int,
                                     c_void_p, c_int64, c_void_p, c_int, c_int64, c_void_p]
     lib.uu_train_set_math.argtypes = [c_void_p, c_int]
+    lib.uu_train_set_token_masking.argtypes = [c_void_p, c_float]
+    lib.uu_get_token_mask.argtypes = [c_void_p, c_void_p, c_int64]
     lib.uu_op_gemm_tf32.argtypes = [c_void_p, c_int64, c_int, c_int, c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p,
                                     c_int64, c_void_p, c_int64, c_void_p]
     lib.uu_op_ln_gemm_bf16.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int,
@@ -146,7 +148,7 @@ EXPORTS = [
     "uu_forward", "uu_forward_host", "uu_forward_video", "uu_forward_video_host", "uu_op_window_gather",
     "uu_set_flip_order", "uu_forward_tta", "uu_forward_video_tta", "uu_op_keyframe_interp", "uu_last_launch_count", "uu_set_profiling", "uu_get_profile", "uu_stride_mask",
     "uu_train_config", "uu_train_forward_backward", "uu_grad_buffer", "uu_get_grad", "uu_get_droppath_scale",
-    "uu_adamw_step", "uu_get_ema_weight", "uu_train_set_math",
+    "uu_adamw_step", "uu_get_ema_weight", "uu_train_set_math", "uu_train_set_token_masking", "uu_get_token_mask",
     "uu_op_build_gather", "uu_op_token_fill", "uu_op_layernorm", "uu_op_attention", "uu_op_spatial", "uu_op_gemm_f32",
     "uu_op_gemm_bf16", "uu_op_gemm_tf32", "uu_op_ln_gemm_bf16", "uu_op_resid_gemm_bf16",
 ]

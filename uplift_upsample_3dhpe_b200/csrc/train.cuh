@@ -33,6 +33,8 @@ cudaError_t launch_act_bwd_mapped(const float* hp, const float* dhp, const RowMa
 cudaError_t launch_residual(const float* base, const RowMap& bmap, const float* y, const float* scale,
                             int rows_per_sample, const float* table, int period, long long rows, int d, float* out,
                             cudaStream_t st);
+cudaError_t launch_token_mask_draw(unsigned long long seed, unsigned long long stream, long long rows, int n_tok, float rate,
+                                   float* keep, cudaStream_t st);
 cudaError_t launch_scale_rows(const float* src, const float* scale, int rps, long long rows, int d, float* dst,
                               cudaStream_t st);
 cudaError_t launch_scatter_add(const float* src, const RowMap& dmap, long long rows, int d, float* dst, cudaStream_t st);

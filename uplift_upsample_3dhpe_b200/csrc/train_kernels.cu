@@ -752,6 +752,26 @@ __global__ void k_droppath_scale(unsigned long long seed, unsigned long long str
   const float u = (float)(z >> 40) * (1.0f / 16777216.0f);      // [0, 1)
   scale[i] = floorf(u + keep) / keep;
 }
+// Random token masking (net:287-311, training only, TOKEN_MASK_RATE > 0, masked value 0): keep[b, n] = 0 where
+// u < rate and n != n_tok / 2 (the central token is never masked), else 1; x[row] *= keep[row].
+__global__ void k_token_mask_draw(unsigned long long seed, unsigned long long stream, long long rows, int n_tok, float rate,
+                                  float* __restrict__ keep) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ULL * (stream * 0x100000001B3ULL + (unsigned long long)i + 1ULL);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  z ^= z >> 31;
+  const float u = (float)(z >> 40) * (1.0f / 16777216.0f);
+  keep[i] = (u < rate && (int)(i % n_tok) != n_tok / 2) ? 0.f : 1.f;
+}
+cudaError_t launch_token_mask_draw(unsigned long long seed, unsigned long long stream, long long rows, int n_tok, float rate,
+                                   float* keep, cudaStream_t st) {
+  if (rows == 0) return cudaSuccess;
+  k_token_mask_draw<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(seed, stream, rows, n_tok, rate, keep);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_droppath_scale(unsigned long long seed, unsigned long long stream, long long n, float keep,
                                   float* scale, cudaStream_t st) {
   if (n == 0) return cudaSuccess;

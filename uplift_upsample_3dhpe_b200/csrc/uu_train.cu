@@ -41,6 +41,8 @@ struct TrainState {
   float *partials = nullptr, *loss = nullptr;
   // math mode 1: forward and dgrad GEMMs of the temporal / strided blocks on tcgen05 kind::tf32 (fp32 data, TF32
   // products, fp32 accumulation — what TensorFlow 2.4 does by default on Ampere+ GPUs); wgrad stays fp32.
+  float token_mask_rate = 0.f;                  // TOKEN_MASK_RATE (net:287-311; masked value 0), training only
+  float* tok_keep = nullptr;                    // [R] 0 / 1 factors drawn for the current step
   int math = 0;
   std::unordered_map<const float*, float*> wt;   // W (K, N) -> W^T (N, K) copies for the forward GEMMs
   std::unordered_set<const float*> wt_valid;     // refreshed once per forward/backward call
@@ -309,6 +311,7 @@ static int ensure_train(uu_model* m, int B) {
       falloc(t, &t->tmp_qkv, std::max(Rs * 3 * ds, R * 3 * d)) || falloc(t, &t->dS, R * J * ds))
     return 1;
   if (falloc(t, &t->partials, loss_blocks(B, (int)N, (int)J, true) + 8) || falloc(t, &t->loss, 4)) return 1;
+  if (falloc(t, &t->tok_keep, R)) return 1;
   t->B = B;
   return 0;
 }
@@ -359,6 +362,11 @@ static int train_fb(uu_model* m, const float* x2d, const uint8_t* mask, const fl
   if (lin_fwd(c, t->sp_normed, J * ds, (int)R, J * ds, W(m, "spatial_to_temporal_fc", 0), d,
               W(m, "spatial_to_temporal_fc", 1), t->s4, d))
     return 1;
+  if (t->token_mask_rate > 0.f) {   // random token masking (net:336-338) before the upsampling-token fill and the PE add
+    UU_TL(launch_token_mask_draw(t->seed, (unsigned long long)step * 64ULL + 63ULL, R, N, t->token_mask_rate, t->tok_keep,
+                                 stream));
+    UU_TL(launch_scale_rows(t->s4, t->tok_keep, 1, R, d, t->s4, stream));
+  }
   UU_TL(launch_fill_fwd(t->s4, use_mask ? mask : nullptr, use_mask ? W(m, "strided_input_token_layer", 0) : nullptr,
                         W(m, "temporal_pe", 0), N, R, d, t->tp[0].x0, stream));
   const BlkDims tp_dims{d, h, N, H, (long long)B, 0};
@@ -449,6 +457,7 @@ static int train_fb(uu_model* m, const float* x2d, const uint8_t* mask, const fl
     UU_TL(launch_period_sum(t->dx_t, R, 1, d, mask, 0, G(m, "strided_input_token_layer", 0), stream));
     UU_TL(launch_fill_bwd(t->dx_t, mask, R, d, t->dx_t, stream));
   }
+  if (t->token_mask_rate > 0.f) UU_TL(launch_scale_rows(t->dx_t, t->tok_keep, 1, R, d, t->dx_t, stream));
   if (lin_bwd(c, t->sp_normed, J * ds, t->dx_t, d, (int)R, J * ds, d, W(m, "spatial_to_temporal_fc", 0), t->dS, J * ds, 0,
               G(m, "spatial_to_temporal_fc", 0), G(m, "spatial_to_temporal_fc", 1)))
     return 1;
@@ -485,6 +494,26 @@ int uu_train_forward_backward(uu_model* m, const float* x2d, const uint8_t* mask
   UU_CHECK(m, "null model");
   if (m->train) m->train->wt_valid.clear();     // weights may have changed since the last call
   return train_fb(m, x2d, mask, gt3d, B, step, loss_dev, (cudaStream_t)stream);
+}
+
+int uu_train_set_token_masking(uu_model* m, float rate) {
+  UU_CHECK(m && rate >= 0.f && rate < 1.f, "TOKEN_MASK_RATE must be in [0, 1)");
+  if (!m->train) m->train = new TrainState();
+  m->train->token_mask_rate = rate;
+  return 0;
+}
+
+int uu_get_token_mask(uu_model* m, float* host, int64_t capacity) {
+  UU_CHECK(m && m->train && host && m->train->tok_keep, "no training step has run yet");
+  const long long R = (long long)m->train->B * m->spec.n_tok;
+  UU_CHECK(R <= capacity, "output buffer too small");
+  UU_CUDA(cudaSetDevice(m->device));
+  if (m->train->token_mask_rate > 0.f) {
+    UU_CUDA(cudaMemcpy(host, m->train->tok_keep, sizeof(float) * R, cudaMemcpyDeviceToHost));
+  } else {
+    for (long long i = 0; i < R; ++i) host[i] = 1.f;
+  }
+  return 0;
 }
 
 int uu_train_set_math(uu_model* m, int mode) {

@@ -84,8 +84,12 @@ def spec_from_config(cfg) -> ModelSpec:
         raise NotImplementedError("OUTPUT_BN=true is not on the hot path (no shipped config enables it)")
     if cfg.DROP_RATE != 0.0 or cfg.ATTENTION_DROP_RATE != 0.0:
         raise NotImplementedError("DROP_RATE / ATTENTION_DROP_RATE > 0 are not supported (0.0 in every shipped config)")
-    if cfg.TOKEN_MASK_RATE != 0.0:
-        raise NotImplementedError("TOKEN_MASK_RATE > 0 is not supported (0.0 in every shipped config)")
+    if not 0.0 <= float(cfg.TOKEN_MASK_RATE) < 1.0:
+        raise ValueError("TOKEN_MASK_RATE must be in [0, 1)")
+    if cfg.TOKEN_MASK_RATE != 0.0 and cfg.LEARNABLE_MASKED_TOKEN:
+        # the learnable variant adds a weight (net:219-220) that no shipped checkpoint contains
+        raise NotImplementedError("TOKEN_MASK_RATE > 0 with LEARNABLE_MASKED_TOKEN=true is not supported "
+                                  "(masked value 0 is; 0.0 in every shipped config)")
     if cfg.SPATIAL_TRANSFORMER_BLOCKS <= 0 or cfg.TEMPORAL_TRANSFORMER_BLOCKS <= 0:
         raise NotImplementedError("spatial/temporal depth 0 variants are not supported")
     if not cfg.QKV_BIAS:

@@ -75,6 +75,8 @@ class Trainer:
                                             float(config.LOSS_WEIGHT_CENTER), float(config.LOSS_WEIGHT_SEQUENCE),
                                             arr, 1 if droppath else 0, seed))
         _lib.check(self.lib.uu_train_set_math(model._h, 1 if math == "tf32" else 0))
+        # random token masking of the temporal input (net:287-311), masked value 0; 0.0 in every shipped config
+        _lib.check(self.lib.uu_train_set_token_masking(model._h, float(getattr(config, "TOKEN_MASK_RATE", 0.0) or 0.0)))
         self._loss = torch.zeros(1, dtype=torch.float32, device=f"cuda:{model.device}")
         self._grad_view = None
 
@@ -139,6 +141,13 @@ class Trainer:
             _lib.check(self.lib.uu_get_ema_weight(self.model._h, g.encode(), k, a.ctypes.data_as(c_void_p), a.size))
             out[(g, k)] = a
         return out
+
+    def token_keep(self, B: int):
+        """(B, n_tok) 0/1 factors (1 - token mask) drawn by the last step's random token masking."""
+        n = B * self.model.spec.n_tok
+        buf = np.empty(n, dtype=np.float32)
+        _lib.check(self.lib.uu_get_token_mask(self.model._h, buf.ctypes.data_as(c_void_p), n))
+        return buf.reshape(B, self.model.spec.n_tok)
 
     def droppath_keeps(self, B: int):
         """{(stage, block): (keep_prob, mask ndarray)} actually used by the last step, in the oracle's format."""
