@@ -56,7 +56,7 @@ def _worker(rank, world, port, out):
 
 
 def test_two_rank_gradient_sum_equals_single_process():
-    mgr = mp.Manager()
+    mgr = mp.get_context("spawn").Manager()      # (fork from a multi-threaded parent can deadlock)
     out = mgr.dict()
     mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
     assert out["grad_err"] < 1e-10 and out["loss_err"] < 1e-12
