@@ -117,6 +117,13 @@ int uu_forward_video_tta(uu_model* m, const float* video2d, int T, const int32_t
  * a video copy it. */
 int uu_op_keyframe_interp(const float* pred, const int32_t* frame_indices, int n, int keyframe_stride, int values_per_frame,
                           float* out, void* stream);
+/* Evaluation metrics on the device (common/dataset/metrics.py:13-81): root-aligned MPJPE and
+ * N-MPJPE (root alignment + optimal per-pose scale).  pred (n, n_joints, 3) and gt (n, n_joints, 4 = x, y, z, valid) are
+ * device arrays; jpe / njpe (optional, device, (n, n_joints)) receive the per-joint errors with -1 at invalid joints
+ * (the reference's normalize=False form); result_host[3] = {mpjpe, nmpjpe, number of valid joints}.  Synchronous.
+ * (P-MPJPE needs a per-pose SVD, metrics.py:84-117, and stays on the host.) */
+int uu_op_pose_metrics(const float* pred, const float* gt, int n, int n_joints, int root, float* jpe, float* njpe,
+                       double* result_host, void* stream);
 /* The gather alone: src (B*n_tok int32 source frame, -1 = zeros), mask (B*n_tok), and, when x2d != NULL, the
  * materialised (B, n_tok, n_joints, 2) windows exactly as the reference generator yields them (unmasked). */
 int uu_op_window_gather(const float* video2d, int T, const int32_t* centers, int B, int n_tok, int n_joints, int s_out,

@@ -2,7 +2,9 @@
 
 flip_tta:      eval.py:152-180 (flip test-time augmentation of both outputs)
 interpolate:   common/dataset/action_wise_eval.py:76-100 (key-frame interpolation)
-Pinned against the reference's own code by tests/golden/tta_*.npz and interp_*.npz (scripts/make_golden.py)."""
+mpjpe, nmpjpe: common/dataset/metrics.py:13-81, :120-133 (root alignment; N-MPJPE with optimal per-pose scale)
+Pinned against the reference's own code by tests/golden/tta_*.npz, interp_*.npz and metrics_*.npz
+(scripts/make_golden.py)."""
 import numpy as np
 
 from . import forward_np
@@ -45,3 +47,25 @@ def interpolate_between_keyframes(pred, frame_indices, stride):
         elif last is not None:
             out[i] = pred[last]
     return out
+
+
+def _root_aligned(pred, gt, root):
+    g = gt[:, :, :3] - gt[:, root, None, :3]
+    p = pred - pred[:, root, None, :]
+    return p, g, gt[:, :, 3] > 0
+
+
+def mpjpe(pred, gt, root, normalize=True):
+    """metrics.py:13-37: mean over valid joints of ||(p - p_root) - (g - g_root)||; per joint (-1 = invalid) otherwise."""
+    p, g, valid = _root_aligned(np.asarray(pred, np.float64), np.asarray(gt, np.float64), root)
+    d = np.sqrt(((p - g) ** 2).sum(-1))
+    return np.where(valid, d, 0.0).sum() / valid.sum() if normalize else np.where(valid, d, -1.0)
+
+
+def nmpjpe(pred, gt, root, normalize=True):
+    """metrics.py:40-81 with alignment="root" and optimal_scaling (:120-133): s = <p, g> / <p, p> over valid joints."""
+    p, g, valid = _root_aligned(np.asarray(pred, np.float64), np.asarray(gt, np.float64), root)
+    v = valid[:, :, None]
+    s = (p * g * v).sum((1, 2)) / (p * p * v).sum((1, 2))
+    d = np.sqrt(((p * s[:, None, None] - g) ** 2).sum(-1))
+    return np.where(valid, d, 0.0).sum() / valid.sum() if normalize else np.where(valid, d, -1.0)

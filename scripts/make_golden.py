@@ -198,6 +198,23 @@ def interp_case(tag, stride, lens, seed):
     print(f"interp_{tag}: {frame_indices.size} frames, {int(keyframes.sum())} key frames")
 
 
+def metrics_case(tag, n, seed, root=0):
+    """MPJPE / N-MPJPE by the reference's own numpy functions (common/dataset/metrics.py:13-81)."""
+    from common.dataset import metrics as ref_metrics
+    rng = np.random.default_rng(seed)
+    gt = rng.normal(0, 0.4, (n, 17, 4)).astype(np.float32)
+    gt[:, :, 3] = (rng.random((n, 17)) > 0.15).astype(np.float32)         # some invalid joints
+    gt[:, root, 3] = 1.0
+    pred = (gt[:, :, :3] * rng.uniform(0.7, 1.3, (n, 1, 1)) + rng.normal(0, 0.05, (n, 17, 3)) + rng.normal(0, 1, (n, 1, 3))).astype(np.float32)
+    p64, g64 = pred.astype(np.float64), gt.astype(np.float64)
+    np.savez_compressed(os.path.join(args.out, f"metrics_{tag}.npz"), pred=pred, gt=gt, root=root,
+                        mpjpe=ref_metrics.mpjpe(p64, g64, root_index=root),
+                        nmpjpe=ref_metrics.nmpjpe(p64, g64, root_index=root),
+                        jpe=ref_metrics.mpjpe(p64, g64, root_index=root, normalize=False),
+                        njpe=ref_metrics.nmpjpe(p64, g64, root_index=root, normalize=False))
+    print(f"metrics_{tag}: mpjpe {ref_metrics.mpjpe(p64, g64, root_index=root):.5f} nmpjpe {ref_metrics.nmpjpe(p64, g64, root_index=root):.5f}")
+
+
 def run_generator(n_tok, stride, mask_stride, mode, n_windows, video_len=400, seed=0, subsample=1):
     """Drive the reference's H36mSequenceGenerator on one synthetic video."""
     rng = np.random.default_rng(7)
@@ -243,6 +260,8 @@ if __name__ == "__main__":
     forward_case("amass_351_train_masks", "amass_351", [5, 10, 20], 6, "train", seed=4)
     tta_case("h36m_351_sin10", "h36m_351", 10, 3, seed=6)
     token_mask_case("h36m_81_sin4_rate03", "h36m_81", 4, 3, seed=8, rate=0.3)
+    metrics_case("n300_root0", 300, seed=9, root=0)
+    metrics_case("n77_root6", 77, seed=10, root=6)
     interp_case("stride5", 5, [23, 41, 5, 1], seed=8)
     interp_case("stride2", 2, [9, 12], seed=9)
     # window + stride-mask generator (bit-exact contract)

@@ -129,3 +129,17 @@ def test_random_token_masking_matches_reference_training_forward():
         # and the mask matters: without it the outputs differ
         _, c0 = OT.forward(spec, OT.to_torch(w, torch.float64), x, torch.tensor(m))
         assert np.abs(c0.numpy()[valid] - z["central"][valid]).max() > 1e-4
+
+
+def test_pose_metrics_match_reference():
+    """MPJPE / N-MPJPE restatement (oracle/eval_np.py) against common/dataset/metrics.py run on the same poses."""
+    from oracle import eval_np as E
+    paths = sorted(glob.glob(os.path.join(GOLDEN, "metrics_*.npz")))
+    assert len(paths) >= 2
+    for path in paths:
+        z = np.load(path, allow_pickle=False)
+        root = int(z["root"])
+        assert abs(E.mpjpe(z["pred"], z["gt"], root) - float(z["mpjpe"])) < 1e-12
+        assert abs(E.nmpjpe(z["pred"], z["gt"], root) - float(z["nmpjpe"])) < 1e-12
+        assert np.abs(E.mpjpe(z["pred"], z["gt"], root, normalize=False) - z["jpe"]).max() < 1e-12
+        assert np.abs(E.nmpjpe(z["pred"], z["gt"], root, normalize=False) - z["njpe"]).max() < 1e-12

@@ -144,3 +144,24 @@ def test_video_tta_equals_tta_on_materialised_windows():
     torch.cuda.synchronize()
     assert torch.equal(c1, c2) and torch.equal(f1, f2)
     model.close()
+
+
+def test_pose_metrics_on_device_match_reference_golden():
+    """uu_op_pose_metrics against common/dataset/metrics.py (tests/golden/metrics_*.npz): fp32 on the device, float64 in
+    the reference."""
+    import ctypes
+    from uplift_upsample_3dhpe_b200 import _lib
+    lib = _lib.load()
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    for path in sorted(glob.glob(os.path.join(GOLDEN, "metrics_*.npz"))):
+        z = np.load(path, allow_pickle=False)
+        pred, gt = torch.from_numpy(z["pred"]).cuda(), torch.from_numpy(z["gt"]).cuda()
+        n, J = pred.shape[0], pred.shape[1]
+        jpe = torch.empty((n, J), device="cuda")
+        njpe = torch.empty((n, J), device="cuda")
+        res = (ctypes.c_double * 3)()
+        _lib.check(lib.uu_op_pose_metrics(P(pred), P(gt), n, J, int(z["root"]), P(jpe), P(njpe), res, None))
+        assert abs(res[0] - float(z["mpjpe"])) < 1e-6 and abs(res[1] - float(z["nmpjpe"])) < 1e-6
+        assert res[2] == float((z["gt"][:, :, 3] > 0).sum())
+        assert np.abs(jpe.cpu().numpy() - z["jpe"]).max() < 2e-6
+        assert np.abs(njpe.cpu().numpy() - z["njpe"]).max() < 2e-6

@@ -160,6 +160,9 @@ cudaError_t launch_window_copy(const float* video, const int* src, int n_tokens,
 struct TcGemmPlan;   // holds the TMA tensor maps of one GEMM call site
 int tc_gemm_plan_create(TcGemmPlan** out, const bf16* A, long long lda, int M, int K, const bf16* Wt, int N_pad,
                         int N);
+// MPJPE / N-MPJPE (metrics.py:13-81): pred (n, J, 3), gt (n, J, 4 = x, y, z, valid); out[3] = mpjpe, nmpjpe, valid count
+cudaError_t launch_pose_metrics(const float* pred, const float* gt, int n, int J, int root, float* jpe, float* njpe,
+                                float* sums, double* out, cudaStream_t st);
 int tc_gemm_plan_create_tf32(TcGemmPlan** out, const float* A, long long lda, int M, int K, const float* Bt, long long ldb,
                              int N);
 void tc_gemm_plan_destroy(TcGemmPlan* p);

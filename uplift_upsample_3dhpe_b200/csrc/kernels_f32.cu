@@ -717,6 +717,65 @@ cudaError_t launch_residual_ln_bx(const bf16* xsrc, const RowMap& smap, const bf
 }
 
 // =================================================================================================
+// Evaluation metrics on the device: root-aligned MPJPE and N-MPJPE (root alignment + per-pose
+// optimal scale s = <p, g> / <p, p> over the valid joints), common/dataset/metrics.py:13-81, :120-133.
+// One warp per pose, lane == joint (J <= 32).  per-joint outputs are -1 where the ground truth is invalid
+// (normalize=False form); sums[pose] = (sum of valid MPJPE distances, sum of valid N-MPJPE distances, valid count),
+// reduced in double by one block in pose order (deterministic).
+// =================================================================================================
+__global__ void k_pose_metrics(const float* __restrict__ pred, const float* __restrict__ gt, int n, int J, int root,
+                               float* __restrict__ jpe, float* __restrict__ njpe, float* __restrict__ sums) {
+  const int lane = threadIdx.x & 31;
+  const int pose = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (pose >= n) return;
+  const float* p = pred + (long long)pose * J * 3;
+  const float* g = gt + (long long)pose * J * 4;
+  const bool in = lane < J;
+  const float pr0 = p[root * 3], pr1 = p[root * 3 + 1], pr2 = p[root * 3 + 2];
+  const float gr0 = g[root * 4], gr1 = g[root * 4 + 1], gr2 = g[root * 4 + 2];
+  float px = 0.f, py = 0.f, pz = 0.f, gx = 0.f, gy = 0.f, gz = 0.f;
+  bool valid = false;
+  if (in) {
+    px = p[lane * 3] - pr0; py = p[lane * 3 + 1] - pr1; pz = p[lane * 3 + 2] - pr2;
+    gx = g[lane * 4] - gr0; gy = g[lane * 4 + 1] - gr1; gz = g[lane * 4 + 2] - gr2;
+    valid = g[lane * 4 + 3] > 0.f;
+  }
+  const float d0 = sqrtf((px - gx) * (px - gx) + (py - gy) * (py - gy) + (pz - gz) * (pz - gz));
+  const float nom = warp_sum(valid ? px * gx + py * gy + pz * gz : 0.f);
+  const float den = warp_sum(valid ? px * px + py * py + pz * pz : 0.f);
+  const float sc = nom / den;
+  const float d1 = sqrtf((sc * px - gx) * (sc * px - gx) + (sc * py - gy) * (sc * py - gy) + (sc * pz - gz) * (sc * pz - gz));
+  if (in) {
+    if (jpe) jpe[(long long)pose * J + lane] = valid ? d0 : -1.f;
+    if (njpe) njpe[(long long)pose * J + lane] = valid ? d1 : -1.f;
+  }
+  const float s0 = warp_sum(valid ? d0 : 0.f), s1 = warp_sum(valid ? d1 : 0.f), cnt = warp_sum(valid ? 1.f : 0.f);
+  if (lane == 0) { sums[pose * 3] = s0; sums[pose * 3 + 1] = s1; sums[pose * 3 + 2] = cnt; }
+}
+__global__ void k_pose_metrics_reduce(const float* __restrict__ sums, int n, double* __restrict__ out) {
+  __shared__ double sh[3][256];
+  double a = 0, b = 0, c = 0;
+  // contiguous slices per thread, then a fixed-order tree: deterministic
+  const int per = (n + 255) / 256, lo = threadIdx.x * per, hi = min(n, lo + per);
+  for (int i = lo; i < hi; ++i) { a += sums[i * 3]; b += sums[i * 3 + 1]; c += sums[i * 3 + 2]; }
+  sh[0][threadIdx.x] = a; sh[1][threadIdx.x] = b; sh[2][threadIdx.x] = c;
+  __syncthreads();
+  for (int o = 128; o; o >>= 1) {
+    if (threadIdx.x < o)
+      for (int k = 0; k < 3; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { out[0] = sh[0][0] / sh[2][0]; out[1] = sh[1][0] / sh[2][0]; out[2] = sh[2][0]; }
+}
+cudaError_t launch_pose_metrics(const float* pred, const float* gt, int n, int J, int root, float* jpe, float* njpe,
+                                float* sums, double* out, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  k_pose_metrics<<<(n + 7) / 8, 256, 0, st>>>(pred, gt, n, J, root, jpe, njpe, sums);
+  k_pose_metrics_reduce<<<1, 256, 0, st>>>(sums, n, out);
+  return cudaGetLastError();
+}
+
+// =================================================================================================
 // K5 (CUDA-core version): softmax attention per (window, head), S <= 128 keys, thread == query.
 // Literal reference arithmetic: logits = q.k / sqrt(dh) + keymask * -1e9 in fp32 (vit:117-123), so
 // an all-masked window reproduces the reference's uniform attention.

@@ -990,6 +990,23 @@ int uu_op_keyframe_interp(const float* pred, const int32_t* frame_indices, int n
   return 0;
 }
 
+int uu_op_pose_metrics(const float* pred, const float* gt, int n, int n_joints, int root, float* jpe, float* njpe,
+                       double* result_host, void* stream) {
+  UU_CHECK(pred && gt && result_host && n > 0 && n_joints >= 1 && n_joints <= 32 && root >= 0 && root < n_joints,
+           "bad argument (n_joints <= 32)");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* sums = nullptr;
+  double* out = nullptr;
+  UU_CUDA(cudaMalloc(&sums, sizeof(float) * 3 * (size_t)n));
+  cudaError_t e = cudaMalloc(&out, sizeof(double) * 3);
+  if (e == cudaSuccess) e = launch_pose_metrics(pred, gt, n, n_joints, root, jpe, njpe, sums, out, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(result_host, out, sizeof(double) * 3, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(sums); cudaFree(out);
+  UU_CUDA(e);
+  return 0;
+}
+
 int uu_op_window_gather(const float* video2d, int T, const int32_t* centers, int B, int n_tok, int n_joints, int s_out,
                         int s_in, int pad_copy, int32_t* src, uint8_t* mask, float* x2d, void* stream) {
   UU_CHECK(centers && src && mask && B > 0 && T > 0 && n_tok > 0, "bad argument");

@@ -281,6 +281,24 @@ def keyframe_interp(pred, frame_indices, keyframe_stride: int):
     return out
 
 
+def pose_metrics(pred, gt, root_index: int, per_joint: bool = False):
+    """metrics.mpjpe / metrics.nmpjpe (root alignment) on the device: pred (n, J, 3), gt (n, J, 4 = x, y, z, valid) float32
+    cuda.  Returns (mpjpe, nmpjpe) floats, plus the two (n, J) per-joint arrays (-1 = invalid joint) when per_joint."""
+    import ctypes
+    torch = _torch()
+    lib = _lib.load()
+    pred, gt = pred.contiguous().float(), gt.contiguous().float()
+    n, J = pred.shape[0], pred.shape[1]
+    assert tuple(pred.shape) == (n, J, 3) and tuple(gt.shape) == (n, J, 4) and gt.device == pred.device
+    jpe = torch.empty((n, J), device=pred.device) if per_joint else None
+    njpe = torch.empty((n, J), device=pred.device) if per_joint else None
+    res = (ctypes.c_double * 3)()
+    stream = torch.cuda.current_stream(pred.device).cuda_stream
+    _lib.check(lib.uu_op_pose_metrics(pred.data_ptr(), gt.data_ptr(), n, J, int(root_index),
+                                      jpe.data_ptr() if per_joint else None, njpe.data_ptr() if per_joint else None, res, stream))
+    return (res[0], res[1], jpe, njpe) if per_joint else (res[0], res[1])
+
+
 def host_stride_mask(n_tok: int, s_out: int, s_in: int, shift: int = 0) -> np.ndarray:
     """uu_stride_mask: the C-ABI twin of stride_mask.stride_mask (bit-exact check target)."""
     lib = _lib.load()
