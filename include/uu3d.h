@@ -117,6 +117,12 @@ int uu_forward_video_tta(uu_model* m, const float* video2d, int T, const int32_t
  * a video copy it. */
 int uu_op_keyframe_interp(const float* pred, const int32_t* frame_indices, int n, int keyframe_stride, int values_per_frame,
                           float* out, void* stream);
+/* Training-data synthesis on the device (uplifiting_dataset.py:669-761 tf_world_to_cam_and_2d):
+ * seq3d (B, points_per_sample, 3) world coordinates, cams (B, 18) = unit quaternion (w, x, y, z), translation (3),
+ * intrinsics (resolution 2, focal length 2, centre 2, radial 3, tangential 2).  cam3d (B, P, 3) and / or p2d (B, P, 2)
+ * receive the camera-space poses and their Human3.6M projection (x/z, y/z clamped to [-1, 1] as in the reference). */
+int uu_op_world_to_cam_and_2d(const float* seq3d, const float* cams, int B, int points_per_sample, float* cam3d, float* p2d,
+                              void* stream);
 /* Evaluation metrics on the device (common/dataset/metrics.py:13-81): root-aligned MPJPE and
  * N-MPJPE (root alignment + optimal per-pose scale).  pred (n, n_joints, 3) and gt (n, n_joints, 4 = x, y, z, valid) are
  * device arrays; jpe / njpe (optional, device, (n, n_joints)) receive the per-joint errors with -1 at invalid joints

@@ -3,7 +3,8 @@
 flip_tta:      eval.py:152-180 (flip test-time augmentation of both outputs)
 interpolate:   common/dataset/action_wise_eval.py:76-100 (key-frame interpolation)
 mpjpe, nmpjpe: common/dataset/metrics.py:13-81, :120-133 (root alignment; N-MPJPE with optimal per-pose scale)
-Pinned against the reference's own code by tests/golden/tta_*.npz, interp_*.npz and metrics_*.npz
+world_to_cam_and_2d: common/dataset/uplifiting_dataset.py:669-761 (quaternion world -> camera, H3.6M projection)
+Pinned against the reference's own code by tests/golden/tta_*.npz, interp_*.npz, metrics_*.npz and projection_*.npz
 (scripts/make_golden.py)."""
 import numpy as np
 
@@ -69,3 +70,22 @@ def nmpjpe(pred, gt, root, normalize=True):
     s = (p * g * v).sum((1, 2)) / (p * p * v).sum((1, 2))
     d = np.sqrt(((p * s[:, None, None] - g) ** 2).sum(-1))
     return np.where(valid, d, 0.0).sum() / valid.sum() if normalize else np.where(valid, d, -1.0)
+
+
+def world_to_cam_and_2d(seq3d, cam):
+    """uplifiting_dataset.py:669-761.  seq3d (..., 3) world coordinates of one sample, cam (18,) = unit quaternion (w, x, y, z),
+    translation (3), intrinsics (res 2, focal 2, centre 2, radial 3, tangential 2).  Returns (camera-space 3-D, 2-D)."""
+    x = np.asarray(seq3d, np.float64)
+    cam = np.asarray(cam, np.float64)
+    w, qv = cam[0], -cam[1:4]                                  # tf_qinverse: conjugate (:712-716)
+    v = x - cam[4:7]                                           # :719-722
+    uv = np.cross(np.broadcast_to(qv, v.shape), v)             # tf_qrot (:701-709)
+    uuv = np.cross(np.broadcast_to(qv, v.shape), uv)
+    xc = v + 2 * (w * uv + uuv)
+    intr = cam[7:18]
+    f, c, k, p = intr[2:4], intr[4:6], intr[6:9], intr[9:11]
+    xx = np.clip(xc[..., :2] / xc[..., 2:], -1.0, 1.0)         # :746-747
+    r2 = (xx ** 2).sum(-1, keepdims=True)
+    radial = 1 + (k * np.concatenate([r2, r2 ** 2, r2 ** 3], axis=-1)).sum(-1, keepdims=True)
+    tan = (p * xx).sum(-1, keepdims=True)
+    return xc, f * (xx * (radial + tan) + p * r2) + c           # :752-757

@@ -137,8 +137,29 @@ def norm(x, axis=None):
     return _np.sqrt(_np.sum(x * x, axis=axis))
 
 
-def reduce_sum(x, axis=None):
-    return _np.sum(_plain(x), axis=axis)
+def reduce_sum(x, axis=None, keepdims=False):
+    return _np.sum(_plain(x), axis=axis, keepdims=keepdims)
+
+
+def minimum(a, b):
+    return _np.minimum(_plain(a), b)
+
+
+def maximum(a, b):
+    return _np.maximum(_plain(a), b)
+
+
+def tile(x, multiples):
+    return _np.tile(_plain(x), tuple(int(m) for m in multiples))
+
+
+class _Linalg:
+    @staticmethod
+    def cross(a, b):
+        return _np.cross(_plain(a), _plain(b))
+
+
+linalg = _Linalg()
 
 
 def reduce_mean(x, axis=None):

@@ -215,6 +215,27 @@ def metrics_case(tag, n, seed, root=0):
     print(f"metrics_{tag}: mpjpe {ref_metrics.mpjpe(p64, g64, root_index=root):.5f} nmpjpe {ref_metrics.nmpjpe(p64, g64, root_index=root):.5f}")
 
 
+def projection_case(tag, B, n_frames, seed):
+    """AMASS-style virtual-camera projection (uplifiting_dataset.py:669-761): world -> camera by quaternion, then the
+    Human3.6M projection with radial / tangential distortion, by the reference's own tf_world_to_cam_and_2d."""
+    from common.dataset.uplifiting_dataset import tf_world_to_cam_and_2d
+    tf.set_float_dtype("float64")
+    rng = np.random.default_rng(seed)
+    seq = (rng.normal(0, 0.5, (B, n_frames, 17, 3)) + np.array([0.0, 0.0, 1.0])).astype(np.float32)
+    q = rng.normal(size=(B, 4)); q /= np.linalg.norm(q, axis=1, keepdims=True)
+    trans = rng.normal(0, 1.0, (B, 3)) + np.array([0.0, -4.0, 1.5])
+    intr = np.concatenate([np.tile([1000.0, 1002.0], (B, 1)), rng.uniform(1100, 1200, (B, 2)), rng.uniform(480, 540, (B, 2)),
+                           rng.normal(0, 0.1, (B, 3)), rng.normal(0, 0.01, (B, 2))], axis=1)
+    cams = np.concatenate([q, trans, intr], axis=1).astype(np.float32)                  # (B, 4 + 3 + 11)
+    cam3d, p2d = [], []
+    for b in range(B):
+        out = tf_world_to_cam_and_2d(seq[b].astype(np.float64), cams[b].astype(np.float64), None, None, None, None, None)
+        cam3d.append(np.asarray(out[0])); p2d.append(np.asarray(out[1]))
+    np.savez_compressed(os.path.join(args.out, f"projection_{tag}.npz"), seq3d=seq, cams=cams, cam3d=np.stack(cam3d),
+                        p2d=np.stack(p2d))
+    print(f"projection_{tag}: 2d range {np.stack(p2d).min():.1f} .. {np.stack(p2d).max():.1f}")
+
+
 def run_generator(n_tok, stride, mask_stride, mode, n_windows, video_len=400, seed=0, subsample=1):
     """Drive the reference's H36mSequenceGenerator on one synthetic video."""
     rng = np.random.default_rng(7)
@@ -262,6 +283,7 @@ if __name__ == "__main__":
     token_mask_case("h36m_81_sin4_rate03", "h36m_81", 4, 3, seed=8, rate=0.3)
     metrics_case("n300_root0", 300, seed=9, root=0)
     metrics_case("n77_root6", 77, seed=10, root=6)
+    projection_case("b6_n9", 6, 9, seed=12)
     interp_case("stride5", 5, [23, 41, 5, 1], seed=8)
     interp_case("stride2", 2, [9, 12], seed=9)
     # window + stride-mask generator (bit-exact contract)

@@ -143,3 +143,15 @@ def test_pose_metrics_match_reference():
         assert abs(E.nmpjpe(z["pred"], z["gt"], root) - float(z["nmpjpe"])) < 1e-12
         assert np.abs(E.mpjpe(z["pred"], z["gt"], root, normalize=False) - z["jpe"]).max() < 1e-12
         assert np.abs(E.nmpjpe(z["pred"], z["gt"], root, normalize=False) - z["njpe"]).max() < 1e-12
+
+
+def test_camera_projection_matches_reference():
+    """world -> camera -> 2-D restatement against uplifiting_dataset.tf_world_to_cam_and_2d (run over the shim)."""
+    from oracle import eval_np as E
+    paths = sorted(glob.glob(os.path.join(GOLDEN, "projection_*.npz")))
+    assert paths
+    for path in paths:
+        z = np.load(path, allow_pickle=False)
+        for b in range(z["seq3d"].shape[0]):
+            c3, p2 = E.world_to_cam_and_2d(z["seq3d"][b], z["cams"][b])
+            assert np.abs(c3 - z["cam3d"][b]).max() < 1e-12 and np.abs(p2 - z["p2d"][b]).max() < 1e-9

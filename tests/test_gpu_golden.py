@@ -165,3 +165,14 @@ def test_pose_metrics_on_device_match_reference_golden():
         assert res[2] == float((z["gt"][:, :, 3] > 0).sum())
         assert np.abs(jpe.cpu().numpy() - z["jpe"]).max() < 2e-6
         assert np.abs(njpe.cpu().numpy() - z["njpe"]).max() < 2e-6
+
+
+def test_camera_projection_on_device_matches_reference_golden():
+    """uu_op_world_to_cam_and_2d against tf_world_to_cam_and_2d (tests/golden/projection_*.npz); fp32 on the device:
+    camera-space poses to 1e-5, pixel coordinates (|value| up to ~1.6e3) to 2e-3."""
+    from uplift_upsample_3dhpe_b200.model import world_to_cam_and_2d
+    for path in sorted(glob.glob(os.path.join(GOLDEN, "projection_*.npz"))):
+        z = np.load(path, allow_pickle=False)
+        c3, p2 = world_to_cam_and_2d(torch.from_numpy(z["seq3d"]).cuda(), torch.from_numpy(z["cams"]).cuda())
+        assert np.abs(c3.cpu().numpy() - z["cam3d"]).max() < 1e-5
+        assert np.abs(p2.cpu().numpy() - z["p2d"]).max() < 2e-3

@@ -160,6 +160,9 @@ cudaError_t launch_window_copy(const float* video, const int* src, int n_tokens,
 struct TcGemmPlan;   // holds the TMA tensor maps of one GEMM call site
 int tc_gemm_plan_create(TcGemmPlan** out, const bf16* A, long long lda, int M, int K, const bf16* Wt, int N_pad,
                         int N);
+// world -> camera -> 2-D (uplifiting_dataset.py:669-761): x3d (B * points_per_sample, 3), cams (B, 18)
+cudaError_t launch_world_to_cam_2d(const float* x3d, const float* cams, long long n_points, int points_per_sample,
+                                   float* cam3d, float* p2d, cudaStream_t st);
 // MPJPE / N-MPJPE (metrics.py:13-81): pred (n, J, 3), gt (n, J, 4 = x, y, z, valid); out[3] = mpjpe, nmpjpe, valid count
 cudaError_t launch_pose_metrics(const float* pred, const float* gt, int n, int J, int root, float* jpe, float* njpe,
                                 float* sums, double* out, cudaStream_t st);

@@ -717,6 +717,41 @@ cudaError_t launch_residual_ln_bx(const bf16* xsrc, const RowMap& smap, const bf
 }
 
 // =================================================================================================
+// Virtual-camera projection for on-device training-data synthesis (uplifiting_dataset.py:669-761):
+// world -> camera with the inverse of the unit quaternion cam[0:4] after subtracting the translation cam[4:7]
+// (tf_world_to_cam / tf_qrot), then the Human3.6M projection with radial and tangential distortion
+// (tf_project_to_2d: x/z clamped to [-1, 1]).  One thread per point; cams is (B, 18), points_per_sample points share
+// a camera.
+// =================================================================================================
+__global__ void k_world_to_cam_2d(const float* __restrict__ x3d, const float* __restrict__ cams, long long n_points,
+                                  int points_per_sample, float* __restrict__ cam3d, float* __restrict__ p2d) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n_points) return;
+  const float* cam = cams + (i / points_per_sample) * 18;
+  const float w = cam[0], qx = -cam[1], qy = -cam[2], qz = -cam[3];          // conjugate = inverse rotation
+  const float vx = x3d[i * 3] - cam[4], vy = x3d[i * 3 + 1] - cam[5], vz = x3d[i * 3 + 2] - cam[6];
+  const float ux = qy * vz - qz * vy, uy = qz * vx - qx * vz, uz = qx * vy - qy * vx;            // q x v
+  const float wx = qy * uz - qz * uy, wy = qz * ux - qx * uz, wz = qx * uy - qy * ux;            // q x (q x v)
+  const float cx = vx + 2.f * (w * ux + wx), cy = vy + 2.f * (w * uy + wy), cz = vz + 2.f * (w * uz + wz);
+  if (cam3d) { cam3d[i * 3] = cx; cam3d[i * 3 + 1] = cy; cam3d[i * 3 + 2] = cz; }
+  if (p2d) {
+    const float* in = cam + 7;     // res (2), focal (2), centre (2), radial (3), tangential (2)
+    const float xx = fminf(fmaxf(cx / cz, -1.f), 1.f), yy = fminf(fmaxf(cy / cz, -1.f), 1.f);
+    const float r2 = xx * xx + yy * yy;
+    const float radial = 1.f + in[6] * r2 + in[7] * r2 * r2 + in[8] * r2 * r2 * r2;
+    const float tan = in[9] * xx + in[10] * yy;
+    p2d[i * 2] = in[2] * (xx * (radial + tan) + in[9] * r2) + in[4];
+    p2d[i * 2 + 1] = in[3] * (yy * (radial + tan) + in[10] * r2) + in[5];
+  }
+}
+cudaError_t launch_world_to_cam_2d(const float* x3d, const float* cams, long long n_points, int points_per_sample,
+                                   float* cam3d, float* p2d, cudaStream_t st) {
+  if (n_points == 0) return cudaSuccess;
+  k_world_to_cam_2d<<<(unsigned)((n_points + 255) / 256), 256, 0, st>>>(x3d, cams, n_points, points_per_sample, cam3d, p2d);
+  return cudaGetLastError();
+}
+
+// =================================================================================================
 // Evaluation metrics on the device: root-aligned MPJPE and N-MPJPE (root alignment + per-pose
 // optimal scale s = <p, g> / <p, p> over the valid joints), common/dataset/metrics.py:13-81, :120-133.
 // One warp per pose, lane == joint (J <= 32).  per-joint outputs are -1 where the ground truth is invalid

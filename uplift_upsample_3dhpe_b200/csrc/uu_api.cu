@@ -990,6 +990,14 @@ int uu_op_keyframe_interp(const float* pred, const int32_t* frame_indices, int n
   return 0;
 }
 
+int uu_op_world_to_cam_and_2d(const float* seq3d, const float* cams, int B, int points_per_sample, float* cam3d, float* p2d,
+                              void* stream) {
+  UU_CHECK(seq3d && cams && B > 0 && points_per_sample > 0 && (cam3d || p2d), "bad argument");
+  UU_CUDA(launch_world_to_cam_2d(seq3d, cams, (long long)B * points_per_sample, points_per_sample, cam3d, p2d,
+                                 (cudaStream_t)stream));
+  return 0;
+}
+
 int uu_op_pose_metrics(const float* pred, const float* gt, int n, int n_joints, int root, float* jpe, float* njpe,
                        double* result_host, void* stream) {
   UU_CHECK(pred && gt && result_host && n > 0 && n_joints >= 1 && n_joints <= 32 && root >= 0 && root < n_joints,

@@ -281,6 +281,22 @@ def keyframe_interp(pred, frame_indices, keyframe_stride: int):
     return out
 
 
+def world_to_cam_and_2d(seq3d, cams):
+    """uplifiting_dataset.tf_world_to_cam_and_2d on the device for a batch: seq3d (B, ..., 3) world coordinates and
+    cams (B, 18) float32 cuda -> (camera-space 3-D, 2-D projection) with the leading shape of seq3d."""
+    torch = _torch()
+    lib = _lib.load()
+    seq3d, cams = seq3d.contiguous().float(), cams.contiguous().float()
+    B = seq3d.shape[0]
+    assert seq3d.shape[-1] == 3 and tuple(cams.shape) == (B, 18) and cams.device == seq3d.device
+    pps = seq3d[0].numel() // 3
+    cam3d = torch.empty_like(seq3d)
+    p2d = torch.empty(seq3d.shape[:-1] + (2,), device=seq3d.device)
+    stream = torch.cuda.current_stream(seq3d.device).cuda_stream
+    _lib.check(lib.uu_op_world_to_cam_and_2d(seq3d.data_ptr(), cams.data_ptr(), B, pps, cam3d.data_ptr(), p2d.data_ptr(), stream))
+    return cam3d, p2d
+
+
 def pose_metrics(pred, gt, root_index: int, per_joint: bool = False):
     """metrics.mpjpe / metrics.nmpjpe (root alignment) on the device: pred (n, J, 3), gt (n, J, 4 = x, y, z, valid) float32
     cuda.  Returns (mpjpe, nmpjpe) floats, plus the two (n, J) per-joint arrays (-1 = invalid joint) when per_joint."""
