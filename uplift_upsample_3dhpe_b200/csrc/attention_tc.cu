@@ -68,6 +68,8 @@ __global__ void __launch_bounds__(32 * ST) k_attention_tc(const bf16* __restrict
   // heads are the fastest-varying block index: the 8 CTAs of a window run together, so the 96-byte head slices of
   // one 2304-byte q|k|v row (1.5 DRAM bursts each) are fetched once while they sit in L2 (the ncu capture of the
   // (window, head) order showed 1.7x the algorithmic DRAM traffic)
+  pdl_trigger();
+  pdl_wait();          // (no prologue worth overlapping: the first instruction reads the previous kernel's q|k|v)
   const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const int d = heads * DH;
@@ -208,9 +210,9 @@ static cudaError_t att_tc_dh(const bf16* qkv, int B, int S, int heads, const uin
       }                                                                                              \
     }                                                                                                \
     if (S <= 16 * T - 8)                                                                             \
-      k_attention_tc<DH, T, true><<<grid, 32 * T, smem, st>>>(qkv, S, heads, mask, mask_stride, out); \
+      return launch_pdl(k_attention_tc<DH, T, true>, grid, dim3(32 * T), smem, st, qkv, S, heads, mask, mask_stride, out); \
     else                                                                                             \
-      k_attention_tc<DH, T, false><<<grid, 32 * T, smem, st>>>(qkv, S, heads, mask, mask_stride, out); \
+      return launch_pdl(k_attention_tc<DH, T, false>, grid, dim3(32 * T), smem, st, qkv, S, heads, mask, mask_stride, out); \
   } break;
   switch (tiles) {
     UU_ATT_CASE(1) UU_ATT_CASE(2) UU_ATT_CASE(3) UU_ATT_CASE(4)

@@ -1,5 +1,6 @@
 // Shared declarations of the uu3d CUDA library (sm_100a only).
 #pragma once
+#include <utility>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <cstdint>
@@ -59,6 +60,25 @@ enum EpiFlags : int {
                       //   out = rstd[r] * (acc - mean[r] * csum[col]) + bias'[col]   ( == LN(x) W + b )
   EPI_RESID_BF16 = 16 // out = acc + bias + res_bf16[r][col], rounded to bf16; optional row statistics of the result
 };
+
+// Programmatic dependent launch (PDL): a kernel launched with the attribute may become resident while the previous
+// kernel of the stream drains; it runs its prologue (barrier init, TMEM allocation, descriptor prefetch) and then
+// blocks in pdl_wait() until the previous grid has completed and its writes are visible.  pdl_trigger() at the start
+// of a kernel lets ITS successor do the same.  Both are no-ops for launches without the attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled();            // UU_PDL=0 / 1 forces; default: what the running schedule asked for (pdl_set_auto)
+void pdl_set_auto(bool on);
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 // Epilogue description shared by the SIMT and the tcgen05 GEMM.
 struct Epilogue {

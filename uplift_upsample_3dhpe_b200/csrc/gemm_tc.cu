@@ -359,6 +359,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
   using Cfg = TcCfg<BLOCK_N>;
   constexpr int BK = TF32 ? TC_BLOCK_K / 2 : TC_BLOCK_K;      // elements per 128-byte k-block row: 32 fp32 or 64 bf16
   extern __shared__ uint8_t smem_raw[];
+  pdl_trigger();
   const int m_eff = epi.m_dev ? min(M, *epi.m_dev) : M;
   const int m_tiles = (m_eff + TC_BLOCK_M - 1) / TC_BLOCK_M;
   const int total_tiles = m_tiles * n_tiles;
@@ -400,6 +401,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();          // everything above overlapped the previous kernel's tail; its results are needed from here on
 
   if (warp == 0) {
     // ---------------- TMA producer ----------------
@@ -694,6 +696,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
                bf16* __restrict__ C, long long ldc) {
   using Cfg = Tc2Cfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
+  pdl_trigger();
   const int m_pairs = (M + 2 * TC_BLOCK_M - 1) / (2 * TC_BLOCK_M);
   const int total_tiles = m_pairs * n_tiles;
   const uint32_t rank = cluster_ctarank();
@@ -735,6 +738,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
   cluster_sync_all();                        // peer barriers are initialised before anyone signals them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp == 0) {
     // ---------------- TMA producer (both CTAs) ----------------
@@ -939,6 +943,16 @@ void tc_gemm_plan_destroy(TcGemmPlan* p) { delete p; }
 
 static int g_num_sms = 0;
 
+// Measured (h36m_351, one box, CUDA-graph replay): B = 512 windows per call 1.432 -> 1.365 ms (+4.9 %), B = 4096
+// 9.45 -> 9.6-9.9 ms (slower), so the schedules ask for it only for small batches (pdl_set_auto); UU_PDL=0 / 1 forces it.
+static bool g_pdl_auto = false;
+void pdl_set_auto(bool on) { g_pdl_auto = on; }
+bool pdl_enabled() {
+  static int mode = -1;     // 0 off, 1 on, 2 auto
+  if (mode < 0) { const char* e = getenv("UU_PDL"); mode = !e ? 2 : (e[0] == '0' ? 0 : 1); }
+  return mode == 1 || (mode == 2 && g_pdl_auto);
+}
+
 template <int BLOCK_N, typename TC, bool TMA_OUT, int EMODE = 0, bool TF32 = false>
 static cudaError_t tc_launch_t(const TcGemmPlan* p, const Epilogue& epi, void* C, long long ldc, cudaStream_t st) {
   using Cfg = TcCfg<BLOCK_N>;
@@ -957,9 +971,8 @@ static cudaError_t tc_launch_t(const TcGemmPlan* p, const Epilogue& epi, void* C
   const int n_tiles = p->N_pad / BLOCK_N;
   const int total = ((p->M + TC_BLOCK_M - 1) / TC_BLOCK_M) * n_tiles;
   const int grid = total < g_num_sms ? total : g_num_sms;          // persistent: one CTA per SM
-  k_gemm_tc<BLOCK_N, TC, TMA_OUT, EMODE, TF32><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(
-      p->map_a, p->map_b, p->map_c, p->M, p->N, n_tiles, p->K, epi, reinterpret_cast<TC*>(C), ldc);
-  return cudaGetLastError();
+  return launch_pdl(k_gemm_tc<BLOCK_N, TC, TMA_OUT, EMODE, TF32>, dim3(grid), dim3(TC_THREADS), Cfg::SMEM_BYTES, st, p->map_a,
+                    p->map_b, p->map_c, p->M, p->N, n_tiles, p->K, epi, reinterpret_cast<TC*>(C), (long long)ldc);
 }
 
 template <int BLOCK_N, int EMODE = 0>
@@ -979,9 +992,8 @@ static cudaError_t tc2_launch_t(const TcGemmPlan* p, const Epilogue& epi, void* 
   const int n_tiles = p->N_pad / BLOCK_N;
   const int total = ((p->M + 2 * TC_BLOCK_M - 1) / (2 * TC_BLOCK_M)) * n_tiles;
   const int clusters = total < g_num_sms / 2 ? total : g_num_sms / 2;      // persistent: one CTA pair per TPC
-  k_gemm_tc2<BLOCK_N, EMODE><<<2 * clusters, TC_THREADS, Cfg::SMEM_BYTES, st>>>(p->map_a, p->map_b2, p->map_c, p->M, n_tiles, p->K, epi,
-                                                                          reinterpret_cast<bf16*>(C), ldc);
-  return cudaGetLastError();
+  return launch_pdl(k_gemm_tc2<BLOCK_N, EMODE>, dim3(2 * clusters), dim3(TC_THREADS), Cfg::SMEM_BYTES, st, p->map_a, p->map_b2,
+                    p->map_c, p->M, n_tiles, p->K, epi, reinterpret_cast<bf16*>(C), (long long)ldc);
 }
 
 static int g_use_2cta = -1;     // UU_GEMM_2CTA=0/1 forces the single-CTA / 2-CTA kernel (A/B comparison)

@@ -517,7 +517,11 @@ static int run_forward_impl(uu_model* m, const float* x2d, const uint8_t* mask, 
   const int R = B * N;
   const bool use_mask = s.has_strided_input != 0;
   if (f.tc) {
-    if (run_forward_bf16(f, x2d, mask, full, central)) return 1;
+    static const int pdl_max_b = [] { const char* e = getenv("UU_PDL_MAX_B"); return e ? atoi(e) : 1024; }();
+    pdl_set_auto(B <= pdl_max_b);     // programmatic dependent launch pays for small batches only (gemm_tc.cu)
+    const int rc = run_forward_bf16(f, x2d, mask, full, central);
+    pdl_set_auto(false);
+    if (rc) return 1;
     m->plan_B = B; m->plan_full = want_full;
     m->launches = f.launches;
     return 0;
