@@ -430,6 +430,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
             }
           }
         }
+        if ((epi.flags & 128) && (epi.flags & 4096)) continue;
         for (int kb = 0; kb < num_kb; ++kb, ++it, s = (s + 1 == Cfg::STAGES ? 0 : s + 1), ph ^= (s == 0)) {
           mbar_wait(empty_bar + s, ph ^ 1);
           uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
@@ -462,6 +463,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
         mbar_wait(tmem_empty_bar + as, aph ^ 1);          // epilogue has drained this accumulator
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BLOCK_N);
+        if ((epi.flags & 128) && (epi.flags & 4096)) {     // (timing experiment UU_GEMM_NOLOAD + UU_GEMM_ONECOMMIT: the
+                                                            // tile's MMAs back to back on stale smem, one commit, no ring)
+          if (elect_one()) {
+            for (int kb = 0; kb < num_kb; ++kb)
+#pragma unroll
+              for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k)
+                umma_bf16(tmem_d, a_desc0 + 2 * k, b_desc0 + 2 * k, idesc, (kb | k) != 0);
+            umma_commit(tmem_full_bar + as);
+          }
+          __syncwarp();
+          continue;
+        }
 #pragma unroll 1
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar + s, ph);
@@ -1015,6 +1028,7 @@ cudaError_t tc_gemm_launch(TcGemmPlan* p, const Epilogue& epi_in, void* C, int c
   static int noload = -1;
   if (noload < 0) { const char* e = getenv("UU_GEMM_NOLOAD"); noload = (e && e[0] == '1') ? 1 : 0; }
   if (noload) epi.flags |= 128;
+  if (getenv("UU_GEMM_ONECOMMIT")) epi.flags |= 4096;
   static int nopf = -1;
   if (nopf < 0) { const char* e = getenv("UU_GEMM_NOPREFETCH"); nopf = (e && e[0] == '1') ? 1 : 0; }
   if (nopf) epi.flags |= 256;
