@@ -12,7 +12,8 @@
  *   uu_forward / uu_forward_host
  *                               model([x2d, stride_mask], training=False) -> (full, central)
  *                               common/net/uplift_upsample_transformer.py:388-421 ; caller eval.py:63-71
- *   uu_train_step               train_step(): loss, gradients, AdamW   train.py:464-506, :403-415
+ *   uu_train_config / uu_train_forward_backward / uu_grad_buffer / uu_comm_init / uu_allreduce_gradients / uu_adamw_step
+ *                               train_step(): loss, gradients, gradient all-reduce, AdamW   train.py:464-506, :403-415
  *   uu_stride_mask              stride-mask rule of the data generators
  *                               common/dataset/uplifiting_dataset.py:377-394
  *
@@ -174,7 +175,10 @@ int uu_get_token_mask(uu_model* m, float* host, int64_t capacity);
 int uu_train_set_math(uu_model* m, int mode);
 int uu_grad_buffer(uu_model* m, float** dev_ptr, int64_t* n_floats);
 int uu_get_grad(uu_model* m, const char* group, int index, float* host, int64_t capacity);
-int uu_get_droppath_scale(uu_model* m, int stage, int block, float* host, int64_t capacity, float* keep_prob);
+/* Per-sample stochastic-depth factors (mask / keep_prob) drawn by the last step for `branch` 0 (attention residual) or 1
+ * (MLP residual) of block `block` in stage 0 (spatial, B * n_tok samples), 1 (temporal) or 2 (strided, B samples): the
+ * reference calls its DropPath layer once per branch with independent draws (vision_transformer.py:185-190). */
+int uu_get_droppath_scale(uu_model* m, int stage, int block, int branch, float* host, int64_t capacity, float* keep_prob);
 int uu_adamw_step(uu_model* m, float lr_t, float wd_t, float beta1, float beta2, float epsilon, int64_t t,
                   float ema_decay, void* stream);
 int uu_get_ema_weight(uu_model* m, const char* group, int index, float* host, int64_t capacity);

@@ -48,16 +48,17 @@ def _drop(z, keep):
     return (z / keep_prob) * mask.view(-1, *([1] * (z.dim() - 1)))
 
 
-def block(x, p, H, act, key_mask=None, keep=None):
-    """vit:176-195."""
+def block(x, p, H, act, key_mask=None, keep=None, keep2=None):
+    """vit:176-195.  keep / keep2: the DropPath draws of the attention branch (vit:185-186) and of the MLP branch
+    (vit:189-190) — the layer is called twice, each call draws its own tf.random.uniform."""
     x = x + _drop(mha(layer_norm(x, p[0], p[1], 1e-5), p[2:10], H, key_mask), keep)
     z = layer_norm(x, p[10], p[11], 1e-5)
     z = act(z @ p[12] + p[13]) @ p[14] + p[15]
-    return x + _drop(z, keep)
+    return x + _drop(z, keep2)
 
 
-def strided_block(x, pe, p, H, stride, pad, keep=None):
-    """net:122-160 with StridedMLP net:81-90."""
+def strided_block(x, pe, p, H, stride, pad, keep=None, keep2=None):
+    """net:122-160 with StridedMLP net:81-90 (DropPath draws: net:131-132 and net:134-135)."""
     x = x + pe
     x = x + _drop(mha(layer_norm(x, p[0], p[1], 1e-5), p[2:10], H), keep)
     z = layer_norm(x, p[10], p[11], 1e-5)
@@ -65,7 +66,7 @@ def strided_block(x, pe, p, H, stride, pad, keep=None):
     z = F.pad(z, (0, 0, pad[0], pad[1]))
     # Conv1D channels-last, kernel (k, in, out) -> torch conv1d (out, in, k) on (B, C, L)
     z = F.conv1d(z.transpose(1, 2), p[14].permute(2, 1, 0), p[15], stride=stride).transpose(1, 2)
-    z = _drop(z, keep)
+    z = _drop(z, keep2)
     ident = x
     if stride > 1:
         if pad[0] == 0:
@@ -86,8 +87,8 @@ def group(w, name):
 
 def forward(spec, w, x2d, stride_mask, keeps=None, token_keep=None):
     """net:388-421.  w: {(group, index): tensor}; x2d (B,N,J,2) already masked by the caller;
-    stride_mask (B,N) bool or None.  keeps: optional {(stage, i): (keep_prob, mask)} DropPath masks
-    for training-mode parity (stage in 'spatial' | 'temporal' | 'strided').  token_keep: optional (B,N) 0/1 factors
+    stride_mask (B,N) bool or None.  keeps: optional {(stage, i, branch): (keep_prob, mask)} DropPath masks
+    for training-mode parity (stage in 'spatial' | 'temporal' | 'strided'; branch 0 = attention, 1 = MLP).  token_keep: optional (B,N) 0/1 factors
     = 1 - token_mask of random_token_masking (net:287-311, masked value 0), training mode only."""
     keeps = keeps or {}
     B, N, J, _ = x2d.shape
@@ -96,7 +97,8 @@ def forward(spec, w, x2d, stride_mask, keeps=None, token_keep=None):
     ke = group(w, "keypoint_embedding")
     x = x @ ke[0] + ke[1] + w[("spatial_pe", 0)]
     for i in range(spec.spatial_depth):
-        x = block(x, group(w, f"spatial_block_{i + 1}"), H, lambda t: F.gelu(t), keep=keeps.get(("spatial", i)))
+        x = block(x, group(w, f"spatial_block_{i + 1}"), H, lambda t: F.gelu(t), keep=keeps.get(("spatial", i, 0)),
+                  keep2=keeps.get(("spatial", i, 1)))
     sn = group(w, "spatial_norm")
     x = layer_norm(x, sn[0], sn[1], 1e-6).reshape(B, N, J * spec.d_spatial)
     fc = group(w, "spatial_to_temporal_fc")
@@ -111,14 +113,15 @@ def forward(spec, w, x2d, stride_mask, keeps=None, token_keep=None):
     x = x + w[("temporal_pe", 0)]
     for i in range(spec.temporal_depth):
         km = inv if (spec.has_strided_input and i < spec.first_strided_token_attention_layer) else None
-        x = block(x, group(w, f"temporal_block_{i + 1}"), H, torch.relu, km, keep=keeps.get(("temporal", i)))
+        x = block(x, group(w, f"temporal_block_{i + 1}"), H, torch.relu, km, keep=keeps.get(("temporal", i, 0)),
+                  keep2=keeps.get(("temporal", i, 1)))
     full = None
     if spec.full_output:
         h1 = group(w, "temporal_fc")
         full = (x @ h1[0] + h1[1]).view(B, N, J, 3)
     for i, s in enumerate(spec.strides):
         x = strided_block(x, w[(f"strided_temporal_pe_{i + 1}", 0)], group(w, f"strided_temporal_block_{i + 1}"),
-                          H, s, spec.paddings[i], keep=keeps.get(("strided", i)))
+                          H, s, spec.paddings[i], keep=keeps.get(("strided", i, 0)), keep2=keeps.get(("strided", i, 1)))
     h2 = group(w, "strided_temporal_fc")
     central = (x @ h2[0] + h2[1]).view(B, J, 3)
     return full, central

@@ -67,6 +67,40 @@ def test_loss_and_gradients_match_autograd(name, B, droppath, math):
     model.close()
 
 
+def test_droppath_draws_are_independent_per_branch_and_hit_the_rate():
+    """D1 (vit:16-43, :185-190): the attention and the MLP branch of a block draw their own per-sample masks, with
+    drop rate linspace(0, dpr, depth)[i]; spatial blocks draw per frame (B * n_tok samples), the others per window."""
+    B = 96
+    cfg = UpliftUpsampleConfig.preset("h36m_81", BATCH_SIZE=B)
+    spec = spec_from_config(cfg)
+    w = weights.init_weights(spec, 1, perturb=True)
+    x, gt, m = _data(cfg, spec, B)
+    model = build_uplift_upsample_transformer(cfg, precision="fp32", weights=w)
+    tr = Trainer(model, cfg, droppath=True, seed=11)
+    tr.forward_backward(torch.from_numpy(x).cuda(), torch.from_numpy(gt).cuda(), torch.from_numpy(m).cuda())
+    torch.cuda.synchronize()
+    raw = tr.droppath_keeps(B)
+    dpr = cfg.DROP_PATH_RATE
+    depth = {"spatial": spec.spatial_depth, "temporal": spec.temporal_depth, "strided": len(spec.strides)}
+    stage_i = {"spatial": 0, "temporal": 1, "strided": 2}
+    seen = 0
+    for (stage, i, branch), (kp, mask) in raw.items():
+        rate = dpr[stage_i[stage]] * i / (depth[stage] - 1)
+        assert abs(kp - (1 - rate)) < 1e-6
+        n = mask.size
+        sigma = (rate * (1 - rate) / n) ** 0.5
+        assert abs((1 - mask.mean()) - rate) < 4.5 * sigma + 1e-9, (stage, i, branch, 1 - mask.mean(), rate)
+        if branch == 0 and n >= 1000:
+            other = raw[(stage, i, 1)][1]
+            assert (mask != other).any(), "the two branches of a block must not share one draw"
+            # independence: P(both dropped) ~ rate^2, far from rate (what a shared draw would give)
+            both = float(((mask == 0) & (other == 0)).mean())
+            assert both < 0.5 * rate, (stage, i, both, rate)
+            seen += 1
+    assert seen >= 3
+    model.close()
+
+
 def test_random_token_masking_matches_autograd():
     """D2 (net:287-311, :336-338): TOKEN_MASK_RATE > 0, masked value 0.  The mask the library drew is fed to the oracle;
     the central token must never be masked and the rate must be plausible."""

@@ -18,8 +18,9 @@ LIB_PATH = os.path.join(_HERE, "libuu3d.so")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 SOURCES = ["kernels_f32.cu", "spatial_tc.cu", "attention_tc.cu", "gemm_tc.cu", "train_kernels.cu", "uu_train.cu",
            "uu_api.cu"]
+OBJ_DIR = os.path.join(_HERE, "build")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "550,177"]
+              "-Xcompiler", "-fPIC", "-diag-suppress", "550,177"]
 
 UU_MAX_STRIDED = 8
 PRECISION = {"fp32": 0, "bf16": 1}
@@ -38,43 +39,104 @@ class UUSpec(ctypes.Structure):
     ]
 
 
+def _headers() -> list:
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join(INCLUDE, "uu3d.h")]
+
+
+def _digest(paths) -> str:
+    """Content hash (not mtimes: a repository snapshot copied to another machine does not keep their order)."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for p in paths:
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def _source_digest() -> str:
+    return _digest([os.path.join(CSRC, f) for f in SOURCES] + _headers())
+
+
+def _read(path) -> str:
+    try:
+        with open(path) as f:
+            return f.read().strip()
+    except OSError:
+        return ""
+
+
 def _stale() -> bool:
-    if not os.path.exists(LIB_PATH):
-        return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(INCLUDE, "uu3d.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    return not os.path.exists(LIB_PATH) or _read(LIB_PATH + ".srchash") != _source_digest()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every CUDA source for sm_100a into libuu3d.so (in-tree, so it travels with the repo)."""
+    """Compile every CUDA source for sm_100a into libuu3d.so (in-tree, so it travels with the repo).
+
+    One object per translation unit (compiled in parallel, re-used while neither the source nor any header changed),
+    linked into a temporary file that replaces libuu3d.so atomically; an exclusive file lock serialises concurrent
+    builders (ranks of one torchrun launch), so nobody ever loads a half-written library."""
     if not force and not _stale():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libuu3d.so")
-    cmd = [nvcc] + NVCC_FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB_PATH]
-    if verbose:
-        print(" ".join(cmd))
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    import fcntl
+    from concurrent.futures import ThreadPoolExecutor
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    with open(os.path.join(OBJ_DIR, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not _stale():          # another process built it while we waited
+            return LIB_PATH
+        hdrs = _headers()
+
+        def compile_one(src):
+            obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+            path = os.path.join(CSRC, src)
+            dig = _digest([path] + hdrs)
+            if not force and os.path.exists(obj) and _read(obj + ".srchash") == dig:
+                return obj
+            cmd = [nvcc] + NVCC_FLAGS + ["-c", path, "-o", obj]
+            if verbose:
+                print(" ".join(cmd))
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError("nvcc failed on " + src + ":\n" + r.stdout + r.stderr)
+            with open(obj + ".srchash", "w") as f:
+                f.write(dig)
+            return obj
+
+        with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as ex:
+            objs = list(ex.map(compile_one, SOURCES))
+        tmp = LIB_PATH + ".tmp.%d" % os.getpid()
+        r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a"] + objs + ["-o", tmp],
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+        os.replace(tmp, LIB_PATH)
+        with open(LIB_PATH + ".srchash", "w") as f:
+            f.write(_source_digest())
     return LIB_PATH
 
 
 _lib = None
+EXPECTED_VERSION = 200          # uu_version() of the library this binding was written against
 
 
 def load() -> ctypes.CDLL:
-    """Load the library (building it first when it is missing and nvcc is present)."""
+    """Load the library; (re)build it first when it is missing or older than its sources and nvcc is present."""
     global _lib
     if _lib is not None:
         return _lib
     path = os.environ.get("UU3D_LIB") or LIB_PATH      # UU3D_LIB: development override (A/B builds of the library)
-    if path == LIB_PATH and not os.path.exists(LIB_PATH):
-        build()
+    if path == LIB_PATH:
+        have_nvcc = bool(shutil.which("nvcc")) or os.path.exists("/usr/local/cuda/bin/nvcc")
+        if not os.path.exists(LIB_PATH) or (have_nvcc and _stale()):
+            build()
     lib = ctypes.CDLL(path)
     _declare(lib)
+    if lib.uu_version() != EXPECTED_VERSION:
+        raise RuntimeError("libuu3d.so reports version %d, this binding expects %d: rebuild the library"
+                           % (lib.uu_version(), EXPECTED_VERSION))
     _lib = lib
     return lib
 
@@ -103,7 +165,7 @@ def _declare(lib) -> None:
     lib.uu_train_forward_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p]
     lib.uu_grad_buffer.argtypes = [c_void_p, P(c_void_p), P(c_int64)]
     lib.uu_get_grad.argtypes = [c_void_p, c_char_p, c_int, c_void_p, c_int64]
-    lib.uu_get_droppath_scale.argtypes = [c_void_p, c_int, c_int, c_void_p, c_int64, P(c_float)]
+    lib.uu_get_droppath_scale.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_int64, P(c_float)]
     lib.uu_adamw_step.argtypes = [c_void_p, c_float, c_float, c_float, c_float, c_float, c_int64, c_float, c_void_p]
     lib.uu_get_ema_weight.argtypes = [c_void_p, c_char_p, c_int, c_void_p, c_int64]
     lib.uu_stride_mask.argtypes = [c_int, c_int, c_int, c_int64, c_void_p]

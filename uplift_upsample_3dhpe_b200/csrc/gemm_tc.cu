@@ -17,6 +17,14 @@
 
 namespace uu {
 
+// Timing-experiment switches (DESIGN.md "GEMM analysis") exist only in builds with -DUU_EXPERIMENT: most of them
+// produce wrong results on purpose, so the shipped library never reads them from the environment.
+#ifdef UU_EXPERIMENT
+#define UU_EXP_FLAG(epi, bit) (((epi).flags & (bit)) != 0)
+#else
+#define UU_EXP_FLAG(epi, bit) false
+#endif
+
 constexpr int TC_BLOCK_M = 128;
 constexpr int TC_BLOCK_K = 64;          // 64 bf16 = 128 B = one swizzle atom row
 constexpr int TC_UMMA_K = 16;
@@ -153,7 +161,11 @@ struct EpiPre {
 };
 __device__ __forceinline__ void epi_load_residual(EpiPre& pre, const Epilogue& epi, int row, int col, int m_eff, long long ldc) {
   const uint4* rp = reinterpret_cast<const uint4*>(epi.res_bf16 + (long long)row * ldc + col);
+#ifdef UU_EXPERIMENT
   const bool ok = row < m_eff && !(epi.flags & 1024);     // (flag 1024: timing experiment UU_GEMM_NORES)
+#else
+  const bool ok = row < m_eff;
+#endif
 #pragma unroll
   for (int g = 0; g < 8; ++g) pre.rres[g] = ok ? rp[g] : make_uint4(0u, 0u, 0u, 0u);
 }
@@ -241,7 +253,9 @@ __device__ __forceinline__ void epi_warp_store_tile(uint32_t tmem_acc, int first
       else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
     __syncwarp();
+#ifdef UU_EXPERIMENT
     if (!(epi.flags & 512))                 // (flag 512: timing experiment UU_GEMM_NOEPI — no conversion)
+#endif
 #pragma unroll
     for (int g = 0; g < 8; ++g) {           // 8 columns -> one 16-byte chunk
       const int cb = col0 + sub * 64 + 8 * g;
@@ -308,7 +322,11 @@ __device__ __forceinline__ void epi_warp_store_tile(uint32_t tmem_acc, int first
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async proxy
     __syncwarp();
     if (boxed) {
+#ifdef UU_EXPERIMENT
       if (lane == 0 && !(epi.flags & 64)) {   // (flag 64: timing experiment, UU_GEMM_NOSTORE)
+#else
+      if (lane == 0) {
+#endif
         asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map_c),
                      "r"(smem_u32(sbuf)), "r"(col0 + sub * 64), "r"(dst_row)
                      : "memory");
@@ -416,28 +434,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
         // that will own column block 0 of a row block pulls that row block into L2 one tile ahead.
         {
           const int nt = tile + tile_step;
-          if (nt < total_tiles && (nt % n_tiles) == 0 && !(epi.flags & 256)) {
+          if (nt < total_tiles && (nt % n_tiles) == 0 && !UU_EXP_FLAG(epi, 256)) {
             const int prow = (nt / n_tiles) * TC_BLOCK_M;
             for (int kb = 0; kb < num_kb; ++kb) tma_prefetch_2d(&map_a, kb * BK, prow);
           }
           if constexpr (TMA_OUT && EMODE == EMODE_RESID) {
             // residual rows of this CTA's next tile (the output map describes the same matrix): the epilogue's
             // row-per-lane loads then hit L2 instead of paying the DRAM latency in front of a sub-tile
-            if (nt < total_tiles && !(epi.flags & 256)) {
+            if (nt < total_tiles && !UU_EXP_FLAG(epi, 256)) {
               const int prow = (nt / n_tiles) * TC_BLOCK_M, pcol = (nt % n_tiles) * BLOCK_N;
               for (int r = 0; r < TC_BLOCK_M; r += 32)
                 for (int c = 0; c < BLOCK_N; c += 64) tma_prefetch_2d(&map_c, pcol + c, prow + r);
             }
           }
         }
+#ifdef UU_EXPERIMENT
         if ((epi.flags & 128) && (epi.flags & 4096)) continue;
+#endif
         for (int kb = 0; kb < num_kb; ++kb, ++it, s = (s + 1 == Cfg::STAGES ? 0 : s + 1), ph ^= (s == 0)) {
           mbar_wait(empty_bar + s, ph ^ 1);
           uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
+#ifdef UU_EXPERIMENT
           if (epi.flags & 128) {                 // (flag 128: timing experiment UU_GEMM_NOLOAD — MMA on stale smem)
             mbar_arrive(full_bar + s);
             continue;
           }
+#endif
           mbar_expect_tx(full_bar + s, Cfg::STAGE_BYTES);
           tma_load_2d(a_dst, &map_a, full_bar + s, kb * BK, row0);
           tma_load_2d(a_dst + Cfg::A_BYTES, &map_b, full_bar + s, kb * BK, col0);
@@ -463,6 +485,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
         mbar_wait(tmem_empty_bar + as, aph ^ 1);          // epilogue has drained this accumulator
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BLOCK_N);
+#ifdef UU_EXPERIMENT
         if ((epi.flags & 128) && (epi.flags & 4096)) {     // (timing experiment UU_GEMM_NOLOAD + UU_GEMM_ONECOMMIT: the
                                                             // tile's MMAs back to back on stale smem, one commit, no ring)
           if (elect_one()) {
@@ -475,6 +498,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
           __syncwarp();
           continue;
         }
+#endif
 #pragma unroll 1
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar + s, ph);
@@ -762,12 +786,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         const int col0 = (tile % n_tiles) * BLOCK_N + (int)rank * (BLOCK_N / 2);
         {   // pull this CTA's rows of the cluster's next tile into L2 (see the single-CTA kernel)
           const int nt = tile + n_clusters;
-          if (nt < total_tiles && (nt % n_tiles) == 0 && !(epi.flags & 256)) {
+          if (nt < total_tiles && (nt % n_tiles) == 0 && !UU_EXP_FLAG(epi, 256)) {
             const int prow = (nt / n_tiles) * (2 * TC_BLOCK_M) + (int)rank * TC_BLOCK_M;
             for (int kb = 0; kb < num_kb; ++kb) tma_prefetch_2d(&map_a, kb * TC_BLOCK_K, prow);
           }
           if constexpr (EMODE == EMODE_RESID) {      // residual rows of this CTA's half of the next tile
-            if (nt < total_tiles && !(epi.flags & 256)) {
+            if (nt < total_tiles && !UU_EXP_FLAG(epi, 256)) {
               const int prow = (nt / n_tiles) * (2 * TC_BLOCK_M) + (int)rank * TC_BLOCK_M, pcol = (nt % n_tiles) * BLOCK_N;
               for (int r = 0; r < TC_BLOCK_M; r += 32)
                 for (int c = 0; c < BLOCK_N; c += 64) tma_prefetch_2d(&map_c, pcol + c, prow + r);
@@ -912,10 +936,12 @@ int tc_gemm_plan_create(TcGemmPlan** out, const bf16* A, long long lda, int M, i
   p->M = M; p->N = N; p->N_pad = N_pad; p->K = K;
   // widest tile that divides the padded N: 256 (fc1), 192 (q|k|v, 384-wide outputs), 128, 64 (heads)
   p->block_n = (N_pad % 256 == 0) ? 256 : (N_pad % 192 == 0) ? 192 : (N_pad % 128 == 0) ? 128 : 64;
+#ifdef UU_EXPERIMENT
   if (const char* e = getenv("UU_GEMM_BN")) {           // tile-width experiment
     const int bn = atoi(e);
     if ((bn == 64 || bn == 128 || bn == 192 || bn == 256) && N_pad % bn == 0) p->block_n = bn;
   }
+#endif
   if (N_pad % p->block_n != 0) {
     delete p;
     set_error("tcgen05 GEMM needs the packed weight rows padded to a multiple of 64");
@@ -1021,23 +1047,16 @@ static bool tma_out_eligible(const TcGemmPlan* p, const Epilogue& epi, int c_bf1
 cudaError_t tc_gemm_launch(TcGemmPlan* p, const Epilogue& epi_in, void* C, int c_bf16, long long ldc, cudaStream_t st) {
   if ((epi_in.flags & (EPI_LNFOLD | EPI_RESID_BF16)) && !tma_out_eligible(p, epi_in, c_bf16, ldc))
     return cudaErrorInvalidValue;     // folded-LayerNorm / bf16-residual epilogues exist on the TMA-store path only
-  static int nostore = -1;
-  if (nostore < 0) { const char* e = getenv("UU_GEMM_NOSTORE"); nostore = (e && e[0] == '1') ? 1 : 0; }
   Epilogue epi = epi_in;
-  if (nostore) epi.flags |= 64;
-  static int noload = -1;
-  if (noload < 0) { const char* e = getenv("UU_GEMM_NOLOAD"); noload = (e && e[0] == '1') ? 1 : 0; }
-  if (noload) epi.flags |= 128;
-  if (getenv("UU_GEMM_ONECOMMIT")) epi.flags |= 4096;
-  static int nopf = -1;
-  if (nopf < 0) { const char* e = getenv("UU_GEMM_NOPREFETCH"); nopf = (e && e[0] == '1') ? 1 : 0; }
-  if (nopf) epi.flags |= 256;
-  static int noepi = -1;
-  if (noepi < 0) { const char* e = getenv("UU_GEMM_NOEPI"); noepi = (e && e[0] == '1') ? 1 : 0; }
-  if (noepi) epi.flags |= 512;
-  static int nores = -1;
-  if (nores < 0) { const char* e = getenv("UU_GEMM_NORES"); nores = (e && e[0] == '1') ? 1 : 0; }
-  if (nores) epi.flags |= 1024;
+#ifdef UU_EXPERIMENT
+  {
+    auto on = [](const char* name) { const char* e = getenv(name); return e && e[0] == '1'; };
+    static const int exp_flags = (on("UU_GEMM_NOSTORE") ? 64 : 0) | (on("UU_GEMM_NOLOAD") ? 128 : 0) |
+                                 (on("UU_GEMM_NOPREFETCH") ? 256 : 0) | (on("UU_GEMM_NOEPI") ? 512 : 0) |
+                                 (on("UU_GEMM_NORES") ? 1024 : 0) | (getenv("UU_GEMM_ONECOMMIT") ? 4096 : 0);
+    epi.flags |= exp_flags;
+  }
+#endif
   if (p->tf32) {
     if (c_bf16 || (epi.flags & (EPI_LNFOLD | EPI_RESID_BF16))) return cudaErrorInvalidValue;
     switch (p->block_n) {
@@ -1057,8 +1076,10 @@ cudaError_t tc_gemm_launch(TcGemmPlan* p, const Epilogue& epi_in, void* C, int c
       p->c_ptr = C; p->c_ld = ldc;
     }
     if (g_use_2cta < 0) {
-      const char* e = getenv("UU_GEMM_2CTA");
-      g_use_2cta = e ? (e[0] == '1' ? 1 : 0) : 2;   // default (2): only where it measured faster, the K >= 768 GEMMs
+      g_use_2cta = 2;                               // default (2): only where it measured faster, the K >= 768 GEMMs
+#ifdef UU_EXPERIMENT
+      if (const char* e = getenv("UU_GEMM_2CTA")) g_use_2cta = e[0] == '1' ? 1 : 0;
+#endif
     }
     const bool scatter = epi.c_rowidx || epi.m_dev || epi.cmap.rpb != 0x7fffffff;
     const bool two_cta = !scatter && (g_use_2cta == 1 || (g_use_2cta == 2 && p->K >= 768)) && p->M >= 512;

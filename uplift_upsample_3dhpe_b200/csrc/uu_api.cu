@@ -135,20 +135,20 @@ int dev_alloc(std::vector<void*>& pool, void** p, size_t bytes, bool zero) {
   return 0;
 }
 
-static int make_pack(uu_model* m, Pack& pk, const float* Wsrc, int K, int N) {
+static int make_pack(uu_model* m, Pack& pk, const float* Wsrc, int K, int N, cudaStream_t st) {
   pk.k = K; pk.n = N; pk.n_pad = (N + 63) / 64 * 64;
   if (!pk.ptr) {
     void* p;
     if (dev_alloc(m->derived_allocs, &p, sizeof(bf16) * (size_t)pk.n_pad * K, false)) return 1;
     pk.ptr = (bf16*)p;
   }
-  k_pack_wt<<<256, 256>>>(Wsrc, K, N, pk.n_pad, pk.ptr);
+  k_pack_wt<<<256, 256, 0, st>>>(Wsrc, K, N, pk.n_pad, pk.ptr);
   UU_CUDA(cudaGetLastError());
   return 0;
 }
 
 static int make_pack_ln(uu_model* m, Pack& pk, float*& csum, float*& bias_out, const float* Wsrc, int K, int N,
-                        const float* gamma, const float* beta, const float* bias) {
+                        const float* gamma, const float* beta, const float* bias, cudaStream_t st) {
   pk.k = K; pk.n = N; pk.n_pad = (N + 63) / 64 * 64;
   if (!pk.ptr) {
     void* p;
@@ -159,12 +159,12 @@ static int make_pack_ln(uu_model* m, Pack& pk, float*& csum, float*& bias_out, c
     if (dev_alloc(m->derived_allocs, &p, sizeof(float) * pk.n_pad, false)) return 1;
     bias_out = (float*)p;
   }
-  k_pack_wt_ln<<<(pk.n_pad + 7) / 8, 256>>>(Wsrc, K, N, pk.n_pad, gamma, beta, bias, pk.ptr, csum, bias_out);
+  k_pack_wt_ln<<<(pk.n_pad + 7) / 8, 256, 0, st>>>(Wsrc, K, N, pk.n_pad, gamma, beta, bias, pk.ptr, csum, bias_out);
   UU_CUDA(cudaGetLastError());
   return 0;
 }
 
-static int setup_block(uu_model* m, BlockW& b, const std::string& g, int d, int h, bool strided) {
+static int setup_block(uu_model* m, BlockW& b, const std::string& g, int d, int h, bool strided, cudaStream_t st) {
   b.ln1_g = W(m, g, 0); b.ln1_b = W(m, g, 1);
   b.wp = W(m, g, 8); b.bp = W(m, g, 9);
   b.ln2_g = W(m, g, 10); b.ln2_b = W(m, g, 11);
@@ -176,21 +176,24 @@ static int setup_block(uu_model* m, BlockW& b, const std::string& g, int d, int 
     if (dev_alloc(m->derived_allocs, &p, sizeof(float) * 3 * d, false)) return 1;
     b.bqkv = (float*)p;
   }
-  k_concat_cols<<<256, 256>>>(W(m, g, 2), W(m, g, 4), W(m, g, 6), d, d, b.wqkv);
-  k_concat_cols<<<1, 256>>>(W(m, g, 3), W(m, g, 5), W(m, g, 7), 1, d, b.bqkv);
+  k_concat_cols<<<256, 256, 0, st>>>(W(m, g, 2), W(m, g, 4), W(m, g, 6), d, d, b.wqkv);
+  k_concat_cols<<<1, 256, 0, st>>>(W(m, g, 3), W(m, g, 5), W(m, g, 7), 1, d, b.bqkv);
   UU_CUDA(cudaGetLastError());
-  if (make_pack(m, b.p_qkv, b.wqkv, d, 3 * d)) return 1;
-  if (make_pack(m, b.p_proj, b.wp, d, d)) return 1;
-  if (make_pack(m, b.p_fc1, b.w1, d, h)) return 1;
-  if (make_pack(m, b.p_fc2, b.w2, strided ? 3 * h : h, d)) return 1;
+  if (make_pack(m, b.p_qkv, b.wqkv, d, 3 * d, st)) return 1;
+  if (make_pack(m, b.p_proj, b.wp, d, d, st)) return 1;
+  if (make_pack(m, b.p_fc1, b.w1, d, h, st)) return 1;
+  if (make_pack(m, b.p_fc2, b.w2, strided ? 3 * h : h, d, st)) return 1;
   // (strided blocks: fc1 is the k=1 Conv1D, a (d, h) matrix like the dense fc1)
-  if (make_pack_ln(m, b.p_qkv_ln, b.cs_qkv, b.bl_qkv, b.wqkv, d, 3 * d, b.ln1_g, b.ln1_b, b.bqkv)) return 1;
-  if (make_pack_ln(m, b.p_fc1_ln, b.cs_fc1, b.bl_fc1, b.w1, d, h, b.ln2_g, b.ln2_b, b.b1)) return 1;
+  if (make_pack_ln(m, b.p_qkv_ln, b.cs_qkv, b.bl_qkv, b.wqkv, d, 3 * d, b.ln1_g, b.ln1_b, b.bqkv, st)) return 1;
+  if (make_pack_ln(m, b.p_fc1_ln, b.cs_fc1, b.bl_fc1, b.w1, d, h, b.ln2_g, b.ln2_b, b.b1, st)) return 1;
   return 0;
 }
 
-// (Re)derive fused / packed weights after uu_set_weight.
-static int commit_weights(uu_model* m) {
+// (Re)derive fused / packed weights after uu_set_weight / uu_adamw_step.  The repack kernels run on the CALLER's stream
+// `st`: they read m->params, which the AdamW update of the same stream may just have written (a repack on the legacy
+// stream would not be ordered behind an update enqueued on a non-blocking stream).  The host then waits for that stream,
+// so a later forward on any other stream sees finished packs.
+static int commit_weights(uu_model* m, cudaStream_t st) {
   if (!m->dirty) return 0;
   const uu_spec& s = m->spec;
   UU_CUDA(cudaSetDevice(m->device));
@@ -211,17 +214,17 @@ static int commit_weights(uu_model* m) {
   }
   UU_CUDA(launch_spatial_pack(m->spatial_ptrs, s.spatial_depth, W(m, "keypoint_embedding", 0),
                               W(m, "keypoint_embedding", 1), W(m, "spatial_pe", 0), W(m, "spatial_norm", 0),
-                              W(m, "spatial_norm", 1), m->sp_frags, m->sp_params, 0));
+                              W(m, "spatial_norm", 1), m->sp_frags, m->sp_params, st));
   m->tblocks.resize(s.temporal_depth);
   m->sblocks.resize(s.n_strided);
   for (int i = 0; i < s.temporal_depth; ++i)
-    if (setup_block(m, m->tblocks[i], "temporal_block_" + std::to_string(i + 1), s.d_temporal, s.h_temporal, false)) return 1;
+    if (setup_block(m, m->tblocks[i], "temporal_block_" + std::to_string(i + 1), s.d_temporal, s.h_temporal, false, st)) return 1;
   for (int i = 0; i < s.n_strided; ++i)
-    if (setup_block(m, m->sblocks[i], "strided_temporal_block_" + std::to_string(i + 1), s.d_temporal, s.h_temporal, true)) return 1;
-  if (make_pack(m, m->p_s2t, W(m, "spatial_to_temporal_fc", 0), s.n_joints * s.d_spatial, s.d_temporal)) return 1;
-  if (s.full_output && make_pack(m, m->p_head1, W(m, "temporal_fc", 0), s.d_temporal, 3 * s.n_joints)) return 1;
-  if (make_pack(m, m->p_head2, W(m, "strided_temporal_fc", 0), s.d_temporal, 3 * s.n_joints)) return 1;
-  UU_CUDA(cudaDeviceSynchronize());
+    if (setup_block(m, m->sblocks[i], "strided_temporal_block_" + std::to_string(i + 1), s.d_temporal, s.h_temporal, true, st)) return 1;
+  if (make_pack(m, m->p_s2t, W(m, "spatial_to_temporal_fc", 0), s.n_joints * s.d_spatial, s.d_temporal, st)) return 1;
+  if (s.full_output && make_pack(m, m->p_head1, W(m, "temporal_fc", 0), s.d_temporal, 3 * s.n_joints, st)) return 1;
+  if (make_pack(m, m->p_head2, W(m, "strided_temporal_fc", 0), s.d_temporal, 3 * s.n_joints, st)) return 1;
+  UU_CUDA(cudaStreamSynchronize(st));
   m->dirty = false;
   return 0;
 }
@@ -505,7 +508,7 @@ static int run_forward_impl(uu_model* m, const float* x2d, const uint8_t* mask, 
   UU_CHECK(x2d && central, "x2d and central must not be null");
   UU_CHECK(!s.has_strided_input || mask, "this model has strided input: a stride mask is required");
   UU_CUDA(cudaSetDevice(m->device));
-  if (commit_weights(m)) return 1;
+  if (commit_weights(m, st)) return 1;
   if (ensure_workspace(m, B)) return 1;
   Fwd f;
   f.m = m; f.st = st; f.B = B; f.tc = m->precision == UU_PRECISION_BF16;
@@ -660,7 +663,7 @@ static int check_spec(const uu_spec& s, std::vector<int>& lens) {
 extern "C" {
 
 const char* uu_last_error(void) { return g_error.c_str(); }
-int uu_version(void) { return 100; }
+int uu_version(void) { return 200; }
 
 int uu_create(const uu_spec* spec, int device, uu_model** out) {
   UU_CHECK(spec && out, "null argument");
@@ -792,7 +795,7 @@ int uu_forward(uu_model* m, const float* x2d, const uint8_t* mask, int B, float*
   if (!use_graphs || st == nullptr || st == cudaStreamLegacy || m->precision != UU_PRECISION_BF16 || m->profiling || B <= 0)
     return run_forward(m, x2d, mask, B, full, central, st);
   UU_CUDA(cudaSetDevice(m->device));
-  if (commit_weights(m)) return 1;                   // derived weights are rebuilt outside any capture
+  if (commit_weights(m, st)) return 1;               // derived weights are rebuilt outside any capture
   if (ensure_workspace(m, B)) return 1;              // (drops the cache when it reallocates)
   const uu_model::GraphKey key{B, x2d, mask, full, central, st};
   if (m->graphs.size() > 32 && !m->graphs.count(key)) drop_graphs(m);
@@ -1007,14 +1010,16 @@ int uu_op_pose_metrics(const float* pred, const float* gt, int n, int n_joints, 
   UU_CHECK(pred && gt && result_host && n > 0 && n_joints >= 1 && n_joints <= 32 && root >= 0 && root < n_joints,
            "bad argument (n_joints <= 32)");
   cudaStream_t st = (cudaStream_t)stream;
+  // scratch from the stream-ordered pool: no device-wide synchronisation, re-used from call to call
   float* sums = nullptr;
   double* out = nullptr;
-  UU_CUDA(cudaMalloc(&sums, sizeof(float) * 3 * (size_t)n));
-  cudaError_t e = cudaMalloc(&out, sizeof(double) * 3);
+  UU_CUDA(cudaMallocAsync(&sums, sizeof(float) * 3 * (size_t)n + 64, st));
+  cudaError_t e = cudaMallocAsync(&out, sizeof(double) * 3, st);
   if (e == cudaSuccess) e = launch_pose_metrics(pred, gt, n, n_joints, root, jpe, njpe, sums, out, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(result_host, out, sizeof(double) * 3, cudaMemcpyDeviceToHost, st);
+  cudaFreeAsync(sums, st);
+  if (out) cudaFreeAsync(out, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  cudaFree(sums); cudaFree(out);
   UU_CUDA(e);
   return 0;
 }
@@ -1091,7 +1096,7 @@ int uu_op_spatial(uu_model* m, const float* x2d, const uint8_t* mask, int B, voi
   const uu_spec& s = m->spec;
   cudaStream_t st = (cudaStream_t)stream;
   UU_CUDA(cudaSetDevice(m->device));
-  if (commit_weights(m)) return 1;
+  if (commit_weights(m, st)) return 1;
   if (ensure_workspace(m, B)) return 1;
   const int R = B * s.n_tok;
   const bool use_mask = mask != nullptr;

@@ -15,7 +15,10 @@ const std::string& get_error();
 
 struct BlkTape {   // saved activations of one transformer block
   float *x0 = nullptr, *y1 = nullptr, *qkv = nullptr, *o = nullptr, *x1 = nullptr, *y2 = nullptr, *hpre = nullptr,
-        *hact = nullptr, *x2 = nullptr, *scale = nullptr;
+        *hact = nullptr, *x2 = nullptr;
+  // stochastic depth: the reference calls drop_path_layer twice per block (vit:185-190, net:131-135), each call with
+  // its own tf.random.uniform draw, so the attention branch and the MLP branch are dropped independently
+  float *scale = nullptr, *scale2 = nullptr;      // per-sample factors of the attention / MLP branch
   float keep = 1.f;
 };
 
@@ -181,7 +184,7 @@ struct BlkDims {
 static int alloc_tape(TrainState* t, BlkTape& tp, const BlkDims& b, bool strided) {
   const size_t R = (size_t)b.nb * b.S;
   if (falloc(t, &tp.y1, R * b.d) || falloc(t, &tp.qkv, R * 3 * b.d) || falloc(t, &tp.o, R * b.d) ||
-      falloc(t, &tp.x1, R * b.d) || falloc(t, &tp.y2, R * b.d) || falloc(t, &tp.scale, b.nb))
+      falloc(t, &tp.x1, R * b.d) || falloc(t, &tp.y2, R * b.d) || falloc(t, &tp.scale, b.nb) || falloc(t, &tp.scale2, b.nb))
     return 1;
   if (!strided) {
     if (falloc(t, &tp.hpre, R * b.h) || falloc(t, &tp.hact, R * b.h) || falloc(t, &tp.x2, R * b.d)) return 1;
@@ -232,7 +235,7 @@ static int block_fwd(Ctx& c, const BlkDims& b, const std::string& g, BlkTape& tp
   UU_TL(launch_act_fwd(tp.hpre, R * h, b.act, tp.hact, c.st));
   if (lin_fwd(c, tp.hact, h, (int)R, h, W(m, g, 14), d, W(m, g, 15), c.t->tmp1, d)) return 1;
   const RowMap plain;
-  UU_TL(launch_residual(tp.x1, plain, c.t->tmp1, tp.keep < 1.f ? tp.scale : nullptr, b.S, nullptr, 1, R, d, tp.x2, c.st));
+  UU_TL(launch_residual(tp.x1, plain, c.t->tmp1, tp.keep < 1.f ? tp.scale2 : nullptr, b.S, nullptr, 1, R, d, tp.x2, c.st));
   return 0;
 }
 // dx: d/d(x2) on entry, d/d(x0) on exit (in place)
@@ -243,7 +246,7 @@ static int block_bwd(Ctx& c, const BlkDims& b, const std::string& g, BlkTape& tp
   const long long R = b.nb * b.S;
   const int d = b.d, h = b.h;
   const RowMap plain;
-  UU_TL(launch_scale_rows(dx, tp.keep < 1.f ? tp.scale : nullptr, b.S, R, d, t->tmp1, c.st));
+  UU_TL(launch_scale_rows(dx, tp.keep < 1.f ? tp.scale2 : nullptr, b.S, R, d, t->tmp1, c.st));
   if (lin_bwd(c, tp.hact, h, t->tmp1, d, (int)R, h, d, W(m, g, 14), t->tmp_h, h, 0, G(m, g, 14), G(m, g, 15))) return 1;
   UU_TL(launch_act_bwd(tp.hpre, t->tmp_h, plain, h, R, h, b.act, t->tmp_h, c.st));
   if (lin_bwd(c, tp.y2, d, t->tmp_h, h, (int)R, d, h, W(m, g, 12), t->tmp2, d, 0, G(m, g, 12), G(m, g, 13))) return 1;
@@ -345,9 +348,12 @@ static int train_fb(uu_model* m, const float* x2d, const uint8_t* mask, const fl
     const long long ns = stage == 0 ? R : B;
     for (size_t i = 0; i < tapes.size(); ++i) {
       tapes[i].keep = block_keep(t, stage, (int)i, (int)tapes.size());
-      if (tapes[i].keep < 1.f)
-        UU_TL(launch_droppath_scale(t->seed, (unsigned long long)step * 64ULL + stage * 16 + i, ns, tapes[i].keep,
+      if (tapes[i].keep < 1.f) {      // two independent draws per block: RNG stream ids 2i (attention) and 2i + 1 (MLP)
+        UU_TL(launch_droppath_scale(t->seed, (unsigned long long)step * 64ULL + stage * 16 + 2 * i, ns, tapes[i].keep,
                                     tapes[i].scale, stream));
+        UU_TL(launch_droppath_scale(t->seed, (unsigned long long)step * 64ULL + stage * 16 + 2 * i + 1, ns, tapes[i].keep,
+                                    tapes[i].scale2, stream));
+      }
     }
   }
 
@@ -398,7 +404,7 @@ static int train_fb(uu_model* m, const float* x2d, const uint8_t* mask, const fl
     if (lin_fwd(c, t->hp[i], (long long)st_i * h, (int)Ro, 3 * h, W(m, g, 14), d, W(m, g, 15), t->tmp1, d)) return 1;
     RowMap idm;
     idm.rpb = Lo; idm.batch_rows = L; idm.offset = (st_i > 1 && pl == 0) ? 1 : 0; idm.step = st_i;
-    UU_TL(launch_residual(tp.x1, idm, t->tmp1, tp.keep < 1.f ? tp.scale : nullptr, Lo, nullptr, 1, Ro, d, tp.x2, stream));
+    UU_TL(launch_residual(tp.x1, idm, t->tmp1, tp.keep < 1.f ? tp.scale2 : nullptr, Lo, nullptr, 1, Ro, d, tp.x2, stream));
     x_in = tp.x2;
   }
   if (lin_fwd(c, x_in, d, B, d, W(m, "strided_temporal_fc", 0), 3 * J, W(m, "strided_temporal_fc", 1), t->central, 3 * J))
@@ -423,7 +429,7 @@ static int train_fb(uu_model* m, const float* x2d, const uint8_t* mask, const fl
     const BlkDims bd{d, h, L, H, (long long)B, 0};
     float* dx_prev = i > 0 ? t->dx_s[i - 1] : t->dx_t;        // gradient w.r.t. this block's input sequence
     // z path
-    UU_TL(launch_scale_rows(dx, tp.keep < 1.f ? tp.scale : nullptr, Lo, Ro, d, t->tmp1, stream));
+    UU_TL(launch_scale_rows(dx, tp.keep < 1.f ? tp.scale2 : nullptr, Lo, Ro, d, t->tmp1, stream));
     UU_CUDA(cudaMemsetAsync(t->dhp[i], 0, sizeof(float) * (size_t)B * Lo * st_i * h, stream));
     if (lin_bwd(c, t->hp[i], (long long)st_i * h, t->tmp1, d, (int)Ro, 3 * h, d, W(m, g, 14), t->dhp[i],
                 (long long)st_i * h, 0, G(m, g, 14), G(m, g, 15)))
@@ -550,8 +556,8 @@ int uu_get_grad(uu_model* m, const char* group, int index, float* host, int64_t 
   return 0;
 }
 
-int uu_get_droppath_scale(uu_model* m, int stage, int block, float* host, int64_t capacity, float* keep_prob) {
-  UU_CHECK(m && m->train && host && keep_prob, "bad argument");
+int uu_get_droppath_scale(uu_model* m, int stage, int block, int branch, float* host, int64_t capacity, float* keep_prob) {
+  UU_CHECK(m && m->train && host && keep_prob && (branch == 0 || branch == 1), "bad argument (branch: 0 attention, 1 MLP)");
   TrainState* t = m->train;
   UU_CHECK(stage >= 0 && stage < 3, "stage must be 0 (spatial), 1 (temporal) or 2 (strided)");
   std::vector<BlkTape>& tapes = stage == 0 ? t->sp : stage == 1 ? t->tp : t->st;
@@ -561,7 +567,7 @@ int uu_get_droppath_scale(uu_model* m, int stage, int block, float* host, int64_
   *keep_prob = tapes[block].keep;
   UU_CUDA(cudaSetDevice(m->device));
   if (tapes[block].keep < 1.f) {
-    UU_CUDA(cudaMemcpy(host, tapes[block].scale, sizeof(float) * ns, cudaMemcpyDeviceToHost));
+    UU_CUDA(cudaMemcpy(host, branch ? tapes[block].scale2 : tapes[block].scale, sizeof(float) * ns, cudaMemcpyDeviceToHost));
   } else {
     for (long long i = 0; i < ns; ++i) host[i] = 1.f;
   }
@@ -575,7 +581,7 @@ int uu_adamw_step(uu_model* m, float lr_t, float wd_t, float beta1, float beta2,
   UU_CUDA(cudaSetDevice(m->device));
   if (ema_decay >= 0.f && !m->ema) {   // EMA clone starts as a copy of the weights (train.py:396-401)
     UU_CUDA(cudaMalloc(&m->ema, sizeof(float) * m->n_alloc));
-    UU_CUDA(cudaMemcpy(m->ema, m->params, sizeof(float) * m->n_alloc, cudaMemcpyDeviceToDevice));
+    UU_CUDA(cudaMemcpyAsync(m->ema, m->params, sizeof(float) * m->n_alloc, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   }
   const double alpha = (double)lr_t * std::sqrt(1.0 - std::pow((double)beta2, (double)t)) /
                        (1.0 - std::pow((double)beta1, (double)t));

@@ -64,8 +64,17 @@ class Trainer:
         wd_params = copy.deepcopy(config.SCHEDULE_PARAMS)            # train.py:408-411
         wd_params["initial_learning_rate"] = config.WEIGHT_DECAY
         self.wd_schedule = mk(**wd_params)
-        self.beta1, self.beta2 = 0.9, 0.999
-        self.epsilon = float(config.OPTIMIZER_PARAMS.get("epsilon", 1e-8))     # train.py:414
+        # train.py:412-415 forwards **OPTIMIZER_PARAMS to tfa.optimizers.AdamW: honour what the fused update implements,
+        # reject the rest loudly
+        op = dict(config.OPTIMIZER_PARAMS or {})
+        self.beta1 = float(op.pop("beta_1", 0.9))
+        self.beta2 = float(op.pop("beta_2", 0.999))
+        self.epsilon = float(op.pop("epsilon", 1e-7))                           # Keras Adam default; shipped configs set 1e-8
+        if op.pop("amsgrad", False):
+            raise NotImplementedError("OPTIMIZER_PARAMS amsgrad=True is not implemented by the fused AdamW update")
+        op.pop("name", None)
+        if op:
+            raise NotImplementedError(f"unsupported OPTIMIZER_PARAMS keys: {sorted(op)}")
         self.iterations = 0
         self.ema_enabled = bool(config.EMA_ENABLED)
         self.ema_decay = config.EMA_DECAY
@@ -112,7 +121,7 @@ class Trainer:
         ema = -1.0
         if self.ema_enabled:
             ema = min(self.ema_decay, (1 + it) / (10 + it))
-        stream = self.torch.cuda.current_stream().cuda_stream
+        stream = self.torch.cuda.current_stream(self.model.device).cuda_stream
         _lib.check(self.lib.uu_adamw_step(self.model._h, lr_t, wd_t, self.beta1, self.beta2, self.epsilon, it + 1,
                                           ema, stream))
         self.iterations += 1
@@ -150,15 +159,18 @@ class Trainer:
         return buf.reshape(B, self.model.spec.n_tok)
 
     def droppath_keeps(self, B: int):
-        """{(stage, block): (keep_prob, mask ndarray)} actually used by the last step, in the oracle's format."""
+        """{(stage, block, branch): (keep_prob, mask ndarray)} actually used by the last step, in the oracle's format
+        (branch 0 = attention residual, 1 = MLP residual: independent draws, vision_transformer.py:185-190)."""
         s = self.model.spec
         out = {}
         for si, (stage, depth, n) in enumerate((("spatial", s.spatial_depth, B * s.n_tok), ("temporal", s.temporal_depth, B),
                                                  ("strided", len(s.strides), B))):
             for i in range(depth):
-                buf = np.empty(n, dtype=np.float32)
-                kp = c_float()
-                _lib.check(self.lib.uu_get_droppath_scale(self.model._h, si, i, buf.ctypes.data_as(c_void_p), n, byref(kp)))
-                if kp.value < 1.0:
-                    out[(stage, i)] = (kp.value, buf * kp.value)
+                for branch in (0, 1):
+                    buf = np.empty(n, dtype=np.float32)
+                    kp = c_float()
+                    _lib.check(self.lib.uu_get_droppath_scale(self.model._h, si, i, branch, buf.ctypes.data_as(c_void_p), n,
+                                                              byref(kp)))
+                    if kp.value < 1.0:
+                        out[(stage, i, branch)] = (kp.value, buf * kp.value)
         return out
