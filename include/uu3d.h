@@ -12,8 +12,11 @@
  *   uu_forward / uu_forward_host
  *                               model([x2d, stride_mask], training=False) -> (full, central)
  *                               common/net/uplift_upsample_transformer.py:388-421 ; caller eval.py:63-71
- *   uu_train_config / uu_train_forward_backward / uu_grad_buffer / uu_comm_init / uu_allreduce_gradients / uu_adamw_step
- *                               train_step(): loss, gradients, gradient all-reduce, AdamW   train.py:464-506, :403-415
+ *   uu_train_config / uu_train_forward_backward / uu_grad_buffer / uu_adamw_step ; uu_train_step (all of it in one call)
+ *                               train_step(): loss, gradients, AdamW                        train.py:464-506, :403-415
+ *   uu_comm_unique_id / uu_comm_init / uu_comm_destroy / uu_allreduce_gradients
+ *                               the gradient exchange of the reference's tf.distribute strategy (train.py:464-506 runs
+ *                               under strategy.run): NCCL sum all-reduce over NVLink
  *   uu_stride_mask              stride-mask rule of the data generators
  *                               common/dataset/uplifiting_dataset.py:377-394
  *
@@ -182,6 +185,24 @@ int uu_get_droppath_scale(uu_model* m, int stage, int block, int branch, float* 
 int uu_adamw_step(uu_model* m, float lr_t, float wd_t, float beta1, float beta2, float epsilon, int64_t t,
                   float ema_decay, void* stream);
 int uu_get_ema_weight(uu_model* m, const char* group, int index, float* host, int64_t capacity);
+
+/* ---- data-parallel training: one process (or thread) per GPU, one model per process ------------------------
+ * uu_comm_unique_id : rank 0 obtains a 128-byte NCCL id and sends it to the other ranks by any means.
+ * uu_comm_init      : every rank creates its communicator (collective call); world == 1 is a no-op.  NCCL is resolved at
+ *                     run time (the libnccl.so.2 already loaded into the process, else the system one).
+ * uu_allreduce_gradients : sum all-reduce of the whole flat gradient buffer, ordered after the work on `stream`.
+ * uu_train_step     : forward + backward of the B local windows, gradient all-reduce issued in three buckets on a side
+ *                     stream as the backward pass finishes them (strided blocks + heads, temporal blocks, the rest) so the
+ *                     exchange overlaps the remaining backward work, all-reduced loss in loss_dev (device float), then the
+ *                     fused AdamW / EMA update with the host-evaluated lr_t / wd_t (Adam t = step + 1).  Without a
+ *                     communicator it is a plain local step. */
+int uu_comm_unique_id(void* id_out_128_bytes, int capacity);
+int uu_comm_init(uu_model* m, const void* unique_id_128_bytes, int rank, int world);
+int uu_comm_destroy(uu_model* m);
+int uu_comm_world_size(const uu_model* m);
+int uu_allreduce_gradients(uu_model* m, void* stream);
+int uu_train_step(uu_model* m, const float* x2d, const uint8_t* mask, const float* gt3d, int B, int64_t step, float lr_t,
+                  float wd_t, float beta1, float beta2, float epsilon, float ema_decay, float* loss_dev, void* stream);
 
 /* Stride-mask rule (host, integer, bit-exact): mask[n] = ((n - n_tok/2)*s_out + shift) floor-mod s_in == 0.
  * shift = centre frame index (eval, global alignment) or rand_shift*s_out (training). */

@@ -119,6 +119,13 @@ struct uu_model {
   float *adam_m = nullptr, *adam_v = nullptr, *ema = nullptr;
   struct TrainState* train = nullptr;
 
+  // ---- data-parallel training (uu_comm.cu): NCCL communicator owned by the model, a side stream for the bucketed
+  // gradient all-reduce and the events that order it against the backward pass
+  void* nccl_comm = nullptr;
+  int comm_rank = 0, comm_world = 1;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t comm_ev_ready[4] = {}, comm_ev_done = nullptr;
+
   // optional per-kernel-kind timing (uu_set_profiling): CUDA events around every launch
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -133,4 +140,10 @@ size_t tensor_offset(const uu_model* m, const std::string& g, int i);   // (size
 int dev_alloc(std::vector<void*>& pool, void** p, size_t bytes, bool zero);
 void free_pool(std::vector<void*>& pool);
 void train_state_destroy(uu_model* m);
+// uu_comm.cu: sum all-reduce of grads[lo, hi) on the model's communication stream, ordered after everything enqueued on
+// `main` so far (no-op without a communicator); comm_join makes `main` wait for every bucket issued since the last join
+int comm_allreduce_range(uu_model* m, size_t lo, size_t hi, int bucket, cudaStream_t main);
+int comm_allreduce_scalar(uu_model* m, float* dev_value, cudaStream_t main);
+int comm_join(uu_model* m, cudaStream_t main);
+void comm_destroy(uu_model* m);
 }  // namespace uu

@@ -706,6 +706,7 @@ int uu_destroy(uu_model* m) {
   free_pool(m->ws_allocs);
   free_pool(m->derived_allocs);
   train_state_destroy(m);
+  comm_destroy(m);
   cudaFree(m->grads); cudaFree(m->adam_m); cudaFree(m->adam_v); cudaFree(m->ema);
   cudaFree(m->params);
   cudaFree(m->d_x);

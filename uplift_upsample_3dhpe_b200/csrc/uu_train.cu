@@ -325,8 +325,11 @@ static float block_keep(const TrainState* t, int stage, int i, int depth) {
   return 1.f - rate;
 }
 
+// overlap_comm: issue the gradient all-reduce (uu_comm.cu) bucket by bucket as the backward pass finishes regions of the
+// flat gradient buffer: [strided blocks, heads] after the strided stage, [temporal blocks] after the temporal stage,
+// the rest (embeddings, positional tables, spatial blocks, spatial_to_temporal_fc) at the end.
 static int train_fb(uu_model* m, const float* x2d, const uint8_t* mask, const float* gt3d, int B, long long step,
-                    float* loss_out, cudaStream_t stream) {
+                    float* loss_out, cudaStream_t stream, bool overlap_comm = false) {
   const uu_spec& s = m->spec;
   UU_CHECK(m->train && m->train->global_batch > 0, "call uu_train_config first");
   UU_CHECK(B > 0 && x2d && gt3d && loss_out, "bad argument");
@@ -453,10 +456,13 @@ static int train_fb(uu_model* m, const float* x2d, const uint8_t* mask, const fl
   if (lin_bwd(c, xT, d, t->dfull, 3 * J, (int)R, d, 3 * J, W(m, "temporal_fc", 0), t->dx_t, d, 1, G(m, "temporal_fc", 0),
               G(m, "temporal_fc", 1)))
     return 1;
+  const size_t off_temporal = tensor_offset(m, "temporal_block_1", 0), off_strided = tensor_offset(m, "strided_temporal_block_1", 0);
+  if (overlap_comm && comm_allreduce_range(m, off_strided, m->n_alloc, 0, stream)) return 1;
   for (int i = s.temporal_depth - 1; i >= 0; --i) {
     const uint8_t* km = (use_mask && i < s.first_strided_token_attention_layer) ? mask : nullptr;
     if (block_bwd(c, tp_dims, "temporal_block_" + std::to_string(i + 1), t->tp[i], km, N, t->dx_t)) return 1;
   }
+  if (overlap_comm && comm_allreduce_range(m, off_temporal, off_strided, 1, stream)) return 1;
   // temporal input: x = m*s4 + (1-m)*token + PE
   UU_TL(launch_period_sum(t->dx_t, R, N, d, nullptr, 0, G(m, "temporal_pe", 0), stream));
   if (use_mask) {
@@ -474,6 +480,11 @@ static int train_fb(uu_model* m, const float* x2d, const uint8_t* mask, const fl
   UU_TL(launch_colsum(t->dx_sp, (int)Rs, ds, ds, G(m, "keypoint_embedding", 1), stream));
   UU_TL(launch_period_sum(t->dx_sp, Rs, J, ds, nullptr, 0, G(m, "spatial_pe", 0), stream));
   UU_TL(launch_embed_wgrad(x2d, use_mask ? mask : nullptr, J, t->dx_sp, Rs, ds, G(m, "keypoint_embedding", 0), stream));
+  if (overlap_comm) {
+    if (comm_allreduce_range(m, 0, off_temporal, 2, stream)) return 1;
+    if (comm_allreduce_scalar(m, loss_out, stream)) return 1;
+    if (comm_join(m, stream)) return 1;
+  }
   return 0;
 }
 
@@ -500,6 +511,17 @@ int uu_train_forward_backward(uu_model* m, const float* x2d, const uint8_t* mask
   UU_CHECK(m, "null model");
   if (m->train) m->train->wt_valid.clear();     // weights may have changed since the last call
   return train_fb(m, x2d, mask, gt3d, B, step, loss_dev, (cudaStream_t)stream);
+}
+
+/* One data-parallel training step through the C ABI alone (train.py:464-506): forward + backward of the local windows,
+ * the bucketed NCCL sum all-reduce of the gradients overlapped with the backward pass (after uu_comm_init; a plain local
+ * step without a communicator), the all-reduced loss in loss_dev, and the fused AdamW / EMA update. */
+int uu_train_step(uu_model* m, const float* x2d, const uint8_t* mask, const float* gt3d, int B, int64_t step, float lr_t,
+                  float wd_t, float beta1, float beta2, float epsilon, float ema_decay, float* loss_dev, void* stream) {
+  UU_CHECK(m, "null model");
+  if (m->train) m->train->wt_valid.clear();
+  if (train_fb(m, x2d, mask, gt3d, B, step, loss_dev, (cudaStream_t)stream, true)) return 1;
+  return uu_adamw_step(m, lr_t, wd_t, beta1, beta2, epsilon, step + 1, ema_decay, stream);
 }
 
 int uu_train_set_token_masking(uu_model* m, float rate) {

@@ -69,7 +69,7 @@ class Trainer:
         op = dict(config.OPTIMIZER_PARAMS or {})
         self.beta1 = float(op.pop("beta_1", 0.9))
         self.beta2 = float(op.pop("beta_2", 0.999))
-        self.epsilon = float(op.pop("epsilon", 1e-7))                           # Keras Adam default; shipped configs set 1e-8
+        self.epsilon = float(op.pop("epsilon", 1e-8))                           # train.py:414 passes epsilon=1e-8
         if op.pop("amsgrad", False):
             raise NotImplementedError("OPTIMIZER_PARAMS amsgrad=True is not implemented by the fused AdamW update")
         op.pop("name", None)
@@ -126,13 +126,57 @@ class Trainer:
                                           ema, stream))
         self.iterations += 1
 
+    def init_comm(self, dist) -> None:
+        """Create the library's own NCCL communicator (uu_comm_init): rank 0 draws the 128-byte id, torch.distributed
+        only carries it to the other ranks.  Afterwards train_step runs the whole step inside the library, with the
+        gradient all-reduce bucketed and overlapped with the backward pass."""
+        torch = self.torch
+        world, rank = dist.get_world_size(), dist.get_rank()
+        if world <= 1:
+            return
+        buf = (ctypes.c_uint8 * 128)()
+        if rank == 0:
+            _lib.check(self.lib.uu_comm_unique_id(buf, 128))
+        idt = torch.tensor(list(buf), dtype=torch.uint8)
+        if dist.get_backend() == "nccl":
+            idt = idt.to(f"cuda:{self.model.device}")
+        dist.broadcast(idt, src=0)
+        raw = (ctypes.c_uint8 * 128)(*idt.cpu().tolist())
+        _lib.check(self.lib.uu_comm_init(self.model._h, raw, rank, world))
+        self._comm = True
+
     def train_step(self, keypoints2d, keypoints3d, stride_masks, dist=None):
+        """One optimisation step (train.py:464-506).  With a library communicator (init_comm) the step is ONE C-ABI call:
+        forward, backward, bucketed all-reduce overlapped with the backward pass, AdamW.  Otherwise the gradients are
+        summed with torch.distributed between forward_backward and apply_gradients (dist given), or not at all."""
+        if getattr(self, "_comm", False):
+            return self._fused_step(keypoints2d, keypoints3d, stride_masks)
         loss = self.forward_backward(keypoints2d, keypoints3d, stride_masks)
         if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
             allreduce_gradients(self.grad_view(), dist)                   # NCCL sum over NVLink
             dist.all_reduce(loss, op=dist.ReduceOp.SUM)
         self.apply_gradients()
         return loss
+
+    def _fused_step(self, keypoints2d, keypoints3d, stride_masks):
+        torch = self.torch
+        s = self.model.spec
+        x = keypoints2d.contiguous().float()
+        g = keypoints3d.contiguous().float()
+        B = x.shape[0]
+        assert tuple(x.shape[1:]) == (s.n_tok, s.n_joints, 2) and tuple(g.shape) == (B, s.n_tok, s.n_joints, 3)
+        mptr = None
+        if self.model.has_strided_input:
+            mk = stride_masks.to(device=x.device, dtype=torch.uint8).contiguous()
+            mptr = mk.data_ptr()
+        it = self.iterations
+        ema = min(self.ema_decay, (1 + it) / (10 + it)) if self.ema_enabled else -1.0
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        _lib.check(self.lib.uu_train_step(self.model._h, x.data_ptr(), mptr, g.data_ptr(), B, it, self.lr_schedule(it),
+                                          self.wd_schedule(it), self.beta1, self.beta2, self.epsilon, ema,
+                                          self._loss.data_ptr(), stream))
+        self.iterations += 1
+        return self._loss
 
     # ---- introspection for the parity tests ----------------------------------------------------------
     def get_grads(self):
