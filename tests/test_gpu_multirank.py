@@ -84,9 +84,11 @@ def test_n_rank_step_equals_one_rank_step(math):
         # tensor-core mode additionally re-tiles its split-K reductions with the local row count
         gtol = 1e-4 if math == "fp32" else 2e-3
         assert np.allclose(a["losses"], b["losses"], rtol=1e-5 if math == "fp32" else 1e-4, atol=0)
+        # (key biases have a mathematically zero gradient: compare against a floor relative to the largest gradient)
+        floor = 1e-6 * max(np.abs(a[k]).max() for k in a.files if k.startswith("g|"))
         for k in a.files:
             if k.startswith("g|"):
-                assert np.abs(a[k] - b[k]).max() <= gtol * np.abs(a[k]).max() + 1e-9, k
+                assert np.abs(a[k] - b[k]).max() <= gtol * np.abs(a[k]).max() + floor, k
         w0 = {k: v for k, v in a.items() if k.startswith("w|")}
         for k in w0:
             # three steps move a weight by ~3 lr = 1.2e-4; weights must agree far inside that (key biases: gradient is
