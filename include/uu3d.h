@@ -233,6 +233,12 @@ int uu_op_gemm_bf16(const void* A, int64_t lda, int M, int K, const void* Wt, in
  * with pitches lda / ldb (multiples of 4), N % 64 == 0; C fp32 = A . B (+ bias) (ReLU: flags & 1) (+ res: flags & 2). */
 int uu_op_gemm_tf32(const float* A, int64_t lda, int M, int K, const float* Bt, int64_t ldb, int N, const float* bias,
                     int flags, const float* res, int64_t ldr, float* C, int64_t ldc, void* stream);
+/* tcgen05 kind::tf32 weight gradient of the training step: dW (Kd, Nd) (+)= X^T dY with X (R, Kd) and dY (R, Nd) fp32
+ * row-major (pitches ldx / ldy): the contraction runs over the row index, both operands are read MN-major through TMA,
+ * split-K partials are summed in a fixed order (deterministic).  R >= 256, Kd % 32 == 0 (>= 128), Nd % 64 == 0.
+ * Synchronous (temporary scratch). */
+int uu_op_wgrad_tf32(const float* X, int64_t ldx, const float* dY, int64_t ldy, int64_t R, int Kd, int Nd, float* dW,
+                     int accumulate, void* stream);
 /* The folded epilogues of the bf16 schedule in isolation ("LayerNorm and residual folding"); they
  * replace LayerNormalization + Dense (vit:168-171, :183-195) and Dense + residual add.  Synchronous (temporaries).
  *   out[rows, N] (bf16) = act( LN(x; gamma, beta, eps) . W + bias ),  x bf16 [rows, d], W fp32 (d, N) on the device */

@@ -95,4 +95,6 @@ def test_n_rank_step_equals_one_rank_step(math):
             # round-off noise that Adam normalises to +-lr, excluded as in test_three_adamw_steps_match_oracle)
             if k.endswith("|5") and "block" in k:
                 continue
-            assert np.abs(a[k] - b[k]).max() < 2e-5, k
+            # (tf32 mode: entries whose gradient is dominated by the TF32 rounding of different partial sums can take one
+            # Adam step of +-lr = 4e-5 in the other direction)
+            assert np.abs(a[k] - b[k]).max() < (2e-5 if math == "fp32" else 1e-4), k

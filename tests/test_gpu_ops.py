@@ -213,6 +213,33 @@ def test_gemm_tf32_tcgen05(lib, M, N, K, flags):
     assert err < 8e-3, err
 
 
+@pytest.mark.parametrize("R,Kd,Nd,ldx_extra,acc", [(300, 384, 384, 0, 0), (5000, 384, 768, 0, 1), (36352, 768, 384, 0, 1),
+                                                    (1000, 544, 384, 0, 0), (777, 2304, 384, 768, 1), (4100, 384, 64, 0, 0),
+                                                    (2900, 384, 384, 768, 1)])
+def test_wgrad_tf32_tcgen05(lib, R, Kd, Nd, ldx_extra, acc):
+    """dW (+)= X^T dY on tcgen05 kind::tf32 with MN-major operands (contraction over the row index, TMA straight from the
+    row-major tape), split-K partials summed in a fixed order.  Reference: float64 on the same fp32 data; TF32 truncation
+    gives ~1e-3 of the output scale (outputs here have unit variance).  ldx_extra > 0: strided rows (the zero-padded
+    conv input / a column slice of the q|k|v gradient).  Two runs must agree bit for bit (no atomics)."""
+    rng = np.random.default_rng(R + Kd + Nd)
+    ldx, ldy = Kd + ldx_extra, Nd + (128 if ldx_extra else 0)
+    Xf = rng.normal(size=(R, ldx)).astype(np.float32)
+    Yf = (rng.normal(size=(R, ldy)) / math.sqrt(R)).astype(np.float32)
+    W0 = rng.normal(size=(Kd, Nd)).astype(np.float32)
+    want = Xf[:, :Kd].astype(np.float64).T @ Yf[:, :Nd].astype(np.float64) + (W0 if acc else 0)
+    Xd, Yd = dev(Xf), dev(Yf)
+    outs = []
+    for _ in range(2):
+        Wd = dev(W0.copy())
+        _lib.check(lib.uu_op_wgrad_tf32(P(Xd), ldx, P(Yd), ldy, R, Kd, Nd, P(Wd), acc, None))
+        torch.cuda.synchronize()
+        outs.append(Wd.cpu().numpy())
+    err = np.abs(outs[0] - want).max()
+    print(f"tf32 wgrad R={R} {Kd}x{Nd}: max err {err:.2e}")
+    assert err < 8e-3, err
+    assert np.array_equal(outs[0], outs[1]), "split-K reduction must be deterministic"
+
+
 @pytest.mark.parametrize("rows,N,relu", [(71, 1152, 0), (300, 768, 1), (36352, 1152, 0), (5000, 128, 1)])
 def test_layernorm_folded_into_gemm(lib, rows, N, relu):
     """EPI_LNFOLD: the GEMM reads the raw bf16 stream with gamma folded into W and finishes LayerNorm (vit:168-171) in

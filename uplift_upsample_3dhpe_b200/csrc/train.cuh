@@ -54,4 +54,11 @@ cudaError_t launch_droppath_scale(unsigned long long seed, unsigned long long st
 cudaError_t launch_adamw(float* p, float* m, float* v, const float* g, long long n, float wd, float alpha, float b1,
                          float b2, float eps, float* ema, float ema_decay, cudaStream_t st);
 
+
+// ---- tcgen05 kind::tf32 weight gradients (wgrad_tc.cu): dW [Kd, Nd] (+)= X^T dY, deterministic split-K ------------
+size_t wgrad_tc_scratch_bytes();
+bool wgrad_tc_ok(const float* X, long long ldx, const float* dY, long long ldy, long long R, int Kd, int Nd);
+int wgrad_tc(const float* X, long long ldx, const float* dY, long long ldy, long long R, int Kd, int Nd, float* dW,
+             int accumulate, float* scratch, int num_sms, cudaStream_t st);
+
 }  // namespace uu

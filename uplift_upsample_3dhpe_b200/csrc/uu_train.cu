@@ -47,6 +47,7 @@ struct TrainState {
   float token_mask_rate = 0.f;                  // TOKEN_MASK_RATE (net:287-311; masked value 0), training only
   float* tok_keep = nullptr;                    // [R] 0 / 1 factors drawn for the current step
   int math = 0;
+  float* wg_scratch = nullptr;                  // split-K partial tiles of the tensor-core wgrad (wgrad_tc.cu)
   std::unordered_map<const float*, float*> wt;   // W (K, N) -> W^T (N, K) copies for the forward GEMMs
   std::unordered_set<const float*> wt_valid;     // refreshed once per forward/backward call
 };
@@ -159,7 +160,10 @@ static int lin_bwd(Ctx& c, const float* X, long long ldx, const float* dY, long 
     if (dxmap) g.cmap = *dxmap;
     UU_TL(launch_gemm_gen(g, c.st));
   }
-  {
+  if (c.t->math == 1 && wgrad_tc_ok(X, ldx, dY, ldy, M, K, N)) {
+    // dW += X^T dY on tcgen05 kind::tf32, both operands read MN-major straight from the tape (wgrad_tc.cu)
+    if (wgrad_tc(X, ldx, dY, ldy, M, K, N, dW, 1, c.t->wg_scratch, c.m->num_sms, c.st)) return 1;
+  } else {
     GemmGen g;
     g.A = X; g.lda = ldx; g.transA = 1; g.B = dY; g.ldb = ldy; g.C = dW; g.ldc = N; g.M = K; g.N = N; g.K = M;
     g.accumulate = 1;
@@ -315,6 +319,7 @@ static int ensure_train(uu_model* m, int B) {
     return 1;
   if (falloc(t, &t->partials, loss_blocks(B, (int)N, (int)J, true) + 8) || falloc(t, &t->loss, 4)) return 1;
   if (falloc(t, &t->tok_keep, R)) return 1;
+  if (falloc(t, &t->wg_scratch, wgrad_tc_scratch_bytes() / sizeof(float))) return 1;
   t->B = B;
   return 0;
 }
@@ -549,6 +554,21 @@ int uu_train_set_math(uu_model* m, int mode) {
   if (!m->train) m->train = new TrainState();
   m->train->math = mode;
   return 0;
+}
+
+int uu_op_wgrad_tf32(const float* X, int64_t ldx, const float* dY, int64_t ldy, int64_t R, int Kd, int Nd, float* dW,
+                     int accumulate, void* stream) {
+  UU_CHECK(X && dY && dW, "null argument");
+  UU_CHECK(wgrad_tc_ok(X, ldx, dY, ldy, R, Kd, Nd), "shape not supported: R >= 256, Kd % 32 == 0 (>= 128), Nd % 64 == 0, pitches % 4 == 0");
+  int dev = 0, sms = 148;
+  UU_CUDA(cudaGetDevice(&dev));
+  UU_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  float* scratch = nullptr;
+  UU_CUDA(cudaMalloc(&scratch, wgrad_tc_scratch_bytes()));
+  const int rc = wgrad_tc(X, ldx, dY, ldy, R, Kd, Nd, dW, accumulate, scratch, sms, (cudaStream_t)stream);
+  cudaStreamSynchronize((cudaStream_t)stream);
+  cudaFree(scratch);
+  return rc;
 }
 
 int uu_grad_buffer(uu_model* m, float** dev_ptr, int64_t* n_floats) {
