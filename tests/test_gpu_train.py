@@ -67,6 +67,30 @@ def test_loss_and_gradients_match_autograd(name, B, droppath, math):
     model.close()
 
 
+@pytest.mark.parametrize("math", ["fp32", "tf32"])
+def test_gradients_are_bitwise_reproducible(math):
+    """Every cross-CTA gradient reduction (biases, LayerNorm gamma / beta, positional tables, split-K weight gradients
+    on CUDA cores and on tcgen05) is a two-pass sum in a fixed order: no floating-point atomics, so two runs of the same
+    step give identical bits."""
+    B = 12
+    cfg = UpliftUpsampleConfig.preset("h36m_81", BATCH_SIZE=B)
+    spec = spec_from_config(cfg)
+    w = weights.init_weights(spec, 1, perturb=True)
+    x, gt, m = _data(cfg, spec, B)
+    model = build_uplift_upsample_transformer(cfg, precision="fp32", weights=w)
+    tr = Trainer(model, cfg, droppath=True, seed=3, math=math)
+    args = (torch.from_numpy(x).cuda(), torch.from_numpy(gt).cuda(), torch.from_numpy(m).cuda())
+    runs = []
+    for _ in range(2):
+        loss = tr.forward_backward(*args)
+        torch.cuda.synchronize()
+        runs.append((float(loss.item()), tr.get_grads()))
+    assert runs[0][0] == runs[1][0]
+    for k in runs[0][1]:
+        assert np.array_equal(runs[0][1][k], runs[1][1][k]), k
+    model.close()
+
+
 def test_droppath_draws_are_independent_per_branch_and_hit_the_rate():
     """D1 (vit:16-43, :185-190): the attention and the MLP branch of a block draw their own per-sample masks, with
     drop rate linspace(0, dpr, depth)[i]; spatial blocks draw per frame (B * n_tok samples), the others per window."""

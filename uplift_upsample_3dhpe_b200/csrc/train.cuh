@@ -12,10 +12,17 @@ struct GemmGen {
   const float* bias = nullptr;   // forward only
   int relu = 0;                  // forward only
   int accumulate = 0;            // C += ...
-  int split_k = 1;               // > 1: fp32 atomics into C (requires accumulate)
+  int split_k = 1;               // > 1: split-K partial slabs, reduced in split order (requires accumulate, plain C)
+  float* partial = nullptr;      // set by launch_gemm_gen
 };
+// scratch for the deterministic two-pass reductions of this translation unit (set before launching a step)
+void train_reduce_scratch(float* p, size_t n_floats);
+size_t train_reduce_scratch_floats();
 cudaError_t launch_gemm_gen(const GemmGen& g, cudaStream_t st);
-void gemm_gen_tile(int N, int* bm, int* bn);      // tile shape launch_gemm_gen picks for an N-wide output
+void gemm_gen_tile(int N, int* bm, int* bn);
+bool wgrad_skinny_ok(const float* X, long long ldx, const float* dY, long long ldy, long long rows, int K, int N);
+cudaError_t launch_wgrad_skinny(const float* X, long long ldx, const float* dY, long long ldy, long long rows, int K, int N,
+                                float* dW, float* db, cudaStream_t st);      // tile shape launch_gemm_gen picks for an N-wide output
 cudaError_t launch_colsum(const float* Y, int M, int N, long long ld, float* out, cudaStream_t st);
 cudaError_t launch_period_sum(const float* X, long long rows, int period, int d, const uint8_t* rowmask, int want,
                               float* out, cudaStream_t st);

@@ -17,11 +17,35 @@ __device__ __forceinline__ float warp_sum_t(float v) {
   return v;
 }
 
+// ---- deterministic cross-CTA reductions ---------------------------------------------------------------------------
+// Gradients that sum over rows (biases, LayerNorm gamma / beta, positional tables, split-K weight gradients) are reduced
+// in two passes: every CTA writes its partial sums into a scratch slab [part][n], k_reduce_partials adds the slabs to the
+// gradient in slab order.  No floating-point atomics: two runs of a step give bit-identical gradients.
+static float* g_red_scratch = nullptr;
+static size_t g_red_floats = 0;
+void train_reduce_scratch(float* p, size_t n_floats) { g_red_scratch = p; g_red_floats = n_floats; }
+size_t train_reduce_scratch_floats() { return (size_t)6 << 20; }
+
+// out[i] += sum_p part[p * n + i]; elements i >= n0 go to out1[i - n0] (two destination tensors, e.g. gamma | beta)
+__global__ void k_reduce_partials(const float* __restrict__ part, int nparts, long long n, float* __restrict__ out0,
+                                  long long n0, float* __restrict__ out1) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int p = 0; p < nparts; ++p) s += part[(long long)p * n + i];
+    float* dst = i < n0 ? out0 + i : out1 + (i - n0);
+    *dst += s;
+  }
+}
+static cudaError_t reduce_partials(int nparts, long long n, float* out0, long long n0, float* out1, cudaStream_t st) {
+  k_reduce_partials<<<(unsigned)std::min<long long>((n + 255) / 256, 592), 256, 0, st>>>(g_red_scratch, nparts, n, out0, n0, out1);
+  return cudaGetLastError();
+}
+
 // =================================================================================================
 // Generic fp32 GEMM: C[crow(r)][n] (+)= sum_k opA(r,k) * opB(k,n)   (+ bias[n])
 //   opA(r,k) = TA ? A[k*lda + r] : A[arow(r)*lda + k]   (arow via RowMap, dropped rows read as 0)
 //   opB(k,n) = TB ? B[n*ldb + k] : B[k*ldb + n]
-//   split-K over gridDim.z with fp32 atomics (C must be pre-initialised; used for weight gradients).
+//   split-K over gridDim.z into partial slabs reduced in split order (used for weight gradients).
 // =================================================================================================
 // BM x BN x 16 tiles, 256 threads, 8 x TN outputs per thread (4-wide strips so that every shared-memory read is a
 // conflict-free float4), 16-byte global loads with a scalar fallback for unaligned / ragged edges, next tile
@@ -153,8 +177,8 @@ __global__ void __launch_bounds__(256, 2) k_gemm_gen(GemmGen g) {
       if (c >= g.N) continue;
       float v = acc[i][j];
       float* dst = g.C + cr * g.ldc + c;
-      if (gridDim.z > 1) {
-        atomicAdd(dst, v);
+      if (gridDim.z > 1) {       // split-K: partial slab [split][M][N] (plain output rows, ldc == N), reduced in split order
+        g.partial[((long long)blockIdx.z * g.M + r) * g.N + c] = v;
       } else {
         if (g.bias) v += g.bias[c];
         if (g.relu) v = fmaxf(v, 0.f);
@@ -162,6 +186,90 @@ __global__ void __launch_bounds__(256, 2) k_gemm_gen(GemmGen g) {
       }
     }
   }
+}
+
+// ---- narrow weight gradients (spatial blocks: 32 / 64-wide layers over B * n_tok * 17 rows) ----------------------
+// dW[KD][ND] += X^T dY and db[ND] += colsum(dY) in ONE pass over the rows: these products are memory-bound (one read of
+// X and dY), so every CTA streams a contiguous row range through shared memory, keeps its KD x ND partial sums in
+// registers (thread (k, n-chunk) owns KD/32 x ND/8 of them) and writes one partial slab; slabs are reduced in order.
+template <int KD, int ND>
+__global__ void __launch_bounds__(256) k_wgrad_skinny(const float* __restrict__ X, long long ldx, const float* __restrict__ dY,
+                                                      long long ldy, long long rows, float* __restrict__ partial) {
+  constexpr int TR = 64, KPT = KD / 32, NPT = ND / 8;
+  __shared__ __align__(16) float Xs[TR][KD];
+  __shared__ __align__(16) float Ys[TR][ND];
+  const int tid = threadIdx.x, k0 = tid >> 3, n0 = (tid & 7) * NPT;
+  const long long per = ((rows + gridDim.x - 1) / gridDim.x + TR - 1) / TR * TR;
+  const long long r0 = blockIdx.x * per, r1 = min(rows, r0 + per);
+  float acc[KPT][NPT], bs[NPT];
+#pragma unroll
+  for (int j = 0; j < NPT; ++j) {
+    bs[j] = 0.f;
+#pragma unroll
+    for (int i = 0; i < KPT; ++i) acc[i][j] = 0.f;
+  }
+  for (long long t0 = r0; t0 < r1; t0 += TR) {
+    for (int i = tid; i < TR * KD / 4; i += 256) {
+      const int r = i / (KD / 4), c = (i - r * (KD / 4)) * 4;
+      *reinterpret_cast<float4*>(&Xs[r][c]) = (t0 + r < r1) ? *reinterpret_cast<const float4*>(X + (t0 + r) * ldx + c)
+                                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int i = tid; i < TR * ND / 4; i += 256) {
+      const int r = i / (ND / 4), c = (i - r * (ND / 4)) * 4;
+      *reinterpret_cast<float4*>(&Ys[r][c]) = (t0 + r < r1) ? *reinterpret_cast<const float4*>(dY + (t0 + r) * ldy + c)
+                                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int r = 0; r < TR; ++r) {
+      float y[NPT];
+#pragma unroll
+      for (int j = 0; j < NPT; j += 4) {
+        const float4 q = *reinterpret_cast<const float4*>(&Ys[r][n0 + j]);
+        y[j] = q.x; y[j + 1] = q.y; y[j + 2] = q.z; y[j + 3] = q.w;
+      }
+#pragma unroll
+      for (int i = 0; i < KPT; ++i) {
+        const float xv = Xs[r][k0 + 32 * i];
+#pragma unroll
+        for (int j = 0; j < NPT; ++j) acc[i][j] = fmaf(xv, y[j], acc[i][j]);
+      }
+      if (k0 == 0) {
+#pragma unroll
+        for (int j = 0; j < NPT; ++j) bs[j] += y[j];
+      }
+    }
+    __syncthreads();
+  }
+  float* out = partial + (long long)blockIdx.x * (KD * ND + ND);
+#pragma unroll
+  for (int i = 0; i < KPT; ++i)
+#pragma unroll
+    for (int j = 0; j < NPT; ++j) out[(k0 + 32 * i) * ND + n0 + j] = acc[i][j];
+  if (k0 == 0) {
+#pragma unroll
+    for (int j = 0; j < NPT; ++j) out[KD * ND + n0 + j] = bs[j];
+  }
+}
+bool wgrad_skinny_ok(const float* X, long long ldx, const float* dY, long long ldy, long long rows, int K, int N) {
+  return rows >= 4096 && (K == 32 || K == 64) && (N == 32 || N == 64 || N == 96) && ldx % 4 == 0 && ldy % 4 == 0 &&
+         ((uintptr_t)X & 15) == 0 && ((uintptr_t)dY & 15) == 0;
+}
+// dW [K, N] += X^T dY, db [N] += colsum(dY) (db may be null)
+cudaError_t launch_wgrad_skinny(const float* X, long long ldx, const float* dY, long long ldy, long long rows, int K, int N,
+                                float* dW, float* db, cudaStream_t st) {
+  const unsigned grid = (unsigned)std::min<long long>(148 * 4, (rows + 255) / 256);
+  if ((size_t)grid * (K * N + N) > g_red_floats) return cudaErrorInvalidValue;
+#define UU_WS(KD, ND) if (K == KD && N == ND) k_wgrad_skinny<KD, ND><<<grid, 256, 0, st>>>(X, ldx, dY, ldy, rows, g_red_scratch); else
+  UU_WS(32, 32) UU_WS(32, 64) UU_WS(32, 96) UU_WS(64, 32) UU_WS(64, 64) UU_WS(64, 96) return cudaErrorInvalidValue;
+#undef UU_WS
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (db) return reduce_partials((int)grid, (long long)K * N + N, dW, (long long)K * N, db, st);
+  // without a bias gradient the slab still carries the N column sums: reduce the K * N part only (strided slabs)
+  k_reduce_partials<<<(unsigned)std::min<long long>(((long long)K * N + 255) / 256, 592), 256, 0, st>>>(
+      g_red_scratch, (int)grid, (long long)K * N + N, dW, (long long)K * N, g_red_scratch + (size_t)grid * (K * N + N));
+  return cudaGetLastError();
 }
 
 void gemm_gen_tile(int N, int* bm, int* bn) {
@@ -185,13 +293,21 @@ static void gg_launch(const GemmGen& g, int splits, cudaStream_t st) {
 cudaError_t launch_gemm_gen(const GemmGen& g, cudaStream_t st) {
   if (g.M == 0 || g.N == 0 || g.K == 0) return cudaSuccess;
   int splits = g.split_k < 1 ? 1 : g.split_k;
-  if (splits > 1 && (g.bias || g.relu || !g.accumulate)) return cudaErrorInvalidValue;
+  if (splits > 1 && (g.bias || g.relu || !g.accumulate || g.cmap.rpb != 0x7fffffff || g.ldc != g.N)) return cudaErrorInvalidValue;
+  GemmGen gg = g;
+  if (splits > 1) {
+    splits = (int)std::min<size_t>(splits, g_red_floats / ((size_t)g.M * g.N));
+    if (splits < 1) return cudaErrorInvalidValue;
+    gg.partial = g_red_scratch;
+  }
   int bm, bn;
   gemm_gen_tile(g.N, &bm, &bn);
-  if (bn == 128) gg_launch<128, 128>(g, splits, st);
-  else if (bn == 64) gg_launch<128, 64>(g, splits, st);
-  else gg_launch<256, 32>(g, splits, st);
-  return cudaGetLastError();
+  if (bn == 128) gg_launch<128, 128>(gg, splits, st);
+  else if (bn == 64) gg_launch<128, 64>(gg, splits, st);
+  else gg_launch<256, 32>(gg, splits, st);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess || splits == 1) return e;
+  return reduce_partials(splits, (long long)g.M * g.N, g.C, (long long)g.M * g.N, nullptr, st);
 }
 
 // out[n] += sum_r Y[r*ld + n]   (bias gradients)
@@ -208,14 +324,15 @@ __global__ void k_colsum(const float* __restrict__ Y, int M, int N, long long ld
   __syncthreads();
   if (rl == 0 && n < N) {
     for (int i = 1; i < nr; ++i) s += sm[i][threadIdx.x & 31];
-    atomicAdd(out + n, s);
+    out[(long long)blockIdx.y * N + n] = s;          // partial slab of this row range
   }
 }
 cudaError_t launch_colsum(const float* Y, int M, int N, long long ld, float* out, cudaStream_t st) {
   if (M == 0 || N == 0) return cudaSuccess;
-  dim3 grid((N + 31) / 32, std::max(1, std::min(256, M / 64)));
-  k_colsum<<<grid, 256, 0, st>>>(Y, M, N, ld, out);
-  return cudaGetLastError();
+  dim3 grid((N + 31) / 32, std::max(1, std::min(128, M / 256)));
+  if ((size_t)grid.y * N > g_red_floats) return cudaErrorInvalidValue;
+  k_colsum<<<grid, 256, 0, st>>>(Y, M, N, ld, g_red_scratch);
+  return reduce_partials(grid.y, N, out, N, nullptr, st);
 }
 
 // out[(r % period)*d + c] += X[r*d + c]  (positional-encoding gradients: sum over the batch);
@@ -234,16 +351,19 @@ __global__ void k_period_sum(const float* __restrict__ X, long long rows, int pe
     if (rowmask && ((rowmask[r] != 0) != (want != 0))) continue;
     s += X[r * d + c];
   }
-  atomicAdd(out + (long long)p * d + c, s);
+  out[((long long)blockIdx.z * gridDim.y + p) * d + c] = s;      // partial slab of this batch range
 }
 cudaError_t launch_period_sum(const float* X, long long rows, int period, int d, const uint8_t* rowmask, int want,
                               float* out, cudaStream_t st) {
   if (rows == 0) return cudaSuccess;
   const int bx = d >= 128 ? 128 : 32;
   const long long nb = rows / period;
-  dim3 grid((d + bx - 1) / bx, period, (unsigned)std::max<long long>(1, std::min<long long>(64, nb / 32)));
-  k_period_sum<<<grid, bx, 0, st>>>(X, rows, period, d, rowmask, want, out);
-  return cudaGetLastError();
+  long long nz = std::max<long long>(1, std::min<long long>(64, nb / 32));
+  nz = std::max<long long>(1, std::min<long long>(nz, (long long)(g_red_floats / ((size_t)period * d))));
+  dim3 grid((d + bx - 1) / bx, period, (unsigned)nz);
+  if ((size_t)period * d > g_red_floats) return cudaErrorInvalidValue;
+  k_period_sum<<<grid, bx, 0, st>>>(X, rows, period, d, rowmask, want, g_red_scratch);
+  return reduce_partials((int)nz, (long long)period * d, out, (long long)period * d, nullptr, st);
 }
 
 // =================================================================================================
@@ -276,51 +396,85 @@ cudaError_t launch_ln_fwd_gen(const float* x, long long rows, int d, const float
   return cudaGetLastError();
 }
 
-__global__ void k_ln_bwd_gen(const float* __restrict__ x, const float* __restrict__ dy, long long rows, int d,
+// One warp per row; lane l owns columns l, l + 32, ... (at most LN_CPL of them): its share of dgamma / dbeta stays in
+// registers over all rows of the warp, warps of a CTA are then summed through shared memory in warp order and the CTA
+// writes one partial slab [2 d] (no atomics; launch_ln_bwd_gen reduces the slabs in order).
+template <int LN_CPL>          // columns per lane: d <= 32 * LN_CPL
+__global__ void __launch_bounds__(256) k_ln_bwd_gen(const float* __restrict__ x, const float* __restrict__ dy, long long rows, int d,
                              const float* __restrict__ gamma, float eps, float* __restrict__ dx, int accumulate,
-                             float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  extern __shared__ float sm[];            // [2][d] per-block partial dgamma / dbeta
-  float* sg = sm;
-  float* sb = sm + d;
-  for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) sm[c] = 0.f;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-  for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * wpb) {
+                             float* __restrict__ partial) {
+  extern __shared__ float sm[];            // [warps][2 d]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  float pg[LN_CPL], pb[LN_CPL], gm[LN_CPL];
+#pragma unroll
+  for (int i = 0; i < LN_CPL; ++i) {
+    pg[i] = 0.f; pb[i] = 0.f;
+    gm[i] = (lane + 32 * i) < d ? gamma[lane + 32 * i] : 0.f;
+  }
+  for (long long row = (long long)blockIdx.x * wpb + warp; row < rows; row += (long long)gridDim.x * wpb) {
     const float* xr = x + row * d;
     const float* dyr = dy + row * d;
+    float xv[LN_CPL], gv[LN_CPL];
     float s = 0.f;
-    for (int c = lane; c < d; c += 32) s += xr[c];
+#pragma unroll
+    for (int i = 0; i < LN_CPL; ++i) {
+      const int c = lane + 32 * i;
+      xv[i] = c < d ? xr[c] : 0.f;
+      gv[i] = c < d ? dyr[c] : 0.f;
+      s += xv[i];
+    }
     const float mean = warp_sum_t(s) / d;
     float q = 0.f;
-    for (int c = lane; c < d; c += 32) { const float t = xr[c] - mean; q += t * t; }
+#pragma unroll
+    for (int i = 0; i < LN_CPL; ++i) { const float t = (lane + 32 * i) < d ? xv[i] - mean : 0.f; q += t * t; }
     const float rstd = rsqrtf(warp_sum_t(q) / d + eps);
     float m1 = 0.f, m2 = 0.f;
-    for (int c = lane; c < d; c += 32) {
-      const float xh = (xr[c] - mean) * rstd, g = dyr[c] * gamma[c];
-      m1 += g; m2 += g * xh;
+#pragma unroll
+    for (int i = 0; i < LN_CPL; ++i) {
+      const float xh = (xv[i] - mean) * rstd, g = gv[i] * gm[i];
+      xv[i] = (lane + 32 * i) < d ? xh : 0.f;
+      m1 += g; m2 += g * xv[i];
     }
     m1 = warp_sum_t(m1) / d; m2 = warp_sum_t(m2) / d;
     float* dxr = dx + row * d;
-    for (int c = lane; c < d; c += 32) {
-      const float xh = (xr[c] - mean) * rstd, g = dyr[c] * gamma[c];
-      const float v = rstd * (g - m1 - xh * m2);
-      dxr[c] = accumulate ? dxr[c] + v : v;
-      atomicAdd(sg + c, dyr[c] * xh);
-      atomicAdd(sb + c, dyr[c]);
+#pragma unroll
+    for (int i = 0; i < LN_CPL; ++i) {
+      const int c = lane + 32 * i;
+      if (c < d) {
+        const float v = rstd * (gv[i] * gm[i] - m1 - xv[i] * m2);
+        dxr[c] = accumulate ? dxr[c] + v : v;
+        pg[i] = fmaf(gv[i], xv[i], pg[i]);
+        pb[i] += gv[i];
+      }
     }
   }
+#pragma unroll
+  for (int i = 0; i < LN_CPL; ++i) {
+    const int c = lane + 32 * i;
+    if (c < d) { sm[warp * 2 * d + c] = pg[i]; sm[warp * 2 * d + d + c] = pb[i]; }
+  }
   __syncthreads();
-  for (int c = threadIdx.x; c < d; c += blockDim.x) {
-    atomicAdd(dgamma + c, sg[c]);
-    atomicAdd(dbeta + c, sb[c]);
+  for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) {
+    float t = 0.f;
+    for (int w = 0; w < wpb; ++w) t += sm[w * 2 * d + c];
+    partial[(long long)blockIdx.x * 2 * d + c] = t;
   }
 }
 cudaError_t launch_ln_bwd_gen(const float* x, const float* dy, long long rows, int d, const float* gamma, float eps,
                               float* dx, int accumulate, float* dgamma, float* dbeta, cudaStream_t st) {
   if (rows == 0) return cudaSuccess;
-  const unsigned grid = (unsigned)std::min<long long>((rows + 7) / 8, 148 * 8);
-  k_ln_bwd_gen<<<grid, 256, 2 * d * sizeof(float), st>>>(x, dy, rows, d, gamma, eps, dx, accumulate, dgamma, dbeta);
-  return cudaGetLastError();
+  if (d > 512) return cudaErrorInvalidValue;
+  unsigned grid = (unsigned)std::min<long long>((rows + 7) / 8, 148 * 4);
+  grid = (unsigned)std::min<size_t>(grid, g_red_floats / (2 * (size_t)d));
+  if (grid == 0) return cudaErrorInvalidValue;
+  const size_t smem = 8 * 2 * d * sizeof(float);
+  if (d <= 32) k_ln_bwd_gen<1><<<grid, 256, smem, st>>>(x, dy, rows, d, gamma, eps, dx, accumulate, g_red_scratch);
+  else if (d <= 64) k_ln_bwd_gen<2><<<grid, 256, smem, st>>>(x, dy, rows, d, gamma, eps, dx, accumulate, g_red_scratch);
+  else if (d <= 384) k_ln_bwd_gen<12><<<grid, 256, smem, st>>>(x, dy, rows, d, gamma, eps, dx, accumulate, g_red_scratch);
+  else k_ln_bwd_gen<16><<<grid, 256, smem, st>>>(x, dy, rows, d, gamma, eps, dx, accumulate, g_red_scratch);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  return reduce_partials((int)grid, 2LL * d, dgamma, d, dbeta, st);
 }
 
 // =================================================================================================
@@ -625,15 +779,23 @@ __global__ void k_embed_wgrad(const float* __restrict__ x2d, const uint8_t* __re
     s0 = fmaf(x2d[2 * r], g, s0);
     s1 = fmaf(x2d[2 * r + 1], g, s1);
   }
-  atomicAdd(dW + c, s0);
-  atomicAdd(dW + d + c, s1);
+  __shared__ float red[2][256];
+  red[0][threadIdx.x] = s0; red[1][threadIdx.x] = s1;
+  __syncthreads();
+  if (sub == 0) {
+    for (int i = 1; i < nsub; ++i) { s0 += red[0][i * d + c]; s1 += red[1][i * d + c]; }
+    dW[(long long)blockIdx.x * 2 * d + c] = s0;                 // partial slab of this row range
+    dW[(long long)blockIdx.x * 2 * d + d + c] = s1;
+  }
 }
 cudaError_t launch_embed_wgrad(const float* x2d, const uint8_t* mask, int J, const float* de, long long rows, int d,
                                float* dW, cudaStream_t st) {
   if (rows == 0) return cudaSuccess;
   if (256 % d) return cudaErrorInvalidValue;
-  k_embed_wgrad<<<(unsigned)std::min<long long>(148 * 4, (rows + 255) / 256), 256, 0, st>>>(x2d, mask, J, de, rows, d, dW);
-  return cudaGetLastError();
+  const unsigned grid = (unsigned)std::min<long long>(148 * 4, (rows + 255) / 256);
+  if ((size_t)grid * 2 * d > g_red_floats) return cudaErrorInvalidValue;
+  k_embed_wgrad<<<grid, 256, 0, st>>>(x2d, mask, J, de, rows, d, g_red_scratch);
+  return reduce_partials((int)grid, 2LL * d, dW, 2LL * d, nullptr, st);
 }
 
 // Token fill (net:350-352), dense form used in training:

@@ -48,6 +48,7 @@ struct TrainState {
   float* tok_keep = nullptr;                    // [R] 0 / 1 factors drawn for the current step
   int math = 0;
   float* wg_scratch = nullptr;                  // split-K partial tiles of the tensor-core wgrad (wgrad_tc.cu)
+  float* red_scratch = nullptr;                 // partial slabs of the deterministic two-pass reductions (train_kernels.cu)
   std::unordered_map<const float*, float*> wt;   // W (K, N) -> W^T (N, K) copies for the forward GEMMs
   std::unordered_set<const float*> wt_valid;     // refreshed once per forward/backward call
 };
@@ -159,6 +160,11 @@ static int lin_bwd(Ctx& c, const float* X, long long ldx, const float* dY, long 
     g.accumulate = accumulate_dx;
     if (dxmap) g.cmap = *dxmap;
     UU_TL(launch_gemm_gen(g, c.st));
+  }
+  if (wgrad_skinny_ok(X, ldx, dY, ldy, M, K, N) && db) {
+    // narrow layers of the spatial blocks: one streaming pass gives dW and db (train_kernels.cu)
+    UU_TL(launch_wgrad_skinny(X, ldx, dY, ldy, M, K, N, dW, db, c.st));
+    return 0;
   }
   if (c.t->math == 1 && wgrad_tc_ok(X, ldx, dY, ldy, M, K, N)) {
     // dW += X^T dY on tcgen05 kind::tf32, both operands read MN-major straight from the tape (wgrad_tc.cu)
@@ -320,6 +326,7 @@ static int ensure_train(uu_model* m, int B) {
   if (falloc(t, &t->partials, loss_blocks(B, (int)N, (int)J, true) + 8) || falloc(t, &t->loss, 4)) return 1;
   if (falloc(t, &t->tok_keep, R)) return 1;
   if (falloc(t, &t->wg_scratch, wgrad_tc_scratch_bytes() / sizeof(float))) return 1;
+  if (falloc(t, &t->red_scratch, train_reduce_scratch_floats() + 4096)) return 1;
   t->B = B;
   return 0;
 }
@@ -343,6 +350,7 @@ static int train_fb(uu_model* m, const float* x2d, const uint8_t* mask, const fl
   UU_CUDA(cudaSetDevice(m->device));
   if (ensure_train(m, B)) return 1;
   TrainState* t = m->train;
+  train_reduce_scratch(t->red_scratch, train_reduce_scratch_floats());
   Ctx c{m, t, stream};
   const int N = s.n_tok, J = s.n_joints, ds = s.d_spatial, d = s.d_temporal, h = s.h_temporal, H = s.num_heads;
   const long long R = (long long)B * N, Rs = R * J;
@@ -403,7 +411,14 @@ static int train_fb(uu_model* m, const float* x2d, const uint8_t* mask, const fl
     UU_TL(launch_ln_fwd_gen(tp.x1, Rl, d, W(m, g, 10), W(m, g, 11), 1e-5f, tp.y2, stream));
     RowMap cm;
     cm.rpb = L; cm.batch_rows = Lo * st_i; cm.offset = pl; cm.step = 1;
-    {   // Conv1D k=1 + ReLU straight into the zero-padded layout (pad rows stay zero)
+    if (tf32_ok(c, tp.y2, d, W(m, g, 12), d, (int)Rl, h, d, t->hp[i], h)) {
+      // Conv1D k=1 + ReLU straight into the zero-padded layout (pad rows stay zero), tcgen05 kind::tf32
+      const float* Wt;
+      if (weight_transposed(c, W(m, g, 12), d, h, &Wt)) return 1;
+      Epilogue e;
+      e.bias = W(m, g, 13); e.flags = EPI_RELU; e.cmap = cm;
+      if (tf32_gemm(c, tp.y2, d, (int)Rl, d, Wt, d, h, e, t->hp[i], h)) return 1;
+    } else {
       GemmGen gg;
       gg.A = tp.y2; gg.lda = d; gg.B = W(m, g, 12); gg.ldb = h; gg.C = t->hp[i]; gg.ldc = h; gg.cmap = cm;
       gg.M = (int)Rl; gg.N = h; gg.K = d; gg.bias = W(m, g, 13); gg.relu = 1;
