@@ -26,18 +26,28 @@ static size_t g_red_floats = 0;
 void train_reduce_scratch(float* p, size_t n_floats) { g_red_scratch = p; g_red_floats = n_floats; }
 size_t train_reduce_scratch_floats() { return (size_t)6 << 20; }
 
-// out[i] += sum_p part[p * n + i]; elements i >= n0 go to out1[i - n0] (two destination tensors, e.g. gamma | beta)
-__global__ void k_reduce_partials(const float* __restrict__ part, int nparts, long long n, float* __restrict__ out0,
-                                  long long n0, float* __restrict__ out1) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    float s = 0.f;
-    for (int p = 0; p < nparts; ++p) s += part[(long long)p * n + i];
+// out[i] += sum_p part[p * n + i]; elements i >= n0 go to out1[i - n0] (two destination tensors, e.g. gamma | beta).
+// A CTA owns 32 elements; 8 thread rows each sum every 8th slab in slab order, then the 8 sums are added in row order:
+// the association is fixed by (nparts), never by timing.
+__global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict__ part, int nparts, long long n,
+                                                         float* __restrict__ out0, long long n0, float* __restrict__ out1) {
+  __shared__ float sm[8][32];
+  const int e = threadIdx.x & 31, pl = threadIdx.x >> 5;
+  const long long i = (long long)blockIdx.x * 32 + e;
+  float s = 0.f;
+  if (i < n)
+    for (int p = pl; p < nparts; p += 8) s += part[(long long)p * n + i];
+  sm[pl][e] = s;
+  __syncthreads();
+  if (pl == 0 && i < n) {
+#pragma unroll
+    for (int q = 1; q < 8; ++q) s += sm[q][e];
     float* dst = i < n0 ? out0 + i : out1 + (i - n0);
     *dst += s;
   }
 }
 static cudaError_t reduce_partials(int nparts, long long n, float* out0, long long n0, float* out1, cudaStream_t st) {
-  k_reduce_partials<<<(unsigned)std::min<long long>((n + 255) / 256, 592), 256, 0, st>>>(g_red_scratch, nparts, n, out0, n0, out1);
+  k_reduce_partials<<<(unsigned)((n + 31) / 32), 256, 0, st>>>(g_red_scratch, nparts, n, out0, n0, out1);
   return cudaGetLastError();
 }
 
@@ -195,18 +205,22 @@ __global__ void __launch_bounds__(256, 2) k_gemm_gen(GemmGen g) {
 template <int KD, int ND>
 __global__ void __launch_bounds__(256) k_wgrad_skinny(const float* __restrict__ X, long long ldx, const float* __restrict__ dY,
                                                       long long ldy, long long rows, float* __restrict__ partial) {
-  constexpr int TR = 64, KPT = KD / 32, NPT = ND / 8;
+  // Every warp takes every 8th row of a 64-row tile and accumulates the WHOLE KD x ND product of its rows: lane
+  // (lk, ln) = (lane / 8, lane % 8) owns the KD/4 x ND/8 block at (lk * KD/4, ln * ND/8), so a row costs two or three
+  // float4 shared-memory reads per operand for KD/4 * ND/8 FMAs.  The 8 warps are summed in warp order at the end.
+  constexpr int TR = 64, KPL = KD / 4, NPL = ND / 8;
   __shared__ __align__(16) float Xs[TR][KD];
   __shared__ __align__(16) float Ys[TR][ND];
-  const int tid = threadIdx.x, k0 = tid >> 3, n0 = (tid & 7) * NPT;
+  __shared__ __align__(16) float Rs[KD * ND + ND];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, lk = lane >> 3, ln = lane & 7;
   const long long per = ((rows + gridDim.x - 1) / gridDim.x + TR - 1) / TR * TR;
   const long long r0 = blockIdx.x * per, r1 = min(rows, r0 + per);
-  float acc[KPT][NPT], bs[NPT];
+  float acc[KPL][NPL], bs[NPL];
 #pragma unroll
-  for (int j = 0; j < NPT; ++j) {
+  for (int j = 0; j < NPL; ++j) {
     bs[j] = 0.f;
 #pragma unroll
-    for (int i = 0; i < KPT; ++i) acc[i][j] = 0.f;
+    for (int i = 0; i < KPL; ++i) acc[i][j] = 0.f;
   }
   for (long long t0 = r0; t0 < r1; t0 += TR) {
     for (int i = tid; i < TR * KD / 4; i += 256) {
@@ -220,39 +234,52 @@ __global__ void __launch_bounds__(256) k_wgrad_skinny(const float* __restrict__ 
                                                              : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
-#pragma unroll 8
-    for (int r = 0; r < TR; ++r) {
-      float y[NPT];
+#pragma unroll 2
+    for (int r = warp; r < TR; r += 8) {
+      float xv[KPL], y[NPL];
 #pragma unroll
-      for (int j = 0; j < NPT; j += 4) {
-        const float4 q = *reinterpret_cast<const float4*>(&Ys[r][n0 + j]);
+      for (int i = 0; i < KPL; i += 4) {
+        const float4 q = *reinterpret_cast<const float4*>(&Xs[r][lk * KPL + i]);
+        xv[i] = q.x; xv[i + 1] = q.y; xv[i + 2] = q.z; xv[i + 3] = q.w;
+      }
+#pragma unroll
+      for (int j = 0; j < NPL; j += 4) {
+        const float4 q = *reinterpret_cast<const float4*>(&Ys[r][ln * NPL + j]);
         y[j] = q.x; y[j + 1] = q.y; y[j + 2] = q.z; y[j + 3] = q.w;
       }
 #pragma unroll
-      for (int i = 0; i < KPT; ++i) {
-        const float xv = Xs[r][k0 + 32 * i];
+      for (int i = 0; i < KPL; ++i)
 #pragma unroll
-        for (int j = 0; j < NPT; ++j) acc[i][j] = fmaf(xv, y[j], acc[i][j]);
-      }
-      if (k0 == 0) {
+        for (int j = 0; j < NPL; ++j) acc[i][j] = fmaf(xv[i], y[j], acc[i][j]);
 #pragma unroll
-        for (int j = 0; j < NPT; ++j) bs[j] += y[j];
+      for (int j = 0; j < NPL; ++j) bs[j] += y[j];
+    }
+    __syncthreads();
+  }
+  for (int w = 0; w < 8; ++w) {            // warps add their blocks in warp order
+    if (warp == w) {
+#pragma unroll
+      for (int i = 0; i < KPL; ++i)
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) {
+          float* p = &Rs[(lk * KPL + i) * ND + ln * NPL + j];
+          *p = w == 0 ? acc[i][j] : *p + acc[i][j];
+        }
+      if (lk == 0) {
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) {
+          float* p = &Rs[KD * ND + ln * NPL + j];
+          *p = w == 0 ? bs[j] : *p + bs[j];
+        }
       }
     }
     __syncthreads();
   }
   float* out = partial + (long long)blockIdx.x * (KD * ND + ND);
-#pragma unroll
-  for (int i = 0; i < KPT; ++i)
-#pragma unroll
-    for (int j = 0; j < NPT; ++j) out[(k0 + 32 * i) * ND + n0 + j] = acc[i][j];
-  if (k0 == 0) {
-#pragma unroll
-    for (int j = 0; j < NPT; ++j) out[KD * ND + n0 + j] = bs[j];
-  }
+  for (int i = tid; i < KD * ND + ND; i += 256) out[i] = Rs[i];
 }
 bool wgrad_skinny_ok(const float* X, long long ldx, const float* dY, long long ldy, long long rows, int K, int N) {
-  return rows >= 4096 && (K == 32 || K == 64) && (N == 32 || N == 64 || N == 96) && ldx % 4 == 0 && ldy % 4 == 0 &&
+  return rows >= 4096 && ((K == 32 && (N == 32 || N == 64 || N == 96)) || (K == 64 && N == 32)) && ldx % 4 == 0 && ldy % 4 == 0 &&
          ((uintptr_t)X & 15) == 0 && ((uintptr_t)dY & 15) == 0;
 }
 // dW [K, N] += X^T dY, db [N] += colsum(dY) (db may be null)
@@ -261,13 +288,13 @@ cudaError_t launch_wgrad_skinny(const float* X, long long ldx, const float* dY, 
   const unsigned grid = (unsigned)std::min<long long>(148 * 4, (rows + 255) / 256);
   if ((size_t)grid * (K * N + N) > g_red_floats) return cudaErrorInvalidValue;
 #define UU_WS(KD, ND) if (K == KD && N == ND) k_wgrad_skinny<KD, ND><<<grid, 256, 0, st>>>(X, ldx, dY, ldy, rows, g_red_scratch); else
-  UU_WS(32, 32) UU_WS(32, 64) UU_WS(32, 96) UU_WS(64, 32) UU_WS(64, 64) UU_WS(64, 96) return cudaErrorInvalidValue;
+  UU_WS(32, 32) UU_WS(32, 64) UU_WS(32, 96) UU_WS(64, 32) return cudaErrorInvalidValue;
 #undef UU_WS
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (db) return reduce_partials((int)grid, (long long)K * N + N, dW, (long long)K * N, db, st);
   // without a bias gradient the slab still carries the N column sums: reduce the K * N part only (strided slabs)
-  k_reduce_partials<<<(unsigned)std::min<long long>(((long long)K * N + 255) / 256, 592), 256, 0, st>>>(
+  k_reduce_partials<<<(unsigned)(((long long)K * N + N + 31) / 32), 256, 0, st>>>(
       g_red_scratch, (int)grid, (long long)K * N + N, dW, (long long)K * N, g_red_scratch + (size_t)grid * (K * N + N));
   return cudaGetLastError();
 }
@@ -460,6 +487,56 @@ __global__ void __launch_bounds__(256) k_ln_bwd_gen(const float* __restrict__ x,
     partial[(long long)blockIdx.x * 2 * d + c] = t;
   }
 }
+// d == 32 (spatial blocks): a row is 8 lanes x float4, a warp handles 4 rows at a time and two such groups per loop
+// iteration, so that enough loads are in flight (one warp per 128-byte row was latency-bound at 1.2 TB/s).
+__global__ void __launch_bounds__(256) k_ln_bwd_d32(const float* __restrict__ x, const float* __restrict__ dy, long long rows,
+                                                    const float* __restrict__ gamma, float eps, float* __restrict__ dx,
+                                                    int accumulate, float* __restrict__ partial) {
+  __shared__ float sm[32][64];             // [warp-quarter = 8 warps x 4 row slots][gamma 32 | beta 32]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane >> 3, c4 = (lane & 7) * 4;
+  const float4 gm = *reinterpret_cast<const float4*>(gamma + c4);
+  float4 pg = make_float4(0.f, 0.f, 0.f, 0.f), pb = pg;
+  const long long stride = (long long)gridDim.x * 64;       // rows per grid pass: 8 warps x 4 rows x 2
+  for (long long wb = (long long)blockIdx.x * 64 + warp * 8; wb < rows; wb += stride) {     // (warp-uniform bound)
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long row = wb + sub + 4 * u;
+      const bool ok = row < rows;
+      const float4 xv = ok ? *reinterpret_cast<const float4*>(x + row * 32 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 gv = ok ? *reinterpret_cast<const float4*>(dy + row * 32 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float s = xv.x + xv.y + xv.z + xv.w;
+      s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);
+      const float mean = s * (1.f / 32);
+      const float d0 = xv.x - mean, d1 = xv.y - mean, d2 = xv.z - mean, d3 = xv.w - mean;
+      float q = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+      q += __shfl_xor_sync(0xffffffffu, q, 1); q += __shfl_xor_sync(0xffffffffu, q, 2); q += __shfl_xor_sync(0xffffffffu, q, 4);
+      const float rstd = rsqrtf(q * (1.f / 32) + eps);
+      const float h0 = d0 * rstd, h1 = d1 * rstd, h2 = d2 * rstd, h3 = d3 * rstd;
+      const float g0 = gv.x * gm.x, g1 = gv.y * gm.y, g2 = gv.z * gm.z, g3 = gv.w * gm.w;
+      float m1 = g0 + g1 + g2 + g3, m2 = g0 * h0 + g1 * h1 + g2 * h2 + g3 * h3;
+      m1 += __shfl_xor_sync(0xffffffffu, m1, 1); m1 += __shfl_xor_sync(0xffffffffu, m1, 2); m1 += __shfl_xor_sync(0xffffffffu, m1, 4);
+      m2 += __shfl_xor_sync(0xffffffffu, m2, 1); m2 += __shfl_xor_sync(0xffffffffu, m2, 2); m2 += __shfl_xor_sync(0xffffffffu, m2, 4);
+      m1 *= (1.f / 32); m2 *= (1.f / 32);
+      if (ok) {
+        float4 v = make_float4(rstd * (g0 - m1 - h0 * m2), rstd * (g1 - m1 - h1 * m2), rstd * (g2 - m1 - h2 * m2),
+                               rstd * (g3 - m1 - h3 * m2));
+        float4* dst = reinterpret_cast<float4*>(dx + row * 32 + c4);
+        if (accumulate) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+        *dst = v;
+        pg.x = fmaf(gv.x, h0, pg.x); pg.y = fmaf(gv.y, h1, pg.y); pg.z = fmaf(gv.z, h2, pg.z); pg.w = fmaf(gv.w, h3, pg.w);
+        pb.x += gv.x; pb.y += gv.y; pb.z += gv.z; pb.w += gv.w;
+      }
+    }
+  }
+  *reinterpret_cast<float4*>(&sm[warp * 4 + sub][c4]) = pg;
+  *reinterpret_cast<float4*>(&sm[warp * 4 + sub][32 + c4]) = pb;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float t = 0.f;
+    for (int w = 0; w < 32; ++w) t += sm[w][threadIdx.x];
+    partial[(long long)blockIdx.x * 64 + threadIdx.x] = t;
+  }
+}
 cudaError_t launch_ln_bwd_gen(const float* x, const float* dy, long long rows, int d, const float* gamma, float eps,
                               float* dx, int accumulate, float* dgamma, float* dbeta, cudaStream_t st) {
   if (rows == 0) return cudaSuccess;
@@ -468,7 +545,9 @@ cudaError_t launch_ln_bwd_gen(const float* x, const float* dy, long long rows, i
   grid = (unsigned)std::min<size_t>(grid, g_red_floats / (2 * (size_t)d));
   if (grid == 0) return cudaErrorInvalidValue;
   const size_t smem = 8 * 2 * d * sizeof(float);
-  if (d <= 32) k_ln_bwd_gen<1><<<grid, 256, smem, st>>>(x, dy, rows, d, gamma, eps, dx, accumulate, g_red_scratch);
+  if (d == 32 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)dx & 15) == 0 && ((uintptr_t)gamma & 15) == 0)
+    k_ln_bwd_d32<<<grid, 256, 0, st>>>(x, dy, rows, gamma, eps, dx, accumulate, g_red_scratch);
+  else if (d <= 32) k_ln_bwd_gen<1><<<grid, 256, smem, st>>>(x, dy, rows, d, gamma, eps, dx, accumulate, g_red_scratch);
   else if (d <= 64) k_ln_bwd_gen<2><<<grid, 256, smem, st>>>(x, dy, rows, d, gamma, eps, dx, accumulate, g_red_scratch);
   else if (d <= 384) k_ln_bwd_gen<12><<<grid, 256, smem, st>>>(x, dy, rows, d, gamma, eps, dx, accumulate, g_red_scratch);
   else k_ln_bwd_gen<16><<<grid, 256, smem, st>>>(x, dy, rows, d, gamma, eps, dx, accumulate, g_red_scratch);
