@@ -244,6 +244,10 @@ int uu_op_wgrad_tf32(const float* X, int64_t ldx, const float* dY, int64_t ldy, 
  *   out[rows, N] (bf16) = act( LN(x; gamma, beta, eps) . W + bias ),  x bf16 [rows, d], W fp32 (d, N) on the device */
 int uu_op_ln_gemm_bf16(const void* x, int rows, int d, const float* gamma, const float* beta, float eps, const float* W,
                        const float* bias, int N, int relu, void* out, void* stream);
+/* The fused MLP of a temporal block (vit:190-195): x (bf16 [rows, 384], in place) += fc2(ReLU(fc1(LN(x)))) in one tcgen05
+ * kernel; W1 (384, h) and W2 (h, 384) fp32 on the device, h % 64 == 0.  Synchronous (temporaries). */
+int uu_op_mlp_bf16(void* x, int rows, int d, int h, const float* gamma, const float* beta, float eps, const float* W1,
+                   const float* b1, const float* W2, const float* b2, float* stats_out, void* stream);
 /*   resid != 0: x[rows, d] (bf16, in place) += A . W + bias          A bf16 [rows, K], W fp32 (K, d)
  *   resid == 0: x = A . W + bias + table[row % period]               table fp32 [period, d]
  *   stats_out (optional) [rows, d / 64, 2] fp32 = (sum, sum of squares) of the result per 64-column slot */

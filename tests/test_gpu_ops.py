@@ -268,6 +268,38 @@ def test_layernorm_folded_into_gemm(lib, rows, N, relu):
     assert err.max() < 6e-2 and np.sqrt((err ** 2).mean()) < 1e-2, (err.max(), np.sqrt((err ** 2).mean()))
 
 
+@pytest.mark.parametrize("rows,h", [(256, 768), (300, 768), (71, 768), (36352, 768), (5000, 128), (1000, 512)])
+def test_fused_mlp_tcgen05(lib, rows, h):
+    """mlp_tc.cuh: x += fc2(ReLU(fc1(LN2(x)))) (vit:190-195) as ONE cta_group::2 tcgen05 kernel, hidden chunks handed from
+    the fc1 accumulator to the fc2 operand through shared memory.  Reference: float64 on the same bf16 rows with the fp32
+    weights; the kernel rounds weights and the hidden activation to bf16 (same error budget as the two-GEMM path)."""
+    d = 384
+    rng = np.random.default_rng(rows + h)
+    x = (rng.normal(size=(rows, d)) * rng.uniform(0.5, 3.0, (rows, 1)) + rng.normal(size=(rows, 1)) * 4).astype(np.float32)
+    xb = dev(x, torch.bfloat16)
+    gamma = (1 + 0.3 * rng.normal(size=d)).astype(np.float32)
+    beta = (0.3 * rng.normal(size=d)).astype(np.float32)
+    W1 = (rng.normal(size=(d, h)) / math.sqrt(d)).astype(np.float32)
+    b1 = rng.normal(size=h).astype(np.float32)
+    W2 = (rng.normal(size=(h, d)) / math.sqrt(h)).astype(np.float32)
+    b2 = rng.normal(size=d).astype(np.float32)
+    x64 = xb.float().cpu().numpy().astype(np.float64)
+    mu, var = x64.mean(1, keepdims=True), x64.var(1, keepdims=True)
+    hid = np.maximum(((x64 - mu) / np.sqrt(var + 1e-5) * gamma + beta) @ W1.astype(np.float64) + b1, 0)
+    want = x64 + hid @ W2.astype(np.float64) + b2
+    stats = torch.full((rows, d // 64, 2), float("nan"), dtype=torch.float32, device="cuda")
+    _lib.check(lib.uu_op_mlp_bf16(P(xb), rows, d, h, P(dev(gamma)), P(dev(beta)), 1e-5, P(dev(W1)), P(dev(b1)), P(dev(W2)),
+                                  P(dev(b2)), P(stats), None))
+    got = xb.float().cpu().numpy()
+    assert np.isfinite(got).all()
+    err = np.abs(got - want)
+    print(f"fused mlp rows={rows} h={h}: max err {err.max():.3e} rms {np.sqrt((err ** 2).mean()):.3e}")
+    assert err.max() < 0.12 and np.sqrt((err ** 2).mean()) < 2e-2, (err.max(), np.sqrt((err ** 2).mean()))
+    st = stats.cpu().numpy().astype(np.float64)
+    g64 = got.astype(np.float64).reshape(rows, d // 64, 64)
+    assert np.abs(st[..., 0] - g64.sum(-1)).max() < 1.5 and np.abs(st[..., 1] - (g64 ** 2).sum(-1)).max() < 0.02 * (g64 ** 2).sum(-1).max()
+
+
 @pytest.mark.parametrize("rows,K,resid", [(71, 384, 1), (300, 768, 1), (36352, 384, 1), (2048, 768, 1), (5000, 544, 0), (213, 768, 0)])
 def test_residual_and_table_epilogues(lib, rows, K, resid):
     """EPI_RESID_BF16 (x += A W + b in place) and the positional-table epilogue (x = A W + b + pe[row % period]), both

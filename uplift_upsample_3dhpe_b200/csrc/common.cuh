@@ -192,4 +192,24 @@ void tc_gemm_plan_destroy(TcGemmPlan* p);
 cudaError_t tc_gemm_launch(TcGemmPlan* p, const Epilogue& epi, void* C, int c_bf16, long long ldc,
                            cudaStream_t st);
 
+
+// ---- fused temporal MLP (mlp_tc.cuh, compiled into gemm_tc.cu): x += fc2(ReLU(fc1(LN2(x)))) in one tcgen05 kernel ----
+struct MlpPlan;
+struct MlpArgs {
+  int M;                   // rows of X
+  int n_chunks;            // hidden width / 64
+  const float* ln_stats;   // [M][slots][2] partial sums of the rows of X (EPI_LNFOLD convention)
+  int ln_slots;
+  float ln_inv_k, ln_eps;
+  const float* csum1;      // [h] column sums of bf16(gamma (.) W1)
+  const float* bias1;      // [h] b1 + beta W1
+  Epilogue epi2;           // bias = b2, res_bf16 = X, stats_out, ln_slots, flags = EPI_RESID_BF16
+  bf16* X;
+  long long ldx;
+};
+
+int mlp_plan_create(MlpPlan** out, const bf16* X, long long ldx, int M, int d, int h, const bf16* W1t, const bf16* W2t);
+void mlp_plan_destroy(MlpPlan* p);
+cudaError_t mlp_launch(const MlpPlan* p, const MlpArgs& args, cudaStream_t st);
+
 }  // namespace uu

@@ -993,3 +993,5 @@ cudaError_t tc_gemm_launch(TcGemmPlan* p, const Epilogue& epi_in, void* C, int c
 }
 
 }  // namespace uu
+
+#include "mlp_tc.cuh"

@@ -100,6 +100,7 @@ struct uu_model {
   int plan_B = -1;
   int plan_full = -1;
   std::vector<TcGemmPlan*> plans;
+  std::vector<MlpPlan*> mlp_plans;      // fused temporal MLP call sites (mlp_tc.cuh)
   int launches = 0;
 
   // CUDA-graph cache of the device-pointer forward (uu_forward): key = (batch, buffers, stream); the first call with a

@@ -245,6 +245,8 @@ static void drop_plans(uu_model* m) {
   // at — workspace and weight packs — is only released in ensure_workspace / uu_destroy, which drop the cache)
   for (auto* p : m->plans) tc_gemm_plan_destroy(p);
   m->plans.clear();
+  for (auto* p : m->mlp_plans) mlp_plan_destroy(p);
+  m->mlp_plans.clear();
   m->plan_B = -1;
 }
 
@@ -448,14 +450,33 @@ static int run_forward_bf16(Fwd& f, const float* x2d, const uint8_t* mask, float
     e.res_bf16 = x; e.stats_out = m->ln_stats; e.ln_slots = slots;
     return gemm(f, A, K, rows, K, nullptr, pk, d, e, x, 1, d);
   };
+  static const bool fused_mlp_env = [] { const char* e = getenv("UU_FUSED_MLP"); return !e || e[0] != '0'; }();
+  const bool fused_mlp = fused_mlp_env && d == 384 && h % 128 == 0 && h >= 128 && h <= 768 && R >= 512;
+  size_t mlp_i = 0;
   for (int i = 0; i < s.temporal_depth; ++i) {   // T2 / T3
     const BlockW& w = m->tblocks[i];
     const uint8_t* km = (use_mask && i < s.first_strided_token_attention_layer) ? mask : nullptr;
     if (ln_gemm(X, R, w.p_qkv_ln, 3 * d, w.bl_qkv, w.cs_qkv, false, QKV, nullptr)) return 1;
     UU_LAUNCH(f, UU_KIND_ATTENTION, 1, launch_attention_tc(QKV, B, N, H, dh, km, N, O, st));
     if (resid_gemm(O, d, X, R, w.p_proj, w.bp)) return 1;
-    if (ln_gemm(X, R, w.p_fc1_ln, h, w.bl_fc1, w.cs_fc1, true, Hd, nullptr)) return 1;
-    if (resid_gemm(Hd, h, X, R, w.p_fc2, w.b2)) return 1;
+    if (fused_mlp) {   // fc1 -> ReLU -> fc2 + residual in one kernel: the hidden activation never leaves the SM (mlp_tc.cuh)
+      if (f.building) {
+        MlpPlan* p = nullptr;
+        if (mlp_plan_create(&p, X, d, R, d, h, w.p_fc1_ln.ptr, w.p_fc2.ptr)) return 1;
+        m->mlp_plans.push_back(p);
+      }
+      UU_CHECK(mlp_i < m->mlp_plans.size(), "internal: MLP plan list out of sync");
+      MlpArgs a;
+      a.M = R; a.n_chunks = h / 64; a.ln_stats = m->ln_stats; a.ln_slots = slots; a.ln_inv_k = 1.f / d; a.ln_eps = 1e-5f;
+      a.csum1 = w.cs_fc1; a.bias1 = w.bl_fc1;
+      a.epi2.bias = w.b2; a.epi2.flags = EPI_RESID_BF16; a.epi2.res_bf16 = X; a.epi2.stats_out = m->ln_stats;
+      a.epi2.ln_slots = slots;
+      a.X = X; a.ldx = d;
+      UU_LAUNCH(f, UU_KIND_GEMM_TC, 1, mlp_launch(m->mlp_plans[mlp_i++], a, st));
+    } else {
+      if (ln_gemm(X, R, w.p_fc1_ln, h, w.bl_fc1, w.cs_fc1, true, Hd, nullptr)) return 1;
+      if (resid_gemm(Hd, h, X, R, w.p_fc2, w.b2)) return 1;
+    }
   }
   if (want_full) {   // T4: full-sequence head on the temporal output
     Epilogue e;
@@ -1187,6 +1208,40 @@ int uu_op_ln_gemm_bf16(const void* x, int rows, int d, const float* gamma, const
   tc_gemm_plan_destroy(p);
   UU_CUDA(err);
   UU_CUDA(cudaStreamSynchronize(st));     // temporaries are released on return
+  return 0;
+}
+
+/* x (bf16 [rows, 384], in place) += fc2(ReLU(fc1(LN(x; gamma, beta, eps)))) through the fused MLP kernel (mlp_tc.cuh);
+ * W1 (384, h), W2 (h, 384) fp32 on the device; stats_out (optional) [rows, 6, 2] statistics of the result. */
+int uu_op_mlp_bf16(void* x, int rows, int d, int h, const float* gamma, const float* beta, float eps, const float* W1,
+                   const float* b1, const float* W2, const float* b2, float* stats_out, void* stream) {
+  UU_CHECK(rows > 0 && d == 384 && h % 128 == 0 && h >= 128 && h <= 768, "uu_op_mlp_bf16: d == 384, h % 128 == 0, 128 <= h <= 768 required");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int slots = d / 64;
+  TmpPool tp;
+  void *w1t, *w2t, *cs, *bl, *stats;
+  if (dev_alloc(tp.v, &w1t, sizeof(bf16) * (size_t)h * d, false) || dev_alloc(tp.v, &w2t, sizeof(bf16) * (size_t)h * d, false) ||
+      dev_alloc(tp.v, &cs, sizeof(float) * h, false) || dev_alloc(tp.v, &bl, sizeof(float) * h, false) ||
+      dev_alloc(tp.v, &stats, sizeof(float) * 2 * (size_t)rows * slots, false))
+    return 1;
+  k_pack_wt_ln<<<(h + 7) / 8, 256, 0, st>>>(W1, d, h, h, gamma, beta, b1, (bf16*)w1t, (float*)cs, (float*)bl);
+  k_pack_wt<<<256, 256, 0, st>>>(W2, h, d, d, (bf16*)w2t);
+  UU_CUDA(cudaGetLastError());
+  const RowMap plain;
+  UU_CUDA(launch_residual_ln_bx((const bf16*)x, plain, nullptr, nullptr, rows, d, nullptr, nullptr, 0.f, nullptr, 1, nullptr,
+                                nullptr, st, (float*)stats, slots));
+  MlpPlan* p = nullptr;
+  if (mlp_plan_create(&p, (const bf16*)x, d, rows, d, h, (const bf16*)w1t, (const bf16*)w2t)) return 1;
+  MlpArgs a;
+  a.M = rows; a.n_chunks = h / 64; a.ln_stats = (const float*)stats; a.ln_slots = slots; a.ln_inv_k = 1.f / d; a.ln_eps = eps;
+  a.csum1 = (const float*)cs; a.bias1 = (const float*)bl;
+  a.epi2.bias = b2; a.epi2.flags = EPI_RESID_BF16; a.epi2.res_bf16 = (const bf16*)x; a.epi2.stats_out = stats_out;
+  a.epi2.ln_slots = slots;
+  a.X = (bf16*)x; a.ldx = d;
+  cudaError_t err = mlp_launch(p, a, st);
+  mlp_plan_destroy(p);
+  UU_CUDA(err);
+  UU_CUDA(cudaStreamSynchronize(st));
   return 0;
 }
 
