@@ -217,6 +217,9 @@ int uu_op_layernorm(float* x, int rows, int d, const float* gamma, const float* 
                     int period, void* y, int y_bf16, void* stream);
 int uu_op_attention(const void* qkv, int is_bf16, int B, int S, int heads, int dh, const uint8_t* keep_mask,
                     int mask_stride, void* out, void* stream);
+/* The tcgen05 / TMEM attention kernel of the bf16 schedule (vit:99-130): q | k | v rows bf16 (B * S, 1152) fed by TMA,
+ * scores and probabilities in tensor memory, P . V with P read from tensor memory; 8 heads of dimension 48, S <= 80. */
+int uu_op_attention_tc5(const void* qkv, int B, int S, const uint8_t* keep_mask, int mask_stride, void* out, void* stream);
 /* C = act(A @ W + bias) (+ res); flags: 1 = ReLU, 2 = residual.  fp32 CUDA-core GEMM, W is (K, N). */
 /* K2 alone: the fused spatial transformer (S1-S3 + spatial_norm, net:313-330) of a loaded model on the frames the
  * mask keeps (mask NULL: all B*n_tok frames).  precision fp32 -> out is float, bf16 -> out is bf16; out holds

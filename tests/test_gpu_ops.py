@@ -138,6 +138,38 @@ def test_attention(lib, S, dh, masked):
     assert np.abs(out16.float().cpu().numpy() - want).max() < 6e-2
 
 
+@pytest.mark.parametrize("S,B,masked", [(71, 5, False), (71, 300, True), (41, 7, True), (24, 9, False), (8, 33, False),
+                                        (3, 4, False), (80, 3, True), (1, 5, False), (16, 2, True)])
+def test_attention_tcgen05(lib, S, B, masked):
+    """attn_tc5.cu: q k^T and P v on tcgen05 (scores / probabilities in tensor memory, P read back as the TMEM A operand,
+    V read MN-major from the TMA box), softmax with the reference's literal -1e9 key term (vit:117-123): all-masked
+    windows give uniform attention.  Reference: fp32 numpy on the bf16-rounded inputs."""
+    rng = np.random.default_rng(S + B)
+    H, dh = 8, 48
+    d = H * dh
+    qkv = rng.normal(size=(B, S, 3 * d)).astype(np.float32)
+    q16 = dev(qkv, torch.bfloat16)
+    qr = q16.float().cpu().numpy()
+    keep = np.ones((B, S), dtype=bool)
+    if masked:
+        keep = rng.random((B, S)) < 0.3
+        keep[0] = False
+        keep[1, :] = False; keep[1, S // 2] = True
+    q, k, v = [qr[..., i * d:(i + 1) * d].reshape(B, S, H, dh).transpose(0, 2, 1, 3) for i in range(3)]
+    logits = (q @ k.transpose(0, 1, 3, 2)) / np.float32(math.sqrt(dh))
+    if masked:
+        logits = logits + (1 - keep[:, None, None, :].astype(np.float32)) * np.float32(-1e9)
+    want = (O.softmax(logits) @ v).transpose(0, 2, 1, 3).reshape(B, S, d)
+    out16 = torch.full((B, S, d), float("nan"), dtype=torch.bfloat16, device="cuda")
+    _lib.check(lib.uu_op_attention_tc5(P(q16), B, S, P(dev(keep.astype(np.uint8))) if masked else None, S, P(out16), None))
+    torch.cuda.synchronize()
+    got = out16.float().cpu().numpy()
+    assert np.isfinite(got).all()
+    err = np.abs(got - want).max()
+    print(f"tcgen05 attention S={S} B={B}: max err {err:.3e}")
+    assert err < 6e-2, err
+
+
 @pytest.mark.parametrize("M,N,K,flags", [(300, 384, 384, 0), (129, 51, 384, 0), (1000, 768, 384, 1),
                                          (77, 384, 2304, 2), (64, 1152, 544, 3)])
 def test_gemm_f32(lib, M, N, K, flags):

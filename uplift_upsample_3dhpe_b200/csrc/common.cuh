@@ -156,6 +156,11 @@ cudaError_t launch_gemm_simt(const void* A, int a_bf16, long long lda, const flo
 cudaError_t launch_attention_tc(const bf16* qkv, int B, int S, int heads, int dh, const uint8_t* mask, int mask_stride,
                                 bf16* out, cudaStream_t st);
 
+// ---- tcgen05 / TMEM attention fed by TMA (attn_tc5.cu): 8 heads of dimension 48, S <= 80 tokens per window ----
+bool attention_tc5_ok(int S, int heads, int dh);
+cudaError_t launch_attention_tc5(const bf16* qkv, int B, int S, const uint8_t* mask, int mask_stride, bf16* out, int num_sms,
+                                 cudaStream_t st);
+
 // ---- tensor-core spatial transformer (spatial_tc.cu) -------------------------------------------
 size_t spatial_tc_frag_bytes(int depth);
 size_t spatial_tc_param_bytes(int depth);

@@ -450,6 +450,7 @@ static int run_forward_bf16(Fwd& f, const float* x2d, const uint8_t* mask, float
     e.res_bf16 = x; e.stats_out = m->ln_stats; e.ln_slots = slots;
     return gemm(f, A, K, rows, K, nullptr, pk, d, e, x, 1, d);
   };
+  static const bool attn5 = [] { const char* e = getenv("UU_ATTN5"); return !e || e[0] != '0'; }();
   static const bool fused_mlp_env = [] { const char* e = getenv("UU_FUSED_MLP"); return !e || e[0] != '0'; }();
   const bool fused_mlp = fused_mlp_env && d == 384 && h % 128 == 0 && h >= 128 && h <= 768 && R >= 512;
   size_t mlp_i = 0;
@@ -457,7 +458,10 @@ static int run_forward_bf16(Fwd& f, const float* x2d, const uint8_t* mask, float
     const BlockW& w = m->tblocks[i];
     const uint8_t* km = (use_mask && i < s.first_strided_token_attention_layer) ? mask : nullptr;
     if (ln_gemm(X, R, w.p_qkv_ln, 3 * d, w.bl_qkv, w.cs_qkv, false, QKV, nullptr)) return 1;
-    UU_LAUNCH(f, UU_KIND_ATTENTION, 1, launch_attention_tc(QKV, B, N, H, dh, km, N, O, st));
+    if (attn5 && attention_tc5_ok(N, H, dh))
+      UU_LAUNCH(f, UU_KIND_ATTENTION, 1, launch_attention_tc5(QKV, B, N, km, N, O, m->num_sms, st));
+    else
+      UU_LAUNCH(f, UU_KIND_ATTENTION, 1, launch_attention_tc(QKV, B, N, H, dh, km, N, O, st));
     if (resid_gemm(O, d, X, R, w.p_proj, w.bp)) return 1;
     if (fused_mlp) {   // fc1 -> ReLU -> fc2 + residual in one kernel: the hidden activation never leaves the SM (mlp_tc.cuh)
       if (f.building) {
@@ -493,7 +497,10 @@ static int run_forward_bf16(Fwd& f, const float* x2d, const uint8_t* mask, float
     const int L = m->seq_lens[i], Lo = m->seq_lens[i + 1], st_i = s.strides[i], pl = s.pad_left[i];
     const int Rl = B * L, Ro = B * Lo;
     if (ln_gemm(x_in, Rl, w.p_qkv_ln, 3 * d, w.bl_qkv, w.cs_qkv, false, QKV, nullptr)) return 1;
-    UU_LAUNCH(f, UU_KIND_ATTENTION, 1, launch_attention_tc(QKV, B, L, H, dh, nullptr, L, O, st));
+    if (attn5 && attention_tc5_ok(L, H, dh))
+      UU_LAUNCH(f, UU_KIND_ATTENTION, 1, launch_attention_tc5(QKV, B, L, nullptr, L, O, m->num_sms, st));
+    else
+      UU_LAUNCH(f, UU_KIND_ATTENTION, 1, launch_attention_tc(QKV, B, L, H, dh, nullptr, L, O, st));
     if (resid_gemm(O, d, x_in, Rl, w.p_proj, w.bp)) return 1;
     RowMap cm;   // Conv1D k=1 + ReLU into the zero-padded layout [B, Lo*s, h]
     cm.rpb = L; cm.batch_rows = Lo * st_i; cm.offset = pl; cm.step = 1;
@@ -1110,6 +1117,15 @@ int uu_op_layernorm(float* x, int rows, int d, const float* gamma, const float* 
 int uu_op_attention(const void* qkv, int is_bf16, int B, int S, int heads, int dh, const uint8_t* keep_mask,
                     int mask_stride, void* out, void* stream) {
   UU_CUDA(launch_attention(qkv, is_bf16, B, S, heads, dh, keep_mask, mask_stride, out, (cudaStream_t)stream));
+  return 0;
+}
+/* T3 on tcgen05 / TMEM / TMA (attn_tc5.cu): bf16 q | k | v rows (B * S, 1152) -> bf16 (B * S, 384), 8 heads of 48. */
+int uu_op_attention_tc5(const void* qkv, int B, int S, const uint8_t* keep_mask, int mask_stride, void* out, void* stream) {
+  UU_CHECK(qkv && out && B > 0 && attention_tc5_ok(S, 8, 48), "uu_op_attention_tc5: 1 <= S <= 80 (8 heads of dimension 48)");
+  int dev = 0, sms = 148;
+  UU_CUDA(cudaGetDevice(&dev));
+  UU_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  UU_CUDA(launch_attention_tc5((const bf16*)qkv, B, S, keep_mask, mask_stride, (bf16*)out, sms, (cudaStream_t)stream));
   return 0;
 }
 int uu_op_spatial(uu_model* m, const float* x2d, const uint8_t* mask, int B, void* out, int32_t* n_valid_out,
