@@ -22,12 +22,12 @@ namespace uu {
 constexpr int ML_D = 384, ML_KB = ML_D / 64, ML_NC = 64;
 constexpr int ML_THREADS = 512;          // warp 0 TMA (X, W1), warp 1 fc1 MMA, warps 2..5 chunk epilogue, 6..13 output epilogue,
                                          // warp 14 fc2 MMA, warp 15 TMA (W2)
-constexpr int ML_W1_STAGES = 8, ML_W2_STAGES = 2;
+constexpr int ML_W1_STAGES = 2, ML_W2_STAGES = 3;     // a W1 stage = the chunk's six k-block tiles (one barrier, one wait)
 constexpr int ML_XKB_BYTES = 128 * 128;  // one k-block of this CTA's rows
-constexpr int ML_W1_SLOT = 32 * 128;     // this CTA's 32 of the chunk's 64 weight rows
+constexpr int ML_W1_KB = 32 * 128;       // this CTA's 32 of the chunk's 64 weight rows, one k-block
+constexpr int ML_W1_SLOT = ML_KB * ML_W1_KB;
 constexpr int ML_W2_SLOT = 96 * 128;     // this CTA's 96 of a 192-row half of W2^T
-constexpr int ML_OFF_H = ML_KB * ML_XKB_BYTES;
-constexpr int ML_OFF_W1 = ML_OFF_H + 2 * ML_XKB_BYTES;
+constexpr int ML_OFF_W1 = ML_KB * ML_XKB_BYTES;
 constexpr int ML_OFF_W2 = ML_OFF_W1 + ML_W1_STAGES * ML_W1_SLOT;
 constexpr int ML_OFF_STG = ML_OFF_W2 + ML_W2_STAGES * ML_W2_SLOT;
 constexpr int ML_OFF_PAR = ML_OFF_STG + 8 * 32 * 128;     // fp32 csum1[h] | bias1[h] (h <= ML_MAX_H)
@@ -36,6 +36,25 @@ constexpr int ML_OFF_BAR = ML_OFF_PAR + 2 * ML_MAX_H * 4;
 constexpr int ML_SMEM_BYTES = ML_OFF_BAR + 512 + 1024;
 static_assert(ML_SMEM_BYTES <= 227 * 1024, "fused MLP shared memory budget");
 
+__device__ __forceinline__ void umma_bf16_ts_2sm(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]),
+      "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]),
+      "r"(v[31])
+      : "memory");
+}
 // "buffer drained" arrivals only order tensor-memory reads (tcgen05.fence::before_thread_sync), not memory: relaxed
 // semantics keep the MEMBAR + ERRBAR of a release out of the epilogue loops
 __device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
@@ -87,9 +106,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ML_THREADS, 1)
     for (int i = 0; i < ML_W2_STAGES; ++i) { mbar_init(w2_full + i, 1); mbar_init(w2_empty + i, 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(acc1_full + i, 1);      // multicast commit
-      mbar_init(acc1_empty + i, 8);     // 4 chunk-epilogue warps of each CTA (leader's copy is the one waited on)
-      mbar_init(h_full + i, 8);
-      mbar_init(h_empty + i, 1);        // multicast commit
+      mbar_init(acc1_empty + i, 1);     // multicast commit of fc2: the hidden chunk held in this accumulator has been consumed
+      mbar_init(h_full + i, 8);         // 4 chunk-epilogue warps of each CTA (leader's copy is the one waited on)
+      mbar_init(h_empty + i, 1);        // (unused)
       mbar_init(acc2_full + i, 1);      // multicast commit
       mbar_init(acc2_empty + i, 16);    // 8 output-epilogue warps of each CTA
     }
@@ -128,14 +147,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ML_THREADS, 1)
         }
         if (tile + n_clusters < total_tiles)           // the next row block of this CTA: pull it into L2 meanwhile
           for (int kb = 0; kb < ML_KB; ++kb) tma_prefetch_2d(&map_x, kb * 64, row0 + n_clusters * 256);
-        for (int j = 0; j < n_chunks; ++j)
-          for (int kb = 0; kb < ML_KB; ++kb) {
-            mbar_wait(w1_empty + s1, ph1 ^ 1);
-            if (leader) mbar_expect_tx(w1_full + s1, 2 * ML_W1_SLOT);
-            tma_load_2d_2sm(smem + ML_OFF_W1 + s1 * ML_W1_SLOT, &map_w1, mapa_rank(w1_full + s1, 0), kb * 64,
+        for (int j = 0; j < n_chunks; ++j) {
+          mbar_wait(w1_empty + s1, ph1 ^ 1);
+          if (leader) mbar_expect_tx(w1_full + s1, 2 * ML_W1_SLOT);
+          for (int kb = 0; kb < ML_KB; ++kb)
+            tma_load_2d_2sm(smem + ML_OFF_W1 + s1 * ML_W1_SLOT + kb * ML_W1_KB, &map_w1, mapa_rank(w1_full + s1, 0), kb * 64,
                             j * ML_NC + (int)rank * 32);
-            if (++s1 == ML_W1_STAGES) { s1 = 0; ph1 ^= 1; }
-          }
+          if (++s1 == ML_W1_STAGES) { s1 = 0; ph1 ^= 1; }
+        }
       }
     }
   } else if (warp == 15) {
@@ -171,23 +190,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ML_THREADS, 1)
           const int b = c1 & 1;
           mbar_wait(acc1_empty + b, ((c1 >> 1) & 1) ^ 1);
           tcgen05_fence_after();
-#pragma unroll 1
-          for (int kb = 0; kb < ML_KB; ++kb) {
-            mbar_wait(w1_full + s1, ph1);
-            tcgen05_fence_after();
-            if (elect_one()) {
+          mbar_wait(w1_full + s1, ph1);                  // the chunk's six weight tiles (one barrier)
+          tcgen05_fence_after();
+          if (elect_one()) {
+            const uint64_t bd0 = w1_desc0 + (uint64_t)((s1 * ML_W1_SLOT) >> 4);
+#pragma unroll
+            for (int kb = 0; kb < ML_KB; ++kb) {
               const uint64_t ad = x_desc0 + (uint64_t)((kb * ML_XKB_BYTES) >> 4);
-              const uint64_t bd = w1_desc0 + (uint64_t)((s1 * ML_W1_SLOT) >> 4);
+              const uint64_t bd = bd0 + (uint64_t)((kb * ML_W1_KB) >> 4);
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 umma_bf16_2sm(tmem_base + (uint32_t)(ML_D + b * ML_NC), ad + 2 * k, bd + 2 * k, idesc1, (kb | k) != 0);
-              umma_commit_2sm(w1_empty + s1);
               if (j == n_chunks - 1) umma_commit_2sm(x_empty + kb);      // the row block may be refilled
-              if (kb == ML_KB - 1) umma_commit_2sm(acc1_full + b);
             }
-            __syncwarp();
-            if (++s1 == ML_W1_STAGES) { s1 = 0; ph1 ^= 1; }
+            umma_commit_2sm(w1_empty + s1);
+            umma_commit_2sm(acc1_full + b);
           }
+          __syncwarp();
+          if (++s1 == ML_W1_STAGES) { s1 = 0; ph1 ^= 1; }
         }
       }
     }
@@ -195,7 +215,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ML_THREADS, 1)
     // ---------------- fc2 MMA issuer (leader CTA): acc2 += H_j . W2^T[:, 64 j ..) as two 192-column halves ----------------
     if (leader) {
       constexpr uint32_t idesc2 = make_idesc_bf16(256, 192);
-      const uint64_t h_desc0 = make_sw128_desc(smem_u32(smem + ML_OFF_H));
       const uint64_t w2_desc0 = make_sw128_desc(smem_u32(smem + ML_OFF_W2));
       int s2 = 0;
       uint32_t ph2 = 0, c2 = 0, tcnt = 0;
@@ -213,13 +232,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ML_THREADS, 1)
             mbar_wait(w2_full + s2, ph2);
             tcgen05_fence_after();
             if (elect_one()) {
-              const uint64_t ad = h_desc0 + (uint64_t)((b * ML_XKB_BYTES) >> 4);
+              // A = the hidden chunk in TENSOR MEMORY (bf16 pairs over the fc1 accumulator, 8 columns per 16-wide k-step)
+              const uint32_t ta = tmem_base + (uint32_t)(ML_D + b * ML_NC);
               const uint64_t bd = w2_desc0 + (uint64_t)((s2 * ML_W2_SLOT) >> 4);
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                umma_bf16_2sm(tmem_base + (uint32_t)(hf * 192), ad + 2 * k, bd + 2 * k, idesc2, (j | k) != 0);
+                umma_bf16_ts_2sm(tmem_base + (uint32_t)(hf * 192), ta + 8 * k, bd + 2 * k, idesc2, (j | k) != 0);
               umma_commit_2sm(w2_empty + s2);
-              if (hf == 1) umma_commit_2sm(h_empty + b);
+              if (hf == 1) umma_commit_2sm(acc1_empty + b);       // accumulator / hidden chunk free for fc1 of chunk j + 2
               if (j == n_chunks - 1) umma_commit_2sm(acc2_full + hf);
             }
             __syncwarp();
@@ -254,12 +274,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ML_THREADS, 1)
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ML_D + b * ML_NC);
         tmem_ld_32x32b_x32(taddr, v0);
         tmem_ld_32x32b_x32(taddr + 32, v1);
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster_relaxed(mapa_rank(acc1_empty + b, 0));     // accumulator free for fc1 of chunk j + 2
-        mbar_wait(h_empty + b, use ^ 1);                                        // fc2 of chunk j - 2 has read this buffer
-        uint8_t* hrow = smem + ML_OFF_H + b * ML_XKB_BYTES + (q * 32 + lane) * 128;
         const int cb0 = j * ML_NC;
+        uint32_t hk[32];                     // the thread's 64 hidden values as bf16 pairs
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
           const int cb = cb0 + 8 * g;
@@ -277,17 +293,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ML_THREADS, 1)
           o[2] = ffma2(a1, o[2], ffma2(a2, make_float2(c1.x, c1.y), make_float2(b1.x, b1.y)));
           o[3] = ffma2(a1, o[3], ffma2(a2, make_float2(c1.z, c1.w), make_float2(b1.z, b1.w)));
 #pragma unroll
-          for (int i = 0; i < 4; ++i) o[i] = make_float2(fmaxf(o[i].x, 0.f), fmaxf(o[i].y, 0.f));
-          __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0].x, o[0].y), p1 = __floats2bfloat162_rn(o[1].x, o[1].y);
-          __nv_bfloat162 p2 = __floats2bfloat162_rn(o[2].x, o[2].y), p3 = __floats2bfloat162_rn(o[3].x, o[3].y);
-          uint4 pk;
-          pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
-          pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
-          *reinterpret_cast<uint4*>(hrow + ((g ^ (lane & 7)) << 4)) = pk;
+          for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 pb = __floats2bfloat162_rn(fmaxf(o[i].x, 0.f), fmaxf(o[i].y, 0.f));
+            hk[4 * g + i] = *reinterpret_cast<uint32_t*>(&pb);
+          }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic writes -> tensor-core (async proxy) reads
+        // the hidden chunk goes back into TENSOR MEMORY over the accumulator it came from (columns 0 .. 31 of the 64): fc2
+        // reads it as its A operand from there, so the hidden activation touches neither shared memory nor HBM
+        tmem_st_32x32b_x32(taddr, hk);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_remote_cta_release(mapa_rank(h_full + b, 0));
+        if (lane == 0) mbar_arrive_cluster_relaxed(mapa_rank(h_full + b, 0));
       }
     }
   } else if (warp < 14) {
