@@ -1,7 +1,8 @@
 """Summarise an `ncu --page raw --csv` export of one forward pass: per-kernel table (markdown) and the DRAM
 traffic per launch by kernel kind (JSON, read by bench.py for roofline.traffic).
-usage: python scripts/summarize_ncu_raw.py gpurun_out/prof_raw.csv BATCH profiles/NAME [LAST_N]  (writes NAME.md,
-ncu_traffic.json; LAST_N keeps only the last N launches = the final forward pass of a longer capture)"""
+usage: python scripts/summarize_ncu_raw.py gpurun_out/prof_raw.csv BATCH profiles/NAME [LAST_N] [TRAFFIC_JSON]  (writes
+NAME.md and TRAFFIC_JSON (default ncu_traffic_r2.json) next to it; LAST_N keeps only the last N launches = the final
+forward pass of a longer capture)"""
 import collections
 import csv
 import json
@@ -12,8 +13,9 @@ import sys
 path, batch, out = sys.argv[1], int(sys.argv[2]), sys.argv[3]
 rows = list(csv.reader(l for l in open(path) if not l.startswith("==")))
 hdr, units, data = rows[0], rows[1], rows[2:]
-if len(sys.argv) > 4:
+if len(sys.argv) > 4 and int(sys.argv[4]) > 0:
     data = data[-int(sys.argv[4]):]
+traffic_name = sys.argv[5] if len(sys.argv) > 5 else "ncu_traffic_r2.json"
 col = {h: i for i, h in enumerate(hdr)}
 
 
@@ -32,7 +34,7 @@ def get(r, name, kind=None):
     return scale(r[col[name]], units[col[name]], kind)
 
 
-KIND = [("k_gemm_tc", "gemm_tc"), ("k_spatial_tc", "spatial"), ("k_attention_tc", "attention"),
+KIND = [("k_gemm_tc", "gemm_tc"), ("k_mlp_tc", "gemm_tc"), ("k_spatial_tc", "spatial"), ("k_attention_tc", "attention"),
         ("k_residual_ln", "layernorm"), ("k_layernorm", "layernorm"), ("k_token_fill", "token_fill"),
         ("k_mask", "gather"), ("k_window", "gather")]
 agg = collections.OrderedDict()
@@ -74,5 +76,5 @@ with open(out + ".md", "w") as f:
 json.dump({"source": os.path.basename(path), "batch": batch,
            "kinds": {k: {"launches": int(v["n"]), "us": round(v["us"], 1),
                          "dram_bytes_per_launch": round(v["bytes"] / v["n"])} for k, v in kinds.items()}},
-          open(os.path.join(os.path.dirname(out), "ncu_traffic.json"), "w"), indent=1)
+          open(os.path.join(os.path.dirname(out), traffic_name), "w"), indent=1)
 print(open(out + ".md").read())

@@ -132,3 +132,21 @@ def test_no_mask_stride_drops_token_tensor():
     spec = spec_from_config(UpliftUpsampleConfig.preset("h36m_351", MASK_STRIDE=None))
     assert not spec.has_strided_input and "strided_input_token_layer" not in weights.inventory(spec)
     assert weights.param_count(spec) == 10_404_902 - 384
+
+
+def test_host_side_schedules():
+    """common/utils/schedules.py: staircase ExponentialDecay (every shipped config) and ExponentialDecayWithSteps
+    (:36-99: the small staircase skips the steps where the large one fires)."""
+    torch = pytest.importorskip("torch")  # noqa: F841  (train.py imports lazily, the schedules are pure Python)
+    from uplift_upsample_3dhpe_b200.train import scheduler_by_name
+    s = scheduler_by_name("ExponentialDecay")(initial_learning_rate=4e-5, decay_steps=6000, decay_rate=0.99, staircase=True)
+    assert s(0) == 4e-5 and s(5999) == 4e-5 and abs(s(6000) - 4e-5 * 0.99) < 1e-18 and abs(s(12001) - 4e-5 * 0.99 ** 2) < 1e-18
+    w = scheduler_by_name("ExponentialDecayWithSteps")(initial_learning_rate=1e-3, decay_steps=100, decay_rate=0.9,
+                                                       large_decay_steps=1000, large_decay_rate=0.5)
+    assert w(0) == 1e-3 and w(99) == 1e-3
+    assert abs(w(100) - 1e-3 * 0.9) < 1e-15 and abs(w(950) - 1e-3 * 0.9 ** 9) < 1e-15
+    # step 1000: floor(1000/100) - floor(1000/1000) = 9 small decays and one large one
+    assert abs(w(1000) - 1e-3 * 0.9 ** 9 * 0.5) < 1e-15
+    assert abs(w(2345) - 1e-3 * 0.9 ** (23 - 2) * 0.5 ** 2) < 1e-15
+    with pytest.raises(NotImplementedError):
+        scheduler_by_name("CosineDecayRestarts")

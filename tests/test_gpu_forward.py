@@ -14,8 +14,8 @@ from uplift_upsample_3dhpe_b200.model import test_step as run_test_step
 # Tolerances (absolute, outputs are O(1..10) with the perturbed random-init weights):
 #   fp32 path: <= 1e-4 against the fp64 oracle (north_star's fp32 bound; the fp32 oracle itself sits ~1e-5 away)
 #   bf16 path: bf16/fp16 operands, fp32 accumulation, LayerNorm/softmax/residual adds in fp32 registers, bf16-resident
-#              activations — measured 0.09-0.15 on outputs of magnitude ~10; bound 0.25
-TOL = {"fp32": 1e-4, "bf16": 0.25}
+#              activations — measured 0.09-0.15 on outputs of magnitude ~10 (rms ~3); bound 0.2 = 1.33 x the largest measurement
+TOL = {"fp32": 1e-4, "bf16": 0.2}
 
 
 def _case(name, s_in, B, mode, seed=0):

@@ -1,6 +1,6 @@
 """CUDA path (through the C ABI) against the golden vectors the reference's own code produced
 (tests/golden, scripts/make_golden.py).  fp32 path: <= 1e-4 of the reference's float32 run on every
-window (incl. all-masked ones) and of its float64 run where a valid token exists; bf16 path: <= 0.25
+window (incl. all-masked ones) and of its float64 run where a valid token exists; bf16 path: <= 0.2
 absolute on O(10) outputs (bf16 operands, fp32 accumulation)."""
 import os
 
@@ -25,7 +25,7 @@ def test_cuda_forward_matches_reference_golden(path, precision):
     torch.cuda.synchronize()
     full, central = full.cpu().numpy(), central.cpu().numpy()
     model.close()
-    tol = 1e-4 if precision == "fp32" else 0.25
+    tol = 1e-4 if precision == "fp32" else 0.2
     e32 = max(np.abs(central - z["central_f32"]).max(), np.abs(full - z["full_f32"]).max())
     valid = m.sum(axis=1) > 0
     e64 = max(np.abs(central[valid] - z["central"][valid]).max(), np.abs(full[valid] - z["full"][valid]).max())
@@ -108,7 +108,7 @@ def test_flip_tta_matches_reference_golden(precision):
         model = build_uplift_upsample_transformer(cfg, precision=precision, weights=w)
         full, central = model.forward_tta([torch.from_numpy(z["x"]).cuda(), torch.from_numpy(z["mask"]).cuda()])
         torch.cuda.synchronize()
-        tol = 1e-4 if precision == "fp32" else 0.25
+        tol = 1e-4 if precision == "fp32" else 0.2
         e = max(np.abs(central.cpu().numpy() - z["central"]).max(), np.abs(full.cpu().numpy() - z["full"]).max())
         print(f"tta {os.path.basename(path)} {precision}: max|err| {e:.3e}")
         assert e <= tol

@@ -23,18 +23,29 @@ from .sharding import allreduce_gradients
 
 
 def scheduler_by_name(name: str):
-    """common/utils/schedules.py:17-32.  Only the schedule the shipped configs use is implemented."""
-    if name != "ExponentialDecay":
-        raise NotImplementedError(f"schedule {name!r} (shipped configs use ExponentialDecay)")
-
-    def make(initial_learning_rate, decay_steps, decay_rate, staircase=False):
-        def schedule(step: int) -> float:
-            p = step / decay_steps
-            if staircase:
-                p = math.floor(p)
-            return initial_learning_rate * decay_rate ** p
-        return schedule
-    return make
+    """common/utils/schedules.py:16-32: schedule name -> factory of a host-side callable step -> value.
+    ExponentialDecay (every shipped config) and the repository's own ExponentialDecayWithSteps (:36-99) are implemented;
+    the Keras-only PiecewiseConstantDecay / CosineDecayRestarts are not."""
+    if name == "ExponentialDecay":
+        def make(initial_learning_rate, decay_steps, decay_rate, staircase=False):
+            def schedule(step: int) -> float:
+                p = step / decay_steps
+                if staircase:
+                    p = math.floor(p)
+                return initial_learning_rate * decay_rate ** p
+            return schedule
+        return make
+    if name == "ExponentialDecayWithSteps":
+        # two staircases: every `decay_steps` steps one factor `decay_rate`, except that every `large_decay_steps`-th
+        # step applies `large_decay_rate` instead (schedules.py:84-97: p = floor(t / small) - floor(t / large))
+        def make(initial_learning_rate, decay_steps, decay_rate, large_decay_steps, large_decay_rate, name=None):
+            def schedule(step: int) -> float:
+                large_p = math.floor(step / large_decay_steps)
+                small_p = math.floor(step / decay_steps) - large_p
+                return initial_learning_rate * decay_rate ** small_p * large_decay_rate ** large_p
+            return schedule
+        return make
+    raise NotImplementedError(f"schedule {name!r} (implemented: ExponentialDecay, ExponentialDecayWithSteps)")
 
 
 class _DevView:
