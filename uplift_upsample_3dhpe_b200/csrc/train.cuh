@@ -30,6 +30,8 @@ cudaError_t launch_ln_fwd_gen(const float* x, long long rows, int d, const float
                               float* y, cudaStream_t st);
 cudaError_t launch_ln_bwd_gen(const float* x, const float* dy, long long rows, int d, const float* gamma, float eps,
                               float* dx, int accumulate, float* dgamma, float* dbeta, cudaStream_t st);
+bool attention_small_ok(int S, int heads, int dh, const uint8_t* mask);
+cudaError_t launch_attention_small_fwd(const float* qkv, long long frames, int S, float* out, cudaStream_t st);
 cudaError_t launch_attention_bwd(const float* qkv, const float* dO, long long B, int S, int heads, int dh,
                                  const uint8_t* mask, int mask_stride, float* dqkv, cudaStream_t st);
 cudaError_t launch_act_fwd(const float* pre, long long n, int act, float* out, cudaStream_t st);

@@ -211,7 +211,10 @@ static int attn_half_fwd(Ctx& c, const BlkDims& b, const std::string& g, BlkTape
   UU_TL(launch_ln_fwd_gen(tp.x0, R, d, W(m, g, 0), W(m, g, 1), 1e-5f, tp.y1, c.st));
   for (int k = 0; k < 3; ++k)
     if (lin_fwd(c, tp.y1, d, (int)R, d, W(m, g, 2 + 2 * k), d, W(m, g, 3 + 2 * k), tp.qkv + k * d, 3 * d)) return 1;
-  UU_TL(launch_attention(tp.qkv, 0, (int)b.nb, b.S, b.heads, d / b.heads, keymask, mask_stride, tp.o, c.st));
+  if (attention_small_ok(b.S, b.heads, d / b.heads, keymask))       // spatial blocks: one warp per frame (train_kernels.cu)
+    UU_TL(launch_attention_small_fwd(tp.qkv, b.nb, b.S, tp.o, c.st));
+  else
+    UU_TL(launch_attention(tp.qkv, 0, (int)b.nb, b.S, b.heads, d / b.heads, keymask, mask_stride, tp.o, c.st));
   if (lin_fwd(c, tp.o, d, (int)R, d, W(m, g, 8), d, W(m, g, 9), c.t->tmp1, d)) return 1;
   const RowMap plain;
   UU_TL(launch_residual(tp.x0, plain, c.t->tmp1, tp.keep < 1.f ? tp.scale : nullptr, b.S, nullptr, 1, R, d, tp.x1, c.st));
