@@ -262,13 +262,14 @@ def train_measure(a, rank, world, local_rank, dist, peaks, steps=5, warmup=3):
     return out
 
 
-def quick_infer(cfg_name: str, s_in: int, B: int, local_rank: int, rank: int, steps: int, peaks, dist, world: int):
+def quick_infer(cfg_name: str, s_in: int, B: int, local_rank: int, rank: int, steps: int, peaks, dist, world: int,
+                precision: str = "bf16"):
     """Device-timed forward throughput of one more configuration (BASELINE configs 1, 3, 5): same method as the headline
     (rotating input pool larger than L2, CUDA events, max over ranks), fewer steps."""
     from uplift_upsample_3dhpe_b200.model import build_uplift_upsample_transformer
     cfg = UpliftUpsampleConfig.preset(cfg_name)
     spec = spec_from_config(cfg)
-    model = build_uplift_upsample_transformer(cfg, device=local_rank, precision="bf16")
+    model = build_uplift_upsample_transformer(cfg, device=local_rank, precision=precision)
     x_np, m_np, valid = synth_inputs(spec, cfg, B, s_in, seed=rank)
     pool_n = max(2, int(np.ceil(160e6 / (x_np.nbytes + m_np.nbytes))))
     pool_n = min(pool_n, 12)
@@ -308,12 +309,12 @@ def quick_infer(cfg_name: str, s_in: int, B: int, local_rank: int, rank: int, st
     hb = hbm_kernel_bytes(spec, B, valid)
     hbm = {k: {"ms": round(prof[k][0], 4), "algorithmic_mb": round(hb[k] / 1e6, 2),
                "achieved_gbs": round(hb[k] / (prof[k][0] * 1e-3) / 1e9, 1), "peak_gbs": peaks["hbm"]}
-           for k in hb if k in prof and prof[k][1] > 0 and prof[k][0] > 0}
+           for k in hb if k in prof and prof[k][1] > 0 and prof[k][0] > 0} if precision == "bf16" else None
     model.close()
     del model, xs, full, central
     torch.cuda.empty_cache()
     val = world * B / (ms / 1e3)
-    return {"workload": f"config/{cfg_name}.json forward, s_in={s_in}, {B} windows/GPU/step", "value": val, "unit": UNIT,
+    return {"workload": f"config/{cfg_name}.json forward, s_in={s_in}, {B} windows/GPU/step, {precision} schedule", "value": val, "unit": UNIT,
             "ms_per_step": ms, "steps": steps, "valid_tokens": valid, "n_tok": spec.n_tok,
             "whole_step_frac_of_tensor_peak_burst": round(flops * B / (ms * 1e-3) / 1e12 / peaks["tensor_burst"], 4),
             "whole_step_frac_of_tensor_peak_sustained": round(flops * B / (ms * 1e-3) / 1e12 / peaks["tensor_sustained"], 4),
@@ -351,7 +352,7 @@ def golden_accuracy(local_rank: int):
     ref = np.concatenate([z["full"][valid].ravel(), z["central"][valid].ravel()])
     out["rms_output"] = float(np.sqrt((ref ** 2).mean()))
     out["max_abs_output"] = float(np.abs(ref).max())
-    for prec in ("bf16", "fp32"):
+    for prec in ("bf16", "tf32", "fp32"):
         model = build_uplift_upsample_transformer(cfg, device=local_rank, precision=prec, weights=w)
         full, central = test_step(model, torch.from_numpy(z["x"]).cuda(), torch.from_numpy(z["mask"]).cuda())
         got = np.concatenate([full.cpu().numpy()[valid].ravel(), central.cpu().numpy()[valid].ravel()]).astype(np.float64)
@@ -615,6 +616,9 @@ def main():
         for key, (cn, si, bb) in (("s_in20", ("h36m_351", 20, B)), ("h36m_81", ("h36m_81", 4, B)),
                                   ("b512", (a.config, a.s_in, 512))):
             sub[key] = quick_infer(cn, si, bb, local_rank, rank, 10, peaks, dist, world)
+        # accuracy / throughput curve of the three schedules (same workload, 512 windows per step)
+        for prec in ("tf32", "fp32"):
+            sub["b512_" + prec] = quick_infer(a.config, a.s_in, 512, local_rank, rank, 5, peaks, dist, world, precision=prec)
         if rank == 0:
             accuracy = golden_accuracy(local_rank)
         train = train_measure(a, rank, world, local_rank, dist, peaks)

@@ -62,8 +62,11 @@ typedef struct uu_spec {
 
 /* Arithmetic of the dense contractions. */
 enum { UU_PRECISION_FP32 = 0,    /* CUDA-core fp32 end to end, <= 1e-4 abs of the reference's float32 outputs */
-       UU_PRECISION_BF16 = 1 };  /* bf16 operands on tensor cores (tcgen05 / mma.sync), fp32 accumulation; LayerNorm,
+       UU_PRECISION_BF16 = 1,    /* bf16 operands on tensor cores (tcgen05 / mma.sync), fp32 accumulation; LayerNorm,
                                     softmax and residual adds in fp32 registers, activations stored as bf16 */
+       UU_PRECISION_TF32 = 2 };  /* the fp32 schedule (fp32 activations, LayerNorm, softmax, spatial stage) with the large
+                                    GEMMs on tcgen05 kind::tf32 (TF32 products, fp32 accumulation): the intermediate point
+                                    of the accuracy / throughput curve, what TensorFlow >= 2.4 computes on Ampere+ GPUs */
 
 const char* uu_last_error(void);
 int uu_version(void);

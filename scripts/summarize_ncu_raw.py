@@ -12,6 +12,16 @@ import sys
 
 path, batch, out = sys.argv[1], int(sys.argv[2]), sys.argv[3]
 rows = list(csv.reader(l for l in open(path) if not l.startswith("==")))
+if "Metric Name" in rows[0]:          # long format of `ncu --csv --log-file` (one row per launch and metric) -> wide
+    h0 = rows[0]
+    iid, ik, imn, imu, imv = (h0.index(x) for x in ("ID", "Kernel Name", "Metric Name", "Metric Unit", "Metric Value"))
+    names, unit_of, by_id = [], {}, collections.OrderedDict()
+    for r in rows[1:]:
+        if r[imn] not in unit_of:
+            names.append(r[imn]); unit_of[r[imn]] = r[imu]
+        by_id.setdefault(r[iid], {"Kernel Name": r[ik]})[r[imn]] = r[imv]
+    rows = [["Kernel Name"] + names, [""] + [unit_of[n] for n in names]] + \
+           [[d["Kernel Name"]] + [d.get(n, "") for n in names] for d in by_id.values()]
 hdr, units, data = rows[0], rows[1], rows[2:]
 if len(sys.argv) > 4 and int(sys.argv[4]) > 0:
     data = data[-int(sys.argv[4]):]
@@ -62,9 +72,9 @@ for r in data:
     kk["n"] += 1; kk["us"] += t; kk["bytes"] += rd + wr
 tot = sum(a["us"] for a in agg.values())
 with open(out + ".md", "w") as f:
-    f.write(f"source: {path} ({len(data)} launches = one forward pass, B = {batch} windows; ncu sections SpeedOfLight, "
-            "MemoryWorkloadAnalysis, ComputeWorkloadAnalysis, LaunchStats, Occupancy, WarpStateStats, SchedulerStats; "
-            "--clock-control none; per-launch times are cold-cache and serialised: compare shares)\n\n")
+    f.write(f"source: {path} ({len(data)} launches = one forward pass, B = {batch} windows; ncu --metrics gpu__time_duration, "
+            "sm__pipe_tensor_cycles_active, smsp__issue_active, gpu__dram_throughput, lts__throughput, dram__bytes_read / "
+            "write, registers; --clock-control none; per-launch times are cold-cache and serialised: compare shares)\n\n")
     f.write("| kernel | launches | total us | share | DRAM MB (read+write, or read if split) | DRAM write MB | DRAM GB/s | tensor pipe % | issue % | DRAM % | L2 % | regs |\n")
     f.write("|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|\n")
     for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["us"]):

@@ -15,7 +15,7 @@ from uplift_upsample_3dhpe_b200.model import build_uplift_upsample_transformer  
 from uplift_upsample_3dhpe_b200.model import test_step as run_test_step  # noqa: E402
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
 @pytest.mark.parametrize("path", FORWARD, ids=[os.path.basename(p)[8:-4] for p in FORWARD])
 def test_cuda_forward_matches_reference_golden(path, precision):
     cfg, spec, w, z = load_forward_case(path)
@@ -25,7 +25,8 @@ def test_cuda_forward_matches_reference_golden(path, precision):
     torch.cuda.synchronize()
     full, central = full.cpu().numpy(), central.cpu().numpy()
     model.close()
-    tol = 1e-4 if precision == "fp32" else 0.2
+    # tf32: the fp32 schedule with TF32 products in the large GEMMs (10-bit mantissa operands): measured up to 1.9e-2 (truncation, not rounding, of the operands)
+    tol = {"fp32": 1e-4, "tf32": 3e-2, "bf16": 0.2}[precision]
     e32 = max(np.abs(central - z["central_f32"]).max(), np.abs(full - z["full_f32"]).max())
     valid = m.sum(axis=1) > 0
     e64 = max(np.abs(central[valid] - z["central"][valid]).max(), np.abs(full[valid] - z["full"][valid]).max())

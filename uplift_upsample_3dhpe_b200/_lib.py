@@ -23,7 +23,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "-diag-suppress", "550,177"]
 
 UU_MAX_STRIDED = 8
-PRECISION = {"fp32": 0, "bf16": 1}
+PRECISION = {"fp32": 0, "bf16": 1, "tf32": 2}
 KINDS = ["gather", "spatial", "token_fill", "layernorm", "attention", "gemm_tc", "gemm_f32", "cast"]
 
 

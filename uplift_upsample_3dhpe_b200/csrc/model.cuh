@@ -31,6 +31,7 @@ struct BlockW {        // one temporal / strided block
   // w2: fc2 (h, d) or strided conv (3, h, d) == [3h, d]
   const float *wp = nullptr, *bp = nullptr, *w1 = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr;
   Pack p_qkv, p_proj, p_fc1, p_fc2;
+  float *t_qkv = nullptr, *t_proj = nullptr, *t_fc1 = nullptr, *t_fc2 = nullptr;   // fp32 W^T (N, K): B operand of the tf32 schedule
   // temporal blocks, bf16 schedule: LayerNorm folded into the consuming GEMM (EPI_LNFOLD).
   //   p_*_ln = bf16((gamma (.) W)^T), cs_* = column sums of that bf16 matrix, bl_* = b + beta W
   Pack p_qkv_ln, p_fc1_ln;
@@ -62,6 +63,7 @@ struct uu_model {
   float* sp_params = nullptr;
   int num_sms = 148;
   Pack p_s2t, p_head1, p_head2;
+  float* t_s2t = nullptr;                  // fp32 W^T of spatial_to_temporal_fc (tf32 schedule)
   std::vector<void*> derived_allocs;
 
   // workspace (sized for cap_B windows in the current precision)

@@ -128,6 +128,15 @@ __global__ void k_pack_wt_ln(const float* __restrict__ Wm, int K, int N, int n_p
   }
 }
 
+// Wt[n][k] = W[k][n] in fp32: K-major B operand of the kind::tf32 GEMM
+__global__ void k_pack_wt32(const float* __restrict__ Wm, int K, int N, float* __restrict__ Wt) {
+  long long total = (long long)N * K;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int n = (int)(i / K), k = (int)(i % K);
+    Wt[i] = Wm[(long long)k * N + n];
+  }
+}
+
 int dev_alloc(std::vector<void*>& pool, void** p, size_t bytes, bool zero) {
   UU_CUDA(cudaMalloc(p, bytes ? bytes : 16));
   pool.push_back(*p);
@@ -164,6 +173,17 @@ static int make_pack_ln(uu_model* m, Pack& pk, float*& csum, float*& bias_out, c
   return 0;
 }
 
+static int make_pack32(uu_model* m, float*& dst, const float* Wsrc, int K, int N, cudaStream_t st) {
+  if (!dst) {
+    void* p;
+    if (dev_alloc(m->derived_allocs, &p, sizeof(float) * (size_t)N * K, false)) return 1;
+    dst = (float*)p;
+  }
+  k_pack_wt32<<<256, 256, 0, st>>>(Wsrc, K, N, dst);
+  UU_CUDA(cudaGetLastError());
+  return 0;
+}
+
 static int setup_block(uu_model* m, BlockW& b, const std::string& g, int d, int h, bool strided, cudaStream_t st) {
   b.ln1_g = W(m, g, 0); b.ln1_b = W(m, g, 1);
   b.wp = W(m, g, 8); b.bp = W(m, g, 9);
@@ -186,6 +206,11 @@ static int setup_block(uu_model* m, BlockW& b, const std::string& g, int d, int 
   // (strided blocks: fc1 is the k=1 Conv1D, a (d, h) matrix like the dense fc1)
   if (make_pack_ln(m, b.p_qkv_ln, b.cs_qkv, b.bl_qkv, b.wqkv, d, 3 * d, b.ln1_g, b.ln1_b, b.bqkv, st)) return 1;
   if (make_pack_ln(m, b.p_fc1_ln, b.cs_fc1, b.bl_fc1, b.w1, d, h, b.ln2_g, b.ln2_b, b.b1, st)) return 1;
+  if (m->precision == UU_PRECISION_TF32) {
+    if (make_pack32(m, b.t_qkv, b.wqkv, d, 3 * d, st) || make_pack32(m, b.t_proj, b.wp, d, d, st) ||
+        make_pack32(m, b.t_fc1, b.w1, d, h, st) || make_pack32(m, b.t_fc2, b.w2, strided ? 3 * h : h, d, st))
+      return 1;
+  }
   return 0;
 }
 
@@ -222,6 +247,9 @@ static int commit_weights(uu_model* m, cudaStream_t st) {
   for (int i = 0; i < s.n_strided; ++i)
     if (setup_block(m, m->sblocks[i], "strided_temporal_block_" + std::to_string(i + 1), s.d_temporal, s.h_temporal, true, st)) return 1;
   if (make_pack(m, m->p_s2t, W(m, "spatial_to_temporal_fc", 0), s.n_joints * s.d_spatial, s.d_temporal, st)) return 1;
+  if (m->precision == UU_PRECISION_TF32 &&
+      make_pack32(m, m->t_s2t, W(m, "spatial_to_temporal_fc", 0), s.n_joints * s.d_spatial, s.d_temporal, st))
+    return 1;
   if (s.full_output && make_pack(m, m->p_head1, W(m, "temporal_fc", 0), s.d_temporal, 3 * s.n_joints, st)) return 1;
   if (make_pack(m, m->p_head2, W(m, "strided_temporal_fc", 0), s.d_temporal, 3 * s.n_joints, st)) return 1;
   UU_CUDA(cudaStreamSynchronize(st));
@@ -301,6 +329,7 @@ struct Fwd {
   bool building;       // first run at this batch size: create TMA plans
   size_t plan_i = 0;
   int launches = 0;
+  const float* wt32 = nullptr;   // tf32 schedule: fp32 W^T of the NEXT gemm() call (consumed by it)
 };
 
 static cudaEvent_t prof_event(uu_model* m) {
@@ -339,8 +368,17 @@ static int gemm(Fwd& f, const void* A, long long lda, int M, int K, const float*
     }
     UU_CHECK(f.plan_i < f.m->plans.size(), "internal: GEMM plan list out of sync");
     UU_LAUNCH(f, UU_KIND_GEMM_TC, 1, tc_gemm_launch(f.m->plans[f.plan_i++], epi, C, c_bf16, ldc, f.st));
+  } else if (f.wt32 && M >= 256 && N % 64 == 0 && K % 4 == 0 && lda % 4 == 0 && ldc % 4 == 0 && !c_bf16) {
+    // tf32 schedule: fp32 activations, W^T fp32, tcgen05 kind::tf32 (the plan is a pair of tensor maps: built per call)
+    TcGemmPlan* p = nullptr;
+    if (tc_gemm_plan_create_tf32(&p, (const float*)A, lda, M, K, f.wt32, K, N)) return 1;
+    cudaError_t err = cudaSuccess;
+    UU_LAUNCH(f, UU_KIND_GEMM_TC, 1, (err = tc_gemm_launch(p, epi, C, 0, ldc, f.st)));
+    tc_gemm_plan_destroy(p);
+    f.wt32 = nullptr;
   } else {
     UU_LAUNCH(f, UU_KIND_GEMM_F32, 1, launch_gemm_simt(A, 0, lda, Wf, M, N, K, epi, C, c_bf16, ldc, f.st));
+    f.wt32 = nullptr;
   }
   return 0;
 }
@@ -350,13 +388,16 @@ static int attention_block(Fwd& f, const BlockW& w, float* x, int L, const uint8
   uu_model* m = f.m;
   const uu_spec& s = m->spec;
   const int d = s.d_temporal, R = f.B * L, bf = f.tc ? 1 : 0;
+  const bool tf = m->precision == UU_PRECISION_TF32;
   Epilogue e;
   e.bias = w.bqkv;
+  f.wt32 = tf ? w.t_qkv : nullptr;
   if (gemm(f, m->Y, d, R, d, w.wqkv, w.p_qkv, 3 * d, e, m->QKV, bf, 3 * d)) return 1;
   UU_LAUNCH(f, UU_KIND_ATTENTION, 1,
             launch_attention(m->QKV, bf, f.B, L, s.num_heads, d / s.num_heads, keymask, s.n_tok, m->O, f.st));
   Epilogue ep;
   ep.bias = w.bp; ep.flags = EPI_RESIDUAL; ep.res = x; ep.ldr = d;
+  f.wt32 = tf ? w.t_proj : nullptr;
   if (gemm(f, m->O, d, R, d, w.wp, w.p_proj, d, ep, x, 0, d)) return 1;
   return 0;
 }
@@ -562,7 +603,9 @@ static int run_forward_impl(uu_model* m, const float* x2d, const uint8_t* mask, 
     return 0;
   }
 
-  // ---- fp32 ("exact") schedule: CUDA-core kernels, fp32 activations -----------------------------------------
+  // ---- fp32 ("exact") schedule: CUDA-core kernels, fp32 activations; UU_PRECISION_TF32 runs the same schedule with the
+  // large GEMMs on tcgen05 kind::tf32 (gemm() consumes f.wt32) ---------------------------------------------------------
+  const bool tf = m->precision == UU_PRECISION_TF32;
   // K1a: gather list of frames that carry a 2-D pose
   if (use_mask) {
     UU_LAUNCH(f, UU_KIND_GATHER, 3, launch_build_gather(mask, B, N, m->g_scratch, m->g_list, m->g_count, st));
@@ -582,6 +625,7 @@ static int run_forward_impl(uu_model* m, const float* x2d, const uint8_t* mask, 
     e.bias = W(m, "spatial_to_temporal_fc", 1);
     e.flags = EPI_ROWTABLE; e.table = W(m, "temporal_pe", 0); e.table_period = N;
     if (use_mask) { e.c_rowidx = m->g_list; e.m_dev = m->g_count; }
+    f.wt32 = tf ? m->t_s2t : nullptr;
     if (gemm(f, m->S, J * ds, R, J * ds, W(m, "spatial_to_temporal_fc", 0), m->p_s2t, d, e, m->X, 0, d)) return 1;
     if (use_mask) {
       UU_LAUNCH(f, UU_KIND_TOKEN_FILL, 1,
@@ -597,9 +641,11 @@ static int run_forward_impl(uu_model* m, const float* x2d, const uint8_t* mask, 
     UU_LAUNCH(f, UU_KIND_LAYERNORM, 1, launch_layernorm(m->X, R, d, w.ln2_g, w.ln2_b, 1e-5f, nullptr, 1, m->Y, bf, st));
     Epilogue e1;
     e1.bias = w.b1; e1.flags = EPI_RELU;
+    f.wt32 = tf ? w.t_fc1 : nullptr;
     if (gemm(f, m->Y, d, R, d, w.w1, w.p_fc1, h, e1, m->Hd, bf, h)) return 1;
     Epilogue e2;
     e2.bias = w.b2; e2.flags = EPI_RESIDUAL; e2.res = m->X; e2.ldr = d;
+    f.wt32 = tf ? w.t_fc2 : nullptr;
     if (gemm(f, m->Hd, h, R, h, w.w2, w.p_fc2, d, e2, m->X, 0, d)) return 1;
   }
   // T4: full-sequence head (before the strided blocks modify X in place)
@@ -626,6 +672,7 @@ static int run_forward_impl(uu_model* m, const float* x2d, const uint8_t* mask, 
     Epilogue e1;
     e1.bias = w.b1; e1.flags = EPI_RELU;
     e1.cmap.rpb = L; e1.cmap.batch_rows = Lo * st_i; e1.cmap.offset = pl; e1.cmap.step = 1;
+    f.wt32 = tf ? w.t_fc1 : nullptr;
     if (gemm(f, m->Y, d, Rl, d, w.w1, w.p_fc1, h, e1, m->Hp[i], bf, h)) return 1;
     // strided Conv1D k=3 as an implicit GEMM: row (b,t) = Hp[b, t*s : t*s+3, :] is contiguous (3h values),
     // consecutive rows are s*h apart.  Residual = x[b, c0 + t*s] (MaxPool1D(pool 1, stride s) of the trimmed x).
@@ -634,6 +681,7 @@ static int run_forward_impl(uu_model* m, const float* x2d, const uint8_t* mask, 
     e2.rmap.rpb = Lo; e2.rmap.batch_rows = L;
     e2.rmap.offset = (st_i > 1 && pl == 0) ? 1 : 0; e2.rmap.step = st_i;
     (void)pr;
+    f.wt32 = tf ? w.t_fc2 : nullptr;
     if (gemm(f, m->Hp[i], (long long)st_i * h, B * Lo, 3 * h, w.w2, w.p_fc2, d, e2, m->Xs[i], 0, d)) return 1;
     x_in = m->Xs[i];
   }
@@ -760,8 +808,11 @@ int uu_destroy(uu_model* m) {
 
 int uu_set_precision(uu_model* m, int precision) {
   UU_CHECK(m, "null model");
-  UU_CHECK(precision == UU_PRECISION_FP32 || precision == UU_PRECISION_BF16, "unknown precision");
-  if (precision != m->precision) drop_graphs(m);
+  UU_CHECK(precision == UU_PRECISION_FP32 || precision == UU_PRECISION_BF16 || precision == UU_PRECISION_TF32, "unknown precision");
+  if (precision != m->precision) {
+    drop_graphs(m);
+    if (precision == UU_PRECISION_TF32) m->dirty = true;      // the fp32 W^T copies are built on the next commit
+  }
   m->precision = precision;
   return 0;
 }
