@@ -95,6 +95,12 @@ def test_n_rank_step_equals_one_rank_step(math):
             # round-off noise that Adam normalises to +-lr, excluded as in test_three_adamw_steps_match_oracle)
             if k.endswith("|5") and "block" in k:
                 continue
-            # (tf32 mode: entries whose gradient is dominated by the TF32 rounding of different partial sums can take one
-            # Adam step of +-lr = 4e-5 in the other direction)
-            assert np.abs(a[k] - b[k]).max() < (2e-5 if math == "fp32" else 1e-4), k
+            diff = np.abs(a[k] - b[k])
+            if math == "fp32":
+                assert diff.max() < 2e-5, k
+            else:
+                # tf32 mode: the split-K tiling of the tensor-core weight gradients follows the local row count, so the
+                # TF32-rounded partial sums differ between 1 and 2 ranks; where a gradient entry is dominated by that
+                # rounding Adam's m / sqrt(v) turns the difference into +-lr per step (3 steps x 4e-5 x 2 at most).
+                # Bulk of the entries must still agree far inside one step.
+                assert diff.max() <= 2.5e-4 and np.quantile(diff, 0.999) < 2e-5, (k, diff.max(), np.quantile(diff, 0.999))

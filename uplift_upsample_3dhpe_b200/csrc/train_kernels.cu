@@ -691,12 +691,12 @@ __global__ void __launch_bounds__(128) k_attention_bwd(const float* __restrict__
 // Spatial attention of the training step (17 joint tokens, 8 heads of dimension 4, no key mask; vit:99-130 inside
 // net:313-333): the generic kernels spend one CTA per (frame, head) on a 17 x 17 problem.  Here one WARP owns a frame:
 // its q | k | v rows (17 x 96 floats, contiguous) sit in the warp's shared-memory slot, lane i is query token i and walks
-// the 8 heads (479 -> 304 us per layer at 36352 frames).  A backward kernel of the same shape (17 x 17 weight / gradient
-// tiles exchanged through the warp's shared-memory slot) measured SLOWER than the generic one (1110 vs 603 us: 128
-// registers, 70 KB of shared memory per CTA) and was dropped.  S <= 32, heads * 4 == 32.
+// the 8 heads.  S == 17 (compile-time: with a run-time S the unrolled key loops were half predicated-off instructions),
+// heads * 4 == 32.
 // =================================================================================================
-constexpr int SA_WARPS = 4, SA_MAXS = 32;
-__global__ void __launch_bounds__(SA_WARPS * 32) k_attn_small_fwd(const float* __restrict__ qkv, long long frames, int S,
+constexpr int SA_WARPS = 4;
+template <int S>      // S tokens per frame: a compile-time constant, so the key loops unroll without predication
+__global__ void __launch_bounds__(SA_WARPS * 32) k_attn_small_fwd(const float* __restrict__ qkv, long long frames,
                                                                    float* __restrict__ out) {
   extern __shared__ __align__(16) float sa_sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -712,25 +712,23 @@ __global__ void __launch_bounds__(SA_WARPS * 32) k_attn_small_fwd(const float* _
 #pragma unroll 1
       for (int h = 0; h < 8; ++h) {
         const float4 q = *reinterpret_cast<const float4*>(sq + lane * 96 + 4 * h);
-        float sc[SA_MAXS];
+        float sc[S];
         float m = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < SA_MAXS; ++j)
-          if (j < S) {
-            const float4 k = *reinterpret_cast<const float4*>(sq + j * 96 + 32 + 4 * h);
-            sc[j] = (q.x * k.x + q.y * k.y + q.z * k.z + q.w * k.w) * scale;
-            m = fmaxf(m, sc[j]);
-          }
+        for (int j = 0; j < S; ++j) {
+          const float4 k = *reinterpret_cast<const float4*>(sq + j * 96 + 32 + 4 * h);
+          sc[j] = (q.x * k.x + q.y * k.y + q.z * k.z + q.w * k.w) * scale;
+          m = fmaxf(m, sc[j]);
+        }
         float l = 0.f;
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < SA_MAXS; ++j)
-          if (j < S) {
-            const float p = expf(sc[j] - m);
-            const float4 v = *reinterpret_cast<const float4*>(sq + j * 96 + 64 + 4 * h);
-            l += p;
-            o.x = fmaf(p, v.x, o.x); o.y = fmaf(p, v.y, o.y); o.z = fmaf(p, v.z, o.z); o.w = fmaf(p, v.w, o.w);
-          }
+        for (int j = 0; j < S; ++j) {
+          const float p = expf(sc[j] - m);
+          const float4 v = *reinterpret_cast<const float4*>(sq + j * 96 + 64 + 4 * h);
+          l += p;
+          o.x = fmaf(p, v.x, o.x); o.y = fmaf(p, v.y, o.y); o.z = fmaf(p, v.z, o.z); o.w = fmaf(p, v.w, o.w);
+        }
         const float inv = 1.f / l;
         *reinterpret_cast<float4*>(so + lane * 32 + 4 * h) = make_float4(o.x * inv, o.y * inv, o.z * inv, o.w * inv);
       }
@@ -741,23 +739,120 @@ __global__ void __launch_bounds__(SA_WARPS * 32) k_attn_small_fwd(const float* _
   }
 }
 
-bool attention_small_ok(int S, int heads, int dh, const uint8_t* mask) { return dh == 4 && heads == 8 && S <= SA_MAXS && S >= 1 && !mask; }
+// Backward of the same problem: lane i first acts as query i (row i of the attention weights A and of dS, dQ_i), the two
+// S x S tiles go through the warp's shared-memory slot, then lane j acts as key j (dK_j = scale sum_i dS_ij q_i,
+// dV_j = sum_i A_ij dO_i).  One read of q | k | v and dO per frame (the per-(frame, head) kernel moved 3.5 GB per launch:
+// every head re-fetched the 32-byte sectors it shares with its neighbour).
+template <int S>
+__global__ void __launch_bounds__(SA_WARPS * 32) k_attn_small_bwd(const float* __restrict__ qkv, const float* __restrict__ dO,
+                                                                   long long frames, float* __restrict__ dqkv) {
+  extern __shared__ __align__(16) float sa_sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int ST = S | 1;                            // odd row stride of the S x S tiles
+  constexpr int SLOT = (S * 96 * 2 + S * 32 + 2 * S * ST + 3) & ~3;
+  float* sq = sa_sm + warp * SLOT;
+  float* sg = sq + S * 96;                             // [S][96] dq | dk | dv
+  float* sd = sg + S * 96;                             // [S][32] dO
+  float* sa = sd + S * 32;                             // [S][ST] attention weights
+  float* sds = sa + S * ST;                            // [S][ST] dS
+  const float scale = 0.5f;
+  for (long long f = (long long)blockIdx.x * SA_WARPS + warp; f < frames; f += (long long)gridDim.x * SA_WARPS) {
+    const float4* src = reinterpret_cast<const float4*>(qkv + f * S * 96);
+    const float4* gsrc = reinterpret_cast<const float4*>(dO + f * S * 32);
+    __syncwarp();
+    for (int i = lane; i < S * 24; i += 32) reinterpret_cast<float4*>(sq)[i] = src[i];
+    for (int i = lane; i < S * 8; i += 32) reinterpret_cast<float4*>(sd)[i] = gsrc[i];
+    __syncwarp();
+#pragma unroll 1
+    for (int h = 0; h < 8; ++h) {
+      if (lane < S) {
+        const float4 q = *reinterpret_cast<const float4*>(sq + lane * 96 + 4 * h);
+        const float4 g = *reinterpret_cast<const float4*>(sd + lane * 32 + 4 * h);
+        float a[S];
+        float m = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+          const float4 k = *reinterpret_cast<const float4*>(sq + j * 96 + 32 + 4 * h);
+          a[j] = (q.x * k.x + q.y * k.y + q.z * k.z + q.w * k.w) * scale;
+          m = fmaxf(m, a[j]);
+        }
+        float l = 0.f;
+#pragma unroll
+        for (int j = 0; j < S; ++j) { a[j] = expf(a[j] - m); l += a[j]; }
+        const float inv = 1.f / l;
+        float dot = 0.f;
+        float da[S];
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+          const float4 v = *reinterpret_cast<const float4*>(sq + j * 96 + 64 + 4 * h);
+          a[j] *= inv;
+          da[j] = g.x * v.x + g.y * v.y + g.z * v.z + g.w * v.w;
+          dot = fmaf(da[j], a[j], dot);
+        }
+        float4 dq = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+          const float ds = a[j] * (da[j] - dot);
+          const float4 k = *reinterpret_cast<const float4*>(sq + j * 96 + 32 + 4 * h);
+          dq.x = fmaf(ds, k.x, dq.x); dq.y = fmaf(ds, k.y, dq.y); dq.z = fmaf(ds, k.z, dq.z); dq.w = fmaf(ds, k.w, dq.w);
+          sa[lane * ST + j] = a[j];
+          sds[lane * ST + j] = ds;
+        }
+        *reinterpret_cast<float4*>(sg + lane * 96 + 4 * h) = make_float4(dq.x * scale, dq.y * scale, dq.z * scale, dq.w * scale);
+      }
+      __syncwarp();
+      if (lane < S) {
+        float4 dk = make_float4(0.f, 0.f, 0.f, 0.f), dv = dk;
+#pragma unroll
+        for (int i = 0; i < S; ++i) {
+          const float ds = sds[i * ST + lane], aa = sa[i * ST + lane];
+          const float4 q = *reinterpret_cast<const float4*>(sq + i * 96 + 4 * h);
+          const float4 g = *reinterpret_cast<const float4*>(sd + i * 32 + 4 * h);
+          dk.x = fmaf(ds, q.x, dk.x); dk.y = fmaf(ds, q.y, dk.y); dk.z = fmaf(ds, q.z, dk.z); dk.w = fmaf(ds, q.w, dk.w);
+          dv.x = fmaf(aa, g.x, dv.x); dv.y = fmaf(aa, g.y, dv.y); dv.z = fmaf(aa, g.z, dv.z); dv.w = fmaf(aa, g.w, dv.w);
+        }
+        *reinterpret_cast<float4*>(sg + lane * 96 + 32 + 4 * h) = make_float4(dk.x * scale, dk.y * scale, dk.z * scale, dk.w * scale);
+        *reinterpret_cast<float4*>(sg + lane * 96 + 64 + 4 * h) = dv;
+      }
+      __syncwarp();
+    }
+    float4* dst = reinterpret_cast<float4*>(dqkv + f * S * 96);
+    for (int i = lane; i < S * 24; i += 32) dst[i] = reinterpret_cast<const float4*>(sg)[i];
+  }
+}
+bool attention_small_ok(int S, int heads, int dh, const uint8_t* mask) { return dh == 4 && heads == 8 && S == 17 && !mask; }
 cudaError_t launch_attention_small_fwd(const float* qkv, long long frames, int S, float* out, cudaStream_t st) {
-  const size_t smem = sizeof(float) * SA_WARPS * (S * 96 + S * 32);
-  static size_t attr = 0;
-  if (smem > attr) {
-    cudaError_t e = cudaFuncSetAttribute(k_attn_small_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (S != 17) return cudaErrorInvalidValue;
+  constexpr size_t smem = sizeof(float) * SA_WARPS * (17 * 96 + 17 * 32);
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(k_attn_small_fwd<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    attr = smem;
+    attr = true;
   }
   const unsigned grid = (unsigned)std::min<long long>((frames + SA_WARPS - 1) / SA_WARPS, 148 * 8);
-  k_attn_small_fwd<<<grid, SA_WARPS * 32, smem, st>>>(qkv, frames, S, out);
+  k_attn_small_fwd<17><<<grid, SA_WARPS * 32, smem, st>>>(qkv, frames, out);
   return cudaGetLastError();
 }
+cudaError_t launch_attention_small_bwd(const float* qkv, const float* dO, long long frames, int S, float* dqkv, cudaStream_t st) {
+  if (S != 17) return cudaErrorInvalidValue;
+  constexpr size_t smem = sizeof(float) * SA_WARPS * ((17 * 96 * 2 + 17 * 32 + 2 * 17 * 17 + 3) & ~3);
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(k_attn_small_bwd<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  const unsigned grid = (unsigned)std::min<long long>((frames + SA_WARPS - 1) / SA_WARPS, 148 * 4);
+  k_attn_small_bwd<17><<<grid, SA_WARPS * 32, smem, st>>>(qkv, dO, frames, dqkv);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_attention_bwd(const float* qkv, const float* dO, long long B, int S, int heads, int dh,
                                  const uint8_t* mask, int mask_stride, float* dqkv, cudaStream_t st) {
   if (B == 0) return cudaSuccess;
   if (S < 1 || S > 128) return cudaErrorInvalidValue;
+  if (attention_small_ok(S, heads, dh, mask)) return launch_attention_small_bwd(qkv, dO, B, S, dqkv, st);
   const size_t smem = sizeof(float) * (4 * S * dh + ((S + 3) & ~3) + 2 * S * (S | 1));
   dim3 grid((unsigned)B, heads);
   const int threads = (S + 31) / 32 * 32;

@@ -368,7 +368,7 @@ static int gemm(Fwd& f, const void* A, long long lda, int M, int K, const float*
     }
     UU_CHECK(f.plan_i < f.m->plans.size(), "internal: GEMM plan list out of sync");
     UU_LAUNCH(f, UU_KIND_GEMM_TC, 1, tc_gemm_launch(f.m->plans[f.plan_i++], epi, C, c_bf16, ldc, f.st));
-  } else if (f.wt32 && M >= 256 && N % 64 == 0 && K % 4 == 0 && lda % 4 == 0 && ldc % 4 == 0 && !c_bf16) {
+  } else if (f.wt32 && M >= 64 && N % 64 == 0 && K % 4 == 0 && lda % 4 == 0 && ldc % 4 == 0 && !c_bf16) {
     // tf32 schedule: fp32 activations, W^T fp32, tcgen05 kind::tf32 (the plan is a pair of tensor maps: built per call)
     TcGemmPlan* p = nullptr;
     if (tc_gemm_plan_create_tf32(&p, (const float*)A, lda, M, K, f.wt32, K, N)) return 1;
