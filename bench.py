@@ -626,6 +626,12 @@ def main():
     if rank == 0 and world == 1:
         r = cpu_reference_run(spec, cfg, a.s_in, a.cpu_sample, steps=5, warmup=1, budget_s=25.0)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+        if sub is not None:          # CPU baselines of BASELINE configs 1 and 3 (same port, smaller sample)
+            for key, (cn, si) in (("s_in20", ("h36m_351", 20)), ("h36m_81", ("h36m_81", 4))):
+                cfg_k = UpliftUpsampleConfig.preset(cn)
+                rk = cpu_reference_run(spec_from_config(cfg_k), cfg_k, si, 32, steps=3, warmup=1, budget_s=10.0)
+                sub[key]["cpu_baseline"] = {"value": rk["value"], "unit": UNIT, "cores": rk["cores"], "kind": "port",
+                                            "sample": rk["sample"]}
     if rank == 0:
         emit({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,

@@ -223,6 +223,12 @@ int uu_op_attention(const void* qkv, int is_bf16, int B, int S, int heads, int d
 /* The tcgen05 / TMEM attention kernel of the bf16 schedule (vit:99-130): q | k | v rows bf16 (B * S, 1152) fed by TMA,
  * scores and probabilities in tensor memory, P . V with P read from tensor memory; 8 heads of dimension 48, S <= 80. */
 int uu_op_attention_tc5(const void* qkv, int B, int S, const uint8_t* keep_mask, int mask_stride, void* out, void* stream);
+/* Attention of the training step (vit:99-130 and its gradient) on mma.sync TF32 with fp32 rows as the tape holds them:
+ * qkv (B * S, 3 * heads * dh), keep_mask as uu_op_attention.  dO == NULL: forward into out (B * S, heads * dh);
+ * otherwise backward: dqkv (B * S, 3 * heads * dh) from dO (B * S, heads * dh).  nsplit 3 = error-compensated TF32
+ * (hi / lo operand split, fp32-grade), 1 = plain TF32.  S <= 80, dh in {32, 48, 64}. */
+int uu_op_attention_train(const float* qkv, const float* dO, int B, int S, int heads, int dh, const uint8_t* keep_mask,
+                          int mask_stride, float* out, float* dqkv, int nsplit, void* stream);
 /* C = act(A @ W + bias) (+ res); flags: 1 = ReLU, 2 = residual.  fp32 CUDA-core GEMM, W is (K, N). */
 /* K2 alone: the fused spatial transformer (S1-S3 + spatial_norm, net:313-330) of a loaded model on the frames the
  * mask keeps (mask NULL: all B*n_tok frames).  precision fp32 -> out is float, bf16 -> out is bf16; out holds

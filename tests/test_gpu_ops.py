@@ -170,6 +170,52 @@ def test_attention_tcgen05(lib, S, B, masked):
     assert err < 6e-2, err
 
 
+@pytest.mark.parametrize("S,B,H,dh,masked", [(71, 5, 8, 48, True), (71, 3, 8, 48, False), (41, 4, 8, 48, True),
+                                             (24, 9, 8, 48, False), (8, 17, 8, 48, False), (3, 4, 8, 48, False),
+                                             (80, 2, 8, 48, True), (1, 5, 8, 48, False), (30, 3, 4, 32, True),
+                                             (71, 2, 8, 64, True)])
+@pytest.mark.parametrize("nsplit", [3, 1])
+def test_attention_train_mma(lib, S, B, H, dh, masked, nsplit):
+    """attn_mma.cu (training step, vit:99-130 and its gradient): forward and backward on mma.sync TF32 against a float64
+    autograd evaluation of the same lines.  nsplit = 3 (hi / lo operand split) must be fp32-grade: 2e-5 of the tensor
+    scale; nsplit = 1 (plain TF32, 10-bit operands) 1e-2.  All-masked windows give uniform attention (-1e9 term)."""
+    rng = np.random.default_rng(S * 7 + B)
+    d = H * dh
+    qkv = rng.normal(size=(B, S, 3 * d)).astype(np.float32)
+    dO = rng.normal(size=(B, S, d)).astype(np.float32)
+    keep = np.ones((B, S), dtype=bool)
+    if masked:
+        keep = rng.random((B, S)) < 0.4
+        keep[0] = False
+        keep[1, :] = False; keep[1, S // 2] = True
+    t = torch.tensor(qkv, dtype=torch.float64, requires_grad=True)
+    q, k, v = [t[..., i * d:(i + 1) * d].reshape(B, S, H, dh).permute(0, 2, 1, 3) for i in range(3)]
+    logits = (q @ k.transpose(-1, -2)) / math.sqrt(dh)
+    if masked:
+        # fp32 semantics of `logits + (1 - mask) * -1e9` (vit:117-119): the score is absorbed (|score| < 32 = half an ulp
+        # of 1e9), the value is exactly -1e9 and the gradient still passes through the addition
+        drop = torch.tensor(~keep[:, None, None, :]).expand_as(logits)
+        logits = torch.where(drop, logits + (-1e9 - logits).detach(), logits)
+    want = (torch.softmax(logits, -1) @ v).permute(0, 2, 1, 3).reshape(B, S, d)
+    want.backward(torch.tensor(dO, dtype=torch.float64))
+    want_g = t.grad.numpy()
+    want = want.detach().numpy()
+    qd, gd = dev(qkv), dev(dO)
+    km = P(dev(keep.astype(np.uint8))) if masked else None
+    out = torch.full((B, S, d), float("nan"), dtype=torch.float32, device="cuda")
+    dq = torch.full((B, S, 3 * d), float("nan"), dtype=torch.float32, device="cuda")
+    _lib.check(lib.uu_op_attention_train(P(qd), None, B, S, H, dh, km, S, P(out), None, nsplit, None))
+    _lib.check(lib.uu_op_attention_train(P(qd), P(gd), B, S, H, dh, km, S, None, P(dq), nsplit, None))
+    torch.cuda.synchronize()
+    got, got_g = out.cpu().numpy(), dq.cpu().numpy()
+    assert np.isfinite(got).all() and np.isfinite(got_g).all()
+    e_f = np.abs(got - want).max() / np.abs(want).max()
+    e_b = np.abs(got_g - want_g).max() / np.abs(want_g).max()
+    print(f"mma attention S={S} B={B} dh={dh} nsplit={nsplit}: fwd {e_f:.2e} bwd {e_b:.2e} (relative to the tensor max)")
+    tol = 2e-5 if nsplit == 3 else 1e-2
+    assert e_f < tol and e_b < tol, (e_f, e_b)
+
+
 @pytest.mark.parametrize("M,N,K,flags", [(300, 384, 384, 0), (129, 51, 384, 0), (1000, 768, 384, 1),
                                          (77, 384, 2304, 2), (64, 1152, 544, 3)])
 def test_gemm_f32(lib, M, N, K, flags):

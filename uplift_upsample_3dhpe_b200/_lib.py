@@ -17,7 +17,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libuu3d.so")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 SOURCES = ["kernels_f32.cu", "spatial_tc.cu", "attention_tc.cu", "gemm_tc.cu", "train_kernels.cu", "uu_train.cu",
-           "uu_comm.cu", "wgrad_tc.cu", "attn_tc5.cu", "uu_api.cu"]
+           "uu_comm.cu", "wgrad_tc.cu", "attn_tc5.cu", "attn_mma.cu", "uu_api.cu"]
 OBJ_DIR = os.path.join(_HERE, "build")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-diag-suppress", "550,177"]
@@ -202,6 +202,8 @@ def _declare(lib) -> None:
     lib.uu_op_resid_gemm_bf16.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p,
                                           c_int, c_void_p, c_void_p]
     lib.uu_op_attention_tc5.argtypes = [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]
+    lib.uu_op_attention_train.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p,
+                                          c_int, c_void_p]
     lib.uu_op_mlp_bf16.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p]
     lib.uu_op_wgrad_tf32.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_int, c_void_p]
@@ -226,7 +228,7 @@ EXPORTS = [
     "uu_adamw_step", "uu_get_ema_weight", "uu_train_set_math", "uu_train_set_token_masking", "uu_get_token_mask",
     "uu_op_build_gather", "uu_op_token_fill", "uu_op_layernorm", "uu_op_attention", "uu_op_spatial", "uu_op_gemm_f32",
     "uu_op_gemm_bf16", "uu_op_gemm_tf32", "uu_op_ln_gemm_bf16", "uu_op_resid_gemm_bf16",
-    "uu_op_wgrad_tf32", "uu_op_mlp_bf16", "uu_op_attention_tc5", "uu_comm_unique_id", "uu_comm_init", "uu_comm_destroy", "uu_comm_world_size", "uu_allreduce_gradients", "uu_train_step",
+    "uu_op_wgrad_tf32", "uu_op_mlp_bf16", "uu_op_attention_tc5", "uu_op_attention_train", "uu_comm_unique_id", "uu_comm_init", "uu_comm_destroy", "uu_comm_world_size", "uu_allreduce_gradients", "uu_train_step",
 ]
 
 

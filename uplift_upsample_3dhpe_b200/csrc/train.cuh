@@ -34,6 +34,13 @@ bool attention_small_ok(int S, int heads, int dh, const uint8_t* mask);
 cudaError_t launch_attention_small_fwd(const float* qkv, long long frames, int S, float* out, cudaStream_t st);
 cudaError_t launch_attention_bwd(const float* qkv, const float* dO, long long B, int S, int heads, int dh,
                                  const uint8_t* mask, int mask_stride, float* dqkv, cudaStream_t st);
+// tensor-core attention of the training step (attn_mma.cu): S <= 80, head dimension 32 / 48 / 64; nsplit 3 = compensated
+// TF32 (fp32-grade), 1 = plain TF32
+bool attention_mma_ok(long long B, int S, int heads, int dh);
+cudaError_t launch_attention_mma_fwd(const float* qkv, long long B, int S, int heads, int dh, const uint8_t* mask,
+                                     int mask_stride, float* out, int nsplit, cudaStream_t st);
+cudaError_t launch_attention_mma_bwd(const float* qkv, const float* dO, long long B, int S, int heads, int dh,
+                                     const uint8_t* mask, int mask_stride, float* dqkv, int nsplit, cudaStream_t st);
 cudaError_t launch_act_fwd(const float* pre, long long n, int act, float* out, cudaStream_t st);
 cudaError_t launch_act_bwd(const float* pre, const float* dout, const RowMap& dmap, long long ldd, long long rows,
                            int cols, int act, float* dpre, cudaStream_t st);

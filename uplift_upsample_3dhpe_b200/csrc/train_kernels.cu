@@ -27,27 +27,28 @@ void train_reduce_scratch(float* p, size_t n_floats) { g_red_scratch = p; g_red_
 size_t train_reduce_scratch_floats() { return (size_t)6 << 20; }
 
 // out[i] += sum_p part[p * n + i]; elements i >= n0 go to out1[i - n0] (two destination tensors, e.g. gamma | beta).
-// A CTA owns 32 elements; 8 thread rows each sum every 8th slab in slab order, then the 8 sums are added in row order:
+// A CTA owns 32 elements; RP_ROWS thread rows each sum every RP_ROWS-th slab in slab order, then the sums are added in row order:
 // the association is fixed by (nparts), never by timing.
-__global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict__ part, int nparts, long long n,
+constexpr int RP_ROWS = 32;      // slab rows summed in parallel by one CTA (1024 threads: short dependent chains)
+__global__ void __launch_bounds__(32 * RP_ROWS) k_reduce_partials(const float* __restrict__ part, int nparts, long long n,
                                                          float* __restrict__ out0, long long n0, float* __restrict__ out1) {
-  __shared__ float sm[8][32];
+  __shared__ float sm[RP_ROWS][32];
   const int e = threadIdx.x & 31, pl = threadIdx.x >> 5;
   const long long i = (long long)blockIdx.x * 32 + e;
   float s = 0.f;
   if (i < n)
-    for (int p = pl; p < nparts; p += 8) s += part[(long long)p * n + i];
+    for (int p = pl; p < nparts; p += RP_ROWS) s += part[(long long)p * n + i];
   sm[pl][e] = s;
   __syncthreads();
   if (pl == 0 && i < n) {
 #pragma unroll
-    for (int q = 1; q < 8; ++q) s += sm[q][e];
+    for (int q = 1; q < RP_ROWS; ++q) s += sm[q][e];
     float* dst = i < n0 ? out0 + i : out1 + (i - n0);
     *dst += s;
   }
 }
 static cudaError_t reduce_partials(int nparts, long long n, float* out0, long long n0, float* out1, cudaStream_t st) {
-  k_reduce_partials<<<(unsigned)((n + 31) / 32), 256, 0, st>>>(g_red_scratch, nparts, n, out0, n0, out1);
+  k_reduce_partials<<<(unsigned)((n + 31) / 32), 32 * RP_ROWS, 0, st>>>(g_red_scratch, nparts, n, out0, n0, out1);
   return cudaGetLastError();
 }
 
@@ -294,7 +295,7 @@ cudaError_t launch_wgrad_skinny(const float* X, long long ldx, const float* dY, 
   if (e != cudaSuccess) return e;
   if (db) return reduce_partials((int)grid, (long long)K * N + N, dW, (long long)K * N, db, st);
   // without a bias gradient the slab still carries the N column sums: reduce the K * N part only (strided slabs)
-  k_reduce_partials<<<(unsigned)(((long long)K * N + N + 31) / 32), 256, 0, st>>>(
+  k_reduce_partials<<<(unsigned)(((long long)K * N + N + 31) / 32), 32 * RP_ROWS, 0, st>>>(
       g_red_scratch, (int)grid, (long long)K * N + N, dW, (long long)K * N, g_red_scratch + (size_t)grid * (K * N + N));
   return cudaGetLastError();
 }
@@ -416,9 +417,60 @@ __global__ void k_ln_fwd_gen(const float* __restrict__ x, long long rows, int d,
     yr[c] = xr[c] * inv + (beta[c] - mean * inv);
   }
 }
+// d == 4 * LPR * VPL: a row is LPR lanes x VPL float4 (32 / LPR rows per warp), held in registers between the statistics and
+// the normalisation: one 16-byte read and one 16-byte write per element quad (the scalar kernel above re-read the row three
+// times through 4-byte accesses and ran at 1.1 TB/s).
+template <int LPR, int VPL>
+__global__ void __launch_bounds__(256) k_ln_fwd_v4(const float* __restrict__ x, long long rows, const float* __restrict__ gamma,
+                                                   const float* __restrict__ beta, float eps, float* __restrict__ y) {
+  constexpr int D = 4 * LPR * VPL, RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, sub = lane / LPR, l = lane % LPR;
+  const long long row = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * RPW + sub;
+  const bool ok = row < rows;
+  float4 v[VPL];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    v[i] = ok ? *reinterpret_cast<const float4*>(x + row * D + 4 * (l + LPR * i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s * (1.f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + e * e);
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q * (1.f / D) + eps);
+  if (!ok) return;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c = 4 * (l + LPR * i);
+    const float4 g = *reinterpret_cast<const float4*>(gamma + c), b = *reinterpret_cast<const float4*>(beta + c);
+    float4 o;
+    o.x = (v[i].x - mean) * (g.x * rstd) + b.x; o.y = (v[i].y - mean) * (g.y * rstd) + b.y;
+    o.z = (v[i].z - mean) * (g.z * rstd) + b.z; o.w = (v[i].w - mean) * (g.w * rstd) + b.w;
+    *reinterpret_cast<float4*>(y + row * D + c) = o;
+  }
+}
+static inline bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 cudaError_t launch_ln_fwd_gen(const float* x, long long rows, int d, const float* gamma, const float* beta, float eps,
                               float* y, cudaStream_t st) {
   if (rows == 0) return cudaSuccess;
+  if (al16(x) && al16(y) && al16(gamma) && al16(beta)) {
+#define UU_LNF(LPR, VPL)                                                                                                  \
+  if (d == 4 * LPR * VPL) {                                                                                               \
+    const long long rpc = 8 * (32 / LPR);                                                                                 \
+    k_ln_fwd_v4<LPR, VPL><<<(unsigned)((rows + rpc - 1) / rpc), 256, 0, st>>>(x, rows, gamma, beta, eps, y);              \
+    return cudaGetLastError();                                                                                            \
+  }
+    UU_LNF(8, 1) UU_LNF(16, 1) UU_LNF(32, 1) UU_LNF(32, 2) UU_LNF(32, 3) UU_LNF(32, 4)
+#undef UU_LNF
+  }
   k_ln_fwd_gen<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, rows, d, gamma, beta, eps, y);
   return cudaGetLastError();
 }
@@ -537,6 +589,72 @@ __global__ void __launch_bounds__(256) k_ln_bwd_d32(const float* __restrict__ x,
     partial[(long long)blockIdx.x * 64 + threadIdx.x] = t;
   }
 }
+// d == 128 * VPL (temporal / strided blocks): lane l owns the float4 columns 4 l + 128 i; x, dy (and dx when accumulating)
+// move as 16-byte accesses, the gamma / beta partials of the lane stay in registers over all rows of the warp.
+template <int VPL>
+__global__ void __launch_bounds__(256) k_ln_bwd_v4(const float* __restrict__ x, const float* __restrict__ dy, long long rows,
+                                                   const float* __restrict__ gamma, float eps, float* __restrict__ dx,
+                                                   int accumulate, float* __restrict__ partial) {
+  constexpr int D = 128 * VPL;
+  extern __shared__ __align__(16) float sm[];            // [warps][2 D]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  float4 pg[VPL], pb[VPL], gm[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    pg[i] = make_float4(0.f, 0.f, 0.f, 0.f); pb[i] = pg[i];
+    gm[i] = *reinterpret_cast<const float4*>(gamma + 4 * lane + 128 * i);
+  }
+  for (long long row = (long long)blockIdx.x * wpb + warp; row < rows; row += (long long)gridDim.x * wpb) {
+    float4 xv[VPL], gv[VPL];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      xv[i] = *reinterpret_cast<const float4*>(x + row * D + 4 * lane + 128 * i);
+      gv[i] = *reinterpret_cast<const float4*>(dy + row * D + 4 * lane + 128 * i);
+      s += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
+    }
+    const float mean = warp_sum_t(s) * (1.f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      xv[i].x -= mean; xv[i].y -= mean; xv[i].z -= mean; xv[i].w -= mean;
+      q += (xv[i].x * xv[i].x + xv[i].y * xv[i].y) + (xv[i].z * xv[i].z + xv[i].w * xv[i].w);
+    }
+    const float rstd = rsqrtf(warp_sum_t(q) * (1.f / D) + eps);
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      xv[i].x *= rstd; xv[i].y *= rstd; xv[i].z *= rstd; xv[i].w *= rstd;          // xhat
+      const float g0 = gv[i].x * gm[i].x, g1 = gv[i].y * gm[i].y, g2 = gv[i].z * gm[i].z, g3 = gv[i].w * gm[i].w;
+      m1 += (g0 + g1) + (g2 + g3);
+      m2 += (g0 * xv[i].x + g1 * xv[i].y) + (g2 * xv[i].z + g3 * xv[i].w);
+    }
+    m1 = warp_sum_t(m1) * (1.f / D); m2 = warp_sum_t(m2) * (1.f / D);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      float4 v;
+      v.x = rstd * (gv[i].x * gm[i].x - m1 - xv[i].x * m2); v.y = rstd * (gv[i].y * gm[i].y - m1 - xv[i].y * m2);
+      v.z = rstd * (gv[i].z * gm[i].z - m1 - xv[i].z * m2); v.w = rstd * (gv[i].w * gm[i].w - m1 - xv[i].w * m2);
+      float4* dst = reinterpret_cast<float4*>(dx + row * D + 4 * lane + 128 * i);
+      if (accumulate) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+      *dst = v;
+      pg[i].x = fmaf(gv[i].x, xv[i].x, pg[i].x); pg[i].y = fmaf(gv[i].y, xv[i].y, pg[i].y);
+      pg[i].z = fmaf(gv[i].z, xv[i].z, pg[i].z); pg[i].w = fmaf(gv[i].w, xv[i].w, pg[i].w);
+      pb[i].x += gv[i].x; pb[i].y += gv[i].y; pb[i].z += gv[i].z; pb[i].w += gv[i].w;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    *reinterpret_cast<float4*>(sm + warp * 2 * D + 4 * lane + 128 * i) = pg[i];
+    *reinterpret_cast<float4*>(sm + warp * 2 * D + D + 4 * lane + 128 * i) = pb[i];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) {
+    float t = 0.f;
+    for (int w = 0; w < wpb; ++w) t += sm[w * 2 * D + c];
+    partial[(long long)blockIdx.x * 2 * D + c] = t;
+  }
+}
 cudaError_t launch_ln_bwd_gen(const float* x, const float* dy, long long rows, int d, const float* gamma, float eps,
                               float* dx, int accumulate, float* dgamma, float* dbeta, cudaStream_t st) {
   if (rows == 0) return cudaSuccess;
@@ -547,6 +665,14 @@ cudaError_t launch_ln_bwd_gen(const float* x, const float* dy, long long rows, i
   const size_t smem = 8 * 2 * d * sizeof(float);
   if (d == 32 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)dx & 15) == 0 && ((uintptr_t)gamma & 15) == 0)
     k_ln_bwd_d32<<<grid, 256, 0, st>>>(x, dy, rows, gamma, eps, dx, accumulate, g_red_scratch);
+  else if (d % 128 == 0 && al16(x) && al16(dy) && al16(dx) && al16(gamma)) {
+    switch (d / 128) {
+      case 1: k_ln_bwd_v4<1><<<grid, 256, smem, st>>>(x, dy, rows, gamma, eps, dx, accumulate, g_red_scratch); break;
+      case 2: k_ln_bwd_v4<2><<<grid, 256, smem, st>>>(x, dy, rows, gamma, eps, dx, accumulate, g_red_scratch); break;
+      case 3: k_ln_bwd_v4<3><<<grid, 256, smem, st>>>(x, dy, rows, gamma, eps, dx, accumulate, g_red_scratch); break;
+      default: k_ln_bwd_v4<4><<<grid, 256, smem, st>>>(x, dy, rows, gamma, eps, dx, accumulate, g_red_scratch); break;
+    }
+  }
   else if (d <= 32) k_ln_bwd_gen<1><<<grid, 256, smem, st>>>(x, dy, rows, d, gamma, eps, dx, accumulate, g_red_scratch);
   else if (d <= 64) k_ln_bwd_gen<2><<<grid, 256, smem, st>>>(x, dy, rows, d, gamma, eps, dx, accumulate, g_red_scratch);
   else if (d <= 384) k_ln_bwd_gen<12><<<grid, 256, smem, st>>>(x, dy, rows, d, gamma, eps, dx, accumulate, g_red_scratch);
@@ -915,16 +1041,81 @@ __global__ void k_act_bwd_mapped(const float* __restrict__ hp, const float* __re
     dpre[i] = (pr >= 0 && hp[pr * ld + c] > 0.f) ? dhp[pr * ld + c] : 0.f;
   }
 }
+// ---- 16-byte variants of the element-wise kernels: one float4 per thread and step, ONE 32-bit index division per four
+// elements (the scalar kernels above spend a 64-bit division per element and ran at 2.0 - 2.6 TB/s); used whenever the
+// widths are multiples of 4, the pointers 16-byte aligned and the element count fits 32 bits.
+__device__ __forceinline__ float act_fwd1(float v, int act) {
+  return act == 0 ? fmaxf(v, 0.f) : 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float act_grad1(float v, int act) {
+  if (act == 0) return v > 0.f ? 1.f : 0.f;     // TF: relu'(0) = 0
+  return 0.5f * (1.f + erff(v * 0.70710678118654752440f)) + v * 0.3989422804014327f * expf(-0.5f * v * v);
+}
+__global__ void __launch_bounds__(256) k_act_fwd4(const float4* __restrict__ pre, uint32_t n4, int act, float4* __restrict__ out) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    const float4 v = pre[i];
+    out[i] = make_float4(act_fwd1(v.x, act), act_fwd1(v.y, act), act_fwd1(v.z, act), act_fwd1(v.w, act));
+  }
+}
+__global__ void __launch_bounds__(256) k_act_bwd4(const float4* __restrict__ pre, const float* __restrict__ dout, RowMap dmap,
+                                                  long long ldd, uint32_t n4, uint32_t cols4, int act, float4* __restrict__ dpre) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    const uint32_t r = i / cols4, c = (i - r * cols4) * 4;
+    const long long dr = map_row(dmap, (int)r);
+    const float4 g = dr < 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(dout + dr * ldd + c);
+    const float4 v = pre[i];
+    dpre[i] = make_float4(g.x * act_grad1(v.x, act), g.y * act_grad1(v.y, act), g.z * act_grad1(v.z, act),
+                          g.w * act_grad1(v.w, act));
+  }
+}
+__global__ void __launch_bounds__(256) k_residual4(const float* __restrict__ base, RowMap bmap, const float4* __restrict__ y,
+                                                   const float* __restrict__ scale, uint32_t rows_per_sample,
+                                                   const float* __restrict__ table, uint32_t period, uint32_t n4, uint32_t d4,
+                                                   float4* __restrict__ out) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    const uint32_t r = i / d4, c = (i - r * d4) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (y) {
+      v = y[i];
+      if (scale) { const float sc = scale[r / rows_per_sample]; v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc; }
+    }
+    if (base) {
+      const float4 b = *reinterpret_cast<const float4*>(base + map_row(bmap, (int)r) * (long long)(4 * d4) + c);
+      v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    }
+    if (table) {
+      const float4 t = *reinterpret_cast<const float4*>(table + (long long)(r % period) * (4 * d4) + c);
+      v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+    }
+    out[i] = v;
+  }
+}
+__global__ void __launch_bounds__(256) k_scale_rows4(const float4* __restrict__ src, const float* __restrict__ scale, uint32_t rps,
+                                                     uint32_t n4, uint32_t d4, float4* __restrict__ dst) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    float4 v = src[i];
+    if (scale) { const float sc = scale[(i / d4) / rps]; v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc; }
+    dst[i] = v;
+  }
+}
 static inline unsigned ew_grid(long long n) { return (unsigned)std::min<long long>((n + 255) / 256, 148 * 32); }
+static inline bool fits_u32(long long n) { return n > 0 && n < (1ll << 31); }
 cudaError_t launch_act_fwd(const float* pre, long long n, int act, float* out, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
-  k_act_fwd<<<ew_grid(n), 256, 0, st>>>(pre, n, act, out);
+  if (n % 4 == 0 && fits_u32(n) && al16(pre) && al16(out))
+    k_act_fwd4<<<ew_grid(n / 4), 256, 0, st>>>((const float4*)pre, (uint32_t)(n / 4), act, (float4*)out);
+  else
+    k_act_fwd<<<ew_grid(n), 256, 0, st>>>(pre, n, act, out);
   return cudaGetLastError();
 }
 cudaError_t launch_act_bwd(const float* pre, const float* dout, const RowMap& dmap, long long ldd, long long rows, int cols,
                            int act, float* dpre, cudaStream_t st) {
   if (rows == 0) return cudaSuccess;
-  k_act_bwd<<<ew_grid(rows * cols), 256, 0, st>>>(pre, dout, dmap, ldd, rows, cols, act, dpre);
+  if (cols % 4 == 0 && ldd % 4 == 0 && fits_u32(rows * cols) && al16(pre) && al16(dout) && al16(dpre))
+    k_act_bwd4<<<ew_grid(rows * cols / 4), 256, 0, st>>>((const float4*)pre, dout, dmap, ldd, (uint32_t)(rows * cols / 4),
+                                                         (uint32_t)(cols / 4), act, (float4*)dpre);
+  else
+    k_act_bwd<<<ew_grid(rows * cols), 256, 0, st>>>(pre, dout, dmap, ldd, rows, cols, act, dpre);
   return cudaGetLastError();
 }
 
@@ -953,7 +1144,11 @@ cudaError_t launch_residual(const float* base, const RowMap& bmap, const float* 
                             int rows_per_sample, const float* table, int period, long long rows, int d, float* out,
                             cudaStream_t st) {
   if (rows == 0) return cudaSuccess;
-  k_residual<<<ew_grid(rows * d), 256, 0, st>>>(base, bmap, y, scale, rows_per_sample, table, period, rows, d, out);
+  if (d % 4 == 0 && fits_u32(rows * d) && al16(base) && al16(y) && al16(table) && al16(out))
+    k_residual4<<<ew_grid(rows * d / 4), 256, 0, st>>>(base, bmap, (const float4*)y, scale, (uint32_t)rows_per_sample, table,
+                                                       (uint32_t)period, (uint32_t)(rows * d / 4), (uint32_t)(d / 4), (float4*)out);
+  else
+    k_residual<<<ew_grid(rows * d), 256, 0, st>>>(base, bmap, y, scale, rows_per_sample, table, period, rows, d, out);
   return cudaGetLastError();
 }
 
@@ -967,7 +1162,11 @@ __global__ void k_scale_rows(const float* __restrict__ src, const float* __restr
 cudaError_t launch_scale_rows(const float* src, const float* scale, int rps, long long rows, int d, float* dst,
                               cudaStream_t st) {
   if (rows == 0) return cudaSuccess;
-  k_scale_rows<<<ew_grid(rows * d), 256, 0, st>>>(src, scale, rps, rows, d, dst);
+  if (d % 4 == 0 && fits_u32(rows * d) && al16(src) && al16(dst))
+    k_scale_rows4<<<ew_grid(rows * d / 4), 256, 0, st>>>((const float4*)src, scale, (uint32_t)rps, (uint32_t)(rows * d / 4),
+                                                         (uint32_t)(d / 4), (float4*)dst);
+  else
+    k_scale_rows<<<ew_grid(rows * d), 256, 0, st>>>(src, scale, rps, rows, d, dst);
   return cudaGetLastError();
 }
 

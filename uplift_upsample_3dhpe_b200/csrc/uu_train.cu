@@ -47,8 +47,12 @@ struct TrainState {
   float token_mask_rate = 0.f;                  // TOKEN_MASK_RATE (net:287-311; masked value 0), training only
   float* tok_keep = nullptr;                    // [R] 0 / 1 factors drawn for the current step
   int math = 0;
+  int attn_split = 3;                           // attn_mma.cu: 3 = compensated TF32 (fp32-grade), 1 = plain TF32
   float* wg_scratch = nullptr;                  // split-K partial tiles of the tensor-core wgrad (wgrad_tc.cu)
   float* red_scratch = nullptr;                 // partial slabs of the deterministic two-pass reductions (train_kernels.cu)
+  struct PackedQkv { float *W = nullptr, *b = nullptr, *dW = nullptr, *db = nullptr; };
+  std::unordered_map<const float*, PackedQkv> pk;   // W_q -> [W_q | W_k | W_v] (d, 3d), bias (3d) and their gradient slabs
+  std::unordered_set<const float*> pk_valid;         // packed copies refreshed once per step
   std::unordered_map<const float*, float*> wt;   // W (K, N) -> W^T (N, K) copies for the forward GEMMs
   std::unordered_set<const float*> wt_valid;     // refreshed once per forward/backward call
 };
@@ -122,6 +126,60 @@ static int weight_transposed(Ctx& c, const float* Wm, int K, int N, const float*
     k_transpose_f32<<<dim3((N + 31) / 32, (K + 31) / 32), dim3(32, 8), 0, c.st>>>(Wm, K, N, it->second);
     UU_CUDA(cudaGetLastError());
     t->wt_valid.insert(Wm);
+  }
+  *out = it->second;
+  return 0;
+}
+
+// q | k | v as ONE linear layer: the three Keras tensors (d, d) are packed side by side into (d, 3d) once per step, so the
+// block reads its LayerNorm output once (forward), writes dX once instead of three accumulating passes (dgrad) and reads X /
+// dQKV once (wgrad); the packed gradient slab is added back onto the three tensors' gradient slots.
+__global__ void k_pack_qkv(const float* __restrict__ wq, const float* __restrict__ wk, const float* __restrict__ wv,
+                           const float* __restrict__ bq, const float* __restrict__ bk, const float* __restrict__ bv, int d,
+                           float* __restrict__ W, float* __restrict__ b) {
+  const int n = d * 3 * d;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n + 3 * d; i += gridDim.x * blockDim.x) {
+    if (i < n) {
+      const int r = i / (3 * d), c = i - r * 3 * d, k = c / d, cc = c - k * d;
+      W[i] = (k == 0 ? wq : k == 1 ? wk : wv)[r * d + cc];
+    } else {
+      const int c = i - n, k = c / d, cc = c - k * d;
+      b[c] = (k == 0 ? bq : k == 1 ? bk : bv)[cc];
+    }
+  }
+}
+__global__ void k_unpack_qkv_add(const float* __restrict__ dW, const float* __restrict__ db, int d, float* __restrict__ gq,
+                                 float* __restrict__ gk, float* __restrict__ gv, float* __restrict__ gbq,
+                                 float* __restrict__ gbk, float* __restrict__ gbv) {
+  const int n = d * 3 * d;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n + 3 * d; i += gridDim.x * blockDim.x) {
+    if (i < n) {
+      const int r = i / (3 * d), c = i - r * 3 * d, k = c / d, cc = c - k * d;
+      (k == 0 ? gq : k == 1 ? gk : gv)[r * d + cc] += dW[i];
+    } else {
+      const int c = i - n, k = c / d, cc = c - k * d;
+      (k == 0 ? gbq : k == 1 ? gbk : gbv)[cc] += db[c];
+    }
+  }
+}
+static int packed_qkv(Ctx& c, const std::string& g, int d, TrainState::PackedQkv* out) {
+  TrainState* t = c.t;
+  uu_model* m = c.m;
+  const float* key = W(m, g, 2);
+  auto it = t->pk.find(key);
+  if (it == t->pk.end()) {
+    TrainState::PackedQkv p;
+    if (falloc(t, &p.W, (size_t)d * 3 * d) || falloc(t, &p.b, 3 * (size_t)d) || falloc(t, &p.dW, (size_t)d * 3 * d) ||
+        falloc(t, &p.db, 3 * (size_t)d))
+      return 1;
+    it = t->pk.emplace(key, p).first;
+  }
+  if (!t->pk_valid.count(key)) {
+    const int n = d * 3 * d + 3 * d;
+    k_pack_qkv<<<std::min(148 * 4, (n + 255) / 256), 256, 0, c.st>>>(W(m, g, 2), W(m, g, 4), W(m, g, 6), W(m, g, 3), W(m, g, 5),
+                                                                   W(m, g, 7), d, it->second.W, it->second.b);
+    UU_CUDA(cudaGetLastError());
+    t->pk_valid.insert(key);
   }
   *out = it->second;
   return 0;
@@ -209,10 +267,13 @@ static int attn_half_fwd(Ctx& c, const BlkDims& b, const std::string& g, BlkTape
   const long long R = b.nb * b.S;
   const int d = b.d;
   UU_TL(launch_ln_fwd_gen(tp.x0, R, d, W(m, g, 0), W(m, g, 1), 1e-5f, tp.y1, c.st));
-  for (int k = 0; k < 3; ++k)
-    if (lin_fwd(c, tp.y1, d, (int)R, d, W(m, g, 2 + 2 * k), d, W(m, g, 3 + 2 * k), tp.qkv + k * d, 3 * d)) return 1;
+  TrainState::PackedQkv pq;
+  if (packed_qkv(c, g, d, &pq)) return 1;
+  if (lin_fwd(c, tp.y1, d, (int)R, d, pq.W, 3 * d, pq.b, tp.qkv, 3 * d)) return 1;
   if (attention_small_ok(b.S, b.heads, d / b.heads, keymask))       // spatial blocks: one warp per frame (train_kernels.cu)
     UU_TL(launch_attention_small_fwd(tp.qkv, b.nb, b.S, tp.o, c.st));
+  else if (attention_mma_ok(b.nb, b.S, b.heads, d / b.heads))        // temporal / strided blocks: mma.sync TF32 (attn_mma.cu)
+    UU_TL(launch_attention_mma_fwd(tp.qkv, b.nb, b.S, b.heads, d / b.heads, keymask, mask_stride, tp.o, c.t->attn_split, c.st));
   else
     UU_TL(launch_attention(tp.qkv, 0, (int)b.nb, b.S, b.heads, d / b.heads, keymask, mask_stride, tp.o, c.st));
   if (lin_fwd(c, tp.o, d, (int)R, d, W(m, g, 8), d, W(m, g, 9), c.t->tmp1, d)) return 1;
@@ -229,11 +290,22 @@ static int attn_half_bwd(Ctx& c, const BlkDims& b, const std::string& g, BlkTape
   const int d = b.d;
   UU_TL(launch_scale_rows(dx, tp.keep < 1.f ? tp.scale : nullptr, b.S, R, d, t->tmp1, c.st));
   if (lin_bwd(c, tp.o, d, t->tmp1, d, (int)R, d, d, W(m, g, 8), t->tmp2, d, 0, G(m, g, 8), G(m, g, 9))) return 1;
-  UU_TL(launch_attention_bwd(tp.qkv, t->tmp2, b.nb, b.S, b.heads, d / b.heads, keymask, mask_stride, t->tmp_qkv, c.st));
-  for (int k = 0; k < 3; ++k)
-    if (lin_bwd(c, tp.y1, d, t->tmp_qkv + k * d, 3 * d, (int)R, d, d, W(m, g, 2 + 2 * k), t->tmp2, d, k > 0,
-                G(m, g, 2 + 2 * k), G(m, g, 3 + 2 * k)))
-      return 1;
+  if (!attention_small_ok(b.S, b.heads, d / b.heads, keymask) && attention_mma_ok(b.nb, b.S, b.heads, d / b.heads))
+    UU_TL(launch_attention_mma_bwd(tp.qkv, t->tmp2, b.nb, b.S, b.heads, d / b.heads, keymask, mask_stride, t->tmp_qkv,
+                                   t->attn_split, c.st));
+  else
+    UU_TL(launch_attention_bwd(tp.qkv, t->tmp2, b.nb, b.S, b.heads, d / b.heads, keymask, mask_stride, t->tmp_qkv, c.st));
+  TrainState::PackedQkv pq;
+  if (packed_qkv(c, g, d, &pq)) return 1;
+  UU_CUDA(cudaMemsetAsync(pq.dW, 0, sizeof(float) * (size_t)d * 3 * d, c.st));
+  UU_CUDA(cudaMemsetAsync(pq.db, 0, sizeof(float) * 3 * (size_t)d, c.st));
+  if (lin_bwd(c, tp.y1, d, t->tmp_qkv, 3 * d, (int)R, d, 3 * d, pq.W, t->tmp2, d, 0, pq.dW, pq.db)) return 1;
+  {
+    const int n = d * 3 * d + 3 * d;
+    k_unpack_qkv_add<<<std::min(148 * 4, (n + 255) / 256), 256, 0, c.st>>>(pq.dW, pq.db, d, G(m, g, 2), G(m, g, 4), G(m, g, 6),
+                                                                         G(m, g, 3), G(m, g, 5), G(m, g, 7));
+    UU_CUDA(cudaGetLastError());
+  }
   UU_TL(launch_ln_bwd_gen(tp.x0, t->tmp2, R, d, W(m, g, 0), 1e-5f, dx, 1, G(m, g, 0), G(m, g, 1), c.st));
   return 0;
 }
@@ -283,6 +355,7 @@ static int ensure_train(uu_model* m, int B) {
   UU_CUDA(cudaDeviceSynchronize());
   free_pool(t->pool);
   t->wt.clear(); t->wt_valid.clear();          // the transposed-weight copies live in the same pool
+  t->pk.clear(); t->pk_valid.clear();
   t->sp.assign(s.spatial_depth, BlkTape());
   t->tp.assign(s.temporal_depth, BlkTape());
   t->st.assign(s.n_strided, BlkTape());
@@ -532,7 +605,7 @@ int uu_train_config(uu_model* m, int global_batch, int root_keypoint, float w_ce
 int uu_train_forward_backward(uu_model* m, const float* x2d, const uint8_t* mask, const float* gt3d, int B,
                               int64_t step, float* loss_dev, void* stream) {
   UU_CHECK(m, "null model");
-  if (m->train) m->train->wt_valid.clear();     // weights may have changed since the last call
+  if (m->train) { m->train->wt_valid.clear(); m->train->pk_valid.clear(); }     // weights may have changed since the last call
   return train_fb(m, x2d, mask, gt3d, B, step, loss_dev, (cudaStream_t)stream);
 }
 
@@ -542,7 +615,7 @@ int uu_train_forward_backward(uu_model* m, const float* x2d, const uint8_t* mask
 int uu_train_step(uu_model* m, const float* x2d, const uint8_t* mask, const float* gt3d, int B, int64_t step, float lr_t,
                   float wd_t, float beta1, float beta2, float epsilon, float ema_decay, float* loss_dev, void* stream) {
   UU_CHECK(m, "null model");
-  if (m->train) m->train->wt_valid.clear();
+  if (m->train) { m->train->wt_valid.clear(); m->train->pk_valid.clear(); }
   if (train_fb(m, x2d, mask, gt3d, B, step, loss_dev, (cudaStream_t)stream, true)) return 1;
   return uu_adamw_step(m, lr_t, wd_t, beta1, beta2, epsilon, step + 1, ema_decay, stream);
 }
@@ -571,6 +644,8 @@ int uu_train_set_math(uu_model* m, int mode) {
   UU_CHECK(m && (mode == 0 || mode == 1), "math mode: 0 = fp32, 1 = tf32 tensor cores");
   if (!m->train) m->train = new TrainState();
   m->train->math = mode;
+  m->train->attn_split = 3;
+  if (const char* e = getenv("UU_ATTN_SPLIT_TMP")) m->train->attn_split = atoi(e) == 1 ? 1 : 3;   // TEMPORARY (measurement)
   return 0;
 }
 
