@@ -191,7 +191,12 @@ def train_measure(a, rank, world, local_rank, dist, peaks, steps=5, warmup=3):
            "math": a.train_math, "unit": "windows/s", "steps": steps, "warmup": warmup,
            "parity": "gradients vs fp32 torch autograd: tests/test_gpu_train.py (autodiff / AdamW arithmetic of TF is "
                      "parity-unpinned: no TensorFlow here)"}
-    flop_per_window = 3 * 2 * sum(macs_by_kind(spec, spec.n_tok)[k] for k in ("spatial", "attention", "gemm_tc"))
+    # algorithmic FLOPs: frames the stride mask drops are skipped; the training masks mix the
+    # MASK_STRIDE values, so the valid-frame count is the mean over one drawn batch
+    m_probe = stride_mask.batch_stride_masks_train(spec.n_tok, cfg.SEQUENCE_STRIDE, cfg.MASK_STRIDE, Bg, seed=0)
+    valid_mean = float(m_probe.sum()) / Bg
+    out["valid_frames_per_window_mean"] = round(valid_mean, 2)
+    flop_per_window = 3 * 2 * sum(macs_by_kind(spec, valid_mean)[k] for k in ("spatial", "attention", "gemm_tc"))
     for mode in (("strong", "weak") if world > 1 else ("strong",)):
         B = Bg // world if mode == "strong" else Bg
         model = build_uplift_upsample_transformer(cfg, device=local_rank, precision="fp32")
@@ -246,7 +251,7 @@ def train_measure(a, rank, world, local_rank, dist, peaks, steps=5, warmup=3):
                                   "peak": peaks["tensor_burst"], "frac": round(tfl / peaks["tensor_burst"], 4),
                                   "frac_of_sustained": round(tfl / peaks["tensor_sustained"], 4),
                                   "algorithmic_gflop_per_step": round(flop_per_window * total / 1e9, 1),
-                                  "note": "3 x forward FLOPs (fwd + dgrad + wgrad) over the whole step"},
+                                  "note": "3 x forward FLOPs (fwd + dgrad + wgrad; masked frames skipped in the spatial stage) over the whole step"},
                      "adamw": {"ms": round(adam_ms, 4), "bytes_per_param": bytes_pp,
                                "achieved_gbs": round(bytes_pp * model.param_count / (adam_ms * 1e-3) / 1e9, 1),
                                "peak_gbs": peaks["hbm"],

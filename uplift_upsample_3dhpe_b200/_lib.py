@@ -17,7 +17,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libuu3d.so")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 SOURCES = ["kernels_f32.cu", "spatial_tc.cu", "attention_tc.cu", "gemm_tc.cu", "train_kernels.cu", "uu_train.cu",
-           "uu_comm.cu", "wgrad_tc.cu", "attn_tc5.cu", "attn_mma.cu", "uu_api.cu"]
+           "uu_comm.cu", "wgrad_tc.cu", "attn_tc5.cu", "attn_mma.cu", "spatial_train.cu", "uu_api.cu"]
 OBJ_DIR = os.path.join(_HERE, "build")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-diag-suppress", "550,177"]

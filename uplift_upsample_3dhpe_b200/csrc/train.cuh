@@ -41,6 +41,12 @@ cudaError_t launch_attention_mma_fwd(const float* qkv, long long B, int S, int h
                                      int mask_stride, float* out, int nsplit, cudaStream_t st);
 cudaError_t launch_attention_mma_bwd(const float* qkv, const float* dO, long long B, int S, int heads, int dh,
                                      const uint8_t* mask, int mask_stride, float* dqkv, int nsplit, cudaStream_t st);
+// one spatial transformer block forward with its tape in a single launch (spatial_train.cu): 17 joints, d = 32, hidden 64,
+// 8 heads, GELU
+bool spatial_block_fused_ok(int J, int d, int h, int heads, int act);
+cudaError_t launch_spatial_block_fwd_tape(const float* x0, const float* const* weights, const float* scale, const float* scale2,
+                                          long long frames, float* y1, float* qkv, float* o, float* x1, float* y2, float* hpre,
+                                          float* hact, float* x2, int num_sms, cudaStream_t st);
 cudaError_t launch_act_fwd(const float* pre, long long n, int act, float* out, cudaStream_t st);
 cudaError_t launch_act_bwd(const float* pre, const float* dout, const RowMap& dmap, long long ldd, long long rows,
                            int cols, int act, float* dpre, cudaStream_t st);
@@ -54,13 +60,16 @@ cudaError_t launch_token_mask_draw(unsigned long long seed, unsigned long long s
 cudaError_t launch_scale_rows(const float* src, const float* scale, int rps, long long rows, int d, float* dst,
                               cudaStream_t st);
 cudaError_t launch_scatter_add(const float* src, const RowMap& dmap, long long rows, int d, float* dst, cudaStream_t st);
-cudaError_t launch_embed_fwd(const float* x2d, const uint8_t* mask, int J, long long rows, int d, const float* Wk,
-                             const float* b, const float* pe, float* out, cudaStream_t st);
-cudaError_t launch_embed_wgrad(const float* x2d, const uint8_t* mask, int J, const float* de, long long rows, int d,
-                               float* dW, cudaStream_t st);
-cudaError_t launch_fill_fwd(const float* s, const uint8_t* mask, const float* token, const float* pe, int n_tok,
-                            long long rows, int d, float* x, cudaStream_t st);
-cudaError_t launch_fill_bwd(const float* dx, const uint8_t* mask, long long rows, int d, float* ds, cudaStream_t st);
+cudaError_t launch_embed_fwd(const float* x2d, const uint8_t* mask, const int* list, int J, long long rows, int d,
+                             const float* Wk, const float* b, const float* pe, float* out, cudaStream_t st);
+cudaError_t launch_embed_wgrad(const float* x2d, const uint8_t* mask, const int* list, int J, const float* de, long long rows,
+                               int d, float* dW, cudaStream_t st);
+cudaError_t launch_fill_fwd(const float* s, const uint8_t* mask, const int* pos, const float* keep, const float* token,
+                            const float* pe, int n_tok, long long rows, int d, float* x, cudaStream_t st);
+cudaError_t launch_fill_bwd(const float* dx, const uint8_t* mask, const int* list, const float* keep, long long rows, int d,
+                            float* ds, cudaStream_t st);
+cudaError_t launch_invert_list(const int* list, int n, int* pos, cudaStream_t st);
+cudaError_t launch_gather_f32(const float* src, const int* list, int n, float* dst, cudaStream_t st);
 int loss_blocks(int B, int n_tok, int J, bool has_full);
 cudaError_t launch_loss(const float* full, const float* central, const float* gt, int B, int n_tok, int J, int root,
                         float w_seq, float w_cen, float* dfull, float* dcentral, float* partials, float* loss,

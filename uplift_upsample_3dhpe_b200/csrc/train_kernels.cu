@@ -816,161 +816,151 @@ __global__ void __launch_bounds__(128) k_attention_bwd(const float* __restrict__
 // =================================================================================================
 // Spatial attention of the training step (17 joint tokens, 8 heads of dimension 4, no key mask; vit:99-130 inside
 // net:313-333): the generic kernels spend one CTA per (frame, head) on a 17 x 17 problem.  Here one WARP owns a frame:
-// its q | k | v rows (17 x 96 floats, contiguous) sit in the warp's shared-memory slot, lane i is query token i and walks
-// the 8 heads.  S == 17 (compile-time: with a run-time S the unrolled key loops were half predicated-off instructions),
-// heads * 4 == 32.
+// its q | k | v rows (17 x 96 floats, contiguous in the tape) sit in the warp's shared-memory slot and the 17 x 8 = 136
+// (token, head) pairs are dealt to the lanes, head fastest (5 rounds, 85 % of the lanes busy; one lane per token left 15
+// of 32 idle).  All lanes of a round walk the same key / query index, so every shared-memory read is 8 distinct 16-byte
+// chunks (the heads) broadcast to the lanes that share them: one wavefront, no conflicts.
+// Backward in two passes without any 17 x 17 tile: pass 1, pair = (query i, head): softmax row, dot = sum_j dA_ij A_ij,
+// dQ_i, and the row statistics (max, 1 / sum, dot) parked in shared memory; pass 2, pair = (key j, head): the score column
+// is recomputed with the same expression (bit-identical to pass 1), A_ij from the statistics, dK_j = scale sum_i dS_ij q_i,
+// dV_j = sum_i A_ij dO_i.  Results go straight to global memory (a round writes 128-byte runs).  S is a compile-time
+// constant (with a run-time S the unrolled loops were half predicated-off instructions); heads * 4 == 32.
 // =================================================================================================
 constexpr int SA_WARPS = 4;
-template <int S>      // S tokens per frame: a compile-time constant, so the key loops unroll without predication
-__global__ void __launch_bounds__(SA_WARPS * 32) k_attn_small_fwd(const float* __restrict__ qkv, long long frames,
+// the loops below are fully unrolled; without a scheduling fence every few iterations ptxas hoists all 17 (x 2 or 3) float4
+// shared-memory loads of a loop to its top (255 registers, two resident CTAs)
+#define UU_SA_FENCE(idx) do { if (((idx) & 3) == 3) asm volatile("" ::: "memory"); } while (0)
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) { return fmaf(a.w, b.w, fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x))); }
+template <int S>
+__global__ void __launch_bounds__(SA_WARPS * 32, 6) k_attn_small_fwd(const float* __restrict__ qkv, long long frames,
                                                                    float* __restrict__ out) {
-  extern __shared__ __align__(16) float sa_sm[];
+  __shared__ __align__(16) float sa_sm[SA_WARPS][S * 96];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* sq = sa_sm + warp * (S * 96 + S * 32);      // [S][96] q | k | v rows, then [S][32] output staging
-  float* so = sq + S * 96;
+  float* sq = sa_sm[warp];
   const float scale = 0.5f;                            // 1 / sqrt(4)
   for (long long f = (long long)blockIdx.x * SA_WARPS + warp; f < frames; f += (long long)gridDim.x * SA_WARPS) {
     const float4* src = reinterpret_cast<const float4*>(qkv + f * S * 96);
     __syncwarp();
     for (int i = lane; i < S * 24; i += 32) reinterpret_cast<float4*>(sq)[i] = src[i];
     __syncwarp();
-    if (lane < S) {
 #pragma unroll 1
-      for (int h = 0; h < 8; ++h) {
-        const float4 q = *reinterpret_cast<const float4*>(sq + lane * 96 + 4 * h);
-        float sc[S];
-        float m = -INFINITY;
+    for (int item = lane; item < S * 8; item += 32) {
+      const int i = item >> 3, h = item & 7;
+      const float4 q = *reinterpret_cast<const float4*>(sq + i * 96 + 4 * h);
+      float sc[S];
+      float m = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < S; ++j) {
-          const float4 k = *reinterpret_cast<const float4*>(sq + j * 96 + 32 + 4 * h);
-          sc[j] = (q.x * k.x + q.y * k.y + q.z * k.z + q.w * k.w) * scale;
-          m = fmaxf(m, sc[j]);
-        }
-        float l = 0.f;
-        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int j = 0; j < S; ++j) {
-          const float p = expf(sc[j] - m);
-          const float4 v = *reinterpret_cast<const float4*>(sq + j * 96 + 64 + 4 * h);
-          l += p;
-          o.x = fmaf(p, v.x, o.x); o.y = fmaf(p, v.y, o.y); o.z = fmaf(p, v.z, o.z); o.w = fmaf(p, v.w, o.w);
-        }
-        const float inv = 1.f / l;
-        *reinterpret_cast<float4*>(so + lane * 32 + 4 * h) = make_float4(o.x * inv, o.y * inv, o.z * inv, o.w * inv);
+      for (int j = 0; j < S; ++j) {
+        sc[j] = dot4(q, *reinterpret_cast<const float4*>(sq + j * 96 + 32 + 4 * h)) * scale;
+        m = fmaxf(m, sc[j]);
+        UU_SA_FENCE(j);
       }
+      float l = 0.f;
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < S; ++j) {
+        const float p = __expf(sc[j] - m);
+        const float4 v = *reinterpret_cast<const float4*>(sq + j * 96 + 64 + 4 * h);
+        l += p;
+        o.x = fmaf(p, v.x, o.x); o.y = fmaf(p, v.y, o.y); o.z = fmaf(p, v.z, o.z); o.w = fmaf(p, v.w, o.w);
+        UU_SA_FENCE(j);
+      }
+      const float inv = 1.f / l;
+      *reinterpret_cast<float4*>(out + f * S * 32 + i * 32 + 4 * h) = make_float4(o.x * inv, o.y * inv, o.z * inv, o.w * inv);
     }
-    __syncwarp();
-    float4* dst = reinterpret_cast<float4*>(out + f * S * 32);
-    for (int i = lane; i < S * 8; i += 32) dst[i] = reinterpret_cast<const float4*>(so)[i];
   }
 }
 
-// Backward of the same problem: lane i first acts as query i (row i of the attention weights A and of dS, dQ_i), the two
-// S x S tiles go through the warp's shared-memory slot, then lane j acts as key j (dK_j = scale sum_i dS_ij q_i,
-// dV_j = sum_i A_ij dO_i).  One read of q | k | v and dO per frame (the per-(frame, head) kernel moved 3.5 GB per launch:
-// every head re-fetched the 32-byte sectors it shares with its neighbour).
 template <int S>
-__global__ void __launch_bounds__(SA_WARPS * 32) k_attn_small_bwd(const float* __restrict__ qkv, const float* __restrict__ dO,
+__global__ void __launch_bounds__(SA_WARPS * 32, 5) k_attn_small_bwd(const float* __restrict__ qkv, const float* __restrict__ dO,
                                                                    long long frames, float* __restrict__ dqkv) {
-  extern __shared__ __align__(16) float sa_sm[];
+  constexpr int SLOT = S * 96 + S * 32 + S * 8 * 4;    // q | k | v rows, dO rows, (max, 1 / sum, dot, -) per (query, head)
+  __shared__ __align__(16) float sa_sm[SA_WARPS][SLOT];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int ST = S | 1;                            // odd row stride of the S x S tiles
-  constexpr int SLOT = (S * 96 * 2 + S * 32 + 2 * S * ST + 3) & ~3;
-  float* sq = sa_sm + warp * SLOT;
-  float* sg = sq + S * 96;                             // [S][96] dq | dk | dv
-  float* sd = sg + S * 96;                             // [S][32] dO
-  float* sa = sd + S * 32;                             // [S][ST] attention weights
-  float* sds = sa + S * ST;                            // [S][ST] dS
+  float* sq = sa_sm[warp];
+  float* sd = sq + S * 96;
+  float4* sst = reinterpret_cast<float4*>(sd + S * 32);
   const float scale = 0.5f;
   for (long long f = (long long)blockIdx.x * SA_WARPS + warp; f < frames; f += (long long)gridDim.x * SA_WARPS) {
     const float4* src = reinterpret_cast<const float4*>(qkv + f * S * 96);
     const float4* gsrc = reinterpret_cast<const float4*>(dO + f * S * 32);
+    float* dst = dqkv + f * S * 96;
     __syncwarp();
     for (int i = lane; i < S * 24; i += 32) reinterpret_cast<float4*>(sq)[i] = src[i];
     for (int i = lane; i < S * 8; i += 32) reinterpret_cast<float4*>(sd)[i] = gsrc[i];
     __syncwarp();
+    // ---- pass 1: pair = (query i, head h)
 #pragma unroll 1
-    for (int h = 0; h < 8; ++h) {
-      if (lane < S) {
-        const float4 q = *reinterpret_cast<const float4*>(sq + lane * 96 + 4 * h);
-        const float4 g = *reinterpret_cast<const float4*>(sd + lane * 32 + 4 * h);
-        float a[S];
-        float m = -INFINITY;
+    for (int item = lane; item < S * 8; item += 32) {
+      const int i = item >> 3, h = item & 7;
+      const float4 q = *reinterpret_cast<const float4*>(sq + i * 96 + 4 * h);
+      const float4 g = *reinterpret_cast<const float4*>(sd + i * 32 + 4 * h);
+      float a[S], da[S];
+      float m = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < S; ++j) {
-          const float4 k = *reinterpret_cast<const float4*>(sq + j * 96 + 32 + 4 * h);
-          a[j] = (q.x * k.x + q.y * k.y + q.z * k.z + q.w * k.w) * scale;
-          m = fmaxf(m, a[j]);
-        }
-        float l = 0.f;
-#pragma unroll
-        for (int j = 0; j < S; ++j) { a[j] = expf(a[j] - m); l += a[j]; }
-        const float inv = 1.f / l;
-        float dot = 0.f;
-        float da[S];
-#pragma unroll
-        for (int j = 0; j < S; ++j) {
-          const float4 v = *reinterpret_cast<const float4*>(sq + j * 96 + 64 + 4 * h);
-          a[j] *= inv;
-          da[j] = g.x * v.x + g.y * v.y + g.z * v.z + g.w * v.w;
-          dot = fmaf(da[j], a[j], dot);
-        }
-        float4 dq = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int j = 0; j < S; ++j) {
-          const float ds = a[j] * (da[j] - dot);
-          const float4 k = *reinterpret_cast<const float4*>(sq + j * 96 + 32 + 4 * h);
-          dq.x = fmaf(ds, k.x, dq.x); dq.y = fmaf(ds, k.y, dq.y); dq.z = fmaf(ds, k.z, dq.z); dq.w = fmaf(ds, k.w, dq.w);
-          sa[lane * ST + j] = a[j];
-          sds[lane * ST + j] = ds;
-        }
-        *reinterpret_cast<float4*>(sg + lane * 96 + 4 * h) = make_float4(dq.x * scale, dq.y * scale, dq.z * scale, dq.w * scale);
+      for (int j = 0; j < S; ++j) {
+        a[j] = dot4(q, *reinterpret_cast<const float4*>(sq + j * 96 + 32 + 4 * h)) * scale;
+        m = fmaxf(m, a[j]);
+        UU_SA_FENCE(j);
       }
-      __syncwarp();
-      if (lane < S) {
-        float4 dk = make_float4(0.f, 0.f, 0.f, 0.f), dv = dk;
+      float l = 0.f;
 #pragma unroll
-        for (int i = 0; i < S; ++i) {
-          const float ds = sds[i * ST + lane], aa = sa[i * ST + lane];
-          const float4 q = *reinterpret_cast<const float4*>(sq + i * 96 + 4 * h);
-          const float4 g = *reinterpret_cast<const float4*>(sd + i * 32 + 4 * h);
-          dk.x = fmaf(ds, q.x, dk.x); dk.y = fmaf(ds, q.y, dk.y); dk.z = fmaf(ds, q.z, dk.z); dk.w = fmaf(ds, q.w, dk.w);
-          dv.x = fmaf(aa, g.x, dv.x); dv.y = fmaf(aa, g.y, dv.y); dv.z = fmaf(aa, g.z, dv.z); dv.w = fmaf(aa, g.w, dv.w);
-        }
-        *reinterpret_cast<float4*>(sg + lane * 96 + 32 + 4 * h) = make_float4(dk.x * scale, dk.y * scale, dk.z * scale, dk.w * scale);
-        *reinterpret_cast<float4*>(sg + lane * 96 + 64 + 4 * h) = dv;
+      for (int j = 0; j < S; ++j) { a[j] = __expf(a[j] - m); l += a[j]; }
+      const float inv = 1.f / l;
+      float dot = 0.f;
+#pragma unroll
+      for (int j = 0; j < S; ++j) {
+        da[j] = dot4(g, *reinterpret_cast<const float4*>(sq + j * 96 + 64 + 4 * h));
+        a[j] *= inv;
+        dot = fmaf(da[j], a[j], dot);
+        UU_SA_FENCE(j);
       }
-      __syncwarp();
+      float4 dq = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < S; ++j) {
+        const float ds = a[j] * (da[j] - dot);
+        const float4 k = *reinterpret_cast<const float4*>(sq + j * 96 + 32 + 4 * h);
+        dq.x = fmaf(ds, k.x, dq.x); dq.y = fmaf(ds, k.y, dq.y); dq.z = fmaf(ds, k.z, dq.z); dq.w = fmaf(ds, k.w, dq.w);
+        UU_SA_FENCE(j);
+      }
+      sst[item] = make_float4(m, inv, dot, 0.f);
+      *reinterpret_cast<float4*>(dst + i * 96 + 4 * h) = make_float4(dq.x * scale, dq.y * scale, dq.z * scale, dq.w * scale);
     }
-    float4* dst = reinterpret_cast<float4*>(dqkv + f * S * 96);
-    for (int i = lane; i < S * 24; i += 32) dst[i] = reinterpret_cast<const float4*>(sg)[i];
+    __syncwarp();
+    // ---- pass 2: pair = (key j, head h)
+#pragma unroll 1
+    for (int item = lane; item < S * 8; item += 32) {
+      const int j = item >> 3, h = item & 7;
+      const float4 k = *reinterpret_cast<const float4*>(sq + j * 96 + 32 + 4 * h);
+      const float4 v = *reinterpret_cast<const float4*>(sq + j * 96 + 64 + 4 * h);
+      float4 dk = make_float4(0.f, 0.f, 0.f, 0.f), dv = dk;
+#pragma unroll
+      for (int i = 0; i < S; ++i) {
+        const float4 q = *reinterpret_cast<const float4*>(sq + i * 96 + 4 * h);
+        const float4 g = *reinterpret_cast<const float4*>(sd + i * 32 + 4 * h);
+        const float4 st = sst[i * 8 + h];
+        const float aa = __expf(dot4(q, k) * scale - st.x) * st.y;      // same expression as pass 1: identical bits
+        const float ds = aa * (dot4(g, v) - st.z);
+        dk.x = fmaf(ds, q.x, dk.x); dk.y = fmaf(ds, q.y, dk.y); dk.z = fmaf(ds, q.z, dk.z); dk.w = fmaf(ds, q.w, dk.w);
+        dv.x = fmaf(aa, g.x, dv.x); dv.y = fmaf(aa, g.y, dv.y); dv.z = fmaf(aa, g.z, dv.z); dv.w = fmaf(aa, g.w, dv.w);
+        UU_SA_FENCE(i);
+      }
+      *reinterpret_cast<float4*>(dst + j * 96 + 32 + 4 * h) = make_float4(dk.x * scale, dk.y * scale, dk.z * scale, dk.w * scale);
+      *reinterpret_cast<float4*>(dst + j * 96 + 64 + 4 * h) = dv;
+    }
   }
 }
 bool attention_small_ok(int S, int heads, int dh, const uint8_t* mask) { return dh == 4 && heads == 8 && S == 17 && !mask; }
 cudaError_t launch_attention_small_fwd(const float* qkv, long long frames, int S, float* out, cudaStream_t st) {
   if (S != 17) return cudaErrorInvalidValue;
-  constexpr size_t smem = sizeof(float) * SA_WARPS * (17 * 96 + 17 * 32);
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(k_attn_small_fwd<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    attr = true;
-  }
   const unsigned grid = (unsigned)std::min<long long>((frames + SA_WARPS - 1) / SA_WARPS, 148 * 8);
-  k_attn_small_fwd<17><<<grid, SA_WARPS * 32, smem, st>>>(qkv, frames, out);
+  k_attn_small_fwd<17><<<grid, SA_WARPS * 32, 0, st>>>(qkv, frames, out);
   return cudaGetLastError();
 }
 cudaError_t launch_attention_small_bwd(const float* qkv, const float* dO, long long frames, int S, float* dqkv, cudaStream_t st) {
   if (S != 17) return cudaErrorInvalidValue;
-  constexpr size_t smem = sizeof(float) * SA_WARPS * ((17 * 96 * 2 + 17 * 32 + 2 * 17 * 17 + 3) & ~3);
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(k_attn_small_bwd<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    attr = true;
-  }
-  const unsigned grid = (unsigned)std::min<long long>((frames + SA_WARPS - 1) / SA_WARPS, 148 * 4);
-  k_attn_small_bwd<17><<<grid, SA_WARPS * 32, smem, st>>>(qkv, dO, frames, dqkv);
+  const unsigned grid = (unsigned)std::min<long long>((frames + SA_WARPS - 1) / SA_WARPS, 148 * 5);
+  k_attn_small_bwd<17><<<grid, SA_WARPS * 32, 0, st>>>(qkv, dO, frames, dqkv);
   return cudaGetLastError();
 }
 
@@ -1187,26 +1177,30 @@ cudaError_t launch_scatter_add(const float* src, const RowMap& dmap, long long r
 
 // Key-point embedding (K = 2): e[r][c] = x[r][0] W[0][c] + x[r][1] W[1][c] + b[c] + pe[r % J][c]  (net:321-323);
 // frames without 2-D input see zeros (the caller-side mask multiply, train.py:474).
-__global__ void k_embed_fwd(const float* __restrict__ x2d, const uint8_t* __restrict__ mask, int J, long long rows, int d,
-                            const float* __restrict__ Wk, const float* __restrict__ b, const float* __restrict__ pe,
-                            float* __restrict__ out) {
+// With `list` (the valid-frame gather list of the stride mask) output frame f reads input frame list[f]: the spatial stage of
+// the training step only runs on frames whose result survives the token fill (masked frames have zero gradient, net:350).
+__global__ void k_embed_fwd(const float* __restrict__ x2d, const uint8_t* __restrict__ mask, const int* __restrict__ list, int J,
+                            long long rows, int d, const float* __restrict__ Wk, const float* __restrict__ b,
+                            const float* __restrict__ pe, float* __restrict__ out) {
   const long long n = rows * d;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / d;
     const int c = (int)(i - r * d);
-    const bool ok = !mask || mask[r / J];
-    const float x0 = ok ? x2d[2 * r] : 0.f, x1 = ok ? x2d[2 * r + 1] : 0.f;
-    out[i] = (fmaf(x1, Wk[d + c], x0 * Wk[c]) + b[c]) + pe[(r % J) * d + c];
+    const long long f = r / J, j = r - f * J;
+    const long long sr = list ? (long long)list[f] * J + j : r;
+    const bool ok = list || !mask || mask[f];
+    const float x0 = ok ? x2d[2 * sr] : 0.f, x1 = ok ? x2d[2 * sr + 1] : 0.f;
+    out[i] = (fmaf(x1, Wk[d + c], x0 * Wk[c]) + b[c]) + pe[j * d + c];
   }
 }
-cudaError_t launch_embed_fwd(const float* x2d, const uint8_t* mask, int J, long long rows, int d, const float* Wk,
-                             const float* b, const float* pe, float* out, cudaStream_t st) {
+cudaError_t launch_embed_fwd(const float* x2d, const uint8_t* mask, const int* list, int J, long long rows, int d,
+                             const float* Wk, const float* b, const float* pe, float* out, cudaStream_t st) {
   if (rows == 0) return cudaSuccess;
-  k_embed_fwd<<<ew_grid(rows * d), 256, 0, st>>>(x2d, mask, J, rows, d, Wk, b, pe, out);
+  k_embed_fwd<<<ew_grid(rows * d), 256, 0, st>>>(x2d, mask, list, J, rows, d, Wk, b, pe, out);
   return cudaGetLastError();
 }
 // dW[k][c] += sum_r x[r][k] * de[r][c]   (k in {0,1})
-__global__ void k_embed_wgrad(const float* __restrict__ x2d, const uint8_t* __restrict__ mask, int J,
+__global__ void k_embed_wgrad(const float* __restrict__ x2d, const uint8_t* __restrict__ mask, const int* __restrict__ list, int J,
                               const float* __restrict__ de, long long rows, int d, float* __restrict__ dW) {
   const int c = threadIdx.x % d;
   const int sub = threadIdx.x / d, nsub = blockDim.x / d;
@@ -1214,10 +1208,12 @@ __global__ void k_embed_wgrad(const float* __restrict__ x2d, const uint8_t* __re
   const long long r0 = blockIdx.x * per, r1 = min(rows, r0 + per);
   float s0 = 0.f, s1 = 0.f;
   for (long long r = r0 + sub; r < r1; r += nsub) {
-    if (mask && !mask[r / J]) continue;
+    const long long f = r / J;
+    if (!list && mask && !mask[f]) continue;
+    const long long sr = list ? (long long)list[f] * J + (r - f * J) : r;
     const float g = de[r * d + c];
-    s0 = fmaf(x2d[2 * r], g, s0);
-    s1 = fmaf(x2d[2 * r + 1], g, s1);
+    s0 = fmaf(x2d[2 * sr], g, s0);
+    s1 = fmaf(x2d[2 * sr + 1], g, s1);
   }
   __shared__ float red[2][256];
   red[0][threadIdx.x] = s0; red[1][threadIdx.x] = s1;
@@ -1228,43 +1224,74 @@ __global__ void k_embed_wgrad(const float* __restrict__ x2d, const uint8_t* __re
     dW[(long long)blockIdx.x * 2 * d + d + c] = s1;
   }
 }
-cudaError_t launch_embed_wgrad(const float* x2d, const uint8_t* mask, int J, const float* de, long long rows, int d,
-                               float* dW, cudaStream_t st) {
+cudaError_t launch_embed_wgrad(const float* x2d, const uint8_t* mask, const int* list, int J, const float* de, long long rows,
+                               int d, float* dW, cudaStream_t st) {
   if (rows == 0) return cudaSuccess;
   if (256 % d) return cudaErrorInvalidValue;
   const unsigned grid = (unsigned)std::min<long long>(148 * 4, (rows + 255) / 256);
   if ((size_t)grid * 2 * d > g_red_floats) return cudaErrorInvalidValue;
-  k_embed_wgrad<<<grid, 256, 0, st>>>(x2d, mask, J, de, rows, d, g_red_scratch);
+  k_embed_wgrad<<<grid, 256, 0, st>>>(x2d, mask, list, J, de, rows, d, g_red_scratch);
   return reduce_partials((int)grid, 2LL * d, dW, 2LL * d, nullptr, st);
 }
 
 // Token fill (net:350-352), dense form used in training:
-//   x[r] = m ? s[r] : token ; x += pe[r % n_tok].  Backward: ds[r] = m ? dx[r] : 0.
-__global__ void k_fill_fwd(const float* __restrict__ s, const uint8_t* __restrict__ mask, const float* __restrict__ token,
-                           const float* __restrict__ pe, int n_tok, long long rows, int d, float* __restrict__ x) {
+//   x[r] = m ? keep[r] * s[pos[r]] : token ; x += pe[r % n_tok].  Backward: ds[i] = keep[list[i]] * dx[list[i]].
+// `pos` maps a token row to its row in the compact (valid frames only) output of the spatial stage and `list` is its
+// inverse; both null: s / ds are dense (models without a stride mask).  `keep` = the random token-masking factors
+// (net:336-338), null when TOKEN_MASK_RATE is 0.
+__global__ void k_fill_fwd(const float* __restrict__ s, const uint8_t* __restrict__ mask, const int* __restrict__ pos,
+                           const float* __restrict__ keep, const float* __restrict__ token, const float* __restrict__ pe,
+                           int n_tok, long long rows, int d, float* __restrict__ x) {
   const long long n = rows * d;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / d;
     const int c = (int)(i - r * d);
-    const float v = (!mask || mask[r]) ? s[i] : token[c];
+    float v;
+    if (!mask || mask[r]) v = s[(pos ? (long long)pos[r] : r) * d + c] * (keep ? keep[r] : 1.f);
+    else v = token[c];
     x[i] = v + pe[(r % n_tok) * d + c];
   }
 }
-__global__ void k_fill_bwd(const float* __restrict__ dx, const uint8_t* __restrict__ mask, long long rows, int d,
-                           float* __restrict__ ds) {
+// rows = rows of ds: the compact count with a list, all token rows otherwise
+__global__ void k_fill_bwd(const float* __restrict__ dx, const uint8_t* __restrict__ mask, const int* __restrict__ list,
+                           const float* __restrict__ keep, long long rows, int d, float* __restrict__ ds) {
   const long long n = rows * d;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    ds[i] = (!mask || mask[i / d]) ? dx[i] : 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / d;
+    const long long sr = list ? (long long)list[r] : r;
+    const float v = (list || !mask || mask[sr]) ? dx[sr * d + (i - r * d)] : 0.f;
+    ds[i] = v * (keep ? keep[sr] : 1.f);
+  }
 }
-cudaError_t launch_fill_fwd(const float* s, const uint8_t* mask, const float* token, const float* pe, int n_tok,
-                            long long rows, int d, float* x, cudaStream_t st) {
+cudaError_t launch_fill_fwd(const float* s, const uint8_t* mask, const int* pos, const float* keep, const float* token,
+                            const float* pe, int n_tok, long long rows, int d, float* x, cudaStream_t st) {
   if (rows == 0) return cudaSuccess;
-  k_fill_fwd<<<ew_grid(rows * d), 256, 0, st>>>(s, mask, token, pe, n_tok, rows, d, x);
+  k_fill_fwd<<<ew_grid(rows * d), 256, 0, st>>>(s, mask, pos, keep, token, pe, n_tok, rows, d, x);
   return cudaGetLastError();
 }
-cudaError_t launch_fill_bwd(const float* dx, const uint8_t* mask, long long rows, int d, float* ds, cudaStream_t st) {
+cudaError_t launch_fill_bwd(const float* dx, const uint8_t* mask, const int* list, const float* keep, long long rows, int d,
+                            float* ds, cudaStream_t st) {
   if (rows == 0) return cudaSuccess;
-  k_fill_bwd<<<ew_grid(rows * d), 256, 0, st>>>(dx, mask, rows, d, ds);
+  k_fill_bwd<<<ew_grid(rows * d), 256, 0, st>>>(dx, mask, list, keep, rows, d, ds);
+  return cudaGetLastError();
+}
+// pos[list[i]] = i (inverse of the gather list) and dst[i] = src[list[i]] (per-frame stochastic-depth factors -> compact order)
+__global__ void k_invert_list(const int* __restrict__ list, int n, int* __restrict__ pos) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) pos[list[i]] = i;
+}
+__global__ void k_gather_f32(const float* __restrict__ src, const int* __restrict__ list, int n, float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[list[i]];
+}
+cudaError_t launch_invert_list(const int* list, int n, int* pos, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  k_invert_list<<<(n + 255) / 256, 256, 0, st>>>(list, n, pos);
+  return cudaGetLastError();
+}
+cudaError_t launch_gather_f32(const float* src, const int* list, int n, float* dst, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  k_gather_f32<<<(n + 255) / 256, 256, 0, st>>>(src, list, n, dst);
   return cudaGetLastError();
 }
 

@@ -19,6 +19,9 @@ struct BlkTape {   // saved activations of one transformer block
   // stochastic depth: the reference calls drop_path_layer twice per block (vit:185-190, net:131-135), each call with
   // its own tf.random.uniform draw, so the attention branch and the MLP branch are dropped independently
   float *scale = nullptr, *scale2 = nullptr;      // per-sample factors of the attention / MLP branch
+  // spatial blocks of a strided-input model run on the valid frames only: the draws are made per frame of the full batch
+  // (what uu_get_droppath_scale reports) and gathered into scale / scale2 in compact order
+  float *scale_full = nullptr, *scale2_full = nullptr;
   float keep = 1.f;
 };
 
@@ -47,6 +50,7 @@ struct TrainState {
   float token_mask_rate = 0.f;                  // TOKEN_MASK_RATE (net:287-311; masked value 0), training only
   float* tok_keep = nullptr;                    // [R] 0 / 1 factors drawn for the current step
   int math = 0;
+  int *gl_scratch = nullptr, *gl_list = nullptr, *gl_pos = nullptr, *gl_count = nullptr;   // valid-frame gather list (stride mask)
   int attn_split = 3;                           // attn_mma.cu: 3 = compensated TF32 (fp32-grade), 1 = plain TF32
   float* wg_scratch = nullptr;                  // split-K partial tiles of the tensor-core wgrad (wgrad_tc.cu)
   float* red_scratch = nullptr;                 // partial slabs of the deterministic two-pass reductions (train_kernels.cu)
@@ -401,6 +405,19 @@ static int ensure_train(uu_model* m, int B) {
     return 1;
   if (falloc(t, &t->partials, loss_blocks(B, (int)N, (int)J, true) + 8) || falloc(t, &t->loss, 4)) return 1;
   if (falloc(t, &t->tok_keep, R)) return 1;
+  if (s.has_strided_input) {
+    float* q;
+    if (falloc(t, &q, (size_t)B + 2)) return 1;
+    t->gl_scratch = reinterpret_cast<int*>(q);
+    if (falloc(t, &q, R)) return 1;
+    t->gl_list = reinterpret_cast<int*>(q);
+    if (falloc(t, &q, R)) return 1;
+    t->gl_pos = reinterpret_cast<int*>(q);
+    if (falloc(t, &q, 4)) return 1;
+    t->gl_count = reinterpret_cast<int*>(q);
+    for (int i = 0; i < s.spatial_depth; ++i)
+      if (falloc(t, &t->sp[i].scale_full, R) || falloc(t, &t->sp[i].scale2_full, R)) return 1;
+  }
   if (falloc(t, &t->wg_scratch, wgrad_tc_scratch_bytes() / sizeof(float))) return 1;
   if (falloc(t, &t->red_scratch, train_reduce_scratch_floats() + 4096)) return 1;
   t->B = B;
@@ -434,6 +451,21 @@ static int train_fb(uu_model* m, const float* x2d, const uint8_t* mask, const fl
   const RowMap plain;
   UU_CUDA(cudaMemsetAsync(m->grads, 0, sizeof(float) * m->n_alloc, stream));
 
+  // Frames the stride mask drops never influence the loss (their spatial result is replaced by the upsampling token,
+  // net:350-352) and receive a zero gradient: the spatial stage runs on the Rv valid frames only, in gather-list order.
+  long long Rv = R;
+  const int *glist = nullptr, *gpos = nullptr;
+  if (use_mask) {
+    UU_TL(launch_build_gather(mask, B, N, t->gl_scratch, t->gl_list, t->gl_count, stream));
+    int nv = 0;
+    UU_CUDA(cudaMemcpyAsync(&nv, t->gl_count, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    UU_CUDA(cudaStreamSynchronize(stream));            // (the launch sizes of the spatial stage depend on the count)
+    Rv = nv;
+    glist = t->gl_list; gpos = t->gl_pos;
+    UU_TL(launch_invert_list(glist, (int)Rv, t->gl_pos, stream));
+  }
+  const long long Rsv = Rv * J;
+
   // stochastic-depth factors for this step
   for (int stage = 0; stage < 3; ++stage) {
     std::vector<BlkTape>& tapes = stage == 0 ? t->sp : stage == 1 ? t->tp : t->st;
@@ -441,31 +473,47 @@ static int train_fb(uu_model* m, const float* x2d, const uint8_t* mask, const fl
     for (size_t i = 0; i < tapes.size(); ++i) {
       tapes[i].keep = block_keep(t, stage, (int)i, (int)tapes.size());
       if (tapes[i].keep < 1.f) {      // two independent draws per block: RNG stream ids 2i (attention) and 2i + 1 (MLP)
+        const bool compact = stage == 0 && glist;
         UU_TL(launch_droppath_scale(t->seed, (unsigned long long)step * 64ULL + stage * 16 + 2 * i, ns, tapes[i].keep,
-                                    tapes[i].scale, stream));
+                                    compact ? tapes[i].scale_full : tapes[i].scale, stream));
         UU_TL(launch_droppath_scale(t->seed, (unsigned long long)step * 64ULL + stage * 16 + 2 * i + 1, ns, tapes[i].keep,
-                                    tapes[i].scale2, stream));
+                                    compact ? tapes[i].scale2_full : tapes[i].scale2, stream));
+        if (compact) {
+          UU_TL(launch_gather_f32(tapes[i].scale_full, glist, (int)Rv, tapes[i].scale, stream));
+          UU_TL(launch_gather_f32(tapes[i].scale2_full, glist, (int)Rv, tapes[i].scale2, stream));
+        }
       }
     }
   }
 
   // ================= forward =================
-  UU_TL(launch_embed_fwd(x2d, use_mask ? mask : nullptr, J, Rs, ds, W(m, "keypoint_embedding", 0),
+  UU_TL(launch_embed_fwd(x2d, use_mask ? mask : nullptr, glist, J, Rsv, ds, W(m, "keypoint_embedding", 0),
                          W(m, "keypoint_embedding", 1), W(m, "spatial_pe", 0), t->sp[0].x0, stream));
-  const BlkDims sp_dims{ds, s.h_spatial, J, H, R, 1};
-  for (int i = 0; i < s.spatial_depth; ++i)
-    if (block_fwd(c, sp_dims, "spatial_block_" + std::to_string(i + 1), t->sp[i], nullptr, 0)) return 1;
+  const BlkDims sp_dims{ds, s.h_spatial, J, H, Rv, 1};
+  for (int i = 0; i < s.spatial_depth; ++i) {
+    const std::string g = "spatial_block_" + std::to_string(i + 1);
+    BlkTape& tp = t->sp[i];
+    if (spatial_block_fused_ok(J, ds, s.h_spatial, H, sp_dims.act)) {     // one launch per block (spatial_train.cu)
+      const float* wl[16];
+      for (int k = 0; k < 16; ++k) wl[k] = W(m, g, k);
+      UU_TL(launch_spatial_block_fwd_tape(tp.x0, wl, tp.keep < 1.f ? tp.scale : nullptr, tp.keep < 1.f ? tp.scale2 : nullptr, Rv,
+                                          tp.y1, tp.qkv, tp.o, tp.x1, tp.y2, tp.hpre, tp.hact, tp.x2, m->num_sms, stream));
+    } else if (block_fwd(c, sp_dims, g, tp, nullptr, 0)) {
+      return 1;
+    }
+  }
   float* sp_out = t->sp[s.spatial_depth - 1].x2;
-  UU_TL(launch_ln_fwd_gen(sp_out, Rs, ds, W(m, "spatial_norm", 0), W(m, "spatial_norm", 1), 1e-6f, t->sp_normed, stream));
-  if (lin_fwd(c, t->sp_normed, J * ds, (int)R, J * ds, W(m, "spatial_to_temporal_fc", 0), d,
+  UU_TL(launch_ln_fwd_gen(sp_out, Rsv, ds, W(m, "spatial_norm", 0), W(m, "spatial_norm", 1), 1e-6f, t->sp_normed, stream));
+  if (lin_fwd(c, t->sp_normed, J * ds, (int)Rv, J * ds, W(m, "spatial_to_temporal_fc", 0), d,
               W(m, "spatial_to_temporal_fc", 1), t->s4, d))
     return 1;
+  const float* tok_keep = nullptr;
   if (t->token_mask_rate > 0.f) {   // random token masking (net:336-338) before the upsampling-token fill and the PE add
     UU_TL(launch_token_mask_draw(t->seed, (unsigned long long)step * 64ULL + 63ULL, R, N, t->token_mask_rate, t->tok_keep,
                                  stream));
-    UU_TL(launch_scale_rows(t->s4, t->tok_keep, 1, R, d, t->s4, stream));
+    tok_keep = t->tok_keep;         // applied inside the fill (forward) and the gather of its gradient (backward)
   }
-  UU_TL(launch_fill_fwd(t->s4, use_mask ? mask : nullptr, use_mask ? W(m, "strided_input_token_layer", 0) : nullptr,
+  UU_TL(launch_fill_fwd(t->s4, use_mask ? mask : nullptr, gpos, tok_keep, use_mask ? W(m, "strided_input_token_layer", 0) : nullptr,
                         W(m, "temporal_pe", 0), N, R, d, t->tp[0].x0, stream));
   const BlkDims tp_dims{d, h, N, H, (long long)B, 0};
   for (int i = 0; i < s.temporal_depth; ++i) {
@@ -563,19 +611,19 @@ static int train_fb(uu_model* m, const float* x2d, const uint8_t* mask, const fl
   UU_TL(launch_period_sum(t->dx_t, R, N, d, nullptr, 0, G(m, "temporal_pe", 0), stream));
   if (use_mask) {
     UU_TL(launch_period_sum(t->dx_t, R, 1, d, mask, 0, G(m, "strided_input_token_layer", 0), stream));
-    UU_TL(launch_fill_bwd(t->dx_t, mask, R, d, t->dx_t, stream));
   }
-  if (t->token_mask_rate > 0.f) UU_TL(launch_scale_rows(t->dx_t, t->tok_keep, 1, R, d, t->dx_t, stream));
-  if (lin_bwd(c, t->sp_normed, J * ds, t->dx_t, d, (int)R, J * ds, d, W(m, "spatial_to_temporal_fc", 0), t->dS, J * ds, 0,
+  // gradient of the compact spatial_to_temporal_fc output: rows of dx_t in gather-list order (x token-masking factors)
+  UU_TL(launch_fill_bwd(t->dx_t, use_mask ? mask : nullptr, glist, tok_keep, Rv, d, t->tmp1, stream));
+  if (lin_bwd(c, t->sp_normed, J * ds, t->tmp1, d, (int)Rv, J * ds, d, W(m, "spatial_to_temporal_fc", 0), t->dS, J * ds, 0,
               G(m, "spatial_to_temporal_fc", 0), G(m, "spatial_to_temporal_fc", 1)))
     return 1;
-  UU_TL(launch_ln_bwd_gen(sp_out, t->dS, Rs, ds, W(m, "spatial_norm", 0), 1e-6f, t->dx_sp, 0, G(m, "spatial_norm", 0),
+  UU_TL(launch_ln_bwd_gen(sp_out, t->dS, Rsv, ds, W(m, "spatial_norm", 0), 1e-6f, t->dx_sp, 0, G(m, "spatial_norm", 0),
                           G(m, "spatial_norm", 1), stream));
   for (int i = s.spatial_depth - 1; i >= 0; --i)
     if (block_bwd(c, sp_dims, "spatial_block_" + std::to_string(i + 1), t->sp[i], nullptr, 0, t->dx_sp)) return 1;
-  UU_TL(launch_colsum(t->dx_sp, (int)Rs, ds, ds, G(m, "keypoint_embedding", 1), stream));
-  UU_TL(launch_period_sum(t->dx_sp, Rs, J, ds, nullptr, 0, G(m, "spatial_pe", 0), stream));
-  UU_TL(launch_embed_wgrad(x2d, use_mask ? mask : nullptr, J, t->dx_sp, Rs, ds, G(m, "keypoint_embedding", 0), stream));
+  UU_TL(launch_colsum(t->dx_sp, (int)Rsv, ds, ds, G(m, "keypoint_embedding", 1), stream));
+  UU_TL(launch_period_sum(t->dx_sp, Rsv, J, ds, nullptr, 0, G(m, "spatial_pe", 0), stream));
+  UU_TL(launch_embed_wgrad(x2d, use_mask ? mask : nullptr, glist, J, t->dx_sp, Rsv, ds, G(m, "keypoint_embedding", 0), stream));
   if (overlap_comm) {
     if (comm_allreduce_range(m, 0, off_temporal, 2, stream)) return 1;
     if (comm_allreduce_scalar(m, loss_out, stream)) return 1;
@@ -702,7 +750,9 @@ int uu_get_droppath_scale(uu_model* m, int stage, int block, int branch, float* 
   *keep_prob = tapes[block].keep;
   UU_CUDA(cudaSetDevice(m->device));
   if (tapes[block].keep < 1.f) {
-    UU_CUDA(cudaMemcpy(host, branch ? tapes[block].scale2 : tapes[block].scale, sizeof(float) * ns, cudaMemcpyDeviceToHost));
+    const BlkTape& bt = tapes[block];
+    const float* src = branch ? (bt.scale2_full ? bt.scale2_full : bt.scale2) : (bt.scale_full ? bt.scale_full : bt.scale);
+    UU_CUDA(cudaMemcpy(host, src, sizeof(float) * ns, cudaMemcpyDeviceToHost));
   } else {
     for (long long i = 0; i < ns; ++i) host[i] = 1.f;
   }
