@@ -225,8 +225,9 @@ int uu_op_attention(const void* qkv, int is_bf16, int B, int S, int heads, int d
 int uu_op_attention_tc5(const void* qkv, int B, int S, const uint8_t* keep_mask, int mask_stride, void* out, void* stream);
 /* Attention of the training step (vit:99-130 and its gradient) on mma.sync TF32 with fp32 rows as the tape holds them:
  * qkv (B * S, 3 * heads * dh), keep_mask as uu_op_attention.  dO == NULL: forward into out (B * S, heads * dh);
- * otherwise backward: dqkv (B * S, 3 * heads * dh) from dO (B * S, heads * dh).  nsplit 3 = error-compensated TF32
- * (hi / lo operand split, fp32-grade), 1 = plain TF32.  S <= 80, dh in {32, 48, 64}. */
+ * otherwise backward: dqkv (B * S, 3 * heads * dh) from dO (B * S, heads * dh).  nsplit 2 = bf16 hi + lo operand planes on
+ * m16n8k16 (16 mantissa bits per operand; what uu_train_step uses), 3 = error-compensated TF32 (hi / lo operand split,
+ * fp32-grade), 1 = plain TF32.  S <= 80, dh in {32, 48, 64}. */
 int uu_op_attention_train(const float* qkv, const float* dO, int B, int S, int heads, int dh, const uint8_t* keep_mask,
                           int mask_stride, float* out, float* dqkv, int nsplit, void* stream);
 /* C = act(A @ W + bias) (+ res); flags: 1 = ReLU, 2 = residual.  fp32 CUDA-core GEMM, W is (K, N). */

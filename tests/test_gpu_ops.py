@@ -174,11 +174,12 @@ def test_attention_tcgen05(lib, S, B, masked):
                                              (24, 9, 8, 48, False), (8, 17, 8, 48, False), (3, 4, 8, 48, False),
                                              (80, 2, 8, 48, True), (1, 5, 8, 48, False), (30, 3, 4, 32, True),
                                              (71, 2, 8, 64, True)])
-@pytest.mark.parametrize("nsplit", [3, 1])
+@pytest.mark.parametrize("nsplit", [2, 3, 1])
 def test_attention_train_mma(lib, S, B, H, dh, masked, nsplit):
     """attn_mma.cu (training step, vit:99-130 and its gradient): forward and backward on mma.sync TF32 against a float64
-    autograd evaluation of the same lines.  nsplit = 3 (hi / lo operand split) must be fp32-grade: 2e-5 of the tensor
-    scale; nsplit = 1 (plain TF32, 10-bit operands) 1e-2.  All-masked windows give uniform attention (-1e9 term)."""
+    autograd evaluation of the same lines.  nsplit = 3 (TF32 hi / lo operand split) must be fp32-grade: 2e-5 of the tensor
+    scale; nsplit = 2 (bf16 hi + lo planes, 16 mantissa bits per operand: the training default) 2e-4; nsplit = 1 (plain TF32,
+    10-bit operands) 1e-2.  All-masked windows give uniform attention (-1e9 term)."""
     rng = np.random.default_rng(S * 7 + B)
     d = H * dh
     qkv = rng.normal(size=(B, S, 3 * d)).astype(np.float32)
@@ -212,7 +213,7 @@ def test_attention_train_mma(lib, S, B, H, dh, masked, nsplit):
     e_f = np.abs(got - want).max() / np.abs(want).max()
     e_b = np.abs(got_g - want_g).max() / np.abs(want_g).max()
     print(f"mma attention S={S} B={B} dh={dh} nsplit={nsplit}: fwd {e_f:.2e} bwd {e_b:.2e} (relative to the tensor max)")
-    tol = 2e-5 if nsplit == 3 else 1e-2
+    tol = {3: 2e-5, 2: 2e-4, 1: 1e-2}[nsplit]
     assert e_f < tol and e_b < tol, (e_f, e_b)
 
 

@@ -1185,11 +1185,11 @@ int uu_op_attention_tc5(const void* qkv, int B, int S, const uint8_t* keep_mask,
   return 0;
 }
 /* Attention of the training step on mma.sync TF32 (attn_mma.cu), fp32 rows.  dO == NULL: forward, out (B * S, heads * dh);
- * otherwise backward, dqkv (B * S, 3 * heads * dh).  nsplit 3 = compensated TF32 (fp32-grade), 1 = plain TF32. */
+ * otherwise backward, dqkv (B * S, 3 * heads * dh).  nsplit 2 = bf16 hi + lo planes, 3 = compensated TF32, 1 = plain TF32. */
 int uu_op_attention_train(const float* qkv, const float* dO, int B, int S, int heads, int dh, const uint8_t* keep_mask,
                           int mask_stride, float* out, float* dqkv, int nsplit, void* stream) {
   UU_CHECK(qkv && B > 0 && attention_mma_ok(B, S, heads, dh), "uu_op_attention_train: 1 <= S <= 80, head dimension 32 / 48 / 64");
-  UU_CHECK(nsplit == 1 || nsplit == 3, "uu_op_attention_train: nsplit is 1 or 3");
+  UU_CHECK(nsplit >= 1 && nsplit <= 3, "uu_op_attention_train: nsplit is 1, 2 or 3");
   if (!dO) {
     UU_CHECK(out, "uu_op_attention_train: forward needs out");
     UU_CUDA(launch_attention_mma_fwd(qkv, B, S, heads, dh, keep_mask, mask_stride, out, nsplit, (cudaStream_t)stream));

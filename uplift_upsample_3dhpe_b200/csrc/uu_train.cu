@@ -51,7 +51,7 @@ struct TrainState {
   float* tok_keep = nullptr;                    // [R] 0 / 1 factors drawn for the current step
   int math = 0;
   int *gl_scratch = nullptr, *gl_list = nullptr, *gl_pos = nullptr, *gl_count = nullptr;   // valid-frame gather list (stride mask)
-  int attn_split = 3;                           // attn_mma.cu: 3 = compensated TF32 (fp32-grade), 1 = plain TF32
+  int attn_split = 2;                           // attn_mma.cu: 2 = bf16 hi + lo planes (2^-16 per product), 3 = compensated TF32, 1 = TF32
   float* wg_scratch = nullptr;                  // split-K partial tiles of the tensor-core wgrad (wgrad_tc.cu)
   float* red_scratch = nullptr;                 // partial slabs of the deterministic two-pass reductions (train_kernels.cu)
   struct PackedQkv { float *W = nullptr, *b = nullptr, *dW = nullptr, *db = nullptr; };
@@ -223,6 +223,7 @@ static int lin_bwd(Ctx& c, const float* X, long long ldx, const float* dY, long 
     if (dxmap) g.cmap = *dxmap;
     UU_TL(launch_gemm_gen(g, c.st));
   }
+  if (!dW) return 0;                                    // input gradient only (the caller takes the weight gradients)
   if (wgrad_skinny_ok(X, ldx, dY, ldy, M, K, N) && db) {
     // narrow layers of the spatial blocks: one streaming pass gives dW and db (train_kernels.cu)
     UU_TL(launch_wgrad_skinny(X, ldx, dY, ldy, M, K, N, dW, db, c.st));
@@ -301,10 +302,16 @@ static int attn_half_bwd(Ctx& c, const BlkDims& b, const std::string& g, BlkTape
     UU_TL(launch_attention_bwd(tp.qkv, t->tmp2, b.nb, b.S, b.heads, d / b.heads, keymask, mask_stride, t->tmp_qkv, c.st));
   TrainState::PackedQkv pq;
   if (packed_qkv(c, g, d, &pq)) return 1;
-  UU_CUDA(cudaMemsetAsync(pq.dW, 0, sizeof(float) * (size_t)d * 3 * d, c.st));
-  UU_CUDA(cudaMemsetAsync(pq.db, 0, sizeof(float) * 3 * (size_t)d, c.st));
-  if (lin_bwd(c, tp.y1, d, t->tmp_qkv, 3 * d, (int)R, d, 3 * d, pq.W, t->tmp2, d, 0, pq.dW, pq.db)) return 1;
-  {
+  if (wgrad_skinny_ok(tp.y1, d, t->tmp_qkv, 3 * d, R, d, d)) {
+    // narrow (spatial) layers: packed input gradient, but the one-pass dW / db kernel per tensor (its 32 x 96 instantiation
+    // holds 96 accumulators per thread and runs at half the speed of three 32 x 32 passes)
+    if (lin_bwd(c, tp.y1, d, t->tmp_qkv, 3 * d, (int)R, d, 3 * d, pq.W, t->tmp2, d, 0, nullptr, nullptr)) return 1;
+    for (int k = 0; k < 3; ++k)
+      UU_TL(launch_wgrad_skinny(tp.y1, d, t->tmp_qkv + k * d, 3 * d, R, d, d, G(m, g, 2 + 2 * k), G(m, g, 3 + 2 * k), c.st));
+  } else {
+    UU_CUDA(cudaMemsetAsync(pq.dW, 0, sizeof(float) * (size_t)d * 3 * d, c.st));
+    UU_CUDA(cudaMemsetAsync(pq.db, 0, sizeof(float) * 3 * (size_t)d, c.st));
+    if (lin_bwd(c, tp.y1, d, t->tmp_qkv, 3 * d, (int)R, d, 3 * d, pq.W, t->tmp2, d, 0, pq.dW, pq.db)) return 1;
     const int n = d * 3 * d + 3 * d;
     k_unpack_qkv_add<<<std::min(148 * 4, (n + 255) / 256), 256, 0, c.st>>>(pq.dW, pq.db, d, G(m, g, 2), G(m, g, 4), G(m, g, 6),
                                                                          G(m, g, 3), G(m, g, 5), G(m, g, 7));
@@ -692,8 +699,6 @@ int uu_train_set_math(uu_model* m, int mode) {
   UU_CHECK(m && (mode == 0 || mode == 1), "math mode: 0 = fp32, 1 = tf32 tensor cores");
   if (!m->train) m->train = new TrainState();
   m->train->math = mode;
-  m->train->attn_split = 3;
-  if (const char* e = getenv("UU_ATTN_SPLIT_TMP")) m->train->attn_split = atoi(e) == 1 ? 1 : 3;   // TEMPORARY (measurement)
   return 0;
 }
 
