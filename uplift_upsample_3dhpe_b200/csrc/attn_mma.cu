@@ -112,16 +112,23 @@ __device__ __forceinline__ void gemm_pb(float (&c)[DH / 8][4], const float (&p)[
   }
 }
 
-// rows [0, S) of one head's slice -> shared memory, rows [S, SP) zero
-template <int DH>
-__device__ __forceinline__ void stage_rows(float* __restrict__ dst, const float* __restrict__ src, long long ld, int S, int SP,
-                                           int tid, int nt) {
-  constexpr int LD = DH + 4;
-  for (int i = tid; i < SP * (DH / 4); i += nt) {
-    const int j = i / (DH / 4), c = (i - j * (DH / 4)) * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (j < S) v = *reinterpret_cast<const float4*>(src + (long long)j * ld + c);
-    *reinterpret_cast<float4*>(dst + j * LD + c) = v;
+// rows [0, S) of one head's slice -> shared memory, rows [S, SP) zero.  The trip count is a compile-time constant and ALL
+// loads of the array are issued before the first store: with a rolled loop every iteration waited for its own global
+// load (24 serialised DRAM latencies per CTA, which made the kernel latency-bound at three CTAs per SM).
+template <int DH, int SP, int NTHR>
+__device__ __forceinline__ void stage_rows(float* __restrict__ dst, const float* __restrict__ src, long long ld, int S, int tid) {
+  constexpr int LD = DH + 4, TOT = SP * (DH / 4), IT = (TOT + NTHR - 1) / NTHR;
+  float4 v[IT];
+#pragma unroll
+  for (int u = 0; u < IT; ++u) {
+    const int i = tid + u * NTHR, j = i / (DH / 4), c = (i - j * (DH / 4)) * 4;
+    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < TOT && j < S) v[u] = *reinterpret_cast<const float4*>(src + (long long)j * ld + c);
+  }
+#pragma unroll
+  for (int u = 0; u < IT; ++u) {
+    const int i = tid + u * NTHR, j = i / (DH / 4), c = (i - j * (DH / 4)) * 4;
+    if (i < TOT) *reinterpret_cast<float4*>(dst + j * LD + c) = v[u];
   }
 }
 
@@ -173,9 +180,9 @@ __global__ void __launch_bounds__(32 * warps_for(NT)) k_attn_mma_fwd(const float
   const int d = heads * DH;
   const long long row0 = (long long)b * S;
   const float* base = qkv + row0 * 3 * d + h * DH;
-  stage_rows<DH>(Qs, base, 3 * d, S, SP, tid, 32 * NW);
-  stage_rows<DH>(Ks, base + d, 3 * d, S, SP, tid, 32 * NW);
-  stage_rows<DH>(Vs, base + 2 * d, 3 * d, S, SP, tid, 32 * NW);
+  stage_rows<DH, SP, 32 * NW>(Qs, base, 3 * d, S, tid);
+  stage_rows<DH, SP, 32 * NW>(Ks, base + d, 3 * d, S, tid);
+  stage_rows<DH, SP, 32 * NW>(Vs, base + 2 * d, 3 * d, S, tid);
   for (int j = tid; j < SP; j += 32 * NW)
     Km[j] = j >= S ? -INFINITY : ((mask && !mask[(long long)b * mask_stride + j]) ? -1e9f : 0.f);
   __syncthreads();
@@ -214,10 +221,10 @@ __global__ void __launch_bounds__(32 * warps_for(NT)) k_attn_mma_bwd(const float
   const int d = heads * DH;
   const long long row0 = (long long)b * S;
   const float* base = qkv + row0 * 3 * d + h * DH;
-  stage_rows<DH>(Qs, base, 3 * d, S, SP, tid, 32 * NW);
-  stage_rows<DH>(Ks, base + d, 3 * d, S, SP, tid, 32 * NW);
-  stage_rows<DH>(Vs, base + 2 * d, 3 * d, S, SP, tid, 32 * NW);
-  stage_rows<DH>(Gs, dO + row0 * d + h * DH, d, S, SP, tid, 32 * NW);
+  stage_rows<DH, SP, 32 * NW>(Qs, base, 3 * d, S, tid);
+  stage_rows<DH, SP, 32 * NW>(Ks, base + d, 3 * d, S, tid);
+  stage_rows<DH, SP, 32 * NW>(Vs, base + 2 * d, 3 * d, S, tid);
+  stage_rows<DH, SP, 32 * NW>(Gs, dO + row0 * d + h * DH, d, S, tid);
   for (int j = tid; j < SP; j += 32 * NW)
     Km[j] = j >= S ? -INFINITY : ((mask && !mask[(long long)b * mask_stride + j]) ? -1e9f : 0.f);
   __syncthreads();
@@ -385,20 +392,29 @@ __device__ __forceinline__ float quad_max(float v) {
 }
 template <int DH> struct Lay { static constexpr int LDW = DH / 2 + 4; };     // row stride of a plane in 32-bit words
 
-// rows [0, S) of one head's slice -> hi / lo planes, rows [S, SP) zero
-template <int DH>
+// rows [0, S) of one head's slice -> hi / lo planes, rows [S, SP) zero (all loads in flight before the first store, see
+// stage_rows above)
+template <int DH, int SP, int NTHR>
 __device__ __forceinline__ void stage_planes(uint32_t* __restrict__ hi, uint32_t* __restrict__ lo, const float* __restrict__ src,
-                                             long long ld, int S, int SP, int tid, int nt) {
-  constexpr int LDW = Lay<DH>::LDW;
-  for (int i = tid; i < SP * (DH / 4); i += nt) {
-    const int j = i / (DH / 4), c = (i - j * (DH / 4)) * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (j < S) v = *reinterpret_cast<const float4*>(src + (long long)j * ld + c);
-    uint2 h, l;
-    pack_hi_lo(v.x, v.y, h.x, l.x);
-    pack_hi_lo(v.z, v.w, h.y, l.y);
-    *reinterpret_cast<uint2*>(hi + j * LDW + c / 2) = h;
-    *reinterpret_cast<uint2*>(lo + j * LDW + c / 2) = l;
+                                             long long ld, int S, int tid) {
+  constexpr int LDW = Lay<DH>::LDW, TOT = SP * (DH / 4), IT = (TOT + NTHR - 1) / NTHR;
+  float4 v[IT];
+#pragma unroll
+  for (int u = 0; u < IT; ++u) {
+    const int i = tid + u * NTHR, j = i / (DH / 4), c = (i - j * (DH / 4)) * 4;
+    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < TOT && j < S) v[u] = *reinterpret_cast<const float4*>(src + (long long)j * ld + c);
+  }
+#pragma unroll
+  for (int u = 0; u < IT; ++u) {
+    const int i = tid + u * NTHR, j = i / (DH / 4), c = (i - j * (DH / 4)) * 4;
+    if (i < TOT) {
+      uint2 h, l;
+      pack_hi_lo(v[u].x, v[u].y, h.x, l.x);
+      pack_hi_lo(v[u].z, v[u].w, h.y, l.y);
+      *reinterpret_cast<uint2*>(hi + j * LDW + c / 2) = h;
+      *reinterpret_cast<uint2*>(lo + j * LDW + c / 2) = l;
+    }
   }
 }
 // c[n] (+)= A B^T : A = 16 rows starting at `ah` / `al` (this warp's tile of a plane pair), B = rows 8n .. 8n+7 of (bh, bl)
@@ -492,9 +508,9 @@ __global__ void __launch_bounds__(32 * warps_for(NT)) k_attn_bf2_fwd(const float
   const int d = heads * DH;
   const long long row0 = (long long)b * S;
   const float* base = qkv + row0 * 3 * d + h * DH;
-  stage_planes<DH>(Qh, Ql, base, 3 * d, S, SP, tid, 32 * NW);
-  stage_planes<DH>(Kh, Kl, base + d, 3 * d, S, SP, tid, 32 * NW);
-  stage_planes<DH>(Vh, Vl, base + 2 * d, 3 * d, S, SP, tid, 32 * NW);
+  stage_planes<DH, SP, 32 * NW>(Qh, Ql, base, 3 * d, S, tid);
+  stage_planes<DH, SP, 32 * NW>(Kh, Kl, base + d, 3 * d, S, tid);
+  stage_planes<DH, SP, 32 * NW>(Vh, Vl, base + 2 * d, 3 * d, S, tid);
   for (int j = tid; j < SP; j += 32 * NW)
     Km[j] = j >= S ? -INFINITY : ((mask && !mask[(long long)b * mask_stride + j]) ? -1e9f : 0.f);
   __syncthreads();
@@ -530,10 +546,10 @@ __global__ void __launch_bounds__(32 * warps_for(NT)) k_attn_bf2_bwd(const float
   const int d = heads * DH;
   const long long row0 = (long long)b * S;
   const float* base = qkv + row0 * 3 * d + h * DH;
-  stage_planes<DH>(Qh, Ql, base, 3 * d, S, SP, tid, 32 * NW);
-  stage_planes<DH>(Kh, Kl, base + d, 3 * d, S, SP, tid, 32 * NW);
-  stage_planes<DH>(Vh, Vl, base + 2 * d, 3 * d, S, SP, tid, 32 * NW);
-  stage_planes<DH>(Gh, Gl, dO + row0 * d + h * DH, d, S, SP, tid, 32 * NW);
+  stage_planes<DH, SP, 32 * NW>(Qh, Ql, base, 3 * d, S, tid);
+  stage_planes<DH, SP, 32 * NW>(Kh, Kl, base + d, 3 * d, S, tid);
+  stage_planes<DH, SP, 32 * NW>(Vh, Vl, base + 2 * d, 3 * d, S, tid);
+  stage_planes<DH, SP, 32 * NW>(Gh, Gl, dO + row0 * d + h * DH, d, S, tid);
   for (int j = tid; j < SP; j += 32 * NW)
     Km[j] = j >= S ? -INFINITY : ((mask && !mask[(long long)b * mask_stride + j]) ? -1e9f : 0.f);
   __syncthreads();

@@ -223,18 +223,37 @@ __global__ void __launch_bounds__(256) k_wgrad_skinny(const float* __restrict__ 
 #pragma unroll
     for (int i = 0; i < KPL; ++i) acc[i][j] = 0.f;
   }
-  for (long long t0 = r0; t0 < r1; t0 += TR) {
-    for (int i = tid; i < TR * KD / 4; i += 256) {
-      const int r = i / (KD / 4), c = (i - r * (KD / 4)) * 4;
-      *reinterpret_cast<float4*>(&Xs[r][c]) = (t0 + r < r1) ? *reinterpret_cast<const float4*>(X + (t0 + r) * ldx + c)
-                                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+  // register-staged, software-pipelined tile loads: the loads of tile t + 1 are in flight while tile t is multiplied (a
+  // rolled load loop made every iteration wait for its own DRAM latency: the kernel ran at 1 - 2 TB/s)
+  constexpr int ITX = TR * KD / 4 / 256, ITY = TR * ND / 4 / 256;
+  static_assert(TR * KD / 4 % 256 == 0 && TR * ND / 4 % 256 == 0, "tile loads are whole passes of the CTA");
+  float4 xr[ITX], yr[ITY];
+  auto fetch = [&](long long t0) {
+#pragma unroll
+    for (int u = 0; u < ITX; ++u) {
+      const int i = tid + 256 * u, r = i / (KD / 4), c = (i - r * (KD / 4)) * 4;
+      xr[u] = (t0 + r < r1) ? *reinterpret_cast<const float4*>(X + (t0 + r) * ldx + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    for (int i = tid; i < TR * ND / 4; i += 256) {
-      const int r = i / (ND / 4), c = (i - r * (ND / 4)) * 4;
-      *reinterpret_cast<float4*>(&Ys[r][c]) = (t0 + r < r1) ? *reinterpret_cast<const float4*>(dY + (t0 + r) * ldy + c)
-                                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < ITY; ++u) {
+      const int i = tid + 256 * u, r = i / (ND / 4), c = (i - r * (ND / 4)) * 4;
+      yr[u] = (t0 + r < r1) ? *reinterpret_cast<const float4*>(dY + (t0 + r) * ldy + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  if (r0 < r1) fetch(r0);
+  for (long long t0 = r0; t0 < r1; t0 += TR) {
+#pragma unroll
+    for (int u = 0; u < ITX; ++u) {
+      const int i = tid + 256 * u, r = i / (KD / 4), c = (i - r * (KD / 4)) * 4;
+      *reinterpret_cast<float4*>(&Xs[r][c]) = xr[u];
+    }
+#pragma unroll
+    for (int u = 0; u < ITY; ++u) {
+      const int i = tid + 256 * u, r = i / (ND / 4), c = (i - r * (ND / 4)) * 4;
+      *reinterpret_cast<float4*>(&Ys[r][c]) = yr[u];
     }
     __syncthreads();
+    if (t0 + TR < r1) fetch(t0 + TR);
 #pragma unroll 2
     for (int r = warp; r < TR; r += 8) {
       float xv[KPL], y[NPL];
@@ -286,6 +305,13 @@ bool wgrad_skinny_ok(const float* X, long long ldx, const float* dY, long long l
 // dW [K, N] += X^T dY, db [N] += colsum(dY) (db may be null)
 cudaError_t launch_wgrad_skinny(const float* X, long long ldx, const float* dY, long long ldy, long long rows, int K, int N,
                                 float* dW, float* db, cudaStream_t st) {
+  if (K == 64 && N == 32) {
+    // two 32 x 32 passes over the halves of X (dW rows 0..31 | 32..63 are contiguous): the 64 x 32 instantiation keeps 64
+    // accumulators per thread and is slower than both passes together (104 vs 2 x 44 us)
+    cudaError_t e = launch_wgrad_skinny(X, ldx, dY, ldy, rows, 32, 32, dW, db, st);
+    if (e != cudaSuccess) return e;
+    return launch_wgrad_skinny(X + 32, ldx, dY, ldy, rows, 32, 32, dW + 32 * 32, nullptr, st);
+  }
   const unsigned grid = (unsigned)std::min<long long>(148 * 4, (rows + 255) / 256);
   if ((size_t)grid * (K * N + N) > g_red_floats) return cudaErrorInvalidValue;
 #define UU_WS(KD, ND) if (K == KD && N == ND) k_wgrad_skinny<KD, ND><<<grid, 256, 0, st>>>(X, ldx, dY, ldy, rows, g_red_scratch); else
@@ -830,6 +856,18 @@ constexpr int SA_WARPS = 4;
 // the loops below are fully unrolled; without a scheduling fence every few iterations ptxas hoists all 17 (x 2 or 3) float4
 // shared-memory loads of a loop to its top (255 registers, two resident CTAs)
 #define UU_SA_FENCE(idx) do { if (((idx) & 3) == 3) asm volatile("" ::: "memory"); } while (0)
+// N float4 from global to the warp's shared-memory slot, all loads in flight before the first store
+template <int N>
+__device__ __forceinline__ void sa_stage(float4* __restrict__ dst, const float4* __restrict__ src, int lane) {
+  constexpr int IT = (N + 31) / 32;
+  float4 v[IT];
+#pragma unroll
+  for (int u = 0; u < IT; ++u)
+    if (lane + 32 * u < N) v[u] = src[lane + 32 * u];
+#pragma unroll
+  for (int u = 0; u < IT; ++u)
+    if (lane + 32 * u < N) dst[lane + 32 * u] = v[u];
+}
 __device__ __forceinline__ float dot4(const float4& a, const float4& b) { return fmaf(a.w, b.w, fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x))); }
 template <int S>
 __global__ void __launch_bounds__(SA_WARPS * 32, 6) k_attn_small_fwd(const float* __restrict__ qkv, long long frames,
@@ -841,7 +879,7 @@ __global__ void __launch_bounds__(SA_WARPS * 32, 6) k_attn_small_fwd(const float
   for (long long f = (long long)blockIdx.x * SA_WARPS + warp; f < frames; f += (long long)gridDim.x * SA_WARPS) {
     const float4* src = reinterpret_cast<const float4*>(qkv + f * S * 96);
     __syncwarp();
-    for (int i = lane; i < S * 24; i += 32) reinterpret_cast<float4*>(sq)[i] = src[i];
+    sa_stage<S * 24>(reinterpret_cast<float4*>(sq), src, lane);
     __syncwarp();
 #pragma unroll 1
     for (int item = lane; item < S * 8; item += 32) {
@@ -886,8 +924,8 @@ __global__ void __launch_bounds__(SA_WARPS * 32, 5) k_attn_small_bwd(const float
     const float4* gsrc = reinterpret_cast<const float4*>(dO + f * S * 32);
     float* dst = dqkv + f * S * 96;
     __syncwarp();
-    for (int i = lane; i < S * 24; i += 32) reinterpret_cast<float4*>(sq)[i] = src[i];
-    for (int i = lane; i < S * 8; i += 32) reinterpret_cast<float4*>(sd)[i] = gsrc[i];
+    sa_stage<S * 24>(reinterpret_cast<float4*>(sq), src, lane);
+    sa_stage<S * 8>(reinterpret_cast<float4*>(sd), gsrc, lane);
     __syncwarp();
     // ---- pass 1: pair = (query i, head h)
 #pragma unroll 1

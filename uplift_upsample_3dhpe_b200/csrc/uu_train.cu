@@ -51,7 +51,7 @@ struct TrainState {
   float* tok_keep = nullptr;                    // [R] 0 / 1 factors drawn for the current step
   int math = 0;
   int *gl_scratch = nullptr, *gl_list = nullptr, *gl_pos = nullptr, *gl_count = nullptr;   // valid-frame gather list (stride mask)
-  int attn_split = 2;                           // attn_mma.cu: 2 = bf16 hi + lo planes (2^-16 per product), 3 = compensated TF32, 1 = TF32
+  int attn_split = 3;                           // attn_mma.cu: 2 = bf16 hi + lo planes (2^-16 per product), 3 = compensated TF32, 1 = TF32
   float* wg_scratch = nullptr;                  // split-K partial tiles of the tensor-core wgrad (wgrad_tc.cu)
   float* red_scratch = nullptr;                 // partial slabs of the deterministic two-pass reductions (train_kernels.cu)
   struct PackedQkv { float *W = nullptr, *b = nullptr, *dW = nullptr, *db = nullptr; };
@@ -293,8 +293,12 @@ static int attn_half_bwd(Ctx& c, const BlkDims& b, const std::string& g, BlkTape
   TrainState* t = c.t;
   const long long R = b.nb * b.S;
   const int d = b.d;
-  UU_TL(launch_scale_rows(dx, tp.keep < 1.f ? tp.scale : nullptr, b.S, R, d, t->tmp1, c.st));
-  if (lin_bwd(c, tp.o, d, t->tmp1, d, (int)R, d, d, W(m, g, 8), t->tmp2, d, 0, G(m, g, 8), G(m, g, 9))) return 1;
+  const float* dy = dx;                       // gradient of the branch output: dx itself unless stochastic depth scales it
+  if (tp.keep < 1.f) {
+    UU_TL(launch_scale_rows(dx, tp.scale, b.S, R, d, t->tmp1, c.st));
+    dy = t->tmp1;
+  }
+  if (lin_bwd(c, tp.o, d, dy, d, (int)R, d, d, W(m, g, 8), t->tmp2, d, 0, G(m, g, 8), G(m, g, 9))) return 1;
   if (!attention_small_ok(b.S, b.heads, d / b.heads, keymask) && attention_mma_ok(b.nb, b.S, b.heads, d / b.heads))
     UU_TL(launch_attention_mma_bwd(tp.qkv, t->tmp2, b.nb, b.S, b.heads, d / b.heads, keymask, mask_stride, t->tmp_qkv,
                                    t->attn_split, c.st));
@@ -342,8 +346,12 @@ static int block_bwd(Ctx& c, const BlkDims& b, const std::string& g, BlkTape& tp
   const long long R = b.nb * b.S;
   const int d = b.d, h = b.h;
   const RowMap plain;
-  UU_TL(launch_scale_rows(dx, tp.keep < 1.f ? tp.scale2 : nullptr, b.S, R, d, t->tmp1, c.st));
-  if (lin_bwd(c, tp.hact, h, t->tmp1, d, (int)R, h, d, W(m, g, 14), t->tmp_h, h, 0, G(m, g, 14), G(m, g, 15))) return 1;
+  const float* dy = dx;
+  if (tp.keep < 1.f) {
+    UU_TL(launch_scale_rows(dx, tp.scale2, b.S, R, d, t->tmp1, c.st));
+    dy = t->tmp1;
+  }
+  if (lin_bwd(c, tp.hact, h, dy, d, (int)R, h, d, W(m, g, 14), t->tmp_h, h, 0, G(m, g, 14), G(m, g, 15))) return 1;
   UU_TL(launch_act_bwd(tp.hpre, t->tmp_h, plain, h, R, h, b.act, t->tmp_h, c.st));
   if (lin_bwd(c, tp.y2, d, t->tmp_h, h, (int)R, d, h, W(m, g, 12), t->tmp2, d, 0, G(m, g, 12), G(m, g, 13))) return 1;
   UU_TL(launch_ln_bwd_gen(tp.x1, t->tmp2, R, d, W(m, g, 10), 1e-5f, dx, 1, G(m, g, 10), G(m, g, 11), c.st));
@@ -583,9 +591,13 @@ static int train_fb(uu_model* m, const float* x2d, const uint8_t* mask, const fl
     const BlkDims bd{d, h, L, H, (long long)B, 0};
     float* dx_prev = i > 0 ? t->dx_s[i - 1] : t->dx_t;        // gradient w.r.t. this block's input sequence
     // z path
-    UU_TL(launch_scale_rows(dx, tp.keep < 1.f ? tp.scale2 : nullptr, Lo, Ro, d, t->tmp1, stream));
+    const float* dy = dx;
+    if (tp.keep < 1.f) {
+      UU_TL(launch_scale_rows(dx, tp.scale2, Lo, Ro, d, t->tmp1, stream));
+      dy = t->tmp1;
+    }
     UU_CUDA(cudaMemsetAsync(t->dhp[i], 0, sizeof(float) * (size_t)B * Lo * st_i * h, stream));
-    if (lin_bwd(c, t->hp[i], (long long)st_i * h, t->tmp1, d, (int)Ro, 3 * h, d, W(m, g, 14), t->dhp[i],
+    if (lin_bwd(c, t->hp[i], (long long)st_i * h, dy, d, (int)Ro, 3 * h, d, W(m, g, 14), t->dhp[i],
                 (long long)st_i * h, 0, G(m, g, 14), G(m, g, 15)))
       return 1;
     RowMap cm;
@@ -699,6 +711,9 @@ int uu_train_set_math(uu_model* m, int mode) {
   UU_CHECK(m && (mode == 0 || mode == 1), "math mode: 0 = fp32, 1 = tf32 tensor cores");
   if (!m->train) m->train = new TrainState();
   m->train->math = mode;
+  // attention of the temporal / strided blocks (attn_mma.cu): the fp32 parity mode takes the compensated TF32 form (fp32-grade:
+  // Adam turns relative gradient errors into +-lr steps wherever a gradient is small), the tensor-core mode the bf16 hi + lo form
+  m->train->attn_split = mode == 0 ? 3 : 2;
   return 0;
 }
 
