@@ -153,6 +153,32 @@ def test_random_token_masking_matches_autograd():
     model.close()
 
 
+def test_masked_frames_are_never_read_in_training():
+    """The spatial stage of the training step runs on the valid frames only (device gather list): frames the stride mask
+    drops are replaced by the upsampling token (net:350-352), so poisoning their 2-D input with NaN must leave the loss and
+    every gradient bit-identical."""
+    B = 7
+    cfg = UpliftUpsampleConfig.preset("h36m_351", BATCH_SIZE=B)
+    spec = spec_from_config(cfg)
+    w = weights.init_weights(spec, 1, perturb=True)
+    x, gt, m = _data(cfg, spec, B)
+    assert 0 < m.sum() < m.size and len({int(r.sum()) for r in m}) > 1      # mixed mask strides in the batch
+    xp = x.copy()
+    xp[~m] = np.nan
+    out = []
+    for xin in (x, xp):
+        model = build_uplift_upsample_transformer(cfg, precision="fp32", weights=w)
+        tr = Trainer(model, cfg, droppath=True, seed=3, math="tf32")
+        loss = tr.forward_backward(torch.from_numpy(xin).cuda(), torch.from_numpy(gt).cuda(), torch.from_numpy(m).cuda())
+        torch.cuda.synchronize()
+        out.append((float(loss.item()), tr.get_grads()))
+        model.close()
+    assert np.isfinite(out[1][0]) and out[0][0] == out[1][0]
+    for k in out[0][1]:
+        assert np.isfinite(out[1][1][k]).all(), k
+        assert np.array_equal(out[0][1][k], out[1][1][k]), k
+
+
 def test_three_adamw_steps_match_oracle():
     cfg = UpliftUpsampleConfig.preset("h36m_81", BATCH_SIZE=4)
     spec = spec_from_config(cfg)

@@ -23,6 +23,9 @@ void gemm_gen_tile(int N, int* bm, int* bn);
 bool wgrad_skinny_ok(const float* X, long long ldx, const float* dY, long long ldy, long long rows, int K, int N);
 cudaError_t launch_wgrad_skinny(const float* X, long long ldx, const float* dY, long long ldy, long long rows, int K, int N,
                                 float* dW, float* db, cudaStream_t st);      // tile shape launch_gemm_gen picks for an N-wide output
+bool dgrad_skinny_ok(const float* dY, long long ldy, long long rows, int KI, int NO, const float* dX, long long ldx);
+cudaError_t launch_dgrad_skinny(const float* dY, long long ldy, const float* Wm, long long rows, int KI, int NO, float* dX,
+                                long long ldx, int accumulate, cudaStream_t st);      // dX (+)= dY W^T, W (NO, KI)
 cudaError_t launch_colsum(const float* Y, int M, int N, long long ld, float* out, cudaStream_t st);
 cudaError_t launch_period_sum(const float* X, long long rows, int period, int d, const uint8_t* rowmask, int want,
                               float* out, cudaStream_t st);

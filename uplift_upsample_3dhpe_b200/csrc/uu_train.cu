@@ -216,6 +216,9 @@ static int lin_bwd(Ctx& c, const float* X, long long ldx, const float* dY, long 
     if (dxmap) e.cmap = *dxmap;
     if (accumulate_dx) { e.flags = EPI_RESIDUAL; e.res = dX; e.ldr = lddx; if (dxmap) e.rmap = *dxmap; }
     if (tf32_gemm(c, dY, ldy, M, N, Wm, N, K, e, dX, lddx)) return 1;
+  } else if (dX && !dxmap && dgrad_skinny_ok(dY, ldy, M, N, K, dX, lddx)) {
+    // narrow layers of the spatial blocks: streaming kernel (train_kernels.cu); W is (K, N) = (outputs of dX, inputs dY)
+    UU_TL(launch_dgrad_skinny(dY, ldy, Wm, M, N, K, dX, lddx, accumulate_dx, c.st));
   } else if (dX) {
     GemmGen g;
     g.A = dY; g.lda = ldy; g.B = Wm; g.ldb = N; g.transB = 1; g.C = dX; g.ldc = lddx; g.M = M; g.N = K; g.K = N;
