@@ -477,12 +477,46 @@ __global__ void k_colsum(const float* __restrict__ Y, int M, int N, long long ld
     out[(long long)blockIdx.y * N + n] = s;          // partial slab of this row range
   }
 }
+// 16-byte variant: a warp covers 128 columns, the 8 warps of a CTA take every 8th row of the CTA's row range, four rows per
+// thread in flight; warps are summed in warp order through shared memory (fixed association).
+__global__ void __launch_bounds__(256) k_colsum4(const float* __restrict__ Y, int M, int N, long long ld, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int n = blockIdx.x * 128 + 4 * lane;
+  const int rows_per = (M + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (n < N) {
+    int r = r0 + rl;
+    for (; r + 24 < r1; r += 32) {
+      const float4 a = *reinterpret_cast<const float4*>(Y + (long long)r * ld + n);
+      const float4 b = *reinterpret_cast<const float4*>(Y + (long long)(r + 8) * ld + n);
+      const float4 c = *reinterpret_cast<const float4*>(Y + (long long)(r + 16) * ld + n);
+      const float4 d = *reinterpret_cast<const float4*>(Y + (long long)(r + 24) * ld + n);
+      s.x += (a.x + b.x) + (c.x + d.x); s.y += (a.y + b.y) + (c.y + d.y);
+      s.z += (a.z + b.z) + (c.z + d.z); s.w += (a.w + b.w) + (c.w + d.w);
+    }
+    for (; r < r1; r += 8) {
+      const float4 a = *reinterpret_cast<const float4*>(Y + (long long)r * ld + n);
+      s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+    }
+  }
+  __shared__ __align__(16) float4 sm4[8][32];
+  sm4[rl][lane] = s;
+  __syncthreads();
+  if (rl == 0 && n < N) {
+    for (int i = 1; i < 8; ++i) { const float4 t = sm4[i][lane]; s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
+    *reinterpret_cast<float4*>(out + (long long)blockIdx.y * N + n) = s;          // partial slab of this row range
+  }
+}
 cudaError_t launch_colsum(const float* Y, int M, int N, long long ld, float* out, cudaStream_t st) {
   if (M == 0 || N == 0) return cudaSuccess;
-  dim3 grid((N + 31) / 32, std::max(1, std::min(128, M / 256)));
-  if ((size_t)grid.y * N > g_red_floats) return cudaErrorInvalidValue;
-  k_colsum<<<grid, 256, 0, st>>>(Y, M, N, ld, g_red_scratch);
-  return reduce_partials(grid.y, N, out, N, nullptr, st);
+  const int splits = std::max(1, std::min(128, M / 256));
+  if ((size_t)splits * N > g_red_floats) return cudaErrorInvalidValue;
+  if (N % 4 == 0 && ld % 4 == 0 && ((uintptr_t)Y & 15) == 0 && ((uintptr_t)g_red_scratch & 15) == 0)
+    k_colsum4<<<dim3((N + 127) / 128, splits), 256, 0, st>>>(Y, M, N, ld, g_red_scratch);
+  else
+    k_colsum<<<dim3((N + 31) / 32, splits), 256, 0, st>>>(Y, M, N, ld, g_red_scratch);
+  return reduce_partials(splits, N, out, N, nullptr, st);
 }
 
 // out[(r % period)*d + c] += X[r*d + c]  (positional-encoding gradients: sum over the batch);
