@@ -542,7 +542,7 @@ cudaError_t launch_period_sum(const float* X, long long rows, int period, int d,
   if (rows == 0) return cudaSuccess;
   const int bx = d >= 128 ? 128 : 32;
   const long long nb = rows / period;
-  long long nz = std::max<long long>(1, std::min<long long>(64, nb / 32));
+  long long nz = std::max<long long>(1, std::min<long long>(64, nb / 8));      // (3 x 3 x 16 CTAs of 128 threads ran at 1 TB/s)
   nz = std::max<long long>(1, std::min<long long>(nz, (long long)(g_red_floats / ((size_t)period * d))));
   dim3 grid((d + bx - 1) / bx, period, (unsigned)nz);
   if ((size_t)period * d > g_red_floats) return cudaErrorInvalidValue;
@@ -1292,10 +1292,28 @@ __global__ void k_residual(const float* __restrict__ base, RowMap bmap, const fl
     out[i] = v;
   }
 }
+__global__ void __launch_bounds__(256) k_act_bwd_mapped4(const float* __restrict__ hp, const float* __restrict__ dhp, RowMap map,
+                                                         long long ld, uint32_t n4, uint32_t cols4, float4* __restrict__ dpre) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    const uint32_t r = i / cols4, c = (i - r * cols4) * 4;
+    const long long pr = map_row(map, (int)r);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pr >= 0) {
+      const float4 h = *reinterpret_cast<const float4*>(hp + pr * ld + c);
+      const float4 g = *reinterpret_cast<const float4*>(dhp + pr * ld + c);
+      v = make_float4(h.x > 0.f ? g.x : 0.f, h.y > 0.f ? g.y : 0.f, h.z > 0.f ? g.z : 0.f, h.w > 0.f ? g.w : 0.f);
+    }
+    dpre[i] = v;
+  }
+}
 cudaError_t launch_act_bwd_mapped(const float* hp, const float* dhp, const RowMap& map, long long ld, long long rows,
                                   int cols, float* dpre, cudaStream_t st) {
   if (rows == 0) return cudaSuccess;
-  k_act_bwd_mapped<<<ew_grid(rows * cols), 256, 0, st>>>(hp, dhp, map, ld, rows, cols, dpre);
+  if (cols % 4 == 0 && ld % 4 == 0 && fits_u32(rows * cols) && al16(hp) && al16(dhp) && al16(dpre))
+    k_act_bwd_mapped4<<<ew_grid(rows * cols / 4), 256, 0, st>>>(hp, dhp, map, ld, (uint32_t)(rows * cols / 4),
+                                                                (uint32_t)(cols / 4), (float4*)dpre);
+  else
+    k_act_bwd_mapped<<<ew_grid(rows * cols), 256, 0, st>>>(hp, dhp, map, ld, rows, cols, dpre);
   return cudaGetLastError();
 }
 cudaError_t launch_residual(const float* base, const RowMap& bmap, const float* y, const float* scale,
@@ -1431,16 +1449,53 @@ __global__ void k_fill_bwd(const float* __restrict__ dx, const uint8_t* __restri
     ds[i] = v * (keep ? keep[sr] : 1.f);
   }
 }
+// 16-byte forms of the two kernels above (d % 4 == 0, aligned pointers, 32-bit element counts)
+__global__ void __launch_bounds__(256) k_fill_fwd4(const float* __restrict__ s, const uint8_t* __restrict__ mask,
+                                                   const int* __restrict__ pos, const float* __restrict__ keep,
+                                                   const float* __restrict__ token, const float* __restrict__ pe, uint32_t n_tok,
+                                                   uint32_t n4, uint32_t d4, float4* __restrict__ x) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    const uint32_t r = i / d4, c = (i - r * d4) * 4;
+    float4 v;
+    if (!mask || mask[r]) {
+      v = *reinterpret_cast<const float4*>(s + (pos ? (long long)pos[r] : (long long)r) * (4 * d4) + c);
+      if (keep) { const float kf = keep[r]; v.x *= kf; v.y *= kf; v.z *= kf; v.w *= kf; }
+    } else {
+      v = *reinterpret_cast<const float4*>(token + c);
+    }
+    const float4 e = *reinterpret_cast<const float4*>(pe + (long long)(r % n_tok) * (4 * d4) + c);
+    x[i] = make_float4(v.x + e.x, v.y + e.y, v.z + e.z, v.w + e.w);
+  }
+}
+__global__ void __launch_bounds__(256) k_fill_bwd4(const float* __restrict__ dx, const uint8_t* __restrict__ mask,
+                                                   const int* __restrict__ list, const float* __restrict__ keep, uint32_t n4,
+                                                   uint32_t d4, float4* __restrict__ ds) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    const uint32_t r = i / d4, c = (i - r * d4) * 4;
+    const long long sr = list ? (long long)list[r] : (long long)r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (list || !mask || mask[sr]) v = *reinterpret_cast<const float4*>(dx + sr * (4 * d4) + c);
+    if (keep) { const float kf = keep[sr]; v.x *= kf; v.y *= kf; v.z *= kf; v.w *= kf; }
+    ds[i] = v;
+  }
+}
 cudaError_t launch_fill_fwd(const float* s, const uint8_t* mask, const int* pos, const float* keep, const float* token,
                             const float* pe, int n_tok, long long rows, int d, float* x, cudaStream_t st) {
   if (rows == 0) return cudaSuccess;
-  k_fill_fwd<<<ew_grid(rows * d), 256, 0, st>>>(s, mask, pos, keep, token, pe, n_tok, rows, d, x);
+  if (d % 4 == 0 && fits_u32(rows * d) && al16(s) && al16(token) && al16(pe) && al16(x))
+    k_fill_fwd4<<<ew_grid(rows * d / 4), 256, 0, st>>>(s, mask, pos, keep, token, pe, (uint32_t)n_tok, (uint32_t)(rows * d / 4),
+                                                       (uint32_t)(d / 4), (float4*)x);
+  else
+    k_fill_fwd<<<ew_grid(rows * d), 256, 0, st>>>(s, mask, pos, keep, token, pe, n_tok, rows, d, x);
   return cudaGetLastError();
 }
 cudaError_t launch_fill_bwd(const float* dx, const uint8_t* mask, const int* list, const float* keep, long long rows, int d,
                             float* ds, cudaStream_t st) {
   if (rows == 0) return cudaSuccess;
-  k_fill_bwd<<<ew_grid(rows * d), 256, 0, st>>>(dx, mask, list, keep, rows, d, ds);
+  if (d % 4 == 0 && fits_u32(rows * d) && al16(dx) && al16(ds))
+    k_fill_bwd4<<<ew_grid(rows * d / 4), 256, 0, st>>>(dx, mask, list, keep, (uint32_t)(rows * d / 4), (uint32_t)(d / 4), (float4*)ds);
+  else
+    k_fill_bwd<<<ew_grid(rows * d), 256, 0, st>>>(dx, mask, list, keep, rows, d, ds);
   return cudaGetLastError();
 }
 // pos[list[i]] = i (inverse of the gather list) and dst[i] = src[list[i]] (per-frame stochastic-depth factors -> compact order)

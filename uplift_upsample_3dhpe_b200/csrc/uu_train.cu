@@ -216,6 +216,18 @@ static int lin_bwd(Ctx& c, const float* X, long long ldx, const float* dY, long 
     if (dxmap) e.cmap = *dxmap;
     if (accumulate_dx) { e.flags = EPI_RESIDUAL; e.res = dX; e.ldr = lddx; if (dxmap) e.rmap = *dxmap; }
     if (tf32_gemm(c, dY, ldy, M, N, Wm, N, K, e, dX, lddx)) return 1;
+  } else if (dX && !dxmap && c.t->math == 1 && K > 64 && K % 64 != 0 &&
+             tf32_ok(c, dY, ldy, Wm, N, M, K / 64 * 64, N, dX, lddx)) {
+    // an output width that is not a multiple of the tensor-core column tile (the 544-wide input of spatial_to_temporal_fc):
+    // the first floor(K / 64) * 64 columns on tcgen05 kind::tf32, the remaining K % 64 on the generic kernel
+    const int K0 = K / 64 * 64;
+    Epilogue e;
+    if (accumulate_dx) { e.flags = EPI_RESIDUAL; e.res = dX; e.ldr = lddx; }
+    if (tf32_gemm(c, dY, ldy, M, N, Wm, N, K0, e, dX, lddx)) return 1;
+    GemmGen g;
+    g.A = dY; g.lda = ldy; g.B = Wm + (long long)K0 * N; g.ldb = N; g.transB = 1; g.C = dX + K0; g.ldc = lddx; g.M = M;
+    g.N = K - K0; g.K = N; g.accumulate = accumulate_dx;
+    UU_TL(launch_gemm_gen(g, c.st));
   } else if (dX && !dxmap && dgrad_skinny_ok(dY, ldy, M, N, K, dX, lddx)) {
     // narrow layers of the spatial blocks: streaming kernel (train_kernels.cu); W is (K, N) = (outputs of dX, inputs dY)
     UU_TL(launch_dgrad_skinny(dY, ldy, Wm, M, N, K, dX, lddx, accumulate_dx, c.st));
