@@ -134,6 +134,31 @@ def test_large_batch_properties(precision):
     model.close()
 
 
+def test_benched_batch_against_the_oracle():
+    """The benched configuration at its full size (h36m_351, s_in = 5, 4096 windows, bf16 schedule — bench.py's step) against
+    the torch-CPU fp32 restatement of the reference forward over EVERY window (the fp32 restatement sits ~1e-5 from the float64
+    one; a few seconds on the host cores), plus the error statistics the bench line quotes."""
+    from oracle import forward_torch as OT
+    cfg, spec, w, x, m = _case("h36m_351", 5, 4096, "centred", seed=11)
+    model = build_uplift_upsample_transformer(cfg, precision="bf16", weights=w)
+    full, central = run_test_step(model, torch.from_numpy(x).cuda(), torch.from_numpy(m).cuda())
+    torch.cuda.synchronize()
+    wt = OT.to_torch(w, torch.float32)
+    ref_f, ref_c = [], []
+    with torch.no_grad():
+        for i in range(0, 4096, 256):
+            f, c = OT.test_step(spec, wt, torch.from_numpy(x[i:i + 256]), torch.from_numpy(m[i:i + 256].astype(bool)))
+            ref_f.append(f.numpy()); ref_c.append(c.numpy())
+    ref_f, ref_c = np.concatenate(ref_f), np.concatenate(ref_c)
+    e_f, e_c = np.abs(full.cpu().numpy() - ref_f), np.abs(central.cpu().numpy() - ref_c)
+    print(f"B=4096 bf16: max|err| full {e_f.max():.3e} central {e_c.max():.3e}, rms {np.sqrt((e_f ** 2).mean()):.3e} "
+          f"(output rms {np.sqrt((ref_f ** 2).mean()):.3f})")
+    assert np.isfinite(full.cpu().numpy()).all()
+    assert e_f.max() <= TOL["bf16"] and e_c.max() <= TOL["bf16"]
+    assert np.sqrt((e_f ** 2).mean()) <= 0.04
+    model.close()
+
+
 @pytest.mark.parametrize("s_in", [5, 20])
 def test_chunked_host_forward_is_identical_to_device_forward(s_in):
     """uu_forward_host splits the input copy of large bf16 batches into chunks overlapped with the spatial

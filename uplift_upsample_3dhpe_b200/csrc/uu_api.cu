@@ -394,8 +394,16 @@ static int attention_block(Fwd& f, const BlockW& w, float* x, int L, const uint8
   e.bias = w.bqkv;
   f.wt32 = tf ? w.t_qkv : nullptr;
   if (gemm(f, m->Y, d, R, d, w.wqkv, w.p_qkv, 3 * d, e, m->QKV, bf, 3 * d)) return 1;
-  UU_LAUNCH(f, UU_KIND_ATTENTION, 1,
-            launch_attention(m->QKV, bf, f.B, L, s.num_heads, d / s.num_heads, keymask, s.n_tok, m->O, f.st));
+  if (tf && attention_mma_ok(f.B, L, s.num_heads, d / s.num_heads)) {
+    // tf32 schedule: fp32 rows, attention on mma.sync with bf16 hi + lo operand planes (attn_mma.cu; 2^-16 per product, finer
+    // than the TF32 GEMMs around it) instead of the CUDA-core kernel of the fp32 schedule
+    UU_LAUNCH(f, UU_KIND_ATTENTION, 1,
+              launch_attention_mma_fwd((const float*)m->QKV, f.B, L, s.num_heads, d / s.num_heads, keymask, s.n_tok, (float*)m->O,
+                                       2, f.st));
+  } else {
+    UU_LAUNCH(f, UU_KIND_ATTENTION, 1,
+              launch_attention(m->QKV, bf, f.B, L, s.num_heads, d / s.num_heads, keymask, s.n_tok, m->O, f.st));
+  }
   Epilogue ep;
   ep.bias = w.bp; ep.flags = EPI_RESIDUAL; ep.res = x; ep.ldr = d;
   f.wt32 = tf ? w.t_proj : nullptr;

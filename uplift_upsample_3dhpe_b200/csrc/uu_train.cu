@@ -45,8 +45,8 @@ struct TrainState {
   std::vector<float*> dx_s;                     // per strided level output: [B*Lo, d]
   float *tmp1 = nullptr, *tmp2 = nullptr, *tmp_h = nullptr, *tmp_qkv = nullptr, *dS = nullptr;
   float *partials = nullptr, *loss = nullptr;
-  // math mode 1: forward and dgrad GEMMs of the temporal / strided blocks on tcgen05 kind::tf32 (fp32 data, TF32
-  // products, fp32 accumulation — what TensorFlow 2.4 does by default on Ampere+ GPUs); wgrad stays fp32.
+  // math mode 1: forward, dgrad and wgrad GEMMs of the temporal / strided blocks on tcgen05 kind::tf32 (fp32 data, TF32
+  // products, fp32 accumulation — what TensorFlow 2.4 does by default on Ampere+ GPUs), their attention on bf16 hi + lo planes.
   float token_mask_rate = 0.f;                  // TOKEN_MASK_RATE (net:287-311; masked value 0), training only
   float* tok_keep = nullptr;                    // [R] 0 / 1 factors drawn for the current step
   int math = 0;

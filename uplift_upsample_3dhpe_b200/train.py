@@ -57,9 +57,9 @@ class _DevView:
 
 class Trainer:
     def __init__(self, model, config, droppath: bool = True, seed: int = 0, math: str = "fp32"):
-        """math: "fp32" (CUDA-core GEMMs, gradients within 2e-3 of fp32 autograd) or "tf32" (forward and dgrad GEMMs of
-        the temporal / strided blocks on the tcgen05 tensor cores with TF32 products — TensorFlow's own default on
-        Ampere-or-newer GPUs)."""
+        """math: "fp32" (CUDA-core GEMMs, fp32-grade tensor-core attention, gradients within 2e-3 of fp32 autograd) or
+        "tf32" (forward, dgrad and wgrad GEMMs of the temporal / strided blocks on the tcgen05 tensor cores with TF32
+        products — TensorFlow's own default on Ampere-or-newer GPUs — and their attention on bf16 hi + lo operand planes)."""
         import torch
         if math not in ("fp32", "tf32"):
             raise ValueError("math must be 'fp32' or 'tf32'")
