@@ -18,6 +18,12 @@ struct GemmGen {
 // scratch for the deterministic two-pass reductions of this translation unit (set before launching a step)
 void train_reduce_scratch(float* p, size_t n_floats);
 size_t train_reduce_scratch_floats();
+// deferred second passes (the backward pass of a training step): producers take fresh regions of `arena`, their reductions are
+// recorded and run by train_reduce_flush in ONE launch; train_reduce_defer_end flushes and returns to the immediate form
+void train_reduce_defer_begin(float* arena, size_t arena_floats);
+cudaError_t train_reduce_flush(cudaStream_t st);
+cudaError_t train_reduce_defer_end(cudaStream_t st);
+void train_reduce_defer_abort();      // error paths: drop what was recorded, back to the immediate form
 cudaError_t launch_gemm_gen(const GemmGen& g, cudaStream_t st);
 void gemm_gen_tile(int N, int* bm, int* bn);
 bool wgrad_skinny_ok(const float* X, long long ldx, const float* dY, long long ldy, long long rows, int K, int N);

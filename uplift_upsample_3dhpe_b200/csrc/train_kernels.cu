@@ -5,6 +5,7 @@
 // The reference relies on TensorFlow autodiff for all of this; every formula below
 // is the hand-derived adjoint of the forward op it names.
 #include <algorithm>
+#include <vector>
 
 #include "common.cuh"
 #include "train.cuh"
@@ -30,11 +31,10 @@ size_t train_reduce_scratch_floats() { return (size_t)6 << 20; }
 // A CTA owns 32 elements; RP_ROWS thread rows each sum every RP_ROWS-th slab in slab order, then the sums are added in row order:
 // the association is fixed by (nparts), never by timing.
 constexpr int RP_ROWS = 32;      // slab rows summed in parallel by one CTA (1024 threads: short dependent chains)
-__global__ void __launch_bounds__(32 * RP_ROWS) k_reduce_partials(const float* __restrict__ part, int nparts, long long n,
-                                                         float* __restrict__ out0, long long n0, float* __restrict__ out1) {
-  __shared__ float sm[RP_ROWS][32];
+__device__ __forceinline__ void reduce_chunk(const float* __restrict__ part, int nparts, long long n, float* __restrict__ out0,
+                                             long long n0, float* __restrict__ out1, long long chunk, float (*sm)[32]) {
   const int e = threadIdx.x & 31, pl = threadIdx.x >> 5;
-  const long long i = (long long)blockIdx.x * 32 + e;
+  const long long i = chunk * 32 + e;
   float s = 0.f;
   if (i < n)
     for (int p = pl; p < nparts; p += RP_ROWS) s += part[(long long)p * n + i];
@@ -47,8 +47,90 @@ __global__ void __launch_bounds__(32 * RP_ROWS) k_reduce_partials(const float* _
     *dst += s;
   }
 }
-static cudaError_t reduce_partials(int nparts, long long n, float* out0, long long n0, float* out1, cudaStream_t st) {
-  k_reduce_partials<<<(unsigned)((n + 31) / 32), 32 * RP_ROWS, 0, st>>>(g_red_scratch, nparts, n, out0, n0, out1);
+__global__ void __launch_bounds__(32 * RP_ROWS) k_reduce_partials(const float* __restrict__ part, int nparts, long long n,
+                                                         float* __restrict__ out0, long long n0, float* __restrict__ out1) {
+  __shared__ float sm[RP_ROWS][32];
+  reduce_chunk(part, nparts, n, out0, n0, out1, blockIdx.x, sm);
+}
+
+// Deferred mode (the backward pass of a training step): every producer takes a FRESH region of a large arena and its
+// second pass is only recorded; train_reduce_flush() then runs all recorded reductions in ONE launch (a step had ~90
+// second-pass launches of ~5 us each).  Same per-element association as the immediate form.  One process per GPU: the state
+// below is per process.
+struct RedJob {
+  const float* part; float* out0; float* out1;
+  long long n, n0;
+  int nparts, chunk0;
+};
+__global__ void __launch_bounds__(32 * RP_ROWS) k_reduce_jobs(const RedJob* __restrict__ jobs, int njobs) {
+  __shared__ float sm[RP_ROWS][32];
+  int lo = 0, hi = njobs - 1;
+  while (lo < hi) {                                   // last job whose first chunk is <= blockIdx.x
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].chunk0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const RedJob j = jobs[lo];
+  reduce_chunk(j.part, j.nparts, j.n, j.out0, j.n0, j.out1, (long long)blockIdx.x - j.chunk0, sm);
+}
+constexpr int RED_MAX_JOBS = 256, RED_SLOTS = 64;
+static bool g_defer = false;
+static float* g_arena = nullptr;
+static size_t g_arena_floats = 0, g_arena_used = 0;
+static std::vector<RedJob> g_jobs;
+static int g_job_chunks = 0, g_job_slot = 0;
+static RedJob *g_jobs_host = nullptr, *g_jobs_dev = nullptr;      // RED_SLOTS x RED_MAX_JOBS, pinned / device
+cudaError_t train_reduce_flush(cudaStream_t st) {
+  g_arena_used = 0;                                   // regions are re-used in stream order behind the reduction
+  if (g_jobs.empty()) return cudaSuccess;
+  if (!g_jobs_host) {
+    cudaError_t e = cudaMallocHost(&g_jobs_host, sizeof(RedJob) * RED_SLOTS * RED_MAX_JOBS);
+    if (e != cudaSuccess) return e;
+    e = cudaMalloc(&g_jobs_dev, sizeof(RedJob) * RED_SLOTS * RED_MAX_JOBS);
+    if (e != cudaSuccess) return e;
+  }
+  // a slot is re-used RED_SLOTS = 64 flushes later.  A step flushes about six times, and the host cannot run further ahead of
+  // the device than the driver's launch queue (~1000 launches, two steps), so the copy that last read the slot has completed
+  const int slot = g_job_slot++ % RED_SLOTS, nj = (int)g_jobs.size();
+  RedJob* h = g_jobs_host + (size_t)slot * RED_MAX_JOBS;
+  RedJob* dv = g_jobs_dev + (size_t)slot * RED_MAX_JOBS;
+  std::copy(g_jobs.begin(), g_jobs.end(), h);
+  cudaError_t e = cudaMemcpyAsync(dv, h, sizeof(RedJob) * nj, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return e;
+  k_reduce_jobs<<<(unsigned)g_job_chunks, 32 * RP_ROWS, 0, st>>>(dv, nj);
+  g_jobs.clear();
+  g_job_chunks = 0;
+  return cudaGetLastError();
+}
+void train_reduce_defer_begin(float* arena, size_t arena_floats) {
+  g_defer = true; g_arena = arena; g_arena_floats = arena_floats; g_arena_used = 0;
+  g_jobs.clear(); g_job_chunks = 0;
+}
+cudaError_t train_reduce_defer_end(cudaStream_t st) {
+  cudaError_t e = train_reduce_flush(st);
+  g_defer = false;
+  return e;
+}
+void train_reduce_defer_abort() { g_defer = false; g_jobs.clear(); g_job_chunks = 0; g_arena_used = 0; }
+// scratch region for n floats of partial slabs (immediate mode: the one shared scratch buffer)
+static float* red_region(size_t n, cudaStream_t st) {
+  if (!g_defer) return n <= g_red_floats + 4096 ? g_red_scratch : nullptr;
+  n = (n + 31) & ~(size_t)31;
+  if (n > g_arena_floats) return nullptr;
+  if (g_arena_used + n > g_arena_floats && train_reduce_flush(st) != cudaSuccess) return nullptr;
+  float* p = g_arena + g_arena_used;
+  g_arena_used += n;
+  return p;
+}
+static cudaError_t reduce_partials(const float* part, int nparts, long long n, float* out0, long long n0, float* out1,
+                                   cudaStream_t st) {
+  if (g_defer) {
+    RedJob j;
+    j.part = part; j.out0 = out0; j.out1 = out1; j.n = n; j.n0 = n0; j.nparts = nparts; j.chunk0 = g_job_chunks;
+    g_jobs.push_back(j);
+    g_job_chunks += (int)((n + 31) / 32);
+    return (int)g_jobs.size() >= RED_MAX_JOBS ? train_reduce_flush(st) : cudaSuccess;
+  }
+  k_reduce_partials<<<(unsigned)((n + 31) / 32), 32 * RP_ROWS, 0, st>>>(part, nparts, n, out0, n0, out1);
   return cudaGetLastError();
 }
 
@@ -314,16 +396,16 @@ cudaError_t launch_wgrad_skinny(const float* X, long long ldx, const float* dY, 
   }
   const unsigned grid = (unsigned)std::min<long long>(148 * 4, (rows + 255) / 256);
   if ((size_t)grid * (K * N + N) > g_red_floats) return cudaErrorInvalidValue;
-#define UU_WS(KD, ND) if (K == KD && N == ND) k_wgrad_skinny<KD, ND><<<grid, 256, 0, st>>>(X, ldx, dY, ldy, rows, g_red_scratch); else
+  float* scr = red_region((size_t)grid * (K * N + N) + N, st);      // (+ N: dump area of the column sums when db is null)
+  if (!scr) return cudaErrorInvalidValue;
+#define UU_WS(KD, ND) if (K == KD && N == ND) k_wgrad_skinny<KD, ND><<<grid, 256, 0, st>>>(X, ldx, dY, ldy, rows, scr); else
   UU_WS(32, 32) UU_WS(32, 64) UU_WS(32, 96) UU_WS(64, 32) return cudaErrorInvalidValue;
 #undef UU_WS
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  if (db) return reduce_partials((int)grid, (long long)K * N + N, dW, (long long)K * N, db, st);
-  // without a bias gradient the slab still carries the N column sums: reduce the K * N part only (strided slabs)
-  k_reduce_partials<<<(unsigned)(((long long)K * N + N + 31) / 32), 32 * RP_ROWS, 0, st>>>(
-      g_red_scratch, (int)grid, (long long)K * N + N, dW, (long long)K * N, g_red_scratch + (size_t)grid * (K * N + N));
-  return cudaGetLastError();
+  if (db) return reduce_partials(scr, (int)grid, (long long)K * N + N, dW, (long long)K * N, db, st);
+  // without a bias gradient the slab still carries the N column sums: they are added onto a dump area behind the slabs
+  return reduce_partials(scr, (int)grid, (long long)K * N + N, dW, (long long)K * N, scr + (size_t)grid * (K * N + N), st);
 }
 
 // ---- narrow input gradients (spatial blocks): dX[R, NO] (+)= dY[R, KI] W^T with W (NO, KI) as the forward layer stores it ----
@@ -448,7 +530,8 @@ cudaError_t launch_gemm_gen(const GemmGen& g, cudaStream_t st) {
   if (splits > 1) {
     splits = (int)std::min<size_t>(splits, g_red_floats / ((size_t)g.M * g.N));
     if (splits < 1) return cudaErrorInvalidValue;
-    gg.partial = g_red_scratch;
+    gg.partial = red_region((size_t)splits * g.M * g.N, st);
+    if (!gg.partial) return cudaErrorInvalidValue;
   }
   int bm, bn;
   gemm_gen_tile(g.N, &bm, &bn);
@@ -457,7 +540,7 @@ cudaError_t launch_gemm_gen(const GemmGen& g, cudaStream_t st) {
   else gg_launch<256, 32>(gg, splits, st);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess || splits == 1) return e;
-  return reduce_partials(splits, (long long)g.M * g.N, g.C, (long long)g.M * g.N, nullptr, st);
+  return reduce_partials(gg.partial, splits, (long long)g.M * g.N, g.C, (long long)g.M * g.N, nullptr, st);
 }
 
 // out[n] += sum_r Y[r*ld + n]   (bias gradients)
@@ -512,11 +595,13 @@ cudaError_t launch_colsum(const float* Y, int M, int N, long long ld, float* out
   if (M == 0 || N == 0) return cudaSuccess;
   const int splits = std::max(1, std::min(128, M / 256));
   if ((size_t)splits * N > g_red_floats) return cudaErrorInvalidValue;
-  if (N % 4 == 0 && ld % 4 == 0 && ((uintptr_t)Y & 15) == 0 && ((uintptr_t)g_red_scratch & 15) == 0)
-    k_colsum4<<<dim3((N + 127) / 128, splits), 256, 0, st>>>(Y, M, N, ld, g_red_scratch);
+  float* scr = red_region((size_t)splits * N, st);
+  if (!scr) return cudaErrorInvalidValue;
+  if (N % 4 == 0 && ld % 4 == 0 && ((uintptr_t)Y & 15) == 0 && ((uintptr_t)scr & 15) == 0)
+    k_colsum4<<<dim3((N + 127) / 128, splits), 256, 0, st>>>(Y, M, N, ld, scr);
   else
-    k_colsum<<<dim3((N + 31) / 32, splits), 256, 0, st>>>(Y, M, N, ld, g_red_scratch);
-  return reduce_partials(splits, N, out, N, nullptr, st);
+    k_colsum<<<dim3((N + 31) / 32, splits), 256, 0, st>>>(Y, M, N, ld, scr);
+  return reduce_partials(scr, splits, N, out, N, nullptr, st);
 }
 
 // out[(r % period)*d + c] += X[r*d + c]  (positional-encoding gradients: sum over the batch);
@@ -546,8 +631,10 @@ cudaError_t launch_period_sum(const float* X, long long rows, int period, int d,
   nz = std::max<long long>(1, std::min<long long>(nz, (long long)(g_red_floats / ((size_t)period * d))));
   dim3 grid((d + bx - 1) / bx, period, (unsigned)nz);
   if ((size_t)period * d > g_red_floats) return cudaErrorInvalidValue;
-  k_period_sum<<<grid, bx, 0, st>>>(X, rows, period, d, rowmask, want, g_red_scratch);
-  return reduce_partials((int)nz, (long long)period * d, out, (long long)period * d, nullptr, st);
+  float* scr = red_region((size_t)nz * period * d, st);
+  if (!scr) return cudaErrorInvalidValue;
+  k_period_sum<<<grid, bx, 0, st>>>(X, rows, period, d, rowmask, want, scr);
+  return reduce_partials(scr, (int)nz, (long long)period * d, out, (long long)period * d, nullptr, st);
 }
 
 // =================================================================================================
@@ -819,23 +906,25 @@ cudaError_t launch_ln_bwd_gen(const float* x, const float* dy, long long rows, i
   grid = (unsigned)std::min<size_t>(grid, g_red_floats / (2 * (size_t)d));
   if (grid == 0) return cudaErrorInvalidValue;
   const size_t smem = 8 * 2 * d * sizeof(float);
+  float* scr = red_region((size_t)grid * 2 * d, st);
+  if (!scr) return cudaErrorInvalidValue;
   if (d == 32 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)dx & 15) == 0 && ((uintptr_t)gamma & 15) == 0)
-    k_ln_bwd_d32<<<grid, 256, 0, st>>>(x, dy, rows, gamma, eps, dx, accumulate, g_red_scratch);
+    k_ln_bwd_d32<<<grid, 256, 0, st>>>(x, dy, rows, gamma, eps, dx, accumulate, scr);
   else if (d % 128 == 0 && al16(x) && al16(dy) && al16(dx) && al16(gamma)) {
     switch (d / 128) {
-      case 1: k_ln_bwd_v4<1><<<grid, 256, smem, st>>>(x, dy, rows, gamma, eps, dx, accumulate, g_red_scratch); break;
-      case 2: k_ln_bwd_v4<2><<<grid, 256, smem, st>>>(x, dy, rows, gamma, eps, dx, accumulate, g_red_scratch); break;
-      case 3: k_ln_bwd_v4<3><<<grid, 256, smem, st>>>(x, dy, rows, gamma, eps, dx, accumulate, g_red_scratch); break;
-      default: k_ln_bwd_v4<4><<<grid, 256, smem, st>>>(x, dy, rows, gamma, eps, dx, accumulate, g_red_scratch); break;
+      case 1: k_ln_bwd_v4<1><<<grid, 256, smem, st>>>(x, dy, rows, gamma, eps, dx, accumulate, scr); break;
+      case 2: k_ln_bwd_v4<2><<<grid, 256, smem, st>>>(x, dy, rows, gamma, eps, dx, accumulate, scr); break;
+      case 3: k_ln_bwd_v4<3><<<grid, 256, smem, st>>>(x, dy, rows, gamma, eps, dx, accumulate, scr); break;
+      default: k_ln_bwd_v4<4><<<grid, 256, smem, st>>>(x, dy, rows, gamma, eps, dx, accumulate, scr); break;
     }
   }
-  else if (d <= 32) k_ln_bwd_gen<1><<<grid, 256, smem, st>>>(x, dy, rows, d, gamma, eps, dx, accumulate, g_red_scratch);
-  else if (d <= 64) k_ln_bwd_gen<2><<<grid, 256, smem, st>>>(x, dy, rows, d, gamma, eps, dx, accumulate, g_red_scratch);
-  else if (d <= 384) k_ln_bwd_gen<12><<<grid, 256, smem, st>>>(x, dy, rows, d, gamma, eps, dx, accumulate, g_red_scratch);
-  else k_ln_bwd_gen<16><<<grid, 256, smem, st>>>(x, dy, rows, d, gamma, eps, dx, accumulate, g_red_scratch);
+  else if (d <= 32) k_ln_bwd_gen<1><<<grid, 256, smem, st>>>(x, dy, rows, d, gamma, eps, dx, accumulate, scr);
+  else if (d <= 64) k_ln_bwd_gen<2><<<grid, 256, smem, st>>>(x, dy, rows, d, gamma, eps, dx, accumulate, scr);
+  else if (d <= 384) k_ln_bwd_gen<12><<<grid, 256, smem, st>>>(x, dy, rows, d, gamma, eps, dx, accumulate, scr);
+  else k_ln_bwd_gen<16><<<grid, 256, smem, st>>>(x, dy, rows, d, gamma, eps, dx, accumulate, scr);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  return reduce_partials((int)grid, 2LL * d, dgamma, d, dbeta, st);
+  return reduce_partials(scr, (int)grid, 2LL * d, dgamma, d, dbeta, st);
 }
 
 // =================================================================================================
@@ -1416,8 +1505,10 @@ cudaError_t launch_embed_wgrad(const float* x2d, const uint8_t* mask, const int*
   if (256 % d) return cudaErrorInvalidValue;
   const unsigned grid = (unsigned)std::min<long long>(148 * 4, (rows + 255) / 256);
   if ((size_t)grid * 2 * d > g_red_floats) return cudaErrorInvalidValue;
-  k_embed_wgrad<<<grid, 256, 0, st>>>(x2d, mask, list, J, de, rows, d, g_red_scratch);
-  return reduce_partials((int)grid, 2LL * d, dW, 2LL * d, nullptr, st);
+  float* scr = red_region((size_t)grid * 2 * d, st);
+  if (!scr) return cudaErrorInvalidValue;
+  k_embed_wgrad<<<grid, 256, 0, st>>>(x2d, mask, list, J, de, rows, d, scr);
+  return reduce_partials(scr, (int)grid, 2LL * d, dW, 2LL * d, nullptr, st);
 }
 
 // Token fill (net:350-352), dense form used in training:

@@ -54,6 +54,7 @@ struct TrainState {
   int attn_split = 3;                           // attn_mma.cu: 2 = bf16 hi + lo planes (2^-16 per product), 3 = compensated TF32, 1 = TF32
   float* wg_scratch = nullptr;                  // split-K partial tiles of the tensor-core wgrad (wgrad_tc.cu)
   float* red_scratch = nullptr;                 // partial slabs of the deterministic two-pass reductions (train_kernels.cu)
+  float* red_arena = nullptr;                   // ... of the backward pass, whose second passes are batched (RED_ARENA_FLOATS)
   struct PackedQkv { float *W = nullptr, *b = nullptr, *dW = nullptr, *db = nullptr; };
   std::unordered_map<const float*, PackedQkv> pk;   // W_q -> [W_q | W_k | W_v] (d, 3d), bias (3d) and their gradient slabs
   std::unordered_set<const float*> pk_valid;         // packed copies refreshed once per step
@@ -72,6 +73,11 @@ static float* G(uu_model* m, const std::string& g, int i) {   // gradient slot o
   const size_t off = tensor_offset(m, g, i);
   return off == (size_t)-1 ? nullptr : m->grads + off;
 }
+
+constexpr size_t RED_ARENA_FLOATS = (size_t)48 << 20;      // 192 MB: about one backward pass of 512 windows between flushes
+struct DeferGuard {                                         // the deferred-reduction mode never outlives train_fb
+  ~DeferGuard() { train_reduce_defer_abort(); }
+};
 
 struct Ctx {
   uu_model* m;
@@ -106,7 +112,7 @@ __global__ void k_transpose_f32(const float* __restrict__ in, int rows, int cols
 // tcgen05 kind::tf32 path for the large, regular GEMMs (math mode 1)
 static bool tf32_ok(const Ctx& c, const void* A, long long lda, const void* Bt, long long ldb, int M, int N, int K,
                     const void* C, long long ldc) {
-  return c.t->math == 1 && M >= 64 && N >= 64 && N % 64 == 0 && K >= 64 && K % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 &&
+  return c.t->math == 1 && M >= 128 && N >= 64 && N % 64 == 0 && K >= 64 && K % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 &&
          ldc % 4 == 0 && ((uintptr_t)A & 15) == 0 && ((uintptr_t)Bt & 15) == 0 && ((uintptr_t)C & 15) == 0;
 }
 static int tf32_gemm(Ctx& c, const float* A, long long lda, int M, int K, const float* Bt, long long ldb, int N,
@@ -450,6 +456,7 @@ static int ensure_train(uu_model* m, int B) {
   }
   if (falloc(t, &t->wg_scratch, wgrad_tc_scratch_bytes() / sizeof(float))) return 1;
   if (falloc(t, &t->red_scratch, train_reduce_scratch_floats() + 4096)) return 1;
+  if (falloc(t, &t->red_arena, RED_ARENA_FLOATS)) return 1;
   t->B = B;
   return 0;
 }
@@ -594,6 +601,10 @@ static int train_fb(uu_model* m, const float* x2d, const uint8_t* mask, const fl
   UU_CUDA(cudaMemcpyAsync(loss_out, t->loss, sizeof(float), cudaMemcpyDeviceToDevice, stream));
 
   // ================= backward =================
+  // second passes of the two-pass reductions are recorded and run in one launch per flush (before each gradient bucket
+  // leaves, and at the end)
+  DeferGuard defer_guard;
+  train_reduce_defer_begin(t->red_arena, RED_ARENA_FLOATS);
   float* dx = t->dx_s[s.n_strided - 1];
   if (lin_bwd(c, x_in, d, t->dcentral, 3 * J, B, d, 3 * J, W(m, "strided_temporal_fc", 0), dx, d, 0,
               G(m, "strided_temporal_fc", 0), G(m, "strided_temporal_fc", 1)))
@@ -635,11 +646,13 @@ static int train_fb(uu_model* m, const float* x2d, const uint8_t* mask, const fl
               G(m, "temporal_fc", 1)))
     return 1;
   const size_t off_temporal = tensor_offset(m, "temporal_block_1", 0), off_strided = tensor_offset(m, "strided_temporal_block_1", 0);
+  UU_TL(train_reduce_flush(stream));
   if (overlap_comm && comm_allreduce_range(m, off_strided, m->n_alloc, 0, stream)) return 1;
   for (int i = s.temporal_depth - 1; i >= 0; --i) {
     const uint8_t* km = (use_mask && i < s.first_strided_token_attention_layer) ? mask : nullptr;
     if (block_bwd(c, tp_dims, "temporal_block_" + std::to_string(i + 1), t->tp[i], km, N, t->dx_t)) return 1;
   }
+  UU_TL(train_reduce_flush(stream));
   if (overlap_comm && comm_allreduce_range(m, off_temporal, off_strided, 1, stream)) return 1;
   // temporal input: x = m*s4 + (1-m)*token + PE
   UU_TL(launch_period_sum(t->dx_t, R, N, d, nullptr, 0, G(m, "temporal_pe", 0), stream));
@@ -658,6 +671,7 @@ static int train_fb(uu_model* m, const float* x2d, const uint8_t* mask, const fl
   UU_TL(launch_colsum(t->dx_sp, (int)Rsv, ds, ds, G(m, "keypoint_embedding", 1), stream));
   UU_TL(launch_period_sum(t->dx_sp, Rsv, J, ds, nullptr, 0, G(m, "spatial_pe", 0), stream));
   UU_TL(launch_embed_wgrad(x2d, use_mask ? mask : nullptr, glist, J, t->dx_sp, Rsv, ds, G(m, "keypoint_embedding", 0), stream));
+  UU_TL(train_reduce_defer_end(stream));
   if (overlap_comm) {
     if (comm_allreduce_range(m, 0, off_temporal, 2, stream)) return 1;
     if (comm_allreduce_scalar(m, loss_out, stream)) return 1;
