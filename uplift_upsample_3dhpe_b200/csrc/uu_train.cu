@@ -162,7 +162,7 @@ __global__ void k_unpack_qkv_add(const float* __restrict__ dW, const float* __re
                                  float* __restrict__ gk, float* __restrict__ gv, float* __restrict__ gbq,
                                  float* __restrict__ gbk, float* __restrict__ gbv) {
   const int n = d * 3 * d;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n + 3 * d; i += gridDim.x * blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n + (db ? 3 * d : 0); i += gridDim.x * blockDim.x) {
     if (i < n) {
       const int r = i / (3 * d), c = i - r * 3 * d, k = c / d, cc = c - k * d;
       (k == 0 ? gq : k == 1 ? gk : gv)[r * d + cc] += dW[i];
@@ -333,14 +333,23 @@ static int attn_half_bwd(Ctx& c, const BlkDims& b, const std::string& g, BlkTape
     if (lin_bwd(c, tp.y1, d, t->tmp_qkv, 3 * d, (int)R, d, 3 * d, pq.W, t->tmp2, d, 0, nullptr, nullptr)) return 1;
     for (int k = 0; k < 3; ++k)
       UU_TL(launch_wgrad_skinny(tp.y1, d, t->tmp_qkv + k * d, 3 * d, R, d, d, G(m, g, 2 + 2 * k), G(m, g, 3 + 2 * k), c.st));
-  } else {
+  } else if (c.t->math == 1 && wgrad_tc_ok(tp.y1, d, t->tmp_qkv, 3 * d, R, d, 3 * d)) {
+    // one tcgen05 wgrad over the packed (d, 3d) slab (its split-K reducer runs at once), added back onto the three tensors;
+    // the bias gradients go straight to their slots (their second pass is deferred: nothing may read a packed copy of them)
     UU_CUDA(cudaMemsetAsync(pq.dW, 0, sizeof(float) * (size_t)d * 3 * d, c.st));
-    UU_CUDA(cudaMemsetAsync(pq.db, 0, sizeof(float) * 3 * (size_t)d, c.st));
-    if (lin_bwd(c, tp.y1, d, t->tmp_qkv, 3 * d, (int)R, d, 3 * d, pq.W, t->tmp2, d, 0, pq.dW, pq.db)) return 1;
-    const int n = d * 3 * d + 3 * d;
-    k_unpack_qkv_add<<<std::min(148 * 4, (n + 255) / 256), 256, 0, c.st>>>(pq.dW, pq.db, d, G(m, g, 2), G(m, g, 4), G(m, g, 6),
-                                                                         G(m, g, 3), G(m, g, 5), G(m, g, 7));
+    if (lin_bwd(c, tp.y1, d, t->tmp_qkv, 3 * d, (int)R, d, 3 * d, pq.W, t->tmp2, d, 0, pq.dW, nullptr)) return 1;
+    const int n = d * 3 * d;
+    k_unpack_qkv_add<<<std::min(148 * 4, (n + 255) / 256), 256, 0, c.st>>>(pq.dW, nullptr, d, G(m, g, 2), G(m, g, 4), G(m, g, 6),
+                                                                         nullptr, nullptr, nullptr);
     UU_CUDA(cudaGetLastError());
+    for (int k = 0; k < 3; ++k) UU_TL(launch_colsum(t->tmp_qkv + k * d, (int)R, d, 3 * d, G(m, g, 3 + 2 * k), c.st));
+  } else {
+    // packed input gradient, per-tensor weight / bias gradients written straight to their slots
+    if (lin_bwd(c, tp.y1, d, t->tmp_qkv, 3 * d, (int)R, d, 3 * d, pq.W, t->tmp2, d, 0, nullptr, nullptr)) return 1;
+    for (int k = 0; k < 3; ++k)
+      if (lin_bwd(c, tp.y1, d, t->tmp_qkv + k * d, 3 * d, (int)R, d, d, nullptr, nullptr, 0, 0, G(m, g, 2 + 2 * k),
+                  G(m, g, 3 + 2 * k)))
+        return 1;
   }
   UU_TL(launch_ln_bwd_gen(tp.x0, t->tmp2, R, d, W(m, g, 0), 1e-5f, dx, 1, G(m, g, 0), G(m, g, 1), c.st));
   return 0;
