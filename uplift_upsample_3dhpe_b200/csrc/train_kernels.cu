@@ -1061,20 +1061,17 @@ __global__ void __launch_bounds__(128) k_attention_bwd(const float* __restrict__
 // =================================================================================================
 // Spatial attention of the training step (17 joint tokens, 8 heads of dimension 4, no key mask; vit:99-130 inside
 // net:313-333): the generic kernels spend one CTA per (frame, head) on a 17 x 17 problem.  Here one WARP owns a frame:
-// its q | k | v rows (17 x 96 floats, contiguous in the tape) sit in the warp's shared-memory slot and the 17 x 8 = 136
-// (token, head) pairs are dealt to the lanes, head fastest (5 rounds, 85 % of the lanes busy; one lane per token left 15
-// of 32 idle).  All lanes of a round walk the same key / query index, so every shared-memory read is 8 distinct 16-byte
-// chunks (the heads) broadcast to the lanes that share them: one wavefront, no conflicts.
-// Backward in two passes without any 17 x 17 tile: pass 1, pair = (query i, head): softmax row, dot = sum_j dA_ij A_ij,
-// dQ_i, and the row statistics (max, 1 / sum, dot) parked in shared memory; pass 2, pair = (key j, head): the score column
-// is recomputed with the same expression (bit-identical to pass 1), A_ij from the statistics, dK_j = scale sum_i dS_ij q_i,
-// dV_j = sum_i A_ij dO_i.  Results go straight to global memory (a round writes 128-byte runs).  S is a compile-time
-// constant (with a run-time S the unrolled loops were half predicated-off instructions); heads * 4 == 32.
+// its q | k | v rows (17 x 96 floats, contiguous in the tape) are staged in the warp's shared-memory slot, lane = (head h,
+// key group g) with h = lane & 7, g = lane >> 3, and the lane keeps the k and v rows of ITS keys (j = g, g + 4, ..., five at
+// most) of head h in registers for the whole frame.  The warp then walks the 17 queries: every lane scores the query against
+// its own keys, the softmax statistics (max, sum, and in the backward pass sum_j dA_ij A_ij) are combined over the four key
+// groups with two shuffles each, and the lane accumulates what belongs to its keys — the forward output (reduced over the
+// groups), or dQ_i (reduced) plus dK_j and dV_j (private, written once per frame).  One pass, no 17 x 17 tile, no
+// recomputation, and shared memory is read twice per query (q_i, dO_i) instead of ~50 times per (query, head) pair: the
+// earlier (query, head)-per-lane form was bound by shared-memory bandwidth (every 16-byte key / value chunk was fetched again
+// by each quarter-warp: 76 % of the LSU peak, 186 us per layer).  S is a compile-time constant; heads * 4 == 32.
 // =================================================================================================
 constexpr int SA_WARPS = 4;
-// the loops below are fully unrolled; without a scheduling fence every few iterations ptxas hoists all 17 (x 2 or 3) float4
-// shared-memory loads of a loop to its top (255 registers, two resident CTAs)
-#define UU_SA_FENCE(idx) do { if (((idx) & 3) == 3) asm volatile("" ::: "memory"); } while (0)
 // N float4 from global to the warp's shared-memory slot, all loads in flight before the first store
 template <int N>
 __device__ __forceinline__ void sa_stage(float4* __restrict__ dst, const float4* __restrict__ src, int lane) {
@@ -1088,122 +1085,129 @@ __device__ __forceinline__ void sa_stage(float4* __restrict__ dst, const float4*
     if (lane + 32 * u < N) dst[lane + 32 * u] = v[u];
 }
 __device__ __forceinline__ float dot4(const float4& a, const float4& b) { return fmaf(a.w, b.w, fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x))); }
+__device__ __forceinline__ float grp_sum(float v) {          // over the four key groups (lanes h, h + 8, h + 16, h + 24)
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
+  return v;
+}
+__device__ __forceinline__ float grp_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 8));
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 16));
+  return v;
+}
 template <int S>
 __global__ void __launch_bounds__(SA_WARPS * 32, 6) k_attn_small_fwd(const float* __restrict__ qkv, long long frames,
-                                                                   float* __restrict__ out) {
+                                                                      float* __restrict__ out) {
+  constexpr int NK = (S + 3) / 4;
   __shared__ __align__(16) float sa_sm[SA_WARPS][S * 96];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, h = lane & 7, grp = lane >> 3;
   float* sq = sa_sm[warp];
   const float scale = 0.5f;                            // 1 / sqrt(4)
   for (long long f = (long long)blockIdx.x * SA_WARPS + warp; f < frames; f += (long long)gridDim.x * SA_WARPS) {
-    const float4* src = reinterpret_cast<const float4*>(qkv + f * S * 96);
     __syncwarp();
-    sa_stage<S * 24>(reinterpret_cast<float4*>(sq), src, lane);
+    sa_stage<S * 24>(reinterpret_cast<float4*>(sq), reinterpret_cast<const float4*>(qkv + f * S * 96), lane);
     __syncwarp();
-#pragma unroll 1
-    for (int item = lane; item < S * 8; item += 32) {
-      const int i = item >> 3, h = item & 7;
+    float4 kk[NK], vv[NK];
+#pragma unroll
+    for (int u = 0; u < NK; ++u) {
+      const int j = grp + 4 * u;
+      kk[u] = j < S ? *reinterpret_cast<const float4*>(sq + j * 96 + 32 + 4 * h) : make_float4(0.f, 0.f, 0.f, 0.f);
+      vv[u] = j < S ? *reinterpret_cast<const float4*>(sq + j * 96 + 64 + 4 * h) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll 2
+    for (int i = 0; i < S; ++i) {
       const float4 q = *reinterpret_cast<const float4*>(sq + i * 96 + 4 * h);
-      float sc[S];
+      float p[NK];
       float m = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < S; ++j) {
-        sc[j] = dot4(q, *reinterpret_cast<const float4*>(sq + j * 96 + 32 + 4 * h)) * scale;
-        m = fmaxf(m, sc[j]);
-        UU_SA_FENCE(j);
+      for (int u = 0; u < NK; ++u) {
+        p[u] = (grp + 4 * u < S) ? dot4(q, kk[u]) * scale : -INFINITY;
+        m = fmaxf(m, p[u]);
       }
+      m = grp_max(m);
       float l = 0.f;
       float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int j = 0; j < S; ++j) {
-        const float p = __expf(sc[j] - m);
-        const float4 v = *reinterpret_cast<const float4*>(sq + j * 96 + 64 + 4 * h);
-        l += p;
-        o.x = fmaf(p, v.x, o.x); o.y = fmaf(p, v.y, o.y); o.z = fmaf(p, v.z, o.z); o.w = fmaf(p, v.w, o.w);
-        UU_SA_FENCE(j);
+      for (int u = 0; u < NK; ++u) {
+        p[u] = __expf(p[u] - m);
+        l += p[u];
+        o.x = fmaf(p[u], vv[u].x, o.x); o.y = fmaf(p[u], vv[u].y, o.y); o.z = fmaf(p[u], vv[u].z, o.z); o.w = fmaf(p[u], vv[u].w, o.w);
       }
-      const float inv = 1.f / l;
-      *reinterpret_cast<float4*>(out + f * S * 32 + i * 32 + 4 * h) = make_float4(o.x * inv, o.y * inv, o.z * inv, o.w * inv);
+      const float inv = 1.f / grp_sum(l);
+      o.x = grp_sum(o.x); o.y = grp_sum(o.y); o.z = grp_sum(o.z); o.w = grp_sum(o.w);
+      if (grp == 0)
+        *reinterpret_cast<float4*>(out + f * S * 32 + i * 32 + 4 * h) = make_float4(o.x * inv, o.y * inv, o.z * inv, o.w * inv);
     }
   }
 }
 
 template <int S>
-__global__ void __launch_bounds__(SA_WARPS * 32, 5) k_attn_small_bwd(const float* __restrict__ qkv, const float* __restrict__ dO,
-                                                                   long long frames, float* __restrict__ dqkv) {
-  constexpr int SLOT = S * 96 + S * 32 + S * 8 * 4;    // q | k | v rows, dO rows, (max, 1 / sum, dot, -) per (query, head)
+__global__ void __launch_bounds__(SA_WARPS * 32, 4) k_attn_small_bwd(const float* __restrict__ qkv, const float* __restrict__ dO,
+                                                                      long long frames, float* __restrict__ dqkv) {
+  constexpr int NK = (S + 3) / 4, SLOT = S * 96 + S * 32;      // q | k | v rows, dO rows
   __shared__ __align__(16) float sa_sm[SA_WARPS][SLOT];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, h = lane & 7, grp = lane >> 3;
   float* sq = sa_sm[warp];
   float* sd = sq + S * 96;
-  float4* sst = reinterpret_cast<float4*>(sd + S * 32);
   const float scale = 0.5f;
   for (long long f = (long long)blockIdx.x * SA_WARPS + warp; f < frames; f += (long long)gridDim.x * SA_WARPS) {
-    const float4* src = reinterpret_cast<const float4*>(qkv + f * S * 96);
-    const float4* gsrc = reinterpret_cast<const float4*>(dO + f * S * 32);
     float* dst = dqkv + f * S * 96;
     __syncwarp();
-    sa_stage<S * 24>(reinterpret_cast<float4*>(sq), src, lane);
-    sa_stage<S * 8>(reinterpret_cast<float4*>(sd), gsrc, lane);
+    sa_stage<S * 24>(reinterpret_cast<float4*>(sq), reinterpret_cast<const float4*>(qkv + f * S * 96), lane);
+    sa_stage<S * 8>(reinterpret_cast<float4*>(sd), reinterpret_cast<const float4*>(dO + f * S * 32), lane);
     __syncwarp();
-    // ---- pass 1: pair = (query i, head h)
+    float4 kk[NK], vv[NK], dk[NK], dv[NK];
+#pragma unroll
+    for (int u = 0; u < NK; ++u) {
+      const int j = grp + 4 * u;
+      kk[u] = j < S ? *reinterpret_cast<const float4*>(sq + j * 96 + 32 + 4 * h) : make_float4(0.f, 0.f, 0.f, 0.f);
+      vv[u] = j < S ? *reinterpret_cast<const float4*>(sq + j * 96 + 64 + 4 * h) : make_float4(0.f, 0.f, 0.f, 0.f);
+      dk[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      dv[u] = dk[u];
+    }
 #pragma unroll 1
-    for (int item = lane; item < S * 8; item += 32) {
-      const int i = item >> 3, h = item & 7;
+    for (int i = 0; i < S; ++i) {
       const float4 q = *reinterpret_cast<const float4*>(sq + i * 96 + 4 * h);
       const float4 g = *reinterpret_cast<const float4*>(sd + i * 32 + 4 * h);
-      float a[S], da[S];
+      float a[NK], da[NK];
       float m = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < S; ++j) {
-        a[j] = dot4(q, *reinterpret_cast<const float4*>(sq + j * 96 + 32 + 4 * h)) * scale;
-        m = fmaxf(m, a[j]);
-        UU_SA_FENCE(j);
+      for (int u = 0; u < NK; ++u) {
+        a[u] = (grp + 4 * u < S) ? dot4(q, kk[u]) * scale : -INFINITY;
+        m = fmaxf(m, a[u]);
       }
+      m = grp_max(m);
       float l = 0.f;
 #pragma unroll
-      for (int j = 0; j < S; ++j) { a[j] = __expf(a[j] - m); l += a[j]; }
-      const float inv = 1.f / l;
+      for (int u = 0; u < NK; ++u) { a[u] = __expf(a[u] - m); l += a[u]; }
+      const float inv = 1.f / grp_sum(l);
       float dot = 0.f;
 #pragma unroll
-      for (int j = 0; j < S; ++j) {
-        da[j] = dot4(g, *reinterpret_cast<const float4*>(sq + j * 96 + 64 + 4 * h));
-        a[j] *= inv;
-        dot = fmaf(da[j], a[j], dot);
-        UU_SA_FENCE(j);
+      for (int u = 0; u < NK; ++u) {
+        da[u] = dot4(g, vv[u]);
+        a[u] *= inv;
+        dot = fmaf(da[u], a[u], dot);
       }
+      dot = grp_sum(dot);
       float4 dq = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int j = 0; j < S; ++j) {
-        const float ds = a[j] * (da[j] - dot);
-        const float4 k = *reinterpret_cast<const float4*>(sq + j * 96 + 32 + 4 * h);
-        dq.x = fmaf(ds, k.x, dq.x); dq.y = fmaf(ds, k.y, dq.y); dq.z = fmaf(ds, k.z, dq.z); dq.w = fmaf(ds, k.w, dq.w);
-        UU_SA_FENCE(j);
+      for (int u = 0; u < NK; ++u) {
+        const float ds = a[u] * (da[u] - dot);
+        dq.x = fmaf(ds, kk[u].x, dq.x); dq.y = fmaf(ds, kk[u].y, dq.y); dq.z = fmaf(ds, kk[u].z, dq.z); dq.w = fmaf(ds, kk[u].w, dq.w);
+        dk[u].x = fmaf(ds, q.x, dk[u].x); dk[u].y = fmaf(ds, q.y, dk[u].y); dk[u].z = fmaf(ds, q.z, dk[u].z); dk[u].w = fmaf(ds, q.w, dk[u].w);
+        dv[u].x = fmaf(a[u], g.x, dv[u].x); dv[u].y = fmaf(a[u], g.y, dv[u].y); dv[u].z = fmaf(a[u], g.z, dv[u].z); dv[u].w = fmaf(a[u], g.w, dv[u].w);
       }
-      sst[item] = make_float4(m, inv, dot, 0.f);
-      *reinterpret_cast<float4*>(dst + i * 96 + 4 * h) = make_float4(dq.x * scale, dq.y * scale, dq.z * scale, dq.w * scale);
+      dq.x = grp_sum(dq.x); dq.y = grp_sum(dq.y); dq.z = grp_sum(dq.z); dq.w = grp_sum(dq.w);
+      if (grp == 0)
+        *reinterpret_cast<float4*>(dst + i * 96 + 4 * h) = make_float4(dq.x * scale, dq.y * scale, dq.z * scale, dq.w * scale);
     }
-    __syncwarp();
-    // ---- pass 2: pair = (key j, head h)
-#pragma unroll 1
-    for (int item = lane; item < S * 8; item += 32) {
-      const int j = item >> 3, h = item & 7;
-      const float4 k = *reinterpret_cast<const float4*>(sq + j * 96 + 32 + 4 * h);
-      const float4 v = *reinterpret_cast<const float4*>(sq + j * 96 + 64 + 4 * h);
-      float4 dk = make_float4(0.f, 0.f, 0.f, 0.f), dv = dk;
 #pragma unroll
-      for (int i = 0; i < S; ++i) {
-        const float4 q = *reinterpret_cast<const float4*>(sq + i * 96 + 4 * h);
-        const float4 g = *reinterpret_cast<const float4*>(sd + i * 32 + 4 * h);
-        const float4 st = sst[i * 8 + h];
-        const float aa = __expf(dot4(q, k) * scale - st.x) * st.y;      // same expression as pass 1: identical bits
-        const float ds = aa * (dot4(g, v) - st.z);
-        dk.x = fmaf(ds, q.x, dk.x); dk.y = fmaf(ds, q.y, dk.y); dk.z = fmaf(ds, q.z, dk.z); dk.w = fmaf(ds, q.w, dk.w);
-        dv.x = fmaf(aa, g.x, dv.x); dv.y = fmaf(aa, g.y, dv.y); dv.z = fmaf(aa, g.z, dv.z); dv.w = fmaf(aa, g.w, dv.w);
-        UU_SA_FENCE(i);
+    for (int u = 0; u < NK; ++u) {
+      const int j = grp + 4 * u;
+      if (j < S) {
+        *reinterpret_cast<float4*>(dst + j * 96 + 32 + 4 * h) = make_float4(dk[u].x * scale, dk[u].y * scale, dk[u].z * scale, dk[u].w * scale);
+        *reinterpret_cast<float4*>(dst + j * 96 + 64 + 4 * h) = dv[u];
       }
-      *reinterpret_cast<float4*>(dst + j * 96 + 32 + 4 * h) = make_float4(dk.x * scale, dk.y * scale, dk.z * scale, dk.w * scale);
-      *reinterpret_cast<float4*>(dst + j * 96 + 64 + 4 * h) = dv;
     }
   }
 }
@@ -1216,7 +1220,7 @@ cudaError_t launch_attention_small_fwd(const float* qkv, long long frames, int S
 }
 cudaError_t launch_attention_small_bwd(const float* qkv, const float* dO, long long frames, int S, float* dqkv, cudaStream_t st) {
   if (S != 17) return cudaErrorInvalidValue;
-  const unsigned grid = (unsigned)std::min<long long>((frames + SA_WARPS - 1) / SA_WARPS, 148 * 5);
+  const unsigned grid = (unsigned)std::min<long long>((frames + SA_WARPS - 1) / SA_WARPS, 148 * 4);
   k_attn_small_bwd<17><<<grid, SA_WARPS * 32, 0, st>>>(qkv, dO, frames, dqkv);
   return cudaGetLastError();
 }
