@@ -141,34 +141,52 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_spatial_block_fwd_tape(Params
         }
     }
     __syncwarp();
-    // attention: 17 queries x 8 heads = 136 (query, head) pairs over the lanes, head fastest (vit:117-129), scale 1/2
-#pragma unroll 1
-    for (int it = lane; it < J * HEADS; it += 32) {
-      const int i = it >> 3, h = it & 7;
-      const float4 q = *reinterpret_cast<const float4*>(qs + i * QS + 4 * h);
-      float s[J];
-      float mx = -INFINITY;
+    // attention (vit:117-129, scale 1/2): lane = (head h, key group g) keeps the k / v rows of its keys j = g, g + 4, ... in
+    // registers, the warp walks the 17 queries and combines the softmax statistics and the output over the four key groups
+    // with shuffles (see k_attn_small_fwd in train_kernels.cu: shared memory is read once per query instead of 34 times)
+    {
+      constexpr int NK = (J + 3) / 4;
+      const int h = lane & 7, grp = lane >> 3;
+      float4 kk[NK], vv[NK];
 #pragma unroll
-      for (int j = 0; j < J; ++j) {
-        const float4 kk = *reinterpret_cast<const float4*>(qs + j * QS + 32 + 4 * h);
-        s[j] = fmaf(q.w, kk.w, fmaf(q.z, kk.z, fmaf(q.y, kk.y, q.x * kk.x))) * 0.5f;
-        mx = fmaxf(mx, s[j]);
-        if ((j & 3) == 3) asm volatile("" ::: "memory");      // keep ptxas from hoisting all 17 loads (registers)
+      for (int u = 0; u < NK; ++u) {
+        const int j = grp + 4 * u;
+        kk[u] = j < J ? *reinterpret_cast<const float4*>(qs + j * QS + 32 + 4 * h) : make_float4(0.f, 0.f, 0.f, 0.f);
+        vv[u] = j < J ? *reinterpret_cast<const float4*>(qs + j * QS + 64 + 4 * h) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      float sum = 0.f;
+#pragma unroll 2
+      for (int i = 0; i < J; ++i) {
+        const float4 q = *reinterpret_cast<const float4*>(qs + i * QS + 4 * h);
+        float pr[NK];
+        float mx = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < J; ++j) { s[j] = expf(s[j] - mx); sum += s[j]; }
-      const float inv = 1.f / sum;
-      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int u = 0; u < NK; ++u) {
+          pr[u] = (grp + 4 * u < J) ? fmaf(q.w, kk[u].w, fmaf(q.z, kk[u].z, fmaf(q.y, kk[u].y, q.x * kk[u].x))) * 0.5f : -INFINITY;
+          mx = fmaxf(mx, pr[u]);
+        }
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+        float sum = 0.f;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int j = 0; j < J; ++j) {
-        const float4 v = *reinterpret_cast<const float4*>(qs + j * QS + 64 + 4 * h);
-        const float pj = s[j] * inv;
-        o.x = fmaf(pj, v.x, o.x); o.y = fmaf(pj, v.y, o.y); o.z = fmaf(pj, v.z, o.z); o.w = fmaf(pj, v.w, o.w);
-        if ((j & 3) == 3) asm volatile("" ::: "memory");
+        for (int u = 0; u < NK; ++u) {
+          pr[u] = expf(pr[u] - mx);
+          sum += pr[u];
+          o.x = fmaf(pr[u], vv[u].x, o.x); o.y = fmaf(pr[u], vv[u].y, o.y); o.z = fmaf(pr[u], vv[u].z, o.z); o.w = fmaf(pr[u], vv[u].w, o.w);
+        }
+#pragma unroll
+        for (int sh = 8; sh <= 16; sh <<= 1) {
+          sum += __shfl_xor_sync(0xffffffffu, sum, sh);
+          o.x += __shfl_xor_sync(0xffffffffu, o.x, sh); o.y += __shfl_xor_sync(0xffffffffu, o.y, sh);
+          o.z += __shfl_xor_sync(0xffffffffu, o.z, sh); o.w += __shfl_xor_sync(0xffffffffu, o.w, sh);
+        }
+        if (grp == 0) {
+          const float inv = 1.f / sum;
+          o.x *= inv; o.y *= inv; o.z *= inv; o.w *= inv;
+          *reinterpret_cast<float4*>(ys + i * YS + 4 * h) = o;             // heads merged: channel = 4 h + dim
+          *reinterpret_cast<float4*>(p.o + (row0 + i) * D + 4 * h) = o;
+        }
       }
-      *reinterpret_cast<float4*>(ys + i * YS + 4 * h) = o;               // heads merged: channel = 4 h + dim
-      *reinterpret_cast<float4*>(p.o + (row0 + i) * D + 4 * h) = o;
     }
     __syncwarp();
     {  // x1 = x0 + scale * (o @ Wp + bp)
