@@ -112,7 +112,7 @@ __global__ void k_transpose_f32(const float* __restrict__ in, int rows, int cols
 // tcgen05 kind::tf32 path for the large, regular GEMMs (math mode 1)
 static bool tf32_ok(const Ctx& c, const void* A, long long lda, const void* Bt, long long ldb, int M, int N, int K,
                     const void* C, long long ldc) {
-  return c.t->math == 1 && M >= 128 && N >= 64 && N % 64 == 0 && K >= 64 && K % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 &&
+  return c.t->math == 1 && M >= 256 && N >= 64 && N % 64 == 0 && K >= 64 && K % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 &&
          ldc % 4 == 0 && ((uintptr_t)A & 15) == 0 && ((uintptr_t)Bt & 15) == 0 && ((uintptr_t)C & 15) == 0;
 }
 static int tf32_gemm(Ctx& c, const float* A, long long lda, int M, int K, const float* Bt, long long ldb, int N,
