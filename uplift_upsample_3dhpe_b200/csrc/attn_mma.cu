@@ -11,9 +11,9 @@
 // The default of the training step is the third form (namespace amb, "nsplit 2"): operands are split into bf16 hi + bf16 lo
 // planes ONCE, while the rows are staged into shared memory (the two planes together take the 4 bytes per element the fp32
 // rows took), and a b ~ a_lo b_hi + a_hi b_lo + a_hi b_hi runs on `mma.sync.m16n8k16` bf16: 16 mantissa bits per operand
-// (2^-16 relative per product, 30x finer than TF32) at a quarter of the tensor-pipe time of the compensated TF32 form —
-// legacy TF32 MMAs issue at 16 cycles per 16x8x8 on sm_100a (measured: 385 us per backward launch, MMA-bound), bf16 ones
-// at 8 cycles per 16x8x16 — and without any split arithmetic in the inner loops.  Fragment loads are conflict-free 32-bit
+// (2^-16 relative per product, 30x finer than TF32) with half the MMA instructions of the compensated TF32 form for the same
+// products (ncu: 8.6 cycles per m16n8k16 bf16 MMA and scheduler, tensor pipe 46 % busy in the backward kernel) and without any
+// split arithmetic in the inner loops.  Fragment loads are conflict-free 32-bit
 // reads (row stride DH / 2 + 4 words) and `ldmatrix.trans` for the operands that are contracted over their ROW index.
 //
 // Forward: warp w owns queries 16w..16w+15.  S = Q K^T lands in the m16n8 accumulator layout (row g / g+8, columns
