@@ -75,6 +75,35 @@ __device__ __forceinline__ void warp_linear(const float* __restrict__ in, int in
   }
 }
 
+// 32-column layers (projection, fc2): with one column per lane every lane re-reads all 17 rows (17 broadcast 16-byte reads per
+// four k for 68 FMAs: these two layers were 60 % of the kernel's shared-memory traffic for a third of its FMAs).  Here a half-warp
+// takes half of the rows (0..8 | 9..16) and a lane two adjacent columns: 9 row reads per four k for 72 FMAs.
+// acc[i][0..1] = bias + sum_k in[r0 + i][k] W[k][c0 .. c0 + 1],  r0 = 9 * (lane >> 4), c0 = 2 * (lane & 15); row r0 + 8 of the
+// upper half does not exist (its accumulator is computed on row 16 again and never used).
+template <int K>
+__device__ __forceinline__ void halfwarp_linear32(const float* __restrict__ in, int in_stride, const float* __restrict__ W,
+                                                  const float* __restrict__ bias, float (&acc)[9][2], int lane) {
+  const int r0 = 9 * (lane >> 4), c0 = 2 * (lane & 15);
+  const float2 b = *reinterpret_cast<const float2*>(bias + c0);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) { acc[i][0] = b.x; acc[i][1] = b.y; }
+#pragma unroll 2
+  for (int k = 0; k < K; k += 4) {
+    float2 w[4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) w[kk] = *reinterpret_cast<const float2*>(W + (k + kk) * 32 + c0);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const int r = min(r0 + i, J - 1);
+      const float4 a = *reinterpret_cast<const float4*>(in + r * in_stride + k);
+      acc[i][0] = fmaf(a.x, w[0].x, acc[i][0]); acc[i][1] = fmaf(a.x, w[0].y, acc[i][1]);
+      acc[i][0] = fmaf(a.y, w[1].x, acc[i][0]); acc[i][1] = fmaf(a.y, w[1].y, acc[i][1]);
+      acc[i][0] = fmaf(a.z, w[2].x, acc[i][0]); acc[i][1] = fmaf(a.z, w[2].y, acc[i][1]);
+      acc[i][0] = fmaf(a.w, w[3].x, acc[i][0]); acc[i][1] = fmaf(a.w, w[3].y, acc[i][1]);
+    }
+  }
+}
+
 // Keras LayerNormalization over the 32 channels of each row (lane == channel); result to shared memory and to the tape
 __device__ __forceinline__ void warp_ln_rows(const float* __restrict__ xs, float* __restrict__ ys, float g, float b,
                                              float* __restrict__ tape, int lane) {
@@ -190,14 +219,19 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_spatial_block_fwd_tape(Params
     }
     __syncwarp();
     {  // x1 = x0 + scale * (o @ Wp + bp)
-      float acc[J][1];
-      warp_linear<D, 1>(ys, YS, wbuf + W_P, wbuf + W_BP, acc, lane);
+      float acc[9][2];
+      halfwarp_linear32<D>(ys, YS, wbuf + W_P, wbuf + W_BP, acc, lane);
       const float sc = p.scale ? p.scale[f] : 1.f;
+      const int r0 = 9 * (lane >> 4), c0 = 2 * (lane & 15);
 #pragma unroll
-      for (int r = 0; r < J; ++r) {
-        const float v = fmaf(sc, acc[r][0], xs[r * D + lane]);
-        xs[r * D + lane] = v;
-        p.x1[(row0 + r) * D + lane] = v;
+      for (int i = 0; i < 9; ++i) {
+        const int r = r0 + i;
+        if (r < J) {
+          float2 v = *reinterpret_cast<const float2*>(xs + r * D + c0);
+          v.x = fmaf(sc, acc[i][0], v.x); v.y = fmaf(sc, acc[i][1], v.y);
+          *reinterpret_cast<float2*>(xs + r * D + c0) = v;
+          *reinterpret_cast<float2*>(p.x1 + (row0 + r) * D + c0) = v;
+        }
       }
     }
     __syncwarp();
@@ -221,11 +255,18 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_spatial_block_fwd_tape(Params
     }
     __syncwarp();
     {  // x2 = x1 + scale2 * (hact @ W2 + b2)
-      float acc[J][1];
-      warp_linear<HID, 1>(qs, QS, wbuf + W_FC2, wbuf + W_B2, acc, lane);
+      float acc[9][2];
+      halfwarp_linear32<HID>(qs, QS, wbuf + W_FC2, wbuf + W_B2, acc, lane);
       const float sc = p.scale2 ? p.scale2[f] : 1.f;
+      const int r0 = 9 * (lane >> 4), c0 = 2 * (lane & 15);
 #pragma unroll
-      for (int r = 0; r < J; ++r) p.x2[(row0 + r) * D + lane] = fmaf(sc, acc[r][0], xs[r * D + lane]);
+      for (int i = 0; i < 9; ++i) {
+        const int r = r0 + i;
+        if (r < J) {
+          const float2 x = *reinterpret_cast<const float2*>(xs + r * D + c0);
+          *reinterpret_cast<float2*>(p.x2 + (row0 + r) * D + c0) = make_float2(fmaf(sc, acc[i][0], x.x), fmaf(sc, acc[i][1], x.y));
+        }
+      }
     }
   }
 }
