@@ -174,12 +174,18 @@ int uu_train_forward_backward(uu_model* m, const float* x2d, const uint8_t* mask
 int uu_train_set_token_masking(uu_model* m, float rate);
 int uu_get_token_mask(uu_model* m, float* host, int64_t capacity);
 /* Arithmetic of the training GEMMs.  0 (default): fp32 on CUDA cores, gradients within 2e-3 of fp32 autograd.
- * 1: forward and dgrad GEMMs of the temporal / strided blocks on tcgen05 kind::tf32 (fp32 data, TF32 products, fp32
+ * 1: forward, dgrad and wgrad GEMMs of the temporal / strided blocks on tcgen05 kind::tf32 (fp32 data, TF32 products, fp32
  *    accumulation) -- what TensorFlow 2.4 itself does on Ampere-or-newer GPUs unless
- *    tf.config.experimental.enable_tensor_float_32_execution(False) is called; wgrad, the spatial blocks and everything
- *    that is not a GEMM stay fp32. */
+ *    tf.config.experimental.enable_tensor_float_32_execution(False) is called -- and their attention on mma.sync with bf16
+ *    hi + lo operand planes (16 mantissa bits per operand); the spatial blocks and everything that is not a GEMM stay fp32. */
 int uu_train_set_math(uu_model* m, int mode);
 int uu_grad_buffer(uu_model* m, float** dev_ptr, int64_t* n_floats);
+/* Optimizer state for checkpoint / resume (the reference checkpoints its optimizer with tf.train.Checkpoint, train.py:417-
+ * 430): device pointer to the flat fp32 buffer `which` = 0 (Adam first moment), 1 (Adam second moment) or 2 (EMA copy of the
+ * weights), same layout as the parameters / uu_grad_buffer.  allocate != 0 creates the buffer when it does not exist yet
+ * (moments zero-filled, EMA as a copy of the weights); otherwise *dev_ptr is NULL for a buffer that was never created.  The
+ * step counter lives on the host (uu_train_step's `step`, uu_adamw_step's `t`). */
+int uu_optimizer_state(uu_model* m, int which, int allocate, float** dev_ptr, int64_t* n_floats);
 int uu_get_grad(uu_model* m, const char* group, int index, float* host, int64_t capacity);
 /* Per-sample stochastic-depth factors (mask / keep_prob) drawn by the last step for `branch` 0 (attention residual) or 1
  * (MLP residual) of block `block` in stage 0 (spatial, B * n_tok samples), 1 (temporal) or 2 (strided, B samples): the

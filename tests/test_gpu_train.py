@@ -223,6 +223,38 @@ def test_three_adamw_steps_match_oracle():
     model.close()
 
 
+def test_resume_from_optimizer_state_is_bit_identical():
+    """Checkpoint / resume (train.py:417-430 checkpoints the optimizer next to the weights): weights + Trainer.state_dict()
+    after two steps, loaded into a fresh model and trainer, must reproduce the third step bit for bit (Adam moments, EMA copy,
+    step counter and the counter-based stochastic-depth draws all continue)."""
+    cfg = UpliftUpsampleConfig.preset("h36m_81", BATCH_SIZE=5)
+    spec = spec_from_config(cfg)
+    w0 = weights.init_weights(spec, 1, perturb=True)
+    x, gt, m = _data(cfg, spec, 5)
+    xd, gd, md = torch.from_numpy(x).cuda(), torch.from_numpy(gt).cuda(), torch.from_numpy(m).cuda()
+    model = build_uplift_upsample_transformer(cfg, precision="fp32", weights=w0)
+    tr = Trainer(model, cfg, droppath=True, seed=5, math="tf32")
+    for _ in range(2):
+        tr.train_step(xd, gd, md)
+    torch.cuda.synchronize()
+    w_ck, st_ck = model.get_weights(), tr.state_dict()
+    assert st_ck["iterations"] == 2 and np.abs(st_ck["adam_v"]).max() > 0 and "ema" in st_ck
+    tr.train_step(xd, gd, md)
+    torch.cuda.synchronize()
+    want_w, want_ema = model.get_weights(), tr.get_ema_weights()
+    model.close()
+    model2 = build_uplift_upsample_transformer(cfg, precision="fp32", weights=w_ck)
+    tr2 = Trainer(model2, cfg, droppath=True, seed=5, math="tf32")
+    tr2.load_state_dict(st_ck)
+    tr2.train_step(xd, gd, md)
+    torch.cuda.synchronize()
+    got_w, got_ema = model2.get_weights(), tr2.get_ema_weights()
+    for k in want_w:
+        assert np.array_equal(got_w[k], want_w[k]), k
+        assert np.array_equal(got_ema[k], want_ema[k]), k
+    model2.close()
+
+
 def test_lr_and_wd_schedules():
     from uplift_upsample_3dhpe_b200.train import scheduler_by_name
     s = scheduler_by_name("ExponentialDecay")(initial_learning_rate=4e-5, decay_steps=6000, decay_rate=0.99, staircase=True)

@@ -164,6 +164,7 @@ def _declare(lib) -> None:
     lib.uu_train_config.argtypes = [c_void_p, c_int, c_int, c_float, c_float, P(c_float), c_int, ctypes.c_uint64]
     lib.uu_train_forward_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p]
     lib.uu_grad_buffer.argtypes = [c_void_p, P(c_void_p), P(c_int64)]
+    lib.uu_optimizer_state.argtypes = [c_void_p, c_int, c_int, P(c_void_p), P(c_int64)]
     lib.uu_get_grad.argtypes = [c_void_p, c_char_p, c_int, c_void_p, c_int64]
     lib.uu_get_droppath_scale.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_int64, P(c_float)]
     lib.uu_adamw_step.argtypes = [c_void_p, c_float, c_float, c_float, c_float, c_float, c_int64, c_float, c_void_p]
@@ -224,7 +225,7 @@ EXPORTS = [
     "uu_weight_count", "uu_param_count", "uu_weight_info", "uu_set_weight", "uu_get_weight",
     "uu_forward", "uu_forward_host", "uu_forward_video", "uu_forward_video_host", "uu_op_window_gather",
     "uu_set_flip_order", "uu_forward_tta", "uu_forward_video_tta", "uu_op_keyframe_interp", "uu_op_pose_metrics", "uu_op_world_to_cam_and_2d", "uu_last_launch_count", "uu_set_profiling", "uu_get_profile", "uu_stride_mask",
-    "uu_train_config", "uu_train_forward_backward", "uu_grad_buffer", "uu_get_grad", "uu_get_droppath_scale",
+    "uu_train_config", "uu_train_forward_backward", "uu_grad_buffer", "uu_optimizer_state", "uu_get_grad", "uu_get_droppath_scale",
     "uu_adamw_step", "uu_get_ema_weight", "uu_train_set_math", "uu_train_set_token_masking", "uu_get_token_mask",
     "uu_op_build_gather", "uu_op_token_fill", "uu_op_layernorm", "uu_op_attention", "uu_op_spatial", "uu_op_gemm_f32",
     "uu_op_gemm_bf16", "uu_op_gemm_tf32", "uu_op_ln_gemm_bf16", "uu_op_resid_gemm_bf16",

@@ -770,6 +770,22 @@ int uu_op_wgrad_tf32(const float* X, int64_t ldx, const float* dY, int64_t ldy, 
   return rc;
 }
 
+int uu_optimizer_state(uu_model* m, int which, int allocate, float** dev_ptr, int64_t* n_floats) {
+  UU_CHECK(m && dev_ptr && n_floats && which >= 0 && which <= 2, "uu_optimizer_state: which is 0 (m), 1 (v) or 2 (EMA)");
+  UU_CUDA(cudaSetDevice(m->device));
+  if (allocate && which < 2 && !m->grads) {
+    float* g; int64_t n;
+    if (uu_grad_buffer(m, &g, &n)) return 1;            // creates the gradient and both moment buffers, zero-filled
+  }
+  if (allocate && which == 2 && !m->ema) {
+    UU_CUDA(cudaMalloc(&m->ema, sizeof(float) * m->n_alloc));
+    UU_CUDA(cudaMemcpy(m->ema, m->params, sizeof(float) * m->n_alloc, cudaMemcpyDeviceToDevice));
+  }
+  *dev_ptr = which == 0 ? m->adam_m : which == 1 ? m->adam_v : m->ema;
+  *n_floats = (int64_t)m->n_alloc;
+  return 0;
+}
+
 int uu_grad_buffer(uu_model* m, float** dev_ptr, int64_t* n_floats) {
   UU_CHECK(m && dev_ptr && n_floats, "null argument");
   UU_CUDA(cudaSetDevice(m->device));

@@ -190,6 +190,35 @@ class Trainer:
         return self._loss
 
     # ---- introspection for the parity tests ----------------------------------------------------------
+    def _state_view(self, which: int, allocate: bool):
+        ptr, n = c_void_p(), c_int64()
+        _lib.check(self.lib.uu_optimizer_state(self.model._h, which, 1 if allocate else 0, byref(ptr), byref(n)))
+        if not ptr.value:
+            return None
+        return self.torch.as_tensor(_DevView(ptr.value, n.value), device=f"cuda:{self.model.device}")
+
+    def state_dict(self) -> dict:
+        """Optimizer state for checkpoint / resume (what the reference's tf.train.Checkpoint holds next to the weights,
+        train.py:417-430): the step counter, Adam's flat first / second moments and, when EMA is on, the EMA weights."""
+        self.torch.cuda.synchronize(self.model.device)
+        out = {"iterations": np.int64(self.iterations)}
+        for name, which in (("adam_m", 0), ("adam_v", 1), ("ema", 2)):
+            v = self._state_view(which, False)
+            if v is not None:
+                out[name] = v.cpu().numpy().copy()
+        return out
+
+    def load_state_dict(self, state: dict) -> None:
+        self.iterations = int(state["iterations"])
+        for name, which in (("adam_m", 0), ("adam_v", 1), ("ema", 2)):
+            if name in state:
+                v = self._state_view(which, True)
+                a = np.ascontiguousarray(state[name], dtype=np.float32)
+                if a.size != v.numel():
+                    raise ValueError(f"{name}: {a.size} values for a model with {v.numel()} parameter slots")
+                v.copy_(self.torch.from_numpy(a))
+        self.torch.cuda.synchronize(self.model.device)
+
     def get_grads(self):
         out = {}
         for (g, k), shp in self.model._keys:
