@@ -58,6 +58,10 @@ def test_model_weights_wrapper_and_errors(tmp_path):
     spec351 = spec_from_config(UpliftUpsampleConfig.preset("h36m_351"))
     with pytest.raises(ValueError, match="shape"):
         h5lite.load_keras_weights(p, spec351)
+    # ... unless skip_mismatch: the mismatching tensors are skipped and reported, the matching ones load (weight_io.py:186, :220)
+    rep = {}
+    part = h5lite.load_keras_weights(p, spec351, skip_mismatch=True, verbose=False, report=rep)
+    assert rep["skipped"] and 0 < len(part) < len(w) and all(np.array_equal(part[k], w[k]) for k in part)
     bad = tmp_path / "bad.h5"
     bad.write_bytes(b"not hdf5 at all")
     with pytest.raises(ValueError, match="signature"):
@@ -73,3 +77,39 @@ def test_groups_with_many_links_use_several_symbol_nodes(tmp_path):
     h5lite.write_h5(p, root)
     f = h5lite.H5File(p)
     assert len(f.links()) == 37 and f["d36"].read()[0, 0] == 36 and f.attrs["note"] == b"x"
+
+
+def test_layers_missing_from_the_file_are_reported_not_fatal(tmp_path, capsys):
+    """By-name loading (weight_io.py:241-251): a model layer the file does not hold keeps its values and is listed under "not
+    assigned any weights"; a file layer the model does not have is listed as "not consumed"."""
+    spec = spec_from_config(UpliftUpsampleConfig.preset("h36m_81"))
+    w = weights.init_weights(spec, 3)
+    p = str(tmp_path / "full.h5")
+    h5lite.save_keras_weights(p, spec, w)
+    f = h5lite.H5File(p)
+    layers = [h5lite._decode(n) for n in np.atleast_1d(f.attrs["layer_names"])]
+    drop = "temporal_fc"
+    assert drop in layers
+    # rebuild the file without one layer and with one foreign layer
+    root = h5lite._Node()
+    names = [n for n in layers if n != drop] + ["some_other_head"]
+    root.attrs = [("layer_names", names), ("backend", b"tensorflow"), ("keras_version", b"2.4.0")]
+    inv = weights.inventory(spec)
+    for gname in names:
+        foreign = gname == "some_other_head"
+        tensors = [("some_other_head/kernel:0", (3, 3), None)] if foreign else inv[gname]
+        grp = root.ensure_group([gname])
+        grp.attrs = [("weight_names", [t[0] for t in tensors])]
+        for i, (wn, shape, _) in enumerate(tensors):
+            parts = wn.split("/")
+            arr = np.zeros(shape, np.float32) if foreign else w[(gname, i)]
+            grp.ensure_group(parts[:-1]).children[parts[-1]] = h5lite._Node(arr)
+    q = str(tmp_path / "partial.h5")
+    h5lite.write_h5(q, root)
+    rep = {}
+    back = h5lite.load_keras_weights(q, spec, report=rep)
+    out = capsys.readouterr().out
+    assert rep["unassigned_layers"] == [drop] and rep["unconsumed_layers"] == ["some_other_head"]
+    assert "not assigned any weights" in out and "- " + drop in out and "not consumed" in out
+    assert all(k[0] != drop for k in back) and all(np.array_equal(back[k], w[k]) for k in back)
+    assert len(back) == len(w) - len(inv[drop])

@@ -421,8 +421,14 @@ def _decode(v) -> str:
     return v.decode("utf8") if isinstance(v, (bytes, np.bytes_)) else str(v)
 
 
-def load_keras_weights(path: str, spec) -> Dict[W.WeightKey, np.ndarray]:
-    """Name-based group lookup, position-based tensor matching, shape check — weight_io.py:125-263."""
+def load_keras_weights(path: str, spec, skip_mismatch: bool = False, verbose: bool = True,
+                       report: Optional[dict] = None) -> Dict[W.WeightKey, np.ndarray]:
+    """Name-based group lookup, position-based tensor matching, shape check — weight_io.py:125-263, with its rules:
+    a model layer the file does not hold is NOT an error (it keeps its current values and is listed under "not assigned any
+    weights", :247-251; this is how a pre-trained file without some layers is loaded); a layer whose tensor count or a tensor
+    whose shape disagrees raises ValueError unless ``skip_mismatch`` (:185-195, :219-232: then it is skipped with a warning);
+    file layers the model does not have are listed as "not consumed" (:241-245).  The returned dict may therefore be partial;
+    ``report`` (optional dict) receives the three lists."""
     f: H5Object = H5File(path)
     if "layer_names" not in f.attrs and "model_weights" in f:                 # weight_io.py:119-120
         f = f["model_weights"]
@@ -431,18 +437,43 @@ def load_keras_weights(path: str, spec) -> Dict[W.WeightKey, np.ndarray]:
     file_layers = [_decode(n) for n in np.atleast_1d(f.attrs["layer_names"])]
     inv = W.inventory(spec)
     out: Dict[W.WeightKey, np.ndarray] = {}
+    unassigned, skipped = [], []
     for gname, tensors in inv.items():
         if not tensors:
             continue
         if gname not in file_layers:
-            raise ValueError(f"layer {gname!r} is missing from the weights file")
+            unassigned.append(gname)
+            continue
         g = f[gname]
         names = [_decode(n) for n in np.atleast_1d(g.attrs.get("weight_names", []))]
         if len(names) != len(tensors):                                        # weight_io.py:185-195
-            raise ValueError(f"layer {gname!r}: file has {len(names)} weights, model expects {len(tensors)}")
+            msg = f"layer {gname!r}: file has {len(names)} weights, model expects {len(tensors)}"
+            if not skip_mismatch:
+                raise ValueError(msg)
+            skipped.append(msg)
+            continue
         for i, (wn, (_, shape, _)) in enumerate(zip(names, tensors)):
             a = g[wn].read()
             if tuple(a.shape) != tuple(shape):                                # weight_io.py:219-232
-                raise ValueError(f"layer {gname!r} weight {i}: file shape {a.shape}, model expects {tuple(shape)}")
+                msg = f"layer {gname!r} weight {i}: file shape {a.shape}, model expects {tuple(shape)}"
+                if not skip_mismatch:
+                    raise ValueError(msg)
+                skipped.append(msg)
+                continue
             out[(gname, i)] = a
+    model_layers = {gname for gname, tensors in inv.items() if tensors}
+    unconsumed = [n for n in file_layers if n not in model_layers and len(np.atleast_1d(f[n].attrs.get("weight_names", [])))]
+    if report is not None:
+        report.update({"unassigned_layers": unassigned, "unconsumed_layers": unconsumed, "skipped": skipped})
+    if verbose:
+        if unconsumed:
+            print("The following layers were not consumed from .h5 file:")
+            for n in unconsumed:
+                print("- " + n)
+        if unassigned:
+            print("The following layers were not assigned any weights:")
+            for n in unassigned:
+                print("- " + n)
+        for msg in skipped:
+            print("Skipping loading of weights: " + msg)
     return out

@@ -77,9 +77,13 @@ class UpliftUpsampleTransformer:
             if got != (g, k, tuple(shp)):
                 raise _lib.UUError(f"weight inventory mismatch at {i}: library {got}, host {(g, k, tuple(shp))}")
 
-    def set_weights(self, w: Dict[W.WeightKey, np.ndarray]) -> None:
+    def set_weights(self, w: Dict[W.WeightKey, np.ndarray], partial: bool = False) -> None:
+        """partial: tensors that ``w`` does not hold keep their current values (a by-name load of a file without some
+        layers, weight_io.py:247-251); otherwise a missing tensor is an error."""
         for (g, k), shp in self._keys:
             if (g, k) not in w:
+                if partial:
+                    continue
                 raise ValueError(f"missing weight {g}[{k}]")
             a = np.ascontiguousarray(w[(g, k)], dtype=np.float32)
             shape = (c_int64 * max(a.ndim, 1))(*a.shape)
@@ -93,13 +97,15 @@ class UpliftUpsampleTransformer:
             out[(g, k)] = a
         return out
 
-    def load_weights(self, path: str) -> None:
-        """``.h5`` (Keras layout, weight_io.py:76-263) or the ``.npz`` mirror."""
+    def load_weights(self, path: str, skip_mismatch: bool = False, verbose: bool = True) -> None:
+        """``.h5`` (Keras layout, by-name loading with the rules of weight_io.py:76-263: layers the file does not hold keep
+        their values and are reported, count / shape mismatches raise unless ``skip_mismatch``) or the ``.npz`` mirror."""
         if path.endswith(".npz"):
             self.set_weights(W.load_npz(path, self.spec))
         else:
             from . import h5lite
-            self.set_weights(h5lite.load_keras_weights(path, self.spec))
+            self.set_weights(h5lite.load_keras_weights(path, self.spec, skip_mismatch=skip_mismatch, verbose=verbose),
+                             partial=True)
 
     def save_weights(self, path: str) -> None:
         if path.endswith(".npz"):
