@@ -625,6 +625,11 @@ __global__ void k_period_sum(const float* __restrict__ X, long long rows, int pe
 cudaError_t launch_period_sum(const float* X, long long rows, int period, int d, const uint8_t* rowmask, int want,
                               float* out, cudaStream_t st) {
   if (rows == 0) return cudaSuccess;
+  // without a row mask this is the column sum of X viewed as (rows / period, period * d): the 16-byte kernel (the loop below
+  // ran at 1 TB/s on the positional tables)
+  if (!rowmask && rows % period == 0 && ((long long)period * d) % 4 == 0 && (long long)period * d < (1ll << 30) &&
+      rows / period < (1ll << 31) && ((uintptr_t)X & 15) == 0)
+    return launch_colsum(X, (int)(rows / period), period * d, (long long)period * d, out, st);
   const int bx = d >= 128 ? 128 : 32;
   const long long nb = rows / period;
   long long nz = std::max<long long>(1, std::min<long long>(64, nb / 8));      // (3 x 3 x 16 CTAs of 128 threads ran at 1 TB/s)
