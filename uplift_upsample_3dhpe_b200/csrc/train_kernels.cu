@@ -285,6 +285,8 @@ __global__ void __launch_bounds__(256, 2) k_gemm_gen(GemmGen g) {
 // dW[KD][ND] += X^T dY and db[ND] += colsum(dY) in ONE pass over the rows: these products are memory-bound (one read of
 // X and dY), so every CTA streams a contiguous row range through shared memory, keeps its KD x ND partial sums in
 // registers (thread (k, n-chunk) owns KD/32 x ND/8 of them) and writes one partial slab; slabs are reduced in order.
+// A lane's ND/8 columns are 4-wide chunks interleaved over the 8 lanes (chunk c of lane ln = columns 32 c + 4 ln ..): the
+// 16-byte reads of a quarter-warp are then 128 contiguous bytes (lane-contiguous column blocks of 8 were a 2-way conflict).
 template <int KD, int ND>
 __global__ void __launch_bounds__(256) k_wgrad_skinny(const float* __restrict__ X, long long ldx, const float* __restrict__ dY,
                                                       long long ldy, long long rows, float* __restrict__ partial) {
@@ -346,7 +348,7 @@ __global__ void __launch_bounds__(256) k_wgrad_skinny(const float* __restrict__ 
       }
 #pragma unroll
       for (int j = 0; j < NPL; j += 4) {
-        const float4 q = *reinterpret_cast<const float4*>(&Ys[r][ln * NPL + j]);
+        const float4 q = *reinterpret_cast<const float4*>(&Ys[r][(j / 4) * 32 + ln * 4]);     // j is a multiple of 4
         y[j] = q.x; y[j + 1] = q.y; y[j + 2] = q.z; y[j + 3] = q.w;
       }
 #pragma unroll
@@ -364,13 +366,13 @@ __global__ void __launch_bounds__(256) k_wgrad_skinny(const float* __restrict__ 
       for (int i = 0; i < KPL; ++i)
 #pragma unroll
         for (int j = 0; j < NPL; ++j) {
-          float* p = &Rs[(lk * KPL + i) * ND + ln * NPL + j];
+          float* p = &Rs[(lk * KPL + i) * ND + (j / 4) * 32 + ln * 4 + (j & 3)];
           *p = w == 0 ? acc[i][j] : *p + acc[i][j];
         }
       if (lk == 0) {
 #pragma unroll
         for (int j = 0; j < NPL; ++j) {
-          float* p = &Rs[KD * ND + ln * NPL + j];
+          float* p = &Rs[KD * ND + (j / 4) * 32 + ln * 4 + (j & 3)];
           *p = w == 0 ? bs[j] : *p + bs[j];
         }
       }
@@ -461,7 +463,7 @@ __global__ void __launch_bounds__(256) k_dgrad_skinny(const float* __restrict__ 
         float w[CPT];
 #pragma unroll
         for (int j = 0; j < CPT; j += 4) {
-          const float4 q = *reinterpret_cast<const float4*>(&Bs[(k + kk) * NO + tc * CPT + j]);
+          const float4 q = *reinterpret_cast<const float4*>(&Bs[(k + kk) * NO + (j / 4) * 32 + tc * 4]);   // j multiple of 4
           w[j] = q.x; w[j + 1] = q.y; w[j + 2] = q.z; w[j + 3] = q.w;
         }
 #pragma unroll
@@ -478,7 +480,7 @@ __global__ void __launch_bounds__(256) k_dgrad_skinny(const float* __restrict__ 
       if (r < rows) {
 #pragma unroll
         for (int j = 0; j < CPT; j += 4) {
-          float4* dst = reinterpret_cast<float4*>(dX + r * ldx + tc * CPT + j);
+          float4* dst = reinterpret_cast<float4*>(dX + r * ldx + (j / 4) * 32 + tc * 4);
           float4 v = make_float4(acc[i][j], acc[i][j + 1], acc[i][j + 2], acc[i][j + 3]);
           if (accumulate) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
           *dst = v;
