@@ -228,7 +228,9 @@ int wgrad_tc(const float* X, long long ldx, const float* dY, long long ldy, long
   const int bn = (Nd % 192 == 0) ? 192 : (Nd % 128 == 0) ? 128 : 64;
   const int m_tiles = (Kd + 127) / 128, n_tiles = Nd / bn, tiles = m_tiles * n_tiles;
   const long long kblocks = (R + WG_BKR - 1) / WG_BKR;
-  int splits = std::max(1, (2 * num_sms + tiles - 1) / tiles);           // about two CTAs per SM
+  // ONE wave: the kernel keeps ~176 KB of operand stages, so a single CTA is resident per SM; "about two CTAs per SM" (the first
+  // choice) ran 306 CTAs of the q|k|v wgrad as two full waves plus a third with 10 CTAs
+  int splits = std::max(1, num_sms / tiles);
   splits = (int)std::min<long long>(splits, std::max<long long>(1, kblocks / 8));     // at least 8 k-blocks per CTA
   const size_t per_split = (size_t)m_tiles * 128 * Nd * sizeof(float);
   splits = (int)std::min<size_t>(splits, std::max<size_t>(1, wgrad_tc_scratch_bytes() / per_split));
