@@ -382,6 +382,22 @@ __global__ void __launch_bounds__(256) k_wgrad_skinny(const float* __restrict__ 
   float* out = partial + (long long)blockIdx.x * (KD * ND + ND);
   for (int i = tid; i < KD * ND + ND; i += 256) out[i] = Rs[i];
 }
+// CTAs of one full wave: SM count x resident CTAs per SM of this kernel (queried once).  The persistent skinny kernels split the
+// rows evenly over the grid, so a grid that is a whole number of waves leaves no partly filled last wave (592 CTAs of the
+// 32 x 32 wgrad were 1.33 waves at three resident CTAs per SM).
+template <typename Kern>
+static int wave_ctas(Kern kern, int threads, int* cache) {
+  if (*cache == 0) {
+    int dev = 0, sms = 148, occ = 1;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, 0) != cudaSuccess || occ < 1) occ = 1;
+    *cache = sms * occ;
+  }
+  return *cache;
+}
+template <int KD, int ND> static int wgrad_skinny_wave() { static int c = 0; return wave_ctas(k_wgrad_skinny<KD, ND>, 256, &c); }
+template <int KI, int NO> static int dgrad_skinny_wave();      // (defined behind the kernel)
+
 bool wgrad_skinny_ok(const float* X, long long ldx, const float* dY, long long ldy, long long rows, int K, int N) {
   return rows >= 4096 && ((K == 32 && (N == 32 || N == 64 || N == 96)) || (K == 64 && N == 32)) && ldx % 4 == 0 && ldy % 4 == 0 &&
          ((uintptr_t)X & 15) == 0 && ((uintptr_t)dY & 15) == 0;
@@ -396,8 +412,11 @@ cudaError_t launch_wgrad_skinny(const float* X, long long ldx, const float* dY, 
     if (e != cudaSuccess) return e;
     return launch_wgrad_skinny(X + 32, ldx, dY, ldy, rows, 32, 32, dW + 32 * 32, nullptr, st);
   }
-  const unsigned grid = (unsigned)std::min<long long>(148 * 4, (rows + 255) / 256);
-  if ((size_t)grid * (K * N + N) > g_red_floats) return cudaErrorInvalidValue;
+  const int wave = (K == 32 && N == 32) ? wgrad_skinny_wave<32, 32>() : (K == 32 && N == 64) ? wgrad_skinny_wave<32, 64>()
+                   : (K == 32 && N == 96) ? wgrad_skinny_wave<32, 96>() : wgrad_skinny_wave<64, 32>();
+  unsigned grid = (unsigned)std::min<long long>(wave, (rows + 255) / 256);
+  grid = (unsigned)std::min<size_t>(grid, g_red_floats / (size_t)(K * N + N));
+  if (grid == 0) return cudaErrorInvalidValue;
   float* scr = red_region((size_t)grid * (K * N + N) + N, st);      // (+ N: dump area of the column sums when db is null)
   if (!scr) return cudaErrorInvalidValue;
 #define UU_WS(KD, ND) if (K == KD && N == ND) k_wgrad_skinny<KD, ND><<<grid, 256, 0, st>>>(X, ldx, dY, ldy, rows, scr); else
@@ -489,6 +508,7 @@ __global__ void __launch_bounds__(256) k_dgrad_skinny(const float* __restrict__ 
     }
   }
 }
+template <int KI, int NO> static int dgrad_skinny_wave() { static int c = 0; return wave_ctas(k_dgrad_skinny<KI, NO>, 256, &c); }
 // dX [rows, NO] (+)= dY [rows, KI] . W^T, W (NO, KI) row-major contiguous
 bool dgrad_skinny_ok(const float* dY, long long ldy, long long rows, int KI, int NO, const float* dX, long long ldx) {
   // (the 96 -> 32 shape, the packed q | k | v input gradient, is instantiated but measured slower than the generic kernel:
@@ -499,7 +519,9 @@ bool dgrad_skinny_ok(const float* dY, long long ldy, long long rows, int KI, int
 cudaError_t launch_dgrad_skinny(const float* dY, long long ldy, const float* Wm, long long rows, int KI, int NO, float* dX,
                                 long long ldx, int accumulate, cudaStream_t st) {
   const int tr = KI > 64 ? 64 : 128;
-  const unsigned grid = (unsigned)std::min<long long>((rows + tr - 1) / tr, 148 * 3);
+  const int wave = (KI == 32 && NO == 32) ? dgrad_skinny_wave<32, 32>() : (KI == 64 && NO == 32) ? dgrad_skinny_wave<64, 32>()
+                   : (KI == 96 && NO == 32) ? dgrad_skinny_wave<96, 32>() : dgrad_skinny_wave<32, 64>();
+  const unsigned grid = (unsigned)std::min<long long>((rows + tr - 1) / tr, wave);
 #define UU_DS(KIV, NOV) if (KI == KIV && NO == NOV) k_dgrad_skinny<KIV, NOV><<<grid, 256, 0, st>>>(dY, ldy, Wm, rows, dX, ldx, accumulate); else
   UU_DS(32, 32) UU_DS(64, 32) UU_DS(96, 32) UU_DS(32, 64) return cudaErrorInvalidValue;
 #undef UU_DS
