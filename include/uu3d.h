@@ -14,6 +14,7 @@
  *                               common/net/uplift_upsample_transformer.py:388-421 ; caller eval.py:63-71
  *   uu_train_config / uu_train_forward_backward / uu_grad_buffer / uu_adamw_step ; uu_train_step (all of it in one call)
  *                               train_step(): loss, gradients, AdamW                        train.py:464-506, :403-415
+ *   uu_optimizer_state          the optimizer part of tf.train.Checkpoint (Adam moments, EMA copy)           train.py:417-430
  *   uu_comm_unique_id / uu_comm_init / uu_comm_destroy / uu_allreduce_gradients
  *                               the gradient exchange of the reference's tf.distribute strategy (train.py:464-506 runs
  *                               under strategy.run): NCCL sum all-reduce over NVLink
